@@ -1,0 +1,193 @@
+/*
+ * voxel_cuda.h -- C ABI of the B200 (sm_100a) chunk pipeline: terrain generation, column heights
+ * ("light"), face-culled meshing, batched edits, height-map image.
+ *
+ * This is the drop-in boundary for the chunk pipeline of IvanDimovSIT/voxel_game v1.7.0.  The
+ * reference has no FFI of its own; each entry point below names the Rust function
+ * (file:line under the reference's src/) whose body a maintainer replaces with a call to it.
+ * INTEGRATION.md shows the Rust `extern "C"` block and the call sites.
+ *
+ * Conventions: plain pointers and sizes only; every function returns VX_OK (0) or a negative
+ * vx_status; no exceptions cross the boundary; all state lives in an opaque vx_ctx bound to ONE
+ * CUDA device (one process per GPU, several contexts per process allowed).  A context is
+ * internally locked: calls may come from any thread (the reference enters generation from rayon
+ * workers, world_persistence.rs:90-93,120-123).  There is NO CPU fallback: without a usable CUDA
+ * device vx_create fails with VX_ERR_NO_DEVICE and nothing else can be called.
+ *
+ * Data layouts (identical to the reference's in-memory layouts):
+ *   voxels      32768 bytes per area, index x + 16*y + 256*z, z = 0 is the TOP   (area.rs:58-64)
+ *               byte = Voxel discriminant 0..26                                   (voxel.rs:8-36)
+ *   max_height  256 bytes per area, index x + 16*y                                (area.rs:29-31)
+ *   area_xy     pairs (AreaLocation.x, AreaLocation.y) as u32                     (location.rs:92-96)
+ *   vertices    40 bytes each: position f32x3, uv f32x2, color u8x4, normal f32x4
+ *               (macroquad::ui::Vertex, repr(C); mesh_generator.rs:225-234), 4 per face
+ *   indices     u16, 6 per face: [0,1,2,0,2,3] + 4*k, k = face ordinal inside its voxel
+ *               (mesh_generator.rs:44,131-139)
+ */
+#ifndef VOXEL_CUDA_H
+#define VOXEL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VX_AREA_SIZE 16
+#define VX_AREA_HEIGHT 128
+#define VX_VOXELS_IN_AREA 32768
+#define VX_COLUMNS_IN_AREA 256
+#define VX_VERTEX_BYTES 40
+#define VX_HEIGHTMAP_SIZE 512
+
+typedef enum {
+    VX_OK = 0,
+    VX_ERR_NO_DEVICE = -1,    /* no CUDA device / driver: there is no CPU fallback */
+    VX_ERR_CUDA = -2,         /* a CUDA call failed; vx_last_error(ctx) has the text */
+    VX_ERR_INVALID = -3,      /* bad argument (null pointer, n < 0, voxel id >= 27, z >= 128) */
+    VX_ERR_NO_SEED = -4,      /* vx_set_seed has not been called */
+    VX_ERR_NOT_LOADED = -5,   /* an area named by the call is not resident in the context */
+    VX_ERR_OOM = -6,          /* device or pinned-host allocation failed */
+    VX_ERR_NO_MESH = -7       /* vx_mesh_read without a preceding successful vx_mesh */
+} vx_status;
+
+typedef struct vx_ctx vx_ctx;
+
+/* One visible voxel: key + value of Renderer's mesh_map entry without the vertex payload
+ * (renderer.rs:45-51 `MeshInfo = (u8 face_count, Voxel, Mesh)` keyed by InternalLocation). */
+typedef struct {
+    uint32_t gx, gy;      /* global InternalLocation x, y (location.rs:44-49) */
+    uint32_t packed;      /* gz | voxel << 8 | face_mask << 16 | n_faces << 24 */
+    uint32_t first_face;  /* index of the voxel's first face in the call's face stream:
+                             vertices[first_face*4 ..][n_faces*4], indices[first_face*6 ..] */
+} vx_voxel_rec;
+/* face_mask bits, in the push order of renderer.rs:139-180 (so bit order == face order) */
+#define VX_FACE_LEFT 1u   /* x+1, normal +x */
+#define VX_FACE_RIGHT 2u  /* x-1 */
+#define VX_FACE_FRONT 4u  /* y+1 */
+#define VX_FACE_BACK 8u   /* y-1 */
+#define VX_FACE_DOWN 16u  /* z+1 */
+#define VX_FACE_UP 32u    /* z-1 */
+
+/* One block edit = World::set(location, voxel) (world.rs:184-191). */
+typedef struct {
+    uint32_t gx, gy, gz;
+    uint32_t voxel;
+} vx_edit;
+
+typedef struct {
+    uint64_t n_faces;  /* faces in the stream */
+    uint64_t n_recs;   /* visible voxels */
+    uint64_t vertex_bytes, index_bytes, rec_bytes;
+} vx_mesh_info;
+
+/* Device time of the kernels of the most recent vx_generate / vx_mesh / vx_apply_edits call,
+ * CUDA events on the context's stream.  Only filled while vx_set_timing(ctx, 1). */
+typedef struct {
+    float gen_columns_ms;  /* K1 */
+    float gen_caves_ms;    /* K1b */
+    float gen_finish_ms;   /* K2 (trees + column heights) */
+    float mesh_count_ms;   /* K4a (+ offsets scan) */
+    float mesh_emit_ms;    /* K4b */
+    float edit_ms;         /* K5 */
+    float heightmap_ms;    /* K6 */
+    float light_ms;        /* L-ext */
+    uint32_t gen_launches, mesh_launches, other_launches; /* kernels launched by the last call */
+    uint32_t cave_columns;                                /* K1b work items of the last generate */
+} vx_timings;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int vx_device_count(void);                       /* >= 0, or VX_ERR_NO_DEVICE */
+int vx_create(int device, vx_ctx** out);         /* binds to `device`, creates a stream */
+void vx_destroy(vx_ctx* ctx);
+const char* vx_strerror(int status);
+const char* vx_last_error(vx_ctx* ctx);
+/* Run on an external CUDA stream (a cudaStream_t / CUstream handle, e.g. torch's current
+ * stream) instead of the context's own; NULL restores the own stream. */
+int vx_set_stream(vx_ctx* ctx, void* cuda_stream);
+int vx_sync(vx_ctx* ctx);
+int vx_set_timing(vx_ctx* ctx, int enabled);
+int vx_get_timings(vx_ctx* ctx, vx_timings* out);
+/* Pinned host memory for the output buffers (pageable memory works too, only slower). */
+void* vx_host_alloc(size_t bytes);
+void vx_host_free(void* p);
+
+/* ---- seed: replaces AreaGenerator::new (generator.rs:135-146) and the five noise constructors
+ * (terrain_type.rs:15-24, biome_type.rs:19-23, cave_generator.rs:26-34,
+ * voxel_type_generator.rs:24-29, lake_generator.rs:21-25).  `seed` = hash_world_name(world_name)
+ * (generator.rs:24-28), computed by the Rust side.  Tables are built once per seed instead of
+ * once per area. */
+int vx_set_seed(vx_ctx* ctx, uint64_t seed);
+/* The same hash, for hosts that are not Rust: SipHash-1-3(k0=k1=0) over name bytes || 0xFF. */
+uint64_t vx_hash_world_name(const char* world_name);
+
+/* ---- generation + column heights: replaces AreaGenerator::generate_area (generator.rs:49-64,
+ * which ends in Area::update_all_column_heights, area.rs:34-44) for a whole batch, i.e. the body
+ * of AreaLoader::load_all_blocking / batch_load (world_persistence.rs:85-110) for disk misses.
+ * Areas become resident in the context.  voxels_out (n*32768) / max_height_out (n*256) are host
+ * buffers, either may be NULL to leave the result on the device only. */
+int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out,
+                uint8_t* max_height_out);
+
+/* Areas loaded from disk (world_persistence.rs:62-67): upload voxels and compute their column
+ * heights on the device, as AreaDTO::into_area does (area.rs:209-219). max_height_out may be NULL. */
+int vx_upload(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* voxels,
+              uint8_t* max_height_out);
+
+/* Read resident areas back (World::unload_areas -> store, world.rs:225-240). Outputs may be NULL. */
+int vx_read_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out,
+                  uint8_t* max_height_out);
+
+/* Drop resident areas (World::retain_areas / unload_areas, world.rs:196-240). Unknown areas are
+ * ignored. */
+int vx_unload(vx_ctx* ctx, const uint32_t* area_xy, int n);
+int vx_resident_count(vx_ctx* ctx);
+
+/* Area::update_all_column_heights (area.rs:34-44) as a stand-alone operator on host data. */
+int vx_column_heights(vx_ctx* ctx, const uint8_t* voxels, int n, uint8_t* max_height_out);
+
+/* ---- meshing: replaces Renderer::load_full_area (renderer.rs:310-322) for a batch, i.e. the body
+ * of Renderer::load_all_blocking (renderer.rs:468-472) and load_areas_in_queue (:289-307):
+ * get_renderable_voxels_for_area (world.rs:112-147) + generate_mesh_for_voxel
+ * (renderer.rs:126-195) + MeshGenerator::generate_mesh (mesh_generator.rs:109-147).
+ * Edge neighbours that are not resident are generated first, exactly as the reference's
+ * world.get_with_cache -> load_area does (world.rs:157-174).  The mesh stays on the device until
+ * the next vx_mesh; info tells the caller how large the host buffers for vx_mesh_read must be.
+ * Voxels appear in z,y,x order per area, areas in call order, faces in push order. */
+int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info);
+
+/* Copy the last mesh to host buffers. rec_first/face_first get n+1 entries each (area i owns
+ * recs[rec_first[i] .. rec_first[i+1]) and faces [face_first[i] .. face_first[i+1])).
+ * Any pointer may be NULL.  Lamp positions (RenderArea.lights, renderer.rs:60-67) are the recs
+ * whose voxel byte is 11. */
+int vx_mesh_read(vx_ctx* ctx, uint32_t* rec_first, uint32_t* face_first, vx_voxel_rec* recs,
+                 void* vertices, uint16_t* indices);
+
+/* ---- edits: replaces World::set (world.rs:184-191 -> Area::set, area.rs:99-111, incl. column
+ * height upkeep) for a batch applied in array order (later edits win), and reports the areas whose
+ * meshes Renderer::update_location (renderer.rs:239-286) would have touched: the edited area plus
+ * the edge neighbour when the edit is on a border column.  The caller then re-runs vx_mesh on
+ * dirty_area_xy.  dirty_area_xy must have room for 3*n pairs; all edited areas must be resident. */
+int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_area_xy,
+                   int* n_dirty);
+
+/* ---- height map: replaces HeightMap::generate_height_map's pixel loop (height_map.rs:41-85).
+ * rgba is the persistent 512*512*4 pixel buffer (stale pixels persist, as in the reference);
+ * areas with |dx| or |dy| >= 16 from the camera area are skipped (height_map.rs:90-101);
+ * areas of the list that are not resident read as an empty area (height 127, world.rs:64-69). */
+int vx_heightmap(vx_ctx* ctx, const uint32_t* area_xy, int n, uint32_t cam_area_x,
+                 uint32_t cam_area_y, uint8_t* rgba);
+
+/* ---- L-ext (north star only; the reference has no voxel light): light levels
+ * 0..15 per voxel over the resident areas listed, see DESIGN.md "L-ext". light_out n*32768. */
+int vx_light(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* light_out, int* iterations);
+
+/* ---- diagnostics: measured FP64 DADD+DMUL issue rate of this GPU in Gop/s (no FMA), the
+ * roofline denominator of the noise kernels. */
+int vx_diag_fp64_rate(vx_ctx* ctx, double* gops_per_s, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,283 @@
+"""ctypes binding of the CPU ORACLE (oracle/build/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY.  May be imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (voxel_game_b200) never imports it.
+See oracle/vg_oracle.h for the parity status ("parity unpinned" at the libnoise boundary).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "build", "liboracle.so")
+
+AREA_SIZE = 16
+AREA_HEIGHT = 128
+VOXELS_IN_AREA = AREA_SIZE * AREA_SIZE * AREA_HEIGHT
+COLUMNS_IN_AREA = AREA_SIZE * AREA_SIZE
+LOCATION_OFFSET = 1_000_000
+
+VOXEL_NAMES = [
+    "None", "Cobblestone", "Sand", "Grass", "Wood", "Leaves", "Brick", "Dirt", "Boards", "Stone",
+    "Clay", "Lamp", "Trampoline", "Cactus", "WaterSource", "WaterDown", "Water1", "Water2",
+    "Water3", "Water4", "StoneBrick", "StonePillar", "Snow", "Ice", "Bomb", "ActiveBomb", "Glass",
+]
+V = {n: i for i, n in enumerate(VOXEL_NAMES)}
+TREE_NAMES = ["None", "Short", "Tall", "TallCactus", "DeadTree", "HugeTree", "ShortCactus", "Bush"]
+T = {n: i for i, n in enumerate(TREE_NAMES)}
+
+REC_DTYPE = np.dtype([("gx", "<u4"), ("gy", "<u4"), ("packed", "<u4"), ("first_face", "<u4")])
+VERTEX_DTYPE = np.dtype(
+    [("position", "<f4", 3), ("uv", "<f4", 2), ("color", "u1", 4), ("normal", "<f4", 4)]
+)
+assert VERTEX_DTYPE.itemsize == 40 and REC_DTYPE.itemsize == 16
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with gcc (oracle/Makefile). Returns the .so path."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    stale = not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    )
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+class GenStats(C.Structure):
+    _fields_ = [
+        ("simplex2_evals", C.c_uint64),
+        ("simplex3_evals", C.c_uint64),
+        ("cave_voxels", C.c_uint64),
+        ("cave_columns", C.c_uint64),
+        ("trees_placed", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class _World(C.Structure):
+    _fields_ = [
+        ("ax0", C.c_uint32), ("ay0", C.c_uint32), ("nx", C.c_uint32), ("ny", C.c_uint32),
+        ("voxels", C.c_void_p), ("max_height", C.c_void_p), ("face_mask", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        u8p, u32p, u16p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint16)
+        L.vgo_hash_world_name.restype = C.c_uint64
+        L.vgo_hash_world_name.argtypes = [C.c_char_p]
+        L.vgo_siphash.restype = C.c_uint64
+        L.vgo_siphash.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_char_p, C.c_size_t]
+        L.vgo_chacha12_words.argtypes = [C.c_uint64, u32p, C.c_int]
+        L.vgo_chacha_block_raw.argtypes = [u32p, C.c_uint64, C.c_int, u32p]
+        L.vgo_simplex_new.argtypes = [C.c_void_p, C.c_uint64]
+        L.vgo_simplex2.restype = C.c_double
+        L.vgo_simplex2.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.vgo_simplex3.restype = C.c_double
+        L.vgo_simplex3.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.vgo_generator_new.restype = C.c_void_p
+        L.vgo_generator_new.argtypes = [C.c_uint64]
+        L.vgo_generator_free.argtypes = [C.c_void_p]
+        L.vgo_generate_area.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, u8p, u8p, C.POINTER(GenStats)]
+        L.vgo_sample_column.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
+        L.vgo_generate_areas.restype = C.c_int
+        L.vgo_generate_areas.argtypes = [C.c_uint64, u32p, C.c_int, u8p, u8p, C.c_int, C.c_int, C.POINTER(GenStats)]
+        L.vgo_should_generate_tree.restype = C.c_int
+        L.vgo_should_generate_tree.argtypes = [C.c_uint8, C.c_uint64] + [C.c_uint32] * 5
+        L.vgo_can_generate_tree.restype = C.c_int
+        L.vgo_can_generate_tree.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.vgo_generate_tree.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.vgo_combine_seed.restype = C.c_uint64
+        L.vgo_combine_seed.argtypes = [C.c_uint64] + [C.c_uint32] * 5
+        L.vgo_split_mix64.restype = C.c_uint64
+        L.vgo_split_mix64.argtypes = [C.c_uint64]
+        L.vgo_update_all_column_heights.argtypes = [u8p, u8p]
+        L.vgo_area_new.argtypes = [u8p, u8p]
+        L.vgo_area_set.argtypes = [u8p, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8]
+        L.vgo_height_map.argtypes = [u32p, C.c_int, u8p, C.c_uint32, C.c_uint32, u8p]
+        L.vgo_should_generate_face.restype = C.c_int
+        L.vgo_should_generate_face.argtypes = [C.c_uint8, C.c_uint8]
+        L.vgo_should_generate_top_face.restype = C.c_int
+        L.vgo_should_generate_top_face.argtypes = [C.c_uint8, C.c_uint8]
+        L.vgo_mesh_area.restype = C.c_long
+        L.vgo_mesh_area.argtypes = [C.POINTER(_World), C.c_uint32, C.c_uint32]
+        L.vgo_emit_area.restype = C.c_long
+        L.vgo_emit_area.argtypes = [C.POINTER(_World), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                    C.POINTER(C.c_long), C.c_void_p, C.c_void_p]
+        L.vgo_apply_edit.restype = C.c_int
+        L.vgo_apply_edit.argtypes = [C.POINTER(_World), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8]
+        L.vgo_light_flood_world.argtypes = [C.POINTER(_World), u8p]
+        L.vgo_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _p(a, t=C.c_uint8):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def hash_world_name(name: str) -> int:
+    return int(lib().vgo_hash_world_name(name.encode("utf-8")))
+
+
+def max_threads() -> int:
+    return int(lib().vgo_max_threads())
+
+
+def region_xy(ax0: int, ay0: int, nx: int, ny: int) -> np.ndarray:
+    """Area coordinates of a dense grid, grid index = ix + nx*iy (the vgo_world layout)."""
+    ix, iy = np.meshgrid(np.arange(nx, dtype=np.uint32), np.arange(ny, dtype=np.uint32))
+    xy = np.stack([ix.ravel() + np.uint32(ax0), iy.ravel() + np.uint32(ay0)], axis=1)
+    return np.ascontiguousarray(xy, dtype=np.uint32)
+
+
+class Generator:
+    """AreaGenerator (generator.rs:37-146) for one seed."""
+
+    def __init__(self, seed: int):
+        self.seed = seed & 0xFFFFFFFFFFFFFFFF
+        self._g = lib().vgo_generator_new(self.seed)
+
+    def __del__(self):
+        if getattr(self, "_g", None):
+            lib().vgo_generator_free(self._g)
+            self._g = None
+
+    def generate_area(self, ax: int, ay: int):
+        vox = np.empty(VOXELS_IN_AREA, np.uint8)
+        mh = np.empty(COLUMNS_IN_AREA, np.uint8)
+        st = GenStats()
+        lib().vgo_generate_area(self._g, ax, ay, _p(vox), _p(mh), C.byref(st))
+        return vox, mh, st.as_dict()
+
+    def sample_column(self, ax, ay, x, y):
+        out = np.zeros(4, np.uint32)
+        lib().vgo_sample_column(self._g, ax, ay, x, y, _p(out, C.c_uint32))
+        return tuple(int(v) for v in out)
+
+
+def generate_areas(seed: int, area_xy: np.ndarray, rebuild_tables_per_area=False, threads=0):
+    """AreaLoader::load_all_blocking with every area generated. Returns voxels[n,32768],
+    max_height[n,256], stats dict, threads used."""
+    area_xy = np.ascontiguousarray(area_xy, dtype=np.uint32).reshape(-1, 2)
+    n = area_xy.shape[0]
+    vox = np.empty((n, VOXELS_IN_AREA), np.uint8)
+    mh = np.empty((n, COLUMNS_IN_AREA), np.uint8)
+    st = GenStats()
+    used = lib().vgo_generate_areas(seed & 0xFFFFFFFFFFFFFFFF, _p(area_xy, C.c_uint32), n, _p(vox),
+                                    _p(mh), int(bool(rebuild_tables_per_area)), int(threads),
+                                    C.byref(st))
+    return vox, mh, st.as_dict(), int(used)
+
+
+def update_all_column_heights(vox: np.ndarray) -> np.ndarray:
+    vox = np.ascontiguousarray(vox, np.uint8)
+    mh = np.empty(COLUMNS_IN_AREA, np.uint8)
+    lib().vgo_update_all_column_heights(_p(vox), _p(mh))
+    return mh
+
+
+class Area:
+    """model::area::Area (area.rs:11-201), voxels + max_height only."""
+
+    def __init__(self):
+        self.voxels = np.empty(VOXELS_IN_AREA, np.uint8)
+        self.max_height = np.empty(COLUMNS_IN_AREA, np.uint8)
+        lib().vgo_area_new(_p(self.voxels), _p(self.max_height))
+
+    def set(self, x, y, z, voxel):
+        lib().vgo_area_set(_p(self.voxels), _p(self.max_height), x, y, z, voxel)
+
+    def set_without_updating_max_height(self, x, y, z, voxel):
+        self.voxels[x + 16 * y + 256 * z] = voxel
+
+    def get(self, x, y, z):
+        return int(self.voxels[x + 16 * y + 256 * z])
+
+    def sample_height(self, x, y):
+        return int(self.max_height[x + 16 * y])
+
+    def update_all_column_heights(self):
+        lib().vgo_update_all_column_heights(_p(self.voxels), _p(self.max_height))
+
+
+class World:
+    """A dense loaded grid of areas + Renderer.meshes as per-voxel face masks."""
+
+    def __init__(self, ax0, ay0, nx, ny, voxels, max_height):
+        self.ax0, self.ay0, self.nx, self.ny = ax0, ay0, nx, ny
+        self.voxels = np.ascontiguousarray(voxels, np.uint8).reshape(nx * ny, VOXELS_IN_AREA)
+        self.max_height = np.ascontiguousarray(max_height, np.uint8).reshape(nx * ny, COLUMNS_IN_AREA)
+        self.face_mask = np.zeros_like(self.voxels)
+        self._w = _World(ax0, ay0, nx, ny, self.voxels.ctypes.data, self.max_height.ctypes.data,
+                         self.face_mask.ctypes.data)
+
+    @classmethod
+    def generate(cls, seed, ax0, ay0, nx, ny, threads=0):
+        vox, mh, _, _ = generate_areas(seed, region_xy(ax0, ay0, nx, ny), threads=threads)
+        return cls(ax0, ay0, nx, ny, vox, mh)
+
+    def slot(self, ax, ay):
+        return (ax - self.ax0) + self.nx * (ay - self.ay0)
+
+    def mesh_area(self, ax, ay) -> int:
+        """Renderer::load_full_area. Returns the face count."""
+        r = lib().vgo_mesh_area(C.byref(self._w), ax, ay)
+        if r < 0:
+            raise ValueError("area or one of its neighbours is not loaded")
+        return int(r)
+
+    def emit_area(self, ax, ay, first_face_base=0):
+        """Records, vertices (structured, 4/face) and u16 indices (6/face) of a meshed area."""
+        fm = self.face_mask[self.slot(ax, ay)]
+        n_recs = int(np.count_nonzero(fm))
+        n_faces = int(np.unpackbits(fm).sum())
+        recs = np.zeros(n_recs, REC_DTYPE)
+        verts = np.zeros(n_faces * 4, VERTEX_DTYPE)
+        idx = np.zeros(n_faces * 6, np.uint16)
+        nr = C.c_long(0)
+        nf = lib().vgo_emit_area(C.byref(self._w), ax, ay, first_face_base, recs.ctypes.data,
+                                 C.byref(nr), verts.ctypes.data, idx.ctypes.data)
+        assert nf == n_faces and nr.value == n_recs
+        return recs, verts, idx
+
+    def apply_edit(self, gx, gy, gz, voxel):
+        """world.set + renderer.update_location."""
+        if lib().vgo_apply_edit(C.byref(self._w), gx, gy, gz, voxel) != 0:
+            raise ValueError("edit outside the loaded grid")
+
+    def light_flood(self) -> np.ndarray:
+        light = np.zeros_like(self.voxels)
+        lib().vgo_light_flood_world(C.byref(self._w), _p(light))
+        return light
+
+
+def height_map(area_xy, max_height, cam_ax, cam_ay, pixels=None):
+    area_xy = np.ascontiguousarray(area_xy, np.uint32).reshape(-1, 2)
+    max_height = np.ascontiguousarray(max_height, np.uint8)
+    if pixels is None:
+        pixels = np.full((512, 512, 4), 255, np.uint8)  # Image::gen_image_color(WHITE)
+    lib().vgo_height_map(_p(area_xy, C.c_uint32), area_xy.shape[0], _p(max_height), cam_ax, cam_ay,
+                         _p(pixels))
+    return pixels
+
+
+def should_generate_face(cur, nbr) -> bool:
+    return bool(lib().vgo_should_generate_face(cur, nbr))
+
+
+def should_generate_top_face(cur, nbr) -> bool:
+    return bool(lib().vgo_should_generate_top_face(cur, nbr))

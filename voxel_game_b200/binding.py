@@ -1,0 +1,324 @@
+"""ctypes binding of libvoxel_cuda.so (the C ABI declared in include/voxel_cuda.h).
+
+Python is plumbing here: every voxel, height and vertex is produced by the CUDA kernels in
+voxel_game_b200/csrc.  There is no CPU fallback -- if the shared library is missing or no CUDA
+device is usable, importing/creating fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvoxel_cuda.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+VOXELS_IN_AREA = 32768
+COLUMNS_IN_AREA = 256
+
+REC_DTYPE = np.dtype([("gx", "<u4"), ("gy", "<u4"), ("packed", "<u4"), ("first_face", "<u4")])
+VERTEX_DTYPE = np.dtype(
+    [("position", "<f4", 3), ("uv", "<f4", 2), ("color", "u1", 4), ("normal", "<f4", 4)]
+)
+EDIT_DTYPE = np.dtype([("gx", "<u4"), ("gy", "<u4"), ("gz", "<u4"), ("voxel", "<u4")])
+
+VX_OK = 0
+VX_ERR_NO_DEVICE = -1
+VX_ERR_CUDA = -2
+VX_ERR_INVALID = -3
+VX_ERR_NO_SEED = -4
+VX_ERR_NOT_LOADED = -5
+VX_ERR_OOM = -6
+VX_ERR_NO_MESH = -7
+
+#: every symbol include/voxel_cuda.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "vx_device_count", "vx_create", "vx_destroy", "vx_strerror", "vx_last_error", "vx_set_stream",
+    "vx_sync", "vx_set_timing", "vx_get_timings", "vx_host_alloc", "vx_host_free", "vx_set_seed",
+    "vx_hash_world_name", "vx_generate", "vx_upload", "vx_read_areas", "vx_unload",
+    "vx_resident_count", "vx_column_heights", "vx_mesh", "vx_mesh_read", "vx_apply_edits",
+    "vx_heightmap", "vx_light", "vx_diag_fp64_rate",
+]
+
+
+class VxError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"vx status {status}: {message}")
+        self.status = status
+
+
+class MeshInfo(C.Structure):
+    _fields_ = [("n_faces", C.c_uint64), ("n_recs", C.c_uint64), ("vertex_bytes", C.c_uint64),
+                ("index_bytes", C.c_uint64), ("rec_bytes", C.c_uint64)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("gen_columns_ms", C.c_float), ("gen_caves_ms", C.c_float),
+                ("gen_finish_ms", C.c_float), ("mesh_count_ms", C.c_float),
+                ("mesh_emit_ms", C.c_float), ("edit_ms", C.c_float), ("heightmap_ms", C.c_float),
+                ("light_ms", C.c_float), ("gen_launches", C.c_uint32),
+                ("mesh_launches", C.c_uint32), ("other_launches", C.c_uint32),
+                ("cave_columns", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA library for sm_100a with nvcc (csrc/Makefile). Returns the .so path."""
+    r = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libvoxel_cuda.so failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library and declare the prototypes. Raises if the .so is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a). There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, u8p, u32p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+    L.vx_device_count.restype = C.c_int
+    L.vx_create.restype = C.c_int
+    L.vx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.vx_destroy.argtypes = [vp]
+    L.vx_destroy.restype = None
+    L.vx_strerror.restype = C.c_char_p
+    L.vx_strerror.argtypes = [C.c_int]
+    L.vx_last_error.restype = C.c_char_p
+    L.vx_last_error.argtypes = [vp]
+    L.vx_set_stream.argtypes = [vp, vp]
+    L.vx_sync.argtypes = [vp]
+    L.vx_set_timing.argtypes = [vp, C.c_int]
+    L.vx_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.vx_host_alloc.restype = vp
+    L.vx_host_alloc.argtypes = [C.c_size_t]
+    L.vx_host_free.argtypes = [vp]
+    L.vx_host_free.restype = None
+    L.vx_set_seed.argtypes = [vp, C.c_uint64]
+    L.vx_hash_world_name.restype = C.c_uint64
+    L.vx_hash_world_name.argtypes = [C.c_char_p]
+    L.vx_generate.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.vx_upload.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.vx_read_areas.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.vx_unload.argtypes = [vp, vp, C.c_int]
+    L.vx_resident_count.argtypes = [vp]
+    L.vx_column_heights.argtypes = [vp, vp, C.c_int, vp]
+    L.vx_mesh.argtypes = [vp, vp, C.c_int, C.POINTER(MeshInfo)]
+    L.vx_mesh_read.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.vx_apply_edits.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int)]
+    L.vx_heightmap.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_uint32, vp]
+    L.vx_light.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int)]
+    L.vx_diag_fp64_rate.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    for name in ABI_SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("vx_device_count",):
+            pass
+    _lib = L
+    return L
+
+
+def hash_world_name(name: str) -> int:
+    """hash_world_name (generator.rs:24-28) as computed by the library."""
+    return int(load().vx_hash_world_name(name.encode("utf-8")))
+
+
+class PinnedArray:
+    """numpy view over cudaMallocHost memory (vx_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        self._lib = load()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        self._ptr = self._lib.vx_host_alloc(max(n, 1))
+        if not self._ptr:
+            raise MemoryError(f"vx_host_alloc({n}) failed")
+        buf = (C.c_uint8 * max(n, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            self._lib.vx_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _xy(area_xy) -> np.ndarray:
+    a = np.ascontiguousarray(area_xy, dtype=np.uint32).reshape(-1, 2)
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One vx_ctx: a CUDA device, a seed and the set of resident areas."""
+
+    def __init__(self, device: int = 0, seed: int | None = None, world_name: str | None = None):
+        self._lib = load()
+        h = C.c_void_p()
+        st = self._lib.vx_create(device, C.byref(h))
+        if st != VX_OK:
+            raise VxError(st, self._lib.vx_strerror(st).decode())
+        self._h = h
+        self.device = device
+        if world_name is not None:
+            seed = hash_world_name(world_name)
+        if seed is not None:
+            self.set_seed(seed)
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, st: int):
+        if st != VX_OK:
+            msg = self._lib.vx_last_error(self._h).decode() or self._lib.vx_strerror(st).decode()
+            raise VxError(st, msg)
+
+    def set_seed(self, seed: int):
+        self.seed = seed & 0xFFFFFFFFFFFFFFFF
+        self._check(self._lib.vx_set_seed(self._h, self.seed))
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self._lib.vx_set_stream(self._h, cuda_stream_ptr or None))
+
+    def sync(self):
+        self._check(self._lib.vx_sync(self._h))
+
+    def set_timing(self, enabled: bool):
+        self._check(self._lib.vx_set_timing(self._h, int(enabled)))
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._check(self._lib.vx_get_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+    # -- generation / light
+    def generate(self, area_xy, voxels_out=None, max_height_out=None, read=True):
+        """AreaLoader::load_all_blocking for disk misses. Returns (voxels[n,32768], max_height[n,256])
+        (None, None when read=False and no output buffers are given)."""
+        xy = _xy(area_xy)
+        n = xy.shape[0]
+        if read and voxels_out is None:
+            voxels_out = np.empty((n, VOXELS_IN_AREA), np.uint8)
+        if read and max_height_out is None:
+            max_height_out = np.empty((n, COLUMNS_IN_AREA), np.uint8)
+        self._check(self._lib.vx_generate(self._h, xy.ctypes.data, n, _ptr(voxels_out), _ptr(max_height_out)))
+        return voxels_out, max_height_out
+
+    def upload(self, area_xy, voxels, read_heights=True):
+        xy = _xy(area_xy)
+        n = xy.shape[0]
+        voxels = np.ascontiguousarray(voxels, np.uint8).reshape(n, VOXELS_IN_AREA)
+        mh = np.empty((n, COLUMNS_IN_AREA), np.uint8) if read_heights else None
+        self._check(self._lib.vx_upload(self._h, xy.ctypes.data, n, voxels.ctypes.data, _ptr(mh)))
+        return mh
+
+    def read_areas(self, area_xy, voxels=True, heights=True):
+        xy = _xy(area_xy)
+        n = xy.shape[0]
+        v = np.empty((n, VOXELS_IN_AREA), np.uint8) if voxels else None
+        h = np.empty((n, COLUMNS_IN_AREA), np.uint8) if heights else None
+        self._check(self._lib.vx_read_areas(self._h, xy.ctypes.data, n, _ptr(v), _ptr(h)))
+        return v, h
+
+    def unload(self, area_xy):
+        xy = _xy(area_xy)
+        self._check(self._lib.vx_unload(self._h, xy.ctypes.data, xy.shape[0]))
+
+    def resident_count(self) -> int:
+        return int(self._lib.vx_resident_count(self._h))
+
+    def column_heights(self, voxels) -> np.ndarray:
+        """Area::update_all_column_heights on host data (n areas)."""
+        voxels = np.ascontiguousarray(voxels, np.uint8).reshape(-1, VOXELS_IN_AREA)
+        n = voxels.shape[0]
+        mh = np.empty((n, COLUMNS_IN_AREA), np.uint8)
+        self._check(self._lib.vx_column_heights(self._h, voxels.ctypes.data, n, mh.ctypes.data))
+        return mh
+
+    # -- mesh
+    def mesh(self, area_xy) -> dict:
+        """Renderer::load_all_blocking: mesh on the device; returns the sizes."""
+        xy = _xy(area_xy)
+        info = MeshInfo()
+        self._check(self._lib.vx_mesh(self._h, xy.ctypes.data, xy.shape[0], C.byref(info)))
+        self._mesh_n = xy.shape[0]
+        return {k: int(getattr(info, k)) for k, _ in info._fields_}
+
+    def mesh_read(self, info: dict, out=None):
+        """Copy the last mesh to the host: (rec_first, face_first, recs, vertices, indices)."""
+        n = self._mesh_n
+        if out is None:
+            out = (np.empty(n + 1, np.uint32), np.empty(n + 1, np.uint32),
+                   np.empty(info["n_recs"], REC_DTYPE), np.empty(info["n_faces"] * 4, VERTEX_DTYPE),
+                   np.empty(info["n_faces"] * 6, np.uint16))
+        rf, ff, recs, verts, idx = out
+        self._check(self._lib.vx_mesh_read(self._h, _ptr(rf), _ptr(ff), _ptr(recs), _ptr(verts), _ptr(idx)))
+        return out
+
+    # -- edits
+    def apply_edits(self, edits) -> np.ndarray:
+        """World::set for a batch (array order). Returns the dirty areas as [k,2] u32."""
+        e = np.ascontiguousarray(edits, dtype=EDIT_DTYPE)
+        n = e.shape[0]
+        dirty = np.empty((max(3 * n, 1), 2), np.uint32)
+        nd = C.c_int(0)
+        self._check(self._lib.vx_apply_edits(self._h, e.ctypes.data, n, dirty.ctypes.data, C.byref(nd)))
+        return dirty[: nd.value].copy()
+
+    def heightmap(self, area_xy, cam_ax: int, cam_ay: int, rgba=None) -> np.ndarray:
+        xy = _xy(area_xy)
+        if rgba is None:
+            rgba = np.empty((512, 512, 4), np.uint8)
+        self._check(self._lib.vx_heightmap(self._h, xy.ctypes.data, xy.shape[0], cam_ax, cam_ay, rgba.ctypes.data))
+        return rgba
+
+    def light(self, area_xy):
+        xy = _xy(area_xy)
+        n = xy.shape[0]
+        out = np.empty((n, VOXELS_IN_AREA), np.uint8)
+        it = C.c_int(0)
+        self._check(self._lib.vx_light(self._h, xy.ctypes.data, n, out.ctypes.data, C.byref(it)))
+        return out, it.value
+
+    def fp64_rate(self):
+        g, ms = C.c_double(0), C.c_float(0)
+        self._check(self._lib.vx_diag_fp64_rate(self._h, C.byref(g), C.byref(ms)))
+        return g.value, ms.value

@@ -1,0 +1,845 @@
+// vx_api.cu -- the C ABI of include/voxel_cuda.h: context, resident-area pool, dense area map,
+// kernel sequencing, host<->device copies.  No torch, no CPU compute path: a context cannot be
+// created without a CUDA device, and every voxel / height / vertex is produced by a kernel.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/voxel_cuda.h"
+#include "vx_kernels.hpp"
+
+using namespace vx;
+
+namespace {
+
+struct DevBuf {  // grow-only device scratch buffer (contents not preserved on growth)
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {  // retry with the exact size before giving up
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = std::max<size_t>(bytes * 2, 1 << 16);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+inline uint64_t area_key(uint32_t ax, uint32_t ay) { return ((uint64_t)ax << 32) | ay; }
+
+enum TimerId { TM_GEN_COLUMNS, TM_GEN_CAVES, TM_GEN_FINISH, TM_MESH_COUNT, TM_MESH_EMIT, TM_EDIT,
+               TM_HEIGHTMAP, TM_LIGHT, TM_COUNT };
+
+}  // namespace
+
+struct vx_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::mutex mu;
+    std::string last_error;
+
+    bool has_seed = false;
+    NoiseTables tables{};
+
+    // resident-area pool: slot s owns voxels[s*32768..], heights[s*256..], planes[s*4096 u16..]
+    int capacity = 0;
+    uint8_t* d_voxels = nullptr;
+    uint8_t* d_heights = nullptr;
+    uint16_t* d_planes = nullptr;
+    uint2* d_slot_xy = nullptr;
+    std::vector<uint64_t> slot_key;  // per slot; ~0 = free
+    std::vector<int> free_slots;
+    std::unordered_map<uint64_t, int> index;
+
+    // dense slot map over the bounding box of resident areas
+    std::vector<int32_t> h_map;
+    uint32_t map_ax0 = 0, map_ay0 = 0, map_w = 0, map_h = 0;
+    DevBuf d_map;
+    bool map_dirty = true;
+
+    // scratch
+    PinnedBuf h_stage;   // jobs / lists going to the device
+    PinnedBuf h_small;   // small results coming back
+    DevBuf d_jobs, d_list, d_cave_items, d_counters, d_rec_count, d_face_count;
+    DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
+    DevBuf d_heightmap;
+    bool heightmap_init = false;
+
+    // last mesh
+    DevBuf d_rec_first, d_face_first, d_recs, d_vertices, d_indices;
+    int mesh_n = -1;
+    vx_mesh_info mesh_info{};
+
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[TM_COUNT][2] = {};
+    bool ev_used[TM_COUNT] = {};
+    vx_timings timings{};
+};
+
+namespace {
+
+int fail_cuda(vx_ctx* c, cudaError_t e, const char* what) {
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    c->last_error = buf;
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? VX_ERR_OOM : VX_ERR_CUDA;
+}
+int fail(vx_ctx* c, int status, const char* what) {
+    c->last_error = what;
+    return status;
+}
+
+#define VX_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call);   \
+    } while (0)
+
+struct ScopedTimer {
+    vx_ctx* c;
+    int id;
+    ScopedTimer(vx_ctx* ctx, int which) : c(ctx), id(which) {
+        if (c->timing) {
+            cudaEventRecord(c->ev[id][0], c->stream);
+            c->ev_used[id] = true;
+        }
+    }
+    ~ScopedTimer() {
+        if (c->timing) cudaEventRecord(c->ev[id][1], c->stream);
+    }
+};
+
+void reset_timers(vx_ctx* c) {
+    std::memset(c->ev_used, 0, sizeof c->ev_used);
+    std::memset(&c->timings, 0, sizeof c->timings);
+}
+
+// call after the stream has been synchronised
+void collect_timers(vx_ctx* c) {
+    if (!c->timing) return;
+    float* dst[TM_COUNT] = {&c->timings.gen_columns_ms, &c->timings.gen_caves_ms,
+                            &c->timings.gen_finish_ms,  &c->timings.mesh_count_ms,
+                            &c->timings.mesh_emit_ms,   &c->timings.edit_ms,
+                            &c->timings.heightmap_ms,   &c->timings.light_ms};
+    for (int i = 0; i < TM_COUNT; ++i)
+        if (c->ev_used[i]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->ev[i][0], c->ev[i][1]) == cudaSuccess) *dst[i] += ms;
+            c->ev_used[i] = false;
+        }
+}
+
+int sync_stream(vx_ctx* ctx) {
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    VX_CUDA(cudaGetLastError());
+    collect_timers(ctx);
+    return VX_OK;
+}
+
+// ---- pool ---------------------------------------------------------------------------------
+int grow_pool(vx_ctx* ctx, int min_capacity) {
+    if (min_capacity <= ctx->capacity) return VX_OK;
+    int new_cap = std::max({min_capacity, ctx->capacity * 2, 256});
+    uint8_t *nv = nullptr, *nh = nullptr;
+    uint16_t* np = nullptr;
+    uint2* nxy = nullptr;
+    auto alloc_all = [&](int cap) -> cudaError_t {
+        cudaError_t e;
+        if ((e = cudaMalloc(&nv, (size_t)cap * VOXELS_IN_AREA)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&nh, (size_t)cap * COLUMNS_IN_AREA)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&np, (size_t)cap * 4096 * sizeof(uint16_t))) != cudaSuccess) return e;
+        return cudaMalloc(&nxy, (size_t)cap * sizeof(uint2));
+    };
+    cudaError_t e = alloc_all(new_cap);
+    if (e != cudaSuccess && new_cap > min_capacity) {
+        cudaGetLastError();
+        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy);
+        nv = nh = nullptr; np = nullptr; nxy = nullptr;
+        new_cap = min_capacity;
+        e = alloc_all(new_cap);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy);
+        return fail_cuda(ctx, e, "pool allocation");
+    }
+    if (ctx->capacity > 0) {
+        const size_t c = (size_t)ctx->capacity;
+        VX_CUDA(cudaMemcpyAsync(nv, ctx->d_voxels, c * VOXELS_IN_AREA, cudaMemcpyDeviceToDevice, ctx->stream));
+        VX_CUDA(cudaMemcpyAsync(nh, ctx->d_heights, c * COLUMNS_IN_AREA, cudaMemcpyDeviceToDevice, ctx->stream));
+        VX_CUDA(cudaMemcpyAsync(np, ctx->d_planes, c * 4096 * sizeof(uint16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        VX_CUDA(cudaMemcpyAsync(nxy, ctx->d_slot_xy, c * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
+        VX_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
+    }
+    ctx->d_voxels = nv; ctx->d_heights = nh; ctx->d_planes = np; ctx->d_slot_xy = nxy;
+    ctx->slot_key.resize(new_cap, ~0ull);
+    for (int s = new_cap - 1; s >= ctx->capacity; --s) ctx->free_slots.push_back(s);  // pop -> ascending
+    ctx->capacity = new_cap;
+    return VX_OK;
+}
+
+// slots for the listed areas (existing slot if resident, else a fresh one). Fresh slots of one call
+// are handed out in ascending order so a batch lands contiguously in the pool.
+int acquire_slots(vx_ctx* ctx, const uint32_t* area_xy, int n, std::vector<int>& slots) {
+    slots.resize(n);
+    int missing = 0;
+    for (int i = 0; i < n; ++i)
+        if (!ctx->index.count(area_key(area_xy[2 * i], area_xy[2 * i + 1]))) ++missing;
+    if ((int)ctx->free_slots.size() < missing) {
+        const int used = ctx->capacity - (int)ctx->free_slots.size();
+        int st = grow_pool(ctx, used + missing);
+        if (st != VX_OK) return st;
+    }
+    for (int i = 0; i < n; ++i) {
+        const uint64_t key = area_key(area_xy[2 * i], area_xy[2 * i + 1]);
+        auto it = ctx->index.find(key);
+        if (it != ctx->index.end()) {
+            slots[i] = it->second;
+        } else {
+            const int s = ctx->free_slots.back();
+            ctx->free_slots.pop_back();
+            ctx->index.emplace(key, s);
+            ctx->slot_key[s] = key;
+            slots[i] = s;
+            ctx->map_dirty = true;
+        }
+    }
+    return VX_OK;
+}
+
+int upload_map(vx_ctx* ctx) {
+    if (!ctx->map_dirty) return VX_OK;
+    if (ctx->index.empty()) {
+        ctx->map_w = ctx->map_h = 0;
+        ctx->map_dirty = false;
+        return VX_OK;
+    }
+    uint32_t x0 = ~0u, y0 = ~0u, x1 = 0, y1 = 0;
+    for (const auto& kv : ctx->index) {
+        const uint32_t ax = (uint32_t)(kv.first >> 32), ay = (uint32_t)kv.first;
+        x0 = std::min(x0, ax); x1 = std::max(x1, ax);
+        y0 = std::min(y0, ay); y1 = std::max(y1, ay);
+    }
+    const uint64_t w = (uint64_t)x1 - x0 + 1, h = (uint64_t)y1 - y0 + 1;
+    if (w * h > (1ull << 26)) return fail(ctx, VX_ERR_INVALID, "resident areas too scattered for a dense map");
+    ctx->h_map.assign((size_t)(w * h), -1);
+    for (const auto& kv : ctx->index) {
+        const uint32_t ax = (uint32_t)(kv.first >> 32), ay = (uint32_t)kv.first;
+        ctx->h_map[(ax - x0) + (size_t)w * (ay - y0)] = kv.second;
+    }
+    ctx->map_ax0 = x0; ctx->map_ay0 = y0; ctx->map_w = (uint32_t)w; ctx->map_h = (uint32_t)h;
+    VX_CUDA(ctx->d_map.ensure(ctx->h_map.size() * sizeof(int32_t)));
+    // h_map is pageable: a synchronous copy keeps it safe to modify afterwards
+    VX_CUDA(cudaMemcpyAsync(ctx->d_map.p, ctx->h_map.data(), ctx->h_map.size() * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->map_dirty = false;
+    return VX_OK;
+}
+
+AreaMap device_map(const vx_ctx* ctx) {
+    AreaMap m;
+    m.slots = ctx->d_map.as<int32_t>();
+    m.ax0 = ctx->map_ax0; m.ay0 = ctx->map_ay0; m.w = ctx->map_w; m.h = ctx->map_h;
+    return m;
+}
+
+int host_slot(const vx_ctx* ctx, uint32_t ax, uint32_t ay) {
+    auto it = ctx->index.find(area_key(ax, ay));
+    return it == ctx->index.end() ? -1 : it->second;
+}
+
+// jobs {ax, ay, slot, 0} -> device (through pinned staging; the stream is idle between calls)
+int upload_jobs(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>& slots, int n) {
+    VX_CUDA(ctx->h_stage.ensure((size_t)n * sizeof(uint4)));
+    VX_CUDA(ctx->d_jobs.ensure((size_t)n * sizeof(uint4)));
+    uint4* j = ctx->h_stage.as<uint4>();
+    for (int i = 0; i < n; ++i) j[i] = make_uint4(area_xy[2 * i], area_xy[2 * i + 1], (uint32_t)slots[i], 0u);
+    VX_CUDA(cudaMemcpyAsync(ctx->d_jobs.p, j, (size_t)n * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+    return VX_OK;
+}
+
+// copy per-slot records (stride bytes each) of the listed slots to/from a packed host array, one
+// cudaMemcpyAsync per run of consecutive slots
+int copy_slots(vx_ctx* ctx, const std::vector<int>& slots, int n, uint8_t* dev_base, size_t stride,
+               uint8_t* host, bool to_host) {
+    int i = 0;
+    while (i < n) {
+        int j = i + 1;
+        while (j < n && slots[j] == slots[j - 1] + 1) ++j;
+        uint8_t* d = dev_base + (size_t)slots[i] * stride;
+        uint8_t* h = host + (size_t)i * stride;
+        const size_t bytes = (size_t)(j - i) * stride;
+        if (to_host) VX_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        else VX_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        i = j;
+    }
+    return VX_OK;
+}
+
+// K1 -> K1b -> K2 for areas already holding slots; asynchronous on the stream
+int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>& slots, int n) {
+    int st = upload_jobs(ctx, area_xy, slots, n);
+    if (st != VX_OK) return st;
+    VX_CUDA(ctx->d_cave_items.ensure((size_t)n * COLUMNS_IN_AREA * sizeof(uint32_t)));
+    VX_CUDA(ctx->d_counters.ensure(64));
+    VX_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
+    const uint4* jobs = ctx->d_jobs.as<uint4>();
+    uint32_t* cave_count = ctx->d_counters.as<uint32_t>();
+    {
+        ScopedTimer t(ctx, TM_GEN_COLUMNS);
+        launch_gen_columns(jobs, n, ctx->d_voxels, ctx->d_heights, ctx->d_slot_xy,
+                           ctx->d_cave_items.as<uint32_t>(), cave_count, ctx->stream);
+    }
+    {
+        ScopedTimer t(ctx, TM_GEN_CAVES);
+        launch_gen_caves(ctx->d_cave_items.as<uint32_t>(), cave_count, ctx->d_voxels, ctx->d_heights,
+                         ctx->d_slot_xy, ctx->sm_count, ctx->stream);
+    }
+    {
+        ScopedTimer t(ctx, TM_GEN_FINISH);
+        launch_gen_finish(jobs, n, ctx->d_voxels, ctx->d_heights, ctx->tables.seed, ctx->stream);
+    }
+    ctx->timings.gen_launches += 3;
+    VX_CUDA(cudaGetLastError());
+    return VX_OK;
+}
+
+}  // namespace
+
+// =========================================================================================== ABI
+extern "C" {
+
+int vx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return VX_ERR_NO_DEVICE;
+    }
+    return n;
+}
+
+const char* vx_strerror(int status) {
+    switch (status) {
+    case VX_OK: return "ok";
+    case VX_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case VX_ERR_CUDA: return "CUDA error";
+    case VX_ERR_INVALID: return "invalid argument";
+    case VX_ERR_NO_SEED: return "vx_set_seed has not been called";
+    case VX_ERR_NOT_LOADED: return "area not resident";
+    case VX_ERR_OOM: return "out of memory";
+    case VX_ERR_NO_MESH: return "no mesh available";
+    default: return "unknown status";
+    }
+}
+
+int vx_create(int device, vx_ctx** out) {
+    if (!out) return VX_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return VX_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) return VX_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        cudaGetLastError();
+        return VX_ERR_NO_DEVICE;
+    }
+    vx_ctx* ctx = new vx_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return VX_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < TM_COUNT; ++i)
+        for (int k = 0; k < 2; ++k) cudaEventCreate(&ctx->ev[i][k]);
+    *out = ctx;
+    return VX_OK;
+}
+
+void vx_destroy(vx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
+    DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_list, &ctx->d_cave_items, &ctx->d_counters,
+                      &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
+                      &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
+                      &ctx->d_heightmap, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
+                      &ctx->d_vertices, &ctx->d_indices};
+    for (DevBuf* b : bufs) b->release();
+    ctx->h_stage.release();
+    ctx->h_small.release();
+    for (int i = 0; i < TM_COUNT; ++i)
+        for (int k = 0; k < 2; ++k) cudaEventDestroy(ctx->ev[i][k]);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* vx_last_error(vx_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int vx_set_stream(vx_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return VX_OK;
+}
+
+int vx_sync(vx_ctx* ctx) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    cudaSetDevice(ctx->device);
+    return sync_stream(ctx);
+}
+
+int vx_set_timing(vx_ctx* ctx, int enabled) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->timing = enabled != 0;
+    return VX_OK;
+}
+
+int vx_get_timings(vx_ctx* ctx, vx_timings* out) {
+    if (!ctx || !out) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    *out = ctx->timings;
+    return VX_OK;
+}
+
+void* vx_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void vx_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+uint64_t vx_hash_world_name(const char* world_name) {
+    return world_name ? vx::hash_world_name(world_name) : 0;
+}
+
+int vx_set_seed(vx_ctx* ctx, uint64_t seed) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    build_noise_tables(seed, &ctx->tables);
+    VX_CUDA(upload_noise_tables(ctx->tables, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->has_seed = true;
+    return VX_OK;
+}
+
+int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out,
+                uint8_t* max_height_out) {
+    if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->has_seed) return fail(ctx, VX_ERR_NO_SEED, "vx_generate before vx_set_seed");
+    VX_CUDA(cudaSetDevice(ctx->device));
+    reset_timers(ctx);
+    if (n == 0) return VX_OK;
+    std::vector<int> slots;
+    int st = acquire_slots(ctx, area_xy, n, slots);
+    if (st != VX_OK) return st;
+    if ((st = generate_async(ctx, area_xy, slots, n)) != VX_OK) return st;
+    if (voxels_out && (st = copy_slots(ctx, slots, n, ctx->d_voxels, VOXELS_IN_AREA, voxels_out, true)) != VX_OK) return st;
+    if (max_height_out && (st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, max_height_out, true)) != VX_OK) return st;
+    if ((st = sync_stream(ctx)) != VX_OK) return st;
+    if (ctx->timing) {
+        VX_CUDA(cudaMemcpy(&ctx->timings.cave_columns, ctx->d_counters.p, 4, cudaMemcpyDeviceToHost));
+    }
+    return VX_OK;
+}
+
+int vx_upload(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* voxels,
+              uint8_t* max_height_out) {
+    if (!ctx || n < 0 || (n > 0 && (!area_xy || !voxels))) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    reset_timers(ctx);
+    if (n == 0) return VX_OK;
+    std::vector<int> slots;
+    int st = acquire_slots(ctx, area_xy, n, slots);
+    if (st != VX_OK) return st;
+    if ((st = copy_slots(ctx, slots, n, ctx->d_voxels, VOXELS_IN_AREA, const_cast<uint8_t*>(voxels), false)) != VX_OK) return st;
+    if ((st = upload_jobs(ctx, area_xy, slots, n)) != VX_OK) return st;
+    launch_column_heights(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_heights, ctx->d_slot_xy, ctx->stream);
+    ctx->timings.other_launches += 1;
+    VX_CUDA(cudaGetLastError());
+    if (max_height_out && (st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, max_height_out, true)) != VX_OK) return st;
+    return sync_stream(ctx);
+}
+
+int vx_read_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out,
+                  uint8_t* max_height_out) {
+    if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int> slots(n);
+    for (int i = 0; i < n; ++i) {
+        slots[i] = host_slot(ctx, area_xy[2 * i], area_xy[2 * i + 1]);
+        if (slots[i] < 0) return fail(ctx, VX_ERR_NOT_LOADED, "vx_read_areas: area not resident");
+    }
+    int st;
+    if (voxels_out && (st = copy_slots(ctx, slots, n, ctx->d_voxels, VOXELS_IN_AREA, voxels_out, true)) != VX_OK) return st;
+    if (max_height_out && (st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, max_height_out, true)) != VX_OK) return st;
+    return sync_stream(ctx);
+}
+
+int vx_unload(vx_ctx* ctx, const uint32_t* area_xy, int n) {
+    if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    for (int i = 0; i < n; ++i) {
+        auto it = ctx->index.find(area_key(area_xy[2 * i], area_xy[2 * i + 1]));
+        if (it == ctx->index.end()) continue;
+        ctx->slot_key[it->second] = ~0ull;
+        ctx->free_slots.push_back(it->second);
+        ctx->index.erase(it);
+        ctx->map_dirty = true;
+    }
+    // keep hand-out order ascending so later batches stay contiguous where possible
+    std::sort(ctx->free_slots.begin(), ctx->free_slots.end(), std::greater<int>());
+    return VX_OK;
+}
+
+int vx_resident_count(vx_ctx* ctx) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    return (int)ctx->index.size();
+}
+
+int vx_column_heights(vx_ctx* ctx, const uint8_t* voxels, int n, uint8_t* max_height_out) {
+    if (!ctx || n < 0 || (n > 0 && (!voxels || !max_height_out))) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) return VX_OK;
+    // temporary areas outside the resident pool: [voxels n*32768][heights n*256]
+    const size_t vbytes = (size_t)n * VOXELS_IN_AREA, hbytes = (size_t)n * COLUMNS_IN_AREA;
+    VX_CUDA(ctx->d_tmp.ensure(vbytes + hbytes));
+    uint8_t* dv = ctx->d_tmp.as<uint8_t>();
+    uint8_t* dh = dv + vbytes;
+    VX_CUDA(cudaMemcpyAsync(dv, voxels, vbytes, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(ctx->h_stage.ensure((size_t)n * sizeof(uint4)));
+    VX_CUDA(ctx->d_jobs.ensure((size_t)n * sizeof(uint4)));
+    uint4* j = ctx->h_stage.as<uint4>();
+    for (int i = 0; i < n; ++i) j[i] = make_uint4(0, 0, (uint32_t)i, 0);
+    VX_CUDA(cudaMemcpyAsync(ctx->d_jobs.p, j, (size_t)n * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+    launch_column_heights(ctx->d_jobs.as<uint4>(), n, dv, dh, nullptr, ctx->stream);
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaMemcpyAsync(max_height_out, dh, hbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_stream(ctx);
+}
+
+int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
+    if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    reset_timers(ctx);
+    ctx->mesh_n = -1;
+    std::vector<int> slots(n);
+    for (int i = 0; i < n; ++i) {
+        slots[i] = host_slot(ctx, area_xy[2 * i], area_xy[2 * i + 1]);
+        if (slots[i] < 0) return fail(ctx, VX_ERR_NOT_LOADED, "vx_mesh: area not resident");
+    }
+    // edge neighbours that are not resident are generated, like world.get_with_cache -> load_area
+    std::vector<uint32_t> missing;
+    {
+        std::unordered_map<uint64_t, int> seen;
+        static const int D[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+        for (int i = 0; i < n; ++i)
+            for (int d = 0; d < 4; ++d) {
+                const uint32_t ax = area_xy[2 * i] + D[d][0], ay = area_xy[2 * i + 1] + D[d][1];
+                const uint64_t key = area_key(ax, ay);
+                if (ctx->index.count(key) || seen.count(key)) continue;
+                seen.emplace(key, 1);
+                missing.push_back(ax);
+                missing.push_back(ay);
+            }
+    }
+    int st;
+    if (!missing.empty()) {
+        if (!ctx->has_seed) return fail(ctx, VX_ERR_NO_SEED, "vx_mesh needs to generate edge neighbours but no seed is set");
+        const int m = (int)missing.size() / 2;
+        std::vector<int> mslots;
+        if ((st = acquire_slots(ctx, missing.data(), m, mslots)) != VX_OK) return st;
+        if ((st = generate_async(ctx, missing.data(), mslots, m)) != VX_OK) return st;
+        VX_CUDA(cudaStreamSynchronize(ctx->stream));  // staging buffers are reused below
+        for (int i = 0; i < n; ++i) slots[i] = host_slot(ctx, area_xy[2 * i], area_xy[2 * i + 1]);  // pool may have moved
+    }
+    if ((st = upload_map(ctx)) != VX_OK) return st;
+
+    if (n > 0) {
+        // bit planes of every area read by this call (the meshed ones and their edge neighbours)
+        std::vector<int> plane_slots;
+        {
+            std::vector<uint8_t> mark(ctx->capacity, 0);
+            static const int D[5][2] = {{0, 0}, {1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+            for (int i = 0; i < n; ++i)
+                for (int d = 0; d < 5; ++d) {
+                    const int s = host_slot(ctx, area_xy[2 * i] + D[d][0], area_xy[2 * i + 1] + D[d][1]);
+                    if (s >= 0 && !mark[s]) {
+                        mark[s] = 1;
+                        plane_slots.push_back(s);
+                    }
+                }
+        }
+        const int np = (int)plane_slots.size();
+        // staging: [jobs n uint4][plane slots np int]
+        const size_t jobs_bytes = (size_t)n * sizeof(uint4);
+        VX_CUDA(ctx->h_stage.ensure(jobs_bytes + (size_t)np * sizeof(int)));
+        VX_CUDA(ctx->d_jobs.ensure(jobs_bytes));
+        VX_CUDA(ctx->d_list.ensure((size_t)np * sizeof(int)));
+        uint4* hj = ctx->h_stage.as<uint4>();
+        for (int i = 0; i < n; ++i) hj[i] = make_uint4(area_xy[2 * i], area_xy[2 * i + 1], (uint32_t)slots[i], 0u);
+        int* hp = reinterpret_cast<int*>(ctx->h_stage.as<uint8_t>() + jobs_bytes);
+        std::copy(plane_slots.begin(), plane_slots.end(), hp);
+        VX_CUDA(cudaMemcpyAsync(ctx->d_jobs.p, hj, jobs_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        VX_CUDA(cudaMemcpyAsync(ctx->d_list.p, hp, (size_t)np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+
+        VX_CUDA(ctx->d_rec_count.ensure((size_t)n * 4));
+        VX_CUDA(ctx->d_face_count.ensure((size_t)n * 4));
+        VX_CUDA(ctx->d_rec_first.ensure((size_t)(n + 1) * 4));
+        VX_CUDA(ctx->d_face_first.ensure((size_t)(n + 1) * 4));
+        const AreaMap map = device_map(ctx);
+        {
+            ScopedTimer t(ctx, TM_MESH_COUNT);
+            launch_mesh_planes(ctx->d_list.as<int>(), np, ctx->d_voxels, ctx->d_planes, ctx->stream);
+            launch_mesh_count(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_planes, map,
+                              ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), ctx->stream);
+            launch_mesh_offsets(ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), n,
+                                ctx->d_rec_first.as<uint32_t>(), ctx->d_face_first.as<uint32_t>(), ctx->stream);
+        }
+        ctx->timings.mesh_launches += 3;
+        VX_CUDA(cudaGetLastError());
+        VX_CUDA(ctx->h_small.ensure(16));
+        uint32_t* totals = ctx->h_small.as<uint32_t>();
+        VX_CUDA(cudaMemcpyAsync(&totals[0], ctx->d_rec_first.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        VX_CUDA(cudaMemcpyAsync(&totals[1], ctx->d_face_first.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        VX_CUDA(cudaStreamSynchronize(ctx->stream));
+        const uint64_t n_recs = totals[0], n_faces = totals[1];
+        VX_CUDA(ctx->d_recs.ensure(std::max<size_t>(16, n_recs * 16)));
+        VX_CUDA(ctx->d_vertices.ensure(std::max<size_t>(16, n_faces * 160)));
+        VX_CUDA(ctx->d_indices.ensure(std::max<size_t>(16, n_faces * 12)));
+        MeshOut out;
+        out.rec_first = ctx->d_rec_first.as<uint32_t>();
+        out.face_first = ctx->d_face_first.as<uint32_t>();
+        out.recs = ctx->d_recs.as<uint4>();
+        out.vertices = ctx->d_vertices.as<uint4>();
+        out.indices = ctx->d_indices.as<uint32_t>();
+        {
+            ScopedTimer t(ctx, TM_MESH_EMIT);
+            launch_mesh_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_planes, map, out, ctx->stream);
+        }
+        ctx->timings.mesh_launches += 1;
+        VX_CUDA(cudaGetLastError());
+        if ((st = sync_stream(ctx)) != VX_OK) return st;
+        ctx->mesh_info.n_faces = n_faces;
+        ctx->mesh_info.n_recs = n_recs;
+    } else {
+        ctx->mesh_info.n_faces = ctx->mesh_info.n_recs = 0;
+    }
+    ctx->mesh_info.vertex_bytes = ctx->mesh_info.n_faces * 160;
+    ctx->mesh_info.index_bytes = ctx->mesh_info.n_faces * 12;
+    ctx->mesh_info.rec_bytes = ctx->mesh_info.n_recs * 16;
+    ctx->mesh_n = n;
+    if (info) *info = ctx->mesh_info;
+    return VX_OK;
+}
+
+int vx_mesh_read(vx_ctx* ctx, uint32_t* rec_first, uint32_t* face_first, vx_voxel_rec* recs,
+                 void* vertices, uint16_t* indices) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (ctx->mesh_n < 0) return fail(ctx, VX_ERR_NO_MESH, "vx_mesh_read without vx_mesh");
+    VX_CUDA(cudaSetDevice(ctx->device));
+    const int n = ctx->mesh_n;
+    if (n == 0) {
+        if (rec_first) rec_first[0] = 0;
+        if (face_first) face_first[0] = 0;
+        return VX_OK;
+    }
+    const vx_mesh_info& mi = ctx->mesh_info;
+    if (rec_first) VX_CUDA(cudaMemcpyAsync(rec_first, ctx->d_rec_first.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (face_first) VX_CUDA(cudaMemcpyAsync(face_first, ctx->d_face_first.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (recs && mi.rec_bytes) VX_CUDA(cudaMemcpyAsync(recs, ctx->d_recs.p, mi.rec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (vertices && mi.vertex_bytes) VX_CUDA(cudaMemcpyAsync(vertices, ctx->d_vertices.p, mi.vertex_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (indices && mi.index_bytes) VX_CUDA(cudaMemcpyAsync(indices, ctx->d_indices.p, mi.index_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_area_xy, int* n_dirty) {
+    if (!ctx || n < 0 || (n > 0 && (!edits || !dirty_area_xy)) || !n_dirty) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    reset_timers(ctx);
+    *n_dirty = 0;
+    if (n == 0) return VX_OK;
+    for (int i = 0; i < n; ++i) {  // all-or-nothing validation (reference: world_actions.rs guards)
+        if (edits[i].gz >= (uint32_t)AREA_HEIGHT || edits[i].voxel >= (uint32_t)V_VARIANTS)
+            return fail(ctx, VX_ERR_INVALID, "vx_apply_edits: z >= 128 or voxel id >= 27");
+        if (host_slot(ctx, edits[i].gx / AREA_SIZE, edits[i].gy / AREA_SIZE) < 0)
+            return fail(ctx, VX_ERR_NOT_LOADED, "vx_apply_edits: edited area not resident");
+    }
+    int st;
+    if ((st = upload_map(ctx)) != VX_OK) return st;
+    uint32_t cap = 1024;
+    while (cap < (uint32_t)n * 2u) cap <<= 1;
+    VX_CUDA(ctx->d_hash_keys.ensure((size_t)cap * 8));
+    VX_CUDA(ctx->d_hash_vals.ensure((size_t)cap * 4));
+    VX_CUDA(ctx->d_dirty_flags.ensure((size_t)ctx->capacity * 4));
+    VX_CUDA(ctx->d_dirty_slots.ensure((size_t)ctx->capacity * 4));
+    VX_CUDA(ctx->d_counters.ensure(64));
+    VX_CUDA(ctx->d_edits.ensure((size_t)n * sizeof(uint4)));
+    VX_CUDA(cudaMemsetAsync(ctx->d_hash_keys.p, 0xFF, (size_t)cap * 8, ctx->stream));
+    VX_CUDA(cudaMemsetAsync(ctx->d_hash_vals.p, 0, (size_t)cap * 4, ctx->stream));
+    VX_CUDA(cudaMemsetAsync(ctx->d_dirty_flags.p, 0, (size_t)ctx->capacity * 4, ctx->stream));
+    VX_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
+    static_assert(sizeof(vx_edit) == sizeof(uint4), "vx_edit layout");
+    VX_CUDA(cudaMemcpyAsync(ctx->d_edits.p, edits, (size_t)n * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t* counters = ctx->d_counters.as<uint32_t>();
+    {
+        ScopedTimer t(ctx, TM_EDIT);
+        launch_apply_edits(ctx->d_edits.as<uint4>(), n, device_map(ctx), ctx->d_voxels, ctx->d_heights,
+                           ctx->d_hash_keys.as<unsigned long long>(), ctx->d_hash_vals.as<uint32_t>(), cap,
+                           ctx->d_dirty_flags.as<uint32_t>(), ctx->d_dirty_slots.as<uint32_t>(),
+                           counters /* dirty_count */, reinterpret_cast<int32_t*>(counters + 1), ctx->stream);
+    }
+    ctx->timings.other_launches += 3;
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(ctx->h_small.ensure(16 + (size_t)ctx->capacity * 4));
+    uint32_t* hs = ctx->h_small.as<uint32_t>();
+    VX_CUDA(cudaMemcpyAsync(hs, counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint32_t nd = hs[0];
+    if (nd) {
+        VX_CUDA(cudaMemcpyAsync(hs + 4, ctx->d_dirty_slots.p, (size_t)nd * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if ((st = sync_stream(ctx)) != VX_OK) return st;
+    std::vector<uint32_t> ds(hs + 4, hs + 4 + nd);
+    std::sort(ds.begin(), ds.end());  // deterministic order
+    for (uint32_t i = 0; i < nd; ++i) {
+        const uint64_t key = ctx->slot_key[ds[i]];
+        dirty_area_xy[2 * i] = (uint32_t)(key >> 32);
+        dirty_area_xy[2 * i + 1] = (uint32_t)key;
+    }
+    *n_dirty = (int)nd;
+    return VX_OK;
+}
+
+int vx_heightmap(vx_ctx* ctx, const uint32_t* area_xy, int n, uint32_t cam_area_x,
+                 uint32_t cam_area_y, uint8_t* rgba) {
+    if (!ctx || n < 0 || (n > 0 && !area_xy) || !rgba) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    reset_timers(ctx);
+    const size_t img_bytes = (size_t)VX_HEIGHTMAP_SIZE * VX_HEIGHTMAP_SIZE * 4;
+    int st;
+    if ((st = upload_map(ctx)) != VX_OK) return st;
+    if (!ctx->heightmap_init) {
+        VX_CUDA(ctx->d_heightmap.ensure(img_bytes));
+        VX_CUDA(cudaMemsetAsync(ctx->d_heightmap.p, 0xFF, img_bytes, ctx->stream));  // Image::gen_image_color(WHITE)
+        ctx->heightmap_init = true;
+    }
+    if (n > 0) {
+        VX_CUDA(ctx->h_stage.ensure((size_t)n * 8));
+        VX_CUDA(ctx->d_list.ensure((size_t)n * 8));
+        std::memcpy(ctx->h_stage.p, area_xy, (size_t)n * 8);
+        VX_CUDA(cudaMemcpyAsync(ctx->d_list.p, ctx->h_stage.p, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        ScopedTimer t(ctx, TM_HEIGHTMAP);
+        launch_heightmap(ctx->d_list.as<uint2>(), n, device_map(ctx), ctx->d_heights, cam_area_x, cam_area_y,
+                         ctx->d_heightmap.as<uint32_t>(), ctx->stream);
+        ctx->timings.other_launches += 1;
+    }
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaMemcpyAsync(rgba, ctx->d_heightmap.p, img_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_stream(ctx);
+}
+
+int vx_light(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* light_out, int* iterations) {
+    (void)area_xy; (void)n; (void)light_out; (void)iterations;
+    if (!ctx) return VX_ERR_INVALID;
+    return fail(ctx, VX_ERR_INVALID, "vx_light: not built yet");
+}
+
+int vx_diag_fp64_rate(vx_ctx* ctx, double* gops_per_s, float* ms_out) {
+    if (!ctx || !gops_per_s) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    VX_CUDA(ctx->d_tmp.ensure(64));
+    const int blocks = ctx->sm_count * 8, iters = 1 << 15;
+    cudaEvent_t a, b;
+    VX_CUDA(cudaEventCreate(&a));
+    VX_CUDA(cudaEventCreate(&b));
+    launch_fp64_rate(ctx->d_tmp.as<double>(), blocks, iters / 8, ctx->stream);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(a, ctx->stream);
+        launch_fp64_rate(ctx->d_tmp.as<double>(), blocks, iters, ctx->stream);
+        cudaEventRecord(b, ctx->stream);
+        VX_CUDA(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        VX_CUDA(cudaEventElapsedTime(&ms, a, b));
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    const double ops = (double)blocks * 256.0 * 16.0 * (double)iters;
+    *gops_per_s = ops / (best * 1e-3) / 1e9;
+    if (ms_out) *ms_out = best;
+    return VX_OK;
+}
+
+}  // extern "C"

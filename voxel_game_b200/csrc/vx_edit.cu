@@ -1,0 +1,142 @@
+// vx_edit.cu -- batched block edits (K5) and the height-map image (K6).
+//
+// K5 replaces World::set (world.rs:184-191) -> Area::set (area.rs:99-111) for a batch that must
+// behave as if applied one by one in array order:
+//   pass 1  every edit claims its voxel in an open-addressing hash table and records its index
+//           with atomicMax -> the highest index per voxel is the sequential winner;
+//   pass 2  winners write their voxel, flag their area (and the edge neighbour when the voxel is
+//           on a border column: Renderer::update_location re-meshes the six neighbours,
+//           renderer.rs:244-285) and append newly flagged areas to the dirty list;
+//   pass 3  every edited column is rescanned from the top (area.rs:46-56).  Area::set's
+//           incremental rule (rescan if transparent, else min(prev, z)) yields the same value as a
+//           rescan whenever max_height was consistent before, which generation guarantees.
+// K6 replaces the pixel loop of HeightMap::generate_height_map (height_map.rs:41-85).
+#include "vx_kernels.hpp"
+
+namespace vx {
+namespace {
+
+constexpr unsigned long long EMPTY_KEY = ~0ull;
+
+__device__ __forceinline__ uint32_t hash_u64(unsigned long long k, uint32_t cap_mask) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    return (uint32_t)k & cap_mask;
+}
+
+struct Located {
+    int slot;
+    uint32_t local;  // x + 16 y + 256 z
+    unsigned long long key;
+};
+
+__device__ __forceinline__ Located locate(const uint4 e, const AreaMap& map) {
+    Located l;
+    l.slot = area_slot(map, e.x / AREA_SIZE, e.y / AREA_SIZE);  // world.rs:40-52
+    l.local = (e.x % AREA_SIZE) + (e.y % AREA_SIZE) * AREA_SIZE + e.z * 256u;
+    l.key = (unsigned long long)(uint32_t)l.slot * VOXELS_IN_AREA + l.local;
+    return l;
+}
+
+__global__ void edits_claim_kernel(const uint4* __restrict__ edits, int n, AreaMap map,
+                                   unsigned long long* hash_keys, uint32_t* hash_vals,
+                                   uint32_t cap_mask, int32_t* status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 e = edits[i];
+    const Located l = locate(e, map);
+    if (l.slot < 0) {
+        atomicMin(status, -5);  // VX_ERR_NOT_LOADED
+        return;
+    }
+    uint32_t pos = hash_u64(l.key, cap_mask);
+    while (true) {
+        const unsigned long long prev = atomicCAS(&hash_keys[pos], EMPTY_KEY, l.key);
+        if (prev == EMPTY_KEY || prev == l.key) break;
+        pos = (pos + 1) & cap_mask;
+    }
+    atomicMax(&hash_vals[pos], (uint32_t)i + 1u);
+}
+
+__device__ __forceinline__ void flag_dirty(int slot, uint32_t* dirty_flags, uint32_t* dirty_slots,
+                                           uint32_t* dirty_count) {
+    if (slot < 0) return;  // neighbour not loaded: get_without_loading -> None, skipped
+    if (atomicExch(&dirty_flags[slot], 1u) == 0u) dirty_slots[atomicAdd(dirty_count, 1u)] = (uint32_t)slot;
+}
+
+__global__ void edits_apply_kernel(const uint4* __restrict__ edits, int n, AreaMap map,
+                                   uint8_t* pool_voxels, const unsigned long long* hash_keys,
+                                   const uint32_t* hash_vals, uint32_t cap_mask,
+                                   uint32_t* dirty_flags, uint32_t* dirty_slots,
+                                   uint32_t* dirty_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 e = edits[i];
+    const Located l = locate(e, map);
+    if (l.slot < 0) return;
+    uint32_t pos = hash_u64(l.key, cap_mask);
+    while (hash_keys[pos] != l.key) pos = (pos + 1) & cap_mask;
+    if (hash_vals[pos] != (uint32_t)i + 1u) return;  // a later edit of the same voxel wins
+    pool_voxels[(size_t)l.slot * VOXELS_IN_AREA + l.local] = (uint8_t)e.w;
+    flag_dirty(l.slot, dirty_flags, dirty_slots, dirty_count);
+    const uint32_t ax = e.x / AREA_SIZE, ay = e.y / AREA_SIZE, lx = e.x % AREA_SIZE, ly = e.y % AREA_SIZE;
+    if (lx == 0) flag_dirty(area_slot(map, ax - 1, ay), dirty_flags, dirty_slots, dirty_count);
+    if (lx == AREA_SIZE - 1) flag_dirty(area_slot(map, ax + 1, ay), dirty_flags, dirty_slots, dirty_count);
+    if (ly == 0) flag_dirty(area_slot(map, ax, ay - 1), dirty_flags, dirty_slots, dirty_count);
+    if (ly == AREA_SIZE - 1) flag_dirty(area_slot(map, ax, ay + 1), dirty_flags, dirty_slots, dirty_count);
+}
+
+__global__ void edits_heights_kernel(const uint4* __restrict__ edits, int n, AreaMap map,
+                                     const uint8_t* __restrict__ pool_voxels, uint8_t* pool_heights) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 e = edits[i];
+    const Located l = locate(e, map);
+    if (l.slot < 0) return;
+    const uint32_t col = l.local & 255u;
+    const uint8_t* vox = pool_voxels + (size_t)l.slot * VOXELS_IN_AREA + col;
+    int z = 0;
+    while (z < AREA_HEIGHT && is_transparent(vox[256 * z])) ++z;
+    pool_heights[(size_t)l.slot * COLUMNS_IN_AREA + col] = (uint8_t)(z < AREA_HEIGHT ? z : AREA_HEIGHT - 1);
+}
+
+__global__ void __launch_bounds__(256) heightmap_kernel(const uint2* __restrict__ area_xy, AreaMap map,
+                                                        const uint8_t* __restrict__ pool_heights,
+                                                        uint32_t cam_ax, uint32_t cam_ay,
+                                                        uint32_t* __restrict__ rgba) {
+    const uint2 a = area_xy[blockIdx.x];
+    const int dx = (int)a.x - (int)cam_ax, dy = (int)a.y - (int)cam_ay;
+    // filter_distant_areas (height_map.rs:90-101): |d| < 32 / 2
+    if (dx <= -16 || dx >= 16 || dy <= -16 || dy >= 16) return;
+    const int slot = area_slot(map, a.x, a.y);
+    const int tid = threadIdx.x, x = tid & 15, y = tid >> 4;
+    // get_area_without_loading falls back to an empty area: height 127 (world.rs:64-69)
+    const uint32_t h = slot >= 0 ? pool_heights[(size_t)slot * COLUMNS_IN_AREA + tid] : 127u;
+    const int image_x = 256 + dx * AREA_SIZE + x, image_y = 256 + dy * AREA_SIZE + y;
+    rgba[image_x + image_y * 512] = h * 0x01010101u;  // [height; 4]
+}
+
+}  // namespace
+
+void launch_apply_edits(const uint4* edits, int n, AreaMap map, uint8_t* pool_voxels,
+                        uint8_t* pool_heights, unsigned long long* hash_keys, uint32_t* hash_vals,
+                        uint32_t hash_cap, uint32_t* dirty_flags, uint32_t* dirty_slots,
+                        uint32_t* dirty_count, int32_t* status, cudaStream_t stream) {
+    if (n <= 0) return;
+    const int blocks = (n + 255) / 256;
+    edits_claim_kernel<<<blocks, 256, 0, stream>>>(edits, n, map, hash_keys, hash_vals, hash_cap - 1,
+                                                   status);
+    edits_apply_kernel<<<blocks, 256, 0, stream>>>(edits, n, map, pool_voxels, hash_keys, hash_vals,
+                                                   hash_cap - 1, dirty_flags, dirty_slots,
+                                                   dirty_count);
+    edits_heights_kernel<<<blocks, 256, 0, stream>>>(edits, n, map, pool_voxels, pool_heights);
+}
+
+void launch_heightmap(const uint2* area_xy, int n, AreaMap map, const uint8_t* pool_heights,
+                      uint32_t cam_ax, uint32_t cam_ay, uint32_t* rgba, cudaStream_t stream) {
+    if (n <= 0) return;
+    heightmap_kernel<<<n, 256, 0, stream>>>(area_xy, map, pool_heights, cam_ax, cam_ay, rgba);
+}
+
+}  // namespace vx

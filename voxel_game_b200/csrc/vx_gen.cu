@@ -1,0 +1,472 @@
+// vx_gen.cu -- terrain generation kernels (sm_100a).
+//
+//   K1  gen_columns : one CTA per area, one thread per voxel column.  Column samples
+//                     (generator.rs:108-132), voxel types (voxel_type_generator.rs:31-174), lake
+//                     override (lake_generator.rs:54-74).  The 32 KiB area is assembled in shared
+//                     memory and written to HBM with 16-byte coalesced stores.  Cave-zone columns
+//                     are appended to a work list instead of being carved in place.
+//   K1b gen_caves   : persistent CTAs over the compacted list of cave-zone columns; inside a CTA
+//                     the (column, z) pairs are flattened so that every lane evaluates one
+//                     14-octave 3-D noise value (cave_generator.rs:43-64).  This is the FP64-bound
+//                     part; flattening removes the 60x per-column load imbalance.
+//   K2  gen_finish  : one CTA per area: tree candidates (trees.rs:142-196), ordered placement
+//                     (trees.rs:198-241, one warp, lanes = template cells), column heights
+//                     (area.rs:34-56).
+//   L1  column_heights : Area::update_all_column_heights for uploaded areas.
+//
+// FP64 only (the reference's libnoise is f64 throughout), no FMA contraction (-fmad=false).
+#include "vx_kernels.hpp"
+#include "vx_noise.cuh"
+
+namespace vx {
+
+cudaError_t upload_noise_tables(const NoiseTables& t, cudaStream_t stream) {
+    return cudaMemcpyToSymbolAsync(c_noise, &t, sizeof(NoiseTables), 0, cudaMemcpyHostToDevice,
+                                   stream);
+}
+
+namespace {
+
+enum Biome { DRY = 0, WET = 1, COLD = 2 };
+
+// (128 as f32 * k) as u32 constants of the reference
+constexpr unsigned CAVE_MIN_ZI = 25;      // cave_generator.rs:14
+constexpr unsigned CAVE_MAX_ZI = 115;     // cave_generator.rs:17
+constexpr unsigned LAKE_MAX_TERRAIN = 40; // lake_generator.rs:12
+constexpr unsigned LAKE_TOP_ZI = 34;      // lake_generator.rs:13
+constexpr unsigned SNOW_MOUNTAIN_ZI = 70; // voxel_type_generator.rs:18
+
+__device__ __forceinline__ double normalise(double v) { return (v + 1.0) * 50.0; }  // algorithms.rs:59
+
+// should_generate_alternative_voxel (voxel_type_generator.rs:176-188)
+__device__ __forceinline__ bool alt_voxel(const NoiseShared* s, double px, double py, unsigned zi,
+                                          double threshold) {
+    return normalise(fbm3<FBM_ALT>(s, px, py, (double)zi)) >= threshold;
+}
+// calculate_height_mix (voxel_type_generator.rs:190-192)
+__device__ __forceinline__ double height_mix(unsigned zi, double threshold) {
+    return (1.0 - (double)zi / 128.0) * threshold;
+}
+
+// voxel type of one of the topmost voxels of a column (zi + 3 >= H); everything deeper is Stone
+// in all three biomes (voxel_type_generator.rs:64-174).
+__device__ uint8_t surface_voxel(const NoiseShared* s, int biome, unsigned zi, unsigned H, double px,
+                                 double py) {
+    if (biome == DRY) {
+        // zi + SAND_HEIGHT >= H holds for every caller
+        return alt_voxel(s, px, py, zi, height_mix(zi, 120.0)) ? V_STONE : V_SAND;
+    }
+    if (biome == WET) {
+        if (zi >= SNOW_MOUNTAIN_ZI) {
+            if (zi + 2 < H) return V_STONE;
+            if (alt_voxel(s, px, py, zi, height_mix(zi, 80.0))) return V_SNOW;
+            return zi >= H ? V_DIRT : V_STONE;
+        }
+        if (zi >= H) return alt_voxel(s, px, py, zi, 70.0) ? V_CLAY : V_GRASS;
+        if (zi + 1 >= H) return alt_voxel(s, px, py, zi, 70.0) ? V_CLAY : V_DIRT;
+        return V_STONE;
+    }
+    if (zi >= H) return alt_voxel(s, px, py, zi, 60.0) ? V_ICE : V_SNOW;
+    if (zi + 1 >= H) return alt_voxel(s, px, py, zi, 60.0) ? V_ICE : V_DIRT;
+    return V_STONE;
+}
+
+struct __align__(16) GenSmem {
+    uint4 vox[VOXELS_IN_AREA / 16];
+    NoiseShared noise;
+    unsigned cave_n;
+    unsigned cave_base;
+};
+
+__global__ void __launch_bounds__(256) gen_columns_kernel(const uint4* __restrict__ jobs,
+                                                          uint8_t* __restrict__ pool_voxels,
+                                                          uint8_t* __restrict__ pool_heights,
+                                                          uint2* __restrict__ slot_xy,
+                                                          uint32_t* __restrict__ cave_items,
+                                                          uint32_t* __restrict__ cave_count) {
+    __shared__ GenSmem sm;
+    const int tid = threadIdx.x;
+    const uint4 job = jobs[blockIdx.x];
+    const uint32_t ax = job.x, ay = job.y, slot = job.z;
+
+    for (int i = tid; i < VOXELS_IN_AREA / 16; i += 256) sm.vox[i] = make_uint4(0, 0, 0, 0);
+    load_noise_shared(&sm.noise, tid, 256);
+    if (tid == 0) {
+        sm.cave_n = 0;
+        slot_xy[slot] = make_uint2(ax, ay);
+    }
+    __syncthreads();
+
+    const NoiseShared* s = &sm.noise;
+    uint8_t* vox = reinterpret_cast<uint8_t*>(sm.vox);
+    const unsigned x = tid & 15, y = tid >> 4;
+    // algorithms.rs:12-17: u32 sum, then cast
+    const double px = (double)(x + ax * AREA_SIZE), py = (double)(y + ay * AREA_SIZE);
+
+    // TerrainTypeGenerator::sample (terrain_type.rs:26-32)
+    const double n1 = fbm2<FBM_HEIGHT1>(s, px, py), n2 = fbm2<FBM_HEIGHT2>(s, px, py);
+    double value = fmax(n1, n2);
+    value = value < 0.1 ? 0.1 : (value > 1.0 ? 1.0 : value);
+    const double height_mod = 1.0 - (fbm2<FBM_HEIGHT_MOD>(s, px, py) + 1.0) / 2.0;
+    const unsigned H = f64_as_u32(height_mod * value * 0.55 * 128.0) + 32u;
+    // CaveGenerator::is_cave_zone (cave_generator.rs:36-41)
+    const bool cave_zone = f64_as_i32(normalise(fbm2<FBM_CAVE_CHECK>(s, px, py))) >= 80;
+    // LakeGenerator::sample_lake_depth (lake_generator.rs:27-52)
+    unsigned lake_depth = 0;
+    if (!cave_zone && H <= LAKE_MAX_TERRAIN && H > LAKE_TOP_ZI) {
+        const int d = (f64_as_i32(normalise(fbm2<FBM_LAKE>(s, px, py))) - 70) / 3;
+        lake_depth = d < 2 ? 0u : (unsigned)d;
+    }
+    // BiomeTypeGenerator::sample (biome_type.rs:25-34)
+    const int b = f64_as_i32(normalise(fbm2<FBM_BIOME>(s, px, py)));
+    const int biome = (b >= 0 && b < 20) ? DRY : ((b >= 20 && b < 80) ? WET : COLD);
+
+    // generate_column (generator.rs:70-98) without the cave test; bottom -> top
+    for (unsigned zi = 1; zi <= H; ++zi) {
+        uint8_t v;
+        if (lake_depth != 0 && zi > LAKE_TOP_ZI) {
+            v = V_NONE;  // lake_generator.rs:59-61
+        } else if (lake_depth != 0 && zi >= LAKE_TOP_ZI - lake_depth) {
+            v = (biome == COLD && zi == LAKE_TOP_ZI) ? V_ICE : V_WATER_SOURCE;
+        } else if (zi + 3 < H) {
+            v = V_STONE;
+        } else {
+            v = surface_voxel(s, biome, zi, H, px, py);
+        }
+        vox[tid + 256 * (AREA_HEIGHT - zi)] = v;
+    }
+
+    // scratch for K1b / K2: terrain height (7 bits) | cave flag
+    pool_heights[(size_t)slot * COLUMNS_IN_AREA + tid] = (uint8_t)(H | (cave_zone ? 0x80u : 0u));
+    unsigned my_pos = 0;
+    if (cave_zone) my_pos = atomicAdd(&sm.cave_n, 1u);
+    __syncthreads();
+    if (tid == 0 && sm.cave_n) sm.cave_base = atomicAdd(cave_count, sm.cave_n);
+    __syncthreads();
+    if (cave_zone) cave_items[sm.cave_base + my_pos] = slot * COLUMNS_IN_AREA + tid;
+
+    uint4* dst = reinterpret_cast<uint4*>(pool_voxels + (size_t)slot * VOXELS_IN_AREA);
+    for (int i = tid; i < VOXELS_IN_AREA / 16; i += 256) dst[i] = sm.vox[i];
+}
+
+// ------------------------------------------------------------------------------------------- K1b
+constexpr int CAVE_BATCH = 64;  // cave columns per CTA iteration
+
+struct CaveSmem {
+    uint8_t perm[TAB_COUNT][256];
+    uint32_t item[CAVE_BATCH];
+    uint32_t first[CAVE_BATCH + 1];  // exclusive prefix of per-column voxel counts
+};
+
+__global__ void __launch_bounds__(256) gen_caves_kernel(const uint32_t* __restrict__ cave_items,
+                                                        const uint32_t* __restrict__ cave_count,
+                                                        uint8_t* __restrict__ pool_voxels,
+                                                        const uint8_t* __restrict__ pool_heights,
+                                                        const uint2* __restrict__ slot_xy) {
+    __shared__ CaveSmem sm;
+    const int tid = threadIdx.x;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_noise.t.perm[0][0]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.perm[0][0]);
+        for (int i = tid; i < TAB_COUNT * 256 / 4; i += 256) dst[i] = src[i];
+    }
+    const uint32_t n_items = *cave_count;
+    const FbmParams& q1 = c_noise.t.fbm[FBM_CAVE1];
+    const FbmParams& q2 = c_noise.t.fbm[FBM_CAVE2];
+    const uint8_t* p1 = sm.perm[q1.table];
+    const uint8_t* p2 = sm.perm[q2.table];
+
+    for (uint32_t batch = blockIdx.x; batch * CAVE_BATCH < n_items; batch += gridDim.x) {
+        __syncthreads();  // previous iteration done with sm.item / sm.first (and perm loaded)
+        if (tid < CAVE_BATCH) {
+            const uint32_t idx = batch * CAVE_BATCH + tid;
+            uint32_t item = 0, cnt = 0;
+            if (idx < n_items) {
+                item = cave_items[idx];
+                const unsigned H = pool_heights[item] & 0x7Fu;
+                // should_be_cave evaluates the noise for CAVE_MIN_ZI <= zi < CAVE_MAX_ZI, zi <= H
+                // (in a cave zone lake_depth is 0, so the voxel is never None/WaterSource)
+                const unsigned top = H < CAVE_MAX_ZI - 1 ? H : CAVE_MAX_ZI - 1;
+                cnt = top >= CAVE_MIN_ZI ? top - CAVE_MIN_ZI + 1 : 0;
+            }
+            sm.item[tid] = item;
+            // inclusive scan over the 64 counts (two warps)
+            uint32_t v = cnt;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                if ((tid & 31) >= d) v += o;
+            }
+            sm.first[tid + 1] = v;
+        }
+        __syncthreads();
+        if (tid >= 32 && tid < CAVE_BATCH) sm.first[tid + 1] += sm.first[32];
+        if (tid == 0) sm.first[0] = 0;
+        __syncthreads();
+        const uint32_t total = sm.first[CAVE_BATCH];
+
+        for (uint32_t w = tid; w < total; w += 256) {
+            // column c with first[c] <= w < first[c+1]
+            int lo = 0, hi = CAVE_BATCH;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (sm.first[mid] <= w) lo = mid; else hi = mid;
+            }
+            const uint32_t item = sm.item[lo];
+            const unsigned zi = CAVE_MIN_ZI + (w - sm.first[lo]);
+            const uint32_t slot = item >> 8, col = item & 255u;
+            const uint2 axy = slot_xy[slot];
+            const double px = (double)((col & 15u) + axy.x * AREA_SIZE);
+            const double py = (double)((col >> 4) + axy.y * AREA_SIZE);
+            const double pz = (double)zi;
+
+            // Max<Fbm, Fbm>::sample (cave_generator.rs:27-30,61)
+            double xa = px * q1.frequency, ya = py * q1.frequency, za = pz * q1.frequency, a = 0.0;
+#pragma unroll 1
+            for (int o = 0; o < 6; ++o) {
+                a += q1.amp[o] * simplex3(p1, xa, ya, za);
+                xa *= q1.lacunarity; ya *= q1.lacunarity; za *= q1.lacunarity;
+            }
+            a *= q1.norm;
+            double xb = px * q2.frequency, yb = py * q2.frequency, zb = pz * q2.frequency, bsum = 0.0;
+#pragma unroll 1
+            for (int o = 0; o < 8; ++o) {
+                bsum += q2.amp[o] * simplex3(p2, xb, yb, zb);
+                xb *= q2.lacunarity; yb *= q2.lacunarity; zb *= q2.lacunarity;
+            }
+            bsum *= q2.norm;
+            const int c = f64_as_i32(normalise(fmax(a, bsum)));
+            if (c >= 70 && c < 90)  // cave_generator.rs:10-11,63: leave air
+                pool_voxels[(size_t)slot * VOXELS_IN_AREA + col + 256u * (AREA_HEIGHT - zi)] = V_NONE;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- K2
+struct TreeCell { int8_t x, y, z; uint8_t voxel; };
+enum TreeType { T_NONE = 0, T_SHORT, T_TALL, T_TALL_CACTUS, T_DEAD, T_HUGE, T_SHORT_CACTUS, T_BUSH };
+
+// trees.rs:15-75, indexed by TreeType (trees.rs:77-87)
+__constant__ uint8_t c_tree_cells_n[8] = {0, 8, 9, 3, 2, 27, 1, 1};
+__constant__ TreeCell c_tree_cells[8][27] = {
+    {},
+    // Short
+    {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}, {0, 0, -3, V_WOOD}, {0, 0, -4, V_LEAVES},
+     {0, -1, -3, V_LEAVES}, {0, 1, -3, V_LEAVES}, {1, 0, -3, V_LEAVES}, {-1, 0, -3, V_LEAVES}},
+    // Tall
+    {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}, {0, 0, -3, V_WOOD}, {0, 0, -4, V_WOOD},
+     {0, 0, -5, V_LEAVES}, {0, -1, -4, V_LEAVES}, {0, 1, -4, V_LEAVES}, {1, 0, -4, V_LEAVES},
+     {-1, 0, -4, V_LEAVES}},
+    // TallCactus
+    {{0, 0, -1, V_CACTUS}, {0, 0, -2, V_CACTUS}, {0, 0, -3, V_CACTUS}},
+    // DeadTree
+    {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}},
+    // HugeTree
+    {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}, {0, 0, -3, V_WOOD}, {0, 0, -4, V_WOOD},
+     {0, 0, -5, V_WOOD}, {1, 0, -4, V_WOOD}, {0, 1, -4, V_WOOD}, {0, -1, -4, V_WOOD},
+     {-1, 0, -4, V_WOOD}, {0, -1, -5, V_LEAVES}, {0, -2, -5, V_LEAVES}, {0, 1, -5, V_LEAVES},
+     {0, 2, -5, V_LEAVES}, {1, 0, -5, V_LEAVES}, {2, 0, -5, V_LEAVES}, {-1, 0, -5, V_LEAVES},
+     {-2, 0, -5, V_LEAVES}, {-1, -1, -5, V_LEAVES}, {-1, 1, -5, V_LEAVES}, {1, 1, -5, V_LEAVES},
+     {1, -1, -5, V_LEAVES}, {0, 0, -6, V_LEAVES}, {0, 1, -6, V_LEAVES}, {1, 0, -6, V_LEAVES},
+     {0, -1, -6, V_LEAVES}, {-1, 0, -6, V_LEAVES}, {0, 0, -7, V_LEAVES}},
+    // ShortCactus
+    {{0, 0, -1, V_CACTUS}},
+    // Bush
+    {{0, 0, -1, V_LEAVES}},
+};
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t v, int r) { return (v << r) | (v >> (64 - r)); }
+
+// algorithms.rs:41-55
+__device__ __forceinline__ uint64_t split_mix64(uint64_t s) {
+    uint64_t z = s + 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+// should_generate_tree (trees.rs:142-196) with the weighted pick unrolled per base voxel.
+// TreeType::ALL_TYPES order = Short, Tall, TallCactus, ShortCactus, DeadTree, HugeTree, Bush;
+// weights 1000, 1000, 500, 200, 10, 300, 100 (trees.rs:88-131).
+__device__ int pick_tree(uint8_t base, uint64_t seed, uint32_t ax, uint32_t ay, uint32_t lx,
+                         uint32_t ly, uint32_t lz) {
+    if (!(base == V_GRASS || base == V_DIRT || base == V_CLAY || base == V_SAND)) return T_NONE;
+    // combine_seed (algorithms.rs:28-48)
+    uint64_t c = seed * 0x517cc1b727220a95ull;
+    c = rotl64(c + ax, 11);
+    c = rotl64(c + ay, 13);
+    c = rotl64(c + lx, 17);
+    c = rotl64(c + ly, 19);
+    c = rotl64(c + lz, 23);
+    c *= 0xff51afd7ed558ccdull;
+    const uint64_t r = split_mix64(c);
+    if (((r >> 4) % 60ull) != 0) return T_NONE;
+    const uint64_t pick = split_mix64(r) >> 4;
+    // candidate lists in ALL_TYPES order, filtered by get_allowed_base (trees.rs:104-115)
+    switch (base) {
+    case V_GRASS: {  // Short 1000, Tall 1000, Dead 10, Huge 300, Bush 100  (sum 2410)
+        uint64_t w = pick % 2410ull;
+        if (w < 1000) return T_SHORT;
+        w -= 1000;
+        if (w < 1000) return T_TALL;
+        w -= 1000;
+        if (w < 10) return T_DEAD;
+        w -= 10;
+        if (w < 300) return T_HUGE;
+        return T_BUSH;
+    }
+    case V_CLAY: {  // Short 1000, Tall 1000, Dead 10 (sum 2010)
+        uint64_t w = pick % 2010ull;
+        if (w < 1000) return T_SHORT;
+        w -= 1000;
+        if (w < 1000) return T_TALL;
+        return T_DEAD;
+    }
+    case V_DIRT:  // Dead only
+        return T_DEAD;
+    default: {  // Sand: TallCactus 500, ShortCactus 200, Dead 10, Bush 100 (sum 810)
+        uint64_t w = pick % 810ull;
+        if (w < 500) return T_TALL_CACTUS;
+        w -= 500;
+        if (w < 200) return T_SHORT_CACTUS;
+        w -= 200;
+        if (w < 10) return T_DEAD;
+        return T_BUSH;
+    }
+    }
+}
+
+__global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict__ jobs,
+                                                         uint8_t* __restrict__ pool_voxels,
+                                                         uint8_t* __restrict__ pool_heights,
+                                                         uint64_t seed) {
+    __shared__ uint16_t s_tree[COLUMNS_IN_AREA];  // indexed x*16 + y (generator.rs:54-58 order)
+    __shared__ int s_min_z;
+    const int tid = threadIdx.x;
+    const uint4 job = jobs[blockIdx.x];
+    const uint32_t ax = job.x, ay = job.y, slot = job.z;
+    uint8_t* vox = pool_voxels + (size_t)slot * VOXELS_IN_AREA;
+    uint8_t* heights = pool_heights + (size_t)slot * COLUMNS_IN_AREA;
+    const unsigned x = tid & 15, y = tid >> 4;
+
+    if (tid == 0) s_min_z = AREA_HEIGHT;
+    __syncthreads();
+
+    // max_generated_height = topmost generated non-None voxel (generator.rs:91-93,100)
+    const unsigned H = heights[tid] & 0x7Fu;
+    unsigned z = AREA_HEIGHT - H;
+    atomicMin(&s_min_z, (int)z);
+    uint8_t v = vox[tid + 256u * z];
+    while (v == V_NONE && z < AREA_HEIGHT - 1) {
+        ++z;
+        v = vox[tid + 256u * z];
+    }
+    const int tree = pick_tree(v, seed, ax, ay, x, y, z);
+    s_tree[x * 16 + y] = tree ? (uint16_t)(tree | (z << 8)) : (uint16_t)0;
+    __syncthreads();
+
+    // generate_trees (trees.rs:198-241): candidates in push order, each checked against the
+    // voxels as modified by the trees before it.  One warp; lanes = template cells.
+    if (tid < 32) {
+        const unsigned lane = tid;
+        for (int chunk = 0; chunk < COLUMNS_IN_AREA / 32; ++chunk) {
+            const unsigned mine = s_tree[chunk * 32 + lane];
+            unsigned pending = __ballot_sync(0xFFFFFFFFu, mine != 0);
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const unsigned t = __shfl_sync(0xFFFFFFFFu, mine, src);
+                const int o = chunk * 32 + src;
+                const int type = t & 0xFF, bz = t >> 8, bx = o >> 4, by = o & 15;
+                const int ncell = c_tree_cells_n[type];
+                bool ok = true;
+                int idx = 0;
+                uint8_t cell_voxel = 0;
+                if ((int)lane < ncell) {
+                    const TreeCell c = c_tree_cells[type][lane];
+                    const int cx = bx + c.x, cy = by + c.y, cz = bz + c.z;
+                    cell_voxel = c.voxel;
+                    idx = cx + 16 * cy + 256 * cz;
+                    ok = cx >= 0 && cx < AREA_SIZE && cy >= 0 && cy < AREA_SIZE && cz >= 0 &&
+                         cz < AREA_HEIGHT;
+                    if (ok) ok = vox[idx] == V_NONE;
+                }
+                if (__all_sync(0xFFFFFFFFu, ok) && (int)lane < ncell) vox[idx] = cell_voxel;
+                __syncwarp();  // placed cells are visible to the next candidate's check
+            }
+        }
+    }
+    __syncthreads();
+
+    // update_all_column_heights (area.rs:34-56). Everything above min_z - 7 is still None.
+    int zz = s_min_z - 8;
+    if (zz < 0) zz = 0;
+    while (zz < AREA_HEIGHT && is_transparent(vox[tid + 256 * zz])) ++zz;
+    heights[tid] = (uint8_t)(zz < AREA_HEIGHT ? zz : AREA_HEIGHT - 1);
+}
+
+// ------------------------------------------------------------------------------------------- L1
+__global__ void __launch_bounds__(256) column_heights_kernel(const uint4* __restrict__ jobs,
+                                                             const uint8_t* __restrict__ pool_voxels,
+                                                             uint8_t* __restrict__ pool_heights,
+                                                             uint2* __restrict__ slot_xy) {
+    const int tid = threadIdx.x;
+    const uint4 job = jobs[blockIdx.x];
+    const uint32_t slot = job.z;
+    const uint8_t* vox = pool_voxels + (size_t)slot * VOXELS_IN_AREA;
+    if (tid == 0 && slot_xy) slot_xy[slot] = make_uint2(job.x, job.y);
+    int z = 0;
+    while (z < AREA_HEIGHT && is_transparent(vox[tid + 256 * z])) ++z;
+    pool_heights[(size_t)slot * COLUMNS_IN_AREA + tid] = (uint8_t)(z < AREA_HEIGHT ? z : AREA_HEIGHT - 1);
+}
+
+// ------------------------------------------------------------------------------------------- diag
+// DADD + DMUL issue-rate probe: 8 independent chains per thread, one add and one multiply per
+// chain per step, nothing contractable (-fmad=false).  2 * 8 * iters ops per thread.
+__global__ void __launch_bounds__(256) fp64_rate_kernel(double* sink, int iters) {
+    double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.125, a2 = a0 + 0.25, a3 = a0 + 0.375;
+    double a4 = a0 + 0.5, a5 = a0 + 0.625, a6 = a0 + 0.75, a7 = a0 + 0.875;
+    const double m = 0.9999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * m; a1 = a1 * m; a2 = a2 * m; a3 = a3 * m;
+        a4 = a4 * m; a5 = a5 * m; a6 = a6 * m; a7 = a7 * m;
+        a0 = a0 + c; a1 = a1 + c; a2 = a2 + c; a3 = a3 + c;
+        a4 = a4 + c; a5 = a5 + c; a6 = a6 + c; a7 = a7 + c;
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 12345.678) sink[0] = r;  // never true; keeps the chains alive
+}
+
+}  // namespace
+
+void launch_gen_columns(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
+                        uint2* slot_xy, uint32_t* cave_items, uint32_t* cave_count,
+                        cudaStream_t stream) {
+    if (n <= 0) return;
+    gen_columns_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_heights, slot_xy, cave_items,
+                                              cave_count);
+}
+
+void launch_gen_caves(const uint32_t* cave_items, const uint32_t* cave_count, uint8_t* pool_voxels,
+                      const uint8_t* pool_heights, const uint2* slot_xy, int sm_count,
+                      cudaStream_t stream) {
+    gen_caves_kernel<<<sm_count * 4, 256, 0, stream>>>(cave_items, cave_count, pool_voxels,
+                                                       pool_heights, slot_xy);
+}
+
+void launch_gen_finish(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
+                       uint64_t seed, cudaStream_t stream) {
+    if (n <= 0) return;
+    gen_finish_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_heights, seed);
+}
+
+void launch_column_heights(const uint4* jobs, int n, const uint8_t* pool_voxels,
+                           uint8_t* pool_heights, uint2* slot_xy, cudaStream_t stream) {
+    if (n <= 0) return;
+    column_heights_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_heights, slot_xy);
+}
+
+void launch_fp64_rate(double* sink, int blocks, int iters, cudaStream_t stream) {
+    fp64_rate_kernel<<<blocks, 256, 0, stream>>>(sink, iters);
+}
+
+}  // namespace vx

@@ -1,0 +1,68 @@
+// vx_kernels.hpp -- launchers of the device kernels (implemented in vx_gen.cu, vx_mesh.cu,
+// vx_edit.cu, vx_light.cu); called only from vx_api.cu.  All launches are asynchronous on
+// `stream`; all pointers are device pointers.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "vx_common.cuh"
+#include "vx_tables.hpp"
+
+namespace vx {
+
+// ---- tables
+cudaError_t upload_noise_tables(const NoiseTables& t, cudaStream_t stream);
+
+// ---- generation (K1, K1b, K2) and column heights (L1)
+// jobs: n entries {area x, area y, slot, 0}
+void launch_gen_columns(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
+                        uint2* slot_xy, uint32_t* cave_items, uint32_t* cave_count,
+                        cudaStream_t stream);
+void launch_gen_caves(const uint32_t* cave_items, const uint32_t* cave_count,
+                      uint8_t* pool_voxels, const uint8_t* pool_heights, const uint2* slot_xy,
+                      int sm_count, cudaStream_t stream);
+void launch_gen_finish(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
+                       uint64_t seed, cudaStream_t stream);
+void launch_column_heights(const uint4* jobs, int n, const uint8_t* pool_voxels,
+                           uint8_t* pool_heights, uint2* slot_xy, cudaStream_t stream);
+
+// ---- meshing (K4): count -> offsets -> emit
+struct MeshOut {
+    uint32_t* rec_first;   // n+1
+    uint32_t* face_first;  // n+1
+    uint4* recs;
+    uint4* vertices;       // 10 uint4 per face
+    uint32_t* indices;     // 3 u32 per face
+};
+// planes: per slot uint16 S[2048] ("voxel != None") then uint16 T[2048] ("transparent")
+void launch_mesh_planes(const int* slots, int n, const uint8_t* pool_voxels, uint16_t* pool_planes,
+                        cudaStream_t stream);
+void launch_mesh_count(const uint4* jobs, int n, const uint8_t* pool_voxels,
+                       const uint16_t* pool_planes, AreaMap map, uint32_t* rec_count,
+                       uint32_t* face_count, cudaStream_t stream);
+void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, int n,
+                         uint32_t* rec_first, uint32_t* face_first, cudaStream_t stream);
+void launch_mesh_emit(const uint4* jobs, int n, const uint8_t* pool_voxels,
+                      const uint16_t* pool_planes, AreaMap map, MeshOut out, cudaStream_t stream);
+
+// ---- edits (K5) and height map (K6)
+// hash_keys must be filled with 0xFF bytes, hash_vals / dirty_flags / dirty_count / status with 0
+void launch_apply_edits(const uint4* edits, int n, AreaMap map, uint8_t* pool_voxels,
+                        uint8_t* pool_heights, unsigned long long* hash_keys, uint32_t* hash_vals,
+                        uint32_t hash_cap, uint32_t* dirty_flags /* per slot */,
+                        uint32_t* dirty_slots, uint32_t* dirty_count, int32_t* status,
+                        cudaStream_t stream);
+void launch_heightmap(const uint2* area_xy, int n, AreaMap map, const uint8_t* pool_heights,
+                      uint32_t cam_ax, uint32_t cam_ay, uint32_t* rgba, cudaStream_t stream);
+
+// ---- L-ext
+void launch_light_init(const uint4* jobs, int n, const uint8_t* pool_voxels,
+                       const uint8_t* pool_heights, uint8_t* light, cudaStream_t stream);
+void launch_light_relax(const uint4* jobs, int n, const uint8_t* pool_voxels, AreaMap map,
+                        const int32_t* slot_to_job, uint8_t* light, uint32_t* changed,
+                        cudaStream_t stream);
+
+// ---- diagnostics
+void launch_fp64_rate(double* sink, int blocks, int iters, cudaStream_t stream);
+
+}  // namespace vx

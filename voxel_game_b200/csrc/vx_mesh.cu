@@ -1,0 +1,444 @@
+// vx_mesh.cu -- face-culled meshing (sm_100a), HBM-bound, no tensor cores.
+//
+// Replaces Renderer::load_full_area (renderer.rs:310-322):
+//   get_renderable_voxels_for_area (world.rs:112-147) + Area::has_non_transparent_neighbours
+//   (area.rs:126-201) + generate_mesh_for_voxel (renderer.rs:126-195) + should_generate_face
+//   (mesh_generator.rs:501-518) + generate_mesh / get_verticies_for_voxel
+//   (mesh_generator.rs:109-147,200-498).
+//
+// Data flow per area (one 256-thread CTA):
+//   planes : each 16-voxel row (fixed y,z) is reduced to two 16-bit planes, S = "voxel != None"
+//            and T = "voxel in Voxel::TRANSPARENT".  face(cur, nbr) = cur != nbr && T(nbr)
+//            (the algebraic form of mesh_generator.rs:501-513), so for opaque voxels the six face
+//            masks of a row are S & shifted/neighbouring T rows -- pure bit operations, with the
+//            one-voxel halo taken from the four edge neighbours' planes.  Only transparent
+//            non-None voxels (water, ice, glass) need the byte-wise cur != nbr refinement.
+//   count  : popc of the masks, CTA reduction -> faces and visible voxels per area.
+//   offsets: exclusive scan over areas -> where each area's records / faces start.
+//   emit   : the same masks again; a CTA-wide exclusive scan puts voxels in the reference's
+//            z,y,x order and faces in push order; face descriptors are staged in shared memory so
+//            that the 160-byte vertex blocks and 12-byte index blocks leave as fully coalesced
+//            16-byte / 4-byte stores.
+#include "vx_kernels.hpp"
+
+namespace vx {
+namespace {
+
+constexpr int ROWS = VOXELS_IN_AREA / 16;  // 2048 rows of 16 voxels
+constexpr int LIST_CAP = 4096;             // face descriptors staged per round
+
+// ------------------------------------------------------------------------------------- planes
+// plane layout per slot: uint16 S[2048] followed by uint16 T[2048] (8 KiB)
+__global__ void __launch_bounds__(256) mesh_planes_kernel(const int* __restrict__ slots,
+                                                          const uint8_t* __restrict__ pool_voxels,
+                                                          uint16_t* __restrict__ pool_planes) {
+    const int slot = slots[blockIdx.x];
+    const uint4* vox = reinterpret_cast<const uint4*>(pool_voxels + (size_t)slot * VOXELS_IN_AREA);
+    uint16_t* S = pool_planes + (size_t)slot * (2 * ROWS);
+    uint16_t* T = S + ROWS;
+    for (int r = threadIdx.x; r < ROWS; r += 256) {
+        const uint4 q = vox[r];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t s = 0, t = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t v = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            s |= (v != 0u ? 1u : 0u) << i;
+            t |= ((TRANSPARENT_BITS >> v) & 1u) << i;
+        }
+        S[r] = (uint16_t)s;
+        T[r] = (uint16_t)t;
+    }
+}
+
+// ------------------------------------------------------------------------------------- masks
+struct AreaView {
+    const uint8_t* vox;        // own voxels
+    const uint8_t* vox_n[4];   // +x, -x, +y, -y neighbour voxels
+    const uint16_t* S;         // own planes
+    const uint16_t* T;
+    const uint16_t* T_n[4];    // neighbour T planes
+};
+
+struct RowMasks {
+    uint32_t m[6];  // L(x+1) R(x-1) F(y+1) B(y-1) D(z+1) U(z-1): bit x set = voxel x has the face
+};
+
+__device__ __forceinline__ bool partial_height(uint32_t v) { return v >= V_WATER1 && v <= V_WATER4; }
+
+__device__ __forceinline__ RowMasks row_masks(const AreaView& a, int r) {
+    RowMasks k;
+    const uint32_t s = a.S[r];
+    if (s == 0) {
+#pragma unroll
+        for (int d = 0; d < 6; ++d) k.m[d] = 0;
+        return k;
+    }
+    const int y = r & 15, z = r >> 4;
+    const uint32_t t = a.T[r];
+    const uint32_t t_xp = (t >> 1) | ((uint32_t)(a.T_n[0][r] & 1u) << 15);
+    const uint32_t t_xm = ((t << 1) & 0xFFFFu) | ((uint32_t)a.T_n[1][r] >> 15);
+    const uint32_t t_yp = y < 15 ? a.T[r + 1] : a.T_n[2][r - 15];
+    const uint32_t t_ym = y > 0 ? a.T[r - 1] : a.T_n[3][r + 15];
+    const uint32_t t_zp = z < AREA_HEIGHT - 1 ? a.T[r + 16] : 0u;  // renderer.rs:165
+    const uint32_t t_zm = z > 0 ? a.T[r - 16] : 0u;                // renderer.rs:173
+    k.m[0] = s & t_xp;
+    k.m[1] = s & t_xm;
+    k.m[2] = s & t_yp;
+    k.m[3] = s & t_ym;
+    k.m[4] = s & t_zp;
+    k.m[5] = s & t_zm;
+
+    // transparent non-None voxels: apply cur != nbr, the top-face rule for partial-height water
+    // (mesh_generator.rs:515-518) and the enclosed-voxel pre-filter (area.rs:126-201)
+    uint32_t w = s & t;
+    while (w) {
+        const int x = __ffs(w) - 1;
+        w &= w - 1;
+        const uint32_t bit = 1u << x;
+        const int idx = x + 16 * r;
+        const uint32_t cur = a.vox[idx];
+        if (k.m[0] & bit) {
+            const uint32_t n = x < 15 ? a.vox[idx + 1] : a.vox_n[0][idx - 15];
+            if (n == cur) k.m[0] &= ~bit;
+        }
+        if (k.m[1] & bit) {
+            const uint32_t n = x > 0 ? a.vox[idx - 1] : a.vox_n[1][idx + 15];
+            if (n == cur) k.m[1] &= ~bit;
+        }
+        if (k.m[2] & bit) {
+            const uint32_t n = y < 15 ? a.vox[idx + 16] : a.vox_n[2][idx - 240];
+            if (n == cur) k.m[2] &= ~bit;
+        }
+        if (k.m[3] & bit) {
+            const uint32_t n = y > 0 ? a.vox[idx - 16] : a.vox_n[3][idx + 240];
+            if (n == cur) k.m[3] &= ~bit;
+        }
+        if ((k.m[4] & bit) && a.vox[idx + 256] == cur) k.m[4] &= ~bit;
+        if ((k.m[5] & bit) && a.vox[idx - 256] == cur) k.m[5] &= ~bit;
+        if (partial_height(cur) && z > 0) {
+            const bool any_plain = ((k.m[0] | k.m[1] | k.m[2] | k.m[3] | k.m[4] | k.m[5]) & bit) != 0;
+            const bool interior = x > 0 && x < 15 && y > 0 && y < 15 && z < AREA_HEIGHT - 1;
+            // an enclosed interior voxel is dropped by get_renderable_voxels_for_area before the
+            // top-face rule is ever consulted (world.rs:137-139)
+            if (any_plain || !interior) k.m[5] |= bit;
+        }
+    }
+    return k;
+}
+
+__device__ __forceinline__ AreaView make_view(const uint4 job, const AreaMap& map,
+                                              const uint8_t* pool_voxels,
+                                              const uint16_t* pool_planes) {
+    AreaView a;
+    const uint32_t ax = job.x, ay = job.y;
+    const int slot = (int)job.z;
+    a.vox = pool_voxels + (size_t)slot * VOXELS_IN_AREA;
+    a.S = pool_planes + (size_t)slot * (2 * ROWS);
+    a.T = a.S + ROWS;
+    const int ns[4] = {area_slot(map, ax + 1, ay), area_slot(map, ax - 1, ay),
+                       area_slot(map, ax, ay + 1), area_slot(map, ax, ay - 1)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        // the host guarantees residency (vx_mesh generates missing neighbours first)
+        const int sl = ns[i] < 0 ? slot : ns[i];
+        a.vox_n[i] = pool_voxels + (size_t)sl * VOXELS_IN_AREA;
+        a.T_n[i] = pool_planes + (size_t)sl * (2 * ROWS) + ROWS;
+    }
+    return a;
+}
+
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------- count
+__global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict__ jobs,
+                                                         const uint8_t* __restrict__ pool_voxels,
+                                                         const uint16_t* __restrict__ pool_planes,
+                                                         AreaMap map, uint32_t* __restrict__ rec_count,
+                                                         uint32_t* __restrict__ face_count) {
+    __shared__ uint32_t s_faces[8], s_recs[8];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const AreaView a = make_view(jobs[blockIdx.x], map, pool_voxels, pool_planes);
+    uint32_t faces = 0, recs = 0;
+    for (int r = tid; r < ROWS; r += 256) {
+        const RowMasks k = row_masks(a, r);
+        faces += __popc(k.m[0]) + __popc(k.m[1]) + __popc(k.m[2]) + __popc(k.m[3]) +
+                 __popc(k.m[4]) + __popc(k.m[5]);
+        recs += __popc(k.m[0] | k.m[1] | k.m[2] | k.m[3] | k.m[4] | k.m[5]);
+    }
+    faces = __reduce_add_sync(0xFFFFFFFFu, faces);
+    recs = __reduce_add_sync(0xFFFFFFFFu, recs);
+    if (lane == 0) {
+        s_faces[wid] = faces;
+        s_recs[wid] = recs;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t f = 0, q = 0;
+        for (int i = 0; i < 8; ++i) {
+            f += s_faces[i];
+            q += s_recs[i];
+        }
+        face_count[blockIdx.x] = f;
+        rec_count[blockIdx.x] = q;
+    }
+}
+
+// ------------------------------------------------------------------------------------- offsets
+// single-CTA exclusive scan over the per-area counts (n <= a few 100k: microseconds)
+__global__ void __launch_bounds__(1024) mesh_offsets_kernel(const uint32_t* __restrict__ rec_count,
+                                                            const uint32_t* __restrict__ face_count,
+                                                            int n, uint32_t* __restrict__ rec_first,
+                                                            uint32_t* __restrict__ face_first) {
+    __shared__ uint32_t s_r[32], s_f[32];
+    __shared__ uint32_t carry_r, carry_f;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_r = carry_f = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const uint32_t r = i < n ? rec_count[i] : 0u, f = i < n ? face_count[i] : 0u;
+        uint32_t ir = warp_inclusive_scan(r, lane), jf = warp_inclusive_scan(f, lane);
+        if (lane == 31) {
+            s_r[wid] = ir;
+            s_f[wid] = jf;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t wr = s_r[lane], wf = s_f[lane];
+            wr = warp_inclusive_scan(wr, lane);
+            wf = warp_inclusive_scan(wf, lane);
+            s_r[lane] = wr;
+            s_f[lane] = wf;
+        }
+        __syncthreads();
+        const uint32_t pr = carry_r + (wid ? s_r[wid - 1] : 0u), pf = carry_f + (wid ? s_f[wid - 1] : 0u);
+        if (i < n) {
+            rec_first[i] = pr + ir - r;
+            face_first[i] = pf + jf - f;
+        }
+        __syncthreads();
+        if (tid == 1023) {
+            carry_r = pr + ir;
+            carry_f = pf + jf;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        rec_first[n] = carry_r;
+        face_first[n] = carry_f;
+    }
+}
+
+// ------------------------------------------------------------------------------------- emit
+// Corner code per (direction, vertex): bit0 = +x side, bit1 = +y side, bit2 = bottom z (z + 0.5),
+// bits 3..4 = uv corner.  Transcribed from the six vec![] blocks of mesh_generator.rs:222-487.
+//   Left(x+1):  (x+h,y-h,zb;s1) (x+h,y-h,zt;s2) (x+h,y+h,zt;s3) (x+h,y+h,zb;s0)
+//   Right(x-1): (x-h,y-h,zt;s3) (x-h,y-h,zb;s0) (x-h,y+h,zb;s1) (x-h,y+h,zt;s2)
+//   Front(y+1): (x-h,y+h,zb;s0) (x+h,y+h,zb;s1) (x+h,y+h,zt;s2) (x-h,y+h,zt;s3)
+//   Back(y-1):  (x-h,y-h,zt;s3) (x+h,y-h,zt;s2) (x+h,y-h,zb;s1) (x-h,y-h,zb;s0)
+//   Down(z+1):  (x-h,y-h,zb;b0) (x+h,y-h,zb;b1) (x+h,y+h,zb;b2) (x-h,y+h,zb;b3)
+//   Up(z-1):    (x+h,y-h,zt;t0) (x-h,y-h,zt;t1) (x-h,y+h,zt;t2) (x+h,y+h,zt;t3)
+#define CORNER(px, py, bottom, uv) ((px) | ((py) << 1) | ((bottom) << 2) | ((uv) << 3))
+__constant__ uint8_t c_corner[6][4] = {
+    {CORNER(1, 0, 1, 1), CORNER(1, 0, 0, 2), CORNER(1, 1, 0, 3), CORNER(1, 1, 1, 0)},
+    {CORNER(0, 0, 0, 3), CORNER(0, 0, 1, 0), CORNER(0, 1, 1, 1), CORNER(0, 1, 0, 2)},
+    {CORNER(0, 1, 1, 0), CORNER(1, 1, 1, 1), CORNER(1, 1, 0, 2), CORNER(0, 1, 0, 3)},
+    {CORNER(0, 0, 0, 3), CORNER(1, 0, 0, 2), CORNER(1, 0, 1, 1), CORNER(0, 0, 1, 0)},
+    {CORNER(0, 0, 1, 0), CORNER(1, 0, 1, 1), CORNER(1, 1, 1, 2), CORNER(0, 1, 1, 3)},
+    {CORNER(1, 0, 0, 0), CORNER(0, 0, 0, 1), CORNER(0, 1, 0, 2), CORNER(1, 1, 0, 3)},
+};
+// normals (mesh_generator.rs:45-50), xyz only, w = 0
+__constant__ float c_normal[6][3] = {{1.f, 0.f, 0.f},  {-1.f, 0.f, 0.f}, {0.f, 1.f, 0.f},
+                                     {0.f, -1.f, 0.f}, {0.f, 0.f, 1.f},  {0.f, 0.f, -1.f}};
+
+// TextureManager::VOXELS_WITH_DIFFERENT_FACES (texture_manager.rs:95-102)
+constexpr uint32_t DIFFERENT_FACES_BITS = (1u << V_GRASS) | (1u << V_TRAMPOLINE) | (1u << V_WOOD) |
+                                          (1u << V_STONE_PILLAR) | (1u << V_BOMB) |
+                                          (1u << V_ACTIVE_BOMB);
+
+// one 32-bit word (0..39) of a face's 4 x 40-byte vertex block
+__device__ __forceinline__ uint32_t face_word(int word, int dir, uint32_t voxel, float cx, float cy,
+                                              float cz) {
+    const int vtx = word / 10, field = word - vtx * 10;
+    const uint32_t code = c_corner[dir][vtx];
+    // get_partial_height_offset (mesh_generator.rs:490-498): k / 5 in f32
+    const float ho = partial_height(voxel) ? (float)(voxel - V_WATER1 + 1) / 5.0f : 0.0f;
+    float f;
+    switch (field) {
+    case 0: f = (code & 1u) ? cx + 0.5f : cx - 0.5f; break;
+    case 1: f = (code & 2u) ? cy + 0.5f : cy - 0.5f; break;
+    case 2: f = (code & 4u) ? cz + 0.5f : cz - 0.5f + ho; break;
+    case 3: {
+        const uint32_t c = (code >> 3) & 3u;
+        f = (c == 1u || c == 2u) ? 1.0f : 0.0f;  // every uv table is (0,_) (1,_) (1,_) (0,_)
+        break;
+    }
+    case 4: {
+        const uint32_t c = (code >> 3) & 3u;
+        const bool high = c < 2u;  // corners 0,1 carry the larger v
+        if ((DIFFERENT_FACES_BITS >> voxel) & 1u) {
+            // TOP_UV / SIDE_UV / BOTTOM_UV (mesh_generator.rs:82-99): 64 px tiles, 32 px gaps in a
+            // 256 px atlas -> 0.625/0.375, 1/0.75, 0.25/0
+            if (dir == 5) f = high ? 0.625f : 0.375f;
+            else if (dir == 4) f = high ? 0.25f : 0.0f;
+            else f = high ? 1.0f : 0.75f;
+        } else {
+            f = high ? 1.0f : 0.0f;  // UV_REPEATING (mesh_generator.rs:61-66)
+        }
+        if (dir < 4 && ho > 0.0f && f > 0.0f) f -= ho;  // mesh_generator.rs:214-220 (sides only)
+        break;
+    }
+    case 5: return 0xFFFFFFFFu;  // COLOR (mesh_generator.rs:43)
+    case 6: f = c_normal[dir][0]; break;
+    case 7: f = c_normal[dir][1]; break;
+    case 8: f = c_normal[dir][2]; break;
+    default: f = 0.0f; break;
+    }
+    return __float_as_uint(f);
+}
+
+// face descriptor: row (11) | x (4) << 11 | dir (3) << 15 | ordinal in voxel (3) << 18 | voxel << 21
+__device__ __forceinline__ uint32_t make_desc(int r, int x, int dir, int ord, uint32_t voxel) {
+    return (uint32_t)r | ((uint32_t)x << 11) | ((uint32_t)dir << 15) | ((uint32_t)ord << 18) |
+           (voxel << 21);
+}
+
+__global__ void __launch_bounds__(256) mesh_emit_kernel(const uint4* __restrict__ jobs,
+                                                        const uint8_t* __restrict__ pool_voxels,
+                                                        const uint16_t* __restrict__ pool_planes,
+                                                        AreaMap map, MeshOut out) {
+    __shared__ uint32_t s_list[LIST_CAP];
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint4 job = jobs[blockIdx.x];
+    const AreaView a = make_view(job, map, pool_voxels, pool_planes);
+    const uint32_t gx0 = job.x * AREA_SIZE, gy0 = job.y * AREA_SIZE;
+    uint32_t face_base = out.face_first[blockIdx.x];  // running, in faces
+    uint32_t rec_base = out.rec_first[blockIdx.x];
+
+    for (int chunk = 0; chunk < ROWS / 256; ++chunk) {
+        const int r = chunk * 256 + tid;  // rows in (z, y) order == the reference's z,y loop
+        const RowMasks k = row_masks(a, r);
+        const uint32_t vis = k.m[0] | k.m[1] | k.m[2] | k.m[3] | k.m[4] | k.m[5];
+        const uint32_t nf = __popc(k.m[0]) + __popc(k.m[1]) + __popc(k.m[2]) + __popc(k.m[3]) +
+                            __popc(k.m[4]) + __popc(k.m[5]);
+        // CTA exclusive scan of (faces | recs << 16)
+        const uint32_t packed = nf | ((uint32_t)__popc(vis) << 16);
+        const uint32_t inc = warp_inclusive_scan(packed, lane);
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t run = 0;
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t v = s_warp[i];
+                s_warp[i] = run;
+                run += v;
+            }
+            s_total = run;
+        }
+        __syncthreads();
+        const uint32_t excl = s_warp[wid] + inc - packed;
+        const uint32_t my_face = excl & 0xFFFFu, my_rec = excl >> 16;
+        const uint32_t total_faces = s_total & 0xFFFFu, total_recs = s_total >> 16;
+
+        for (uint32_t lo = 0; lo < total_faces; lo += LIST_CAP) {
+            // scatter this thread's faces that fall into [lo, lo + LIST_CAP) into the list
+            if (vis && my_face < lo + LIST_CAP && my_face + nf > lo) {
+                uint32_t f = my_face, q = my_rec, rest = vis;
+                while (rest) {
+                    const int x = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    const uint32_t voxel = a.vox[x + 16 * r];
+                    uint32_t m6 = 0;
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) m6 |= ((k.m[d] >> x) & 1u) << d;
+                    if (lo == 0) {  // the record is written once, in the first round
+                        const uint32_t z = (uint32_t)r >> 4, y = (uint32_t)r & 15u;
+                        out.recs[rec_base + q] =
+                            make_uint4(gx0 + x, gy0 + y,
+                                       z | (voxel << 8) | (m6 << 16) | ((uint32_t)__popc(m6) << 24),
+                                       face_base + f);
+                    }
+                    ++q;
+                    int ord = 0;
+                    while (m6) {
+                        const int d = __ffs(m6) - 1;
+                        m6 &= m6 - 1;
+                        if (f >= lo && f < lo + LIST_CAP) s_list[f - lo] = make_desc(r, x, d, ord, voxel);
+                        ++f;
+                        ++ord;
+                    }
+                }
+            }
+            __syncthreads();
+            const uint32_t cnt = min((uint32_t)LIST_CAP, total_faces - lo);
+            // vertices: 10 x 16 bytes per face, consecutive threads -> consecutive 16-byte pieces
+            uint4* vdst = out.vertices + (size_t)(face_base + lo) * 10;
+            for (uint32_t w = tid; w < cnt * 10; w += 256) {
+                const uint32_t fi = w / 10, piece = w - fi * 10;
+                const uint32_t d = s_list[fi];
+                const int rr = d & 2047, x = (d >> 11) & 15, dir = (d >> 15) & 7;
+                const uint32_t voxel = d >> 21;
+                // location.rs:19-27: (internal - 1_000_000) as f32; mesh_generator.rs:120-123
+                const float cx = (float)((int)(gx0 + x) - LOCATION_OFFSET);
+                const float cy = (float)((int)(gy0 + (rr & 15)) - LOCATION_OFFSET);
+                const float cz = (float)(rr >> 4);
+                const int w0 = piece * 4;
+                vdst[w] = make_uint4(face_word(w0, dir, voxel, cx, cy, cz),
+                                     face_word(w0 + 1, dir, voxel, cx, cy, cz),
+                                     face_word(w0 + 2, dir, voxel, cx, cy, cz),
+                                     face_word(w0 + 3, dir, voxel, cx, cy, cz));
+            }
+            // indices: [0,1,2,0,2,3] + 4*ord as three u32 words per face
+            uint32_t* idst = out.indices + (size_t)(face_base + lo) * 3;
+            for (uint32_t w = tid; w < cnt * 3; w += 256) {
+                const uint32_t fi = w / 3, part = w - fi * 3;
+                const uint32_t b = ((s_list[fi] >> 18) & 7u) * 4u;
+                const uint32_t lo16 = part == 0 ? b : b + 2u;
+                const uint32_t hi16 = part == 0 ? b + 1u : (part == 1 ? b : b + 3u);
+                idst[w] = lo16 | (hi16 << 16);
+            }
+            __syncthreads();
+        }
+        face_base += total_faces;
+        rec_base += total_recs;
+    }
+}
+
+}  // namespace
+
+void launch_mesh_planes(const int* slots, int n, const uint8_t* pool_voxels, uint16_t* pool_planes,
+                        cudaStream_t stream) {
+    if (n <= 0) return;
+    mesh_planes_kernel<<<n, 256, 0, stream>>>(slots, pool_voxels, pool_planes);
+}
+
+void launch_mesh_count(const uint4* jobs, int n, const uint8_t* pool_voxels,
+                       const uint16_t* pool_planes, AreaMap map, uint32_t* rec_count,
+                       uint32_t* face_count, cudaStream_t stream) {
+    if (n <= 0) return;
+    mesh_count_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_planes, map, rec_count,
+                                             face_count);
+}
+
+void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, int n,
+                         uint32_t* rec_first, uint32_t* face_first, cudaStream_t stream) {
+    mesh_offsets_kernel<<<1, 1024, 0, stream>>>(rec_count, face_count, n, rec_first, face_first);
+}
+
+void launch_mesh_emit(const uint4* jobs, int n, const uint8_t* pool_voxels,
+                      const uint16_t* pool_planes, AreaMap map, MeshOut out, cudaStream_t stream) {
+    if (n <= 0) return;
+    mesh_emit_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_planes, map, out);
+}
+
+}  // namespace vx

@@ -1,0 +1,187 @@
+// vx_noise.cuh -- f64 simplex / fBm evaluation on the device.
+//
+// Follows libnoise 1.1.2 (the crate the reference calls at terrain_type.rs:28-29,
+// biome_type.rs:27, cave_generator.rs:38,61, lake_generator.rs:44, voxel_type_generator.rs:186):
+// every f64 multiply and add below is a separately rounded IEEE operation in the crate's order
+// (the library is compiled with -fmad=false), so results are bit-identical to a scalar CPU
+// evaluation.  What is *re-organised* for the GPU, all value-preserving:
+//   * floor + integer cast are done on the FP64 add pipe with the 1.5*2^52 trick instead of
+//     FRND/F2I (conversion pipe, 1/4 rate);
+//   * the permutation table is kept un-doubled (256 B, at most 2-way bank conflicts) and indexed
+//     modulo 256, which equals indexing the crate's doubled 512-entry table;
+//   * the 3-D gradient dot product g.x (components 0/+-1) is one signed add instead of
+//     3 multiplies + 2 adds (x*1 = x, x*0 = +-0, y + +-0 = y);
+//   * Fbm amplitudes amp_k are precomputed on the host with the same running product.
+#pragma once
+#include <cstdint>
+
+#include "vx_tables.hpp"
+
+namespace vx {
+
+struct NoiseConst {
+    NoiseTables t;
+};
+__constant__ NoiseConst c_noise;  // this header is included by vx_gen.cu only
+
+// 24 unit gradients at 7.5 deg + k*15 deg (digits as published with OpenSimplex2)
+__constant__ double c_grad2[24][2] = {
+    {0.130526192220052, 0.99144486137381},    {0.38268343236509, 0.923879532511287},
+    {0.608761429008721, 0.793353340291235},   {0.793353340291235, 0.608761429008721},
+    {0.923879532511287, 0.38268343236509},    {0.99144486137381, 0.130526192220051},
+    {0.99144486137381, -0.130526192220051},   {0.923879532511287, -0.38268343236509},
+    {0.793353340291235, -0.60876142900872},   {0.608761429008721, -0.793353340291235},
+    {0.38268343236509, -0.923879532511287},   {0.130526192220052, -0.99144486137381},
+    {-0.130526192220052, -0.99144486137381},  {-0.38268343236509, -0.923879532511287},
+    {-0.608761429008721, -0.793353340291235}, {-0.793353340291235, -0.60876142900872},
+    {-0.923879532511287, -0.38268343236509},  {-0.99144486137381, -0.130526192220052},
+    {-0.99144486137381, 0.130526192220051},   {-0.923879532511287, 0.38268343236509},
+    {-0.793353340291235, 0.608761429008721},  {-0.608761429008721, 0.793353340291235},
+    {-0.38268343236509, 0.923879532511287},   {-0.130526192220052, 0.99144486137381}};
+
+// shared-memory working copy of the tables (random access; constant cache would serialise)
+struct NoiseShared {
+    uint8_t perm[TAB_COUNT][256];
+    double grad2[24][2];
+};
+
+__device__ __forceinline__ void load_noise_shared(NoiseShared* s, int tid, int nthreads) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_noise.t.perm[0][0]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&s->perm[0][0]);
+    for (int i = tid; i < TAB_COUNT * 256 / 4; i += nthreads) dst[i] = src[i];
+    for (int i = tid; i < 48; i += nthreads) (&s->grad2[0][0])[i] = (&c_grad2[0][0])[i];
+}
+
+// floor(x) as a double and as an int, |x| < 2^31, on the FP64 add pipe
+__device__ __forceinline__ double floor_split(double x, int& i) {
+    const double MAGIC = 6755399441055744.0;  // 2^52 + 2^51
+    const double t = x + MAGIC;               // rounds x to the nearest integer
+    int n = __double2loint(t);
+    double r = t - MAGIC;
+    if (r > x) {
+        r -= 1.0;
+        n -= 1;
+    }
+    i = n;
+    return r;
+}
+
+__device__ __forceinline__ double corner2(const NoiseShared* s, double x, double y, unsigned h) {
+    const double t = 0.5 - x * x - y * y;
+    const unsigned gi = h % 24u;
+    const double2 g = *reinterpret_cast<const double2*>(&s->grad2[gi][0]);
+    const double d = g.x * x + g.y * y;
+    const double t2 = t * t;
+    const double v = t2 * t2 * d;
+    return t > 0.0 ? v : 0.0;
+}
+
+__device__ __forceinline__ double simplex2(const NoiseShared* s, const uint8_t* p, double x, double y) {
+    const double SKEW = 0.366025403784439, UNSKEW = 0.211324865405187;
+    const double sk = (x + y) * SKEW;
+    int i, j;
+    const double fx = floor_split(x + sk, i), fy = floor_split(y + sk, j);
+    const double un = (fx + fy) * UNSKEW;
+    const double x0 = x - fx + un, y0 = y - fy + un;
+    const bool lower = !(x0 < y0);  // middle corner (1,0) unless x0 < y0
+    const double x1 = x0 - (lower ? 1.0 : 0.0) + UNSKEW, y1 = y0 - (lower ? 0.0 : 1.0) + UNSKEW;
+    const double x2 = x0 - 1.0 + 2.0 * UNSKEW, y2 = y0 - 1.0 + 2.0 * UNSKEW;
+    const unsigned pi0 = p[i & 255], pi1 = p[(i + 1) & 255];
+    const unsigned h0 = p[(pi0 + j) & 255];
+    const unsigned h1 = lower ? p[(pi1 + j) & 255] : p[(pi0 + j + 1) & 255];
+    const unsigned h2 = p[(pi1 + j + 1) & 255];
+    const double n0 = corner2(s, x0, y0, h0);
+    const double n1 = corner2(s, x1, y1, h1);
+    const double n2 = corner2(s, x2, y2, h2);
+    return (n0 + n1 + n2) * 99.83685446303647;
+}
+
+// gradient h % 12 of the edge-midpoint set
+//   0..3: (+-1,+-1,0)   4..7: (+-1,0,+-1)   8..11: (0,+-1,+-1); bit0 negates the first non-zero
+//   component, bit1 the second
+__device__ __forceinline__ double corner3(double x, double y, double z, unsigned h) {
+    const double t = 0.5 - x * x - y * y - z * z;
+    const unsigned gi = h % 12u;
+    const unsigned grp = gi >> 2;
+    double a = grp == 2u ? y : x;
+    double b = grp == 0u ? y : z;
+    a = (gi & 1u) ? -a : a;
+    b = (gi & 2u) ? -b : b;
+    const double d = a + b;
+    const double t2 = t * t;
+    const double v = t2 * t2 * d;
+    return t > 0.0 ? v : 0.0;
+}
+
+__device__ __forceinline__ double simplex3(const uint8_t* p, double x, double y, double z) {
+    const double SKEW = 1.0 / 3.0, UNSKEW = 1.0 / 6.0;
+    const double sk = (x + y + z) * SKEW;
+    int i, j, k;
+    const double fx = floor_split(x + sk, i), fy = floor_split(y + sk, j),
+                 fz = floor_split(z + sk, k);
+    const double un = (fx + fy + fz) * UNSKEW;
+    const double x0 = x - fx + un, y0 = y - fy + un, z0 = z - fz + un;
+    // rank the three coordinates: second corner steps along the largest, third corner along the
+    // two largest (ties: x before y before z, i.e. x0 >= y0, y0 >= z0, x0 >= z0 count as "greater")
+    const bool xy = x0 >= y0, yz = y0 >= z0, xz = x0 >= z0;
+    const bool i1 = xy && xz, j1 = !xy && yz, k1 = !xz && !yz;
+    const bool i2 = xy || xz, j2 = !xy || yz, k2 = !(xz && yz);
+    // selects, not int->double conversions (those run on the slow conversion pipe)
+    const double x1 = x0 - (i1 ? 1.0 : 0.0) + UNSKEW, y1 = y0 - (j1 ? 1.0 : 0.0) + UNSKEW,
+                 z1 = z0 - (k1 ? 1.0 : 0.0) + UNSKEW;
+    const double x2 = x0 - (i2 ? 1.0 : 0.0) + 2.0 * UNSKEW, y2 = y0 - (j2 ? 1.0 : 0.0) + 2.0 * UNSKEW,
+                 z2 = z0 - (k2 ? 1.0 : 0.0) + 2.0 * UNSKEW;
+    const double x3 = x0 - 1.0 + 3.0 * UNSKEW, y3 = y0 - 1.0 + 3.0 * UNSKEW,
+                 z3 = z0 - 1.0 + 3.0 * UNSKEW;
+    const unsigned pi0 = p[i & 255], pi1 = p[(i + 1) & 255];
+    const unsigned h0 = p[(p[(pi0 + j) & 255] + k) & 255];
+    const unsigned h1 = p[(p[((i1 ? pi1 : pi0) + j + (int)j1) & 255] + k + (int)k1) & 255];
+    const unsigned h2 = p[(p[((i2 ? pi1 : pi0) + j + (int)j2) & 255] + k + (int)k2) & 255];
+    const unsigned h3 = p[(p[(pi1 + j + 1) & 255] + k + 1) & 255];
+    const double n0 = corner3(x0, y0, z0, h0);
+    const double n1 = corner3(x1, y1, z1, h1);
+    const double n2 = corner3(x2, y2, z2, h2);
+    const double n3 = corner3(x3, y3, z3, h3);
+    return (n0 + n1 + n2 + n3) * 76.88375854620836;
+}
+
+template <int ID>
+__device__ __forceinline__ double fbm2(const NoiseShared* s, double x, double y) {
+    const FbmParams& q = c_noise.t.fbm[ID];
+    const uint8_t* p = s->perm[q.table];
+    x *= q.frequency;
+    y *= q.frequency;
+    double acc = 0.0;
+#pragma unroll 1
+    for (int o = 0; o < q.octaves; ++o) {
+        acc += q.amp[o] * simplex2(s, p, x, y);
+        x *= q.lacunarity;
+        y *= q.lacunarity;
+    }
+    return acc * q.norm;
+}
+
+template <int ID>
+__device__ __forceinline__ double fbm3(const NoiseShared* s, double x, double y, double z) {
+    const FbmParams& q = c_noise.t.fbm[ID];
+    const uint8_t* p = s->perm[q.table];
+    x *= q.frequency;
+    y *= q.frequency;
+    z *= q.frequency;
+    double acc = 0.0;
+#pragma unroll 1
+    for (int o = 0; o < q.octaves; ++o) {
+        acc += q.amp[o] * simplex3(p, x, y, z);
+        x *= q.lacunarity;
+        y *= q.lacunarity;
+        z *= q.lacunarity;
+    }
+    return acc * q.norm;
+}
+
+// Rust `f64 as i32` / `as u32` for the value ranges that occur here (|v| < 2^31, never NaN:
+// noise outputs are finite); cvt.rzi saturates like Rust does.
+__device__ __forceinline__ int f64_as_i32(double v) { return __double2int_rz(v); }
+__device__ __forceinline__ unsigned f64_as_u32(double v) { return __double2uint_rz(v); }
+
+}  // namespace vx

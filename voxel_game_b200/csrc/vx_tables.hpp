@@ -1,0 +1,46 @@
+// vx_tables.hpp -- seed-dependent noise tables, built once per seed on the host and uploaded to
+// __constant__ memory.  Replaces the nine Simplex::new(..).fbm(..) constructions that the
+// reference repeats for every area (generator.rs:135-146; terrain_type.rs:15-24;
+// biome_type.rs:19-23; cave_generator.rs:26-34; voxel_type_generator.rs:24-29;
+// lake_generator.rs:21-25).
+#pragma once
+#include <cstdint>
+
+namespace vx {
+
+// One Fbm<Simplex> object: which permutation table it reads and its octave schedule.
+struct FbmParams {
+    double frequency;
+    double lacunarity;
+    double norm;    // 1 / sum_{i<octaves} persistence^i   (libnoise Fbm::new)
+    double amp[8];  // amp[0] = 1, amp[i+1] = amp[i] * persistence  (the running `amp *= p`)
+    int octaves;
+    int table;      // index into NoiseTables::perm
+    int pad[2];
+};
+
+enum FbmId {
+    FBM_HEIGHT1 = 0,  // terrain_type.rs:16  seed        6 oct
+    FBM_HEIGHT2,      // terrain_type.rs:17  seed^MAX    4 oct
+    FBM_HEIGHT_MOD,   // terrain_type.rs:18  seed+1      2 oct
+    FBM_BIOME,        // biome_type.rs:21    seed        2 oct
+    FBM_CAVE1,        // cave_generator.rs:27 seed       6 oct (3-D)
+    FBM_CAVE2,        // cave_generator.rs:28 seed^MAX   8 oct (3-D)
+    FBM_CAVE_CHECK,   // cave_generator.rs:32 seed       2 oct
+    FBM_ALT,          // voxel_type_generator.rs:25-27 seed+1 2 oct (3-D)
+    FBM_LAKE,         // lake_generator.rs:22 seed+10    2 oct
+    FBM_COUNT
+};
+
+enum TableId { TAB_SEED = 0, TAB_NOT_SEED, TAB_SEED_PLUS_1, TAB_SEED_PLUS_10, TAB_COUNT };
+
+struct NoiseTables {
+    uint64_t seed;
+    uint8_t perm[TAB_COUNT][256];  // un-doubled; kernels index with (a + b) & 255
+    FbmParams fbm[FBM_COUNT];
+};
+
+void build_noise_tables(uint64_t seed, NoiseTables* out);
+uint64_t hash_world_name(const char* name);
+
+}  // namespace vx
