@@ -90,9 +90,9 @@ struct vx_ctx {
     std::vector<int> free_slots;
     std::unordered_map<uint64_t, int> index;
 
-    // dense slot map over the bounding box of resident areas
-    std::vector<int32_t> h_map;
-    uint32_t map_ax0 = 0, map_ay0 = 0, map_w = 0, map_h = 0;
+    // device copy of `index` as an open-addressing hash table (see AreaMap)
+    std::vector<uint4> h_map;
+    uint32_t map_mask = 0;
     DevBuf d_map;
     bool map_dirty = true;
 
@@ -250,38 +250,29 @@ int acquire_slots(vx_ctx* ctx, const uint32_t* area_xy, int n, std::vector<int>&
 
 int upload_map(vx_ctx* ctx) {
     if (!ctx->map_dirty) return VX_OK;
-    if (ctx->index.empty()) {
-        ctx->map_w = ctx->map_h = 0;
-        ctx->map_dirty = false;
-        return VX_OK;
-    }
-    uint32_t x0 = ~0u, y0 = ~0u, x1 = 0, y1 = 0;
+    uint32_t cap = 64;
+    while (cap < 2 * ctx->index.size()) cap <<= 1;
+    ctx->h_map.assign(cap, make_uint4(0, 0, 0, 0));
+    const uint32_t mask = cap - 1;
     for (const auto& kv : ctx->index) {
         const uint32_t ax = (uint32_t)(kv.first >> 32), ay = (uint32_t)kv.first;
-        x0 = std::min(x0, ax); x1 = std::max(x1, ax);
-        y0 = std::min(y0, ay); y1 = std::max(y1, ay);
+        uint32_t h = area_hash(ax, ay) & mask;
+        while (ctx->h_map[h].w) h = (h + 1) & mask;
+        ctx->h_map[h] = make_uint4(ax, ay, (uint32_t)kv.second, 1u);
     }
-    const uint64_t w = (uint64_t)x1 - x0 + 1, h = (uint64_t)y1 - y0 + 1;
-    if (w * h > (1ull << 26)) return fail(ctx, VX_ERR_INVALID, "resident areas too scattered for a dense map");
-    ctx->h_map.assign((size_t)(w * h), -1);
-    for (const auto& kv : ctx->index) {
-        const uint32_t ax = (uint32_t)(kv.first >> 32), ay = (uint32_t)kv.first;
-        ctx->h_map[(ax - x0) + (size_t)w * (ay - y0)] = kv.second;
-    }
-    ctx->map_ax0 = x0; ctx->map_ay0 = y0; ctx->map_w = (uint32_t)w; ctx->map_h = (uint32_t)h;
-    VX_CUDA(ctx->d_map.ensure(ctx->h_map.size() * sizeof(int32_t)));
-    // h_map is pageable: a synchronous copy keeps it safe to modify afterwards
-    VX_CUDA(cudaMemcpyAsync(ctx->d_map.p, ctx->h_map.data(), ctx->h_map.size() * sizeof(int32_t),
+    ctx->map_mask = mask;
+    VX_CUDA(ctx->d_map.ensure(ctx->h_map.size() * sizeof(uint4)));
+    VX_CUDA(cudaMemcpyAsync(ctx->d_map.p, ctx->h_map.data(), ctx->h_map.size() * sizeof(uint4),
                             cudaMemcpyHostToDevice, ctx->stream));
-    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));  // h_map is pageable and rebuilt later
     ctx->map_dirty = false;
     return VX_OK;
 }
 
 AreaMap device_map(const vx_ctx* ctx) {
     AreaMap m;
-    m.slots = ctx->d_map.as<int32_t>();
-    m.ax0 = ctx->map_ax0; m.ay0 = ctx->map_ay0; m.w = ctx->map_w; m.h = ctx->map_h;
+    m.entries = ctx->d_map.as<uint4>();
+    m.mask = ctx->map_mask;
     return m;
 }
 

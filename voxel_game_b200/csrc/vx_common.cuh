@@ -29,16 +29,32 @@ __host__ __device__ __forceinline__ bool is_transparent(unsigned v) {
     return (TRANSPARENT_BITS >> v) & 1u;
 }
 
-// Resident-area lookup: dense slot map over the bounding box of the loaded areas.
+// Resident-area lookup: open-addressing hash table (AreaLocation -> pool slot), built on the host
+// whenever the resident set changes.  Entry = {ax, ay, slot, used}; capacity is a power of two and
+// at most half full, so probes are short.  Replaces World.areas: HashMap<AreaLocation, Area>
+// (world.rs:16-21) for device-side neighbour lookups.
 struct AreaMap {
-    const int32_t* slots;  // w*h entries, -1 = not resident
-    uint32_t ax0, ay0, w, h;
+    const uint4* entries;
+    uint32_t mask;  // capacity - 1; 0 entries when the table is empty
 };
 
+__host__ __device__ __forceinline__ uint32_t area_hash(uint32_t ax, uint32_t ay) {
+    uint32_t h = ax * 0x9E3779B1u ^ (ay * 0x85EBCA77u);
+    h ^= h >> 15;
+    h *= 0xC2B2AE3Du;
+    h ^= h >> 13;
+    return h;
+}
+
 __device__ __forceinline__ int area_slot(const AreaMap& m, uint32_t ax, uint32_t ay) {
-    const uint32_t ix = ax - m.ax0, iy = ay - m.ay0;  // wraps to huge when below the origin
-    if (ix >= m.w || iy >= m.h) return -1;
-    return m.slots[ix + m.w * iy];
+    if (m.entries == nullptr) return -1;
+    uint32_t h = area_hash(ax, ay) & m.mask;
+    while (true) {
+        const uint4 e = m.entries[h];
+        if (e.w == 0u) return -1;
+        if (e.x == ax && e.y == ay) return (int)e.z;
+        h = (h + 1u) & m.mask;
+    }
 }
 
 }  // namespace vx
