@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- chunks/sec (gen + light + mesh) of the B200 chunk pipeline.
+
+Workload (BASELINE.json configs[2], the config the metric is quoted on): a 128x128 region of
+chunk columns ("areas") centred on the spawn area, world name "test": generate the region plus
+the one-area ring its border faces need (130x130 = 16 900 areas: noise -> block IDs -> trees ->
+column heights), then mesh the 16 384 inner areas (face culling + vertex/index/record emission).
+One step = one such pass.  With N GPUs every rank does its own 128x128 region (rank r is shifted
+by r*128 areas in x): weak scaling, no data-path collective (areas are pure functions of seed and
+coordinates; the halo ring is regenerated, DESIGN.md "Multi-GPU").
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  the CPU restatement of the reference
+                                                           (oracle/, all host threads; the Rust
+                                                           binary cannot be built in this image)
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+REGION = 128           # areas per side meshed per GPU per step
+CPU_SAMPLE = 64        # cpu_baseline sample: 64x64 areas of the same region
+REF_SAMPLE = 32        # --impl reference: 32x32 areas per step
+WORLD_NAME = "test"    # the reference's own test seed (generator.rs:157)
+
+# algorithmic work per unit (DESIGN.md "Roofline accounting")
+F2_OPS = 61            # f64 add/mul per 2-D simplex octave as issued by the kernel
+F3_OPS = 91            # f64 add/mul per 3-D simplex octave
+AREA_BYTES = 32768 + 256
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons during the timed region (pynvml, 20 ms period)."""
+
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+        0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+        0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self._nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------ CPU legs (oracle)
+def cpu_pass(seed, n_side, faithful=True):
+    """One gen+light+mesh pass of the CPU restatement over an n_side^2 sample of the workload
+    region (plus its ring).  faithful: permutation tables rebuilt per area (generator.rs:51), gen
+    parallel over areas on all threads (rayon par_iter, world_persistence.rs:90-93), mesh serial on
+    one thread (renderer.rs:468-472).  generous: tables hoisted, mesh area-parallel too."""
+    import oracle
+    from voxel_game_b200.world import region_xy, spawn_region
+
+    ax0, ay0, _, _ = spawn_region(REGION)
+    ring = region_xy(ax0 - 1, ay0 - 1, n_side + 2, n_side + 2)
+    inner = region_xy(ax0, ay0, n_side, n_side)
+    t0 = time.perf_counter()
+    vox, mh, _, threads = oracle.generate_areas(seed, ring, rebuild_tables_per_area=faithful, threads=0)
+    t1 = time.perf_counter()
+    world = oracle.World(ax0 - 1, ay0 - 1, n_side + 2, n_side + 2, vox, mh)
+    t2 = time.perf_counter()
+    faces, recs = world.mesh_areas(inner, threads=1 if faithful else 0)
+    t3 = time.perf_counter()
+    return {"areas": n_side * n_side, "gen_s": t1 - t0, "mesh_s": t3 - t2,
+            "total_s": (t1 - t0) + (t3 - t2), "threads": threads, "faces": faces}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    import oracle
+
+    seed = oracle.hash_world_name(WORLD_NAME)
+    for _ in range(args.warmup):
+        cpu_pass(seed, REF_SAMPLE)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_pass(seed, REF_SAMPLE)
+    dt = time.perf_counter() - t0
+    value = REF_SAMPLE * REF_SAMPLE * args.steps / dt
+    gen = cpu_pass(seed, REF_SAMPLE, faithful=False)
+    sample = (f"{REF_SAMPLE}x{REF_SAMPLE} areas of the {REGION}x{REGION} region per step (+ ring), "
+              "gen parallel on all threads with per-area table rebuild, mesh on 1 thread (as the reference)")
+    line = {
+        "impl": "reference", "metric": "chunks/sec (gen+light+mesh)", "value": value, "unit": "chunks/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"c3_{REGION}x{REGION}_gen_light_mesh", "world_name": WORLD_NAME,
+                   "seed": seed, "sample": sample,
+                   "note": "C restatement of the reference's CPU path (oracle/); the Rust/rayon binary cannot be built in this image (no cargo)"},
+        "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": last["threads"], "kind": "port",
+                         "sample": sample,
+                         "generous_value": gen["areas"] / gen["total_s"],
+                         "generous_note": "tables hoisted per seed, mesh area-parallel on all threads"},
+        "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    import voxel_game_b200 as vg
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    seed = vg.hash_world_name(WORLD_NAME)
+    ctx = vg.Context(local_rank, seed=seed)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    ax0, ay0, nx, ny = vg.spawn_region(REGION)
+    ax0 += rank * REGION  # weak scaling: every rank owns its own 128x128 region
+    gen_xy = vg.region_xy(ax0 - 1, ay0 - 1, nx + 2, ny + 2)
+    mesh_xy = vg.region_xy(ax0, ay0, nx, ny)
+    n_gen, n_mesh = len(gen_xy), len(mesh_xy)
+
+    def step():
+        ctx.generate(gen_xy, read=False)
+        return ctx.mesh(mesh_xy)
+
+    # ---- device-resident throughput (`value`)
+    ctx.set_timing(True)
+    info = None
+    for _ in range(args.warmup):
+        info = step()
+    kern = {}
+    work = {}
+    launches = 0
+    sampler = ClockSampler(local_rank)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        ctx.generate(gen_xy, read=False)
+        t = ctx.timings()
+        for k in ("gen_columns_ms", "gen_caves_ms", "gen_finish_ms"):
+            kern[k] = kern.get(k, 0.0) + t[k]
+        launches += t["gen_launches"]
+        work = {k: t[k] for k in ("simplex2_evals", "simplex3_evals", "cave_voxels", "cave_columns")}
+        info = ctx.mesh(mesh_xy)
+        t = ctx.timings()
+        for k in ("mesh_count_ms", "mesh_emit_ms"):
+            kern[k] = kern.get(k, 0.0) + t[k]
+        launches += t["mesh_launches"] + t["gen_launches"]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = n_mesh * world * args.steps / (ms * 1e-3)
+    kern = {k: v / args.steps for k, v in kern.items()}
+
+    # ---- end to end through the C ABI with host buffers (`e2e`)
+    pin = {
+        "vox": vg.PinnedArray((n_gen, 32768), np.uint8), "mh": vg.PinnedArray((n_gen, 256), np.uint8),
+        "rf": vg.PinnedArray((n_mesh + 1,), np.uint32), "ff": vg.PinnedArray((n_mesh + 1,), np.uint32),
+        "recs": vg.PinnedArray((info["n_recs"],), vg.REC_DTYPE),
+        "verts": vg.PinnedArray((info["n_faces"] * 4,), vg.VERTEX_DTYPE),
+        "idx": vg.PinnedArray((info["n_faces"] * 6,), np.uint16),
+    }
+    mesh_out = (pin["rf"].array, pin["ff"].array, pin["recs"].array, pin["verts"].array, pin["idx"].array)
+
+    def e2e_step():
+        ctx.generate(gen_xy, voxels_out=pin["vox"].array, max_height_out=pin["mh"].array)
+        inf = ctx.mesh(mesh_xy)
+        ctx.mesh_read(inf, out=mesh_out)
+        return inf
+
+    ctx.set_timing(False)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    f1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+    if world > 1:
+        tms = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tms.item())
+    e2e_value = n_mesh * world * e2e_steps / (e2e_ms * 1e-3)
+    h2d = (n_gen + n_mesh) * 16  # the two job lists {ax, ay, slot, 0}
+    d2h = n_gen * AREA_BYTES + info["rec_bytes"] + info["vertex_bytes"] + info["index_bytes"] + 2 * 4 * (n_mesh + 1) + 8
+
+    # ---- rooflines (per kernel, from the CUDA-event durations collected in the timed region)
+    hbm_peak, hbm_src = measured_peaks()
+    fp64_gops, _ = ctx.fp64_rate()
+    s2, s3, cave_vox = work["simplex2_evals"], work["simplex3_evals"], work["cave_voxels"]
+    alt3 = s3 - 14 * cave_vox
+    mesh_bytes = n_mesh * 8192 + info["n_faces"] * 172 + info["n_recs"] * 17
+    plane_bytes = n_gen * (32768 + 8192)
+
+    def fp64_roof(ops, ms_k):
+        a = ops / (ms_k * 1e-3) / 1e12
+        return {"bound": "fp64", "achieved": a, "peak": fp64_gops / 1e3, "unit": "TFLOP/s",
+                "frac": a / (fp64_gops / 1e3), "traffic": None, "ms": ms_k,
+                "peak_source": "DADD+DMUL issue rate (no FMA) measured live by vx_diag_fp64_rate"}
+
+    def hbm_roof(nbytes, ms_k):
+        a = nbytes / (ms_k * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
+                "traffic": None, "ms": ms_k, "peak_source": hbm_src}
+
+    rooflines = {
+        "gen_columns": fp64_roof(s2 * F2_OPS + alt3 * F3_OPS, kern["gen_columns_ms"]),
+        "gen_caves": fp64_roof(14 * cave_vox * F3_OPS, kern["gen_caves_ms"]),
+        "gen_finish": hbm_roof(n_gen * 256 * 4, kern["gen_finish_ms"]),
+        "mesh_count": hbm_roof(plane_bytes + n_mesh * 8192, kern["mesh_count_ms"]),
+        "mesh_emit": hbm_roof(mesh_bytes, kern["mesh_emit_ms"]),
+    }
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_path):  # dram bytes per launch from the committed ncu --set full capture
+        with open(traffic_path) as f:
+            for k, v in json.load(f).items():
+                if k in rooflines:
+                    rooflines[k]["traffic"] = v
+    dominant = max(rooflines, key=lambda k: rooflines[k]["ms"])
+    roofline = dict(rooflines[dominant], kernel=dominant)
+
+    line = {
+        "metric": "chunks/sec (gen+light+mesh)", "value": value, "unit": "chunks/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"c3_{REGION}x{REGION}_gen_light_mesh", "areas_meshed_per_gpu": n_mesh,
+                   "areas_generated_per_gpu": n_gen, "world_name": WORLD_NAME, "seed": seed,
+                   "faces_per_gpu": info["n_faces"], "visible_voxels_per_gpu": info["n_recs"],
+                   "parallelism": f"areas sharded x{world}, halo regenerated, no collective",
+                   "l2": "no flush needed: each step streams ~0.55 GB of block IDs and ~1.8 GB of mesh, > 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                "note": "vx_generate + vx_mesh + vx_mesh_read into pinned host buffers (block IDs, heights, records, vertices, indices)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "rooflines": rooflines,
+        "kernel_ms_per_step": kern,
+        "work_per_step": {"simplex2_octave_evals": s2, "simplex3_octave_evals": s3, "cave_voxels": cave_vox,
+                          "f64_ops": s2 * F2_OPS + s3 * F3_OPS},
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        c = cpu_pass(oracle.hash_world_name(WORLD_NAME), CPU_SAMPLE, faithful=True)
+        g = cpu_pass(oracle.hash_world_name(WORLD_NAME), CPU_SAMPLE, faithful=False)
+        line["cpu_baseline"] = {
+            "value": c["areas"] / c["total_s"], "unit": "chunks/s", "cores": c["threads"], "kind": "port",
+            "sample": f"{CPU_SAMPLE}x{CPU_SAMPLE} areas of the same region (+ ring): gen {c['gen_s']:.2f} s on "
+                      f"{c['threads']} threads with per-area table rebuild, mesh {c['mesh_s']:.2f} s on 1 thread",
+            "generous_value": g["areas"] / g["total_s"],
+            "generous_note": "tables hoisted per seed, mesh area-parallel on all threads",
+            "note": "C restatement of the reference (oracle/), not the Rust/rayon binary (no cargo in this image)",
+        }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    for p in pin.values():
+        p.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -117,6 +117,8 @@ def lib():
         L.vgo_emit_area.restype = C.c_long
         L.vgo_emit_area.argtypes = [C.POINTER(_World), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                     C.POINTER(C.c_long), C.c_void_p, C.c_void_p]
+        L.vgo_mesh_areas.restype = C.c_long
+        L.vgo_mesh_areas.argtypes = [C.POINTER(_World), u32p, C.c_int, C.c_int, C.POINTER(C.c_long)]
         L.vgo_apply_edit.restype = C.c_int
         L.vgo_apply_edit.argtypes = [C.POINTER(_World), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8]
         L.vgo_light_flood_world.argtypes = [C.POINTER(_World), u8p]
@@ -239,6 +241,16 @@ class World:
         if r < 0:
             raise ValueError("area or one of its neighbours is not loaded")
         return int(r)
+
+    def mesh_areas(self, area_xy, threads=1):
+        """Renderer::load_all_blocking over a list (masks + emission). Returns (faces, recs)."""
+        area_xy = np.ascontiguousarray(area_xy, np.uint32).reshape(-1, 2)
+        nr = C.c_long(0)
+        nf = lib().vgo_mesh_areas(C.byref(self._w), _p(area_xy, C.c_uint32), area_xy.shape[0],
+                                  int(threads), C.byref(nr))
+        if nf < 0:
+            raise ValueError("an area or one of its neighbours is not loaded")
+        return int(nf), int(nr.value)
 
     def emit_area(self, ax, ay, first_face_base=0):
         """Records, vertices (structured, 4/face) and u16 indices (6/face) of a meshed area."""

@@ -319,3 +319,40 @@ void vgo_height_map(const uint32_t* area_xy, int n, const uint8_t* max_height, u
             }
     }
 }
+
+/* ------------------------------------------------------------------ batch (CPU baseline timing)
+ * Renderer::load_all_blocking (renderer.rs:468-472) over a list of areas: face masks + full vertex
+ * and index emission per area (into scratch that is thrown away, like a Mesh that is built and
+ * stored).  threads == 1 is the faithful setting (the reference meshes serially on the main
+ * thread); threads != 1 runs areas in parallel with OpenMP ("generous"). */
+#include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+long vgo_mesh_areas(vgo_world* w, const uint32_t* area_xy, int n, int threads, long* total_recs) {
+    long faces_total = 0, recs_total = 0;
+    int failed = 0;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : faces_total, recs_total)
+#endif
+    for (int i = 0; i < n; i++) {
+        long nf = vgo_mesh_area(w, area_xy[2 * i], area_xy[2 * i + 1]);
+        if (nf < 0) {
+            failed = 1;
+            continue;
+        }
+        uint8_t* verts = (uint8_t*)malloc((size_t)(nf ? nf : 1) * 4 * sizeof(vertex));
+        uint16_t* idx = (uint16_t*)malloc((size_t)(nf ? nf : 1) * 6 * sizeof(uint16_t));
+        vgo_voxel_rec* recs = (vgo_voxel_rec*)malloc((size_t)(nf ? nf : 1) * sizeof(vgo_voxel_rec));
+        long nr = 0;
+        vgo_emit_area(w, area_xy[2 * i], area_xy[2 * i + 1], 0, recs, &nr, verts, idx);
+        faces_total += nf;
+        recs_total += nr;
+        free(verts);
+        free(idx);
+        free(recs);
+    }
+    if (total_recs) *total_recs = recs_total;
+    return failed ? -1 : faces_total;
+}

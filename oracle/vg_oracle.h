@@ -171,6 +171,10 @@ typedef struct {
 long vgo_emit_area(const vgo_world* w, uint32_t ax, uint32_t ay, uint32_t first_face_base,
                    vgo_voxel_rec* recs, long* n_recs, uint8_t* vertices, uint16_t* indices);
 
+/* Batch of vgo_mesh_area + vgo_emit_area (scratch outputs), for CPU-baseline timing.
+ * threads = 1: serial like Renderer::load_all_blocking (renderer.rs:468-472); <= 0: all threads. */
+long vgo_mesh_areas(vgo_world* w, const uint32_t* area_xy, int n, int threads, long* total_recs);
+
 /* world.set (world.rs:184-191) + renderer.update_location (renderer.rs:239-286).
  * Locations whose area is outside the grid are treated as unloaded (skipped). Returns 0 or -1. */
 int vgo_apply_edit(vgo_world* w, uint32_t gx, uint32_t gy, uint32_t gz, uint8_t voxel);

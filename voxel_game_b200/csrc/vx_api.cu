@@ -318,15 +318,16 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
     VX_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
     const uint4* jobs = ctx->d_jobs.as<uint4>();
     uint32_t* cave_count = ctx->d_counters.as<uint32_t>();
+    unsigned long long* stats = ctx->d_counters.as<unsigned long long>() + 2;  // bytes 16..39
     {
         ScopedTimer t(ctx, TM_GEN_COLUMNS);
         launch_gen_columns(jobs, n, ctx->d_voxels, ctx->d_heights, ctx->d_slot_xy,
-                           ctx->d_cave_items.as<uint32_t>(), cave_count, ctx->stream);
+                           ctx->d_cave_items.as<uint32_t>(), cave_count, stats, ctx->stream);
     }
     {
         ScopedTimer t(ctx, TM_GEN_CAVES);
         launch_gen_caves(ctx->d_cave_items.as<uint32_t>(), cave_count, ctx->d_voxels, ctx->d_heights,
-                         ctx->d_slot_xy, ctx->sm_count, ctx->stream);
+                         ctx->d_slot_xy, stats, ctx->sm_count, ctx->stream);
     }
     {
         ScopedTimer t(ctx, TM_GEN_FINISH);
@@ -488,8 +489,13 @@ int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out
     if (voxels_out && (st = copy_slots(ctx, slots, n, ctx->d_voxels, VOXELS_IN_AREA, voxels_out, true)) != VX_OK) return st;
     if (max_height_out && (st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, max_height_out, true)) != VX_OK) return st;
     if ((st = sync_stream(ctx)) != VX_OK) return st;
-    if (ctx->timing) {
-        VX_CUDA(cudaMemcpy(&ctx->timings.cave_columns, ctx->d_counters.p, 4, cudaMemcpyDeviceToHost));
+    if (ctx->timing) {  // work accounting of this call (the roofline numerators)
+        unsigned long long c[5];
+        VX_CUDA(cudaMemcpy(c, ctx->d_counters.p, sizeof c, cudaMemcpyDeviceToHost));
+        ctx->timings.cave_columns = (uint32_t)c[0];
+        ctx->timings.simplex2_evals = c[2];
+        ctx->timings.cave_voxels = c[4];
+        ctx->timings.simplex3_evals = c[3] + 14ull * c[4];
     }
     return VX_OK;
 }

@@ -40,7 +40,8 @@ __device__ __forceinline__ double normalise(double v) { return (v + 1.0) * 50.0;
 
 // should_generate_alternative_voxel (voxel_type_generator.rs:176-188)
 __device__ __forceinline__ bool alt_voxel(const NoiseShared* s, double px, double py, unsigned zi,
-                                          double threshold) {
+                                          double threshold, unsigned& evals3) {
+    evals3 += 2;  // work accounting (roofline numerator): one 2-octave 3-D fBm
     return normalise(fbm3<FBM_ALT>(s, px, py, (double)zi)) >= threshold;
 }
 // calculate_height_mix (voxel_type_generator.rs:190-192)
@@ -51,23 +52,23 @@ __device__ __forceinline__ double height_mix(unsigned zi, double threshold) {
 // voxel type of one of the topmost voxels of a column (zi + 3 >= H); everything deeper is Stone
 // in all three biomes (voxel_type_generator.rs:64-174).
 __device__ uint8_t surface_voxel(const NoiseShared* s, int biome, unsigned zi, unsigned H, double px,
-                                 double py) {
+                                 double py, unsigned& n3) {
     if (biome == DRY) {
         // zi + SAND_HEIGHT >= H holds for every caller
-        return alt_voxel(s, px, py, zi, height_mix(zi, 120.0)) ? V_STONE : V_SAND;
+        return alt_voxel(s, px, py, zi, height_mix(zi, 120.0), n3) ? V_STONE : V_SAND;
     }
     if (biome == WET) {
         if (zi >= SNOW_MOUNTAIN_ZI) {
             if (zi + 2 < H) return V_STONE;
-            if (alt_voxel(s, px, py, zi, height_mix(zi, 80.0))) return V_SNOW;
+            if (alt_voxel(s, px, py, zi, height_mix(zi, 80.0), n3)) return V_SNOW;
             return zi >= H ? V_DIRT : V_STONE;
         }
-        if (zi >= H) return alt_voxel(s, px, py, zi, 70.0) ? V_CLAY : V_GRASS;
-        if (zi + 1 >= H) return alt_voxel(s, px, py, zi, 70.0) ? V_CLAY : V_DIRT;
+        if (zi >= H) return alt_voxel(s, px, py, zi, 70.0, n3) ? V_CLAY : V_GRASS;
+        if (zi + 1 >= H) return alt_voxel(s, px, py, zi, 70.0, n3) ? V_CLAY : V_DIRT;
         return V_STONE;
     }
-    if (zi >= H) return alt_voxel(s, px, py, zi, 60.0) ? V_ICE : V_SNOW;
-    if (zi + 1 >= H) return alt_voxel(s, px, py, zi, 60.0) ? V_ICE : V_DIRT;
+    if (zi >= H) return alt_voxel(s, px, py, zi, 60.0, n3) ? V_ICE : V_SNOW;
+    if (zi + 1 >= H) return alt_voxel(s, px, py, zi, 60.0, n3) ? V_ICE : V_DIRT;
     return V_STONE;
 }
 
@@ -83,7 +84,8 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const uint4* __restric
                                                           uint8_t* __restrict__ pool_heights,
                                                           uint2* __restrict__ slot_xy,
                                                           uint32_t* __restrict__ cave_items,
-                                                          uint32_t* __restrict__ cave_count) {
+                                                          uint32_t* __restrict__ cave_count,
+                                                          unsigned long long* __restrict__ stats) {
     __shared__ GenSmem sm;
     const int tid = threadIdx.x;
     const uint4 job = jobs[blockIdx.x];
@@ -113,7 +115,9 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const uint4* __restric
     const bool cave_zone = f64_as_i32(normalise(fbm2<FBM_CAVE_CHECK>(s, px, py))) >= 80;
     // LakeGenerator::sample_lake_depth (lake_generator.rs:27-52)
     unsigned lake_depth = 0;
+    unsigned evals2 = 16, evals3 = 0;  // simplex evaluations of this column (work accounting)
     if (!cave_zone && H <= LAKE_MAX_TERRAIN && H > LAKE_TOP_ZI) {
+        evals2 += 2;
         const int d = (f64_as_i32(normalise(fbm2<FBM_LAKE>(s, px, py))) - 70) / 3;
         lake_depth = d < 2 ? 0u : (unsigned)d;
     }
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const uint4* __restric
         } else if (zi + 3 < H) {
             v = V_STONE;
         } else {
-            v = surface_voxel(s, biome, zi, H, px, py);
+            v = surface_voxel(s, biome, zi, H, px, py, evals3);
         }
         vox[tid + 256 * (AREA_HEIGHT - zi)] = v;
     }
@@ -144,6 +148,12 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const uint4* __restric
     if (tid == 0 && sm.cave_n) sm.cave_base = atomicAdd(cave_count, sm.cave_n);
     __syncthreads();
     if (cave_zone) cave_items[sm.cave_base + my_pos] = slot * COLUMNS_IN_AREA + tid;
+    evals2 = __reduce_add_sync(0xFFFFFFFFu, evals2);
+    evals3 = __reduce_add_sync(0xFFFFFFFFu, evals3);
+    if ((tid & 31) == 0) {
+        atomicAdd(&stats[0], (unsigned long long)evals2);
+        atomicAdd(&stats[1], (unsigned long long)evals3);
+    }
 
     uint4* dst = reinterpret_cast<uint4*>(pool_voxels + (size_t)slot * VOXELS_IN_AREA);
     for (int i = tid; i < VOXELS_IN_AREA / 16; i += 256) dst[i] = sm.vox[i];
@@ -162,7 +172,8 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const uint32_t* __restri
                                                         const uint32_t* __restrict__ cave_count,
                                                         uint8_t* __restrict__ pool_voxels,
                                                         const uint8_t* __restrict__ pool_heights,
-                                                        const uint2* __restrict__ slot_xy) {
+                                                        const uint2* __restrict__ slot_xy,
+                                                        unsigned long long* __restrict__ stats) {
     __shared__ CaveSmem sm;
     const int tid = threadIdx.x;
     {
@@ -203,6 +214,7 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const uint32_t* __restri
         if (tid == 0) sm.first[0] = 0;
         __syncthreads();
         const uint32_t total = sm.first[CAVE_BATCH];
+        if (tid == 0) atomicAdd(&stats[2], (unsigned long long)total);  // cave voxels evaluated
 
         for (uint32_t w = tid; w < total; w += 256) {
             // column c with first[c] <= w < first[c+1]
@@ -440,17 +452,17 @@ __global__ void __launch_bounds__(256) fp64_rate_kernel(double* sink, int iters)
 
 void launch_gen_columns(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
                         uint2* slot_xy, uint32_t* cave_items, uint32_t* cave_count,
-                        cudaStream_t stream) {
+                        unsigned long long* stats, cudaStream_t stream) {
     if (n <= 0) return;
     gen_columns_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_heights, slot_xy, cave_items,
-                                              cave_count);
+                                              cave_count, stats);
 }
 
 void launch_gen_caves(const uint32_t* cave_items, const uint32_t* cave_count, uint8_t* pool_voxels,
-                      const uint8_t* pool_heights, const uint2* slot_xy, int sm_count,
-                      cudaStream_t stream) {
+                      const uint8_t* pool_heights, const uint2* slot_xy, unsigned long long* stats,
+                      int sm_count, cudaStream_t stream) {
     gen_caves_kernel<<<sm_count * 4, 256, 0, stream>>>(cave_items, cave_count, pool_voxels,
-                                                       pool_heights, slot_xy);
+                                                       pool_heights, slot_xy, stats);
 }
 
 void launch_gen_finish(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,

@@ -17,10 +17,11 @@ cudaError_t upload_noise_tables(const NoiseTables& t, cudaStream_t stream);
 // jobs: n entries {area x, area y, slot, 0}
 void launch_gen_columns(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
                         uint2* slot_xy, uint32_t* cave_items, uint32_t* cave_count,
+                        unsigned long long* stats /* [3]: simplex2, alt simplex3, cave voxels */,
                         cudaStream_t stream);
 void launch_gen_caves(const uint32_t* cave_items, const uint32_t* cave_count,
                       uint8_t* pool_voxels, const uint8_t* pool_heights, const uint2* slot_xy,
-                      int sm_count, cudaStream_t stream);
+                      unsigned long long* stats, int sm_count, cudaStream_t stream);
 void launch_gen_finish(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
                        uint64_t seed, cudaStream_t stream);
 void launch_column_heights(const uint4* jobs, int n, const uint8_t* pool_voxels,
