@@ -25,7 +25,6 @@ namespace vx {
 namespace {
 
 constexpr int ROWS = VOXELS_IN_AREA / 16;  // 2048 rows of 16 voxels
-constexpr int LIST_CAP = 4096;             // face descriptors staged per round
 
 // ------------------------------------------------------------------------------------- planes
 // plane layout per slot: uint16 S[2048] followed by uint16 T[2048] (8 KiB)
@@ -246,64 +245,23 @@ __global__ void __launch_bounds__(1024) mesh_offsets_kernel(const uint32_t* __re
 //   Back(y-1):  (x-h,y-h,zt;s3) (x+h,y-h,zt;s2) (x+h,y-h,zb;s1) (x-h,y-h,zb;s0)
 //   Down(z+1):  (x-h,y-h,zb;b0) (x+h,y-h,zb;b1) (x+h,y+h,zb;b2) (x-h,y+h,zb;b3)
 //   Up(z-1):    (x+h,y-h,zt;t0) (x-h,y-h,zt;t1) (x-h,y+h,zt;t2) (x+h,y+h,zt;t3)
-#define CORNER(px, py, bottom, uv) ((px) | ((py) << 1) | ((bottom) << 2) | ((uv) << 3))
-__constant__ uint8_t c_corner[6][4] = {
-    {CORNER(1, 0, 1, 1), CORNER(1, 0, 0, 2), CORNER(1, 1, 0, 3), CORNER(1, 1, 1, 0)},
-    {CORNER(0, 0, 0, 3), CORNER(0, 0, 1, 0), CORNER(0, 1, 1, 1), CORNER(0, 1, 0, 2)},
-    {CORNER(0, 1, 1, 0), CORNER(1, 1, 1, 1), CORNER(1, 1, 0, 2), CORNER(0, 1, 0, 3)},
-    {CORNER(0, 0, 0, 3), CORNER(1, 0, 0, 2), CORNER(1, 0, 1, 1), CORNER(0, 0, 1, 0)},
-    {CORNER(0, 0, 1, 0), CORNER(1, 0, 1, 1), CORNER(1, 1, 1, 2), CORNER(0, 1, 1, 3)},
-    {CORNER(1, 0, 0, 0), CORNER(0, 0, 0, 1), CORNER(0, 1, 0, 2), CORNER(1, 1, 0, 3)},
-};
-// normals (mesh_generator.rs:45-50), xyz only, w = 0
-__constant__ float c_normal[6][3] = {{1.f, 0.f, 0.f},  {-1.f, 0.f, 0.f}, {0.f, 1.f, 0.f},
-                                     {0.f, -1.f, 0.f}, {0.f, 0.f, 1.f},  {0.f, 0.f, -1.f}};
+// The four 5-bit codes of a direction are packed into 20 bits; three directions per 64-bit word,
+// so the lookup is two shifts on immediates instead of a (lane-divergent) memory access.
+#define CORNER(px, py, bottom, uv) ((unsigned long long)((px) | ((py) << 1) | ((bottom) << 2) | ((uv) << 3)))
+#define CORNER4(a, b, c, d) ((a) | ((b) << 5) | ((c) << 10) | ((d) << 15))
+constexpr unsigned long long CORNERS_LRF =
+    CORNER4(CORNER(1, 0, 1, 1), CORNER(1, 0, 0, 2), CORNER(1, 1, 0, 3), CORNER(1, 1, 1, 0)) |
+    (CORNER4(CORNER(0, 0, 0, 3), CORNER(0, 0, 1, 0), CORNER(0, 1, 1, 1), CORNER(0, 1, 0, 2)) << 20) |
+    (CORNER4(CORNER(0, 1, 1, 0), CORNER(1, 1, 1, 1), CORNER(1, 1, 0, 2), CORNER(0, 1, 0, 3)) << 40);
+constexpr unsigned long long CORNERS_BDU =
+    CORNER4(CORNER(0, 0, 0, 3), CORNER(1, 0, 0, 2), CORNER(1, 0, 1, 1), CORNER(0, 0, 1, 0)) |
+    (CORNER4(CORNER(0, 0, 1, 0), CORNER(1, 0, 1, 1), CORNER(1, 1, 1, 2), CORNER(0, 1, 1, 3)) << 20) |
+    (CORNER4(CORNER(1, 0, 0, 0), CORNER(0, 0, 0, 1), CORNER(0, 1, 0, 2), CORNER(1, 1, 0, 3)) << 40);
 
 // TextureManager::VOXELS_WITH_DIFFERENT_FACES (texture_manager.rs:95-102)
 constexpr uint32_t DIFFERENT_FACES_BITS = (1u << V_GRASS) | (1u << V_TRAMPOLINE) | (1u << V_WOOD) |
                                           (1u << V_STONE_PILLAR) | (1u << V_BOMB) |
                                           (1u << V_ACTIVE_BOMB);
-
-// one 32-bit word (0..39) of a face's 4 x 40-byte vertex block
-__device__ __forceinline__ uint32_t face_word(int word, int dir, uint32_t voxel, float cx, float cy,
-                                              float cz) {
-    const int vtx = word / 10, field = word - vtx * 10;
-    const uint32_t code = c_corner[dir][vtx];
-    // get_partial_height_offset (mesh_generator.rs:490-498): k / 5 in f32
-    const float ho = partial_height(voxel) ? (float)(voxel - V_WATER1 + 1) / 5.0f : 0.0f;
-    float f;
-    switch (field) {
-    case 0: f = (code & 1u) ? cx + 0.5f : cx - 0.5f; break;
-    case 1: f = (code & 2u) ? cy + 0.5f : cy - 0.5f; break;
-    case 2: f = (code & 4u) ? cz + 0.5f : cz - 0.5f + ho; break;
-    case 3: {
-        const uint32_t c = (code >> 3) & 3u;
-        f = (c == 1u || c == 2u) ? 1.0f : 0.0f;  // every uv table is (0,_) (1,_) (1,_) (0,_)
-        break;
-    }
-    case 4: {
-        const uint32_t c = (code >> 3) & 3u;
-        const bool high = c < 2u;  // corners 0,1 carry the larger v
-        if ((DIFFERENT_FACES_BITS >> voxel) & 1u) {
-            // TOP_UV / SIDE_UV / BOTTOM_UV (mesh_generator.rs:82-99): 64 px tiles, 32 px gaps in a
-            // 256 px atlas -> 0.625/0.375, 1/0.75, 0.25/0
-            if (dir == 5) f = high ? 0.625f : 0.375f;
-            else if (dir == 4) f = high ? 0.25f : 0.0f;
-            else f = high ? 1.0f : 0.75f;
-        } else {
-            f = high ? 1.0f : 0.0f;  // UV_REPEATING (mesh_generator.rs:61-66)
-        }
-        if (dir < 4 && ho > 0.0f && f > 0.0f) f -= ho;  // mesh_generator.rs:214-220 (sides only)
-        break;
-    }
-    case 5: return 0xFFFFFFFFu;  // COLOR (mesh_generator.rs:43)
-    case 6: f = c_normal[dir][0]; break;
-    case 7: f = c_normal[dir][1]; break;
-    case 8: f = c_normal[dir][2]; break;
-    default: f = 0.0f; break;
-    }
-    return __float_as_uint(f);
-}
 
 // face descriptor: row (11) | x (4) << 11 | dir (3) << 15 | ordinal in voxel (3) << 18 | voxel << 21
 __device__ __forceinline__ uint32_t make_desc(int r, int x, int dir, int ord, uint32_t voxel) {
@@ -311,19 +269,106 @@ __device__ __forceinline__ uint32_t make_desc(int r, int x, int dir, int ord, ui
            (voxel << 21);
 }
 
+constexpr int LIST_FACES = 3072;   // face descriptors buffered per flush
+constexpr int STAGE_FACES = 128;   // faces assembled in shared memory per sub-round (2 threads each)
+constexpr int STAGE_STRIDE = 11;   // uint4 per staged face: 160 B payload + 16 B pad (bank spread)
+
+struct EmitSmem {
+    uint32_t list[LIST_FACES];
+    uint4 stage[STAGE_FACES * STAGE_STRIDE];
+    uint32_t warp[8];
+    uint32_t total;
+};
+
+// Two vertices (2*half, 2*half + 1) of one face = 20 words = 5 uint4 written to the staging tile.
+// MeshGenerator::get_verticies_for_voxel (mesh_generator.rs:200-488); all f32 operations are the
+// reference's: offset -/+ 0.5, "offset_z - 0.5 + height_offset", "side_uv.y -= height_offset".
+__device__ __forceinline__ void build_half_face(uint4* dst, uint32_t desc, int half, uint32_t gx0,
+                                                uint32_t gy0) {
+    const int rr = desc & 2047, x = (desc >> 11) & 15, dir = (desc >> 15) & 7;
+    const uint32_t voxel = desc >> 21;
+    // location.rs:19-27: (internal - 1_000_000) as f32; mesh_generator.rs:120-123
+    const float cx = (float)((int)(gx0 + x) - LOCATION_OFFSET);
+    const float cy = (float)((int)(gy0 + (rr & 15)) - LOCATION_OFFSET);
+    const float cz = (float)(rr >> 4);
+    // get_partial_height_offset (mesh_generator.rs:490-498): k / 5 in f32
+    const float ho = partial_height(voxel) ? (float)(voxel - V_WATER1 + 1) / 5.0f : 0.0f;
+    const float xm = cx - 0.5f, xp = cx + 0.5f, ym = cy - 0.5f, yp = cy + 0.5f;
+    const float zt = cz - 0.5f + ho, zb = cz + 0.5f;
+    // v coordinate of uv corners {0,1} (high) and {2,3} (low): UV_REPEATING 1/0; TOP_UV 0.625/0.375,
+    // SIDE_UV 1/0.75, BOTTOM_UV 0.25/0 for voxels with different faces (mesh_generator.rs:61-99)
+    float vhi = 1.0f, vlo = 0.0f;
+    if ((DIFFERENT_FACES_BITS >> voxel) & 1u) {
+        vhi = dir == 5 ? 0.625f : (dir == 4 ? 0.25f : 1.0f);
+        vlo = dir == 5 ? 0.375f : (dir == 4 ? 0.0f : 0.75f);
+    }
+    if (dir < 4 && ho > 0.0f) {  // mesh_generator.rs:214-220, side faces only
+        if (vhi > 0.0f) vhi -= ho;
+        if (vlo > 0.0f) vlo -= ho;
+    }
+    // normals (mesh_generator.rs:45-50)
+    const float nx = dir == 0 ? 1.0f : (dir == 1 ? -1.0f : 0.0f);
+    const float ny = dir == 2 ? 1.0f : (dir == 3 ? -1.0f : 0.0f);
+    const float nz = dir == 4 ? 1.0f : (dir == 5 ? -1.0f : 0.0f);
+    const unsigned long long packed = dir < 3 ? CORNERS_LRF : CORNERS_BDU;
+    const uint32_t codes = (uint32_t)(packed >> (20 * (dir < 3 ? dir : dir - 3))) >> (10 * half);
+    const uint32_t c0 = codes & 31u, c1 = (codes >> 5) & 31u;
+    const uint32_t uv0 = c0 >> 3, uv1 = c1 >> 3;
+    const uint32_t COLOR = 0xFFFFFFFFu;  // mesh_generator.rs:43
+    const uint32_t fnx = __float_as_uint(nx), fny = __float_as_uint(ny), fnz = __float_as_uint(nz);
+    dst[0] = make_uint4(__float_as_uint((c0 & 1u) ? xp : xm), __float_as_uint((c0 & 2u) ? yp : ym),
+                        __float_as_uint((c0 & 4u) ? zb : zt),
+                        __float_as_uint((uv0 == 1u || uv0 == 2u) ? 1.0f : 0.0f));
+    dst[1] = make_uint4(__float_as_uint(uv0 < 2u ? vhi : vlo), COLOR, fnx, fny);
+    dst[2] = make_uint4(fnz, 0u, __float_as_uint((c1 & 1u) ? xp : xm),
+                        __float_as_uint((c1 & 2u) ? yp : ym));
+    dst[3] = make_uint4(__float_as_uint((c1 & 4u) ? zb : zt),
+                        __float_as_uint((uv1 == 1u || uv1 == 2u) ? 1.0f : 0.0f),
+                        __float_as_uint(uv1 < 2u ? vhi : vlo), COLOR);
+    dst[4] = make_uint4(fnx, fny, fnz, 0u);
+}
+
+// write `count` buffered faces (descriptors sm.list[0..count)) starting at stream face `first`
+__device__ __forceinline__ void flush_faces(EmitSmem& sm, uint32_t count, uint32_t first,
+                                            const MeshOut& out, uint32_t gx0, uint32_t gy0, int tid) {
+    // vertices: assembled in the staging tile, then stored as consecutive 16-byte pieces
+    for (uint32_t base = 0; base < count; base += STAGE_FACES) {
+        const uint32_t nfaces = min((uint32_t)STAGE_FACES, count - base);
+        const uint32_t f = tid >> 1;
+        if (f < nfaces)
+            build_half_face(&sm.stage[f * STAGE_STRIDE + (tid & 1) * 5], sm.list[base + f], tid & 1,
+                            gx0, gy0);
+        __syncthreads();
+        uint4* vdst = out.vertices + (size_t)(first + base) * 10;
+        for (uint32_t w = tid; w < nfaces * 10; w += 256) {
+            const uint32_t fi = w / 10, piece = w - fi * 10;
+            vdst[w] = sm.stage[fi * STAGE_STRIDE + piece];
+        }
+        __syncthreads();
+    }
+    // indices: [0,1,2,0,2,3] + 4*ord as three u32 words per face (mesh_generator.rs:44,131-139)
+    uint32_t* idst = out.indices + (size_t)first * 3;
+    for (uint32_t w = tid; w < count * 3; w += 256) {
+        const uint32_t fi = w / 3, part = w - fi * 3;
+        const uint32_t b = ((sm.list[fi] >> 18) & 7u) * 4u;
+        const uint32_t lo16 = part == 0 ? b : b + 2u;
+        const uint32_t hi16 = part == 0 ? b + 1u : (part == 1 ? b : b + 3u);
+        idst[w] = lo16 | (hi16 << 16);
+    }
+}
+
 __global__ void __launch_bounds__(256) mesh_emit_kernel(const uint4* __restrict__ jobs,
                                                         const uint8_t* __restrict__ pool_voxels,
                                                         const uint16_t* __restrict__ pool_planes,
                                                         AreaMap map, MeshOut out) {
-    __shared__ uint32_t s_list[LIST_CAP];
-    __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_total;
+    __shared__ EmitSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint4 job = jobs[blockIdx.x];
     const AreaView a = make_view(job, map, pool_voxels, pool_planes);
     const uint32_t gx0 = job.x * AREA_SIZE, gy0 = job.y * AREA_SIZE;
-    uint32_t face_base = out.face_first[blockIdx.x];  // running, in faces
+    uint32_t face_done = out.face_first[blockIdx.x];  // stream index of list[0]
     uint32_t rec_base = out.rec_first[blockIdx.x];
+    uint32_t fill = 0;  // faces buffered in sm.list
 
     for (int chunk = 0; chunk < ROWS / 256; ++chunk) {
         const int r = chunk * 256 + tid;  // rows in (z, y) order == the reference's z,y loop
@@ -334,84 +379,74 @@ __global__ void __launch_bounds__(256) mesh_emit_kernel(const uint4* __restrict_
         // CTA exclusive scan of (faces | recs << 16)
         const uint32_t packed = nf | ((uint32_t)__popc(vis) << 16);
         const uint32_t inc = warp_inclusive_scan(packed, lane);
-        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();  // previous chunk's readers of sm.warp / sm.total are done
+        if (lane == 31) sm.warp[wid] = inc;
         __syncthreads();
         if (tid == 0) {
             uint32_t run = 0;
             for (int i = 0; i < 8; ++i) {
-                const uint32_t v = s_warp[i];
-                s_warp[i] = run;
+                const uint32_t v = sm.warp[i];
+                sm.warp[i] = run;
                 run += v;
             }
-            s_total = run;
+            sm.total = run;
         }
         __syncthreads();
-        const uint32_t excl = s_warp[wid] + inc - packed;
+        const uint32_t excl = sm.warp[wid] + inc - packed;
         const uint32_t my_face = excl & 0xFFFFu, my_rec = excl >> 16;
-        const uint32_t total_faces = s_total & 0xFFFFu, total_recs = s_total >> 16;
+        const uint32_t total_faces = sm.total & 0xFFFFu, total_recs = sm.total >> 16;
+        if (total_faces == 0) continue;  // uniform across the CTA
 
-        for (uint32_t lo = 0; lo < total_faces; lo += LIST_CAP) {
-            // scatter this thread's faces that fall into [lo, lo + LIST_CAP) into the list
-            if (vis && my_face < lo + LIST_CAP && my_face + nf > lo) {
-                uint32_t f = my_face, q = my_rec, rest = vis;
+        // records: one per visible voxel, z,y,x order; first_face = stream index of its first face
+        // (face_done + fill is the stream index of this chunk's face 0, invariant under flushes)
+        if (vis) {
+            uint32_t f = face_done + fill + my_face, q = rec_base + my_rec, rest = vis;
+            const uint32_t z = (uint32_t)r >> 4, y = (uint32_t)r & 15u;
+            while (rest) {
+                const int x = __ffs(rest) - 1;
+                rest &= rest - 1;
+                uint32_t m6 = 0;
+#pragma unroll
+                for (int d = 0; d < 6; ++d) m6 |= ((k.m[d] >> x) & 1u) << d;
+                const uint32_t cnt = __popc(m6);
+                out.recs[q++] = make_uint4(gx0 + x, gy0 + y,
+                                           z | ((uint32_t)a.vox[x + 16 * r] << 8) | (m6 << 16) | (cnt << 24), f);
+                f += cnt;
+            }
+        }
+        // face descriptors -> list. A chunk may exceed the list (worst case 24 576 faces): feed it
+        // through in windows [lo, hi) of chunk-local face indices.
+        for (uint32_t lo = 0; lo < total_faces;) {
+            if (fill == LIST_FACES || (lo == 0 && fill + total_faces > LIST_FACES && fill > 0)) {
+                __syncthreads();
+                flush_faces(sm, fill, face_done, out, gx0, gy0, tid);
+                __syncthreads();
+                face_done += fill;
+                fill = 0;
+            }
+            const uint32_t hi = min(total_faces, lo + (LIST_FACES - fill));
+            if (vis && my_face < hi && my_face + nf > lo) {
+                uint32_t f = my_face, rest = vis;
                 while (rest) {
                     const int x = __ffs(rest) - 1;
                     rest &= rest - 1;
                     const uint32_t voxel = a.vox[x + 16 * r];
-                    uint32_t m6 = 0;
 #pragma unroll
-                    for (int d = 0; d < 6; ++d) m6 |= ((k.m[d] >> x) & 1u) << d;
-                    if (lo == 0) {  // the record is written once, in the first round
-                        const uint32_t z = (uint32_t)r >> 4, y = (uint32_t)r & 15u;
-                        out.recs[rec_base + q] =
-                            make_uint4(gx0 + x, gy0 + y,
-                                       z | (voxel << 8) | (m6 << 16) | ((uint32_t)__popc(m6) << 24),
-                                       face_base + f);
-                    }
-                    ++q;
-                    int ord = 0;
-                    while (m6) {
-                        const int d = __ffs(m6) - 1;
-                        m6 &= m6 - 1;
-                        if (f >= lo && f < lo + LIST_CAP) s_list[f - lo] = make_desc(r, x, d, ord, voxel);
-                        ++f;
-                        ++ord;
-                    }
+                    for (int d = 0, ord = 0; d < 6; ++d)
+                        if ((k.m[d] >> x) & 1u) {
+                            if (f >= lo && f < hi) sm.list[fill + (f - lo)] = make_desc(r, x, d, ord, voxel);
+                            ++f;
+                            ++ord;
+                        }
                 }
             }
-            __syncthreads();
-            const uint32_t cnt = min((uint32_t)LIST_CAP, total_faces - lo);
-            // vertices: 10 x 16 bytes per face, consecutive threads -> consecutive 16-byte pieces
-            uint4* vdst = out.vertices + (size_t)(face_base + lo) * 10;
-            for (uint32_t w = tid; w < cnt * 10; w += 256) {
-                const uint32_t fi = w / 10, piece = w - fi * 10;
-                const uint32_t d = s_list[fi];
-                const int rr = d & 2047, x = (d >> 11) & 15, dir = (d >> 15) & 7;
-                const uint32_t voxel = d >> 21;
-                // location.rs:19-27: (internal - 1_000_000) as f32; mesh_generator.rs:120-123
-                const float cx = (float)((int)(gx0 + x) - LOCATION_OFFSET);
-                const float cy = (float)((int)(gy0 + (rr & 15)) - LOCATION_OFFSET);
-                const float cz = (float)(rr >> 4);
-                const int w0 = piece * 4;
-                vdst[w] = make_uint4(face_word(w0, dir, voxel, cx, cy, cz),
-                                     face_word(w0 + 1, dir, voxel, cx, cy, cz),
-                                     face_word(w0 + 2, dir, voxel, cx, cy, cz),
-                                     face_word(w0 + 3, dir, voxel, cx, cy, cz));
-            }
-            // indices: [0,1,2,0,2,3] + 4*ord as three u32 words per face
-            uint32_t* idst = out.indices + (size_t)(face_base + lo) * 3;
-            for (uint32_t w = tid; w < cnt * 3; w += 256) {
-                const uint32_t fi = w / 3, part = w - fi * 3;
-                const uint32_t b = ((s_list[fi] >> 18) & 7u) * 4u;
-                const uint32_t lo16 = part == 0 ? b : b + 2u;
-                const uint32_t hi16 = part == 0 ? b + 1u : (part == 1 ? b : b + 3u);
-                idst[w] = lo16 | (hi16 << 16);
-            }
-            __syncthreads();
+            fill += hi - lo;
+            lo = hi;
         }
-        face_base += total_faces;
         rec_base += total_recs;
     }
+    __syncthreads();
+    flush_faces(sm, fill, face_done, out, gx0, gy0, tid);
 }
 
 }  // namespace
