@@ -53,3 +53,76 @@ def test_mesh_stream_byte_exact(ctx, seed):
         assert np.array_equal(idx[6 * base:6 * (base + nf)], oidx)
         base += nf
     assert info["n_faces"] == base
+
+
+def _compare_mesh(ctx, world, xy):
+    info = ctx.mesh(xy)
+    rec_first, face_first, recs, verts, idx = ctx.mesh_read(info)
+    base = 0
+    for i, (ax, ay) in enumerate(xy):
+        nf = world.mesh_area(int(ax), int(ay))
+        orecs, overts, oidx = world.emit_area(int(ax), int(ay), first_face_base=base)
+        assert face_first[i] == base and face_first[i + 1] == base + nf, f"face count differs in area {ax},{ay}"
+        assert recs[rec_first[i]:rec_first[i + 1]].tobytes() == orecs.tobytes(), f"records differ in area {ax},{ay}"
+        assert verts[4 * base:4 * (base + nf)].tobytes() == overts.tobytes(), f"vertices differ in area {ax},{ay}"
+        assert np.array_equal(idx[6 * base:6 * (base + nf)], oidx)
+        base += nf
+    assert info["n_faces"] == base
+    return base
+
+
+@pytest.mark.parametrize("p_none", [0.5, 0.9, 0.1])
+def test_mesh_random_voxels_all_types(seed, p_none):
+    """Uploaded (disk-loaded) areas with every one of the 27 voxel types, including glass, ice, all
+    six water kinds next to each other: exercises the cur != nbr rule for transparent voxels, the
+    partial-height top-face rule and the enclosed-voxel pre-filter (area.rs:126-201)."""
+    rng = np.random.default_rng(int(p_none * 100))
+    n = 5
+    ax0, ay0 = 1000, 2000
+    vox = rng.integers(1, 27, size=(n * n, 32768), dtype=np.uint8)
+    vox[rng.random(vox.shape) < p_none] = 0
+    # a solid block of partial-height water so that interior enclosed Water1..4 voxels exist
+    blk = vox[12].reshape(128, 16, 16)
+    blk[40:60, 3:13, 3:13] = oracle.V["Water2"]
+    blk[45:50, 5:9, 5:9] = oracle.V["Water3"]
+    xy_all = vg.region_xy(ax0, ay0, n, n)
+    with vg.Context(0, seed=seed) as c:
+        mh = c.upload(xy_all, vox)
+        omh = np.stack([oracle.update_all_column_heights(v) for v in vox])
+        assert np.array_equal(mh, omh)
+        world = oracle.World(ax0, ay0, n, n, vox, omh)
+        faces = _compare_mesh(c, world, vg.region_xy(ax0 + 1, ay0 + 1, n - 2, n - 2))
+        assert faces > 0
+
+
+def test_mesh_checkerboard_maximum_faces(seed):
+    """Worst case: a 3-D checkerboard has 6 faces on every second voxel (98 304 faces per area),
+    far beyond the shared-memory face list, so the windowed flush path is exercised."""
+    n = 3
+    ax0, ay0 = 500, 500
+    z, y, x = np.meshgrid(np.arange(128), np.arange(16), np.arange(16), indexing="ij")
+    board = (((x + y + z) & 1) * oracle.V["Brick"]).astype(np.uint8).ravel()
+    vox = np.zeros((n * n, 32768), np.uint8)
+    vox[4] = board
+    vox[5] = board  # a second one next to it: faces across the area border
+    xy_all = vg.region_xy(ax0, ay0, n, n)
+    with vg.Context(0, seed=seed) as c:
+        c.upload(xy_all, vox, read_heights=False)
+        omh = np.stack([oracle.update_all_column_heights(v) for v in vox])
+        world = oracle.World(ax0, ay0, n, n, vox, omh)
+        faces = _compare_mesh(c, world, vg.region_xy(ax0 + 1, ay0 + 1, 1, 1))
+        assert faces == 16384 * 6 - 256  # 6 faces per solid voxel, minus Down at z=127 (128) and Up at z=0 (128)
+
+
+def test_work_counters_match_oracle(ctx, seed):
+    """The library's work accounting (roofline numerators) equals the oracle's evaluation counts."""
+    xy = vg.region_xy(SPAWN - 16, SPAWN - 16, 32, 32)
+    ctx.set_timing(True)
+    ctx.generate(xy, read=False)
+    t = ctx.timings()
+    ctx.set_timing(False)
+    _, _, stats, _ = oracle.generate_areas(seed, xy)
+    assert t["simplex2_evals"] == stats["simplex2_evals"]
+    assert t["cave_voxels"] == stats["cave_voxels"]
+    assert t["cave_columns"] == stats["cave_columns"]
+    assert t["simplex3_evals"] == stats["simplex3_evals"]

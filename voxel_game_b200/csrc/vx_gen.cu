@@ -38,37 +38,47 @@ constexpr unsigned SNOW_MOUNTAIN_ZI = 70; // voxel_type_generator.rs:18
 
 __device__ __forceinline__ double normalise(double v) { return (v + 1.0) * 50.0; }  // algorithms.rs:59
 
-// should_generate_alternative_voxel (voxel_type_generator.rs:176-188)
-__device__ __forceinline__ bool alt_voxel(const NoiseShared* s, double px, double py, unsigned zi,
-                                          double threshold, unsigned& evals3) {
-    evals3 += 2;  // work accounting (roofline numerator): one 2-octave 3-D fBm
-    return normalise(fbm3<FBM_ALT>(s, px, py, (double)zi)) >= threshold;
-}
 // calculate_height_mix (voxel_type_generator.rs:190-192)
 __device__ __forceinline__ double height_mix(unsigned zi, double threshold) {
     return (1.0 - (double)zi / 128.0) * threshold;
 }
 
-// voxel type of one of the topmost voxels of a column (zi + 3 >= H); everything deeper is Stone
-// in all three biomes (voxel_type_generator.rs:64-174).
-__device__ uint8_t surface_voxel(const NoiseShared* s, int biome, unsigned zi, unsigned H, double px,
-                                 double py, unsigned& n3) {
-    if (biome == DRY) {
-        // zi + SAND_HEIGHT >= H holds for every caller
-        return alt_voxel(s, px, py, zi, height_mix(zi, 120.0), n3) ? V_STONE : V_SAND;
+// Voxel type of one of the four topmost voxels of a column (zi + 3 >= H); everything deeper is
+// Stone in all three biomes (voxel_type_generator.rs:64-174).  Split in two so that the expensive
+// part -- the 2-octave 3-D noise of should_generate_alternative_voxel -- sits at ONE call site
+// that the lanes of a warp reach together:
+//   surface_query : does this (biome, zi, H) consult the noise, and against which threshold?
+//   surface_pick  : the voxel, given the noise verdict.
+__device__ __forceinline__ bool surface_query(int biome, unsigned zi, unsigned H, double& threshold) {
+    if (biome == DRY) {  // zi + SAND_HEIGHT >= H holds for every caller
+        threshold = height_mix(zi, 120.0);
+        return true;
     }
     if (biome == WET) {
         if (zi >= SNOW_MOUNTAIN_ZI) {
+            threshold = height_mix(zi, 80.0);
+            return zi + 2 >= H;
+        }
+        threshold = 70.0;
+        return zi + 1 >= H;
+    }
+    threshold = 60.0;
+    return zi + 1 >= H;
+}
+__device__ __forceinline__ uint8_t surface_pick(int biome, unsigned zi, unsigned H, bool alt) {
+    if (biome == DRY) return alt ? V_STONE : V_SAND;
+    if (biome == WET) {
+        if (zi >= SNOW_MOUNTAIN_ZI) {
             if (zi + 2 < H) return V_STONE;
-            if (alt_voxel(s, px, py, zi, height_mix(zi, 80.0), n3)) return V_SNOW;
+            if (alt) return V_SNOW;
             return zi >= H ? V_DIRT : V_STONE;
         }
-        if (zi >= H) return alt_voxel(s, px, py, zi, 70.0, n3) ? V_CLAY : V_GRASS;
-        if (zi + 1 >= H) return alt_voxel(s, px, py, zi, 70.0, n3) ? V_CLAY : V_DIRT;
+        if (zi >= H) return alt ? V_CLAY : V_GRASS;
+        if (zi + 1 >= H) return alt ? V_CLAY : V_DIRT;
         return V_STONE;
     }
-    if (zi >= H) return alt_voxel(s, px, py, zi, 60.0, n3) ? V_ICE : V_SNOW;
-    if (zi + 1 >= H) return alt_voxel(s, px, py, zi, 60.0, n3) ? V_ICE : V_DIRT;
+    if (zi >= H) return alt ? V_ICE : V_SNOW;
+    if (zi + 1 >= H) return alt ? V_ICE : V_DIRT;
     return V_STONE;
 }
 
@@ -125,6 +135,24 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const uint4* __restric
     const int b = f64_as_i32(normalise(fbm2<FBM_BIOME>(s, px, py)));
     const int biome = (b >= 0 && b < 20) ? DRY : ((b >= 20 && b < 80) ? WET : COLD);
 
+    // The four topmost voxels first, in a loop all lanes walk together (k-th voxel from H - 3).
+    // A lake column never consults the noise where the lake overrides the voxel
+    // (lake_generator.rs:54-74 replaces the value; the reference computes it and throws it away).
+    unsigned tops = 0;  // voxel of zi = H - 3 + k in byte k
+#pragma unroll 1
+    for (unsigned k = 0; k < 4; ++k) {
+        const unsigned zi = H - 3 + k;
+        double threshold;
+        bool need = surface_query(biome, zi, H, threshold);
+        if (lake_depth != 0 && zi >= LAKE_TOP_ZI - lake_depth) need = false;
+        bool alt = false;
+        if (need) {  // should_generate_alternative_voxel (voxel_type_generator.rs:176-188)
+            evals3 += 2;
+            alt = normalise(fbm3<FBM_ALT>(s, px, py, (double)zi)) >= threshold;
+        }
+        tops |= (unsigned)surface_pick(biome, zi, H, alt) << (8 * k);
+    }
+
     // generate_column (generator.rs:70-98) without the cave test; bottom -> top
     for (unsigned zi = 1; zi <= H; ++zi) {
         uint8_t v;
@@ -135,7 +163,7 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const uint4* __restric
         } else if (zi + 3 < H) {
             v = V_STONE;
         } else {
-            v = surface_voxel(s, biome, zi, H, px, py, evals3);
+            v = (uint8_t)(tops >> (8 * (zi + 3 - H)));
         }
         vox[tid + 256 * (AREA_HEIGHT - zi)] = v;
     }
@@ -164,6 +192,7 @@ constexpr int CAVE_BATCH = 64;  // cave columns per CTA iteration
 
 struct CaveSmem {
     uint8_t perm[TAB_COUNT][256];
+    uint8_t perm12[TAB_COUNT][256];
     uint32_t item[CAVE_BATCH];
     uint32_t first[CAVE_BATCH + 1];  // exclusive prefix of per-column voxel counts
 };
@@ -180,12 +209,16 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const uint32_t* __restri
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_noise.t.perm[0][0]);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.perm[0][0]);
         for (int i = tid; i < TAB_COUNT * 256 / 4; i += 256) dst[i] = src[i];
+        for (int i = tid; i < TAB_COUNT * 256; i += 256)
+            (&sm.perm12[0][0])[i] = (uint8_t)((&c_noise.t.perm[0][0])[i] % 12u);
     }
     const uint32_t n_items = *cave_count;
     const FbmParams& q1 = c_noise.t.fbm[FBM_CAVE1];
     const FbmParams& q2 = c_noise.t.fbm[FBM_CAVE2];
     const uint8_t* p1 = sm.perm[q1.table];
     const uint8_t* p2 = sm.perm[q2.table];
+    const uint8_t* p1g = sm.perm12[q1.table];
+    const uint8_t* p2g = sm.perm12[q2.table];
 
     for (uint32_t batch = blockIdx.x; batch * CAVE_BATCH < n_items; batch += gridDim.x) {
         __syncthreads();  // previous iteration done with sm.item / sm.first (and perm loaded)
@@ -235,14 +268,14 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const uint32_t* __restri
             double xa = px * q1.frequency, ya = py * q1.frequency, za = pz * q1.frequency, a = 0.0;
 #pragma unroll 1
             for (int o = 0; o < 6; ++o) {
-                a += q1.amp[o] * simplex3(p1, xa, ya, za);
+                a += q1.amp[o] * simplex3(p1, p1g, xa, ya, za);
                 xa *= q1.lacunarity; ya *= q1.lacunarity; za *= q1.lacunarity;
             }
             a *= q1.norm;
             double xb = px * q2.frequency, yb = py * q2.frequency, zb = pz * q2.frequency, bsum = 0.0;
 #pragma unroll 1
             for (int o = 0; o < 8; ++o) {
-                bsum += q2.amp[o] * simplex3(p2, xb, yb, zb);
+                bsum += q2.amp[o] * simplex3(p2, p2g, xb, yb, zb);
                 xb *= q2.lacunarity; yb *= q2.lacunarity; zb *= q2.lacunarity;
             }
             bsum *= q2.norm;

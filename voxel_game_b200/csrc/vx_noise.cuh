@@ -11,7 +11,9 @@
 //     modulo 256, which equals indexing the crate's doubled 512-entry table;
 //   * the 3-D gradient dot product g.x (components 0/+-1) is one signed add instead of
 //     3 multiplies + 2 adds (x*1 = x, x*0 = +-0, y + +-0 = y);
-//   * Fbm amplitudes amp_k are precomputed on the host with the same running product.
+//   * Fbm amplitudes amp_k are precomputed on the host with the same running product;
+//   * the last permutation lookup only feeds "% 12" / "% 24", so it reads pre-reduced copies of
+//     the table; "t <= 0 ? 0 : t^4 * g.x" is evaluated as max(t,0)^4 * g.x (same value).
 #pragma once
 #include <cstdint>
 
@@ -42,6 +44,8 @@ __constant__ double c_grad2[24][2] = {
 // shared-memory working copy of the tables (random access; constant cache would serialise)
 struct NoiseShared {
     uint8_t perm[TAB_COUNT][256];
+    uint8_t perm24[TAB_COUNT][256];  // perm % 24: the last hash level only selects a 2-D gradient
+    uint8_t perm12[TAB_COUNT][256];  // perm % 12: ... or a 3-D gradient
     double grad2[24][2];
 };
 
@@ -49,6 +53,11 @@ __device__ __forceinline__ void load_noise_shared(NoiseShared* s, int tid, int n
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_noise.t.perm[0][0]);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&s->perm[0][0]);
     for (int i = tid; i < TAB_COUNT * 256 / 4; i += nthreads) dst[i] = src[i];
+    for (int i = tid; i < TAB_COUNT * 256; i += nthreads) {
+        const unsigned v = (&c_noise.t.perm[0][0])[i];
+        (&s->perm24[0][0])[i] = (uint8_t)(v % 24u);
+        (&s->perm12[0][0])[i] = (uint8_t)(v % 12u);
+    }
     for (int i = tid; i < 48; i += nthreads) (&s->grad2[0][0])[i] = (&c_grad2[0][0])[i];
 }
 
@@ -66,17 +75,19 @@ __device__ __forceinline__ double floor_split(double x, int& i) {
     return r;
 }
 
-__device__ __forceinline__ double corner2(const NoiseShared* s, double x, double y, unsigned h) {
-    const double t = 0.5 - x * x - y * y;
-    const unsigned gi = h % 24u;
+// contribution of one simplex corner; gi = gradient index.  "t <= 0 -> 0" is applied as
+// max(t, 0) before the powers: identical values (0 * d = +-0, and a zero of either sign adds
+// nothing to the sum), one DMNMX instead of a compare and two selects.
+__device__ __forceinline__ double corner2(const NoiseShared* s, double x, double y, unsigned gi) {
+    const double t = fmax(0.5 - x * x - y * y, 0.0);
     const double2 g = *reinterpret_cast<const double2*>(&s->grad2[gi][0]);
     const double d = g.x * x + g.y * y;
     const double t2 = t * t;
-    const double v = t2 * t2 * d;
-    return t > 0.0 ? v : 0.0;
+    return t2 * t2 * d;
 }
 
-__device__ __forceinline__ double simplex2(const NoiseShared* s, const uint8_t* p, double x, double y) {
+__device__ __forceinline__ double simplex2(const NoiseShared* s, const uint8_t* p,
+                                           const uint8_t* p24, double x, double y) {
     const double SKEW = 0.366025403784439, UNSKEW = 0.211324865405187;
     const double sk = (x + y) * SKEW;
     int i, j;
@@ -87,9 +98,9 @@ __device__ __forceinline__ double simplex2(const NoiseShared* s, const uint8_t* 
     const double x1 = x0 - (lower ? 1.0 : 0.0) + UNSKEW, y1 = y0 - (lower ? 0.0 : 1.0) + UNSKEW;
     const double x2 = x0 - 1.0 + 2.0 * UNSKEW, y2 = y0 - 1.0 + 2.0 * UNSKEW;
     const unsigned pi0 = p[i & 255], pi1 = p[(i + 1) & 255];
-    const unsigned h0 = p[(pi0 + j) & 255];
-    const unsigned h1 = lower ? p[(pi1 + j) & 255] : p[(pi0 + j + 1) & 255];
-    const unsigned h2 = p[(pi1 + j + 1) & 255];
+    const unsigned h0 = p24[(pi0 + j) & 255];
+    const unsigned h1 = lower ? p24[(pi1 + j) & 255] : p24[(pi0 + j + 1) & 255];
+    const unsigned h2 = p24[(pi1 + j + 1) & 255];
     const double n0 = corner2(s, x0, y0, h0);
     const double n1 = corner2(s, x1, y1, h1);
     const double n2 = corner2(s, x2, y2, h2);
@@ -99,21 +110,21 @@ __device__ __forceinline__ double simplex2(const NoiseShared* s, const uint8_t* 
 // gradient h % 12 of the edge-midpoint set
 //   0..3: (+-1,+-1,0)   4..7: (+-1,0,+-1)   8..11: (0,+-1,+-1); bit0 negates the first non-zero
 //   component, bit1 the second
-__device__ __forceinline__ double corner3(double x, double y, double z, unsigned h) {
-    const double t = 0.5 - x * x - y * y - z * z;
-    const unsigned gi = h % 12u;
+__device__ __forceinline__ double flip_sign(double v, unsigned sign_bit31) {
+    return __hiloint2double(__double2hiint(v) ^ (int)sign_bit31, __double2loint(v));
+}
+__device__ __forceinline__ double corner3(double x, double y, double z, unsigned gi) {
+    const double t = fmax(0.5 - x * x - y * y - z * z, 0.0);
     const unsigned grp = gi >> 2;
-    double a = grp == 2u ? y : x;
-    double b = grp == 0u ? y : z;
-    a = (gi & 1u) ? -a : a;
-    b = (gi & 2u) ? -b : b;
+    const double a = flip_sign(grp == 2u ? y : x, gi << 31);
+    const double b = flip_sign(grp == 0u ? y : z, (gi << 30) & 0x80000000u);
     const double d = a + b;
     const double t2 = t * t;
-    const double v = t2 * t2 * d;
-    return t > 0.0 ? v : 0.0;
+    return t2 * t2 * d;
 }
 
-__device__ __forceinline__ double simplex3(const uint8_t* p, double x, double y, double z) {
+__device__ __forceinline__ double simplex3(const uint8_t* p, const uint8_t* p12, double x, double y,
+                                           double z) {
     const double SKEW = 1.0 / 3.0, UNSKEW = 1.0 / 6.0;
     const double sk = (x + y + z) * SKEW;
     int i, j, k;
@@ -134,10 +145,10 @@ __device__ __forceinline__ double simplex3(const uint8_t* p, double x, double y,
     const double x3 = x0 - 1.0 + 3.0 * UNSKEW, y3 = y0 - 1.0 + 3.0 * UNSKEW,
                  z3 = z0 - 1.0 + 3.0 * UNSKEW;
     const unsigned pi0 = p[i & 255], pi1 = p[(i + 1) & 255];
-    const unsigned h0 = p[(p[(pi0 + j) & 255] + k) & 255];
-    const unsigned h1 = p[(p[((i1 ? pi1 : pi0) + j + (int)j1) & 255] + k + (int)k1) & 255];
-    const unsigned h2 = p[(p[((i2 ? pi1 : pi0) + j + (int)j2) & 255] + k + (int)k2) & 255];
-    const unsigned h3 = p[(p[(pi1 + j + 1) & 255] + k + 1) & 255];
+    const unsigned h0 = p12[(p[(pi0 + j) & 255] + k) & 255];
+    const unsigned h1 = p12[(p[((i1 ? pi1 : pi0) + j + (int)j1) & 255] + k + (int)k1) & 255];
+    const unsigned h2 = p12[(p[((i2 ? pi1 : pi0) + j + (int)j2) & 255] + k + (int)k2) & 255];
+    const unsigned h3 = p12[(p[(pi1 + j + 1) & 255] + k + 1) & 255];
     const double n0 = corner3(x0, y0, z0, h0);
     const double n1 = corner3(x1, y1, z1, h1);
     const double n2 = corner3(x2, y2, z2, h2);
@@ -149,12 +160,13 @@ template <int ID>
 __device__ __forceinline__ double fbm2(const NoiseShared* s, double x, double y) {
     const FbmParams& q = c_noise.t.fbm[ID];
     const uint8_t* p = s->perm[q.table];
+    const uint8_t* p24 = s->perm24[q.table];
     x *= q.frequency;
     y *= q.frequency;
     double acc = 0.0;
 #pragma unroll 1
     for (int o = 0; o < q.octaves; ++o) {
-        acc += q.amp[o] * simplex2(s, p, x, y);
+        acc += q.amp[o] * simplex2(s, p, p24, x, y);
         x *= q.lacunarity;
         y *= q.lacunarity;
     }
@@ -165,13 +177,14 @@ template <int ID>
 __device__ __forceinline__ double fbm3(const NoiseShared* s, double x, double y, double z) {
     const FbmParams& q = c_noise.t.fbm[ID];
     const uint8_t* p = s->perm[q.table];
+    const uint8_t* p12 = s->perm12[q.table];
     x *= q.frequency;
     y *= q.frequency;
     z *= q.frequency;
     double acc = 0.0;
 #pragma unroll 1
     for (int o = 0; o < q.octaves; ++o) {
-        acc += q.amp[o] * simplex3(p, x, y, z);
+        acc += q.amp[o] * simplex3(p, p12, x, y, z);
         x *= q.lacunarity;
         y *= q.lacunarity;
         z *= q.lacunarity;
