@@ -6,7 +6,6 @@
 #include <cstring>
 #include <mutex>
 #include <string>
-#include <unordered_map>
 #include <vector>
 
 #include "../../include/voxel_cuda.h"
@@ -65,6 +64,62 @@ struct PinnedBuf {
 
 inline uint64_t area_key(uint32_t ax, uint32_t ay) { return ((uint64_t)ax << 32) | ay; }
 
+// AreaLocation -> pool slot.  Open addressing with linear probing over {ax, ay, slot, used}
+// entries, load factor <= 1/2, backward-shift deletion.  The entry array is byte-for-byte the
+// device-side AreaMap table, so publishing a change is one memcpy.
+struct HostAreaMap {
+    std::vector<uint4> e;
+    uint32_t mask = 0;
+    size_t count = 0;
+
+    HostAreaMap() { e.assign(64, make_uint4(0, 0, 0, 0)); mask = 63; }
+    int find(uint32_t ax, uint32_t ay) const {
+        uint32_t h = area_hash(ax, ay) & mask;
+        while (e[h].w) {
+            if (e[h].x == ax && e[h].y == ay) return (int)e[h].z;
+            h = (h + 1) & mask;
+        }
+        return -1;
+    }
+    void grow() {
+        std::vector<uint4> old;
+        old.swap(e);
+        e.assign(old.size() * 2, make_uint4(0, 0, 0, 0));
+        mask = (uint32_t)e.size() - 1;
+        for (const uint4& v : old)
+            if (v.w) place(v.x, v.y, v.z);
+    }
+    void place(uint32_t ax, uint32_t ay, uint32_t slot) {
+        uint32_t h = area_hash(ax, ay) & mask;
+        while (e[h].w) h = (h + 1) & mask;
+        e[h] = make_uint4(ax, ay, slot, 1u);
+    }
+    void insert(uint32_t ax, uint32_t ay, int slot) {  // key must be absent
+        if (2 * (count + 1) > e.size()) grow();
+        place(ax, ay, (uint32_t)slot);
+        ++count;
+    }
+    int erase(uint32_t ax, uint32_t ay) {  // returns the slot, or -1
+        uint32_t h = area_hash(ax, ay) & mask;
+        while (e[h].w && !(e[h].x == ax && e[h].y == ay)) h = (h + 1) & mask;
+        if (!e[h].w) return -1;
+        const int slot = (int)e[h].z;
+        uint32_t hole = h, j = h;
+        while (true) {  // backward-shift: keep every remaining key reachable from its home bucket
+            j = (j + 1) & mask;
+            if (!e[j].w) break;
+            const uint32_t home = area_hash(e[j].x, e[j].y) & mask;
+            if (((j - home) & mask) >= ((j - hole) & mask)) {
+                e[hole] = e[j];
+                hole = j;
+            }
+        }
+        e[hole] = make_uint4(0, 0, 0, 0);
+        --count;
+        return slot;
+    }
+};
+
 enum TimerId { TM_GEN_COLUMNS, TM_GEN_CAVES, TM_GEN_FINISH, TM_MESH_COUNT, TM_MESH_EMIT, TM_EDIT,
                TM_HEIGHTMAP, TM_LIGHT, TM_COUNT };
 
@@ -86,12 +141,12 @@ struct vx_ctx {
     uint8_t* d_heights = nullptr;
     uint16_t* d_planes = nullptr;
     uint2* d_slot_xy = nullptr;
-    std::vector<uint64_t> slot_key;  // per slot; ~0 = free
+    uint8_t* d_plane_flags = nullptr;  // per slot: planes wanted by the running vx_mesh
+    std::vector<uint64_t> slot_key;    // per slot; ~0 = free
     std::vector<int> free_slots;
-    std::unordered_map<uint64_t, int> index;
+    HostAreaMap index;
 
-    // device copy of `index` as an open-addressing hash table (see AreaMap)
-    std::vector<uint4> h_map;
+    // device copy of `index` (see AreaMap)
     uint32_t map_mask = 0;
     DevBuf d_map;
     bool map_dirty = true;
@@ -99,7 +154,7 @@ struct vx_ctx {
     // scratch
     PinnedBuf h_stage;   // jobs / lists going to the device
     PinnedBuf h_small;   // small results coming back
-    DevBuf d_jobs, d_list, d_cave_items, d_counters, d_rec_count, d_face_count;
+    DevBuf d_jobs, d_list, d_missing, d_cave_items, d_counters, d_rec_count, d_face_count;
     DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
     DevBuf d_heightmap;
     bool heightmap_init = false;
@@ -184,8 +239,10 @@ int grow_pool(vx_ctx* ctx, int min_capacity) {
     uint8_t *nv = nullptr, *nh = nullptr;
     uint16_t* np = nullptr;
     uint2* nxy = nullptr;
+    uint8_t* nf = nullptr;
     auto alloc_all = [&](int cap) -> cudaError_t {
         cudaError_t e;
+        if ((e = cudaMalloc(&nf, (size_t)cap)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&nv, (size_t)cap * VOXELS_IN_AREA)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&nh, (size_t)cap * COLUMNS_IN_AREA)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&np, (size_t)cap * 4096 * sizeof(uint16_t))) != cudaSuccess) return e;
@@ -194,15 +251,16 @@ int grow_pool(vx_ctx* ctx, int min_capacity) {
     cudaError_t e = alloc_all(new_cap);
     if (e != cudaSuccess && new_cap > min_capacity) {
         cudaGetLastError();
-        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy);
-        nv = nh = nullptr; np = nullptr; nxy = nullptr;
+        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy); cudaFree(nf);
+        nv = nh = nf = nullptr; np = nullptr; nxy = nullptr;
         new_cap = min_capacity;
         e = alloc_all(new_cap);
     }
     if (e != cudaSuccess) {
-        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy);
+        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy); cudaFree(nf);
         return fail_cuda(ctx, e, "pool allocation");
     }
+    VX_CUDA(cudaMemsetAsync(nf, 0, (size_t)new_cap, ctx->stream));
     if (ctx->capacity > 0) {
         const size_t c = (size_t)ctx->capacity;
         VX_CUDA(cudaMemcpyAsync(nv, ctx->d_voxels, c * VOXELS_IN_AREA, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -211,8 +269,10 @@ int grow_pool(vx_ctx* ctx, int min_capacity) {
         VX_CUDA(cudaMemcpyAsync(nxy, ctx->d_slot_xy, c * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
         VX_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
+        cudaFree(ctx->d_plane_flags);
     }
     ctx->d_voxels = nv; ctx->d_heights = nh; ctx->d_planes = np; ctx->d_slot_xy = nxy;
+    ctx->d_plane_flags = nf;
     ctx->slot_key.resize(new_cap, ~0ull);
     for (int s = new_cap - 1; s >= ctx->capacity; --s) ctx->free_slots.push_back(s);  // pop -> ascending
     ctx->capacity = new_cap;
@@ -223,48 +283,39 @@ int grow_pool(vx_ctx* ctx, int min_capacity) {
 // are handed out in ascending order so a batch lands contiguously in the pool.
 int acquire_slots(vx_ctx* ctx, const uint32_t* area_xy, int n, std::vector<int>& slots) {
     slots.resize(n);
-    int missing = 0;
-    for (int i = 0; i < n; ++i)
-        if (!ctx->index.count(area_key(area_xy[2 * i], area_xy[2 * i + 1]))) ++missing;
-    if ((int)ctx->free_slots.size() < missing) {
-        const int used = ctx->capacity - (int)ctx->free_slots.size();
-        int st = grow_pool(ctx, used + missing);
-        if (st != VX_OK) return st;
+    const int used = ctx->capacity - (int)ctx->free_slots.size();
+    if ((int)ctx->free_slots.size() < n) {
+        // upper bound: every listed area may need a fresh slot (cheap to over-reserve: slots only)
+        int missing = 0;
+        for (int i = 0; i < n; ++i)
+            if (ctx->index.find(area_xy[2 * i], area_xy[2 * i + 1]) < 0) ++missing;
+        if ((int)ctx->free_slots.size() < missing) {
+            const int st = grow_pool(ctx, used + missing);
+            if (st != VX_OK) return st;
+        }
     }
     for (int i = 0; i < n; ++i) {
-        const uint64_t key = area_key(area_xy[2 * i], area_xy[2 * i + 1]);
-        auto it = ctx->index.find(key);
-        if (it != ctx->index.end()) {
-            slots[i] = it->second;
-        } else {
-            const int s = ctx->free_slots.back();
+        const uint32_t ax = area_xy[2 * i], ay = area_xy[2 * i + 1];
+        int s = ctx->index.find(ax, ay);
+        if (s < 0) {
+            s = ctx->free_slots.back();
             ctx->free_slots.pop_back();
-            ctx->index.emplace(key, s);
-            ctx->slot_key[s] = key;
-            slots[i] = s;
+            ctx->index.insert(ax, ay, s);
+            ctx->slot_key[s] = area_key(ax, ay);
             ctx->map_dirty = true;
         }
+        slots[i] = s;
     }
     return VX_OK;
 }
 
 int upload_map(vx_ctx* ctx) {
     if (!ctx->map_dirty) return VX_OK;
-    uint32_t cap = 64;
-    while (cap < 2 * ctx->index.size()) cap <<= 1;
-    ctx->h_map.assign(cap, make_uint4(0, 0, 0, 0));
-    const uint32_t mask = cap - 1;
-    for (const auto& kv : ctx->index) {
-        const uint32_t ax = (uint32_t)(kv.first >> 32), ay = (uint32_t)kv.first;
-        uint32_t h = area_hash(ax, ay) & mask;
-        while (ctx->h_map[h].w) h = (h + 1) & mask;
-        ctx->h_map[h] = make_uint4(ax, ay, (uint32_t)kv.second, 1u);
-    }
-    ctx->map_mask = mask;
-    VX_CUDA(ctx->d_map.ensure(ctx->h_map.size() * sizeof(uint4)));
-    VX_CUDA(cudaMemcpyAsync(ctx->d_map.p, ctx->h_map.data(), ctx->h_map.size() * sizeof(uint4),
-                            cudaMemcpyHostToDevice, ctx->stream));
-    VX_CUDA(cudaStreamSynchronize(ctx->stream));  // h_map is pageable and rebuilt later
+    const size_t bytes = ctx->index.e.size() * sizeof(uint4);
+    VX_CUDA(ctx->d_map.ensure(bytes));
+    VX_CUDA(cudaMemcpyAsync(ctx->d_map.p, ctx->index.e.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));  // the table is pageable and changes later
+    ctx->map_mask = ctx->index.mask;
     ctx->map_dirty = false;
     return VX_OK;
 }
@@ -276,10 +327,7 @@ AreaMap device_map(const vx_ctx* ctx) {
     return m;
 }
 
-int host_slot(const vx_ctx* ctx, uint32_t ax, uint32_t ay) {
-    auto it = ctx->index.find(area_key(ax, ay));
-    return it == ctx->index.end() ? -1 : it->second;
-}
+int host_slot(const vx_ctx* ctx, uint32_t ax, uint32_t ay) { return ctx->index.find(ax, ay); }
 
 // jobs {ax, ay, slot, 0} -> device (through pinned staging; the stream is idle between calls)
 int upload_jobs(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>& slots, int n) {
@@ -400,7 +448,8 @@ void vx_destroy(vx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
-    DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_list, &ctx->d_cave_items, &ctx->d_counters,
+    cudaFree(ctx->d_plane_flags);
+    DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters,
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
                       &ctx->d_heightmap, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
@@ -538,23 +587,26 @@ int vx_read_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_o
 int vx_unload(vx_ctx* ctx, const uint32_t* area_xy, int n) {
     if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    bool any = false;
     for (int i = 0; i < n; ++i) {
-        auto it = ctx->index.find(area_key(area_xy[2 * i], area_xy[2 * i + 1]));
-        if (it == ctx->index.end()) continue;
-        ctx->slot_key[it->second] = ~0ull;
-        ctx->free_slots.push_back(it->second);
-        ctx->index.erase(it);
-        ctx->map_dirty = true;
+        const int s = ctx->index.erase(area_xy[2 * i], area_xy[2 * i + 1]);
+        if (s < 0) continue;
+        ctx->slot_key[s] = ~0ull;
+        ctx->free_slots.push_back(s);
+        any = true;
     }
-    // keep hand-out order ascending so later batches stay contiguous where possible
-    std::sort(ctx->free_slots.begin(), ctx->free_slots.end(), std::greater<int>());
+    if (any) {
+        ctx->map_dirty = true;
+        // keep hand-out order ascending so later batches stay contiguous where possible
+        std::sort(ctx->free_slots.begin(), ctx->free_slots.end(), std::greater<int>());
+    }
     return VX_OK;
 }
 
 int vx_resident_count(vx_ctx* ctx) {
     if (!ctx) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    return (int)ctx->index.size();
+    return (int)ctx->index.count;
 }
 
 int vx_column_heights(vx_ctx* ctx, const uint8_t* voxels, int n, uint8_t* max_height_out) {
@@ -585,87 +637,81 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
     VX_CUDA(cudaSetDevice(ctx->device));
     reset_timers(ctx);
     ctx->mesh_n = -1;
-    std::vector<int> slots(n);
-    for (int i = 0; i < n; ++i) {
-        slots[i] = host_slot(ctx, area_xy[2 * i], area_xy[2 * i + 1]);
-        if (slots[i] < 0) return fail(ctx, VX_ERR_NOT_LOADED, "vx_mesh: area not resident");
-    }
-    // edge neighbours that are not resident are generated, like world.get_with_cache -> load_area
-    std::vector<uint32_t> missing;
-    {
-        std::unordered_map<uint64_t, int> seen;
-        static const int D[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
-        for (int i = 0; i < n; ++i)
-            for (int d = 0; d < 4; ++d) {
-                const uint32_t ax = area_xy[2 * i] + D[d][0], ay = area_xy[2 * i + 1] + D[d][1];
-                const uint64_t key = area_key(ax, ay);
-                if (ctx->index.count(key) || seen.count(key)) continue;
-                seen.emplace(key, 1);
-                missing.push_back(ax);
-                missing.push_back(ay);
-            }
-    }
+    ctx->mesh_info = vx_mesh_info{};
     int st;
-    if (!missing.empty()) {
-        if (!ctx->has_seed) return fail(ctx, VX_ERR_NO_SEED, "vx_mesh needs to generate edge neighbours but no seed is set");
-        const int m = (int)missing.size() / 2;
-        std::vector<int> mslots;
-        if ((st = acquire_slots(ctx, missing.data(), m, mslots)) != VX_OK) return st;
-        if ((st = generate_async(ctx, missing.data(), mslots, m)) != VX_OK) return st;
-        VX_CUDA(cudaStreamSynchronize(ctx->stream));  // staging buffers are reused below
-        for (int i = 0; i < n; ++i) slots[i] = host_slot(ctx, area_xy[2 * i], area_xy[2 * i + 1]);  // pool may have moved
-    }
-    if ((st = upload_map(ctx)) != VX_OK) return st;
-
     if (n > 0) {
-        // bit planes of every area read by this call (the meshed ones and their edge neighbours)
-        std::vector<int> plane_slots;
-        {
-            std::vector<uint8_t> mark(ctx->capacity, 0);
-            static const int D[5][2] = {{0, 0}, {1, 0}, {-1, 0}, {0, 1}, {0, -1}};
-            for (int i = 0; i < n; ++i)
-                for (int d = 0; d < 5; ++d) {
-                    const int s = host_slot(ctx, area_xy[2 * i] + D[d][0], area_xy[2 * i + 1] + D[d][1]);
-                    if (s >= 0 && !mark[s]) {
-                        mark[s] = 1;
-                        plane_slots.push_back(s);
-                    }
-                }
-        }
-        const int np = (int)plane_slots.size();
-        // staging: [jobs n uint4][plane slots np int]
-        const size_t jobs_bytes = (size_t)n * sizeof(uint4);
-        VX_CUDA(ctx->h_stage.ensure(jobs_bytes + (size_t)np * sizeof(int)));
-        VX_CUDA(ctx->d_jobs.ensure(jobs_bytes));
-        VX_CUDA(ctx->d_list.ensure((size_t)np * sizeof(int)));
-        uint4* hj = ctx->h_stage.as<uint4>();
-        for (int i = 0; i < n; ++i) hj[i] = make_uint4(area_xy[2 * i], area_xy[2 * i + 1], (uint32_t)slots[i], 0u);
-        int* hp = reinterpret_cast<int*>(ctx->h_stage.as<uint8_t>() + jobs_bytes);
-        std::copy(plane_slots.begin(), plane_slots.end(), hp);
-        VX_CUDA(cudaMemcpyAsync(ctx->d_jobs.p, hj, jobs_bytes, cudaMemcpyHostToDevice, ctx->stream));
-        VX_CUDA(cudaMemcpyAsync(ctx->d_list.p, hp, (size_t)np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-
+        if (ctx->capacity == 0) return fail(ctx, VX_ERR_NOT_LOADED, "vx_mesh: area not resident");
+        // the area list goes to the device as is; slots, neighbour residency and the set of bit
+        // planes to refresh are resolved there (mesh_prepare_kernel), not in a host loop
+        const size_t xy_bytes = (size_t)n * sizeof(uint2);
+        VX_CUDA(ctx->h_stage.ensure(xy_bytes));
+        VX_CUDA(ctx->h_small.ensure(64 + (size_t)4 * n * sizeof(uint2)));
+        VX_CUDA(ctx->d_list.ensure(xy_bytes));
+        VX_CUDA(ctx->d_jobs.ensure((size_t)n * sizeof(uint4)));
+        VX_CUDA(ctx->d_missing.ensure((size_t)4 * n * sizeof(uint2)));
+        VX_CUDA(ctx->d_counters.ensure(64));
         VX_CUDA(ctx->d_rec_count.ensure((size_t)n * 4));
         VX_CUDA(ctx->d_face_count.ensure((size_t)n * 4));
         VX_CUDA(ctx->d_rec_first.ensure((size_t)(n + 1) * 4));
         VX_CUDA(ctx->d_face_first.ensure((size_t)(n + 1) * 4));
-        const AreaMap map = device_map(ctx);
-        {
-            ScopedTimer t(ctx, TM_MESH_COUNT);
-            launch_mesh_planes(ctx->d_list.as<int>(), np, ctx->d_voxels, ctx->d_planes, ctx->stream);
-            launch_mesh_count(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_planes, map,
-                              ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), ctx->stream);
-            launch_mesh_offsets(ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), n,
-                                ctx->d_rec_first.as<uint32_t>(), ctx->d_face_first.as<uint32_t>(), ctx->stream);
+        std::memcpy(ctx->h_stage.p, area_xy, xy_bytes);
+        VX_CUDA(cudaMemcpyAsync(ctx->d_list.p, ctx->h_stage.p, xy_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        uint32_t* counters = ctx->d_counters.as<uint32_t>();
+        uint32_t* back = ctx->h_small.as<uint32_t>();  // [0] missing self, [1] missing nbrs, [2] recs, [3] faces
+        uint64_t n_recs = 0, n_faces = 0;
+        for (int attempt = 0;; ++attempt) {
+            if ((st = upload_map(ctx)) != VX_OK) return st;
+            const AreaMap map = device_map(ctx);
+            VX_CUDA(cudaMemsetAsync(counters, 0, 8, ctx->stream));
+            {
+                ScopedTimer t(ctx, TM_MESH_COUNT);
+                launch_mesh_prepare(ctx->d_list.as<uint2>(), n, map, ctx->d_jobs.as<uint4>(), ctx->d_plane_flags,
+                                    counters, ctx->d_missing.as<uint2>(), 4u * (uint32_t)n, ctx->stream);
+                launch_mesh_planes(ctx->d_plane_flags, ctx->capacity, ctx->d_voxels, ctx->d_planes, ctx->stream);
+                launch_mesh_count(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_planes, map,
+                                  ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), ctx->stream);
+                launch_mesh_offsets(ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), n,
+                                    ctx->d_rec_first.as<uint32_t>(), ctx->d_face_first.as<uint32_t>(), ctx->stream);
+            }
+            ctx->timings.mesh_launches += 4;
+            VX_CUDA(cudaGetLastError());
+            VX_CUDA(cudaMemcpyAsync(&back[0], counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            VX_CUDA(cudaMemcpyAsync(&back[2], ctx->d_rec_first.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            VX_CUDA(cudaMemcpyAsync(&back[3], ctx->d_face_first.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            VX_CUDA(cudaStreamSynchronize(ctx->stream));
+            collect_timers(ctx);
+            if (back[0] != 0) return fail(ctx, VX_ERR_NOT_LOADED, "vx_mesh: area not resident");
+            if (back[1] == 0) {
+                n_recs = back[2];
+                n_faces = back[3];
+                break;
+            }
+            // edge neighbours that are not resident are generated, like world.get_with_cache ->
+            // load_area (world.rs:157-174), then the pass above is repeated
+            if (attempt > 0) return fail(ctx, VX_ERR_CUDA, "vx_mesh: neighbours still missing after generation");
+            if (!ctx->has_seed) return fail(ctx, VX_ERR_NO_SEED, "vx_mesh needs to generate edge neighbours but no seed is set");
+            const uint32_t nm = std::min<uint32_t>(back[1], 4u * (uint32_t)n);
+            uint2* miss = reinterpret_cast<uint2*>(back + 16);
+            VX_CUDA(cudaMemcpyAsync(miss, ctx->d_missing.p, (size_t)nm * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+            VX_CUDA(cudaStreamSynchronize(ctx->stream));
+            std::vector<uint64_t> keys(nm);
+            for (uint32_t i = 0; i < nm; ++i) keys[i] = area_key(miss[i].x, miss[i].y);
+            std::sort(keys.begin(), keys.end());
+            keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+            std::vector<uint32_t> mxy(2 * keys.size());
+            for (size_t i = 0; i < keys.size(); ++i) {
+                mxy[2 * i] = (uint32_t)(keys[i] >> 32);
+                mxy[2 * i + 1] = (uint32_t)keys[i];
+            }
+            std::vector<int> mslots;
+            if ((st = acquire_slots(ctx, mxy.data(), (int)keys.size(), mslots)) != VX_OK) return st;
+            if ((st = generate_async(ctx, mxy.data(), mslots, (int)keys.size())) != VX_OK) return st;
+            VX_CUDA(cudaStreamSynchronize(ctx->stream));
+            collect_timers(ctx);
+            // generate_async reused h_stage / d_jobs: restore the area list for the retry
+            std::memcpy(ctx->h_stage.p, area_xy, xy_bytes);
+            VX_CUDA(ctx->d_jobs.ensure((size_t)n * sizeof(uint4)));
         }
-        ctx->timings.mesh_launches += 3;
-        VX_CUDA(cudaGetLastError());
-        VX_CUDA(ctx->h_small.ensure(16));
-        uint32_t* totals = ctx->h_small.as<uint32_t>();
-        VX_CUDA(cudaMemcpyAsync(&totals[0], ctx->d_rec_first.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        VX_CUDA(cudaMemcpyAsync(&totals[1], ctx->d_face_first.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        VX_CUDA(cudaStreamSynchronize(ctx->stream));
-        const uint64_t n_recs = totals[0], n_faces = totals[1];
         VX_CUDA(ctx->d_recs.ensure(std::max<size_t>(16, n_recs * 16)));
         VX_CUDA(ctx->d_vertices.ensure(std::max<size_t>(16, n_faces * 160)));
         VX_CUDA(ctx->d_indices.ensure(std::max<size_t>(16, n_faces * 12)));
@@ -677,15 +723,13 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
         out.indices = ctx->d_indices.as<uint32_t>();
         {
             ScopedTimer t(ctx, TM_MESH_EMIT);
-            launch_mesh_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_planes, map, out, ctx->stream);
+            launch_mesh_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_planes, device_map(ctx), out, ctx->stream);
         }
         ctx->timings.mesh_launches += 1;
         VX_CUDA(cudaGetLastError());
         if ((st = sync_stream(ctx)) != VX_OK) return st;
         ctx->mesh_info.n_faces = n_faces;
         ctx->mesh_info.n_recs = n_recs;
-    } else {
-        ctx->mesh_info.n_faces = ctx->mesh_info.n_recs = 0;
     }
     ctx->mesh_info.vertex_bytes = ctx->mesh_info.n_faces * 160;
     ctx->mesh_info.index_bytes = ctx->mesh_info.n_faces * 12;

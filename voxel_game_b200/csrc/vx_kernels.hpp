@@ -36,8 +36,14 @@ struct MeshOut {
     uint32_t* indices;     // 3 u32 per face
 };
 // planes: per slot uint16 S[2048] ("voxel != None") then uint16 T[2048] ("transparent")
-void launch_mesh_planes(const int* slots, int n, const uint8_t* pool_voxels, uint16_t* pool_planes,
-                        cudaStream_t stream);
+// prepare: xy -> jobs {ax, ay, slot, 0}; need_plane[slot] = 1 for every area the call reads;
+// counters[0] = requested areas not resident, counters[1] = neighbours not resident (-> missing[])
+void launch_mesh_prepare(const uint2* xy, int n, AreaMap map, uint4* jobs, uint8_t* need_plane,
+                         uint32_t* counters, uint2* missing, uint32_t missing_cap,
+                         cudaStream_t stream);
+// one CTA per pool slot [0, n_slots); computes the planes of flagged slots and clears the flag
+void launch_mesh_planes(uint8_t* need_plane, int n_slots, const uint8_t* pool_voxels,
+                        uint16_t* pool_planes, cudaStream_t stream);
 void launch_mesh_count(const uint4* jobs, int n, const uint8_t* pool_voxels,
                        const uint16_t* pool_planes, AreaMap map, uint32_t* rec_count,
                        uint32_t* face_count, cudaStream_t stream);
