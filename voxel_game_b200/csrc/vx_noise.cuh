@@ -61,29 +61,28 @@ __device__ __forceinline__ void load_noise_shared(NoiseShared* s, int tid, int n
     for (int i = tid; i < 48; i += nthreads) (&s->grad2[0][0])[i] = (&c_grad2[0][0])[i];
 }
 
-// floor(x) as a double and as an int, |x| < 2^31, on the FP64 add pipe
+// floor(x) as a double and as an int, |x| < 2^31, in two FP64 adds and nothing else: adding
+// 2^52 + 2^51 with round-toward-minus-infinity leaves exactly floor(x) in the low mantissa bits
+// (the ulp of the sum is 1), and subtracting the constant again is exact.
 __device__ __forceinline__ double floor_split(double x, int& i) {
     const double MAGIC = 6755399441055744.0;  // 2^52 + 2^51
-    const double t = x + MAGIC;               // rounds x to the nearest integer
-    int n = __double2loint(t);
-    double r = t - MAGIC;
-    if (r > x) {
-        r -= 1.0;
-        n -= 1;
-    }
-    i = n;
-    return r;
+    const double t = __dadd_rd(x, MAGIC);
+    i = __double2loint(t);
+    return t - MAGIC;
 }
 
-// contribution of one simplex corner; gi = gradient index.  "t <= 0 -> 0" is applied as
-// max(t, 0) before the powers: identical values (0 * d = +-0, and a zero of either sign adds
-// nothing to the sum), one DMNMX instead of a compare and two selects.
-__device__ __forceinline__ double corner2(const NoiseShared* s, double x, double y, unsigned gi) {
-    const double t = fmax(0.5 - x * x - y * y, 0.0);
+// contribution of one simplex corner, added to `sum`; gi = gradient index.  A corner outside its
+// radius (t <= 0) contributes 0 in the crate, i.e. leaves the running sum unchanged, so it is
+// skipped with a predicated add instead of materialising the zero (sum starts at +0.0 and
+// 0.0 + v == v).
+__device__ __forceinline__ void corner2(const NoiseShared* s, double x, double y, unsigned gi,
+                                        double& sum) {
+    const double t = 0.5 - x * x - y * y;
     const double2 g = *reinterpret_cast<const double2*>(&s->grad2[gi][0]);
     const double d = g.x * x + g.y * y;
     const double t2 = t * t;
-    return t2 * t2 * d;
+    const double v = t2 * t2 * d;
+    if (t > 0.0) sum += v;
 }
 
 __device__ __forceinline__ double simplex2(const NoiseShared* s, const uint8_t* p,
@@ -101,10 +100,11 @@ __device__ __forceinline__ double simplex2(const NoiseShared* s, const uint8_t* 
     const unsigned h0 = p24[(pi0 + j) & 255];
     const unsigned h1 = lower ? p24[(pi1 + j) & 255] : p24[(pi0 + j + 1) & 255];
     const unsigned h2 = p24[(pi1 + j + 1) & 255];
-    const double n0 = corner2(s, x0, y0, h0);
-    const double n1 = corner2(s, x1, y1, h1);
-    const double n2 = corner2(s, x2, y2, h2);
-    return (n0 + n1 + n2) * 99.83685446303647;
+    double sum = 0.0;
+    corner2(s, x0, y0, h0, sum);
+    corner2(s, x1, y1, h1, sum);
+    corner2(s, x2, y2, h2, sum);
+    return sum * 99.83685446303647;
 }
 
 // gradient h % 12 of the edge-midpoint set
@@ -113,14 +113,15 @@ __device__ __forceinline__ double simplex2(const NoiseShared* s, const uint8_t* 
 __device__ __forceinline__ double flip_sign(double v, unsigned sign_bit31) {
     return __hiloint2double(__double2hiint(v) ^ (int)sign_bit31, __double2loint(v));
 }
-__device__ __forceinline__ double corner3(double x, double y, double z, unsigned gi) {
-    const double t = fmax(0.5 - x * x - y * y - z * z, 0.0);
+__device__ __forceinline__ void corner3(double x, double y, double z, unsigned gi, double& sum) {
+    const double t = 0.5 - x * x - y * y - z * z;
     const unsigned grp = gi >> 2;
     const double a = flip_sign(grp == 2u ? y : x, gi << 31);
     const double b = flip_sign(grp == 0u ? y : z, (gi << 30) & 0x80000000u);
     const double d = a + b;
     const double t2 = t * t;
-    return t2 * t2 * d;
+    const double v = t2 * t2 * d;
+    if (t > 0.0) sum += v;
 }
 
 __device__ __forceinline__ double simplex3(const uint8_t* p, const uint8_t* p12, double x, double y,
@@ -149,11 +150,12 @@ __device__ __forceinline__ double simplex3(const uint8_t* p, const uint8_t* p12,
     const unsigned h1 = p12[(p[((i1 ? pi1 : pi0) + j + (int)j1) & 255] + k + (int)k1) & 255];
     const unsigned h2 = p12[(p[((i2 ? pi1 : pi0) + j + (int)j2) & 255] + k + (int)k2) & 255];
     const unsigned h3 = p12[(p[(pi1 + j + 1) & 255] + k + 1) & 255];
-    const double n0 = corner3(x0, y0, z0, h0);
-    const double n1 = corner3(x1, y1, z1, h1);
-    const double n2 = corner3(x2, y2, z2, h2);
-    const double n3 = corner3(x3, y3, z3, h3);
-    return (n0 + n1 + n2 + n3) * 76.88375854620836;
+    double sum = 0.0;
+    corner3(x0, y0, z0, h0, sum);
+    corner3(x1, y1, z1, h1, sum);
+    corner3(x2, y2, z2, h2, sum);
+    corner3(x3, y3, z3, h3, sum);
+    return sum * 76.88375854620836;
 }
 
 template <int ID>
