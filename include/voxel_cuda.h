@@ -95,8 +95,8 @@ typedef struct {
     float light_ms;        /* L-ext */
     uint32_t gen_launches, mesh_launches, other_launches; /* kernels launched by the last call */
     uint32_t cave_columns;                                /* K1b work items of the last generate */
-    /* work accounting of the last vx_generate (roofline numerators; comparable with the oracle's
-     * vgo_gen_stats): octave-level simplex evaluations and voxels that ran the cave noise */
+    /* work accounting of the last vx_generate (roofline numerators): octave-level simplex
+     * evaluations executed and voxels that ran the cave noise */
     uint64_t simplex2_evals, simplex3_evals, cave_voxels;
 } vx_timings;
 

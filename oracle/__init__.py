@@ -88,6 +88,14 @@ def lib():
         L.vgo_simplex2.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.vgo_simplex3.restype = C.c_double
         L.vgo_simplex3.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.vgo_grad2_table.argtypes = [C.POINTER(C.c_double)]
+        L.vgo_grad3_table.argtypes = [C.POINTER(C.c_double)]
+        L.vgo_simplex_perm.argtypes = [C.c_void_p, u8p]
+        L.vgo_fbm_new.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.vgo_fbm2.restype = C.c_double
+        L.vgo_fbm2.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.vgo_fbm3.restype = C.c_double
+        L.vgo_fbm3.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
         L.vgo_generator_new.restype = C.c_void_p
         L.vgo_generator_new.argtypes = [C.c_uint64]
         L.vgo_generator_free.argtypes = [C.c_void_p]
@@ -144,6 +152,78 @@ def region_xy(ax0: int, ay0: int, nx: int, ny: int) -> np.ndarray:
     ix, iy = np.meshgrid(np.arange(nx, dtype=np.uint32), np.arange(ny, dtype=np.uint32))
     xy = np.stack([ix.ravel() + np.uint32(ax0), iy.ravel() + np.uint32(ay0)], axis=1)
     return np.ascontiguousarray(xy, dtype=np.uint32)
+
+
+class Simplex:
+    """libnoise Simplex::new(seed) (permutation table) with .sample2/.sample3."""
+
+    def __init__(self, seed: int):
+        self._buf = (C.c_uint8 * 512)()
+        lib().vgo_simplex_new(C.addressof(self._buf), seed & 0xFFFFFFFFFFFFFFFF)
+
+    @property
+    def perm(self) -> np.ndarray:
+        return np.frombuffer(self._buf, dtype=np.uint8).copy()
+
+    def sample2(self, x, y) -> float:
+        return float(lib().vgo_simplex2(C.addressof(self._buf), x, y))
+
+    def sample3(self, x, y, z) -> float:
+        return float(lib().vgo_simplex3(C.addressof(self._buf), x, y, z))
+
+
+class _Fbm(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("octaves", C.c_int), ("frequency", C.c_double),
+                ("lacunarity", C.c_double), ("persistence", C.c_double),
+                ("normalization_factor", C.c_double)]
+
+
+class Fbm:
+    """Simplex::new(seed).fbm(octaves, frequency, lacunarity, persistence)."""
+
+    def __init__(self, simplex: Simplex, octaves, frequency, lacunarity, persistence):
+        self._s = simplex
+        self._f = _Fbm()
+        lib().vgo_fbm_new(C.byref(self._f), C.addressof(simplex._buf), octaves, frequency, lacunarity, persistence)
+
+    @property
+    def normalization_factor(self):
+        return float(self._f.normalization_factor)
+
+    def sample2(self, x, y):
+        return float(lib().vgo_fbm2(C.byref(self._f), x, y))
+
+    def sample3(self, x, y, z):
+        return float(lib().vgo_fbm3(C.byref(self._f), x, y, z))
+
+
+def grad2_table() -> np.ndarray:
+    out = np.zeros((24, 2))
+    lib().vgo_grad2_table(_p(out, C.c_double))
+    return out
+
+
+def grad3_table() -> np.ndarray:
+    out = np.zeros((12, 3))
+    lib().vgo_grad3_table(_p(out, C.c_double))
+    return out
+
+
+def chacha12_words(seed: int, n: int) -> np.ndarray:
+    out = np.zeros(n, np.uint32)
+    lib().vgo_chacha12_words(seed & 0xFFFFFFFFFFFFFFFF, _p(out, C.c_uint32), n)
+    return out
+
+
+def chacha_block(key_words, counter: int, double_rounds: int) -> np.ndarray:
+    key = np.ascontiguousarray(key_words, np.uint32)
+    out = np.zeros(16, np.uint32)
+    lib().vgo_chacha_block_raw(_p(key, C.c_uint32), counter, double_rounds, _p(out, C.c_uint32))
+    return out
+
+
+def siphash(c_rounds, d_rounds, k0, k1, data: bytes) -> int:
+    return int(lib().vgo_siphash(c_rounds, d_rounds, k0, k1, data, len(data)))
 
 
 class Generator:

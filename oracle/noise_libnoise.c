@@ -374,3 +374,8 @@ double vgo_fbm3(const vgo_fbm* f, double x, double y, double z) {
     }
     return noise * f->normalization_factor;
 }
+
+/* gradient tables, exposed so that tests can pin them against the crate's normalisation constants */
+void vgo_grad2_table(double* out48) { memcpy(out48, GRAD2, sizeof GRAD2); }
+void vgo_grad3_table(double* out36) { memcpy(out36, GRAD3, sizeof GRAD3); }
+void vgo_simplex_perm(const vgo_simplex* s, uint8_t* out512) { memcpy(out512, s->perm, 512); }

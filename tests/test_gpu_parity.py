@@ -129,3 +129,243 @@ def test_work_counters_match_oracle(ctx, seed):
     # anyway (the reference evaluates it and discards the result), so it may do fewer, never more
     cave3 = 14 * stats["cave_voxels"]
     assert cave3 < t["simplex3_evals"] <= stats["simplex3_evals"]
+
+
+# ------------------------------------------------------------------------------ golden fixtures
+import hashlib
+import os
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN = ["spawn_8x8_test.npz", "caves_6x6_test.npz", "far_4x4_seed2.npz", "lake_4x4_test.npz", "cold_4x4_test.npz"]
+
+
+def _digest(a):
+    return int(np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest()[:8], np.uint64)[0])
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_cuda_path_reproduces_golden_fixture(name):
+    """Committed fixtures (tests/golden/make_golden.py): block IDs, heights, records, vertices and
+    indices per area, as digests.  Needs nothing but the .npz on the GPU box."""
+    g = np.load(os.path.join(GOLDEN_DIR, name))
+    ax0, ay0, n = int(g["origin"][0]), int(g["origin"][1]), int(g["n"])
+    with vg.Context(0, seed=int(g["seed"])) as c:
+        assert c.seed == vg.hash_world_name(str(g["world_name"]))
+        inner = vg.region_xy(ax0, ay0, n, n)
+        vox, mh = c.generate(inner)           # ring NOT generated here: vx_mesh must do it itself
+        info = c.mesh(inner)
+        assert c.resident_count() == n * n + 4 * n  # the four edge strips were generated on demand
+        rec_first, face_first, recs, verts, idx = c.mesh_read(info)
+    for i, row in enumerate(g["rows"]):
+        assert (int(row[0]), int(row[1])) == (int(inner[i][0]), int(inner[i][1]))
+        assert _digest(vox[i]) == int(row[2]), f"block IDs of area {inner[i]}"
+        assert _digest(mh[i]) == int(row[3]), f"heights of area {inner[i]}"
+        f0, f1 = int(face_first[i]), int(face_first[i + 1])
+        r = recs[rec_first[i]:rec_first[i + 1]].copy()
+        r["first_face"] -= f0                  # fixtures store per-area face indices
+        assert f1 - f0 == int(row[4]) and len(r) == int(row[5])
+        assert _digest(r) == int(row[6]) and _digest(verts[4 * f0:4 * f1]) == int(row[7])
+        assert _digest(idx[6 * f0:6 * f1]) == int(row[8])
+
+
+# ------------------------------------------------------------------------------ light / residency / errors
+def test_column_heights_operator_and_upload_roundtrip(ctx, seed):
+    """Area::update_all_column_heights as an operator (area.rs:34-56), upload -> read back, unload."""
+    rng = np.random.default_rng(5)
+    vox = rng.integers(0, 27, size=(7, 32768), dtype=np.uint8)
+    vox[0] = 0                                   # empty area: every height 127
+    vox[1] = oracle.V["Glass"]                   # only transparent voxels: 127 too
+    vox[2].reshape(128, 256)[:100] = 0           # first opaque voxel deep down
+    want = np.stack([oracle.update_all_column_heights(v) for v in vox])
+    assert np.array_equal(ctx.column_heights(vox), want)
+    assert (want[0] == 127).all() and (want[1] == 127).all()
+    xy = vg.region_xy(40000, 40000, 7, 1)
+    before = ctx.resident_count()
+    assert np.array_equal(ctx.upload(xy, vox), want)
+    v2, h2 = ctx.read_areas(xy[::-1])            # any order
+    assert np.array_equal(v2, vox[::-1]) and np.array_equal(h2, want[::-1])
+    ctx.unload(xy)
+    assert ctx.resident_count() == before
+    with pytest.raises(vg.VxError) as e:
+        ctx.read_areas(xy[:1])
+    assert e.value.status == -5                  # VX_ERR_NOT_LOADED
+
+
+def test_error_paths(seed):
+    with vg.Context(0) as c:                     # no seed yet
+        with pytest.raises(vg.VxError) as e:
+            c.generate(vg.region_xy(1, 1, 1, 1))
+        assert e.value.status == -4              # VX_ERR_NO_SEED
+        with pytest.raises(vg.VxError) as e:
+            c.mesh(vg.region_xy(1, 1, 1, 1))
+        assert e.value.status == -5              # VX_ERR_NOT_LOADED
+        c.set_seed(seed)
+        assert c.mesh(np.zeros((0, 2), np.uint32))["n_faces"] == 0   # empty request
+        c.generate(vg.region_xy(5, 5, 2, 2), read=False)
+        bad = np.zeros(1, vg.EDIT_DTYPE)
+        bad[0] = (5 * 16, 5 * 16, 128, 1)        # z out of range
+        with pytest.raises(vg.VxError) as e:
+            c.apply_edits(bad)
+        assert e.value.status == -3
+        bad[0] = (5 * 16, 5 * 16, 10, 27)        # voxel id out of range
+        with pytest.raises(vg.VxError):
+            c.apply_edits(bad)
+        bad[0] = (900 * 16, 5 * 16, 10, 1)       # area not resident
+        with pytest.raises(vg.VxError) as e:
+            c.apply_edits(bad)
+        assert e.value.status == -5
+
+
+def test_regeneration_and_batch_split_are_deterministic(ctx, seed):
+    """Same areas generated as one batch, as two batches in another order, and twice: identical."""
+    xy = vg.region_xy(62480, 62520, 6, 4)
+    a, ah = ctx.generate(xy)
+    perm = np.random.default_rng(0).permutation(len(xy))
+    with vg.Context(0, seed=seed) as c2:
+        b1, bh1 = c2.generate(xy[perm[:10]])
+        b2, bh2 = c2.generate(xy[perm[10:]])
+    b = np.concatenate([b1, b2])[np.argsort(perm)]
+    bh = np.concatenate([bh1, bh2])[np.argsort(perm)]
+    assert np.array_equal(a, b) and np.array_equal(ah, bh)
+    c, ch = ctx.generate(xy)
+    assert np.array_equal(a, c) and np.array_equal(ah, ch)
+
+
+def test_heightmap_image(ctx, seed):
+    """HeightMap::generate_height_map pixel loop (height_map.rs:41-85) incl. the 31-area window,
+    stale pixels and non-resident areas reading as height 127."""
+    from voxel_game_b200 import world as w
+
+    cam = (62500, 62500)
+    with vg.Context(0, seed=seed) as c:
+        zone = w.render_zone(cam, 17)                              # wider than the 31-area window
+        loaded = vg.region_xy(cam[0] - 10, cam[1] - 10, 21, 21)    # only part of it is resident
+        _, mh = c.generate(loaded)
+        img = c.heightmap(zone, cam[0], cam[1])
+        lookup = {(int(a), int(b)): mh[i] for i, (a, b) in enumerate(loaded)}
+        heights = np.stack([lookup.get((int(a), int(b)), np.full(256, 127, np.uint8)) for a, b in zone])
+        want = oracle.height_map(zone, heights, cam[0], cam[1])
+        assert np.array_equal(img, want)
+        # second frame, camera moved by one area, fewer areas listed: stale pixels persist
+        img2 = c.heightmap(loaded[:50], cam[0] + 1, cam[1])
+        want2 = oracle.height_map(loaded[:50], mh[:50], cam[0] + 1, cam[1], pixels=want.copy())
+        assert np.array_equal(img2, want2)
+
+
+# ------------------------------------------------------------------------------ edits (config 4, reduced)
+def _edit_storm(rng_state, n_edits, ax0, ay0, n_side, world):
+    """SplitMix64 stream; break if occupied, else place one of six plain blocks."""
+    palette = [oracle.V[k] for k in ("Cobblestone", "Brick", "Boards", "Stone", "Lamp", "Glass")]
+    L = oracle.lib()
+    state = rng_state
+
+    def draw():
+        nonlocal state
+        out = L.vgo_split_mix64(state)
+        state = (state + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        return out
+
+    edits = np.zeros(n_edits, vg.EDIT_DTYPE)
+    span = n_side * 16
+    for i in range(n_edits):
+        gx = ax0 * 16 + draw() % span
+        gy = ay0 * 16 + draw() % span
+        gz = 1 + draw() % 126
+        cur = world.voxels[world.slot(gx // 16, gy // 16)][(gx % 16) + 16 * (gy % 16) + 256 * gz]
+        v = 0 if cur != 0 else palette[draw() % 6]
+        edits[i] = (gx, gy, gz, v)
+        world.apply_edit(int(gx), int(gy), int(gz), int(v))   # sequential reference semantics
+    return edits
+
+
+def test_edit_storm_batched_equals_sequential(seed):
+    """Edits applied in GPU batches (last writer wins inside a batch) + relight of edited columns +
+    remesh of dirty areas == the oracle applying World::set + Renderer::update_location one by
+    one (world.rs:184-191, renderer.rs:239-286): voxels, heights, face sets, lamp sets."""
+    n, ax0, ay0 = 6, 62496, 62496
+    world = oracle.World.generate(seed, ax0 - 1, ay0 - 1, n + 2, n + 2)
+    inner = vg.region_xy(ax0, ay0, n, n)
+    for ax, ay in inner:
+        world.mesh_area(int(ax), int(ay))
+    with vg.Context(0, seed=seed) as c:
+        c.generate(vg.region_xy(ax0 - 1, ay0 - 1, n + 2, n + 2), read=False)
+        c.mesh(inner)
+        edits = _edit_storm(0x5EEDED17, 3000, ax0, ay0, n, world)
+        # force duplicates inside one batch: the last writer must win
+        edits[1500:1510] = edits[1499]
+        edits[1505]["voxel"] = oracle.V["Brick"]
+        for e in edits[1500:1510]:
+            world.apply_edit(int(e["gx"]), int(e["gy"]), int(e["gz"]), int(e["voxel"]))
+        dirty_all = set()
+        for lo in range(0, len(edits), 1000):
+            d = c.apply_edits(edits[lo:lo + 1000])
+            dirty_all |= {(int(a), int(b)) for a, b in d}
+        # every edited area is reported dirty, plus edge neighbours for border edits
+        touched = {(int(e["gx"]) // 16, int(e["gy"]) // 16) for e in edits}
+        assert touched <= dirty_all
+        vox, mh = c.read_areas(inner)
+        for i, (ax, ay) in enumerate(inner):
+            s = world.slot(int(ax), int(ay))
+            assert np.array_equal(vox[i], world.voxels[s]), f"voxels of {ax},{ay}"
+            assert np.array_equal(mh[i], world.max_height[s]), f"heights of {ax},{ay}"
+        dirty_inner = np.array(sorted(d for d in dirty_all if ax0 <= d[0] < ax0 + n and ay0 <= d[1] < ay0 + n), np.uint32)
+        info = c.mesh(dirty_inner)
+        rec_first, face_first, recs, verts, idx = c.mesh_read(info)
+        lamps_gpu, lamps_cpu = set(), set()
+        for i, (ax, ay) in enumerate(dirty_inner):
+            s = world.slot(int(ax), int(ay))
+            r = recs[rec_first[i]:rec_first[i + 1]]
+            got = np.zeros(32768, np.uint8)
+            li = (r["gx"] % 16) + 16 * (r["gy"] % 16) + 256 * (r["packed"] & 0xFF)
+            got[li] = (r["packed"] >> 16) & 0xFF
+            assert np.array_equal(got, world.face_mask[s]), f"face set of {ax},{ay}"
+            orecs, overts, oidx = world.emit_area(int(ax), int(ay), first_face_base=int(face_first[i]))
+            assert r.tobytes() == orecs.tobytes()
+            assert verts[4 * face_first[i]:4 * face_first[i + 1]].tobytes() == overts.tobytes()
+            lamps_gpu |= {(int(a["gx"]), int(a["gy"]), int(a["packed"]) & 0xFF) for a in r if (a["packed"] >> 8) & 0xFF == 11}
+            fm = world.face_mask[s]
+            for j in np.flatnonzero((world.voxels[s] == 11) & (fm != 0)):
+                lamps_cpu.add((int(ax) * 16 + int(j) % 16, int(ay) * 16 + (int(j) // 16) % 16, int(j) // 256))
+        assert lamps_gpu == lamps_cpu and len(lamps_cpu) > 0     # RenderArea.lights (renderer.rs:60-67)
+
+
+# ------------------------------------------------------------------------------ full size (config 3)
+def test_full_size_128x128_properties(seed):
+    """BASELINE.json configs[2] at full size through size-independent properties: per-area digests
+    of all 16 384 areas against the oracle (all host threads), column heights idempotent under the
+    stand-alone operator, face counts consistent between records / offsets / totals, index pattern,
+    every vertex within half a voxel of its voxel centre, and the mesh is bit-reproducible."""
+    ax0, ay0, nx, ny = vg.spawn_region(128)
+    ring = vg.region_xy(ax0 - 1, ay0 - 1, nx + 2, ny + 2)
+    inner = vg.region_xy(ax0, ay0, nx, ny)
+    with vg.Context(0, seed=seed) as c:
+        vox, mh = c.generate(ring)
+        ovox, omh, _, _ = oracle.generate_areas(seed, ring)
+        bad = np.flatnonzero((vox != ovox).any(axis=1))
+        assert bad.size == 0, f"{bad.size} of {len(ring)} areas differ, first {ring[bad[0]]}"
+        assert np.array_equal(mh, omh)
+        sample = np.random.default_rng(1).choice(len(ring), 512, replace=False)
+        assert np.array_equal(c.column_heights(vox[sample]), mh[sample])      # idempotence
+        info = c.mesh(inner)
+        rec_first, face_first, recs, verts, idx = c.mesh_read(info)
+        info2 = c.mesh(inner)
+        again = c.mesh_read(info2)
+        assert info == info2 and all(a.tobytes() == b.tobytes() for a, b in zip((rec_first, face_first, recs, verts, idx), again))
+    nf = (recs["packed"] >> 24).astype(np.int64)
+    mask = ((recs["packed"] >> 16) & 0xFF).astype(np.uint8)
+    assert int(nf.sum()) == info["n_faces"] == int(face_first[-1]) and int(rec_first[-1]) == info["n_recs"]
+    assert np.array_equal(nf, np.unpackbits(mask[:, None], axis=1).sum(axis=1))
+    assert np.array_equal(recs["first_face"].astype(np.int64), np.concatenate([[0], np.cumsum(nf)[:-1]]))
+    k = np.arange(info["n_faces"]) - np.repeat(recs["first_face"].astype(np.int64), nf)     # ordinal in voxel
+    want_idx = (np.array([0, 1, 2, 0, 2, 3])[None, :] + 4 * k[:, None]).astype(np.uint16).ravel()
+    assert np.array_equal(idx, want_idx)
+    centre = np.stack([recs["gx"].astype(np.int64) - 1_000_000, recs["gy"].astype(np.int64) - 1_000_000,
+                       (recs["packed"] & 0xFF).astype(np.int64)], axis=1).astype(np.float32)
+    per_vertex_centre = np.repeat(centre, 4 * nf, axis=0)
+    assert np.abs(verts["position"] - per_vertex_centre).max() == 0.5
+    assert (verts["color"] == 255).all() and (np.abs(verts["normal"]).sum(axis=1) == 1).all()
+    # the oracle's face count for a 1 024-area sample of the region (serial CPU meshing is slow)
+    world = oracle.World(ax0 - 1, ay0 - 1, nx + 2, ny + 2, ovox, omh)
+    pick = np.random.default_rng(2).choice(len(inner), 1024, replace=False)
+    for i in pick:
+        assert world.mesh_area(int(inner[i][0]), int(inner[i][1])) == int(face_first[i + 1] - face_first[i])

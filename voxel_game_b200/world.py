@@ -24,7 +24,9 @@ def spawn_region(n: int) -> tuple[int, int, int, int]:
 def render_zone(center: tuple[int, int], render_size: int) -> np.ndarray:
     """get_render_zone (active_zone.rs:10-32): square of side 2r+1, x outer, y inner."""
     r = int(render_size)
-    out = [(center[0] + x, center[1] + y) for x in range(-r, r + 1) for y in range(-r, r + 1)]
+    # `(area_location.x as i32 + x) as u32`: wraps below zero like the reference
+    out = [((center[0] + x) & 0xFFFFFFFF, (center[1] + y) & 0xFFFFFFFF)
+           for x in range(-r, r + 1) for y in range(-r, r + 1)]
     return np.asarray(out, dtype=np.uint32)
 
 
