@@ -291,11 +291,13 @@ def test_edit_storm_batched_equals_sequential(seed):
         c.generate(vg.region_xy(ax0 - 1, ay0 - 1, n + 2, n + 2), read=False)
         c.mesh(inner)
         edits = _edit_storm(0x5EEDED17, 3000, ax0, ay0, n, world)
-        # force duplicates inside one batch: the last writer must win
-        edits[1500:1510] = edits[1499]
-        edits[1505]["voxel"] = oracle.V["Brick"]
-        for e in edits[1500:1510]:
+        # duplicates inside one batch: the last writer must win
+        dup = np.repeat(edits[1499:1500], 10)
+        dup[5]["voxel"] = oracle.V["Glass"]
+        dup[9]["voxel"] = oracle.V["Brick"]
+        for e in dup:
             world.apply_edit(int(e["gx"]), int(e["gy"]), int(e["gz"]), int(e["voxel"]))
+        edits = np.concatenate([edits, dup])
         dirty_all = set()
         for lo in range(0, len(edits), 1000):
             d = c.apply_edits(edits[lo:lo + 1000])
