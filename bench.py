@@ -35,8 +35,8 @@ REF_SAMPLE = 32        # --impl reference: 32x32 areas per step
 WORLD_NAME = "test"    # the reference's own test seed (generator.rs:157)
 
 # algorithmic work per unit (DESIGN.md "Roofline accounting")
-F2_OPS = 61            # f64 add/mul per 2-D simplex octave as issued by the kernel
-F3_OPS = 91            # f64 add/mul per 3-D simplex octave
+F2_OPS = 60            # f64 add/mul issued per 2-D simplex octave incl. the Fbm accumulate
+F3_OPS = 89            # f64 add/mul issued per 3-D simplex octave incl. the Fbm accumulate
 AREA_BYTES = 32768 + 256
 
 

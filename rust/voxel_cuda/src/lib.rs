@@ -1,0 +1,219 @@
+//! Rust side of the drop-in boundary: `extern "C"` bindings of `include/voxel_cuda.h` plus the
+//! thin safe layer the reference's call sites use.
+//!
+//! NOT COMPILED IN THE BUILD IMAGE (no cargo/rustc there); kept in sync with the header by hand and
+//! exercised through the same C ABI by the C++ mirror (`voxel_game_b200/host/`) and the Python
+//! tests.  See INTEGRATION.md for the three reference functions whose bodies call into this.
+//!
+//! There is deliberately no CPU fallback: if `Pipeline::new` fails the game cannot generate terrain.
+#![allow(non_camel_case_types)]
+
+use std::ffi::{c_char, c_int, c_void, CStr};
+
+pub const VOXELS_IN_AREA: usize = 32768; // model/area.rs:9
+pub const COLUMNS_IN_AREA: usize = 256;
+
+#[repr(C)]
+pub struct vx_ctx {
+    _private: [u8; 0],
+}
+
+/// One visible voxel = key + value of `RenderArea.mesh_map` (graphics/renderer.rs:45-51).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct vx_voxel_rec {
+    pub gx: u32,
+    pub gy: u32,
+    /// gz | voxel << 8 | face_mask << 16 | n_faces << 24
+    pub packed: u32,
+    pub first_face: u32,
+}
+
+/// `World::set(location, voxel)` (model/world.rs:184-191).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct vx_edit {
+    pub gx: u32,
+    pub gy: u32,
+    pub gz: u32,
+    pub voxel: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct vx_mesh_info {
+    pub n_faces: u64,
+    pub n_recs: u64,
+    pub vertex_bytes: u64,
+    pub index_bytes: u64,
+    pub rec_bytes: u64,
+}
+
+/// macroquad::ui::Vertex is `#[repr(C)] { position: Vec3, uv: Vec2, color: [u8; 4], normal: Vec4 }`
+/// with glam's scalar-math feature = 40 bytes; the GPU writes exactly these bytes.
+pub const VERTEX_BYTES: usize = 40;
+
+#[link(name = "voxel_cuda")]
+extern "C" {
+    pub fn vx_device_count() -> c_int;
+    pub fn vx_create(device: c_int, out: *mut *mut vx_ctx) -> c_int;
+    pub fn vx_destroy(ctx: *mut vx_ctx);
+    pub fn vx_strerror(status: c_int) -> *const c_char;
+    pub fn vx_last_error(ctx: *mut vx_ctx) -> *const c_char;
+    pub fn vx_set_stream(ctx: *mut vx_ctx, cuda_stream: *mut c_void) -> c_int;
+    pub fn vx_sync(ctx: *mut vx_ctx) -> c_int;
+    pub fn vx_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn vx_host_free(p: *mut c_void);
+    pub fn vx_set_seed(ctx: *mut vx_ctx, seed: u64) -> c_int;
+    pub fn vx_hash_world_name(world_name: *const c_char) -> u64;
+    pub fn vx_generate(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, voxels_out: *mut u8,
+                       max_height_out: *mut u8) -> c_int;
+    pub fn vx_upload(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, voxels: *const u8,
+                     max_height_out: *mut u8) -> c_int;
+    pub fn vx_read_areas(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, voxels_out: *mut u8,
+                         max_height_out: *mut u8) -> c_int;
+    pub fn vx_unload(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int) -> c_int;
+    pub fn vx_resident_count(ctx: *mut vx_ctx) -> c_int;
+    pub fn vx_column_heights(ctx: *mut vx_ctx, voxels: *const u8, n: c_int, max_height_out: *mut u8) -> c_int;
+    pub fn vx_mesh(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, info: *mut vx_mesh_info) -> c_int;
+    pub fn vx_mesh_read(ctx: *mut vx_ctx, rec_first: *mut u32, face_first: *mut u32,
+                        recs: *mut vx_voxel_rec, vertices: *mut c_void, indices: *mut u16) -> c_int;
+    pub fn vx_apply_edits(ctx: *mut vx_ctx, edits: *const vx_edit, n: c_int, dirty_area_xy: *mut u32,
+                          n_dirty: *mut c_int) -> c_int;
+    pub fn vx_heightmap(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, cam_area_x: u32,
+                        cam_area_y: u32, rgba: *mut u8) -> c_int;
+    pub fn vx_light(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, light_out: *mut u8,
+                    iterations: *mut c_int) -> c_int;
+}
+
+#[derive(Debug)]
+pub struct VxError {
+    pub status: i32,
+    pub message: String,
+}
+
+/// Owns one `vx_ctx` (one CUDA device).  `Send + Sync`: the C side locks internally, which is
+/// what lets `AreaLoader`'s rayon workers share it (service/persistence/world_persistence.rs:90-93).
+pub struct Pipeline {
+    ctx: *mut vx_ctx,
+}
+unsafe impl Send for Pipeline {}
+unsafe impl Sync for Pipeline {}
+
+/// Flat mesh of a batch of areas; `recs[rec_first[i]..rec_first[i + 1]]` belong to area `i`.
+pub struct MeshBatch {
+    pub rec_first: Vec<u32>,
+    pub face_first: Vec<u32>,
+    pub recs: Vec<vx_voxel_rec>,
+    /// 4 vertices per face, `VERTEX_BYTES` each, byte-identical to `macroquad::ui::Vertex`
+    pub vertices: Vec<u8>,
+    /// 6 per face: `[0,1,2,0,2,3] + 4 * (face ordinal inside its voxel)`
+    pub indices: Vec<u16>,
+}
+
+impl Pipeline {
+    /// `world_name` is the seed, exactly as in `AreaGenerator::generate_area(_, world_name)`.
+    pub fn new(device: i32, world_name: &str) -> Result<Self, VxError> {
+        let mut ctx = std::ptr::null_mut();
+        let st = unsafe { vx_create(device, &mut ctx) };
+        if st != 0 {
+            return Err(VxError { status: st, message: strerror(st) });
+        }
+        let p = Pipeline { ctx };
+        // hash_world_name stays in Rust (std DefaultHasher, generator.rs:24-28) so that the seed is
+        // whatever the running std produces; vx_hash_world_name is for non-Rust hosts.
+        p.check(unsafe { vx_set_seed(p.ctx, hash_world_name(world_name)) })?;
+        Ok(p)
+    }
+
+    fn check(&self, st: c_int) -> Result<(), VxError> {
+        if st == 0 {
+            return Ok(());
+        }
+        let message = unsafe { CStr::from_ptr(vx_last_error(self.ctx)) }.to_string_lossy().into_owned();
+        Err(VxError { status: st, message })
+    }
+
+    /// Body of `AreaLoader::load_all_blocking` for the areas that are not on disk: returns, per
+    /// area, the 32 768 voxel bytes and the 256 column heights.
+    pub fn generate(&self, areas: &[(u32, u32)]) -> Result<(Vec<u8>, Vec<u8>), VxError> {
+        let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
+        let mut voxels = vec![0u8; areas.len() * VOXELS_IN_AREA];
+        let mut heights = vec![0u8; areas.len() * COLUMNS_IN_AREA];
+        self.check(unsafe {
+            vx_generate(self.ctx, xy.as_ptr(), areas.len() as c_int, voxels.as_mut_ptr(), heights.as_mut_ptr())
+        })?;
+        Ok((voxels, heights))
+    }
+
+    /// Areas read from disk (`read_binary_object` hit in `load_blocking`): make them resident and
+    /// get their column heights (`AreaDTO::into_area`).
+    pub fn upload(&self, areas: &[(u32, u32)], voxels: &[u8]) -> Result<Vec<u8>, VxError> {
+        assert_eq!(voxels.len(), areas.len() * VOXELS_IN_AREA);
+        let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
+        let mut heights = vec![0u8; areas.len() * COLUMNS_IN_AREA];
+        self.check(unsafe {
+            vx_upload(self.ctx, xy.as_ptr(), areas.len() as c_int, voxels.as_ptr(), heights.as_mut_ptr())
+        })?;
+        Ok(heights)
+    }
+
+    pub fn unload(&self, areas: &[(u32, u32)]) -> Result<(), VxError> {
+        let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
+        self.check(unsafe { vx_unload(self.ctx, xy.as_ptr(), areas.len() as c_int) })
+    }
+
+    /// Body of `Renderer::load_all_blocking` / `load_areas_in_queue`.
+    pub fn mesh(&self, areas: &[(u32, u32)]) -> Result<MeshBatch, VxError> {
+        let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
+        let mut info = vx_mesh_info::default();
+        self.check(unsafe { vx_mesh(self.ctx, xy.as_ptr(), areas.len() as c_int, &mut info) })?;
+        let mut m = MeshBatch {
+            rec_first: vec![0; areas.len() + 1],
+            face_first: vec![0; areas.len() + 1],
+            recs: vec![vx_voxel_rec::default(); info.n_recs as usize],
+            vertices: vec![0u8; info.vertex_bytes as usize],
+            indices: vec![0u16; info.n_faces as usize * 6],
+        };
+        self.check(unsafe {
+            vx_mesh_read(self.ctx, m.rec_first.as_mut_ptr(), m.face_first.as_mut_ptr(), m.recs.as_mut_ptr(),
+                         m.vertices.as_mut_ptr() as *mut c_void, m.indices.as_mut_ptr())
+        })?;
+        Ok(m)
+    }
+
+    /// Batched `World::set`; returns the areas whose meshes must be rebuilt with `mesh`.
+    pub fn apply_edits(&self, edits: &[vx_edit]) -> Result<Vec<(u32, u32)>, VxError> {
+        let mut dirty = vec![0u32; edits.len().max(1) * 6];
+        let mut n: c_int = 0;
+        self.check(unsafe {
+            vx_apply_edits(self.ctx, edits.as_ptr(), edits.len() as c_int, dirty.as_mut_ptr(), &mut n)
+        })?;
+        Ok(dirty.chunks(2).take(n as usize).map(|c| (c[0], c[1])).collect())
+    }
+
+    /// Pixel loop of `HeightMap::generate_height_map`; `rgba` is the persistent 512x512 image.
+    pub fn heightmap(&self, areas: &[(u32, u32)], cam: (u32, u32), rgba: &mut [u8]) -> Result<(), VxError> {
+        assert_eq!(rgba.len(), 512 * 512 * 4);
+        let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
+        self.check(unsafe { vx_heightmap(self.ctx, xy.as_ptr(), areas.len() as c_int, cam.0, cam.1, rgba.as_mut_ptr()) })
+    }
+}
+
+impl Drop for Pipeline {
+    fn drop(&mut self) {
+        unsafe { vx_destroy(self.ctx) }
+    }
+}
+
+fn strerror(st: c_int) -> String {
+    unsafe { CStr::from_ptr(vx_strerror(st)) }.to_string_lossy().into_owned()
+}
+
+/// service/area_generation/generator.rs:24-28, unchanged.
+pub fn hash_world_name(world_name: &str) -> u64 {
+    use std::hash::{DefaultHasher, Hash, Hasher};
+    let mut hasher = DefaultHasher::new();
+    world_name.hash(&mut hasher);
+    hasher.finish()
+}

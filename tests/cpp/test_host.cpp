@@ -1,0 +1,123 @@
+// test_host.cpp -- the reference's own unit tests for the hot path, restated against the C++ host
+// mirror (voxel_game_b200/host/voxel_game.hpp) and therefore against the CUDA path through the C
+// ABI.  Needs a GPU; built and run by tests/test_gpu_parity.py::test_cpp_host_mirror.
+//   generator.rs:155-220   test_generate_area, _different_locations, _different_seeds, _same_area,
+//                          _heights_calculated_correctly
+//   world.rs:288-336       test_get_same_location, test_get_renderable_locations_for_area (structural)
+//   renderer                face count bookkeeping, edits through World::set + update_location
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+
+#include "../../voxel_game_b200/host/voxel_game.hpp"
+
+using namespace voxel_game;
+
+#define CHECK(cond)                                                          \
+    do {                                                                     \
+        if (!(cond)) {                                                       \
+            std::fprintf(stderr, "CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            std::exit(1);                                                    \
+        }                                                                    \
+    } while (0)
+
+static bool areas_differ(const Area& a, const Area& b) {  // generator.rs:222-243
+    return a.voxels() != b.voxels() || a.max_height() != b.max_height();
+}
+
+int main() {
+    auto p = std::make_shared<Pipeline>(0, "test");
+
+    // test_generate_area (generator.rs:155-179)
+    Area area = AreaGenerator::generate_area(*p, {123, 456});
+    CHECK(area.has_changed && area.get_x() == 123 && area.get_y() == 456);
+    for (uint32_t x = 0; x < AREA_SIZE; ++x)
+        for (uint32_t y = 0; y < AREA_SIZE; ++y) {
+            int max_height = -1;
+            bool contains_stone = false;
+            for (uint32_t z = 0; z < AREA_HEIGHT; ++z) {
+                const Voxel v = area.get({x, y, z});
+                if (!is_transparent(v) && max_height < 0) max_height = static_cast<int>(z);
+                if (v == Voxel::Stone) contains_stone = true;
+            }
+            CHECK(max_height >= 0);
+            CHECK(contains_stone);
+            CHECK(max_height == area.sample_height(x, y));
+        }
+
+    // test_generate_area_different_locations / _different_seeds / _same_area (generator.rs:181-200)
+    CHECK(areas_differ(area, AreaGenerator::generate_area(*p, {999, 400})));
+    {
+        Pipeline p1(0, "test1"), p2(0, "test2");
+        CHECK(areas_differ(AreaGenerator::generate_area(p1, {123, 456}), AreaGenerator::generate_area(p2, {123, 456})));
+    }
+    CHECK(!areas_differ(area, AreaGenerator::generate_area(*p, {123, 456})));
+
+    // test_genearate_area_heights_calculated_correctly (generator.rs:202-220)
+    for (uint32_t x = 0; x < 10; ++x) {
+        Area a = AreaGenerator::generate_area(*p, {x, 123});
+        Area b = a;
+        b.update_all_column_heights(*p);
+        CHECK(!areas_differ(a, b));
+    }
+
+    // World: get is stable (world.rs:302-316), batch load == single loads
+    World world(p);
+    std::vector<AreaLocation> zone;
+    for (uint32_t x = 62498; x < 62503; ++x)
+        for (uint32_t y = 62498; y < 62503; ++y) zone.push_back({x, y});
+    world.load_all_blocking(zone);
+    CHECK(world.get_loaded_areas_count() == 25);
+    CHECK(!areas_differ(world.get_area_without_loading({62500, 62500}), AreaGenerator::generate_area(*p, {62500, 62500})));
+    const InternalLocation probe = Location{3, 5, 100}.to_internal();
+    CHECK(world.get(probe) == world.get(probe));
+
+    // Renderer: every mesh entry is a non-None voxel of its area with 1..6 faces, 4 vertices and 6
+    // indices per face (renderer.rs:126-219); face count bookkeeping (:455-461)
+    Renderer renderer;
+    std::vector<AreaLocation> inner;
+    for (uint32_t x = 62499; x < 62502; ++x)
+        for (uint32_t y = 62499; y < 62502; ++y) inner.push_back({x, y});
+    renderer.load_all_blocking(world, inner);
+    size_t faces = 0;
+    for (const auto& kv : renderer.meshes())
+        for (const auto& m : kv.second.mesh_map) {
+            const MeshInfo& mi = m.second;
+            CHECK(mi.voxel != Voxel::None && mi.face_count >= 1 && mi.face_count <= 6);
+            CHECK(mi.mesh.vertices.size() == 4u * mi.face_count && mi.mesh.indices.size() == 6u * mi.face_count);
+            CHECK(world.get({m.first.x, m.first.y, m.first.z}) == mi.voxel);
+            CHECK(mi.mesh.indices[0] == 0 && mi.mesh.indices[5] == 3);
+            faces += mi.face_count;
+        }
+    CHECK(faces > 0 && faces == renderer.get_voxel_face_count());
+    const size_t before = renderer.get_voxel_face_count();
+    renderer.load_all_blocking(world, inner);  // already meshed: no-op (renderer.rs:311)
+    CHECK(renderer.get_voxel_face_count() == before);
+
+    // edit: place a Lamp in the air near the spawn point, then break it again
+    const InternalLocation lamp_at = Location{5, 6, 20}.to_internal();  // interior column of area (62500, 62500)
+    CHECK(world.get(lamp_at) == Voxel::None);
+    auto dirty = world.set_batch({{lamp_at, Voxel::Lamp}});
+    CHECK(dirty.size() == 1 && dirty[0] == (AreaLocation{62500, 62500}));
+    CHECK(world.get(lamp_at) == Voxel::Lamp);
+    CHECK(world.get_height(lamp_at) == 20);
+    renderer.update_locations(world, dirty);
+    CHECK(renderer.get_voxel_face_count() == before + 6);  // a lone block has six faces
+    CHECK(renderer.meshes().at({62500, 62500}).lights.size() == 1);
+    dirty = world.set_batch({{lamp_at, Voxel::None}});
+    renderer.update_locations(world, dirty);
+    CHECK(renderer.get_voxel_face_count() == before);
+    CHECK(renderer.meshes().at({62500, 62500}).lights.empty());
+    CHECK(world.get_height(lamp_at) > 20);
+
+    // error behaviour: an unknown device has no CPU fallback
+    bool threw = false;
+    try {
+        Pipeline bad(1000, "test");
+    } catch (const VxError& e) {
+        threw = e.status == VX_ERR_INVALID || e.status == VX_ERR_NO_DEVICE;
+    }
+    CHECK(threw);
+    std::printf("test_host: all checks passed (%zu faces over %zu areas)\n", before, inner.size());
+    return 0;
+}

@@ -371,3 +371,58 @@ def test_full_size_128x128_properties(seed):
     pick = np.random.default_rng(2).choice(len(inner), 1024, replace=False)
     for i in pick:
         assert world.mesh_area(int(inner[i][0]), int(inner[i][1])) == int(face_first[i + 1] - face_first[i])
+
+
+def test_cpp_host_mirror(tmp_path):
+    """The reference's own generator/world/renderer unit tests, restated in C++ against the host
+    mirror (voxel_game_b200/host/voxel_game.hpp) that sits on the C ABI: tests/cpp/test_host.cpp."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_host")
+    libdir = os.path.join(root, "voxel_game_b200")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-o", exe, os.path.join(root, "tests", "cpp", "test_host.cpp"),
+                    "-L" + libdir, "-lvoxel_cuda", "-Wl,-rpath," + libdir], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
+
+
+def test_light_extension_equals_flood_fill(seed):
+    """L-ext (EXTENSION, no reference counterpart -- SURVEY.md F3): the CUDA relaxation reaches the
+    same fixed point as the oracle's sequential BFS flood fill (oracle/light_ext.c) over a 5x5 grid
+    with caves, tree canopies, and lamps placed underground and next to area borders."""
+    n, ax0, ay0 = 5, 62470, 62500
+    world = oracle.World.generate(seed, ax0, ay0, n, n)
+    xy = vg.region_xy(ax0, ay0, n, n)
+    lamps = [(ax0 * 16 + 40, ay0 * 16 + 40, 100), (ax0 * 16 + 15, ay0 * 16 + 33, 90), (ax0 * 16 + 16, ay0 * 16 + 70, 110),
+             (ax0 * 16 + 79, ay0 * 16 + 79, 60), (ax0 * 16 + 1, ay0 * 16 + 1, 120)]
+    edits = np.zeros(len(lamps) * 2, vg.EDIT_DTYPE)
+    for i, (gx, gy, gz) in enumerate(lamps):
+        edits[2 * i] = (gx, gy, gz, oracle.V["Lamp"])
+        edits[2 * i + 1] = (gx, gy, gz - 1, 0)            # a pocket of air above the lamp
+    for e in edits:
+        world.apply_edit(int(e["gx"]), int(e["gy"]), int(e["gz"]), int(e["voxel"]))
+    want = world.light_flood()
+    with vg.Context(0, seed=seed) as c:
+        c.generate(xy, read=False)
+        c.apply_edits(edits)
+        got, iters = c.light(xy)
+    assert 1 <= iters < 64
+    assert np.array_equal(got, want), f"{(got != want).sum()} light values differ"
+    assert (want == 15).any() and ((want > 0) & (want < 15)).sum() > 500    # real gradients exist
+
+
+def test_contexts_with_different_seeds_do_not_interfere():
+    """Two contexts (two worlds) in one process, calls interleaved: each keeps its own noise tables
+    (they travel as a kernel parameter, not as a module-wide __constant__ symbol)."""
+    s1, s2 = oracle.hash_world_name("test1"), oracle.hash_world_name("test2")
+    xy = vg.region_xy(123, 456, 2, 2)
+    with vg.Context(0, seed=s1) as c1, vg.Context(0, seed=s2) as c2:
+        a1, _ = c1.generate(xy)
+        a2, _ = c2.generate(xy)
+        b1, _ = c1.generate(xy)
+    o1, _, _, _ = oracle.generate_areas(s1, xy)
+    o2, _, _, _ = oracle.generate_areas(s2, xy)
+    assert np.array_equal(a1, o1) and np.array_equal(b1, o1) and np.array_equal(a2, o2)
+    assert not np.array_equal(o1, o2)

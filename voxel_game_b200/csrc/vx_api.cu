@@ -156,7 +156,7 @@ struct vx_ctx {
     PinnedBuf h_small;   // small results coming back
     DevBuf d_jobs, d_list, d_missing, d_cave_items, d_counters, d_rec_count, d_face_count;
     DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
-    DevBuf d_heightmap;
+    DevBuf d_heightmap, d_light, d_slot_to_job;
     bool heightmap_init = false;
 
     // last mesh
@@ -369,12 +369,12 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
     unsigned long long* stats = ctx->d_counters.as<unsigned long long>() + 2;  // bytes 16..39
     {
         ScopedTimer t(ctx, TM_GEN_COLUMNS);
-        launch_gen_columns(jobs, n, ctx->d_voxels, ctx->d_heights, ctx->d_slot_xy,
+        launch_gen_columns(ctx->tables, jobs, n, ctx->d_voxels, ctx->d_heights, ctx->d_slot_xy,
                            ctx->d_cave_items.as<uint32_t>(), cave_count, stats, ctx->stream);
     }
     {
         ScopedTimer t(ctx, TM_GEN_CAVES);
-        launch_gen_caves(ctx->d_cave_items.as<uint32_t>(), cave_count, ctx->d_voxels, ctx->d_heights,
+        launch_gen_caves(ctx->tables, ctx->d_cave_items.as<uint32_t>(), cave_count, ctx->d_voxels, ctx->d_heights,
                          ctx->d_slot_xy, stats, ctx->sm_count, ctx->stream);
     }
     {
@@ -452,7 +452,7 @@ void vx_destroy(vx_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters,
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
-                      &ctx->d_heightmap, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
+                      &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
                       &ctx->d_vertices, &ctx->d_indices};
     for (DevBuf* b : bufs) b->release();
     ctx->h_stage.release();
@@ -517,8 +517,6 @@ int vx_set_seed(vx_ctx* ctx, uint64_t seed) {
     VX_CUDA(cudaSetDevice(ctx->device));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     build_noise_tables(seed, &ctx->tables);
-    VX_CUDA(upload_noise_tables(ctx->tables, ctx->stream));
-    VX_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->has_seed = true;
     return VX_OK;
 }
@@ -850,9 +848,54 @@ int vx_heightmap(vx_ctx* ctx, const uint32_t* area_xy, int n, uint32_t cam_area_
 }
 
 int vx_light(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* light_out, int* iterations) {
-    (void)area_xy; (void)n; (void)light_out; (void)iterations;
-    if (!ctx) return VX_ERR_INVALID;
-    return fail(ctx, VX_ERR_INVALID, "vx_light: not built yet");
+    if (!ctx || n < 0 || (n > 0 && (!area_xy || !light_out))) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    reset_timers(ctx);
+    if (iterations) *iterations = 0;
+    if (n == 0) return VX_OK;
+    std::vector<int> slots(n);
+    for (int i = 0; i < n; ++i) {
+        slots[i] = host_slot(ctx, area_xy[2 * i], area_xy[2 * i + 1]);
+        if (slots[i] < 0) return fail(ctx, VX_ERR_NOT_LOADED, "vx_light: area not resident");
+    }
+    int st;
+    if ((st = upload_map(ctx)) != VX_OK) return st;
+    if ((st = upload_jobs(ctx, area_xy, slots, n)) != VX_OK) return st;
+    const size_t bytes = (size_t)n * VOXELS_IN_AREA;
+    VX_CUDA(ctx->d_light.ensure(bytes));
+    VX_CUDA(ctx->d_slot_to_job.ensure((size_t)ctx->capacity * sizeof(int32_t)));
+    VX_CUDA(ctx->d_counters.ensure(64));
+    VX_CUDA(ctx->h_small.ensure(64));
+    VX_CUDA(cudaMemsetAsync(ctx->d_slot_to_job.p, 0xFF, (size_t)ctx->capacity * sizeof(int32_t), ctx->stream));
+    uint32_t* flag = ctx->d_counters.as<uint32_t>();
+    uint32_t* host_flag = ctx->h_small.as<uint32_t>();
+    const uint4* jobs = ctx->d_jobs.as<uint4>();
+    int iters = 0;
+    {
+        ScopedTimer t(ctx, TM_LIGHT);
+        launch_light_init(jobs, n, ctx->d_voxels, ctx->d_heights, ctx->d_light.as<uint8_t>(),
+                          ctx->d_slot_to_job.as<int32_t>(), ctx->stream);
+        ctx->timings.other_launches += 2;
+        // levels travel at most 15 voxels, i.e. across at most one area border per launch pair;
+        // the bound below is generous and only guards against a logic error
+        for (; iters < 64; ++iters) {
+            VX_CUDA(cudaMemsetAsync(flag, 0, 4, ctx->stream));
+            launch_light_relax(jobs, n, ctx->d_voxels, device_map(ctx), ctx->d_slot_to_job.as<int32_t>(),
+                               ctx->d_light.as<uint8_t>(), flag, ctx->stream);
+            ctx->timings.other_launches += 1;
+            VX_CUDA(cudaMemcpyAsync(host_flag, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            VX_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (*host_flag == 0) {
+                ++iters;
+                break;
+            }
+        }
+    }
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaMemcpyAsync(light_out, ctx->d_light.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (iterations) *iterations = iters;
+    return sync_stream(ctx);
 }
 
 int vx_diag_fp64_rate(vx_ctx* ctx, double* gops_per_s, float* ms_out) {

@@ -20,11 +20,6 @@
 
 namespace vx {
 
-cudaError_t upload_noise_tables(const NoiseTables& t, cudaStream_t stream) {
-    return cudaMemcpyToSymbolAsync(c_noise, &t, sizeof(NoiseTables), 0, cudaMemcpyHostToDevice,
-                                   stream);
-}
-
 namespace {
 
 enum Biome { DRY = 0, WET = 1, COLD = 2 };
@@ -89,7 +84,8 @@ struct __align__(16) GenSmem {
     unsigned cave_base;
 };
 
-__global__ void __launch_bounds__(256) gen_columns_kernel(const uint4* __restrict__ jobs,
+__global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant__ NoiseTables nt,
+                                                          const uint4* __restrict__ jobs,
                                                           uint8_t* __restrict__ pool_voxels,
                                                           uint8_t* __restrict__ pool_heights,
                                                           uint2* __restrict__ slot_xy,
@@ -102,7 +98,7 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const uint4* __restric
     const uint32_t ax = job.x, ay = job.y, slot = job.z;
 
     for (int i = tid; i < VOXELS_IN_AREA / 16; i += 256) sm.vox[i] = make_uint4(0, 0, 0, 0);
-    load_noise_shared(&sm.noise, tid, 256);
+    load_noise_shared(&sm.noise, nt, tid, 256);
     if (tid == 0) {
         sm.cave_n = 0;
         slot_xy[slot] = make_uint2(ax, ay);
@@ -116,23 +112,23 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const uint4* __restric
     const double px = (double)(x + ax * AREA_SIZE), py = (double)(y + ay * AREA_SIZE);
 
     // TerrainTypeGenerator::sample (terrain_type.rs:26-32)
-    const double n1 = fbm2<FBM_HEIGHT1>(s, px, py), n2 = fbm2<FBM_HEIGHT2>(s, px, py);
+    const double n1 = fbm2<FBM_HEIGHT1>(nt, s, px, py), n2 = fbm2<FBM_HEIGHT2>(nt, s, px, py);
     double value = fmax(n1, n2);
     value = value < 0.1 ? 0.1 : (value > 1.0 ? 1.0 : value);
-    const double height_mod = 1.0 - (fbm2<FBM_HEIGHT_MOD>(s, px, py) + 1.0) / 2.0;
+    const double height_mod = 1.0 - (fbm2<FBM_HEIGHT_MOD>(nt, s, px, py) + 1.0) / 2.0;
     const unsigned H = f64_as_u32(height_mod * value * 0.55 * 128.0) + 32u;
     // CaveGenerator::is_cave_zone (cave_generator.rs:36-41)
-    const bool cave_zone = f64_as_i32(normalise(fbm2<FBM_CAVE_CHECK>(s, px, py))) >= 80;
+    const bool cave_zone = f64_as_i32(normalise(fbm2<FBM_CAVE_CHECK>(nt, s, px, py))) >= 80;
     // LakeGenerator::sample_lake_depth (lake_generator.rs:27-52)
     unsigned lake_depth = 0;
     unsigned evals2 = 16, evals3 = 0;  // simplex evaluations of this column (work accounting)
     if (!cave_zone && H <= LAKE_MAX_TERRAIN && H > LAKE_TOP_ZI) {
         evals2 += 2;
-        const int d = (f64_as_i32(normalise(fbm2<FBM_LAKE>(s, px, py))) - 70) / 3;
+        const int d = (f64_as_i32(normalise(fbm2<FBM_LAKE>(nt, s, px, py))) - 70) / 3;
         lake_depth = d < 2 ? 0u : (unsigned)d;
     }
     // BiomeTypeGenerator::sample (biome_type.rs:25-34)
-    const int b = f64_as_i32(normalise(fbm2<FBM_BIOME>(s, px, py)));
+    const int b = f64_as_i32(normalise(fbm2<FBM_BIOME>(nt, s, px, py)));
     const int biome = (b >= 0 && b < 20) ? DRY : ((b >= 20 && b < 80) ? WET : COLD);
 
     // The four topmost voxels first, in a loop all lanes walk together (k-th voxel from H - 3).
@@ -148,7 +144,7 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const uint4* __restric
         bool alt = false;
         if (need) {  // should_generate_alternative_voxel (voxel_type_generator.rs:176-188)
             evals3 += 2;
-            alt = normalise(fbm3<FBM_ALT>(s, px, py, (double)zi)) >= threshold;
+            alt = normalise(fbm3<FBM_ALT>(nt, s, px, py, (double)zi)) >= threshold;
         }
         tops |= (unsigned)surface_pick(biome, zi, H, alt) << (8 * k);
     }
@@ -197,7 +193,8 @@ struct CaveSmem {
     uint32_t first[CAVE_BATCH + 1];  // exclusive prefix of per-column voxel counts
 };
 
-__global__ void __launch_bounds__(256) gen_caves_kernel(const uint32_t* __restrict__ cave_items,
+__global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ NoiseTables nt,
+                                                        const uint32_t* __restrict__ cave_items,
                                                         const uint32_t* __restrict__ cave_count,
                                                         uint8_t* __restrict__ pool_voxels,
                                                         const uint8_t* __restrict__ pool_heights,
@@ -206,15 +203,15 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const uint32_t* __restri
     __shared__ CaveSmem sm;
     const int tid = threadIdx.x;
     {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_noise.t.perm[0][0]);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&nt.perm[0][0]);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.perm[0][0]);
         for (int i = tid; i < TAB_COUNT * 256 / 4; i += 256) dst[i] = src[i];
         for (int i = tid; i < TAB_COUNT * 256; i += 256)
-            (&sm.perm12[0][0])[i] = (uint8_t)((&c_noise.t.perm[0][0])[i] % 12u);
+            (&sm.perm12[0][0])[i] = (uint8_t)((&nt.perm[0][0])[i] % 12u);
     }
     const uint32_t n_items = *cave_count;
-    const FbmParams& q1 = c_noise.t.fbm[FBM_CAVE1];
-    const FbmParams& q2 = c_noise.t.fbm[FBM_CAVE2];
+    const FbmParams& q1 = nt.fbm[FBM_CAVE1];
+    const FbmParams& q2 = nt.fbm[FBM_CAVE2];
     const uint8_t* p1 = sm.perm[q1.table];
     const uint8_t* p2 = sm.perm[q2.table];
     const uint8_t* p1g = sm.perm12[q1.table];
@@ -483,18 +480,18 @@ __global__ void __launch_bounds__(256) fp64_rate_kernel(double* sink, int iters)
 
 }  // namespace
 
-void launch_gen_columns(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
+void launch_gen_columns(const NoiseTables& nt, const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
                         uint2* slot_xy, uint32_t* cave_items, uint32_t* cave_count,
                         unsigned long long* stats, cudaStream_t stream) {
     if (n <= 0) return;
-    gen_columns_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_heights, slot_xy, cave_items,
+    gen_columns_kernel<<<n, 256, 0, stream>>>(nt, jobs, pool_voxels, pool_heights, slot_xy, cave_items,
                                               cave_count, stats);
 }
 
-void launch_gen_caves(const uint32_t* cave_items, const uint32_t* cave_count, uint8_t* pool_voxels,
+void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const uint32_t* cave_count, uint8_t* pool_voxels,
                       const uint8_t* pool_heights, const uint2* slot_xy, unsigned long long* stats,
                       int sm_count, cudaStream_t stream) {
-    gen_caves_kernel<<<sm_count * 4, 256, 0, stream>>>(cave_items, cave_count, pool_voxels,
+    gen_caves_kernel<<<sm_count * 4, 256, 0, stream>>>(nt, cave_items, cave_count, pool_voxels,
                                                        pool_heights, slot_xy, stats);
 }
 

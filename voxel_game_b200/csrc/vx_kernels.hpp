@@ -10,16 +10,13 @@
 
 namespace vx {
 
-// ---- tables
-cudaError_t upload_noise_tables(const NoiseTables& t, cudaStream_t stream);
-
 // ---- generation (K1, K1b, K2) and column heights (L1)
 // jobs: n entries {area x, area y, slot, 0}
-void launch_gen_columns(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
+void launch_gen_columns(const NoiseTables& nt, const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
                         uint2* slot_xy, uint32_t* cave_items, uint32_t* cave_count,
                         unsigned long long* stats /* [3]: simplex2, alt simplex3, cave voxels */,
                         cudaStream_t stream);
-void launch_gen_caves(const uint32_t* cave_items, const uint32_t* cave_count,
+void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const uint32_t* cave_count,
                       uint8_t* pool_voxels, const uint8_t* pool_heights, const uint2* slot_xy,
                       unsigned long long* stats, int sm_count, cudaStream_t stream);
 void launch_gen_finish(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
@@ -63,8 +60,10 @@ void launch_heightmap(const uint2* area_xy, int n, AreaMap map, const uint8_t* p
                       uint32_t cam_ax, uint32_t cam_ay, uint32_t* rgba, cudaStream_t stream);
 
 // ---- L-ext
+// light: n * 32768 bytes in job order; slot_to_job must be filled with -1 (0xFF bytes) beforehand
 void launch_light_init(const uint4* jobs, int n, const uint8_t* pool_voxels,
-                       const uint8_t* pool_heights, uint8_t* light, cudaStream_t stream);
+                       const uint8_t* pool_heights, uint8_t* light, int32_t* slot_to_job,
+                       cudaStream_t stream);
 void launch_light_relax(const uint4* jobs, int n, const uint8_t* pool_voxels, AreaMap map,
                         const int32_t* slot_to_job, uint8_t* light, uint32_t* changed,
                         cudaStream_t stream);

@@ -21,10 +21,9 @@
 
 namespace vx {
 
-struct NoiseConst {
-    NoiseTables t;
-};
-__constant__ NoiseConst c_noise;  // this header is included by vx_gen.cu only
+// The per-seed tables travel as a __grid_constant__ kernel parameter (2 KiB, constant bank, one
+// copy per launch): contexts with different seeds in one process cannot disturb each other, which a
+// module-wide __constant__ symbol would allow.
 
 // 24 unit gradients at 7.5 deg + k*15 deg (digits as published with OpenSimplex2)
 __constant__ double c_grad2[24][2] = {
@@ -49,12 +48,13 @@ struct NoiseShared {
     double grad2[24][2];
 };
 
-__device__ __forceinline__ void load_noise_shared(NoiseShared* s, int tid, int nthreads) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_noise.t.perm[0][0]);
+__device__ __forceinline__ void load_noise_shared(NoiseShared* s, const NoiseTables& nt, int tid,
+                                                  int nthreads) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&nt.perm[0][0]);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&s->perm[0][0]);
     for (int i = tid; i < TAB_COUNT * 256 / 4; i += nthreads) dst[i] = src[i];
     for (int i = tid; i < TAB_COUNT * 256; i += nthreads) {
-        const unsigned v = (&c_noise.t.perm[0][0])[i];
+        const unsigned v = (&nt.perm[0][0])[i];
         (&s->perm24[0][0])[i] = (uint8_t)(v % 24u);
         (&s->perm12[0][0])[i] = (uint8_t)(v % 12u);
     }
@@ -159,8 +159,8 @@ __device__ __forceinline__ double simplex3(const uint8_t* p, const uint8_t* p12,
 }
 
 template <int ID>
-__device__ __forceinline__ double fbm2(const NoiseShared* s, double x, double y) {
-    const FbmParams& q = c_noise.t.fbm[ID];
+__device__ __forceinline__ double fbm2(const NoiseTables& nt, const NoiseShared* s, double x, double y) {
+    const FbmParams& q = nt.fbm[ID];
     const uint8_t* p = s->perm[q.table];
     const uint8_t* p24 = s->perm24[q.table];
     x *= q.frequency;
@@ -176,8 +176,9 @@ __device__ __forceinline__ double fbm2(const NoiseShared* s, double x, double y)
 }
 
 template <int ID>
-__device__ __forceinline__ double fbm3(const NoiseShared* s, double x, double y, double z) {
-    const FbmParams& q = c_noise.t.fbm[ID];
+__device__ __forceinline__ double fbm3(const NoiseTables& nt, const NoiseShared* s, double x, double y,
+                                       double z) {
+    const FbmParams& q = nt.fbm[ID];
     const uint8_t* p = s->perm[q.table];
     const uint8_t* p12 = s->perm12[q.table];
     x *= q.frequency;
