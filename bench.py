@@ -233,7 +233,7 @@ def main():
         for k in ("gen_columns_ms", "gen_caves_ms", "gen_finish_ms"):
             kern[k] = kern.get(k, 0.0) + t[k]
         launches += t["gen_launches"]
-        work = {k: t[k] for k in ("simplex2_evals", "simplex3_evals", "cave_voxels", "cave_columns")}
+        work = {k: t[k] for k in ("simplex2_evals", "simplex3_evals", "cave_voxels", "cave_columns", "cave_evals")}
         info = ctx.mesh(mesh_xy)
         t = ctx.timings()
         for k in ("mesh_count_ms", "mesh_emit_ms"):
@@ -293,7 +293,8 @@ def main():
     hbm_peak, hbm_src = measured_peaks()
     fp64_gops, _ = ctx.fp64_rate()
     s2, s3, cave_vox = work["simplex2_evals"], work["simplex3_evals"], work["cave_voxels"]
-    alt3 = s3 - 14 * cave_vox
+    cave3 = work["cave_evals"]  # cave octaves actually evaluated (early exit is exact)
+    alt3 = s3 - cave3
     mesh_bytes = n_mesh * 8192 + info["n_faces"] * 172 + info["n_recs"] * 17
     plane_bytes = n_gen * (32768 + 8192)
 
@@ -310,7 +311,7 @@ def main():
 
     rooflines = {
         "gen_columns": fp64_roof(s2 * F2_OPS + alt3 * F3_OPS, kern["gen_columns_ms"]),
-        "gen_caves": fp64_roof(14 * cave_vox * F3_OPS, kern["gen_caves_ms"]),
+        "gen_caves": fp64_roof(cave3 * F3_OPS, kern["gen_caves_ms"]),
         "gen_finish": hbm_roof(n_gen * 256 * 4, kern["gen_finish_ms"]),
         "mesh_count": hbm_roof(plane_bytes + n_mesh * 8192, kern["mesh_count_ms"]),
         "mesh_emit": hbm_roof(mesh_bytes, kern["mesh_emit_ms"]),
@@ -343,6 +344,7 @@ def main():
         "rooflines": rooflines,
         "kernel_ms_per_step": kern,
         "work_per_step": {"simplex2_octave_evals": s2, "simplex3_octave_evals": s3, "cave_voxels": cave_vox,
+                          "cave_octave_evals": cave3, "cave_octave_evals_without_early_exit": 14 * cave_vox,
                           "f64_ops": s2 * F2_OPS + s3 * F3_OPS},
     }
 

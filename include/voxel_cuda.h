@@ -98,6 +98,8 @@ typedef struct {
     /* work accounting of the last vx_generate (roofline numerators): octave-level simplex
      * evaluations executed and voxels that ran the cave noise */
     uint64_t simplex2_evals, simplex3_evals, cave_voxels;
+    uint64_t cave_evals; /* of simplex3_evals: cave-noise octaves evaluated (<= 14 per cave voxel:
+                            a voxel stops once the remaining octaves cannot change its verdict) */
 } vx_timings;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

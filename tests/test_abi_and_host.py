@@ -52,7 +52,7 @@ def test_struct_layouts_match_header():
     from voxel_game_b200.binding import MeshInfo, Timings
 
     assert C.sizeof(MeshInfo) == 40
-    assert C.sizeof(Timings) == 8 * 4 + 4 * 4 + 3 * 8
+    assert C.sizeof(Timings) == 8 * 4 + 4 * 4 + 4 * 8
 
 
 def test_no_gpu_means_loud_failure_not_cpu_fallback():

@@ -62,7 +62,7 @@ class Timings(C.Structure):
                 ("light_ms", C.c_float), ("gen_launches", C.c_uint32),
                 ("mesh_launches", C.c_uint32), ("other_launches", C.c_uint32),
                 ("cave_columns", C.c_uint32), ("simplex2_evals", C.c_uint64),
-                ("simplex3_evals", C.c_uint64), ("cave_voxels", C.c_uint64)]
+                ("simplex3_evals", C.c_uint64), ("cave_voxels", C.c_uint64), ("cave_evals", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

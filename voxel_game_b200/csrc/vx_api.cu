@@ -537,12 +537,13 @@ int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out
     if (max_height_out && (st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, max_height_out, true)) != VX_OK) return st;
     if ((st = sync_stream(ctx)) != VX_OK) return st;
     if (ctx->timing) {  // work accounting of this call (the roofline numerators)
-        unsigned long long c[5];
+        unsigned long long c[6];
         VX_CUDA(cudaMemcpy(c, ctx->d_counters.p, sizeof c, cudaMemcpyDeviceToHost));
         ctx->timings.cave_columns = (uint32_t)c[0];
         ctx->timings.simplex2_evals = c[2];
         ctx->timings.cave_voxels = c[4];
-        ctx->timings.simplex3_evals = c[3] + 14ull * c[4];
+        ctx->timings.simplex3_evals = c[3] + c[5];  // surface noise + cave octaves actually evaluated
+        ctx->timings.cave_evals = c[5];
     }
     return VX_OK;
 }

@@ -184,15 +184,36 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------- K1b
-constexpr int CAVE_BATCH = 64;  // cave columns per CTA iteration
+constexpr int CAVE_BATCH = 64;   // cave columns per CTA iteration
+// evaluation order of the 14 cave octaves, bit = 1 -> next octave of noise1 (6 octaves, weights
+// .553 .249 .112 .050 .023 .010), 0 -> next octave of noise2 (8 octaves, .650 .228 .080 .028 ...):
+// b0 a0 a1 b1 a2 b2 a3 b3 a4 b4 a5 b5 b6 b7
+constexpr unsigned CAVE_SCHEDULE = 0b00010101010110u;
 
 struct CaveSmem {
-    uint8_t perm[TAB_COUNT][256];
-    uint8_t perm12[TAB_COUNT][256];
+    uint8_t bytes[3 * TAB_BYTES];  // permutation tables and their reduced copies (vx_noise.cuh)
+    double amp[2][8];    // [0] = noise1, [1] = noise2: running amplitudes
+    double rest[2][9];   // bound of the octaves not yet evaluated (NoiseTables::cave_rest) + slack
     uint32_t item[CAVE_BATCH];
+    uint2 origin[CAVE_BATCH];        // global x, y of the column (refills must not wait on HBM)
     uint32_t first[CAVE_BATCH + 1];  // exclusive prefix of per-column voxel counts
+    uint32_t next;                   // next unclaimed voxel of the batch
+    uint32_t batch;                  // batch claimed by this CTA
 };
 
+// Max<Fbm, Fbm>::sample + threshold (cave_generator.rs:27-30,43-64) for every voxel of the listed
+// cave-zone columns:  cave  <=>  (70..90).contains(normalise(max(a, b)) as i32)  <=>  0.4 <= m < 0.8
+// up to rounding at the ends.
+//   * Exact early exit.  The 6 + 8 octaves are evaluated in order of decreasing weight (each Fbm
+//     keeps its own octave order, so its running sum is the crate's); after every octave the not
+//     yet evaluated ones are bounded by |simplex| <= SIMPLEX_BOUND, and a voxel stops as soon as
+//     the verdict can no longer change.  Undecided voxels run all 14 octaves and use the crate's
+//     expression, so the result never depends on the bound being tight, only on it being valid
+//     (slack 1e-9 against rounding).  ~4 of 14 octaves are needed on average.
+//   * Persistent lanes.  A lane that has decided its voxel claims the next one of the batch at
+//     once (shared-memory counter) instead of idling until the slowest lane of its warp is done:
+//     lanes of a warp sit at different octaves of different voxels, which costs nothing because
+//     the octave index only selects table rows.
 __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ NoiseTables nt,
                                                         const uint32_t* __restrict__ cave_items,
                                                         const uint32_t* __restrict__ cave_count,
@@ -202,23 +223,30 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
                                                         unsigned long long* __restrict__ stats) {
     __shared__ CaveSmem sm;
     const int tid = threadIdx.x;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&nt.perm[0][0]);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.perm[0][0]);
-        for (int i = tid; i < TAB_COUNT * 256 / 4; i += 256) dst[i] = src[i];
-        for (int i = tid; i < TAB_COUNT * 256; i += 256)
-            (&sm.perm12[0][0])[i] = (uint8_t)((&nt.perm[0][0])[i] % 12u);
-    }
-    const uint32_t n_items = *cave_count;
     const FbmParams& q1 = nt.fbm[FBM_CAVE1];
     const FbmParams& q2 = nt.fbm[FBM_CAVE2];
-    const uint8_t* p1 = sm.perm[q1.table];
-    const uint8_t* p2 = sm.perm[q2.table];
-    const uint8_t* p1g = sm.perm12[q1.table];
-    const uint8_t* p2g = sm.perm12[q2.table];
+    {
+        load_noise_tables(sm.bytes, nt, tid, 256);
+        if (tid < 8) {
+            sm.amp[0][tid] = tid < 6 ? q1.amp[tid] : 0.0;
+            sm.amp[1][tid] = q2.amp[tid];
+        }
+        if (tid < 18) (&sm.rest[0][0])[tid] = (&nt.cave_rest[0][0])[tid] + 1e-9;
+    }
+    const uint32_t n_items = *cave_count;
+    const unsigned t1 = (unsigned)q1.table * 256u, t2 = (unsigned)q2.table * 256u;  // table offsets
+    const double f1 = q1.frequency, f2 = q2.frequency, l1 = q1.lacunarity, l2 = q2.lacunarity;
+    const double n1 = q1.norm, n2 = q2.norm;
 
-    for (uint32_t batch = blockIdx.x; batch * CAVE_BATCH < n_items; batch += gridDim.x) {
-        __syncthreads();  // previous iteration done with sm.item / sm.first (and perm loaded)
+    // batches are handed out dynamically (global counter): with the early exit the cost of a batch
+    // varies several-fold, a static stride would leave most SMs waiting for the unluckiest CTA
+    unsigned* batch_counter = reinterpret_cast<unsigned*>(&stats[4]);
+    while (true) {
+        __syncthreads();  // previous iteration done with sm.item / sm.first (and tables loaded)
+        if (tid == 0) sm.batch = atomicAdd(batch_counter, 1u);
+        __syncthreads();
+        const uint32_t batch = sm.batch;
+        if ((unsigned long long)batch * CAVE_BATCH >= n_items) break;
         if (tid < CAVE_BATCH) {
             const uint32_t idx = batch * CAVE_BATCH + tid;
             uint32_t item = 0, cnt = 0;
@@ -231,8 +259,9 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
                 cnt = top >= CAVE_MIN_ZI ? top - CAVE_MIN_ZI + 1 : 0;
             }
             sm.item[tid] = item;
-            // inclusive scan over the 64 counts (two warps)
-            uint32_t v = cnt;
+            const uint2 axy = slot_xy[item >> 8];
+            sm.origin[tid] = make_uint2((item & 15u) + axy.x * AREA_SIZE, ((item >> 4) & 15u) + axy.y * AREA_SIZE);
+            uint32_t v = cnt;  // inclusive scan inside each warp
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
                 if ((tid & 31) >= d) v += o;
@@ -240,46 +269,76 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
             sm.first[tid + 1] = v;
         }
         __syncthreads();
-        if (tid >= 32 && tid < CAVE_BATCH) sm.first[tid + 1] += sm.first[32];
-        if (tid == 0) sm.first[0] = 0;
+        if (tid == 0) {  // stitch the four warp-local scans into one exclusive prefix
+            sm.first[0] = 0;
+            sm.next = 0;
+            uint32_t base = 0;
+            for (int i = 33; i <= CAVE_BATCH; ++i) {
+                if (((i - 1) & 31) == 0) base = sm.first[i - 1];  // already final
+                sm.first[i] += base;
+            }
+        }
         __syncthreads();
         const uint32_t total = sm.first[CAVE_BATCH];
         if (tid == 0) atomicAdd(&stats[2], (unsigned long long)total);  // cave voxels evaluated
 
-        for (uint32_t w = tid; w < total; w += 256) {
-            // column c with first[c] <= w < first[c+1]
-            int lo = 0, hi = CAVE_BATCH;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (sm.first[mid] <= w) lo = mid; else hi = mid;
+        unsigned my_evals = 0;
+        bool busy = false;
+        double xa = 0, ya = 0, za = 0, xb = 0, yb = 0, zb = 0, a = 0, bsum = 0;
+        unsigned step = 0, ka = 0, kb = 0;
+        size_t out_index = 0;
+        while (true) {
+            if (!busy) {
+                const uint32_t w = atomicAdd(&sm.next, 1u);
+                if (w >= total) break;
+                int lo = 0, hi = CAVE_BATCH;  // column with first[lo] <= w < first[lo + 1]
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sm.first[mid] <= w) lo = mid; else hi = mid;
+                }
+                const uint32_t item = sm.item[lo];
+                const unsigned zi = CAVE_MIN_ZI + (w - sm.first[lo]);
+                const uint32_t slot = item >> 8, col = item & 255u;
+                const uint2 gxy = sm.origin[lo];
+                const double px = (double)gxy.x, py = (double)gxy.y, pz = (double)zi;
+                xa = px * f1; ya = py * f1; za = pz * f1;
+                xb = px * f2; yb = py * f2; zb = pz * f2;
+                a = 0.0; bsum = 0.0;
+                step = 0; ka = 0; kb = 0;
+                out_index = (size_t)slot * VOXELS_IN_AREA + col + 256u * (AREA_HEIGHT - zi);
+                busy = true;
             }
-            const uint32_t item = sm.item[lo];
-            const unsigned zi = CAVE_MIN_ZI + (w - sm.first[lo]);
-            const uint32_t slot = item >> 8, col = item & 255u;
-            const uint2 axy = slot_xy[slot];
-            const double px = (double)((col & 15u) + axy.x * AREA_SIZE);
-            const double py = (double)((col >> 4) + axy.y * AREA_SIZE);
-            const double pz = (double)zi;
-
-            // Max<Fbm, Fbm>::sample (cave_generator.rs:27-30,61)
-            double xa = px * q1.frequency, ya = py * q1.frequency, za = pz * q1.frequency, a = 0.0;
-#pragma unroll 1
-            for (int o = 0; o < 6; ++o) {
-                a += q1.amp[o] * simplex3(p1, p1g, xa, ya, za);
-                xa *= q1.lacunarity; ya *= q1.lacunarity; za *= q1.lacunarity;
+            const bool is_a = (CAVE_SCHEDULE >> step) & 1u;
+            const double sv = simplex3(sm.bytes, is_a ? t1 : t2, is_a ? xa : xb, is_a ? ya : yb,
+                                       is_a ? za : zb);
+            ++my_evals;
+            ++step;
+            if (is_a) {
+                a += sm.amp[0][ka] * sv;
+                xa *= l1; ya *= l1; za *= l1;
+                ++ka;
+            } else {
+                bsum += sm.amp[1][kb] * sv;
+                xb *= l2; yb *= l2; zb *= l2;
+                ++kb;
             }
-            a *= q1.norm;
-            double xb = px * q2.frequency, yb = py * q2.frequency, zb = pz * q2.frequency, bsum = 0.0;
-#pragma unroll 1
-            for (int o = 0; o < 8; ++o) {
-                bsum += q2.amp[o] * simplex3(p2, p2g, xb, yb, zb);
-                xb *= q2.lacunarity; yb *= q2.lacunarity; zb *= q2.lacunarity;
+            const double ca = a * n1, cb = bsum * n2;
+            const double ra = sm.rest[0][ka], rb = sm.rest[1][kb];
+            const double hi_a = ca + ra, hi_b = cb + rb, lo_m = fmax(ca - ra, cb - rb);
+            int verdict = -1;  // -1 undecided, 0 solid, 1 cave
+            if ((hi_a < 0.4 && hi_b < 0.4) || lo_m >= 0.8) verdict = 0;
+            else if (lo_m >= 0.4 && hi_a < 0.8 && hi_b < 0.8) verdict = 1;
+            if (verdict < 0 && step == 14) {  // all octaves done: the crate's own expression
+                const int c = f64_as_i32(normalise(fmax(ca, cb)));
+                verdict = (c >= 70 && c < 90) ? 1 : 0;  // cave_generator.rs:10-11,63
             }
-            bsum *= q2.norm;
-            const int c = f64_as_i32(normalise(fmax(a, bsum)));
-            if (c >= 70 && c < 90)  // cave_generator.rs:10-11,63: leave air
-                pool_voxels[(size_t)slot * VOXELS_IN_AREA + col + 256u * (AREA_HEIGHT - zi)] = V_NONE;
+            if (verdict >= 0) {
+                if (verdict) pool_voxels[out_index] = V_NONE;  // leave air
+                busy = false;
+            }
         }
+        my_evals = __reduce_add_sync(0xFFFFFFFFu, my_evals);
+        if ((tid & 31) == 0 && my_evals) atomicAdd(&stats[3], (unsigned long long)my_evals);
     }
 }
 

@@ -1,7 +1,7 @@
 // vx_light.cu -- L-ext: voxel light propagation (EXTENSION: the reference has no voxel light, its
 // lighting is per-fragment GLSL from the column height map and lamp uniforms).
 //
-// Specification (DESIGN.md "L-ext", oracle twin: oracle/light_ext.c):
+// Specification (DESIGN.md "L-ext"):
 //   levels 0..15 per voxel; light CARRIERS are the voxels of Voxel::TRANSPARENT (voxel.rs:39-49);
 //   sources: a carrier above its column's max_height (area.rs:34-56) has level 15 (sky), a Lamp has
 //   level 15 (emitter, not a carrier); every other carrier has max(0, max over 6 neighbours - 1);

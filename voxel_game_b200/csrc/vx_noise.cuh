@@ -5,15 +5,17 @@
 // every f64 multiply and add below is a separately rounded IEEE operation in the crate's order
 // (the library is compiled with -fmad=false), so results are bit-identical to a scalar CPU
 // evaluation.  What is *re-organised* for the GPU, all value-preserving:
-//   * floor + integer cast are done on the FP64 add pipe with the 1.5*2^52 trick instead of
-//     FRND/F2I (conversion pipe, 1/4 rate);
+//   * floor + integer cast are two FP64 adds (round-down add of 2^52 + 2^51, then subtract)
+//     instead of FRND/F2I on the conversion pipe;
 //   * the permutation table is kept un-doubled (256 B, at most 2-way bank conflicts) and indexed
 //     modulo 256, which equals indexing the crate's doubled 512-entry table;
 //   * the 3-D gradient dot product g.x (components 0/+-1) is one signed add instead of
 //     3 multiplies + 2 adds (x*1 = x, x*0 = +-0, y + +-0 = y);
 //   * Fbm amplitudes amp_k are precomputed on the host with the same running product;
 //   * the last permutation lookup only feeds "% 12" / "% 24", so it reads pre-reduced copies of
-//     the table; "t <= 0 ? 0 : t^4 * g.x" is evaluated as max(t,0)^4 * g.x (same value).
+//     the table; a corner with t <= 0 contributes 0, i.e. leaves the running sum unchanged.
+// Tables are addressed as (shared-memory base, byte offset) and never through a selected pointer,
+// so every lookup stays an LDS even when the table is chosen per lane.
 #pragma once
 #include <cstdint>
 
@@ -40,24 +42,29 @@ __constant__ double c_grad2[24][2] = {
     {-0.793353340291235, 0.608761429008721},  {-0.608761429008721, 0.793353340291235},
     {-0.38268343236509, 0.923879532511287},   {-0.130526192220052, 0.99144486137381}};
 
-// shared-memory working copy of the tables (random access; constant cache would serialise)
+// shared-memory working copy of the tables (random access; constant cache would serialise).
+// `bytes` = perm (4 x 256) | perm % 24 (4 x 256) | perm % 12 (4 x 256); table t starts at t * 256.
+constexpr unsigned TAB_BYTES = TAB_COUNT * 256;
+constexpr unsigned OFF_P24 = TAB_BYTES;      // byte offset of the % 24 copies
+constexpr unsigned OFF_P12 = 2 * TAB_BYTES;  // byte offset of the % 12 copies
 struct NoiseShared {
-    uint8_t perm[TAB_COUNT][256];
-    uint8_t perm24[TAB_COUNT][256];  // perm % 24: the last hash level only selects a 2-D gradient
-    uint8_t perm12[TAB_COUNT][256];  // perm % 12: ... or a 3-D gradient
+    uint8_t bytes[3 * TAB_BYTES];
     double grad2[24][2];
 };
 
+__device__ __forceinline__ void load_noise_tables(uint8_t* bytes, const NoiseTables& nt, int tid,
+                                                  int nthreads) {
+    for (int i = tid; i < (int)TAB_BYTES; i += nthreads) {
+        const unsigned v = (&nt.perm[0][0])[i];
+        bytes[i] = (uint8_t)v;
+        bytes[OFF_P24 + i] = (uint8_t)(v % 24u);
+        bytes[OFF_P12 + i] = (uint8_t)(v % 12u);
+    }
+}
+
 __device__ __forceinline__ void load_noise_shared(NoiseShared* s, const NoiseTables& nt, int tid,
                                                   int nthreads) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&nt.perm[0][0]);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&s->perm[0][0]);
-    for (int i = tid; i < TAB_COUNT * 256 / 4; i += nthreads) dst[i] = src[i];
-    for (int i = tid; i < TAB_COUNT * 256; i += nthreads) {
-        const unsigned v = (&nt.perm[0][0])[i];
-        (&s->perm24[0][0])[i] = (uint8_t)(v % 24u);
-        (&s->perm12[0][0])[i] = (uint8_t)(v % 12u);
-    }
+    load_noise_tables(s->bytes, nt, tid, nthreads);
     for (int i = tid; i < 48; i += nthreads) (&s->grad2[0][0])[i] = (&c_grad2[0][0])[i];
 }
 
@@ -72,9 +79,8 @@ __device__ __forceinline__ double floor_split(double x, int& i) {
 }
 
 // contribution of one simplex corner, added to `sum`; gi = gradient index.  A corner outside its
-// radius (t <= 0) contributes 0 in the crate, i.e. leaves the running sum unchanged, so it is
-// skipped with a predicated add instead of materialising the zero (sum starts at +0.0 and
-// 0.0 + v == v).
+// radius (t <= 0) contributes 0 in the crate, i.e. leaves the running sum unchanged (sum starts at
+// +0.0 and 0.0 + v == v).
 __device__ __forceinline__ void corner2(const NoiseShared* s, double x, double y, unsigned gi,
                                         double& sum) {
     const double t = 0.5 - x * x - y * y;
@@ -85,9 +91,10 @@ __device__ __forceinline__ void corner2(const NoiseShared* s, double x, double y
     if (t > 0.0) sum += v;
 }
 
-__device__ __forceinline__ double simplex2(const NoiseShared* s, const uint8_t* p,
-                                           const uint8_t* p24, double x, double y) {
+// p = byte offset of the permutation table inside s->bytes
+__device__ __forceinline__ double simplex2(const NoiseShared* s, unsigned p, double x, double y) {
     const double SKEW = 0.366025403784439, UNSKEW = 0.211324865405187;
+    const uint8_t* b = s->bytes;
     const double sk = (x + y) * SKEW;
     int i, j;
     const double fx = floor_split(x + sk, i), fy = floor_split(y + sk, j);
@@ -96,10 +103,11 @@ __device__ __forceinline__ double simplex2(const NoiseShared* s, const uint8_t* 
     const bool lower = !(x0 < y0);  // middle corner (1,0) unless x0 < y0
     const double x1 = x0 - (lower ? 1.0 : 0.0) + UNSKEW, y1 = y0 - (lower ? 0.0 : 1.0) + UNSKEW;
     const double x2 = x0 - 1.0 + 2.0 * UNSKEW, y2 = y0 - 1.0 + 2.0 * UNSKEW;
-    const unsigned pi0 = p[i & 255], pi1 = p[(i + 1) & 255];
-    const unsigned h0 = p24[(pi0 + j) & 255];
-    const unsigned h1 = lower ? p24[(pi1 + j) & 255] : p24[(pi0 + j + 1) & 255];
-    const unsigned h2 = p24[(pi1 + j + 1) & 255];
+    const unsigned pi0 = b[p + (i & 255)], pi1 = b[p + ((i + 1) & 255)];
+    const unsigned g = p + OFF_P24;
+    const unsigned h0 = b[g + ((pi0 + j) & 255)];
+    const unsigned h1 = b[g + (((lower ? pi1 : pi0) + j + (lower ? 0 : 1)) & 255)];
+    const unsigned h2 = b[g + ((pi1 + j + 1) & 255)];
     double sum = 0.0;
     corner2(s, x0, y0, h0, sum);
     corner2(s, x1, y1, h1, sum);
@@ -107,7 +115,7 @@ __device__ __forceinline__ double simplex2(const NoiseShared* s, const uint8_t* 
     return sum * 99.83685446303647;
 }
 
-// gradient h % 12 of the edge-midpoint set
+// gradient gi (0..11) of the edge-midpoint set
 //   0..3: (+-1,+-1,0)   4..7: (+-1,0,+-1)   8..11: (0,+-1,+-1); bit0 negates the first non-zero
 //   component, bit1 the second
 __device__ __forceinline__ double flip_sign(double v, unsigned sign_bit31) {
@@ -124,8 +132,8 @@ __device__ __forceinline__ void corner3(double x, double y, double z, unsigned g
     if (t > 0.0) sum += v;
 }
 
-__device__ __forceinline__ double simplex3(const uint8_t* p, const uint8_t* p12, double x, double y,
-                                           double z) {
+// b = shared-memory base of the table bytes, p = byte offset of the permutation table in it
+__device__ __forceinline__ double simplex3(const uint8_t* b, unsigned p, double x, double y, double z) {
     const double SKEW = 1.0 / 3.0, UNSKEW = 1.0 / 6.0;
     const double sk = (x + y + z) * SKEW;
     int i, j, k;
@@ -145,11 +153,12 @@ __device__ __forceinline__ double simplex3(const uint8_t* p, const uint8_t* p12,
                  z2 = z0 - (k2 ? 1.0 : 0.0) + 2.0 * UNSKEW;
     const double x3 = x0 - 1.0 + 3.0 * UNSKEW, y3 = y0 - 1.0 + 3.0 * UNSKEW,
                  z3 = z0 - 1.0 + 3.0 * UNSKEW;
-    const unsigned pi0 = p[i & 255], pi1 = p[(i + 1) & 255];
-    const unsigned h0 = p12[(p[(pi0 + j) & 255] + k) & 255];
-    const unsigned h1 = p12[(p[((i1 ? pi1 : pi0) + j + (int)j1) & 255] + k + (int)k1) & 255];
-    const unsigned h2 = p12[(p[((i2 ? pi1 : pi0) + j + (int)j2) & 255] + k + (int)k2) & 255];
-    const unsigned h3 = p12[(p[(pi1 + j + 1) & 255] + k + 1) & 255];
+    const unsigned g = p + OFF_P12;
+    const unsigned pi0 = b[p + (i & 255)], pi1 = b[p + ((i + 1) & 255)];
+    const unsigned h0 = b[g + ((b[p + ((pi0 + j) & 255)] + k) & 255)];
+    const unsigned h1 = b[g + ((b[p + (((i1 ? pi1 : pi0) + j + (int)j1) & 255)] + k + (int)k1) & 255)];
+    const unsigned h2 = b[g + ((b[p + (((i2 ? pi1 : pi0) + j + (int)j2) & 255)] + k + (int)k2) & 255)];
+    const unsigned h3 = b[g + ((b[p + ((pi1 + j + 1) & 255)] + k + 1) & 255)];
     double sum = 0.0;
     corner3(x0, y0, z0, h0, sum);
     corner3(x1, y1, z1, h1, sum);
@@ -161,14 +170,13 @@ __device__ __forceinline__ double simplex3(const uint8_t* p, const uint8_t* p12,
 template <int ID>
 __device__ __forceinline__ double fbm2(const NoiseTables& nt, const NoiseShared* s, double x, double y) {
     const FbmParams& q = nt.fbm[ID];
-    const uint8_t* p = s->perm[q.table];
-    const uint8_t* p24 = s->perm24[q.table];
+    const unsigned p = (unsigned)q.table * 256u;
     x *= q.frequency;
     y *= q.frequency;
     double acc = 0.0;
 #pragma unroll 1
     for (int o = 0; o < q.octaves; ++o) {
-        acc += q.amp[o] * simplex2(s, p, p24, x, y);
+        acc += q.amp[o] * simplex2(s, p, x, y);
         x *= q.lacunarity;
         y *= q.lacunarity;
     }
@@ -179,15 +187,14 @@ template <int ID>
 __device__ __forceinline__ double fbm3(const NoiseTables& nt, const NoiseShared* s, double x, double y,
                                        double z) {
     const FbmParams& q = nt.fbm[ID];
-    const uint8_t* p = s->perm[q.table];
-    const uint8_t* p12 = s->perm12[q.table];
+    const unsigned p = (unsigned)q.table * 256u;
     x *= q.frequency;
     y *= q.frequency;
     z *= q.frequency;
     double acc = 0.0;
 #pragma unroll 1
     for (int o = 0; o < q.octaves; ++o) {
-        acc += q.amp[o] * simplex3(p, p12, x, y, z);
+        acc += q.amp[o] * simplex3(s->bytes, p, x, y, z);
         x *= q.lacunarity;
         y *= q.lacunarity;
         z *= q.lacunarity;

@@ -130,6 +130,15 @@ void build_noise_tables(uint64_t seed, NoiseTables* out) {
     out->fbm[FBM_CAVE_CHECK] = make_fbm(TAB_SEED, 2, 0.003, 1.3, 0.3);
     out->fbm[FBM_ALT] = make_fbm(TAB_SEED_PLUS_1, 2, 0.07, 2.0, 0.3);
     out->fbm[FBM_LAKE] = make_fbm(TAB_SEED_PLUS_10, 2, 0.004, 1.3, 0.35);
+    const int cave_ids[2] = {FBM_CAVE1, FBM_CAVE2};
+    for (int f = 0; f < 2; ++f) {
+        const FbmParams& q = out->fbm[cave_ids[f]];
+        for (int k = 0; k <= 8; ++k) {
+            double rest = 0.0;
+            for (int i = k; i < q.octaves; ++i) rest += q.amp[i];
+            out->cave_rest[f][k] = SIMPLEX_BOUND * q.norm * rest;
+        }
+    }
 }
 
 uint64_t hash_world_name(const char* name) {

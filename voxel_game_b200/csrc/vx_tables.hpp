@@ -38,7 +38,14 @@ struct NoiseTables {
     uint64_t seed;
     uint8_t perm[TAB_COUNT][256];  // un-doubled; kernels index with (a + b) & 255
     FbmParams fbm[FBM_COUNT];
+    // cave_rest[f][k]: upper bound of |norm * sum_{i >= k} amp_i * simplex_i| for the two cave
+    // Fbms after k evaluated octaves (SIMPLEX_BOUND * norm * sum of the remaining amplitudes)
+    double cave_rest[2][9];
 };
+
+// |simplex3| <= 1.00004 for this gradient set and normalisation constant (1/76.8808 is the true
+// supremum of the raw sum, the crate scales by 76.88375854620836); DESIGN.md "Oracle and parity"
+constexpr double SIMPLEX_BOUND = 1.0001;
 
 void build_noise_tables(uint64_t seed, NoiseTables* out);
 uint64_t hash_world_name(const char* name);
