@@ -82,6 +82,7 @@ struct __align__(16) GenSmem {
     NoiseShared noise;
     unsigned cave_n;
     unsigned cave_base;
+    unsigned stone_rows;  // zi <= stone_rows is Stone in every column of the area
 };
 
 __global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant__ NoiseTables nt,
@@ -97,10 +98,10 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant_
     const uint4 job = jobs[blockIdx.x];
     const uint32_t ax = job.x, ay = job.y, slot = job.z;
 
-    for (int i = tid; i < VOXELS_IN_AREA / 16; i += 256) sm.vox[i] = make_uint4(0, 0, 0, 0);
     load_noise_shared(&sm.noise, nt, tid, 256);
     if (tid == 0) {
         sm.cave_n = 0;
+        sm.stone_rows = AREA_HEIGHT;
         slot_xy[slot] = make_uint2(ax, ay);
     }
     __syncthreads();
@@ -149,8 +150,22 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant_
         tops |= (unsigned)surface_pick(biome, zi, H, alt) << (8 * k);
     }
 
+    // Deep down every column of the area is Stone: the lowest `stone_rows` slabs are filled by the
+    // whole CTA with 16-byte stores (and everything above with None) before the per-column loop
+    // writes the few voxels that differ.
+    atomicMin(&sm.stone_rows, lake_depth != 0 ? LAKE_TOP_ZI - lake_depth - 1 : H - 4);
+    __syncthreads();
+    const unsigned stone_rows = sm.stone_rows;
+    {
+        const unsigned s4 = V_STONE * 0x01010101u;
+        const uint4 stone = make_uint4(s4, s4, s4, s4), none = make_uint4(0, 0, 0, 0);
+        for (unsigned i = tid; i < VOXELS_IN_AREA / 16; i += 256)  // i / 16 = z of the 16-byte row
+            sm.vox[i] = (i >> 4) >= AREA_HEIGHT - stone_rows ? stone : none;
+    }
+    __syncthreads();
+
     // generate_column (generator.rs:70-98) without the cave test; bottom -> top
-    for (unsigned zi = 1; zi <= H; ++zi) {
+    for (unsigned zi = stone_rows + 1; zi <= H; ++zi) {
         uint8_t v;
         if (lake_depth != 0 && zi > LAKE_TOP_ZI) {
             v = V_NONE;  // lake_generator.rs:59-61
@@ -184,21 +199,22 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------- K1b
-constexpr int CAVE_BATCH = 64;   // cave columns per CTA iteration
+constexpr int CAVE_CHUNK = 32;  // cave columns claimed by a warp at a time (one per lane)
 // evaluation order of the 14 cave octaves, bit = 1 -> next octave of noise1 (6 octaves, weights
 // .553 .249 .112 .050 .023 .010), 0 -> next octave of noise2 (8 octaves, .650 .228 .080 .028 ...):
 // b0 a0 a1 b1 a2 b2 a3 b3 a4 b4 a5 b5 b6 b7
 constexpr unsigned CAVE_SCHEDULE = 0b00010101010110u;
 
+struct CaveWarp {  // per-warp description of the claimed chunk
+    uint32_t first[CAVE_CHUNK + 1];  // exclusive prefix of per-column voxel counts
+    uint32_t item[CAVE_CHUNK];       // slot * 256 + column
+    uint2 origin[CAVE_CHUNK];        // global x, y of the column
+};
 struct CaveSmem {
     uint8_t bytes[3 * TAB_BYTES];  // permutation tables and their reduced copies (vx_noise.cuh)
-    double amp[2][8];    // [0] = noise1, [1] = noise2: running amplitudes
-    double rest[2][9];   // bound of the octaves not yet evaluated (NoiseTables::cave_rest) + slack
-    uint32_t item[CAVE_BATCH];
-    uint2 origin[CAVE_BATCH];        // global x, y of the column (refills must not wait on HBM)
-    uint32_t first[CAVE_BATCH + 1];  // exclusive prefix of per-column voxel counts
-    uint32_t next;                   // next unclaimed voxel of the batch
-    uint32_t batch;                  // batch claimed by this CTA
+    double amp[2][8];              // [0] = noise1, [1] = noise2: running amplitudes
+    double rest[2][9];             // bound of the octaves not yet evaluated (cave_rest) + slack
+    CaveWarp warp[8];
 };
 
 // Max<Fbm, Fbm>::sample + threshold (cave_generator.rs:27-30,43-64) for every voxel of the listed
@@ -210,10 +226,11 @@ struct CaveSmem {
 //     the verdict can no longer change.  Undecided voxels run all 14 octaves and use the crate's
 //     expression, so the result never depends on the bound being tight, only on it being valid
 //     (slack 1e-9 against rounding).  ~4 of 14 octaves are needed on average.
-//   * Persistent lanes.  A lane that has decided its voxel claims the next one of the batch at
-//     once (shared-memory counter) instead of idling until the slowest lane of its warp is done:
-//     lanes of a warp sit at different octaves of different voxels, which costs nothing because
-//     the octave index only selects table rows.
+//   * Warp-autonomous persistent lanes.  A warp claims 32 columns from a global counter and
+//     flattens their (column, z) voxels; a lane that has decided its voxel takes the next unclaimed
+//     one at once (ballot + popc, no atomics, no CTA barrier) instead of idling until the slowest
+//     lane is done.  Lanes of a warp sit at different octaves of different voxels, which costs
+//     nothing because the octave index only selects table rows.
 __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ NoiseTables nt,
                                                         const uint32_t* __restrict__ cave_items,
                                                         const uint32_t* __restrict__ cave_count,
@@ -222,34 +239,34 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
                                                         const uint2* __restrict__ slot_xy,
                                                         unsigned long long* __restrict__ stats) {
     __shared__ CaveSmem sm;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const FbmParams& q1 = nt.fbm[FBM_CAVE1];
     const FbmParams& q2 = nt.fbm[FBM_CAVE2];
-    {
-        load_noise_tables(sm.bytes, nt, tid, 256);
-        if (tid < 8) {
-            sm.amp[0][tid] = tid < 6 ? q1.amp[tid] : 0.0;
-            sm.amp[1][tid] = q2.amp[tid];
-        }
-        if (tid < 18) (&sm.rest[0][0])[tid] = (&nt.cave_rest[0][0])[tid] + 1e-9;
+    load_noise_tables(sm.bytes, nt, tid, 256);
+    if (tid < 8) {
+        sm.amp[0][tid] = tid < 6 ? q1.amp[tid] : 0.0;
+        sm.amp[1][tid] = q2.amp[tid];
     }
+    if (tid < 18) (&sm.rest[0][0])[tid] = (&nt.cave_rest[0][0])[tid] + 1e-9;
+    __syncthreads();
     const uint32_t n_items = *cave_count;
     const unsigned t1 = (unsigned)q1.table * 256u, t2 = (unsigned)q2.table * 256u;  // table offsets
     const double f1 = q1.frequency, f2 = q2.frequency, l1 = q1.lacunarity, l2 = q2.lacunarity;
     const double n1 = q1.norm, n2 = q2.norm;
+    CaveWarp& cw = sm.warp[tid >> 5];
+    unsigned* chunk_counter = reinterpret_cast<unsigned*>(&stats[4]);
+    const unsigned lanes_below = (1u << lane) - 1u;
+    unsigned my_evals = 0;
 
-    // batches are handed out dynamically (global counter): with the early exit the cost of a batch
-    // varies several-fold, a static stride would leave most SMs waiting for the unluckiest CTA
-    unsigned* batch_counter = reinterpret_cast<unsigned*>(&stats[4]);
     while (true) {
-        __syncthreads();  // previous iteration done with sm.item / sm.first (and tables loaded)
-        if (tid == 0) sm.batch = atomicAdd(batch_counter, 1u);
-        __syncthreads();
-        const uint32_t batch = sm.batch;
-        if ((unsigned long long)batch * CAVE_BATCH >= n_items) break;
-        if (tid < CAVE_BATCH) {
-            const uint32_t idx = batch * CAVE_BATCH + tid;
+        unsigned chunk = 0;
+        if (lane == 0) chunk = atomicAdd(chunk_counter, 1u);
+        chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
+        if ((unsigned long long)chunk * CAVE_CHUNK >= n_items) break;
+        {
+            const uint32_t idx = chunk * CAVE_CHUNK + lane;
             uint32_t item = 0, cnt = 0;
+            uint2 org = make_uint2(0, 0);
             if (idx < n_items) {
                 item = cave_items[idx];
                 const unsigned H = pool_heights[item] & 0x7Fu;
@@ -257,89 +274,90 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
                 // (in a cave zone lake_depth is 0, so the voxel is never None/WaterSource)
                 const unsigned top = H < CAVE_MAX_ZI - 1 ? H : CAVE_MAX_ZI - 1;
                 cnt = top >= CAVE_MIN_ZI ? top - CAVE_MIN_ZI + 1 : 0;
+                const uint2 axy = slot_xy[item >> 8];
+                org = make_uint2((item & 15u) + axy.x * AREA_SIZE, ((item >> 4) & 15u) + axy.y * AREA_SIZE);
             }
-            sm.item[tid] = item;
-            const uint2 axy = slot_xy[item >> 8];
-            sm.origin[tid] = make_uint2((item & 15u) + axy.x * AREA_SIZE, ((item >> 4) & 15u) + axy.y * AREA_SIZE);
-            uint32_t v = cnt;  // inclusive scan inside each warp
+            uint32_t v = cnt;
+#pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
-                if ((tid & 31) >= d) v += o;
+                if (lane >= d) v += o;
             }
-            sm.first[tid + 1] = v;
+            __syncwarp();  // every lane is done with the previous chunk's tables
+            cw.item[lane] = item;
+            cw.origin[lane] = org;
+            cw.first[lane + 1] = v;
+            if (lane == 0) cw.first[0] = 0;
+            __syncwarp();
         }
-        __syncthreads();
-        if (tid == 0) {  // stitch the four warp-local scans into one exclusive prefix
-            sm.first[0] = 0;
-            sm.next = 0;
-            uint32_t base = 0;
-            for (int i = 33; i <= CAVE_BATCH; ++i) {
-                if (((i - 1) & 31) == 0) base = sm.first[i - 1];  // already final
-                sm.first[i] += base;
-            }
-        }
-        __syncthreads();
-        const uint32_t total = sm.first[CAVE_BATCH];
-        if (tid == 0) atomicAdd(&stats[2], (unsigned long long)total);  // cave voxels evaluated
+        const uint32_t total = cw.first[CAVE_CHUNK];
+        if (lane == 0) atomicAdd(&stats[2], (unsigned long long)total);  // cave voxels evaluated
 
-        unsigned my_evals = 0;
+        uint32_t next = 0;  // next unclaimed voxel of the chunk (uniform across the warp)
         bool busy = false;
         double xa = 0, ya = 0, za = 0, xb = 0, yb = 0, zb = 0, a = 0, bsum = 0;
         unsigned step = 0, ka = 0, kb = 0;
         size_t out_index = 0;
         while (true) {
+            // idle lanes take the next voxels, in lane order
+            const unsigned want = __ballot_sync(0xFFFFFFFFu, !busy);
             if (!busy) {
-                const uint32_t w = atomicAdd(&sm.next, 1u);
-                if (w >= total) break;
-                int lo = 0, hi = CAVE_BATCH;  // column with first[lo] <= w < first[lo + 1]
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (sm.first[mid] <= w) lo = mid; else hi = mid;
+                const uint32_t w = next + __popc(want & lanes_below);
+                if (w < total) {
+                    int lo = 0, hi = CAVE_CHUNK;  // column with first[lo] <= w < first[lo + 1]
+#pragma unroll
+                    for (int s = 0; s < 5; ++s) {
+                        const int mid = (lo + hi) >> 1;
+                        if (cw.first[mid] <= w) lo = mid; else hi = mid;
+                    }
+                    const uint32_t item = cw.item[lo];
+                    const unsigned zi = CAVE_MIN_ZI + (w - cw.first[lo]);
+                    const uint2 gxy = cw.origin[lo];
+                    const double px = (double)gxy.x, py = (double)gxy.y, pz = (double)zi;
+                    xa = px * f1; ya = py * f1; za = pz * f1;
+                    xb = px * f2; yb = py * f2; zb = pz * f2;
+                    a = 0.0; bsum = 0.0;
+                    step = 0; ka = 0; kb = 0;
+                    out_index = (size_t)(item >> 8) * VOXELS_IN_AREA + (item & 255u) + 256u * (AREA_HEIGHT - zi);
+                    busy = true;
                 }
-                const uint32_t item = sm.item[lo];
-                const unsigned zi = CAVE_MIN_ZI + (w - sm.first[lo]);
-                const uint32_t slot = item >> 8, col = item & 255u;
-                const uint2 gxy = sm.origin[lo];
-                const double px = (double)gxy.x, py = (double)gxy.y, pz = (double)zi;
-                xa = px * f1; ya = py * f1; za = pz * f1;
-                xb = px * f2; yb = py * f2; zb = pz * f2;
-                a = 0.0; bsum = 0.0;
-                step = 0; ka = 0; kb = 0;
-                out_index = (size_t)slot * VOXELS_IN_AREA + col + 256u * (AREA_HEIGHT - zi);
-                busy = true;
             }
-            const bool is_a = (CAVE_SCHEDULE >> step) & 1u;
-            const double sv = simplex3(sm.bytes, is_a ? t1 : t2, is_a ? xa : xb, is_a ? ya : yb,
-                                       is_a ? za : zb);
-            ++my_evals;
-            ++step;
-            if (is_a) {
-                a += sm.amp[0][ka] * sv;
-                xa *= l1; ya *= l1; za *= l1;
-                ++ka;
-            } else {
-                bsum += sm.amp[1][kb] * sv;
-                xb *= l2; yb *= l2; zb *= l2;
-                ++kb;
-            }
-            const double ca = a * n1, cb = bsum * n2;
-            const double ra = sm.rest[0][ka], rb = sm.rest[1][kb];
-            const double hi_a = ca + ra, hi_b = cb + rb, lo_m = fmax(ca - ra, cb - rb);
-            int verdict = -1;  // -1 undecided, 0 solid, 1 cave
-            if ((hi_a < 0.4 && hi_b < 0.4) || lo_m >= 0.8) verdict = 0;
-            else if (lo_m >= 0.4 && hi_a < 0.8 && hi_b < 0.8) verdict = 1;
-            if (verdict < 0 && step == 14) {  // all octaves done: the crate's own expression
-                const int c = f64_as_i32(normalise(fmax(ca, cb)));
-                verdict = (c >= 70 && c < 90) ? 1 : 0;  // cave_generator.rs:10-11,63
-            }
-            if (verdict >= 0) {
-                if (verdict) pool_voxels[out_index] = V_NONE;  // leave air
-                busy = false;
+            next += __popc(want);
+            if (!__any_sync(0xFFFFFFFFu, busy)) break;
+            if (busy) {
+                const bool is_a = (CAVE_SCHEDULE >> step) & 1u;
+                const double sv = simplex3(sm.bytes, is_a ? t1 : t2, is_a ? xa : xb, is_a ? ya : yb,
+                                           is_a ? za : zb);
+                ++my_evals;
+                ++step;
+                if (is_a) {
+                    a += sm.amp[0][ka] * sv;
+                    xa *= l1; ya *= l1; za *= l1;
+                    ++ka;
+                } else {
+                    bsum += sm.amp[1][kb] * sv;
+                    xb *= l2; yb *= l2; zb *= l2;
+                    ++kb;
+                }
+                const double ca = a * n1, cb = bsum * n2;
+                const double ra = sm.rest[0][ka], rb = sm.rest[1][kb];
+                const double hi_a = ca + ra, hi_b = cb + rb, lo_m = fmax(ca - ra, cb - rb);
+                int verdict = -1;  // -1 undecided, 0 solid, 1 cave
+                if ((hi_a < 0.4 && hi_b < 0.4) || lo_m >= 0.8) verdict = 0;
+                else if (lo_m >= 0.4 && hi_a < 0.8 && hi_b < 0.8) verdict = 1;
+                if (verdict < 0 && step == 14) {  // all octaves done: the crate's own expression
+                    const int c = f64_as_i32(normalise(fmax(ca, cb)));
+                    verdict = (c >= 70 && c < 90) ? 1 : 0;  // cave_generator.rs:10-11,63
+                }
+                if (verdict >= 0) {
+                    if (verdict) pool_voxels[out_index] = V_NONE;  // leave air
+                    busy = false;
+                }
             }
         }
-        my_evals = __reduce_add_sync(0xFFFFFFFFu, my_evals);
-        if ((tid & 31) == 0 && my_evals) atomicAdd(&stats[3], (unsigned long long)my_evals);
     }
+    my_evals = __reduce_add_sync(0xFFFFFFFFu, my_evals);
+    if (lane == 0 && my_evals) atomicAdd(&stats[3], (unsigned long long)my_evals);
 }
 
 // ------------------------------------------------------------------------------------------- K2
