@@ -101,24 +101,63 @@ struct RowMasks {
     uint32_t m[6];  // L(x+1) R(x-1) F(y+1) B(y-1) D(z+1) U(z-1): bit x set = voxel x has the face
 };
 
+// The planes one area's culling reads, staged in shared memory by fully coalesced loads: own S and
+// T (2 x 4 KiB), per row the two x-halo bits (T of the +x neighbour's x = 0 and of the -x
+// neighbour's x = 15), and the y-halo rows (T of the +y neighbour's y = 0 row and of the -y
+// neighbour's y = 15 row, per z).
+struct PlaneTile {
+    uint16_t S[ROWS];
+    uint16_t T[ROWS];
+    uint8_t hx[ROWS];              // bit0: T(+x neighbour, x = 0), bit1: T(-x neighbour, x = 15)
+    uint16_t ty[2][AREA_HEIGHT];   // [0]: +y neighbour row y = 0, [1]: -y neighbour row y = 15
+};
+
+__device__ __forceinline__ void load_plane_tile(PlaneTile& p, const AreaView& a, int tid) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(a.S);
+    const uint4* t4 = reinterpret_cast<const uint4*>(a.T);
+    uint4* ds = reinterpret_cast<uint4*>(p.S);
+    uint4* dt = reinterpret_cast<uint4*>(p.T);
+    const uint4* xp4 = reinterpret_cast<const uint4*>(a.T_n[0]);
+    const uint4* xm4 = reinterpret_cast<const uint4*>(a.T_n[1]);
+    uint2* dh = reinterpret_cast<uint2*>(p.hx);
+    for (int i = tid; i < ROWS / 8; i += 256) {  // 8 rows (16 bytes of u16) per iteration
+        ds[i] = s4[i];
+        dt[i] = t4[i];
+        const uint4 xp = xp4[i], xm = xm4[i];
+        const uint32_t wp[4] = {xp.x, xp.y, xp.z, xp.w}, wm[4] = {xm.x, xm.y, xm.z, xm.w};
+        uint32_t h[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t vp = (wp[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+            const uint32_t vm = (wm[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+            h[k >> 2] |= ((vp & 1u) | ((vm >> 15) << 1)) << (8 * (k & 3));
+        }
+        dh[i] = make_uint2(h[0], h[1]);
+    }
+    if (tid < AREA_HEIGHT) {
+        p.ty[0][tid] = a.T_n[2][16 * tid];       // row (y = 0, z = tid) of the +y neighbour
+        p.ty[1][tid] = a.T_n[3][16 * tid + 15];  // row (y = 15, z = tid) of the -y neighbour
+    }
+}
+
 __device__ __forceinline__ bool partial_height(uint32_t v) { return v >= V_WATER1 && v <= V_WATER4; }
 
-__device__ __forceinline__ RowMasks row_masks(const AreaView& a, int r) {
+__device__ __forceinline__ RowMasks row_masks(const PlaneTile& p, const AreaView& a, int r) {
     RowMasks k;
-    const uint32_t s = a.S[r];
+    const uint32_t s = p.S[r];
     if (s == 0) {
 #pragma unroll
         for (int d = 0; d < 6; ++d) k.m[d] = 0;
         return k;
     }
     const int y = r & 15, z = r >> 4;
-    const uint32_t t = a.T[r];
-    const uint32_t t_xp = (t >> 1) | ((uint32_t)(a.T_n[0][r] & 1u) << 15);
-    const uint32_t t_xm = ((t << 1) & 0xFFFFu) | ((uint32_t)a.T_n[1][r] >> 15);
-    const uint32_t t_yp = y < 15 ? a.T[r + 1] : a.T_n[2][r - 15];
-    const uint32_t t_ym = y > 0 ? a.T[r - 1] : a.T_n[3][r + 15];
-    const uint32_t t_zp = z < AREA_HEIGHT - 1 ? a.T[r + 16] : 0u;  // renderer.rs:165
-    const uint32_t t_zm = z > 0 ? a.T[r - 16] : 0u;                // renderer.rs:173
+    const uint32_t t = p.T[r], hx = p.hx[r];
+    const uint32_t t_xp = (t >> 1) | ((hx & 1u) << 15);
+    const uint32_t t_xm = ((t << 1) & 0xFFFFu) | (hx >> 1);
+    const uint32_t t_yp = y < 15 ? p.T[r + 1] : p.ty[0][z];
+    const uint32_t t_ym = y > 0 ? p.T[r - 1] : p.ty[1][z];
+    const uint32_t t_zp = z < AREA_HEIGHT - 1 ? p.T[r + 16] : 0u;  // renderer.rs:165
+    const uint32_t t_zm = z > 0 ? p.T[r - 16] : 0u;                // renderer.rs:173
     k.m[0] = s & t_xp;
     k.m[1] = s & t_xm;
     k.m[2] = s & t_yp;
@@ -194,6 +233,15 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long warp_inclusive_scan64(unsigned long long v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
 // ------------------------------------------------------------------------------------- count
 __global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict__ jobs,
                                                          const uint8_t* __restrict__ pool_voxels,
@@ -201,11 +249,14 @@ __global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict
                                                          AreaMap map, uint32_t* __restrict__ rec_count,
                                                          uint32_t* __restrict__ face_count) {
     __shared__ uint32_t s_faces[8], s_recs[8];
+    __shared__ PlaneTile tile;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const AreaView a = make_view(jobs[blockIdx.x], map, pool_voxels, pool_planes);
+    load_plane_tile(tile, a, tid);
+    __syncthreads();
     uint32_t faces = 0, recs = 0;
     for (int r = tid; r < ROWS; r += 256) {
-        const RowMasks k = row_masks(a, r);
+        const RowMasks k = row_masks(tile, a, r);
         faces += __popc(k.m[0]) + __popc(k.m[1]) + __popc(k.m[2]) + __popc(k.m[3]) +
                  __popc(k.m[4]) + __popc(k.m[5]);
         recs += __popc(k.m[0] | k.m[1] | k.m[2] | k.m[3] | k.m[4] | k.m[5]);
@@ -307,15 +358,20 @@ __device__ __forceinline__ uint32_t make_desc(int r, int x, int dir, int ord, ui
            (voxel << 21);
 }
 
-constexpr int LIST_FACES = 3072;   // face descriptors buffered per flush
-constexpr int STAGE_FACES = 128;   // faces assembled in shared memory per sub-round (2 threads each)
-constexpr int STAGE_STRIDE = 11;   // uint4 per staged face: 160 B payload + 16 B pad (bank spread)
+constexpr int LIST_FACES = 3072;   // face descriptors buffered per flush (typical area: ~600)
+constexpr int WARP_FACES = 16;     // faces a warp assembles per staging round (2 lanes per face)
+constexpr int FACE_U4 = 10;        // uint4 per face (4 vertices x 40 B); with lane pairs writing 5
+                                   // uint4 each at (lane/2)*10 + (lane%2)*5 the 8 lanes of a store
+                                   // phase hit 8 different bank groups, so no padding is needed
+constexpr int CHUNKS = ROWS / 256; // rows per thread
 
 struct EmitSmem {
+    PlaneTile planes;
     uint32_t list[LIST_FACES];
-    uint4 stage[STAGE_FACES * STAGE_STRIDE];
-    uint32_t warp[8];
-    uint32_t total;
+    uint4 stage[8][WARP_FACES * FACE_U4];  // one staging tile per warp
+    unsigned long long part[CHUNKS][8];    // faces | recs << 32 of the rows before (chunk, warp)
+    uint32_t warp_total[CHUNKS][8];        // faces | recs << 16 of (chunk, warp); 0 = nothing to do
+    unsigned long long total;
 };
 
 // Two vertices (2*half, 2*half + 1) of one face = 20 words = 5 uint4 written to the staging tile.
@@ -366,23 +422,21 @@ __device__ __forceinline__ void build_half_face(uint4* dst, uint32_t desc, int h
     dst[4] = make_uint4(fnx, fny, fnz, 0u);
 }
 
-// write `count` buffered faces (descriptors sm.list[0..count)) starting at stream face `first`
+// Write `count` buffered faces (descriptors sm.list[0..count)) starting at stream face `first`.
+// Each warp works on its own: 16 faces are assembled in the warp's staging tile by lane pairs, then
+// the tile leaves as 160 consecutive 16-byte pieces; no CTA barrier is involved.
 __device__ __forceinline__ void flush_faces(EmitSmem& sm, uint32_t count, uint32_t first,
                                             const MeshOut& out, uint32_t gx0, uint32_t gy0, int tid) {
-    // vertices: assembled in the staging tile, then stored as consecutive 16-byte pieces
-    for (uint32_t base = 0; base < count; base += STAGE_FACES) {
-        const uint32_t nfaces = min((uint32_t)STAGE_FACES, count - base);
-        const uint32_t f = tid >> 1;
-        if (f < nfaces)
-            build_half_face(&sm.stage[f * STAGE_STRIDE + (tid & 1) * 5], sm.list[base + f], tid & 1,
-                            gx0, gy0);
-        __syncthreads();
-        uint4* vdst = out.vertices + (size_t)(first + base) * 10;
-        for (uint32_t w = tid; w < nfaces * 10; w += 256) {
-            const uint32_t fi = w / 10, piece = w - fi * 10;
-            vdst[w] = sm.stage[fi * STAGE_STRIDE + piece];
-        }
-        __syncthreads();
+    const int lane = tid & 31, wid = tid >> 5;
+    uint4* tile = sm.stage[wid];
+    for (uint32_t base = wid * WARP_FACES; base < count; base += 8 * WARP_FACES) {
+        const uint32_t nfaces = min((uint32_t)WARP_FACES, count - base);
+        const uint32_t f = lane >> 1;
+        if (f < nfaces) build_half_face(&tile[f * FACE_U4 + (lane & 1) * 5], sm.list[base + f], lane & 1, gx0, gy0);
+        __syncwarp();
+        uint4* vdst = out.vertices + (size_t)(first + base) * FACE_U4;
+        for (uint32_t w = lane; w < nfaces * FACE_U4; w += 32) vdst[w] = tile[w];
+        __syncwarp();
     }
     // indices: [0,1,2,0,2,3] + 4*ord as three u32 words per face (mesh_generator.rs:44,131-139)
     uint32_t* idst = out.indices + (size_t)first * 3;
@@ -395,6 +449,15 @@ __device__ __forceinline__ void flush_faces(EmitSmem& sm, uint32_t count, uint32
     }
 }
 
+__device__ __forceinline__ uint32_t row_counts(const RowMasks& k) {  // faces | visible voxels << 16
+    const uint32_t vis = k.m[0] | k.m[1] | k.m[2] | k.m[3] | k.m[4] | k.m[5];
+    return (__popc(k.m[0]) + __popc(k.m[1]) + __popc(k.m[2]) + __popc(k.m[3]) + __popc(k.m[4]) +
+            __popc(k.m[5])) | ((uint32_t)__popc(vis) << 16);
+}
+__device__ __forceinline__ unsigned long long widen(uint32_t faces_recs16) {
+    return (unsigned long long)(faces_recs16 & 0xFFFFu) | ((unsigned long long)(faces_recs16 >> 16) << 32);
+}
+
 __global__ void __launch_bounds__(256) mesh_emit_kernel(const uint4* __restrict__ jobs,
                                                         const uint8_t* __restrict__ pool_voxels,
                                                         const uint16_t* __restrict__ pool_planes,
@@ -404,87 +467,90 @@ __global__ void __launch_bounds__(256) mesh_emit_kernel(const uint4* __restrict_
     const uint4 job = jobs[blockIdx.x];
     const AreaView a = make_view(job, map, pool_voxels, pool_planes);
     const uint32_t gx0 = job.x * AREA_SIZE, gy0 = job.y * AREA_SIZE;
-    uint32_t face_done = out.face_first[blockIdx.x];  // stream index of list[0]
-    uint32_t rec_base = out.rec_first[blockIdx.x];
-    uint32_t fill = 0;  // faces buffered in sm.list
+    const uint32_t face_base = out.face_first[blockIdx.x];
+    const uint32_t rec_base = out.rec_first[blockIdx.x];
+    load_plane_tile(sm.planes, a, tid);
+    __syncthreads();
 
-    for (int chunk = 0; chunk < ROWS / 256; ++chunk) {
-        const int r = chunk * 256 + tid;  // rows in (z, y) order == the reference's z,y loop
-        const RowMasks k = row_masks(a, r);
-        const uint32_t vis = k.m[0] | k.m[1] | k.m[2] | k.m[3] | k.m[4] | k.m[5];
-        const uint32_t nf = __popc(k.m[0]) + __popc(k.m[1]) + __popc(k.m[2]) + __popc(k.m[3]) +
-                            __popc(k.m[4]) + __popc(k.m[5]);
-        // CTA exclusive scan of (faces | recs << 16)
-        const uint32_t packed = nf | ((uint32_t)__popc(vis) << 16);
-        const uint32_t inc = warp_inclusive_scan(packed, lane);
-        __syncthreads();  // previous chunk's readers of sm.warp / sm.total are done
-        if (lane == 31) sm.warp[wid] = inc;
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t run = 0;
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t v = sm.warp[i];
-                sm.warp[i] = run;
-                run += v;
-            }
-            sm.total = run;
+    // 1. per (chunk, warp) totals.  Row r = chunk * 256 + tid: rows in (z, y) order are the
+    //    reference's z,y loop.  Most (chunk, warp) pairs are all air or all buried and are skipped
+    //    later on the strength of their zero total.
+#pragma unroll 1
+    for (int c = 0; c < CHUNKS; ++c) {
+        const uint32_t v = row_counts(row_masks(sm.planes, a, c * 256 + tid));
+        const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, v);  // <= 32 * 96 faces, 32 * 16 voxels
+        if (lane == 0) {
+            sm.warp_total[c][wid] = tot;
+            sm.part[c][wid] = widen(tot);
         }
-        __syncthreads();
-        const uint32_t excl = sm.warp[wid] + inc - packed;
-        const uint32_t my_face = excl & 0xFFFFu, my_rec = excl >> 16;
-        const uint32_t total_faces = sm.total & 0xFFFFu, total_recs = sm.total >> 16;
-        if (total_faces == 0) continue;  // uniform across the CTA
+    }
+    __syncthreads();
+    // 2. exclusive prefix of the 64 (chunk, warp) totals, in that order
+    if (tid < 64) {
+        const unsigned long long v = (&sm.part[0][0])[tid];
+        const unsigned long long inc = warp_inclusive_scan64(v, lane);
+        (&sm.part[0][0])[tid] = inc - v;  // exclusive inside its half of 32
+        if (tid == 31) sm.total = inc;    // sum of entries 0..31
+    }
+    __syncthreads();
+    if (tid >= 32 && tid < 64) (&sm.part[0][0])[tid] += sm.total;
+    __syncthreads();
+    if (tid == 0) sm.total = sm.part[CHUNKS - 1][7] + widen(sm.warp_total[CHUNKS - 1][7]);
+    __syncthreads();
+    const uint32_t total_faces = (uint32_t)sm.total;
 
-        // records: one per visible voxel, z,y,x order; first_face = stream index of its first face
-        // (face_done + fill is the stream index of this chunk's face 0, invariant under flushes)
-        if (vis) {
-            uint32_t f = face_done + fill + my_face, q = rec_base + my_rec, rest = vis;
+    // 3. records straight to global; face descriptors into the list, in windows if the area has
+    //    more faces than the list holds (worst case 98 304)
+    for (uint32_t lo = 0; lo < total_faces; lo += LIST_FACES) {
+        const uint32_t hi = min(total_faces, lo + LIST_FACES);
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS; ++c) {
+            if (sm.warp_total[c][wid] == 0) continue;  // uniform across the warp
+            const unsigned long long warp_off = sm.part[c][wid];
+            const uint32_t wf0 = (uint32_t)warp_off, wnf = sm.warp_total[c][wid] & 0xFFFFu;
+            if (wf0 >= hi || wf0 + wnf <= lo) continue;  // none of the warp's faces in this window
+            const int r = c * 256 + tid;
+            const RowMasks k = row_masks(sm.planes, a, r);
+            const uint32_t v = row_counts(k);
+            const uint32_t ex = warp_inclusive_scan(v, lane) - v;  // rows of this warp before mine
+            const uint32_t nf = v & 0xFFFFu;
+            const uint32_t f0 = wf0 + (ex & 0xFFFFu);  // area-local index of the row's first face
+            if (nf == 0 || f0 >= hi || f0 + nf <= lo) continue;
+            const bool first_window = f0 >= lo;  // the window the row's first face falls in writes its records
+            // the 16 voxel bytes of the row in one load
+            const uint4 rv = reinterpret_cast<const uint4*>(a.vox)[r];
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            uint32_t rest = k.m[0] | k.m[1] | k.m[2] | k.m[3] | k.m[4] | k.m[5];
+            uint32_t f = f0, q = rec_base + (uint32_t)(warp_off >> 32) + (ex >> 16);
             const uint32_t z = (uint32_t)r >> 4, y = (uint32_t)r & 15u;
             while (rest) {
                 const int x = __ffs(rest) - 1;
                 rest &= rest - 1;
+                uint32_t voxel = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((x >> 2) == j) voxel = (rw[j] >> (8 * (x & 3))) & 0xFFu;
                 uint32_t m6 = 0;
 #pragma unroll
                 for (int d = 0; d < 6; ++d) m6 |= ((k.m[d] >> x) & 1u) << d;
-                const uint32_t cnt = __popc(m6);
-                out.recs[q++] = make_uint4(gx0 + x, gy0 + y,
-                                           z | ((uint32_t)a.vox[x + 16 * r] << 8) | (m6 << 16) | (cnt << 24), f);
-                f += cnt;
-            }
-        }
-        // face descriptors -> list. A chunk may exceed the list (worst case 24 576 faces): feed it
-        // through in windows [lo, hi) of chunk-local face indices.
-        for (uint32_t lo = 0; lo < total_faces;) {
-            if (fill == LIST_FACES || (lo == 0 && fill + total_faces > LIST_FACES && fill > 0)) {
-                __syncthreads();
-                flush_faces(sm, fill, face_done, out, gx0, gy0, tid);
-                __syncthreads();
-                face_done += fill;
-                fill = 0;
-            }
-            const uint32_t hi = min(total_faces, lo + (LIST_FACES - fill));
-            if (vis && my_face < hi && my_face + nf > lo) {
-                uint32_t f = my_face, rest = vis;
-                while (rest) {
-                    const int x = __ffs(rest) - 1;
-                    rest &= rest - 1;
-                    const uint32_t voxel = a.vox[x + 16 * r];
-#pragma unroll
-                    for (int d = 0, ord = 0; d < 6; ++d)
-                        if ((k.m[d] >> x) & 1u) {
-                            if (f >= lo && f < hi) sm.list[fill + (f - lo)] = make_desc(r, x, d, ord, voxel);
-                            ++f;
-                            ++ord;
-                        }
+                if (first_window)
+                    out.recs[q] = make_uint4(gx0 + x, gy0 + y, z | (voxel << 8) | (m6 << 16) | ((uint32_t)__popc(m6) << 24),
+                                             face_base + f);
+                ++q;
+                int ord = 0;
+                while (m6) {
+                    const int d = __ffs(m6) - 1;
+                    m6 &= m6 - 1;
+                    if (f >= lo && f < hi) sm.list[f - lo] = make_desc(r, x, d, ord, voxel);
+                    ++f;
+                    ++ord;
                 }
             }
-            fill += hi - lo;
-            lo = hi;
         }
-        rec_base += total_recs;
+        __syncthreads();
+        flush_faces(sm, hi - lo, face_base + lo, out, gx0, gy0, tid);
+        __syncthreads();
     }
-    __syncthreads();
-    flush_faces(sm, fill, face_done, out, gx0, gy0, tid);
 }
 
 }  // namespace
