@@ -145,6 +145,10 @@ struct vx_ctx {
     std::vector<uint64_t> slot_key;    // per slot; ~0 = free
     std::vector<int> free_slots;
     HostAreaMap index;
+    uint64_t index_version = 0;  // bumped whenever the resident set changes
+    std::vector<uint32_t> last_gen_xy;  // area list + slots of the previous vx_generate
+    std::vector<int> last_gen_slots;
+    uint64_t last_gen_version = ~0ull;
 
     // device copy of `index` (see AreaMap)
     uint32_t map_mask = 0;
@@ -156,7 +160,7 @@ struct vx_ctx {
     PinnedBuf h_small;   // small results coming back
     DevBuf d_jobs, d_list, d_missing, d_cave_items, d_counters, d_rec_count, d_face_count;
     DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
-    DevBuf d_heightmap, d_light, d_slot_to_job;
+    DevBuf d_heightmap, d_light, d_slot_to_job, d_finished;
     bool heightmap_init = false;
 
     // last mesh
@@ -303,6 +307,7 @@ int acquire_slots(vx_ctx* ctx, const uint32_t* area_xy, int n, std::vector<int>&
             ctx->index.insert(ax, ay, s);
             ctx->slot_key[s] = area_key(ax, ay);
             ctx->map_dirty = true;
+            ++ctx->index_version;
         }
         slots[i] = s;
     }
@@ -362,6 +367,7 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
     int st = upload_jobs(ctx, area_xy, slots, n);
     if (st != VX_OK) return st;
     VX_CUDA(ctx->d_cave_items.ensure((size_t)n * COLUMNS_IN_AREA * sizeof(uint32_t)));
+    VX_CUDA(ctx->d_finished.ensure((size_t)n));
     VX_CUDA(ctx->d_counters.ensure(64));
     VX_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
     const uint4* jobs = ctx->d_jobs.as<uint4>();
@@ -370,7 +376,8 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
     {
         ScopedTimer t(ctx, TM_GEN_COLUMNS);
         launch_gen_columns(ctx->tables, jobs, n, ctx->d_voxels, ctx->d_heights, ctx->d_slot_xy,
-                           ctx->d_cave_items.as<uint32_t>(), cave_count, stats, ctx->stream);
+                           ctx->d_cave_items.as<uint32_t>(), cave_count, stats, ctx->d_planes,
+                           ctx->d_finished.as<uint8_t>(), ctx->stream);
     }
     {
         ScopedTimer t(ctx, TM_GEN_CAVES);
@@ -379,7 +386,8 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
     }
     {
         ScopedTimer t(ctx, TM_GEN_FINISH);
-        launch_gen_finish(jobs, n, ctx->d_voxels, ctx->d_heights, ctx->tables.seed, ctx->stream);
+        launch_gen_finish(jobs, ctx->d_finished.as<uint8_t>(), n, ctx->d_voxels, ctx->d_heights, ctx->d_planes,
+                          ctx->tables.seed, ctx->stream);
     }
     ctx->timings.gen_launches += 3;
     VX_CUDA(cudaGetLastError());
@@ -452,7 +460,7 @@ void vx_destroy(vx_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters,
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
-                      &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
+                      &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
                       &ctx->d_vertices, &ctx->d_indices};
     for (DevBuf* b : bufs) b->release();
     ctx->h_stage.release();
@@ -529,16 +537,28 @@ int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out
     VX_CUDA(cudaSetDevice(ctx->device));
     reset_timers(ctx);
     if (n == 0) return VX_OK;
-    std::vector<int> slots;
-    int st = acquire_slots(ctx, area_xy, n, slots);
-    if (st != VX_OK) return st;
+    // Regenerating the list of the previous call with an unchanged resident set (world
+    // pre-generation sweeps, benchmarks) reuses its slot assignment: no hashing on the host.
+    std::vector<int>& slots = ctx->last_gen_slots;
+    const bool same_list = ctx->last_gen_version == ctx->index_version && (int)ctx->last_gen_xy.size() == 2 * n &&
+                           std::memcmp(ctx->last_gen_xy.data(), area_xy, (size_t)n * 8) == 0;
+    int st;
+    if (!same_list) {
+        if ((st = acquire_slots(ctx, area_xy, n, slots)) != VX_OK) return st;
+        ctx->last_gen_xy.assign(area_xy, area_xy + 2 * (size_t)n);
+        ctx->last_gen_version = ctx->index_version;
+    }
     if ((st = generate_async(ctx, area_xy, slots, n)) != VX_OK) return st;
     if (voxels_out && (st = copy_slots(ctx, slots, n, ctx->d_voxels, VOXELS_IN_AREA, voxels_out, true)) != VX_OK) return st;
     if (max_height_out && (st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, max_height_out, true)) != VX_OK) return st;
-    if ((st = sync_stream(ctx)) != VX_OK) return st;
+    unsigned long long* c = nullptr;
     if (ctx->timing) {  // work accounting of this call (the roofline numerators)
-        unsigned long long c[6];
-        VX_CUDA(cudaMemcpy(c, ctx->d_counters.p, sizeof c, cudaMemcpyDeviceToHost));
+        VX_CUDA(ctx->h_small.ensure(64));
+        c = ctx->h_small.as<unsigned long long>();
+        VX_CUDA(cudaMemcpyAsync(c, ctx->d_counters.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if ((st = sync_stream(ctx)) != VX_OK) return st;
+    if (c) {
         ctx->timings.cave_columns = (uint32_t)c[0];
         ctx->timings.simplex2_evals = c[2];
         ctx->timings.cave_voxels = c[4];
@@ -560,7 +580,8 @@ int vx_upload(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* voxels
     if (st != VX_OK) return st;
     if ((st = copy_slots(ctx, slots, n, ctx->d_voxels, VOXELS_IN_AREA, const_cast<uint8_t*>(voxels), false)) != VX_OK) return st;
     if ((st = upload_jobs(ctx, area_xy, slots, n)) != VX_OK) return st;
-    launch_column_heights(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_heights, ctx->d_slot_xy, ctx->stream);
+    launch_column_heights(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_heights, ctx->d_slot_xy, ctx->d_planes,
+                          ctx->stream);
     ctx->timings.other_launches += 1;
     VX_CUDA(cudaGetLastError());
     if (max_height_out && (st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, max_height_out, true)) != VX_OK) return st;
@@ -596,6 +617,7 @@ int vx_unload(vx_ctx* ctx, const uint32_t* area_xy, int n) {
     }
     if (any) {
         ctx->map_dirty = true;
+        ++ctx->index_version;
         // keep hand-out order ascending so later batches stay contiguous where possible
         std::sort(ctx->free_slots.begin(), ctx->free_slots.end(), std::greater<int>());
     }
@@ -624,7 +646,7 @@ int vx_column_heights(vx_ctx* ctx, const uint8_t* voxels, int n, uint8_t* max_he
     uint4* j = ctx->h_stage.as<uint4>();
     for (int i = 0; i < n; ++i) j[i] = make_uint4(0, 0, (uint32_t)i, 0);
     VX_CUDA(cudaMemcpyAsync(ctx->d_jobs.p, j, (size_t)n * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
-    launch_column_heights(ctx->d_jobs.as<uint4>(), n, dv, dh, nullptr, ctx->stream);
+    launch_column_heights(ctx->d_jobs.as<uint4>(), n, dv, dh, nullptr, nullptr, ctx->stream);
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaMemcpyAsync(max_height_out, dh, hbytes, cudaMemcpyDeviceToHost, ctx->stream));
     return sync_stream(ctx);
@@ -664,15 +686,14 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
             VX_CUDA(cudaMemsetAsync(counters, 0, 8, ctx->stream));
             {
                 ScopedTimer t(ctx, TM_MESH_COUNT);
-                launch_mesh_prepare(ctx->d_list.as<uint2>(), n, map, ctx->d_jobs.as<uint4>(), ctx->d_plane_flags,
-                                    counters, ctx->d_missing.as<uint2>(), 4u * (uint32_t)n, ctx->stream);
-                launch_mesh_planes(ctx->d_plane_flags, ctx->capacity, ctx->d_voxels, ctx->d_planes, ctx->stream);
+                launch_mesh_prepare(ctx->d_list.as<uint2>(), n, map, ctx->d_jobs.as<uint4>(), counters,
+                                    ctx->d_missing.as<uint2>(), 4u * (uint32_t)n, ctx->stream);
                 launch_mesh_count(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_planes, map,
                                   ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), ctx->stream);
                 launch_mesh_offsets(ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), n,
                                     ctx->d_rec_first.as<uint32_t>(), ctx->d_face_first.as<uint32_t>(), ctx->stream);
             }
-            ctx->timings.mesh_launches += 4;
+            ctx->timings.mesh_launches += 3;
             VX_CUDA(cudaGetLastError());
             VX_CUDA(cudaMemcpyAsync(&back[0], counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
             VX_CUDA(cudaMemcpyAsync(&back[2], ctx->d_rec_first.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -792,7 +813,7 @@ int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_are
     uint32_t* counters = ctx->d_counters.as<uint32_t>();
     {
         ScopedTimer t(ctx, TM_EDIT);
-        launch_apply_edits(ctx->d_edits.as<uint4>(), n, device_map(ctx), ctx->d_voxels, ctx->d_heights,
+        launch_apply_edits(ctx->d_edits.as<uint4>(), n, device_map(ctx), ctx->d_voxels, ctx->d_heights, ctx->d_planes,
                            ctx->d_hash_keys.as<unsigned long long>(), ctx->d_hash_vals.as<uint32_t>(), cap,
                            ctx->d_dirty_flags.as<uint32_t>(), ctx->d_dirty_slots.as<uint32_t>(),
                            counters /* dirty_count */, reinterpret_cast<int32_t*>(counters + 1), ctx->stream);

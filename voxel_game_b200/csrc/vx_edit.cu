@@ -66,7 +66,8 @@ __device__ __forceinline__ void flag_dirty(int slot, uint32_t* dirty_flags, uint
 }
 
 __global__ void edits_apply_kernel(const uint4* __restrict__ edits, int n, AreaMap map,
-                                   uint8_t* pool_voxels, const unsigned long long* hash_keys,
+                                   uint8_t* pool_voxels, uint16_t* pool_planes,
+                                   const unsigned long long* hash_keys,
                                    const uint32_t* hash_vals, uint32_t cap_mask,
                                    uint32_t* dirty_flags, uint32_t* dirty_slots,
                                    uint32_t* dirty_count) {
@@ -79,6 +80,13 @@ __global__ void edits_apply_kernel(const uint4* __restrict__ edits, int n, AreaM
     while (hash_keys[pos] != l.key) pos = (pos + 1) & cap_mask;
     if (hash_vals[pos] != (uint32_t)i + 1u) return;  // a later edit of the same voxel wins
     pool_voxels[(size_t)l.slot * VOXELS_IN_AREA + l.local] = (uint8_t)e.w;
+    {   // keep the area's S / T bit planes (vx_mesh.cu) current: one bit each, in 32-bit words
+        const uint32_t row = l.local >> 4, bit = 1u << ((l.local & 15u) + 16u * (row & 1u));
+        uint32_t* S = reinterpret_cast<uint32_t*>(pool_planes + (size_t)l.slot * (VOXELS_IN_AREA / 8)) + (row >> 1);
+        uint32_t* T = S + VOXELS_IN_AREA / 32;
+        if (e.w != 0u) atomicOr(S, bit); else atomicAnd(S, ~bit);
+        if (is_transparent(e.w)) atomicOr(T, bit); else atomicAnd(T, ~bit);
+    }
     flag_dirty(l.slot, dirty_flags, dirty_slots, dirty_count);
     const uint32_t ax = e.x / AREA_SIZE, ay = e.y / AREA_SIZE, lx = e.x % AREA_SIZE, ly = e.y % AREA_SIZE;
     if (lx == 0) flag_dirty(area_slot(map, ax - 1, ay), dirty_flags, dirty_slots, dirty_count);
@@ -120,14 +128,14 @@ __global__ void __launch_bounds__(256) heightmap_kernel(const uint2* __restrict_
 }  // namespace
 
 void launch_apply_edits(const uint4* edits, int n, AreaMap map, uint8_t* pool_voxels,
-                        uint8_t* pool_heights, unsigned long long* hash_keys, uint32_t* hash_vals,
-                        uint32_t hash_cap, uint32_t* dirty_flags, uint32_t* dirty_slots,
+                        uint8_t* pool_heights, uint16_t* pool_planes, unsigned long long* hash_keys,
+                        uint32_t* hash_vals, uint32_t hash_cap, uint32_t* dirty_flags, uint32_t* dirty_slots,
                         uint32_t* dirty_count, int32_t* status, cudaStream_t stream) {
     if (n <= 0) return;
     const int blocks = (n + 255) / 256;
     edits_claim_kernel<<<blocks, 256, 0, stream>>>(edits, n, map, hash_keys, hash_vals, hash_cap - 1,
                                                    status);
-    edits_apply_kernel<<<blocks, 256, 0, stream>>>(edits, n, map, pool_voxels, hash_keys, hash_vals,
+    edits_apply_kernel<<<blocks, 256, 0, stream>>>(edits, n, map, pool_voxels, pool_planes, hash_keys, hash_vals,
                                                    hash_cap - 1, dirty_flags, dirty_slots,
                                                    dirty_count);
     edits_heights_kernel<<<blocks, 256, 0, stream>>>(edits, n, map, pool_voxels, pool_heights);

@@ -77,12 +77,163 @@ __device__ __forceinline__ uint8_t surface_pick(int biome, unsigned zi, unsigned
     return V_STONE;
 }
 
+struct TreeCell { int8_t x, y, z; uint8_t voxel; };
+enum TreeType { T_NONE = 0, T_SHORT, T_TALL, T_TALL_CACTUS, T_DEAD, T_HUGE, T_SHORT_CACTUS, T_BUSH };
+
+// trees.rs:15-75, indexed by TreeType (trees.rs:77-87)
+__constant__ uint8_t c_tree_cells_n[8] = {0, 8, 9, 3, 2, 27, 1, 1};
+__constant__ TreeCell c_tree_cells[8][27] = {
+    {},
+    // Short
+    {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}, {0, 0, -3, V_WOOD}, {0, 0, -4, V_LEAVES},
+     {0, -1, -3, V_LEAVES}, {0, 1, -3, V_LEAVES}, {1, 0, -3, V_LEAVES}, {-1, 0, -3, V_LEAVES}},
+    // Tall
+    {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}, {0, 0, -3, V_WOOD}, {0, 0, -4, V_WOOD},
+     {0, 0, -5, V_LEAVES}, {0, -1, -4, V_LEAVES}, {0, 1, -4, V_LEAVES}, {1, 0, -4, V_LEAVES},
+     {-1, 0, -4, V_LEAVES}},
+    // TallCactus
+    {{0, 0, -1, V_CACTUS}, {0, 0, -2, V_CACTUS}, {0, 0, -3, V_CACTUS}},
+    // DeadTree
+    {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}},
+    // HugeTree
+    {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}, {0, 0, -3, V_WOOD}, {0, 0, -4, V_WOOD},
+     {0, 0, -5, V_WOOD}, {1, 0, -4, V_WOOD}, {0, 1, -4, V_WOOD}, {0, -1, -4, V_WOOD},
+     {-1, 0, -4, V_WOOD}, {0, -1, -5, V_LEAVES}, {0, -2, -5, V_LEAVES}, {0, 1, -5, V_LEAVES},
+     {0, 2, -5, V_LEAVES}, {1, 0, -5, V_LEAVES}, {2, 0, -5, V_LEAVES}, {-1, 0, -5, V_LEAVES},
+     {-2, 0, -5, V_LEAVES}, {-1, -1, -5, V_LEAVES}, {-1, 1, -5, V_LEAVES}, {1, 1, -5, V_LEAVES},
+     {1, -1, -5, V_LEAVES}, {0, 0, -6, V_LEAVES}, {0, 1, -6, V_LEAVES}, {1, 0, -6, V_LEAVES},
+     {0, -1, -6, V_LEAVES}, {-1, 0, -6, V_LEAVES}, {0, 0, -7, V_LEAVES}},
+    // ShortCactus
+    {{0, 0, -1, V_CACTUS}},
+    // Bush
+    {{0, 0, -1, V_LEAVES}},
+};
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t v, int r) { return (v << r) | (v >> (64 - r)); }
+
+// algorithms.rs:41-55
+__device__ __forceinline__ uint64_t split_mix64(uint64_t s) {
+    uint64_t z = s + 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+// should_generate_tree (trees.rs:142-196) with the weighted pick unrolled per base voxel.
+// TreeType::ALL_TYPES order = Short, Tall, TallCactus, ShortCactus, DeadTree, HugeTree, Bush;
+// weights 1000, 1000, 500, 200, 10, 300, 100 (trees.rs:88-131).
+__device__ int pick_tree(uint8_t base, uint64_t seed, uint32_t ax, uint32_t ay, uint32_t lx,
+                         uint32_t ly, uint32_t lz) {
+    if (!(base == V_GRASS || base == V_DIRT || base == V_CLAY || base == V_SAND)) return T_NONE;
+    // combine_seed (algorithms.rs:28-48)
+    uint64_t c = seed * 0x517cc1b727220a95ull;
+    c = rotl64(c + ax, 11);
+    c = rotl64(c + ay, 13);
+    c = rotl64(c + lx, 17);
+    c = rotl64(c + ly, 19);
+    c = rotl64(c + lz, 23);
+    c *= 0xff51afd7ed558ccdull;
+    const uint64_t r = split_mix64(c);
+    if (((r >> 4) % 60ull) != 0) return T_NONE;
+    const uint64_t pick = split_mix64(r) >> 4;
+    // candidate lists in ALL_TYPES order, filtered by get_allowed_base (trees.rs:104-115)
+    switch (base) {
+    case V_GRASS: {  // Short 1000, Tall 1000, Dead 10, Huge 300, Bush 100  (sum 2410)
+        uint64_t w = pick % 2410ull;
+        if (w < 1000) return T_SHORT;
+        w -= 1000;
+        if (w < 1000) return T_TALL;
+        w -= 1000;
+        if (w < 10) return T_DEAD;
+        w -= 10;
+        if (w < 300) return T_HUGE;
+        return T_BUSH;
+    }
+    case V_CLAY: {  // Short 1000, Tall 1000, Dead 10 (sum 2010)
+        uint64_t w = pick % 2010ull;
+        if (w < 1000) return T_SHORT;
+        w -= 1000;
+        if (w < 1000) return T_TALL;
+        return T_DEAD;
+    }
+    case V_DIRT:  // Dead only
+        return T_DEAD;
+    default: {  // Sand: TallCactus 500, ShortCactus 200, Dead 10, Bush 100 (sum 810)
+        uint64_t w = pick % 810ull;
+        if (w < 500) return T_TALL_CACTUS;
+        w -= 500;
+        if (w < 200) return T_SHORT_CACTUS;
+        w -= 200;
+        if (w < 10) return T_DEAD;
+        return T_BUSH;
+    }
+    }
+}
+
+// generate_trees (trees.rs:198-241): candidates in push order (s_tree indexed x * 16 + y, the
+// column order of generator.rs:54-58; entry = tree type | base z << 8, 0 = none), each checked
+// against the voxels as modified by the trees before it.  Run by ONE warp; lanes = template cells.
+// `vox` may point to shared memory (K1) or to the area in HBM (K2).
+__device__ __forceinline__ void place_trees(uint8_t* vox, const uint16_t* s_tree, unsigned lane) {
+    for (int chunk = 0; chunk < COLUMNS_IN_AREA / 32; ++chunk) {
+        const unsigned mine = s_tree[chunk * 32 + lane];
+        unsigned pending = __ballot_sync(0xFFFFFFFFu, mine != 0);
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const unsigned t = __shfl_sync(0xFFFFFFFFu, mine, src);
+            const int o = chunk * 32 + src;
+            const int type = t & 0xFF, bz = t >> 8, bx = o >> 4, by = o & 15;
+            const int ncell = c_tree_cells_n[type];
+            bool ok = true;
+            int idx = 0;
+            uint8_t cell_voxel = 0;
+            if ((int)lane < ncell) {
+                const TreeCell c = c_tree_cells[type][lane];
+                const int cx = bx + c.x, cy = by + c.y, cz = bz + c.z;
+                cell_voxel = c.voxel;
+                idx = cx + 16 * cy + 256 * cz;
+                ok = cx >= 0 && cx < AREA_SIZE && cy >= 0 && cy < AREA_SIZE && cz >= 0 && cz < AREA_HEIGHT;
+                if (ok) ok = vox[idx] == V_NONE;
+            }
+            if (__all_sync(0xFFFFFFFFu, ok) && (int)lane < ncell) vox[idx] = cell_voxel;
+            __syncwarp();  // placed cells are visible to the next candidate's check
+        }
+    }
+}
+
+// S ("voxel != None") and T ("voxel in Voxel::TRANSPARENT") bit planes of 16-voxel rows from the
+// voxel bytes (layout: vx_mesh.cu).  One row = one 16-byte load.
+__device__ __forceinline__ void planes_of_row(const uint4 q, uint32_t& s_bits, uint32_t& t_bits) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t s = 0, t = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t v = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+        s |= (v != 0u ? 1u : 0u) << i;
+        t |= ((TRANSPARENT_BITS >> v) & 1u) << i;
+    }
+    s_bits = s;
+    t_bits = t;
+}
+__device__ __forceinline__ void planes_of_area(const uint8_t* vox, uint16_t* planes, int tid) {
+    const uint4* rows = reinterpret_cast<const uint4*>(vox);
+    for (int r = tid; r < VOXELS_IN_AREA / 16; r += 256) {
+        uint32_t sb, tb;
+        planes_of_row(rows[r], sb, tb);
+        planes[r] = (uint16_t)sb;
+        planes[VOXELS_IN_AREA / 16 + r] = (uint16_t)tb;
+    }
+}
+
 struct __align__(16) GenSmem {
     uint4 vox[VOXELS_IN_AREA / 16];
     NoiseShared noise;
     unsigned cave_n;
     unsigned cave_base;
     unsigned stone_rows;  // zi <= stone_rows is Stone in every column of the area
+    int min_z;            // smallest z holding generated terrain (= 128 - max H)
+    uint16_t tree[COLUMNS_IN_AREA];  // tree candidates, indexed x * 16 + y
 };
 
 __global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant__ NoiseTables nt,
@@ -92,7 +243,9 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant_
                                                           uint2* __restrict__ slot_xy,
                                                           uint32_t* __restrict__ cave_items,
                                                           uint32_t* __restrict__ cave_count,
-                                                          unsigned long long* __restrict__ stats) {
+                                                          unsigned long long* __restrict__ stats,
+                                                          uint16_t* __restrict__ pool_planes,
+                                                          uint8_t* __restrict__ finished) {
     __shared__ GenSmem sm;
     const int tid = threadIdx.x;
     const uint4 job = jobs[blockIdx.x];
@@ -102,6 +255,7 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant_
     if (tid == 0) {
         sm.cave_n = 0;
         sm.stone_rows = AREA_HEIGHT;
+        sm.min_z = AREA_HEIGHT;
         slot_xy[slot] = make_uint2(ax, ay);
     }
     __syncthreads();
@@ -154,6 +308,8 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant_
     // whole CTA with 16-byte stores (and everything above with None) before the per-column loop
     // writes the few voxels that differ.
     atomicMin(&sm.stone_rows, lake_depth != 0 ? LAKE_TOP_ZI - lake_depth - 1 : H - 4);
+    atomicMin(&sm.min_z, (int)(AREA_HEIGHT - H));
+    if (cave_zone) atomicAdd(&sm.cave_n, 1u);
     __syncthreads();
     const unsigned stone_rows = sm.stone_rows;
     {
@@ -179,19 +335,66 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant_
         vox[tid + 256 * (AREA_HEIGHT - zi)] = v;
     }
 
-    // scratch for K1b / K2: terrain height (7 bits) | cave flag
-    pool_heights[(size_t)slot * COLUMNS_IN_AREA + tid] = (uint8_t)(H | (cave_zone ? 0x80u : 0u));
-    unsigned my_pos = 0;
-    if (cave_zone) my_pos = atomicAdd(&sm.cave_n, 1u);
-    __syncthreads();
-    if (tid == 0 && sm.cave_n) sm.cave_base = atomicAdd(cave_count, sm.cave_n);
-    __syncthreads();
-    if (cave_zone) cave_items[sm.cave_base + my_pos] = slot * COLUMNS_IN_AREA + tid;
     evals2 = __reduce_add_sync(0xFFFFFFFFu, evals2);
     evals3 = __reduce_add_sync(0xFFFFFFFFu, evals3);
     if ((tid & 31) == 0) {
         atomicAdd(&stats[0], (unsigned long long)evals2);
         atomicAdd(&stats[1], (unsigned long long)evals3);
+    }
+    uint8_t* heights = pool_heights + (size_t)slot * COLUMNS_IN_AREA;
+    __syncthreads();  // the area is complete in shared memory
+    const unsigned n_cave = sm.cave_n;  // final since the barrier before the fill
+    __syncthreads();                    // everyone has read it before it is reused as a cursor
+
+    if (n_cave != 0) {
+        // Cave zone in this area: K1b carves it in HBM and K2 finishes it (trees, heights, planes).
+        // Scratch for both: terrain height (7 bits) | cave flag per column; work items per cave column.
+        heights[tid] = (uint8_t)(H | (cave_zone ? 0x80u : 0u));
+        if (tid == 0) {
+            sm.cave_base = atomicAdd(cave_count, n_cave);
+            sm.cave_n = 0;
+            finished[blockIdx.x] = 0;
+        }
+        __syncthreads();
+        if (cave_zone) cave_items[sm.cave_base + atomicAdd(&sm.cave_n, 1u)] = slot * COLUMNS_IN_AREA + tid;
+    } else {
+        // No caves (most areas): trees, column heights and bit planes straight from shared memory.
+        // The topmost generated non-None voxel (generator.rs:91-93,100) is the surface voxel, or the
+        // lake surface (water / ice cap at zi = 34) in a lake column.
+        const unsigned z_top = AREA_HEIGHT - (lake_depth != 0 ? LAKE_TOP_ZI : H);
+        const int tree = pick_tree(vox[tid + 256u * z_top], nt.seed, ax, ay, x, y, z_top);
+        sm.tree[x * 16 + y] = tree ? (uint16_t)(tree | (z_top << 8)) : (uint16_t)0;
+        __syncthreads();
+        if (tid < 32) place_trees(vox, sm.tree, tid);
+        __syncthreads();
+        // update_all_column_heights (area.rs:34-56); everything above min_z - 7 is still None
+        const int z_lo = max(sm.min_z - 8, 0);
+        int zz = z_lo;
+        while (zz < AREA_HEIGHT && is_transparent(vox[tid + 256 * zz])) ++zz;
+        heights[tid] = (uint8_t)(zz < AREA_HEIGHT ? zz : AREA_HEIGHT - 1);
+        // planes: slabs above z_lo are all None, slabs from z_hi on are all Stone; in between one
+        // ballot per slab and warp gives the two rows (y = 2 * warp, 2 * warp + 1) of both planes
+        uint16_t* planes = pool_planes + (size_t)slot * (VOXELS_IN_AREA / 8);
+        const int z_hi = AREA_HEIGHT - (int)stone_rows;
+        {
+            const int z = tid >> 1;  // thread i owns rows 8i .. 8i+7 = half of slab z = i / 2
+            if (z < z_lo || z >= z_hi) {
+                const uint32_t sv = z < z_lo ? 0u : 0xFFFFFFFFu;
+                reinterpret_cast<uint4*>(planes)[tid] = make_uint4(sv, sv, sv, sv);
+                reinterpret_cast<uint4*>(planes + VOXELS_IN_AREA / 16)[tid] = make_uint4(~sv, ~sv, ~sv, ~sv);
+            }
+        }
+        const int wid = tid >> 5;
+        for (int z = z_lo; z < z_hi; ++z) {
+            const unsigned v = vox[tid + 256 * z];
+            const unsigned sb = __ballot_sync(0xFFFFFFFFu, v != 0u);
+            const unsigned tb = __ballot_sync(0xFFFFFFFFu, is_transparent(v));
+            if ((tid & 31) == 0) {  // rows r = 16 z + 2 wid and r + 1 are one 32-bit word
+                reinterpret_cast<uint32_t*>(planes)[8 * z + wid] = sb;
+                reinterpret_cast<uint32_t*>(planes + VOXELS_IN_AREA / 16)[8 * z + wid] = tb;
+            }
+        }
+        if (tid == 0) finished[blockIdx.x] = 1;
     }
 
     uint4* dst = reinterpret_cast<uint4*>(pool_voxels + (size_t)slot * VOXELS_IN_AREA);
@@ -361,105 +564,16 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------- K2
-struct TreeCell { int8_t x, y, z; uint8_t voxel; };
-enum TreeType { T_NONE = 0, T_SHORT, T_TALL, T_TALL_CACTUS, T_DEAD, T_HUGE, T_SHORT_CACTUS, T_BUSH };
-
-// trees.rs:15-75, indexed by TreeType (trees.rs:77-87)
-__constant__ uint8_t c_tree_cells_n[8] = {0, 8, 9, 3, 2, 27, 1, 1};
-__constant__ TreeCell c_tree_cells[8][27] = {
-    {},
-    // Short
-    {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}, {0, 0, -3, V_WOOD}, {0, 0, -4, V_LEAVES},
-     {0, -1, -3, V_LEAVES}, {0, 1, -3, V_LEAVES}, {1, 0, -3, V_LEAVES}, {-1, 0, -3, V_LEAVES}},
-    // Tall
-    {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}, {0, 0, -3, V_WOOD}, {0, 0, -4, V_WOOD},
-     {0, 0, -5, V_LEAVES}, {0, -1, -4, V_LEAVES}, {0, 1, -4, V_LEAVES}, {1, 0, -4, V_LEAVES},
-     {-1, 0, -4, V_LEAVES}},
-    // TallCactus
-    {{0, 0, -1, V_CACTUS}, {0, 0, -2, V_CACTUS}, {0, 0, -3, V_CACTUS}},
-    // DeadTree
-    {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}},
-    // HugeTree
-    {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}, {0, 0, -3, V_WOOD}, {0, 0, -4, V_WOOD},
-     {0, 0, -5, V_WOOD}, {1, 0, -4, V_WOOD}, {0, 1, -4, V_WOOD}, {0, -1, -4, V_WOOD},
-     {-1, 0, -4, V_WOOD}, {0, -1, -5, V_LEAVES}, {0, -2, -5, V_LEAVES}, {0, 1, -5, V_LEAVES},
-     {0, 2, -5, V_LEAVES}, {1, 0, -5, V_LEAVES}, {2, 0, -5, V_LEAVES}, {-1, 0, -5, V_LEAVES},
-     {-2, 0, -5, V_LEAVES}, {-1, -1, -5, V_LEAVES}, {-1, 1, -5, V_LEAVES}, {1, 1, -5, V_LEAVES},
-     {1, -1, -5, V_LEAVES}, {0, 0, -6, V_LEAVES}, {0, 1, -6, V_LEAVES}, {1, 0, -6, V_LEAVES},
-     {0, -1, -6, V_LEAVES}, {-1, 0, -6, V_LEAVES}, {0, 0, -7, V_LEAVES}},
-    // ShortCactus
-    {{0, 0, -1, V_CACTUS}},
-    // Bush
-    {{0, 0, -1, V_LEAVES}},
-};
-
-__device__ __forceinline__ uint64_t rotl64(uint64_t v, int r) { return (v << r) | (v >> (64 - r)); }
-
-// algorithms.rs:41-55
-__device__ __forceinline__ uint64_t split_mix64(uint64_t s) {
-    uint64_t z = s + 0x9e3779b97f4a7c15ull;
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-    return z ^ (z >> 31);
-}
-
-// should_generate_tree (trees.rs:142-196) with the weighted pick unrolled per base voxel.
-// TreeType::ALL_TYPES order = Short, Tall, TallCactus, ShortCactus, DeadTree, HugeTree, Bush;
-// weights 1000, 1000, 500, 200, 10, 300, 100 (trees.rs:88-131).
-__device__ int pick_tree(uint8_t base, uint64_t seed, uint32_t ax, uint32_t ay, uint32_t lx,
-                         uint32_t ly, uint32_t lz) {
-    if (!(base == V_GRASS || base == V_DIRT || base == V_CLAY || base == V_SAND)) return T_NONE;
-    // combine_seed (algorithms.rs:28-48)
-    uint64_t c = seed * 0x517cc1b727220a95ull;
-    c = rotl64(c + ax, 11);
-    c = rotl64(c + ay, 13);
-    c = rotl64(c + lx, 17);
-    c = rotl64(c + ly, 19);
-    c = rotl64(c + lz, 23);
-    c *= 0xff51afd7ed558ccdull;
-    const uint64_t r = split_mix64(c);
-    if (((r >> 4) % 60ull) != 0) return T_NONE;
-    const uint64_t pick = split_mix64(r) >> 4;
-    // candidate lists in ALL_TYPES order, filtered by get_allowed_base (trees.rs:104-115)
-    switch (base) {
-    case V_GRASS: {  // Short 1000, Tall 1000, Dead 10, Huge 300, Bush 100  (sum 2410)
-        uint64_t w = pick % 2410ull;
-        if (w < 1000) return T_SHORT;
-        w -= 1000;
-        if (w < 1000) return T_TALL;
-        w -= 1000;
-        if (w < 10) return T_DEAD;
-        w -= 10;
-        if (w < 300) return T_HUGE;
-        return T_BUSH;
-    }
-    case V_CLAY: {  // Short 1000, Tall 1000, Dead 10 (sum 2010)
-        uint64_t w = pick % 2010ull;
-        if (w < 1000) return T_SHORT;
-        w -= 1000;
-        if (w < 1000) return T_TALL;
-        return T_DEAD;
-    }
-    case V_DIRT:  // Dead only
-        return T_DEAD;
-    default: {  // Sand: TallCactus 500, ShortCactus 200, Dead 10, Bush 100 (sum 810)
-        uint64_t w = pick % 810ull;
-        if (w < 500) return T_TALL_CACTUS;
-        w -= 500;
-        if (w < 200) return T_SHORT_CACTUS;
-        w -= 200;
-        if (w < 10) return T_DEAD;
-        return T_BUSH;
-    }
-    }
-}
-
+// K2: areas that contain cave-zone columns (K1 finished all others in shared memory).
 __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict__ jobs,
+                                                         const uint8_t* __restrict__ finished,
                                                          uint8_t* __restrict__ pool_voxels,
                                                          uint8_t* __restrict__ pool_heights,
+                                                         uint16_t* __restrict__ pool_planes,
                                                          uint64_t seed) {
     __shared__ uint16_t s_tree[COLUMNS_IN_AREA];  // indexed x*16 + y (generator.rs:54-58 order)
     __shared__ int s_min_z;
+    if (finished[blockIdx.x]) return;
     const int tid = threadIdx.x;
     const uint4 job = jobs[blockIdx.x];
     const uint32_t ax = job.x, ay = job.y, slot = job.z;
@@ -482,38 +596,7 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
     const int tree = pick_tree(v, seed, ax, ay, x, y, z);
     s_tree[x * 16 + y] = tree ? (uint16_t)(tree | (z << 8)) : (uint16_t)0;
     __syncthreads();
-
-    // generate_trees (trees.rs:198-241): candidates in push order, each checked against the
-    // voxels as modified by the trees before it.  One warp; lanes = template cells.
-    if (tid < 32) {
-        const unsigned lane = tid;
-        for (int chunk = 0; chunk < COLUMNS_IN_AREA / 32; ++chunk) {
-            const unsigned mine = s_tree[chunk * 32 + lane];
-            unsigned pending = __ballot_sync(0xFFFFFFFFu, mine != 0);
-            while (pending) {
-                const int src = __ffs(pending) - 1;
-                pending &= pending - 1;
-                const unsigned t = __shfl_sync(0xFFFFFFFFu, mine, src);
-                const int o = chunk * 32 + src;
-                const int type = t & 0xFF, bz = t >> 8, bx = o >> 4, by = o & 15;
-                const int ncell = c_tree_cells_n[type];
-                bool ok = true;
-                int idx = 0;
-                uint8_t cell_voxel = 0;
-                if ((int)lane < ncell) {
-                    const TreeCell c = c_tree_cells[type][lane];
-                    const int cx = bx + c.x, cy = by + c.y, cz = bz + c.z;
-                    cell_voxel = c.voxel;
-                    idx = cx + 16 * cy + 256 * cz;
-                    ok = cx >= 0 && cx < AREA_SIZE && cy >= 0 && cy < AREA_SIZE && cz >= 0 &&
-                         cz < AREA_HEIGHT;
-                    if (ok) ok = vox[idx] == V_NONE;
-                }
-                if (__all_sync(0xFFFFFFFFu, ok) && (int)lane < ncell) vox[idx] = cell_voxel;
-                __syncwarp();  // placed cells are visible to the next candidate's check
-            }
-        }
-    }
+    if (tid < 32) place_trees(vox, s_tree, tid);
     __syncthreads();
 
     // update_all_column_heights (area.rs:34-56). Everything above min_z - 7 is still None.
@@ -521,18 +604,21 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
     if (zz < 0) zz = 0;
     while (zz < AREA_HEIGHT && is_transparent(vox[tid + 256 * zz])) ++zz;
     heights[tid] = (uint8_t)(zz < AREA_HEIGHT ? zz : AREA_HEIGHT - 1);
+    planes_of_area(vox, pool_planes + (size_t)slot * (VOXELS_IN_AREA / 8), tid);
 }
 
 // ------------------------------------------------------------------------------------------- L1
 __global__ void __launch_bounds__(256) column_heights_kernel(const uint4* __restrict__ jobs,
                                                              const uint8_t* __restrict__ pool_voxels,
                                                              uint8_t* __restrict__ pool_heights,
-                                                             uint2* __restrict__ slot_xy) {
+                                                             uint2* __restrict__ slot_xy,
+                                                             uint16_t* __restrict__ pool_planes) {
     const int tid = threadIdx.x;
     const uint4 job = jobs[blockIdx.x];
     const uint32_t slot = job.z;
     const uint8_t* vox = pool_voxels + (size_t)slot * VOXELS_IN_AREA;
     if (tid == 0 && slot_xy) slot_xy[slot] = make_uint2(job.x, job.y);
+    if (pool_planes) planes_of_area(vox, pool_planes + (size_t)slot * (VOXELS_IN_AREA / 8), tid);
     int z = 0;
     while (z < AREA_HEIGHT && is_transparent(vox[tid + 256 * z])) ++z;
     pool_heights[(size_t)slot * COLUMNS_IN_AREA + tid] = (uint8_t)(z < AREA_HEIGHT ? z : AREA_HEIGHT - 1);
@@ -559,10 +645,11 @@ __global__ void __launch_bounds__(256) fp64_rate_kernel(double* sink, int iters)
 
 void launch_gen_columns(const NoiseTables& nt, const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
                         uint2* slot_xy, uint32_t* cave_items, uint32_t* cave_count,
-                        unsigned long long* stats, cudaStream_t stream) {
+                        unsigned long long* stats, uint16_t* pool_planes, uint8_t* finished,
+                        cudaStream_t stream) {
     if (n <= 0) return;
     gen_columns_kernel<<<n, 256, 0, stream>>>(nt, jobs, pool_voxels, pool_heights, slot_xy, cave_items,
-                                              cave_count, stats);
+                                              cave_count, stats, pool_planes, finished);
 }
 
 void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const uint32_t* cave_count, uint8_t* pool_voxels,
@@ -572,16 +659,17 @@ void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const u
                                                        pool_heights, slot_xy, stats);
 }
 
-void launch_gen_finish(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
-                       uint64_t seed, cudaStream_t stream) {
+void launch_gen_finish(const uint4* jobs, const uint8_t* finished, int n, uint8_t* pool_voxels,
+                       uint8_t* pool_heights, uint16_t* pool_planes, uint64_t seed, cudaStream_t stream) {
     if (n <= 0) return;
-    gen_finish_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_heights, seed);
+    gen_finish_kernel<<<n, 256, 0, stream>>>(jobs, finished, pool_voxels, pool_heights, pool_planes, seed);
 }
 
 void launch_column_heights(const uint4* jobs, int n, const uint8_t* pool_voxels,
-                           uint8_t* pool_heights, uint2* slot_xy, cudaStream_t stream) {
+                           uint8_t* pool_heights, uint2* slot_xy, uint16_t* pool_planes,
+                           cudaStream_t stream) {
     if (n <= 0) return;
-    column_heights_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_heights, slot_xy);
+    column_heights_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_heights, slot_xy, pool_planes);
 }
 
 void launch_fp64_rate(double* sink, int blocks, int iters, cudaStream_t stream) {

@@ -14,15 +14,18 @@ namespace vx {
 // jobs: n entries {area x, area y, slot, 0}
 void launch_gen_columns(const NoiseTables& nt, const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
                         uint2* slot_xy, uint32_t* cave_items, uint32_t* cave_count,
-                        unsigned long long* stats /* [3]: simplex2, alt simplex3, cave voxels */,
+                        unsigned long long* stats /* [5]: simplex2, alt simplex3, cave voxels, cave evals, cursor */,
+                        uint16_t* pool_planes, uint8_t* finished /* per job: 1 = K1 completed the area */,
                         cudaStream_t stream);
 void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const uint32_t* cave_count,
                       uint8_t* pool_voxels, const uint8_t* pool_heights, const uint2* slot_xy,
                       unsigned long long* stats, int sm_count, cudaStream_t stream);
-void launch_gen_finish(const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
-                       uint64_t seed, cudaStream_t stream);
+void launch_gen_finish(const uint4* jobs, const uint8_t* finished, int n, uint8_t* pool_voxels,
+                       uint8_t* pool_heights, uint16_t* pool_planes, uint64_t seed, cudaStream_t stream);
+// pool_planes may be null (temporary areas that are never meshed)
 void launch_column_heights(const uint4* jobs, int n, const uint8_t* pool_voxels,
-                           uint8_t* pool_heights, uint2* slot_xy, cudaStream_t stream);
+                           uint8_t* pool_heights, uint2* slot_xy, uint16_t* pool_planes,
+                           cudaStream_t stream);
 
 // ---- meshing (K4): count -> offsets -> emit
 struct MeshOut {
@@ -33,14 +36,12 @@ struct MeshOut {
     uint32_t* indices;     // 3 u32 per face
 };
 // planes: per slot uint16 S[2048] ("voxel != None") then uint16 T[2048] ("transparent")
-// prepare: xy -> jobs {ax, ay, slot, 0}; need_plane[slot] = 1 for every area the call reads;
+// The planes of every resident area are kept current by whoever writes its voxels (generation,
+// upload, edits).
+// prepare: xy -> jobs {ax, ay, slot, 0};
 // counters[0] = requested areas not resident, counters[1] = neighbours not resident (-> missing[])
-void launch_mesh_prepare(const uint2* xy, int n, AreaMap map, uint4* jobs, uint8_t* need_plane,
-                         uint32_t* counters, uint2* missing, uint32_t missing_cap,
-                         cudaStream_t stream);
-// one CTA per pool slot [0, n_slots); computes the planes of flagged slots and clears the flag
-void launch_mesh_planes(uint8_t* need_plane, int n_slots, const uint8_t* pool_voxels,
-                        uint16_t* pool_planes, cudaStream_t stream);
+void launch_mesh_prepare(const uint2* xy, int n, AreaMap map, uint4* jobs, uint32_t* counters,
+                         uint2* missing, uint32_t missing_cap, cudaStream_t stream);
 void launch_mesh_count(const uint4* jobs, int n, const uint8_t* pool_voxels,
                        const uint16_t* pool_planes, AreaMap map, uint32_t* rec_count,
                        uint32_t* face_count, cudaStream_t stream);
@@ -52,7 +53,7 @@ void launch_mesh_emit(const uint4* jobs, int n, const uint8_t* pool_voxels,
 // ---- edits (K5) and height map (K6)
 // hash_keys must be filled with 0xFF bytes, hash_vals / dirty_flags / dirty_count / status with 0
 void launch_apply_edits(const uint4* edits, int n, AreaMap map, uint8_t* pool_voxels,
-                        uint8_t* pool_heights, unsigned long long* hash_keys, uint32_t* hash_vals,
+                        uint8_t* pool_heights, uint16_t* pool_planes, unsigned long long* hash_keys, uint32_t* hash_vals,
                         uint32_t hash_cap, uint32_t* dirty_flags /* per slot */,
                         uint32_t* dirty_slots, uint32_t* dirty_count, int32_t* status,
                         cudaStream_t stream);

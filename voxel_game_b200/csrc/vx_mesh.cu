@@ -28,15 +28,14 @@ constexpr int ROWS = VOXELS_IN_AREA / 16;  // 2048 rows of 16 voxels
 
 // ------------------------------------------------------------------------------------- planes
 // plane layout per slot: uint16 S[2048] followed by uint16 T[2048] (8 KiB)
-// One thread per requested area: resolve its pool slot through the device map, flag the bit planes
-// this call will read (the area itself and its four edge neighbours) and report what is not
-// resident.  Keeps the host out of the per-area loop (no hash lookups on the CPU).
+// (the planes of a resident area are written by generation / upload / edits, never here)
+// One thread per requested area: resolve its pool slot through the device map and report what is
+// not resident.  Keeps the host out of the per-area loop (no hash lookups on the CPU).
 //   counters[0] = requested areas that are not resident (an error)
 //   counters[1] = neighbour areas that are not resident (the host generates them and retries)
 __global__ void mesh_prepare_kernel(const uint2* __restrict__ xy, int n, AreaMap map,
-                                    uint4* __restrict__ jobs, uint8_t* __restrict__ need_plane,
-                                    uint32_t* __restrict__ counters, uint2* __restrict__ missing,
-                                    uint32_t missing_cap) {
+                                    uint4* __restrict__ jobs, uint32_t* __restrict__ counters,
+                                    uint2* __restrict__ missing, uint32_t missing_cap) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint2 a = xy[i];
@@ -47,45 +46,14 @@ __global__ void mesh_prepare_kernel(const uint2* __restrict__ xy, int n, AreaMap
         return;
     }
     jobs[i] = make_uint4(a.x, a.y, (uint32_t)slot, 0u);
-    need_plane[slot] = 1;
     const uint2 nb[4] = {make_uint2(a.x + 1, a.y), make_uint2(a.x - 1, a.y), make_uint2(a.x, a.y + 1),
                          make_uint2(a.x, a.y - 1)};
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-        const int ns = area_slot(map, nb[d].x, nb[d].y);
-        if (ns >= 0) {
-            need_plane[ns] = 1;
-        } else {
+    for (int d = 0; d < 4; ++d)
+        if (area_slot(map, nb[d].x, nb[d].y) < 0) {
             const uint32_t k = atomicAdd(&counters[1], 1u);
             if (k < missing_cap) missing[k] = nb[d];
         }
-    }
-}
-
-// one CTA per pool slot; slots whose planes are not needed by this call exit immediately
-__global__ void __launch_bounds__(256) mesh_planes_kernel(uint8_t* __restrict__ need_plane,
-                                                          const uint8_t* __restrict__ pool_voxels,
-                                                          uint16_t* __restrict__ pool_planes) {
-    const int slot = blockIdx.x;
-    if (!need_plane[slot]) return;
-    __syncthreads();
-    if (threadIdx.x == 0) need_plane[slot] = 0;
-    const uint4* vox = reinterpret_cast<const uint4*>(pool_voxels + (size_t)slot * VOXELS_IN_AREA);
-    uint16_t* S = pool_planes + (size_t)slot * (2 * ROWS);
-    uint16_t* T = S + ROWS;
-    for (int r = threadIdx.x; r < ROWS; r += 256) {
-        const uint4 q = vox[r];
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        uint32_t s = 0, t = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint32_t v = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-            s |= (v != 0u ? 1u : 0u) << i;
-            t |= ((TRANSPARENT_BITS >> v) & 1u) << i;
-        }
-        S[r] = (uint16_t)s;
-        T[r] = (uint16_t)t;
-    }
 }
 
 // ------------------------------------------------------------------------------------- masks
@@ -555,18 +523,10 @@ __global__ void __launch_bounds__(256) mesh_emit_kernel(const uint4* __restrict_
 
 }  // namespace
 
-void launch_mesh_prepare(const uint2* xy, int n, AreaMap map, uint4* jobs, uint8_t* need_plane,
-                         uint32_t* counters, uint2* missing, uint32_t missing_cap,
-                         cudaStream_t stream) {
+void launch_mesh_prepare(const uint2* xy, int n, AreaMap map, uint4* jobs, uint32_t* counters,
+                         uint2* missing, uint32_t missing_cap, cudaStream_t stream) {
     if (n <= 0) return;
-    mesh_prepare_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xy, n, map, jobs, need_plane, counters,
-                                                            missing, missing_cap);
-}
-
-void launch_mesh_planes(uint8_t* need_plane, int n_slots, const uint8_t* pool_voxels,
-                        uint16_t* pool_planes, cudaStream_t stream) {
-    if (n_slots <= 0) return;
-    mesh_planes_kernel<<<n_slots, 256, 0, stream>>>(need_plane, pool_voxels, pool_planes);
+    mesh_prepare_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xy, n, map, jobs, counters, missing, missing_cap);
 }
 
 void launch_mesh_count(const uint4* jobs, int n, const uint8_t* pool_voxels,
