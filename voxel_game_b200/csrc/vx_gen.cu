@@ -403,10 +403,8 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant_
 
 // ------------------------------------------------------------------------------------------- K1b
 constexpr int CAVE_CHUNK = 32;  // cave columns claimed by a warp at a time (one per lane)
-// evaluation order of the 14 cave octaves, bit = 1 -> next octave of noise1 (6 octaves, weights
-// .553 .249 .112 .050 .023 .010), 0 -> next octave of noise2 (8 octaves, .650 .228 .080 .028 ...):
-// b0 a0 a1 b1 a2 b2 a3 b3 a4 b4 a5 b5 b6 b7
-constexpr unsigned CAVE_SCHEDULE = 0b00010101010110u;
+// The 14 cave octaves are evaluated in rounds: round k = octave k of noise2 (8 octaves, weights
+// .650 .228 .080 .028 ...) and, for k < 6, octave k of noise1 (6 octaves, .553 .249 .112 .050 ...).
 
 struct CaveWarp {  // per-warp description of the claimed chunk
     uint32_t first[CAVE_CHUNK + 1];  // exclusive prefix of per-column voxel counts
@@ -423,12 +421,12 @@ struct CaveSmem {
 // Max<Fbm, Fbm>::sample + threshold (cave_generator.rs:27-30,43-64) for every voxel of the listed
 // cave-zone columns:  cave  <=>  (70..90).contains(normalise(max(a, b)) as i32)  <=>  0.4 <= m < 0.8
 // up to rounding at the ends.
-//   * Exact early exit.  The 6 + 8 octaves are evaluated in order of decreasing weight (each Fbm
-//     keeps its own octave order, so its running sum is the crate's); after every octave the not
-//     yet evaluated ones are bounded by |simplex| <= SIMPLEX_BOUND, and a voxel stops as soon as
+//   * Exact early exit.  The octaves are evaluated in rounds of one octave per Fbm (each Fbm keeps
+//     its own octave order, so its running sum is the crate's); after every round the not yet
+//     evaluated octaves are bounded by |simplex| <= SIMPLEX_BOUND, and a voxel stops as soon as
 //     the verdict can no longer change.  Undecided voxels run all 14 octaves and use the crate's
 //     expression, so the result never depends on the bound being tight, only on it being valid
-//     (slack 1e-9 against rounding).  ~4 of 14 octaves are needed on average.
+//     (slack 1e-9 against rounding).  ~5 of 14 octaves are needed on average.
 //   * Warp-autonomous persistent lanes.  A warp claims 32 columns from a global counter and
 //     flattens their (column, z) voxels; a lane that has decided its voxel takes the next unclaimed
 //     one at once (ballot + popc, no atomics, no CTA barrier) instead of idling until the slowest
@@ -461,101 +459,108 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
     const unsigned lanes_below = (1u << lane) - 1u;
     unsigned my_evals = 0;
 
+    uint32_t next = 0, total = 0;  // unclaimed voxels [next, total) of the warp's current chunk
+    bool more = true;              // the global list still has unclaimed chunks
+    bool busy = false;
+    double xa = 0, ya = 0, za = 0, xb = 0, yb = 0, zb = 0, a = 0, bsum = 0;
+    unsigned step = 0;
+    size_t out_index = 0;
     while (true) {
-        unsigned chunk = 0;
-        if (lane == 0) chunk = atomicAdd(chunk_counter, 1u);
-        chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
-        if ((unsigned long long)chunk * CAVE_CHUNK >= n_items) break;
-        {
-            const uint32_t idx = chunk * CAVE_CHUNK + lane;
-            uint32_t item = 0, cnt = 0;
-            uint2 org = make_uint2(0, 0);
-            if (idx < n_items) {
-                item = cave_items[idx];
-                const unsigned H = pool_heights[item] & 0x7Fu;
-                // should_be_cave evaluates the noise for CAVE_MIN_ZI <= zi < CAVE_MAX_ZI, zi <= H
-                // (in a cave zone lake_depth is 0, so the voxel is never None/WaterSource)
-                const unsigned top = H < CAVE_MAX_ZI - 1 ? H : CAVE_MAX_ZI - 1;
-                cnt = top >= CAVE_MIN_ZI ? top - CAVE_MIN_ZI + 1 : 0;
-                const uint2 axy = slot_xy[item >> 8];
-                org = make_uint2((item & 15u) + axy.x * AREA_SIZE, ((item >> 4) & 15u) + axy.y * AREA_SIZE);
-            }
-            uint32_t v = cnt;
+        const unsigned want = __ballot_sync(0xFFFFFFFFu, !busy);
+        if (want != 0 && next >= total && more) {
+            // The current chunk is used up: claim the next 32 columns right away.  Lanes that are
+            // still evaluating keep their state in registers, so the warp never drains.
+            unsigned chunk = 0;
+            if (lane == 0) chunk = atomicAdd(chunk_counter, 1u);
+            chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
+            if ((unsigned long long)chunk * CAVE_CHUNK >= n_items) {
+                more = false;
+            } else {
+                const uint32_t idx = chunk * CAVE_CHUNK + lane;
+                uint32_t item = 0, cnt = 0;
+                uint2 org = make_uint2(0, 0);
+                if (idx < n_items) {
+                    item = cave_items[idx];
+                    const unsigned H = pool_heights[item] & 0x7Fu;
+                    // should_be_cave evaluates the noise for CAVE_MIN_ZI <= zi < CAVE_MAX_ZI, zi <= H
+                    // (in a cave zone lake_depth is 0, so the voxel is never None/WaterSource)
+                    const unsigned top = H < CAVE_MAX_ZI - 1 ? H : CAVE_MAX_ZI - 1;
+                    cnt = top >= CAVE_MIN_ZI ? top - CAVE_MIN_ZI + 1 : 0;
+                    const uint2 axy = slot_xy[item >> 8];
+                    org = make_uint2((item & 15u) + axy.x * AREA_SIZE, ((item >> 4) & 15u) + axy.y * AREA_SIZE);
+                }
+                uint32_t v = cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
-                if (lane >= d) v += o;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                    if (lane >= d) v += o;
+                }
+                __syncwarp();  // nobody is still reading the previous chunk's tables
+                cw.item[lane] = item;
+                cw.origin[lane] = org;
+                cw.first[lane + 1] = v;
+                if (lane == 0) cw.first[0] = 0;
+                __syncwarp();
+                total = cw.first[CAVE_CHUNK];
+                next = 0;
+                if (lane == 0) atomicAdd(&stats[2], (unsigned long long)total);  // cave voxels evaluated
             }
-            __syncwarp();  // every lane is done with the previous chunk's tables
-            cw.item[lane] = item;
-            cw.origin[lane] = org;
-            cw.first[lane + 1] = v;
-            if (lane == 0) cw.first[0] = 0;
-            __syncwarp();
         }
-        const uint32_t total = cw.first[CAVE_CHUNK];
-        if (lane == 0) atomicAdd(&stats[2], (unsigned long long)total);  // cave voxels evaluated
-
-        uint32_t next = 0;  // next unclaimed voxel of the chunk (uniform across the warp)
-        bool busy = false;
-        double xa = 0, ya = 0, za = 0, xb = 0, yb = 0, zb = 0, a = 0, bsum = 0;
-        unsigned step = 0, ka = 0, kb = 0;
-        size_t out_index = 0;
-        while (true) {
-            // idle lanes take the next voxels, in lane order
-            const unsigned want = __ballot_sync(0xFFFFFFFFu, !busy);
-            if (!busy) {
-                const uint32_t w = next + __popc(want & lanes_below);
-                if (w < total) {
-                    int lo = 0, hi = CAVE_CHUNK;  // column with first[lo] <= w < first[lo + 1]
+        // idle lanes take the next voxels of the chunk, in lane order
+        if (!busy) {
+            const uint32_t w = next + __popc(want & lanes_below);
+            if (w < total) {
+                int lo = 0, hi = CAVE_CHUNK;  // column with first[lo] <= w < first[lo + 1]
 #pragma unroll
-                    for (int s = 0; s < 5; ++s) {
-                        const int mid = (lo + hi) >> 1;
-                        if (cw.first[mid] <= w) lo = mid; else hi = mid;
-                    }
-                    const uint32_t item = cw.item[lo];
-                    const unsigned zi = CAVE_MIN_ZI + (w - cw.first[lo]);
-                    const uint2 gxy = cw.origin[lo];
-                    const double px = (double)gxy.x, py = (double)gxy.y, pz = (double)zi;
-                    xa = px * f1; ya = py * f1; za = pz * f1;
-                    xb = px * f2; yb = py * f2; zb = pz * f2;
-                    a = 0.0; bsum = 0.0;
-                    step = 0; ka = 0; kb = 0;
-                    out_index = (size_t)(item >> 8) * VOXELS_IN_AREA + (item & 255u) + 256u * (AREA_HEIGHT - zi);
-                    busy = true;
+                for (int s = 0; s < 5; ++s) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cw.first[mid] <= w) lo = mid; else hi = mid;
                 }
+                const uint32_t item = cw.item[lo];
+                const unsigned zi = CAVE_MIN_ZI + (w - cw.first[lo]);
+                const uint2 gxy = cw.origin[lo];
+                const double px = (double)gxy.x, py = (double)gxy.y, pz = (double)zi;
+                xa = px * f1; ya = py * f1; za = pz * f1;
+                xb = px * f2; yb = py * f2; zb = pz * f2;
+                a = 0.0; bsum = 0.0;
+                step = 0;
+                out_index = (size_t)(item >> 8) * VOXELS_IN_AREA + (item & 255u) + 256u * (AREA_HEIGHT - zi);
+                busy = true;
             }
-            next += __popc(want);
-            if (!__any_sync(0xFFFFFFFFu, busy)) break;
-            if (busy) {
-                const bool is_a = (CAVE_SCHEDULE >> step) & 1u;
-                const double sv = simplex3(sm.bytes, is_a ? t1 : t2, is_a ? xa : xb, is_a ? ya : yb,
-                                           is_a ? za : zb);
+        }
+        next = min(total, next + (uint32_t)__popc(want));
+        if (!__any_sync(0xFFFFFFFFu, busy)) {
+            if (!more && next >= total) break;  // list exhausted and nothing in flight
+            continue;                           // an empty chunk (or lanes waiting for the next one)
+        }
+        if (busy) {
+            // one octave of each Fbm per round (noise1 has 6, noise2 has 8): no per-lane selection
+            // of coordinates, and two independent evaluations in flight
+            const unsigned k = step;
+            const double svb = simplex3(sm.bytes, t2, xb, yb, zb);
+            bsum += sm.amp[1][k] * svb;
+            xb *= l2; yb *= l2; zb *= l2;
+            ++my_evals;
+            if (k < 6) {
+                const double sva = simplex3(sm.bytes, t1, xa, ya, za);
+                a += sm.amp[0][k] * sva;
+                xa *= l1; ya *= l1; za *= l1;
                 ++my_evals;
-                ++step;
-                if (is_a) {
-                    a += sm.amp[0][ka] * sv;
-                    xa *= l1; ya *= l1; za *= l1;
-                    ++ka;
-                } else {
-                    bsum += sm.amp[1][kb] * sv;
-                    xb *= l2; yb *= l2; zb *= l2;
-                    ++kb;
-                }
-                const double ca = a * n1, cb = bsum * n2;
-                const double ra = sm.rest[0][ka], rb = sm.rest[1][kb];
-                const double hi_a = ca + ra, hi_b = cb + rb, lo_m = fmax(ca - ra, cb - rb);
-                int verdict = -1;  // -1 undecided, 0 solid, 1 cave
-                if ((hi_a < 0.4 && hi_b < 0.4) || lo_m >= 0.8) verdict = 0;
-                else if (lo_m >= 0.4 && hi_a < 0.8 && hi_b < 0.8) verdict = 1;
-                if (verdict < 0 && step == 14) {  // all octaves done: the crate's own expression
-                    const int c = f64_as_i32(normalise(fmax(ca, cb)));
-                    verdict = (c >= 70 && c < 90) ? 1 : 0;  // cave_generator.rs:10-11,63
-                }
-                if (verdict >= 0) {
-                    if (verdict) pool_voxels[out_index] = V_NONE;  // leave air
-                    busy = false;
-                }
+            }
+            ++step;
+            const double ca = a * n1, cb = bsum * n2;
+            const double ra = sm.rest[0][step < 6 ? step : 6], rb = sm.rest[1][step];
+            const double hi_a = ca + ra, hi_b = cb + rb, lo_m = fmax(ca - ra, cb - rb);
+            int verdict = -1;  // -1 undecided, 0 solid, 1 cave
+            if ((hi_a < 0.4 && hi_b < 0.4) || lo_m >= 0.8) verdict = 0;
+            else if (lo_m >= 0.4 && hi_a < 0.8 && hi_b < 0.8) verdict = 1;
+            if (verdict < 0 && step == 8) {  // all octaves done: the crate's own expression
+                const int c = f64_as_i32(normalise(fmax(ca, cb)));
+                verdict = (c >= 70 && c < 90) ? 1 : 0;  // cave_generator.rs:10-11,63
+            }
+            if (verdict >= 0) {
+                if (verdict) pool_voxels[out_index] = V_NONE;  // leave air
+                busy = false;
             }
         }
     }
