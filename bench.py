@@ -295,8 +295,8 @@ def main():
     s2, s3, cave_vox = work["simplex2_evals"], work["simplex3_evals"], work["cave_voxels"]
     cave3 = work["cave_evals"]  # cave octaves actually evaluated (early exit is exact)
     alt3 = s3 - cave3
-    mesh_bytes = n_mesh * 8192 + info["n_faces"] * 172 + info["n_recs"] * 17
-    plane_bytes = n_gen * (32768 + 8192)
+    mesh_bytes = n_mesh * 9216 + info["n_faces"] * 172 + info["n_recs"] * 17
+    count_bytes = n_mesh * 9216  # own S/T planes (8 KiB) + one-voxel halo of four neighbours (4 x 2048 bits)
 
     def fp64_roof(ops, ms_k):
         a = ops / (ms_k * 1e-3) / 1e12
@@ -312,8 +312,8 @@ def main():
     rooflines = {
         "gen_columns": fp64_roof(s2 * F2_OPS + alt3 * F3_OPS, kern["gen_columns_ms"]),
         "gen_caves": fp64_roof(cave3 * F3_OPS, kern["gen_caves_ms"]),
-        "gen_finish": hbm_roof(n_gen * 256 * 4, kern["gen_finish_ms"]),
-        "mesh_count": hbm_roof(plane_bytes + n_mesh * 8192, kern["mesh_count_ms"]),
+        "gen_finish": hbm_roof(work["cave_columns"] / 256 * (32768 + 8192 + 1024), kern["gen_finish_ms"]),
+        "mesh_count": hbm_roof(count_bytes, kern["mesh_count_ms"]),
         "mesh_emit": hbm_roof(mesh_bytes, kern["mesh_emit_ms"]),
     }
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
