@@ -297,9 +297,28 @@ __global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant_
         bool need = surface_query(biome, zi, H, threshold);
         if (lake_depth != 0 && zi >= LAKE_TOP_ZI - lake_depth) need = false;
         bool alt = false;
-        if (need) {  // should_generate_alternative_voxel (voxel_type_generator.rs:176-188)
-            evals3 += 2;
-            alt = normalise(fbm3<FBM_ALT>(nt, s, px, py, (double)zi)) >= threshold;
+        if (need) {
+            // should_generate_alternative_voxel (voxel_type_generator.rs:176-188): a 2-octave Fbm
+            // (weights 1/1.3 and 0.3/1.3) against a threshold.  The second octave is bounded by
+            // |simplex| <= SIMPLEX_BOUND, so it is evaluated only when it can still change the
+            // verdict; normalise() is monotone, so testing it at the bounds is exact.
+            const FbmParams& q = nt.fbm[FBM_ALT];
+            const unsigned tab = (unsigned)q.table * 256u;
+            double x3 = px * q.frequency, y3 = py * q.frequency, z3 = (double)zi * q.frequency;
+            double acc = 0.0;
+            acc += q.amp[0] * simplex3(s->bytes, tab, x3, y3, z3);
+            evals3 += 1;
+            const double mid = acc * q.norm, rest = SIMPLEX_BOUND * q.amp[1] * q.norm + 1e-9;
+            if (normalise(mid - rest) - 1e-9 >= threshold) {
+                alt = true;
+            } else if (normalise(mid + rest) + 1e-9 < threshold) {
+                alt = false;
+            } else {
+                x3 *= q.lacunarity; y3 *= q.lacunarity; z3 *= q.lacunarity;
+                acc += q.amp[1] * simplex3(s->bytes, tab, x3, y3, z3);
+                evals3 += 1;
+                alt = normalise(acc * q.norm) >= threshold;
+            }
         }
         tops |= (unsigned)surface_pick(biome, zi, H, alt) << (8 * k);
     }
