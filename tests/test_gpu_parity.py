@@ -427,3 +427,103 @@ def test_contexts_with_different_seeds_do_not_interfere():
     o2, _, _, _ = oracle.generate_areas(s2, xy)
     assert np.array_equal(a1, o1) and np.array_equal(b1, o1) and np.array_equal(a2, o2)
     assert not np.array_equal(o1, o2)
+
+
+# ------------------------------------------------------------------------------ full-size configs 4 and 5
+def test_config4_edit_storm_full_size(seed):
+    """BASELINE.json configs[3]: 100 000 random place/break events over a loaded 64x64 region
+    (SURVEY.md 8d C4 recipe), GPU in batches of 1 000 + remesh of dirty areas, against the oracle
+    applying World::set + Renderer::update_location one event at a time."""
+    n, (ax0, ay0) = 64, (62500 - 32, 62500 - 32)
+    world = oracle.World.generate(seed, ax0 - 1, ay0 - 1, n + 2, n + 2)
+    inner = vg.region_xy(ax0, ay0, n, n)
+    world.mesh_areas(inner, threads=0)
+    edits = _edit_storm(0x5EEDED17, 100_000, ax0, ay0, n, world)
+    with vg.Context(0, seed=seed) as c:
+        c.generate(vg.region_xy(ax0 - 1, ay0 - 1, n + 2, n + 2), read=False)
+        c.mesh(inner)
+        dirty_all = set()
+        for lo in range(0, len(edits), 1000):
+            dirty_all |= {(int(a), int(b)) for a, b in c.apply_edits(edits[lo:lo + 1000])}
+        vox, mh = c.read_areas(inner)
+        slots = [world.slot(int(ax), int(ay)) for ax, ay in inner]
+        assert np.array_equal(vox, world.voxels[slots]) and np.array_equal(mh, world.max_height[slots])
+        dirty_inner = np.array(sorted(d for d in dirty_all if ax0 <= d[0] < ax0 + n and ay0 <= d[1] < ay0 + n), np.uint32)
+        assert len(dirty_inner) > 3000          # nearly every area of the region was touched
+        info = c.mesh(dirty_inner)
+        rec_first, face_first, recs, verts, idx = c.mesh_read(info)
+    got = np.zeros((len(dirty_inner), 32768), np.uint8)
+    area_of_rec = np.repeat(np.arange(len(dirty_inner)), np.diff(rec_first.astype(np.int64)))
+    li = (recs["gx"] % 16) + 16 * (recs["gy"] % 16) + 256 * (recs["packed"] & 0xFF)
+    got[area_of_rec, li] = (recs["packed"] >> 16) & 0xFF
+    want = world.face_mask[[world.slot(int(ax), int(ay)) for ax, ay in dirty_inner]]
+    bad = np.flatnonzero((got != want).any(axis=1))
+    assert bad.size == 0, f"face sets differ in {bad.size} areas, first {dirty_inner[bad[0]]}"
+    # vertices of a sample of the dirty areas, byte for byte
+    for i in np.random.default_rng(3).choice(len(dirty_inner), 64, replace=False):
+        ax, ay = int(dirty_inner[i][0]), int(dirty_inner[i][1])
+        _, overts, oidx = world.emit_area(ax, ay)
+        f0, f1 = int(face_first[i]), int(face_first[i + 1])
+        assert verts[4 * f0:4 * f1].tobytes() == overts.tobytes() and np.array_equal(idx[6 * f0:6 * f1], oidx)
+
+
+def test_config5_512x512_pregeneration_sample(seed):
+    """BASELINE.json configs[4] at one GPU's share of the 8-GPU sweep and beyond: the whole 512x512
+    region (262 144 areas, 8 GiB of block IDs) is generated and meshed on one B200; a fixed
+    1 024-area sample and its meshes are compared with the oracle."""
+    n = 512
+    ax0, ay0, _, _ = vg.spawn_region(n)
+    xy = vg.region_xy(ax0, ay0, n, n)
+    rng = np.random.default_rng(11)
+    with vg.Context(0, seed=seed) as c:
+        c.set_timing(True)
+        c.generate(xy, read=False)
+        t_gen = c.timings()
+        info = c.mesh(xy)                       # the ring of 2 048 edge neighbours is generated on demand
+        t_mesh = c.timings()
+        assert c.resident_count() == n * n + 4 * n
+        assert info["n_faces"] > 100_000_000
+        pick = np.sort(rng.choice(len(xy), 1024, replace=False))
+        vox, mh = c.read_areas(xy[pick])
+        ovox, omh, _, _ = oracle.generate_areas(seed, xy[pick])
+        assert np.array_equal(vox, ovox) and np.array_equal(mh, omh)
+        # meshes of 64 of them: re-mesh just those areas (neighbours are resident) and compare
+        sub = xy[pick[::16]]
+        info2 = c.mesh(sub)
+        rec_first, face_first, recs, verts, idx = c.mesh_read(info2)
+    for i, (ax, ay) in enumerate(sub):
+        w = oracle.World.generate(seed, int(ax) - 1, int(ay) - 1, 3, 3, threads=0)
+        nf = w.mesh_area(int(ax), int(ay))
+        orecs, overts, oidx = w.emit_area(int(ax), int(ay), first_face_base=int(face_first[i]))
+        assert int(face_first[i + 1] - face_first[i]) == nf
+        assert recs[rec_first[i]:rec_first[i + 1]].tobytes() == orecs.tobytes()
+        assert verts[4 * face_first[i]:4 * face_first[i + 1]].tobytes() == overts.tobytes()
+    gen_ms = t_gen["gen_columns_ms"] + t_gen["gen_caves_ms"] + t_gen["gen_finish_ms"]
+    print(f"config5 on one B200: gen {gen_ms:.1f} ms, mesh {t_mesh['mesh_count_ms'] + t_mesh['mesh_emit_ms']:.1f} ms "
+          f"for {n * n} areas, {info['n_faces']} faces")
+
+
+def test_concurrent_callers_share_one_context(seed):
+    """The reference enters generation from rayon workers (world_persistence.rs:90-93): eight host
+    threads hammer one context with disjoint batches; every result equals the oracle's."""
+    import threading
+
+    xy = vg.region_xy(62400, 62600, 16, 8)
+    parts = np.array_split(np.arange(len(xy)), 8)
+    out, errs = {}, []
+    with vg.Context(0, seed=seed) as c:
+        def worker(k):
+            try:
+                for _ in range(3):
+                    out[k] = c.generate(xy[parts[k]])
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        assert not errs, errs
+        assert c.resident_count() == len(xy)
+    ovox, omh, _, _ = oracle.generate_areas(seed, xy)
+    for k in range(8):
+        assert np.array_equal(out[k][0], ovox[parts[k]]) and np.array_equal(out[k][1], omh[parts[k]])
