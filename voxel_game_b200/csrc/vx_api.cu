@@ -160,7 +160,7 @@ struct vx_ctx {
     PinnedBuf h_small;   // small results coming back
     DevBuf d_jobs, d_list, d_missing, d_cave_items, d_counters, d_rec_count, d_face_count;
     DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
-    DevBuf d_heightmap, d_light, d_slot_to_job, d_finished;
+    DevBuf d_heightmap, d_light, d_slot_to_job, d_finished, d_warp_totals;
     bool heightmap_init = false;
 
     // last mesh
@@ -460,7 +460,7 @@ void vx_destroy(vx_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters,
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
-                      &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
+                      &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_warp_totals, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
                       &ctx->d_vertices, &ctx->d_indices};
     for (DevBuf* b : bufs) b->release();
     ctx->h_stage.release();
@@ -673,6 +673,7 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
         VX_CUDA(ctx->d_counters.ensure(64));
         VX_CUDA(ctx->d_rec_count.ensure((size_t)n * 4));
         VX_CUDA(ctx->d_face_count.ensure((size_t)n * 4));
+        VX_CUDA(ctx->d_warp_totals.ensure((size_t)n * 64 * 4));
         VX_CUDA(ctx->d_rec_first.ensure((size_t)(n + 1) * 4));
         VX_CUDA(ctx->d_face_first.ensure((size_t)(n + 1) * 4));
         std::memcpy(ctx->h_stage.p, area_xy, xy_bytes);
@@ -689,7 +690,8 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
                 launch_mesh_prepare(ctx->d_list.as<uint2>(), n, map, ctx->d_jobs.as<uint4>(), counters,
                                     ctx->d_missing.as<uint2>(), 4u * (uint32_t)n, ctx->stream);
                 launch_mesh_count(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_planes, map,
-                                  ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), ctx->stream);
+                                  ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(),
+                                  ctx->d_warp_totals.as<uint32_t>(), ctx->stream);
                 launch_mesh_offsets(ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), n,
                                     ctx->d_rec_first.as<uint32_t>(), ctx->d_face_first.as<uint32_t>(), ctx->stream);
             }
@@ -743,7 +745,8 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
         out.indices = ctx->d_indices.as<uint32_t>();
         {
             ScopedTimer t(ctx, TM_MESH_EMIT);
-            launch_mesh_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_planes, device_map(ctx), out, ctx->stream);
+            launch_mesh_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_planes, device_map(ctx),
+                             ctx->d_warp_totals.as<uint32_t>(), out, ctx->stream);
         }
         ctx->timings.mesh_launches += 1;
         VX_CUDA(cudaGetLastError());

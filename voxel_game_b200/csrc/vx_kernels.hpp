@@ -44,11 +44,12 @@ void launch_mesh_prepare(const uint2* xy, int n, AreaMap map, uint4* jobs, uint3
                          uint2* missing, uint32_t missing_cap, cudaStream_t stream);
 void launch_mesh_count(const uint4* jobs, int n, const uint8_t* pool_voxels,
                        const uint16_t* pool_planes, AreaMap map, uint32_t* rec_count,
-                       uint32_t* face_count, cudaStream_t stream);
+                       uint32_t* face_count, uint32_t* warp_totals /* 64 per area */, cudaStream_t stream);
 void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, int n,
                          uint32_t* rec_first, uint32_t* face_first, cudaStream_t stream);
 void launch_mesh_emit(const uint4* jobs, int n, const uint8_t* pool_voxels,
-                      const uint16_t* pool_planes, AreaMap map, MeshOut out, cudaStream_t stream);
+                      const uint16_t* pool_planes, AreaMap map, const uint32_t* warp_totals, MeshOut out,
+                      cudaStream_t stream);
 
 // ---- edits (K5) and height map (K6)
 // hash_keys must be filled with 0xFF bytes, hash_vals / dirty_flags / dirty_count / status with 0

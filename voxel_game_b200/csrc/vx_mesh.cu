@@ -211,11 +211,21 @@ __device__ __forceinline__ unsigned long long warp_inclusive_scan64(unsigned lon
 }
 
 // ------------------------------------------------------------------------------------- count
+// faces | visible voxels << 16 of one row
+__device__ __forceinline__ uint32_t row_counts(const RowMasks& k) {
+    const uint32_t vis = k.m[0] | k.m[1] | k.m[2] | k.m[3] | k.m[4] | k.m[5];
+    return (__popc(k.m[0]) + __popc(k.m[1]) + __popc(k.m[2]) + __popc(k.m[3]) + __popc(k.m[4]) +
+            __popc(k.m[5])) | ((uint32_t)__popc(vis) << 16);
+}
+
+// Per area: faces and visible voxels, in total and per (256-row chunk, warp) -- the latter, 64
+// words per area, let the emit kernel place every row without recounting the area.
 __global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict__ jobs,
                                                          const uint8_t* __restrict__ pool_voxels,
                                                          const uint16_t* __restrict__ pool_planes,
                                                          AreaMap map, uint32_t* __restrict__ rec_count,
-                                                         uint32_t* __restrict__ face_count) {
+                                                         uint32_t* __restrict__ face_count,
+                                                         uint32_t* __restrict__ warp_totals) {
     __shared__ uint32_t s_faces[8], s_recs[8];
     __shared__ PlaneTile tile;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -223,14 +233,15 @@ __global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict
     load_plane_tile(tile, a, tid);
     __syncthreads();
     uint32_t faces = 0, recs = 0;
-    for (int r = tid; r < ROWS; r += 256) {
-        const RowMasks k = row_masks(tile, a, r);
-        faces += __popc(k.m[0]) + __popc(k.m[1]) + __popc(k.m[2]) + __popc(k.m[3]) +
-                 __popc(k.m[4]) + __popc(k.m[5]);
-        recs += __popc(k.m[0] | k.m[1] | k.m[2] | k.m[3] | k.m[4] | k.m[5]);
+    uint32_t* wt = warp_totals + (size_t)blockIdx.x * 64;
+#pragma unroll 1
+    for (int c = 0; c < ROWS / 256; ++c) {
+        const uint32_t v = row_counts(row_masks(tile, a, c * 256 + tid));
+        const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, v);  // <= 32 * 96 faces, 32 * 16 voxels
+        if (lane == 0) wt[c * 8 + wid] = tot;
+        faces += tot & 0xFFFFu;
+        recs += tot >> 16;
     }
-    faces = __reduce_add_sync(0xFFFFFFFFu, faces);
-    recs = __reduce_add_sync(0xFFFFFFFFu, recs);
     if (lane == 0) {
         s_faces[wid] = faces;
         s_recs[wid] = recs;
@@ -417,11 +428,6 @@ __device__ __forceinline__ void flush_faces(EmitSmem& sm, uint32_t count, uint32
     }
 }
 
-__device__ __forceinline__ uint32_t row_counts(const RowMasks& k) {  // faces | visible voxels << 16
-    const uint32_t vis = k.m[0] | k.m[1] | k.m[2] | k.m[3] | k.m[4] | k.m[5];
-    return (__popc(k.m[0]) + __popc(k.m[1]) + __popc(k.m[2]) + __popc(k.m[3]) + __popc(k.m[4]) +
-            __popc(k.m[5])) | ((uint32_t)__popc(vis) << 16);
-}
 __device__ __forceinline__ unsigned long long widen(uint32_t faces_recs16) {
     return (unsigned long long)(faces_recs16 & 0xFFFFu) | ((unsigned long long)(faces_recs16 >> 16) << 32);
 }
@@ -429,7 +435,8 @@ __device__ __forceinline__ unsigned long long widen(uint32_t faces_recs16) {
 __global__ void __launch_bounds__(256) mesh_emit_kernel(const uint4* __restrict__ jobs,
                                                         const uint8_t* __restrict__ pool_voxels,
                                                         const uint16_t* __restrict__ pool_planes,
-                                                        AreaMap map, MeshOut out) {
+                                                        AreaMap map, const uint32_t* __restrict__ warp_totals,
+                                                        MeshOut out) {
     __shared__ EmitSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint4 job = jobs[blockIdx.x];
@@ -440,17 +447,13 @@ __global__ void __launch_bounds__(256) mesh_emit_kernel(const uint4* __restrict_
     load_plane_tile(sm.planes, a, tid);
     __syncthreads();
 
-    // 1. per (chunk, warp) totals.  Row r = chunk * 256 + tid: rows in (z, y) order are the
-    //    reference's z,y loop.  Most (chunk, warp) pairs are all air or all buried and are skipped
-    //    later on the strength of their zero total.
-#pragma unroll 1
-    for (int c = 0; c < CHUNKS; ++c) {
-        const uint32_t v = row_counts(row_masks(sm.planes, a, c * 256 + tid));
-        const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, v);  // <= 32 * 96 faces, 32 * 16 voxels
-        if (lane == 0) {
-            sm.warp_total[c][wid] = tot;
-            sm.part[c][wid] = widen(tot);
-        }
+    // 1. per (chunk, warp) totals from the count kernel.  Row r = chunk * 256 + tid: rows in (z, y)
+    //    order are the reference's z,y loop.  Most (chunk, warp) pairs are all air or all buried and
+    //    are skipped on the strength of their zero total.
+    if (tid < 64) {
+        const uint32_t tot = warp_totals[(size_t)blockIdx.x * 64 + tid];
+        (&sm.warp_total[0][0])[tid] = tot;
+        (&sm.part[0][0])[tid] = widen(tot);
     }
     __syncthreads();
     // 2. exclusive prefix of the 64 (chunk, warp) totals, in that order
@@ -531,10 +534,10 @@ void launch_mesh_prepare(const uint2* xy, int n, AreaMap map, uint4* jobs, uint3
 
 void launch_mesh_count(const uint4* jobs, int n, const uint8_t* pool_voxels,
                        const uint16_t* pool_planes, AreaMap map, uint32_t* rec_count,
-                       uint32_t* face_count, cudaStream_t stream) {
+                       uint32_t* face_count, uint32_t* warp_totals, cudaStream_t stream) {
     if (n <= 0) return;
     mesh_count_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_planes, map, rec_count,
-                                             face_count);
+                                             face_count, warp_totals);
 }
 
 void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, int n,
@@ -543,9 +546,10 @@ void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, 
 }
 
 void launch_mesh_emit(const uint4* jobs, int n, const uint8_t* pool_voxels,
-                      const uint16_t* pool_planes, AreaMap map, MeshOut out, cudaStream_t stream) {
+                      const uint16_t* pool_planes, AreaMap map, const uint32_t* warp_totals, MeshOut out,
+                      cudaStream_t stream) {
     if (n <= 0) return;
-    mesh_emit_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_planes, map, out);
+    mesh_emit_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_planes, map, warp_totals, out);
 }
 
 }  // namespace vx
