@@ -49,6 +49,7 @@ void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, 
                          uint32_t* rec_first, uint32_t* face_first, cudaStream_t stream);
 void launch_mesh_emit(const uint4* jobs, int n, const uint8_t* pool_voxels,
                       const uint16_t* pool_planes, AreaMap map, const uint32_t* warp_totals, MeshOut out,
+                      uint32_t cap_faces, uint32_t cap_recs /* arena capacity; no-op if exceeded */,
                       cudaStream_t stream);
 
 // ---- edits (K5) and height map (K6)

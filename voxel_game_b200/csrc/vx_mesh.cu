@@ -436,7 +436,12 @@ __global__ void __launch_bounds__(256) mesh_emit_kernel(const uint4* __restrict_
                                                         const uint8_t* __restrict__ pool_voxels,
                                                         const uint16_t* __restrict__ pool_planes,
                                                         AreaMap map, const uint32_t* __restrict__ warp_totals,
-                                                        MeshOut out) {
+                                                        MeshOut out, int n, uint32_t cap_faces,
+                                                        uint32_t cap_recs) {
+    // launched speculatively right behind the offsets scan: if the stream does not fit the arena
+    // the whole grid backs off and the host, which sees the totals afterwards, enlarges it and
+    // launches again
+    if (out.face_first[n] > cap_faces || out.rec_first[n] > cap_recs) return;
     __shared__ EmitSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint4 job = jobs[blockIdx.x];
@@ -547,9 +552,10 @@ void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, 
 
 void launch_mesh_emit(const uint4* jobs, int n, const uint8_t* pool_voxels,
                       const uint16_t* pool_planes, AreaMap map, const uint32_t* warp_totals, MeshOut out,
-                      cudaStream_t stream) {
+                      uint32_t cap_faces, uint32_t cap_recs, cudaStream_t stream) {
     if (n <= 0) return;
-    mesh_emit_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_planes, map, warp_totals, out);
+    mesh_emit_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_planes, map, warp_totals, out, n, cap_faces,
+                                            cap_recs);
 }
 
 }  // namespace vx
