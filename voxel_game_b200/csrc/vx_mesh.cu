@@ -364,8 +364,10 @@ __device__ __forceinline__ void build_half_face(uint4* dst, uint32_t desc, int h
     const float cx = (float)((int)(gx0 + x) - LOCATION_OFFSET);
     const float cy = (float)((int)(gy0 + (rr & 15)) - LOCATION_OFFSET);
     const float cz = (float)(rr >> 4);
-    // get_partial_height_offset (mesh_generator.rs:490-498): k / 5 in f32
-    const float ho = partial_height(voxel) ? (float)(voxel - V_WATER1 + 1) / 5.0f : 0.0f;
+    // get_partial_height_offset (mesh_generator.rs:490-498): k / 5 in f32.  A correctly rounded
+    // f32 division k.0 / 5.0 is the f32 nearest to k/5, i.e. the literal below: no divide needed.
+    const float ho = voxel == V_WATER1 ? 0.2f : voxel == V_WATER2 ? 0.4f : voxel == V_WATER3 ? 0.6f
+                   : voxel == V_WATER4 ? 0.8f : 0.0f;
     const float xm = cx - 0.5f, xp = cx + 0.5f, ym = cy - 0.5f, yp = cy + 0.5f;
     const float zt = cz - 0.5f + ho, zb = cz + 0.5f;
     // v coordinate of uv corners {0,1} (high) and {2,3} (low): UV_REPEATING 1/0; TOP_UV 0.625/0.375,
