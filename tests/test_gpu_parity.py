@@ -527,3 +527,60 @@ def test_concurrent_callers_share_one_context(seed):
     ovox, omh, _, _ = oracle.generate_areas(seed, xy)
     for k in range(8):
         assert np.array_equal(out[k][0], ovox[parts[k]]) and np.array_equal(out[k][1], omh[parts[k]])
+
+
+def test_residency_churn_keeps_map_and_pool_consistent(seed):
+    """World::retain_areas-style churn (world.rs:196-240): load, unload, load again in random
+    batches, with pool growth in between.  After every round every resident area reads back
+    bit-exact, unloaded ones are gone, and meshing a resident patch still matches the oracle
+    (exercises the host/device area hash map incl. deletions, slot reuse, scattered slot runs)."""
+    rng = np.random.default_rng(42)
+    universe = vg.region_xy(62440, 62470, 24, 24)
+    ovox, omh, _, _ = oracle.generate_areas(seed, universe)
+    key = {(int(a), int(b)): i for i, (a, b) in enumerate(universe)}
+    resident = set()
+    with vg.Context(0, seed=seed) as c:
+        for rnd in range(8):
+            add = [tuple(map(int, universe[i])) for i in rng.choice(len(universe), 150, replace=False)]
+            c.generate(np.array(add, np.uint32), read=False)
+            resident |= set(add)
+            drop = [a for a in resident if rng.random() < 0.4]
+            c.unload(np.array(drop, np.uint32).reshape(-1, 2))
+            resident -= set(drop)
+            assert c.resident_count() == len(resident)
+            lst = np.array(sorted(resident), np.uint32)
+            perm = rng.permutation(len(lst))
+            v, h = c.read_areas(lst[perm])
+            want = [key[tuple(map(int, a))] for a in lst[perm]]
+            assert np.array_equal(v, ovox[want]) and np.array_equal(h, omh[want]), f"round {rnd}"
+            for a in drop[:3]:
+                with pytest.raises(vg.VxError):
+                    c.read_areas(np.array([a], np.uint32))
+        # mesh a 6x6 patch (vx_mesh generates whatever neighbours the churn left missing)
+        patch = vg.region_xy(62445, 62475, 6, 6)
+        c.generate(patch, read=False)
+        world = oracle.World.generate(seed, 62444, 62474, 8, 8)
+        _compare_mesh(c, world, patch)
+
+
+def test_config1_spawn_area_at_shipped_render_distance(seed):
+    """BASELINE.json configs[0]: what VoxelEngine::load_world does at the default render distance 8
+    (voxel_engine.rs:114-135): world.load_all_blocking over the 19x19 load zone, then
+    renderer.load_all_blocking over the 15x15 render zone, zones in the reference's own order
+    (active_zone.rs:10-56).  Everything compared with the oracle."""
+    from voxel_game_b200 import world as w
+
+    load = w.load_zone_on_world_load(w.SPAWN_AREA, 8)
+    render = w.render_zone_on_world_load(w.SPAWN_AREA, 8)
+    assert len(load) == 361 and len(render) == 225
+    with vg.Context(0, seed=seed) as c:
+        vox, mh = c.generate(load)
+        ovox, omh, _, _ = oracle.generate_areas(seed, load)
+        assert np.array_equal(vox, ovox) and np.array_equal(mh, omh)
+        # oracle world as a dense grid (the zone lists are x-outer, the grid is y-outer)
+        grid = vg.region_xy(int(load[:, 0].min()), int(load[:, 1].min()), 19, 19)
+        gv, gh, _, _ = oracle.generate_areas(seed, grid)
+        world = oracle.World(int(grid[0][0]), int(grid[0][1]), 19, 19, gv, gh)
+        faces = _compare_mesh(c, world, render)
+        assert c.resident_count() == 361        # the render zone's neighbours were all loaded already
+        assert faces > 50_000
