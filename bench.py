@@ -191,6 +191,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if world > 1:  # keep each rank (and the pinned host buffers it first-touches) next to its GPU;
+        try:       # not at N = 1, where the CPU baseline must see every host core
+            import pynvml
+
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:
+            pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
