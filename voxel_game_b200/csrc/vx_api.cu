@@ -1,4 +1,4 @@
-// vx_api.cu -- the C ABI of include/voxel_cuda.h: context, resident-area pool, dense area map,
+// vx_api.cu -- the C ABI of include/voxel_cuda.h: context, resident-area pool, area hash map,
 // kernel sequencing, host<->device copies.  No torch, no CPU compute path: a context cannot be
 // created without a CUDA device, and every voxel / height / vertex is produced by a kernel.
 #include <algorithm>
@@ -141,7 +141,6 @@ struct vx_ctx {
     uint8_t* d_heights = nullptr;
     uint16_t* d_planes = nullptr;
     uint2* d_slot_xy = nullptr;
-    uint8_t* d_plane_flags = nullptr;  // per slot: planes wanted by the running vx_mesh
     std::vector<uint64_t> slot_key;    // per slot; ~0 = free
     std::vector<int> free_slots;
     HostAreaMap index;
@@ -245,10 +244,8 @@ int grow_pool(vx_ctx* ctx, int min_capacity) {
     uint8_t *nv = nullptr, *nh = nullptr;
     uint16_t* np = nullptr;
     uint2* nxy = nullptr;
-    uint8_t* nf = nullptr;
     auto alloc_all = [&](int cap) -> cudaError_t {
         cudaError_t e;
-        if ((e = cudaMalloc(&nf, (size_t)cap)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&nv, (size_t)cap * VOXELS_IN_AREA)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&nh, (size_t)cap * COLUMNS_IN_AREA)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&np, (size_t)cap * 4096 * sizeof(uint16_t))) != cudaSuccess) return e;
@@ -257,16 +254,15 @@ int grow_pool(vx_ctx* ctx, int min_capacity) {
     cudaError_t e = alloc_all(new_cap);
     if (e != cudaSuccess && new_cap > min_capacity) {
         cudaGetLastError();
-        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy); cudaFree(nf);
-        nv = nh = nf = nullptr; np = nullptr; nxy = nullptr;
+        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy);
+        nv = nh = nullptr; np = nullptr; nxy = nullptr;
         new_cap = min_capacity;
         e = alloc_all(new_cap);
     }
     if (e != cudaSuccess) {
-        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy); cudaFree(nf);
+        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy);
         return fail_cuda(ctx, e, "pool allocation");
     }
-    VX_CUDA(cudaMemsetAsync(nf, 0, (size_t)new_cap, ctx->stream));
     if (ctx->capacity > 0) {
         const size_t c = (size_t)ctx->capacity;
         VX_CUDA(cudaMemcpyAsync(nv, ctx->d_voxels, c * VOXELS_IN_AREA, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -275,10 +271,8 @@ int grow_pool(vx_ctx* ctx, int min_capacity) {
         VX_CUDA(cudaMemcpyAsync(nxy, ctx->d_slot_xy, c * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
         VX_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
-        cudaFree(ctx->d_plane_flags);
     }
     ctx->d_voxels = nv; ctx->d_heights = nh; ctx->d_planes = np; ctx->d_slot_xy = nxy;
-    ctx->d_plane_flags = nf;
     ctx->slot_key.resize(new_cap, ~0ull);
     for (int s = new_cap - 1; s >= ctx->capacity; --s) ctx->free_slots.push_back(s);  // pop -> ascending
     ctx->capacity = new_cap;
@@ -466,7 +460,6 @@ void vx_destroy(vx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
-    cudaFree(ctx->d_plane_flags);
     DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_gen_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters,
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,

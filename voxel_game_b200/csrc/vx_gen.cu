@@ -3,16 +3,16 @@
 //   K1  gen_columns : one CTA per area, one thread per voxel column.  Column samples
 //                     (generator.rs:108-132), voxel types (voxel_type_generator.rs:31-174), lake
 //                     override (lake_generator.rs:54-74).  The 32 KiB area is assembled in shared
-//                     memory and written to HBM with 16-byte coalesced stores.  Cave-zone columns
+//                     memory and written to HBM with 16-byte coalesced stores.  An area without
+//                     cave-zone columns (most) is FINISHED here, still in shared memory: tree
+//                     candidates and ordered placement (trees.rs:142-241), column heights
+//                     (area.rs:34-56) and the S/T bit planes the mesher reads.  Cave-zone columns
 //                     are appended to a work list instead of being carved in place.
-//   K1b gen_caves   : persistent CTAs over the compacted list of cave-zone columns; inside a CTA
-//                     the (column, z) pairs are flattened so that every lane evaluates one
-//                     14-octave 3-D noise value (cave_generator.rs:43-64).  This is the FP64-bound
-//                     part; flattening removes the 60x per-column load imbalance.
-//   K2  gen_finish  : one CTA per area: tree candidates (trees.rs:142-196), ordered placement
-//                     (trees.rs:198-241, one warp, lanes = template cells), column heights
-//                     (area.rs:34-56).
-//   L1  column_heights : Area::update_all_column_heights for uploaded areas.
+//   K1b gen_caves   : persistent, warp-autonomous lanes over the list of cave-zone columns
+//                     (cave_generator.rs:43-64): exact early exit on octave bounds, lanes refill
+//                     themselves, warps claim the next chunk while still busy.  FP64-bound part.
+//   K2  gen_finish  : areas with cave columns only: trees, heights, planes from HBM after carving.
+//   L1  column_heights : Area::update_all_column_heights (+ planes) for uploaded areas.
 //
 // FP64 only (the reference's libnoise is f64 throughout), no FMA contraction (-fmad=false).
 #include "vx_kernels.hpp"
