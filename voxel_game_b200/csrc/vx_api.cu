@@ -134,6 +134,7 @@ struct vx_ctx {
 
     bool has_seed = false;
     NoiseTables tables{};
+    NoiseImage* d_noise_image = nullptr;  // lookup tables of the current seed (vx_tables.hpp)
 
     // resident-area pool: slot s owns voxels[s*32768..], heights[s*256..], planes[s*4096 u16..]
     int capacity = 0;
@@ -460,6 +461,7 @@ void vx_destroy(vx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
+    cudaFree(ctx->d_noise_image);
     DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_gen_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters,
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
@@ -527,7 +529,12 @@ int vx_set_seed(vx_ctx* ctx, uint64_t seed) {
     std::lock_guard<std::mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->d_noise_image) VX_CUDA(cudaMalloc(&ctx->d_noise_image, sizeof(NoiseImage)));
     build_noise_tables(seed, &ctx->tables);
+    NoiseImage image;
+    build_noise_image(ctx->tables, &image);
+    VX_CUDA(cudaMemcpy(ctx->d_noise_image, &image, sizeof image, cudaMemcpyHostToDevice));
+    ctx->tables.image = ctx->d_noise_image;
     ctx->has_seed = true;
     return VX_OK;
 }

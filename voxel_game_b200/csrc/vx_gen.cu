@@ -236,7 +236,7 @@ struct __align__(16) GenSmem {
     uint16_t tree[COLUMNS_IN_AREA];  // tree candidates, indexed x * 16 + y
 };
 
-__global__ void __launch_bounds__(256) gen_columns_kernel(const __grid_constant__ NoiseTables nt,
+__global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_constant__ NoiseTables nt,
                                                           const uint4* __restrict__ jobs,
                                                           uint8_t* __restrict__ pool_voxels,
                                                           uint8_t* __restrict__ pool_heights,
@@ -431,7 +431,7 @@ struct CaveWarp {  // per-warp description of the claimed chunk
     uint2 origin[CAVE_CHUNK];        // global x, y of the column
 };
 struct CaveSmem {
-    uint8_t bytes[3 * TAB_BYTES];  // permutation tables and their reduced copies (vx_noise.cuh)
+    alignas(16) uint8_t bytes[3 * TAB_BYTES];  // permutation tables and their reduced copies (vx_noise.cuh)
     double amp[2][8];              // [0] = noise1, [1] = noise2: running amplitudes
     double rest[2][9];             // bound of the octaves not yet evaluated (cave_rest) + slack
     CaveWarp warp[8];
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
     const int tid = threadIdx.x, lane = tid & 31;
     const FbmParams& q1 = nt.fbm[FBM_CAVE1];
     const FbmParams& q2 = nt.fbm[FBM_CAVE2];
-    load_noise_tables(sm.bytes, nt, tid, 256);
+    load_noise_image(sm.bytes, nt, 3 * TAB_BYTES, tid, 256);
     if (tid < 8) {
         sm.amp[0][tid] = tid < 6 ? q1.amp[tid] : 0.0;
         sm.amp[1][tid] = q2.amp[tid];

@@ -23,49 +23,26 @@
 
 namespace vx {
 
-// The per-seed tables travel as a __grid_constant__ kernel parameter (2 KiB, constant bank, one
-// copy per launch): contexts with different seeds in one process cannot disturb each other, which a
-// module-wide __constant__ symbol would allow.
-
-// 24 unit gradients at 7.5 deg + k*15 deg (digits as published with OpenSimplex2)
-__constant__ double c_grad2[24][2] = {
-    {0.130526192220052, 0.99144486137381},    {0.38268343236509, 0.923879532511287},
-    {0.608761429008721, 0.793353340291235},   {0.793353340291235, 0.608761429008721},
-    {0.923879532511287, 0.38268343236509},    {0.99144486137381, 0.130526192220051},
-    {0.99144486137381, -0.130526192220051},   {0.923879532511287, -0.38268343236509},
-    {0.793353340291235, -0.60876142900872},   {0.608761429008721, -0.793353340291235},
-    {0.38268343236509, -0.923879532511287},   {0.130526192220052, -0.99144486137381},
-    {-0.130526192220052, -0.99144486137381},  {-0.38268343236509, -0.923879532511287},
-    {-0.608761429008721, -0.793353340291235}, {-0.793353340291235, -0.60876142900872},
-    {-0.923879532511287, -0.38268343236509},  {-0.99144486137381, -0.130526192220052},
-    {-0.99144486137381, 0.130526192220051},   {-0.923879532511287, 0.38268343236509},
-    {-0.793353340291235, 0.608761429008721},  {-0.608761429008721, 0.793353340291235},
-    {-0.38268343236509, 0.923879532511287},   {-0.130526192220052, 0.99144486137381}};
-
-// shared-memory working copy of the tables (random access; constant cache would serialise).
-// `bytes` = perm (4 x 256) | perm % 24 (4 x 256) | perm % 12 (4 x 256); table t starts at t * 256.
+// The Fbm parameters travel as a __grid_constant__ kernel parameter and the lookup tables as a
+// per-context image in device memory: contexts with different seeds in one process cannot disturb
+// each other, which a module-wide __constant__ symbol would allow.  Lookups are random per lane,
+// so the tables are read from a shared-memory copy (the constant cache would serialise them); the
+// copy is 216 coalesced 16-byte loads per CTA.
 constexpr unsigned TAB_BYTES = TAB_COUNT * 256;
 constexpr unsigned OFF_P24 = TAB_BYTES;      // byte offset of the % 24 copies
 constexpr unsigned OFF_P12 = 2 * TAB_BYTES;  // byte offset of the % 12 copies
-struct NoiseShared {
-    uint8_t bytes[3 * TAB_BYTES];
-    double grad2[24][2];
-};
+using NoiseShared = NoiseImage;
 
-__device__ __forceinline__ void load_noise_tables(uint8_t* bytes, const NoiseTables& nt, int tid,
-                                                  int nthreads) {
-    for (int i = tid; i < (int)TAB_BYTES; i += nthreads) {
-        const unsigned v = (&nt.perm[0][0])[i];
-        bytes[i] = (uint8_t)v;
-        bytes[OFF_P24 + i] = (uint8_t)(v % 24u);
-        bytes[OFF_P12 + i] = (uint8_t)(v % 12u);
-    }
+// first `bytes` bytes of the image (a multiple of 16): the cave kernel only needs the tables
+__device__ __forceinline__ void load_noise_image(void* dst, const NoiseTables& nt, unsigned bytes, int tid,
+                                                 int nthreads) {
+    const uint4* src = static_cast<const uint4*>(nt.image);
+    for (unsigned i = tid; i < bytes / 16u; i += nthreads) static_cast<uint4*>(dst)[i] = __ldg(src + i);
 }
 
 __device__ __forceinline__ void load_noise_shared(NoiseShared* s, const NoiseTables& nt, int tid,
                                                   int nthreads) {
-    load_noise_tables(s->bytes, nt, tid, nthreads);
-    for (int i = tid; i < 48; i += nthreads) (&s->grad2[0][0])[i] = (&c_grad2[0][0])[i];
+    load_noise_image(s, nt, (unsigned)sizeof(NoiseImage), tid, nthreads);
 }
 
 // floor(x) as a double and as an int, |x| < 2^31, in two FP64 adds and nothing else: adding

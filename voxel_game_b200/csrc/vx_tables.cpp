@@ -141,6 +141,32 @@ void build_noise_tables(uint64_t seed, NoiseTables* out) {
     }
 }
 
+// 24 unit gradients at 7.5 deg + k*15 deg (digits as published with OpenSimplex2)
+static const double GRAD2[24][2] = {
+    {0.130526192220052, 0.99144486137381},    {0.38268343236509, 0.923879532511287},
+    {0.608761429008721, 0.793353340291235},   {0.793353340291235, 0.608761429008721},
+    {0.923879532511287, 0.38268343236509},    {0.99144486137381, 0.130526192220051},
+    {0.99144486137381, -0.130526192220051},   {0.923879532511287, -0.38268343236509},
+    {0.793353340291235, -0.60876142900872},   {0.608761429008721, -0.793353340291235},
+    {0.38268343236509, -0.923879532511287},   {0.130526192220052, -0.99144486137381},
+    {-0.130526192220052, -0.99144486137381},  {-0.38268343236509, -0.923879532511287},
+    {-0.608761429008721, -0.793353340291235}, {-0.793353340291235, -0.60876142900872},
+    {-0.923879532511287, -0.38268343236509},  {-0.99144486137381, -0.130526192220052},
+    {-0.99144486137381, 0.130526192220051},   {-0.923879532511287, 0.38268343236509},
+    {-0.793353340291235, 0.608761429008721},  {-0.608761429008721, 0.793353340291235},
+    {-0.38268343236509, 0.923879532511287},   {-0.130526192220052, 0.99144486137381}};
+
+void build_noise_image(const NoiseTables& tables, NoiseImage* out) {
+    const unsigned n = TAB_COUNT * 256;
+    for (unsigned i = 0; i < n; ++i) {
+        const unsigned v = (&tables.perm[0][0])[i];
+        out->bytes[i] = (uint8_t)v;
+        out->bytes[n + i] = (uint8_t)(v % 24u);
+        out->bytes[2 * n + i] = (uint8_t)(v % 12u);
+    }
+    std::memcpy(out->grad2, GRAD2, sizeof GRAD2);
+}
+
 uint64_t hash_world_name(const char* name) {
     // SipHash-1-3, k0 = k1 = 0, message = name bytes followed by 0xFF
     uint64_t v0 = 0x736f6d6570736575ull, v1 = 0x646f72616e646f6dull, v2 = 0x6c7967656e657261ull,

@@ -1,5 +1,6 @@
-// vx_tables.hpp -- seed-dependent noise tables, built once per seed on the host and uploaded to
-// __constant__ memory.  Replaces the nine Simplex::new(..).fbm(..) constructions that the
+// vx_tables.hpp -- seed-dependent noise tables, built once per seed on the host: the Fbm
+// parameters travel to the kernels as a launch parameter, the lookup tables as a 3.4 KiB image in
+// device memory that every CTA copies into shared memory.  Replaces the nine Simplex::new(..).fbm(..) constructions that the
 // reference repeats for every area (generator.rs:135-146; terrain_type.rs:15-24;
 // biome_type.rs:19-23; cave_generator.rs:26-34; voxel_type_generator.rs:24-29;
 // lake_generator.rs:21-25).
@@ -41,6 +42,15 @@ struct NoiseTables {
     // cave_rest[f][k]: upper bound of |norm * sum_{i >= k} amp_i * simplex_i| for the two cave
     // Fbms after k evaluated octaves (SIMPLEX_BOUND * norm * sum of the remaining amplitudes)
     double cave_rest[2][9];
+    const void* image;  // device copy of the NoiseImage of this seed (set by the owner of the tables)
+};
+
+// What the kernels keep in shared memory, byte for byte: the four permutation tables, their
+// "% 24" and "% 12" copies (the last lookup of a 2-D / 3-D corner only feeds that remainder), and
+// the 24 2-D gradients.  bytes = perm (4 x 256) | perm % 24 (4 x 256) | perm % 12 (4 x 256).
+struct alignas(16) NoiseImage {
+    uint8_t bytes[3 * TAB_COUNT * 256];
+    double grad2[24][2];
 };
 
 // |simplex3| <= 1.00004 for this gradient set and normalisation constant (1/76.8808 is the true
@@ -48,6 +58,7 @@ struct NoiseTables {
 constexpr double SIMPLEX_BOUND = 1.0001;
 
 void build_noise_tables(uint64_t seed, NoiseTables* out);
+void build_noise_image(const NoiseTables& tables, NoiseImage* out);
 uint64_t hash_world_name(const char* name);
 
 }  // namespace vx
