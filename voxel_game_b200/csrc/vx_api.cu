@@ -162,7 +162,7 @@ struct vx_ctx {
     PinnedBuf h_small;   // small results coming back
     DevBuf d_jobs, d_gen_jobs, d_list, d_missing, d_cave_items, d_counters, d_rec_count, d_face_count;
     DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
-    DevBuf d_heightmap, d_light, d_slot_to_job, d_finished, d_warp_totals;
+    DevBuf d_heightmap, d_light, d_slot_to_job, d_finished, d_warp_totals, d_mesh_nbr;
     bool heightmap_init = false;
 
     // last mesh
@@ -465,7 +465,7 @@ void vx_destroy(vx_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_gen_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters,
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
-                      &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_warp_totals, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
+                      &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_warp_totals, &ctx->d_mesh_nbr, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
                       &ctx->d_vertices, &ctx->d_indices};
     for (DevBuf* b : bufs) b->release();
     ctx->h_stage.release();
@@ -679,6 +679,7 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
         VX_CUDA(ctx->h_small.ensure(64 + (size_t)4 * n * sizeof(uint2)));
         VX_CUDA(ctx->d_list.ensure(xy_bytes));
         VX_CUDA(ctx->d_jobs.ensure((size_t)n * sizeof(uint4)));
+        VX_CUDA(ctx->d_mesh_nbr.ensure((size_t)n * sizeof(uint4)));
         VX_CUDA(ctx->d_missing.ensure((size_t)4 * n * sizeof(uint2)));
         VX_CUDA(ctx->d_counters.ensure(64));
         VX_CUDA(ctx->d_rec_count.ensure((size_t)n * 4));
@@ -711,7 +712,7 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
             out.vertices = ctx->d_vertices.as<uint4>();
             out.indices = ctx->d_indices.as<uint32_t>();
             ScopedTimer t(ctx, TM_MESH_EMIT);
-            launch_mesh_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_planes, device_map(ctx),
+            launch_mesh_emit(ctx->d_jobs.as<uint4>(), ctx->d_mesh_nbr.as<uint4>(), n, ctx->d_voxels, ctx->d_planes,
                              ctx->d_warp_totals.as<uint32_t>(), out, cap_faces, cap_recs, ctx->stream);
             ctx->timings.mesh_launches += 1;
         };
@@ -722,11 +723,12 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
             {
                 ScopedTimer t(ctx, TM_MESH_COUNT);
                 if (!jobs_ready) {
-                    launch_mesh_prepare(ctx->d_list.as<uint2>(), n, map, ctx->d_jobs.as<uint4>(), counters,
+                    launch_mesh_prepare(ctx->d_list.as<uint2>(), n, map, ctx->d_jobs.as<uint4>(),
+                                        ctx->d_mesh_nbr.as<uint4>(), counters,
                                         ctx->d_missing.as<uint2>(), 4u * (uint32_t)n, ctx->stream);
                     ctx->timings.mesh_launches += 1;
                 }
-                launch_mesh_count(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_planes, map,
+                launch_mesh_count(ctx->d_jobs.as<uint4>(), ctx->d_mesh_nbr.as<uint4>(), n, ctx->d_voxels, ctx->d_planes,
                                   ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(),
                                   ctx->d_warp_totals.as<uint32_t>(), ctx->stream);
                 launch_mesh_offsets(ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), n,

@@ -38,17 +38,17 @@ struct MeshOut {
 // planes: per slot uint16 S[2048] ("voxel != None") then uint16 T[2048] ("transparent")
 // The planes of every resident area are kept current by whoever writes its voxels (generation,
 // upload, edits).
-// prepare: xy -> jobs {ax, ay, slot, 0};
+// prepare: xy -> jobs {ax, ay, slot, 0} and nbr {slots of the +x, -x, +y, -y neighbours};
 // counters[0] = requested areas not resident, counters[1] = neighbours not resident (-> missing[])
-void launch_mesh_prepare(const uint2* xy, int n, AreaMap map, uint4* jobs, uint32_t* counters,
+void launch_mesh_prepare(const uint2* xy, int n, AreaMap map, uint4* jobs, uint4* nbr, uint32_t* counters,
                          uint2* missing, uint32_t missing_cap, cudaStream_t stream);
-void launch_mesh_count(const uint4* jobs, int n, const uint8_t* pool_voxels,
-                       const uint16_t* pool_planes, AreaMap map, uint32_t* rec_count,
+void launch_mesh_count(const uint4* jobs, const uint4* nbr, int n, const uint8_t* pool_voxels,
+                       const uint16_t* pool_planes, uint32_t* rec_count,
                        uint32_t* face_count, uint32_t* warp_totals /* 64 per area */, cudaStream_t stream);
 void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, int n,
                          uint32_t* rec_first, uint32_t* face_first, cudaStream_t stream);
-void launch_mesh_emit(const uint4* jobs, int n, const uint8_t* pool_voxels,
-                      const uint16_t* pool_planes, AreaMap map, const uint32_t* warp_totals, MeshOut out,
+void launch_mesh_emit(const uint4* jobs, const uint4* nbr, int n, const uint8_t* pool_voxels,
+                      const uint16_t* pool_planes, const uint32_t* warp_totals, MeshOut out,
                       uint32_t cap_faces, uint32_t cap_recs /* arena capacity; no-op if exceeded */,
                       cudaStream_t stream);
 

@@ -29,12 +29,13 @@ constexpr int ROWS = VOXELS_IN_AREA / 16;  // 2048 rows of 16 voxels
 // ------------------------------------------------------------------------------------- planes
 // plane layout per slot: uint16 S[2048] followed by uint16 T[2048] (8 KiB)
 // (the planes of a resident area are written by generation / upload / edits, never here)
-// One thread per requested area: resolve its pool slot through the device map and report what is
-// not resident.  Keeps the host out of the per-area loop (no hash lookups on the CPU).
+// One thread per requested area: resolve its pool slot and those of its four edge neighbours
+// through the device map and report what is not resident.  Keeps the host out of the per-area loop (no hash lookups on the CPU).
 //   counters[0] = requested areas that are not resident (an error)
 //   counters[1] = neighbour areas that are not resident (the host generates them and retries)
 __global__ void mesh_prepare_kernel(const uint2* __restrict__ xy, int n, AreaMap map,
-                                    uint4* __restrict__ jobs, uint32_t* __restrict__ counters,
+                                    uint4* __restrict__ jobs, uint4* __restrict__ nbr,
+                                    uint32_t* __restrict__ counters,
                                     uint2* __restrict__ missing, uint32_t missing_cap) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -43,17 +44,23 @@ __global__ void mesh_prepare_kernel(const uint2* __restrict__ xy, int n, AreaMap
     if (slot < 0) {
         atomicAdd(&counters[0], 1u);
         jobs[i] = make_uint4(a.x, a.y, 0u, 0u);
+        nbr[i] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     jobs[i] = make_uint4(a.x, a.y, (uint32_t)slot, 0u);
     const uint2 nb[4] = {make_uint2(a.x + 1, a.y), make_uint2(a.x - 1, a.y), make_uint2(a.x, a.y + 1),
                          make_uint2(a.x, a.y - 1)};
+    uint32_t ns[4];
 #pragma unroll
-    for (int d = 0; d < 4; ++d)
-        if (area_slot(map, nb[d].x, nb[d].y) < 0) {
+    for (int d = 0; d < 4; ++d) {
+        const int sl = area_slot(map, nb[d].x, nb[d].y);
+        ns[d] = sl < 0 ? (uint32_t)slot : (uint32_t)sl;  // placeholder; the host generates it and retries
+        if (sl < 0) {
             const uint32_t k = atomicAdd(&counters[1], 1u);
             if (k < missing_cap) missing[k] = nb[d];
         }
+    }
+    nbr[i] = make_uint4(ns[0], ns[1], ns[2], ns[3]);  // +x, -x, +y, -y: the kernels below do no lookups
 }
 
 // ------------------------------------------------------------------------------------- masks
@@ -171,23 +178,19 @@ __device__ __forceinline__ RowMasks row_masks(const PlaneTile& p, const AreaView
     return k;
 }
 
-__device__ __forceinline__ AreaView make_view(const uint4 job, const AreaMap& map,
+__device__ __forceinline__ AreaView make_view(const uint4 job, const uint4 nb,
                                               const uint8_t* pool_voxels,
                                               const uint16_t* pool_planes) {
     AreaView a;
-    const uint32_t ax = job.x, ay = job.y;
     const int slot = (int)job.z;
     a.vox = pool_voxels + (size_t)slot * VOXELS_IN_AREA;
     a.S = pool_planes + (size_t)slot * (2 * ROWS);
     a.T = a.S + ROWS;
-    const int ns[4] = {area_slot(map, ax + 1, ay), area_slot(map, ax - 1, ay),
-                       area_slot(map, ax, ay + 1), area_slot(map, ax, ay - 1)};
+    const uint32_t ns[4] = {nb.x, nb.y, nb.z, nb.w};  // resident: vx_mesh generates missing ones first
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        // the host guarantees residency (vx_mesh generates missing neighbours first)
-        const int sl = ns[i] < 0 ? slot : ns[i];
-        a.vox_n[i] = pool_voxels + (size_t)sl * VOXELS_IN_AREA;
-        a.T_n[i] = pool_planes + (size_t)sl * (2 * ROWS) + ROWS;
+        a.vox_n[i] = pool_voxels + (size_t)ns[i] * VOXELS_IN_AREA;
+        a.T_n[i] = pool_planes + (size_t)ns[i] * (2 * ROWS) + ROWS;
     }
     return a;
 }
@@ -218,18 +221,25 @@ __device__ __forceinline__ uint32_t row_counts(const RowMasks& k) {
             __popc(k.m[5])) | ((uint32_t)__popc(vis) << 16);
 }
 
+// Per (256-row chunk, warp) of an area: faces (<= 3072, 12 bits) | visible voxels (<= 512, 10 bits)
+// << 12 | rows that have faces (<= 32, 6 bits) << 22.
+__device__ __forceinline__ uint32_t pack_warp_total(uint32_t faces, uint32_t recs, uint32_t rows) {
+    return faces | (recs << 12) | (rows << 22);
+}
+
 // Per area: faces and visible voxels, in total and per (256-row chunk, warp) -- the latter, 64
 // words per area, let the emit kernel place every row without recounting the area.
 __global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict__ jobs,
+                                                         const uint4* __restrict__ nbr,
                                                          const uint8_t* __restrict__ pool_voxels,
                                                          const uint16_t* __restrict__ pool_planes,
-                                                         AreaMap map, uint32_t* __restrict__ rec_count,
+                                                         uint32_t* __restrict__ rec_count,
                                                          uint32_t* __restrict__ face_count,
                                                          uint32_t* __restrict__ warp_totals) {
     __shared__ uint32_t s_faces[8], s_recs[8];
     __shared__ PlaneTile tile;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const AreaView a = make_view(jobs[blockIdx.x], map, pool_voxels, pool_planes);
+    const AreaView a = make_view(jobs[blockIdx.x], nbr[blockIdx.x], pool_voxels, pool_planes);
     load_plane_tile(tile, a, tid);
     __syncthreads();
     uint32_t faces = 0, recs = 0;
@@ -238,7 +248,8 @@ __global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict
     for (int c = 0; c < ROWS / 256; ++c) {
         const uint32_t v = row_counts(row_masks(tile, a, c * 256 + tid));
         const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, v);  // <= 32 * 96 faces, 32 * 16 voxels
-        if (lane == 0) wt[c * 8 + wid] = tot;
+        const uint32_t rows = __popc(__ballot_sync(0xFFFFFFFFu, v != 0u));
+        if (lane == 0) wt[c * 8 + wid] = pack_warp_total(tot & 0xFFFFu, tot >> 16, rows);
         faces += tot & 0xFFFFu;
         recs += tot >> 16;
     }
@@ -337,27 +348,54 @@ __device__ __forceinline__ uint32_t make_desc(int r, int x, int dir, int ord, ui
            (voxel << 21);
 }
 
-constexpr int LIST_FACES = 3072;   // face descriptors buffered per flush (typical area: ~600)
+constexpr int LIST_FACES = 3072;   // face descriptors buffered per flush (typical area: ~800)
+constexpr int ROW_CAP = 512;       // rows with faces staged per pass (typical area: ~100)
 constexpr int WARP_FACES = 16;     // faces a warp assembles per staging round (2 lanes per face)
-constexpr int FACE_U4 = 10;        // uint4 per face (4 vertices x 40 B); with lane pairs writing 5
-                                   // uint4 each at (lane/2)*10 + (lane%2)*5 the 8 lanes of a store
-                                   // phase hit 8 different bank groups, so no padding is needed
+constexpr int FACE_U4 = 10;        // uint4 per face (4 vertices x 40 B)
+constexpr int HALF_U4 = 5;         // a lane stages two vertices: 5 uint4 at (lane / 2) * 10 + (lane % 2) * 5,
+                                   // so the 8 lanes of a store phase hit 8 different bank groups
 constexpr int CHUNKS = ROWS / 256; // rows per thread
+
+// The rows of the current pass that have faces, in any order (40 B per row).
+struct RowEntries {
+    uint4 vox[ROW_CAP];    // the row's 16 voxel bytes
+    uint4 masks[ROW_CAP];  // face masks L | R << 16, F | B << 16, D | U << 16; row index
+    uint2 first[ROW_CAP];  // area-local index of the row's first face and first record
+};
 
 struct EmitSmem {
     PlaneTile planes;
     uint32_t list[LIST_FACES];
-    uint4 stage[8][WARP_FACES * FACE_U4];  // one staging tile per warp
-    unsigned long long part[CHUNKS][8];    // faces | recs << 32 of the rows before (chunk, warp)
-    uint32_t warp_total[CHUNKS][8];        // faces | recs << 16 of (chunk, warp); 0 = nothing to do
-    unsigned long long total;
+    union {  // rows feed the descriptor list, then the list is flushed through the staging tiles
+        RowEntries rows;
+        uint4 stage[8][WARP_FACES * FACE_U4];  // one staging tile per warp
+    } u;
+    unsigned long long part[CHUNKS * 8 + 1];  // running sums before (chunk, warp); [64] = area totals
+    uint32_t tot[CHUNKS * 8];                 // the packed totals themselves; 0 = nothing to do
+};
+static_assert(sizeof(RowEntries) <= sizeof(uint4) * 8 * WARP_FACES * FACE_U4, "row entries alias the staging tiles");
+
+// running sums: faces (<= 98 304) | visible voxels (<= 32 768) << 20 | rows (<= 2048) << 40
+__device__ __forceinline__ unsigned long long widen(uint32_t w) {
+    return (unsigned long long)(w & 0xFFFu) | ((unsigned long long)((w >> 12) & 0x3FFu) << 20) |
+           ((unsigned long long)(w >> 22) << 40);
+}
+__device__ __forceinline__ uint32_t faces_of(unsigned long long p) { return (uint32_t)p & 0xFFFFFu; }
+__device__ __forceinline__ uint32_t recs_of(unsigned long long p) { return (uint32_t)(p >> 20) & 0xFFFFFu; }
+__device__ __forceinline__ uint32_t rows_of(unsigned long long p) { return (uint32_t)(p >> 40); }
+
+// What the four vertices of a face are assembled from.  MeshGenerator::get_verticies_for_voxel
+// (mesh_generator.rs:200-488); all f32 operations are the reference's: offset -/+ 0.5,
+// "offset_z - 0.5 + height_offset", "side_uv.y -= height_offset".
+struct FaceParts {
+    float xm, xp, ym, yp, zt, zb;  // the two candidate values of each coordinate
+    float vhi, vlo;                // v of uv corners {0,1} and {2,3}
+    uint32_t fnx, fny, fnz;        // normal (bit patterns)
+    uint32_t codes;                // four 5-bit corner codes (CORNERS_*)
 };
 
-// Two vertices (2*half, 2*half + 1) of one face = 20 words = 5 uint4 written to the staging tile.
-// MeshGenerator::get_verticies_for_voxel (mesh_generator.rs:200-488); all f32 operations are the
-// reference's: offset -/+ 0.5, "offset_z - 0.5 + height_offset", "side_uv.y -= height_offset".
-__device__ __forceinline__ void build_half_face(uint4* dst, uint32_t desc, int half, uint32_t gx0,
-                                                uint32_t gy0) {
+__device__ __forceinline__ FaceParts decode_face(uint32_t desc, uint32_t gx0, uint32_t gy0) {
+    FaceParts p;
     const int rr = desc & 2047, x = (desc >> 11) & 15, dir = (desc >> 15) & 7;
     const uint32_t voxel = desc >> 21;
     // location.rs:19-27: (internal - 1_000_000) as f32; mesh_generator.rs:120-123
@@ -368,10 +406,10 @@ __device__ __forceinline__ void build_half_face(uint4* dst, uint32_t desc, int h
     // f32 division k.0 / 5.0 is the f32 nearest to k/5, i.e. the literal below: no divide needed.
     const float ho = voxel == V_WATER1 ? 0.2f : voxel == V_WATER2 ? 0.4f : voxel == V_WATER3 ? 0.6f
                    : voxel == V_WATER4 ? 0.8f : 0.0f;
-    const float xm = cx - 0.5f, xp = cx + 0.5f, ym = cy - 0.5f, yp = cy + 0.5f;
-    const float zt = cz - 0.5f + ho, zb = cz + 0.5f;
-    // v coordinate of uv corners {0,1} (high) and {2,3} (low): UV_REPEATING 1/0; TOP_UV 0.625/0.375,
-    // SIDE_UV 1/0.75, BOTTOM_UV 0.25/0 for voxels with different faces (mesh_generator.rs:61-99)
+    p.xm = cx - 0.5f; p.xp = cx + 0.5f; p.ym = cy - 0.5f; p.yp = cy + 0.5f;
+    p.zt = cz - 0.5f + ho; p.zb = cz + 0.5f;
+    // UV_REPEATING 1/0; TOP_UV 0.625/0.375, SIDE_UV 1/0.75, BOTTOM_UV 0.25/0 for voxels with
+    // different faces (mesh_generator.rs:61-99)
     float vhi = 1.0f, vlo = 0.0f;
     if ((DIFFERENT_FACES_BITS >> voxel) & 1u) {
         vhi = dir == 5 ? 0.625f : (dir == 4 ? 0.25f : 1.0f);
@@ -381,42 +419,58 @@ __device__ __forceinline__ void build_half_face(uint4* dst, uint32_t desc, int h
         if (vhi > 0.0f) vhi -= ho;
         if (vlo > 0.0f) vlo -= ho;
     }
+    p.vhi = vhi; p.vlo = vlo;
     // normals (mesh_generator.rs:45-50)
-    const float nx = dir == 0 ? 1.0f : (dir == 1 ? -1.0f : 0.0f);
-    const float ny = dir == 2 ? 1.0f : (dir == 3 ? -1.0f : 0.0f);
-    const float nz = dir == 4 ? 1.0f : (dir == 5 ? -1.0f : 0.0f);
+    p.fnx = __float_as_uint(dir == 0 ? 1.0f : (dir == 1 ? -1.0f : 0.0f));
+    p.fny = __float_as_uint(dir == 2 ? 1.0f : (dir == 3 ? -1.0f : 0.0f));
+    p.fnz = __float_as_uint(dir == 4 ? 1.0f : (dir == 5 ? -1.0f : 0.0f));
     const unsigned long long packed = dir < 3 ? CORNERS_LRF : CORNERS_BDU;
-    const uint32_t codes = (uint32_t)(packed >> (20 * (dir < 3 ? dir : dir - 3))) >> (10 * half);
+    p.codes = (uint32_t)(packed >> (20 * (dir < 3 ? dir : dir - 3))) & 0xFFFFFu;
+    return p;
+}
+
+// Two vertices (2*half, 2*half + 1) of a face = 20 words = 5 uint4 written to the staging tile.
+__device__ __forceinline__ void build_half_face(uint4* dst, const FaceParts& p, int half) {
+    const uint32_t codes = p.codes >> (10 * half);
     const uint32_t c0 = codes & 31u, c1 = (codes >> 5) & 31u;
     const uint32_t uv0 = c0 >> 3, uv1 = c1 >> 3;
     const uint32_t COLOR = 0xFFFFFFFFu;  // mesh_generator.rs:43
-    const uint32_t fnx = __float_as_uint(nx), fny = __float_as_uint(ny), fnz = __float_as_uint(nz);
-    dst[0] = make_uint4(__float_as_uint((c0 & 1u) ? xp : xm), __float_as_uint((c0 & 2u) ? yp : ym),
-                        __float_as_uint((c0 & 4u) ? zb : zt),
+    dst[0] = make_uint4(__float_as_uint((c0 & 1u) ? p.xp : p.xm), __float_as_uint((c0 & 2u) ? p.yp : p.ym),
+                        __float_as_uint((c0 & 4u) ? p.zb : p.zt),
                         __float_as_uint((uv0 == 1u || uv0 == 2u) ? 1.0f : 0.0f));
-    dst[1] = make_uint4(__float_as_uint(uv0 < 2u ? vhi : vlo), COLOR, fnx, fny);
-    dst[2] = make_uint4(fnz, 0u, __float_as_uint((c1 & 1u) ? xp : xm),
-                        __float_as_uint((c1 & 2u) ? yp : ym));
-    dst[3] = make_uint4(__float_as_uint((c1 & 4u) ? zb : zt),
+    dst[1] = make_uint4(__float_as_uint(uv0 < 2u ? p.vhi : p.vlo), COLOR, p.fnx, p.fny);
+    dst[2] = make_uint4(p.fnz, 0u, __float_as_uint((c1 & 1u) ? p.xp : p.xm),
+                        __float_as_uint((c1 & 2u) ? p.yp : p.ym));
+    dst[3] = make_uint4(__float_as_uint((c1 & 4u) ? p.zb : p.zt),
                         __float_as_uint((uv1 == 1u || uv1 == 2u) ? 1.0f : 0.0f),
-                        __float_as_uint(uv1 < 2u ? vhi : vlo), COLOR);
-    dst[4] = make_uint4(fnx, fny, fnz, 0u);
+                        __float_as_uint(uv1 < 2u ? p.vhi : p.vlo), COLOR);
+    dst[4] = make_uint4(p.fnx, p.fny, p.fnz, 0u);
 }
 
 // Write `count` buffered faces (descriptors sm.list[0..count)) starting at stream face `first`.
 // Each warp works on its own: 16 faces are assembled in the warp's staging tile by lane pairs, then
-// the tile leaves as 160 consecutive 16-byte pieces; no CTA barrier is involved.
+// the tile leaves as 160 consecutive 16-byte pieces; no CTA barrier is involved.  (One lane per
+// face with 80-byte half tiles needs fewer instructions but writes partial sectors: measured slower.)
 __device__ __forceinline__ void flush_faces(EmitSmem& sm, uint32_t count, uint32_t first,
                                             const MeshOut& out, uint32_t gx0, uint32_t gy0, int tid) {
     const int lane = tid & 31, wid = tid >> 5;
-    uint4* tile = sm.stage[wid];
+    uint4* tile = sm.u.stage[wid];
+#pragma unroll 1
     for (uint32_t base = wid * WARP_FACES; base < count; base += 8 * WARP_FACES) {
         const uint32_t nfaces = min((uint32_t)WARP_FACES, count - base);
         const uint32_t f = lane >> 1;
-        if (f < nfaces) build_half_face(&tile[f * FACE_U4 + (lane & 1) * 5], sm.list[base + f], lane & 1, gx0, gy0);
+        if (f < nfaces) {
+            const FaceParts p = decode_face(sm.list[base + f], gx0, gy0);
+            build_half_face(&tile[f * FACE_U4 + (lane & 1) * HALF_U4], p, lane & 1);
+        }
         __syncwarp();
         uint4* vdst = out.vertices + (size_t)(first + base) * FACE_U4;
-        for (uint32_t w = lane; w < nfaces * FACE_U4; w += 32) vdst[w] = tile[w];
+        if (nfaces == WARP_FACES) {
+#pragma unroll
+            for (int it = 0; it < WARP_FACES * FACE_U4 / 32; ++it) vdst[it * 32 + lane] = tile[it * 32 + lane];
+        } else {
+            for (uint32_t w = lane; w < nfaces * FACE_U4; w += 32) vdst[w] = tile[w];
+        }
         __syncwarp();
     }
     // indices: [0,1,2,0,2,3] + 4*ord as three u32 words per face (mesh_generator.rs:44,131-139)
@@ -430,120 +484,142 @@ __device__ __forceinline__ void flush_faces(EmitSmem& sm, uint32_t count, uint32
     }
 }
 
-__device__ __forceinline__ unsigned long long widen(uint32_t faces_recs16) {
-    return (unsigned long long)(faces_recs16 & 0xFFFFu) | ((unsigned long long)(faces_recs16 >> 16) << 32);
-}
-
-__global__ void __launch_bounds__(256) mesh_emit_kernel(const uint4* __restrict__ jobs,
+// One CTA per area, three phases per pass (one pass for all but the densest areas):
+//   A  one thread per row (the reference's z,y order): face masks from the plane tile, position of
+//      the row's faces / records from the count kernel's (chunk, warp) totals and a warp scan; rows
+//      that have faces are staged in shared memory with their 16 voxel bytes.  (chunk, warp) pairs
+//      whose total is 0 -- all air or all buried, most of them -- are skipped.
+//   B  one thread per (staged row, x): visible voxels write their record and push their face
+//      descriptors.  The faces cluster in a few z levels, i.e. in a few warps of phase A; spreading
+//      them over the CTA by voxel is what keeps the warps evenly busy.
+//   C  flush: lane pairs expand descriptors into 160-byte vertex blocks (flush_faces).
+__global__ void __launch_bounds__(256, 5) mesh_emit_kernel(const uint4* __restrict__ jobs,
+                                                        const uint4* __restrict__ nbr,
                                                         const uint8_t* __restrict__ pool_voxels,
                                                         const uint16_t* __restrict__ pool_planes,
-                                                        AreaMap map, const uint32_t* __restrict__ warp_totals,
+                                                        const uint32_t* __restrict__ warp_totals,
                                                         MeshOut out, int n, uint32_t cap_faces,
                                                         uint32_t cap_recs) {
+    __shared__ EmitSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // everything this CTA needs from global memory before the planes, requested together
+    const uint32_t stream_faces = out.face_first[n], stream_recs = out.rec_first[n];
+    const uint4 job = jobs[blockIdx.x];
+    const uint4 nb = nbr[blockIdx.x];
+    const uint32_t face_base = out.face_first[blockIdx.x];
+    const uint32_t rec_base = out.rec_first[blockIdx.x];
+    uint2 w2 = make_uint2(0u, 0u);
+    if (wid == 0) w2 = reinterpret_cast<const uint2*>(warp_totals + (size_t)blockIdx.x * (CHUNKS * 8))[lane];
     // launched speculatively right behind the offsets scan: if the stream does not fit the arena
     // the whole grid backs off and the host, which sees the totals afterwards, enlarges it and
     // launches again
-    if (out.face_first[n] > cap_faces || out.rec_first[n] > cap_recs) return;
-    __shared__ EmitSmem sm;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint4 job = jobs[blockIdx.x];
-    const AreaView a = make_view(job, map, pool_voxels, pool_planes);
+    if (stream_faces > cap_faces || stream_recs > cap_recs) return;
+    const AreaView a = make_view(job, nb, pool_voxels, pool_planes);
     const uint32_t gx0 = job.x * AREA_SIZE, gy0 = job.y * AREA_SIZE;
-    const uint32_t face_base = out.face_first[blockIdx.x];
-    const uint32_t rec_base = out.rec_first[blockIdx.x];
     load_plane_tile(sm.planes, a, tid);
-    __syncthreads();
-
-    // 1. per (chunk, warp) totals from the count kernel.  Row r = chunk * 256 + tid: rows in (z, y)
-    //    order are the reference's z,y loop.  Most (chunk, warp) pairs are all air or all buried and
-    //    are skipped on the strength of their zero total.
-    if (tid < 64) {
-        const uint32_t tot = warp_totals[(size_t)blockIdx.x * 64 + tid];
-        (&sm.warp_total[0][0])[tid] = tot;
-        (&sm.part[0][0])[tid] = widen(tot);
+    if (wid == 0) {  // running sums of the 64 (chunk, warp) totals, two per lane
+        const unsigned long long t0 = widen(w2.x), t1 = widen(w2.y);
+        const unsigned long long inc = warp_inclusive_scan64(t0 + t1, lane);
+        sm.part[2 * lane] = inc - t0 - t1;
+        sm.part[2 * lane + 1] = inc - t1;
+        sm.tot[2 * lane] = w2.x;
+        sm.tot[2 * lane + 1] = w2.y;
+        if (lane == 31) sm.part[CHUNKS * 8] = inc;
     }
     __syncthreads();
-    // 2. exclusive prefix of the 64 (chunk, warp) totals, in that order
-    if (tid < 64) {
-        const unsigned long long v = (&sm.part[0][0])[tid];
-        const unsigned long long inc = warp_inclusive_scan64(v, lane);
-        (&sm.part[0][0])[tid] = inc - v;  // exclusive inside its half of 32
-        if (tid == 31) sm.total = inc;    // sum of entries 0..31
-    }
-    __syncthreads();
-    if (tid >= 32 && tid < 64) (&sm.part[0][0])[tid] += sm.total;
-    __syncthreads();
-    if (tid == 0) sm.total = sm.part[CHUNKS - 1][7] + widen(sm.warp_total[CHUNKS - 1][7]);
-    __syncthreads();
-    const uint32_t total_faces = (uint32_t)sm.total;
 
-    // 3. records straight to global; face descriptors into the list, in windows if the area has
-    //    more faces than the list holds (worst case 98 304)
-    for (uint32_t lo = 0; lo < total_faces; lo += LIST_FACES) {
-        const uint32_t hi = min(total_faces, lo + LIST_FACES);
+    const int x = tid & 15;
+    const uint32_t below = (1u << x) - 1u, below2 = below | (below << 16);
+    const unsigned long long area_total = sm.part[CHUNKS * 8];
+    const bool one_pass = rows_of(area_total) <= ROW_CAP && faces_of(area_total) <= LIST_FACES;
+    int c0 = 0;
+    while (c0 < CHUNKS) {
+        // a pass = as many consecutive chunks as fit the row entries and the descriptor list
+        const unsigned long long p0 = sm.part[c0 * 8];
+        int c1 = one_pass ? CHUNKS : c0 + 1;
+        while (c1 < CHUNKS) {
+            const unsigned long long p = sm.part[(c1 + 1) * 8] - p0;  // field-wise: sums only grow
+            if (rows_of(p) > ROW_CAP || faces_of(p) > LIST_FACES) break;
+            ++c1;
+        }
+        const unsigned long long p1 = sm.part[c1 * 8];
+        const uint32_t pass_lo = faces_of(p0), pass_hi = faces_of(p1), rows0 = rows_of(p0);
+        const int nrows = (int)(rows_of(p1) - rows0);
+        // a single chunk can hold up to 24 576 faces: then the list is filled in windows, and the
+        // rows are staged again for each (the staging tiles of the flush overwrite them)
+        const bool windowed = pass_hi - pass_lo > LIST_FACES;
+        for (uint32_t lo = pass_lo; lo < pass_hi; lo += LIST_FACES) {
+            const uint32_t hi = min(pass_hi, lo + LIST_FACES);
+            // ---- A
 #pragma unroll 1
-        for (int c = 0; c < CHUNKS; ++c) {
-            if (sm.warp_total[c][wid] == 0) continue;  // uniform across the warp
-            const unsigned long long warp_off = sm.part[c][wid];
-            const uint32_t wf0 = (uint32_t)warp_off, wnf = sm.warp_total[c][wid] & 0xFFFFu;
-            if (wf0 >= hi || wf0 + wnf <= lo) continue;  // none of the warp's faces in this window
-            const int r = c * 256 + tid;
-            const RowMasks k = row_masks(sm.planes, a, r);
-            const uint32_t v = row_counts(k);
-            const uint32_t ex = warp_inclusive_scan(v, lane) - v;  // rows of this warp before mine
-            const uint32_t nf = v & 0xFFFFu;
-            const uint32_t f0 = wf0 + (ex & 0xFFFFu);  // area-local index of the row's first face
-            if (nf == 0 || f0 >= hi || f0 + nf <= lo) continue;
-            const bool first_window = f0 >= lo;  // the window the row's first face falls in writes its records
-            // the 16 voxel bytes of the row in one load
-            const uint4 rv = reinterpret_cast<const uint4*>(a.vox)[r];
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-            uint32_t rest = k.m[0] | k.m[1] | k.m[2] | k.m[3] | k.m[4] | k.m[5];
-            uint32_t f = f0, q = rec_base + (uint32_t)(warp_off >> 32) + (ex >> 16);
-            const uint32_t z = (uint32_t)r >> 4, y = (uint32_t)r & 15u;
-            while (rest) {
-                const int x = __ffs(rest) - 1;
-                rest &= rest - 1;
-                uint32_t voxel = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if ((x >> 2) == j) voxel = (rw[j] >> (8 * (x & 3))) & 0xFFu;
-                uint32_t m6 = 0;
-#pragma unroll
-                for (int d = 0; d < 6; ++d) m6 |= ((k.m[d] >> x) & 1u) << d;
-                if (first_window)
-                    out.recs[q] = make_uint4(gx0 + x, gy0 + y, z | (voxel << 8) | (m6 << 16) | ((uint32_t)__popc(m6) << 24),
-                                             face_base + f);
-                ++q;
-                int ord = 0;
-                while (m6) {
-                    const int d = __ffs(m6) - 1;
-                    m6 &= m6 - 1;
-                    if (f >= lo && f < hi) sm.list[f - lo] = make_desc(r, x, d, ord, voxel);
-                    ++f;
-                    ++ord;
+            for (int c = c0; c < c1; ++c) {
+                const uint32_t w = sm.tot[c * 8 + wid];
+                if (w == 0) continue;  // uniform across the warp
+                const unsigned long long before = sm.part[c * 8 + wid];
+                const int r = c * 256 + tid;
+                const RowMasks k = row_masks(sm.planes, a, r);
+                const uint32_t v = row_counts(k);
+                const uint32_t ex = warp_inclusive_scan(v, lane) - v;  // rows of this warp before mine
+                const uint32_t with_faces = __ballot_sync(0xFFFFFFFFu, v != 0u);
+                if (v != 0u) {
+                    const uint32_t e = rows_of(before) - rows0 + __popc(with_faces & ((1u << lane) - 1u));
+                    sm.u.rows.vox[e] = reinterpret_cast<const uint4*>(a.vox)[r];
+                    sm.u.rows.masks[e] = make_uint4(k.m[0] | (k.m[1] << 16), k.m[2] | (k.m[3] << 16),
+                                                    k.m[4] | (k.m[5] << 16), (uint32_t)r);
+                    sm.u.rows.first[e] = make_uint2(faces_of(before) + (ex & 0xFFFFu), recs_of(before) + (ex >> 16));
                 }
             }
+            __syncthreads();
+            // ---- B
+#pragma unroll 1
+            for (int e = tid >> 4; e < nrows; e += 16) {
+                const uint4 m = sm.u.rows.masks[e];
+                const uint32_t t0 = (m.x >> x) & 0x10001u, t1 = (m.y >> x) & 0x10001u, t2 = (m.z >> x) & 0x10001u;
+                const uint32_t m6 = (t0 & 1u) | (t0 >> 15) | ((t1 & 1u) << 2) | (t1 >> 13) | ((t2 & 1u) << 4) | (t2 >> 11);
+                if (m6 == 0u) continue;
+                const uint2 fq = sm.u.rows.first[e];
+                const uint32_t vis = (m.x | (m.x >> 16) | m.y | (m.y >> 16) | m.z | (m.z >> 16)) & 0xFFFFu;
+                const uint32_t f = fq.x + __popc(m.x & below2) + __popc(m.y & below2) + __popc(m.z & below2);
+                const uint32_t voxel = reinterpret_cast<const uint8_t*>(&sm.u.rows.vox[e])[x];
+                const uint32_t r = m.w;
+                if (!windowed || (f >= lo && f < hi))  // the window of the voxel's first face writes its record
+                    out.recs[rec_base + fq.y + __popc(vis & below)] =
+                        make_uint4(gx0 + x, gy0 + (r & 15u), (r >> 4) | (voxel << 8) | (m6 << 16) | ((uint32_t)__popc(m6) << 24),
+                                   face_base + f);
+                const uint32_t desc0 = make_desc((int)r, x, 0, 0, voxel);
+                uint32_t g = f - lo;  // list position of the voxel's next face; ordinal in bits 18..20
+                uint32_t ord = 0;
+#pragma unroll
+                for (int d = 0; d < 6; ++d) {
+                    if ((m6 >> d) & 1u) {
+                        if (!windowed || g < hi - lo) sm.list[g] = desc0 | ((uint32_t)d << 15) | (ord << 18);
+                        ++g;  // (g wraps below 0 for faces before the window: the unsigned compare rejects them)
+                        ++ord;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- C
+            flush_faces(sm, hi - lo, face_base + lo, out, gx0, gy0, tid);
+            if (c1 < CHUNKS || hi < pass_hi) __syncthreads();
         }
-        __syncthreads();
-        flush_faces(sm, hi - lo, face_base + lo, out, gx0, gy0, tid);
-        __syncthreads();
+        c0 = c1;
     }
 }
 
 }  // namespace
 
-void launch_mesh_prepare(const uint2* xy, int n, AreaMap map, uint4* jobs, uint32_t* counters,
+void launch_mesh_prepare(const uint2* xy, int n, AreaMap map, uint4* jobs, uint4* nbr, uint32_t* counters,
                          uint2* missing, uint32_t missing_cap, cudaStream_t stream) {
     if (n <= 0) return;
-    mesh_prepare_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xy, n, map, jobs, counters, missing, missing_cap);
+    mesh_prepare_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xy, n, map, jobs, nbr, counters, missing, missing_cap);
 }
 
-void launch_mesh_count(const uint4* jobs, int n, const uint8_t* pool_voxels,
-                       const uint16_t* pool_planes, AreaMap map, uint32_t* rec_count,
+void launch_mesh_count(const uint4* jobs, const uint4* nbr, int n, const uint8_t* pool_voxels,
+                       const uint16_t* pool_planes, uint32_t* rec_count,
                        uint32_t* face_count, uint32_t* warp_totals, cudaStream_t stream) {
     if (n <= 0) return;
-    mesh_count_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_planes, map, rec_count,
+    mesh_count_kernel<<<n, 256, 0, stream>>>(jobs, nbr, pool_voxels, pool_planes, rec_count,
                                              face_count, warp_totals);
 }
 
@@ -552,11 +628,11 @@ void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, 
     mesh_offsets_kernel<<<1, 1024, 0, stream>>>(rec_count, face_count, n, rec_first, face_first);
 }
 
-void launch_mesh_emit(const uint4* jobs, int n, const uint8_t* pool_voxels,
-                      const uint16_t* pool_planes, AreaMap map, const uint32_t* warp_totals, MeshOut out,
+void launch_mesh_emit(const uint4* jobs, const uint4* nbr, int n, const uint8_t* pool_voxels,
+                      const uint16_t* pool_planes, const uint32_t* warp_totals, MeshOut out,
                       uint32_t cap_faces, uint32_t cap_recs, cudaStream_t stream) {
     if (n <= 0) return;
-    mesh_emit_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_planes, map, warp_totals, out, n, cap_faces,
+    mesh_emit_kernel<<<n, 256, 0, stream>>>(jobs, nbr, pool_voxels, pool_planes, warp_totals, out, n, cap_faces,
                                             cap_recs);
 }
 
