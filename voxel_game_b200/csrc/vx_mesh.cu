@@ -85,6 +85,8 @@ struct PlaneTile {
     uint16_t T[ROWS];
     uint8_t hx[ROWS];              // bit0: T(+x neighbour, x = 0), bit1: T(-x neighbour, x = 15)
     uint16_t ty[2][AREA_HEIGHT];   // [0]: +y neighbour row y = 0, [1]: -y neighbour row y = 15
+    uint8_t slab[AREA_HEIGHT];     // per z: bit0 = some voxel != None, bit1 = some transparent voxel
+                                   // in the slab or in its one-voxel halo
 };
 
 __device__ __forceinline__ void load_plane_tile(PlaneTile& p, const AreaView& a, int tid) {
@@ -95,10 +97,22 @@ __device__ __forceinline__ void load_plane_tile(PlaneTile& p, const AreaView& a,
     const uint4* xp4 = reinterpret_cast<const uint4*>(a.T_n[0]);
     const uint4* xm4 = reinterpret_cast<const uint4*>(a.T_n[1]);
     uint2* dh = reinterpret_cast<uint2*>(p.hx);
-    for (int i = tid; i < ROWS / 8; i += 256) {  // 8 rows (16 bytes of u16) per iteration
-        ds[i] = s4[i];
-        dt[i] = t4[i];
+    static_assert(ROWS / 8 == 256, "one iteration per thread: thread i owns rows 8i .. 8i+7, half of slab i / 2");
+    {
+        const int i = tid;
+        const uint4 sv = s4[i], tv = t4[i];
         const uint4 xp = xp4[i], xm = xm4[i];
+        const int z = i >> 1;
+        uint32_t ty_or = 0;
+        if (!(i & 1)) {
+            const uint32_t t0 = a.T_n[2][16 * z];       // row (y = 0, z) of the +y neighbour
+            const uint32_t t1 = a.T_n[3][16 * z + 15];  // row (y = 15, z) of the -y neighbour
+            p.ty[0][z] = (uint16_t)t0;
+            p.ty[1][z] = (uint16_t)t1;
+            ty_or = t0 | t1;
+        }
+        ds[i] = sv;
+        dt[i] = tv;
         const uint32_t wp[4] = {xp.x, xp.y, xp.z, xp.w}, wm[4] = {xm.x, xm.y, xm.z, xm.w};
         uint32_t h[2] = {0, 0};
 #pragma unroll
@@ -108,11 +122,23 @@ __device__ __forceinline__ void load_plane_tile(PlaneTile& p, const AreaView& a,
             h[k >> 2] |= ((vp & 1u) | ((vm >> 15) << 1)) << (8 * (k & 3));
         }
         dh[i] = make_uint2(h[0], h[1]);
+        uint32_t any_s = sv.x | sv.y | sv.z | sv.w;
+        uint32_t any_t = tv.x | tv.y | tv.z | tv.w | h[0] | h[1] | ty_or;
+        any_s |= __shfl_xor_sync(0xFFFFFFFFu, any_s, 1);
+        any_t |= __shfl_xor_sync(0xFFFFFFFFu, any_t, 1);
+        if (!(i & 1)) p.slab[z] = (uint8_t)((any_s != 0u) | ((any_t != 0u) << 1));
     }
-    if (tid < AREA_HEIGHT) {
-        p.ty[0][tid] = a.T_n[2][16 * tid];       // row (y = 0, z = tid) of the +y neighbour
-        p.ty[1][tid] = a.T_n[3][16 * tid + 15];  // row (y = 15, z = tid) of the -y neighbour
-    }
+}
+
+// No voxel of slabs z0, z0 + 1 can have a face: they are all None, or nothing transparent (None
+// included) touches them -- every face mask is "S & some T row of slab z - 1, z or z + 1 or of the
+// halo".  Holds for most of an area: the air above the surface and the rock below it.
+__device__ __forceinline__ bool slab_pair_empty(const PlaneTile& p, int z0) {
+    const uint32_t f0 = p.slab[z0], f1 = p.slab[z0 + 1];
+    const uint32_t below = z0 > 0 ? p.slab[z0 - 1] : 0u, above = z0 + 2 < AREA_HEIGHT ? p.slab[z0 + 2] : 0u;
+    const bool faces0 = (f0 & 1u) && (((below | f0 | f1) & 2u) != 0u);
+    const bool faces1 = (f1 & 1u) && (((f0 | f1 | above) & 2u) != 0u);
+    return !(faces0 || faces1);
 }
 
 __device__ __forceinline__ bool partial_height(uint32_t v) { return v >= V_WATER1 && v <= V_WATER4; }
@@ -246,6 +272,10 @@ __global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict
     uint32_t* wt = warp_totals + (size_t)blockIdx.x * 64;
 #pragma unroll 1
     for (int c = 0; c < ROWS / 256; ++c) {
+        if (slab_pair_empty(tile, 16 * c + 2 * wid)) {  // uniform across the warp (rows of 2 slabs)
+            if (lane == 0) wt[c * 8 + wid] = 0u;
+            continue;
+        }
         const uint32_t v = row_counts(row_masks(tile, a, c * 256 + tid));
         const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, v);  // <= 32 * 96 faces, 32 * 16 voxels
         const uint32_t rows = __popc(__ballot_sync(0xFFFFFFFFu, v != 0u));
@@ -270,7 +300,8 @@ __global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict
 }
 
 // ------------------------------------------------------------------------------------- offsets
-// single-CTA exclusive scan over the per-area counts (n <= a few 100k: microseconds)
+// single-CTA exclusive scan over the per-area counts (n <= a few 100k: microseconds); four areas
+// per thread and round, so 16 384 areas take four rounds
 __global__ void __launch_bounds__(1024) mesh_offsets_kernel(const uint32_t* __restrict__ rec_count,
                                                             const uint32_t* __restrict__ face_count,
                                                             int n, uint32_t* __restrict__ rec_first,
@@ -280,32 +311,48 @@ __global__ void __launch_bounds__(1024) mesh_offsets_kernel(const uint32_t* __re
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) carry_r = carry_f = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + tid;
-        const uint32_t r = i < n ? rec_count[i] : 0u, f = i < n ? face_count[i] : 0u;
-        uint32_t ir = warp_inclusive_scan(r, lane), jf = warp_inclusive_scan(f, lane);
+    for (int base = 0; base < n; base += 4096) {
+        const int i = base + 4 * tid;
+        uint32_t r[4], f[4];
+        if (i + 3 < n) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(rec_count + i);
+            const uint4 fv = *reinterpret_cast<const uint4*>(face_count + i);
+            r[0] = rv.x; r[1] = rv.y; r[2] = rv.z; r[3] = rv.w;
+            f[0] = fv.x; f[1] = fv.y; f[2] = fv.z; f[3] = fv.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                r[k] = i + k < n ? rec_count[i + k] : 0u;
+                f[k] = i + k < n ? face_count[i + k] : 0u;
+            }
+        }
+        const uint32_t sr = r[0] + r[1] + r[2] + r[3], sf = f[0] + f[1] + f[2] + f[3];
+        const uint32_t ir = warp_inclusive_scan(sr, lane), jf = warp_inclusive_scan(sf, lane);
         if (lane == 31) {
             s_r[wid] = ir;
             s_f[wid] = jf;
         }
         __syncthreads();
         if (wid == 0) {
-            uint32_t wr = s_r[lane], wf = s_f[lane];
-            wr = warp_inclusive_scan(wr, lane);
-            wf = warp_inclusive_scan(wf, lane);
+            const uint32_t wr = warp_inclusive_scan(s_r[lane], lane), wf = warp_inclusive_scan(s_f[lane], lane);
             s_r[lane] = wr;
             s_f[lane] = wf;
         }
         __syncthreads();
-        const uint32_t pr = carry_r + (wid ? s_r[wid - 1] : 0u), pf = carry_f + (wid ? s_f[wid - 1] : 0u);
-        if (i < n) {
-            rec_first[i] = pr + ir - r;
-            face_first[i] = pf + jf - f;
+        uint32_t pr = carry_r + (wid ? s_r[wid - 1] : 0u) + ir - sr, pf = carry_f + (wid ? s_f[wid - 1] : 0u) + jf - sf;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < n) {
+                rec_first[i + k] = pr;
+                face_first[i + k] = pf;
+            }
+            pr += r[k];
+            pf += f[k];
         }
         __syncthreads();
         if (tid == 1023) {
-            carry_r = pr + ir;
-            carry_f = pf + jf;
+            carry_r = pr;
+            carry_f = pf;
         }
         __syncthreads();
     }
