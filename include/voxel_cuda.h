@@ -82,7 +82,7 @@ typedef struct {
     uint64_t vertex_bytes, index_bytes, rec_bytes;
 } vx_mesh_info;
 
-/* Device time of the kernels of the most recent vx_generate / vx_mesh / vx_apply_edits call,
+/* Device time of the kernels of the most recent vx_generate / vx_mesh / vx_apply_edits / ... call,
  * CUDA events on the context's stream.  Only filled while vx_set_timing(ctx, 1). */
 typedef struct {
     float gen_columns_ms;  /* K1 */
@@ -93,8 +93,10 @@ typedef struct {
     float edit_ms;         /* K5 */
     float heightmap_ms;    /* K6 */
     float light_ms;        /* L-ext */
+    float visible_ms;      /* K7 (vx_visible) */
     uint32_t gen_launches, mesh_launches, other_launches; /* kernels launched by the last call */
     uint32_t cave_columns;                                /* K1b work items of the last generate */
+    uint32_t reserved;
     /* work accounting of the last vx_generate (roofline numerators): octave-level simplex
      * evaluations executed and voxels that ran the cave noise */
     uint64_t simplex2_evals, simplex3_evals, cave_voxels;
@@ -183,6 +185,37 @@ int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_are
  * areas of the list that are not resident read as an empty area (height 127, world.rs:64-69). */
 int vx_heightmap(vx_ctx* ctx, const uint32_t* area_xy, int n, uint32_t cam_area_x,
                  uint32_t cam_area_y, uint8_t* rgba);
+
+/* ---- per-frame visibility: replaces, for the mesh of the last vx_mesh call, the work
+ * Renderer::set_voxel_shader_and_find_visible_areas and render_voxels do every frame before the
+ * draw calls (renderer.rs:365-462): prepare_visible_areas / is_area_visible (:324-346,507-519),
+ * filter_visible_voxels / is_voxel_visible -- the per-frame loop over every meshed voxel
+ * (:521-547,560-586), optimise_render_order (:349-361) and prepare_lights (:496-501). */
+#define VX_VOXEL_VARIANTS 27
+#define VX_MAX_LIGHTS 64 /* voxel_shader.rs:21 */
+typedef struct vx_view {
+    float cam_pos[3];       /* Camera3D.position */
+    float cam_target_z;     /* Camera3D.target.z */
+    float look[3];          /* (target - position).normalize_or_zero(), as render_voxels computes it */
+    uint32_t render_size;   /* UserSettings::get_render_distance(), in areas */
+    uint32_t head_in_water; /* PlayerInfo::is_head_in_water: water voxels are not drawn */
+    uint32_t show_map;      /* RendererParams::should_show_map: every meshed voxel is drawn */
+} vx_view;
+typedef struct vx_visible_info {
+    uint64_t n_visible; /* voxel meshes to draw (records of the last vx_mesh) */
+    uint64_t n_faces;   /* their faces: render_voxels' second return value */
+    uint32_t n_areas;   /* visible areas: its first return value */
+    uint32_t n_lamps;   /* Lamp records in the visible areas (RenderArea.lights) */
+    uint32_t type_first[VX_VOXEL_VARIANTS + 1]; /* group of voxel type t = [type_first[t], type_first[t+1]) */
+    uint32_t lamps[VX_MAX_LIGHTS];              /* record indices of the first min(64, n_lamps) lamps */
+} vx_visible_info;
+/* Runs the pass on the device; the index list stays there until vx_visible_read. */
+int vx_visible(vx_ctx* ctx, const vx_view* view, vx_visible_info* info);
+/* rec_index: n_visible indices into the records of vx_mesh_read, grouped by voxel type in the
+ * order draw_mesh is called (optimise_render_order); inside a group in area-then-record order (the
+ * reference's order inside a group is HashMap iteration order).  area_visible: one byte per area of
+ * the vx_mesh list.  Either pointer may be NULL. */
+int vx_visible_read(vx_ctx* ctx, uint32_t* rec_index, uint8_t* area_visible);
 
 /* ---- L-ext (north star only; the reference has no voxel light): light levels
  * 0..15 per voxel over the resident areas listed, see DESIGN.md "L-ext". light_out n*32768. */

@@ -68,6 +68,14 @@ class _World(C.Structure):
     ]
 
 
+class View(C.Structure):
+    """vgo_view: the camera state the per-frame visibility pass depends on."""
+    _fields_ = [
+        ("cam_pos", C.c_float * 3), ("cam_target_z", C.c_float), ("look", C.c_float * 3),
+        ("render_size", C.c_uint32), ("head_in_water", C.c_uint32), ("show_map", C.c_uint32),
+    ]
+
+
 _lib = None
 
 
@@ -130,6 +138,16 @@ def lib():
         L.vgo_apply_edit.restype = C.c_int
         L.vgo_apply_edit.argtypes = [C.POINTER(_World), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8]
         L.vgo_light_flood_world.argtypes = [C.POINTER(_World), u8p]
+        L.vgo_area_render_distance.restype = C.c_float
+        L.vgo_area_render_distance.argtypes = [C.POINTER(C.c_float), C.c_uint32]
+        L.vgo_is_area_visible.restype = C.c_int
+        L.vgo_is_area_visible.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(View), C.c_float]
+        L.vgo_is_voxel_visible.restype = C.c_int
+        L.vgo_is_voxel_visible.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float),
+                                           C.POINTER(C.c_float), C.c_float]
+        L.vgo_filter_visible.restype = C.c_long
+        L.vgo_filter_visible.argtypes = [C.c_void_p, u32p, u32p, C.c_int, C.POINTER(View), u8p, u32p, u32p,
+                                         C.POINTER(C.c_long), u32p, C.POINTER(C.c_long)]
         L.vgo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -373,3 +391,56 @@ def should_generate_face(cur, nbr) -> bool:
 
 def should_generate_top_face(cur, nbr) -> bool:
     return bool(lib().vgo_should_generate_top_face(cur, nbr))
+
+
+# ------------------------------------------------------------------------------ per-frame visibility
+def make_view(cam_pos, cam_target, render_size=8, head_in_water=False, show_map=False) -> View:
+    """Camera3D position / target -> View, with look = (target - position).normalize_or_zero()
+    in f32 like glam (renderer.rs:381)."""
+    p = np.asarray(cam_pos, np.float32)
+    t = np.asarray(cam_target, np.float32)
+    d = (t - p).astype(np.float32)
+    length = np.sqrt(np.float32(np.float32(d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]), dtype=np.float32)
+    with np.errstate(divide="ignore"):
+        rcp = np.float32(1.0) / length
+    look = (d * rcp).astype(np.float32) if np.isfinite(rcp) and rcp > 0 else np.zeros(3, np.float32)
+    v = View()
+    v.cam_pos[:] = [float(x) for x in p]
+    v.cam_target_z = float(t[2])
+    v.look[:] = [float(x) for x in look]
+    v.render_size, v.head_in_water, v.show_map = int(render_size), int(bool(head_in_water)), int(bool(show_map))
+    return v
+
+
+def area_render_distance(look, render_size) -> float:
+    a = (C.c_float * 3)(*[float(x) for x in look])
+    return float(lib().vgo_area_render_distance(a, int(render_size)))
+
+
+def is_area_visible(ax, ay, view: View, render_distance) -> bool:
+    return bool(lib().vgo_is_area_visible(int(ax), int(ay), C.byref(view), float(render_distance)))
+
+
+def is_voxel_visible(gx, gy, gz, look, cam_pos, max_distance) -> bool:
+    lk = (C.c_float * 3)(*[float(x) for x in look])
+    cp = (C.c_float * 3)(*[float(x) for x in cam_pos])
+    return bool(lib().vgo_is_voxel_visible(int(gx), int(gy), int(gz), lk, cp, float(max_distance)))
+
+
+def filter_visible(recs, rec_first, area_xy, view: View):
+    """-> dict(area_visible u8[n], visible u32[], type_first u32[28], n_faces, lamps u32[])."""
+    recs = np.ascontiguousarray(recs, dtype=REC_DTYPE)
+    rec_first = np.ascontiguousarray(rec_first, dtype=np.uint32)
+    area_xy = np.ascontiguousarray(area_xy, dtype=np.uint32).reshape(-1, 2)
+    n = len(area_xy)
+    area_visible = np.zeros(n, np.uint8)
+    visible = np.zeros(max(len(recs), 1), np.uint32)
+    lamps = np.zeros(max(len(recs), 1), np.uint32)
+    type_first = np.zeros(28, np.uint32)
+    n_faces, n_lamps = C.c_long(0), C.c_long(0)
+    nv = lib().vgo_filter_visible(recs.ctypes.data_as(C.c_void_p), _p(rec_first, C.c_uint32), _p(area_xy, C.c_uint32),
+                                  n, C.byref(view), _p(area_visible), _p(visible, C.c_uint32),
+                                  _p(type_first, C.c_uint32), C.byref(n_faces), _p(lamps, C.c_uint32),
+                                  C.byref(n_lamps))
+    return dict(area_visible=area_visible, visible=visible[:nv].copy(), type_first=type_first,
+                n_faces=int(n_faces.value), lamps=lamps[:n_lamps.value].copy())

@@ -184,6 +184,41 @@ int vgo_apply_edit(vgo_world* w, uint32_t gx, uint32_t gy, uint32_t gz, uint8_t 
  * Sequential BFS flood fill; light = nx*ny*32768 bytes, same layout as voxels. */
 void vgo_light_flood_world(const vgo_world* w, uint8_t* light);
 
+/* ---------------------------------------------------------------- per-frame visibility
+ * Renderer::set_voxel_shader_and_find_visible_areas + render_voxels (renderer.rs:365-462).
+ * The f32 vector arithmetic lives in glam 0.27.0 (macroquad's Vec3; crate not under
+ * /root/reference, no reference test pins a value: PARITY UNPINNED at that boundary); frame.c
+ * restates it: dot = (x*x + y*y) + z*z, length = sqrt(dot), normalize_or_zero = v * (1 / length)
+ * if that reciprocal is finite and > 0, else zero. */
+typedef struct {
+    float cam_pos[3];       /* Camera3D.position */
+    float cam_target_z;     /* Camera3D.target.z */
+    float look[3];          /* (target - position).normalize_or_zero() */
+    uint32_t render_size;   /* UserSettings::get_render_distance(), in areas */
+    uint32_t head_in_water; /* PlayerInfo::is_head_in_water */
+    uint32_t show_map;      /* RendererParams::should_show_map */
+} vgo_view;
+
+/* calculate_area_render_distance (renderer.rs:549-558) */
+float vgo_area_render_distance(const float look[3], uint32_t render_size);
+/* is_area_visible (renderer.rs:324-346) */
+int vgo_is_area_visible(uint32_t ax, uint32_t ay, const vgo_view* v, float render_distance);
+/* is_voxel_visible (renderer.rs:560-586) */
+int vgo_is_voxel_visible(uint32_t gx, uint32_t gy, uint32_t gz, const float look[3],
+                         const float cam_pos[3], float max_distance);
+/* prepare_visible_areas + filter_visible_voxels + optimise_render_order + prepare_lights over the
+ * meshed areas i = 0..n-1 (records recs[rec_first[i] .. rec_first[i+1])).
+ *   area_visible[n]        1 = the area is in visible_areas
+ *   visible[]              indices of the drawn records, grouped by voxel type (optimise_render_order);
+ *                          inside a group in record order (the reference's order inside a group is
+ *                          HashMap iteration order, i.e. unspecified)
+ *   type_first[28]         group boundaries in visible[]
+ *   lamps[]                indices of the Lamp records of visible areas (prepare_lights), record order
+ * Returns the number of visible records; *n_faces gets their face count, *n_lamps the lamp count. */
+long vgo_filter_visible(const vgo_voxel_rec* recs, const uint32_t* rec_first, const uint32_t* area_xy,
+                        int n, const vgo_view* v, uint8_t* area_visible, uint32_t* visible,
+                        uint32_t* type_first, long* n_faces, uint32_t* lamps, long* n_lamps);
+
 int vgo_max_threads(void);
 
 #ifdef __cplusplus

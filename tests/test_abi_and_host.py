@@ -52,7 +52,10 @@ def test_struct_layouts_match_header():
     from voxel_game_b200.binding import MeshInfo, Timings
 
     assert C.sizeof(MeshInfo) == 40
-    assert C.sizeof(Timings) == 8 * 4 + 4 * 4 + 4 * 8
+    assert C.sizeof(Timings) == 9 * 4 + 5 * 4 + 4 * 8
+    from voxel_game_b200.binding import View, VisibleInfo
+
+    assert C.sizeof(View) == 40 and C.sizeof(VisibleInfo) == 24 + 28 * 4 + 64 * 4
 
 
 def test_no_gpu_means_loud_failure_not_cpu_fallback():

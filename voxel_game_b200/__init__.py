@@ -5,11 +5,11 @@ The product is libvoxel_cuda.so (hand-written CUDA behind the C ABI of include/v
 this package is the thin Python plumbing used by tests and bench.py.  No CPU fallback.
 """
 from .binding import (  # noqa: F401
-    ABI_SYMBOLS, EDIT_DTYPE, LIB_PATH, REC_DTYPE, VERTEX_DTYPE, Context, PinnedArray, VxError,
-    build, hash_world_name, load,
+    ABI_SYMBOLS, EDIT_DTYPE, LIB_PATH, REC_DTYPE, VERTEX_DTYPE, Context, PinnedArray, View, VxError,
+    build, hash_world_name, load, make_view,
 )
 from .world import region_xy, shard_rows, spawn_region  # noqa: F401
 
 __all__ = ["Context", "PinnedArray", "VxError", "build", "load", "hash_world_name", "region_xy",
            "shard_rows", "spawn_region", "ABI_SYMBOLS", "REC_DTYPE", "VERTEX_DTYPE", "EDIT_DTYPE",
-           "LIB_PATH"]
+           "LIB_PATH", "View", "make_view"]

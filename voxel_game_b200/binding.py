@@ -40,7 +40,7 @@ ABI_SYMBOLS = [
     "vx_sync", "vx_set_timing", "vx_get_timings", "vx_host_alloc", "vx_host_free", "vx_set_seed",
     "vx_hash_world_name", "vx_generate", "vx_upload", "vx_read_areas", "vx_unload",
     "vx_resident_count", "vx_column_heights", "vx_mesh", "vx_mesh_read", "vx_apply_edits",
-    "vx_heightmap", "vx_light", "vx_diag_fp64_rate",
+    "vx_heightmap", "vx_visible", "vx_visible_read", "vx_light", "vx_diag_fp64_rate",
 ]
 
 
@@ -59,13 +59,42 @@ class Timings(C.Structure):
     _fields_ = [("gen_columns_ms", C.c_float), ("gen_caves_ms", C.c_float),
                 ("gen_finish_ms", C.c_float), ("mesh_count_ms", C.c_float),
                 ("mesh_emit_ms", C.c_float), ("edit_ms", C.c_float), ("heightmap_ms", C.c_float),
-                ("light_ms", C.c_float), ("gen_launches", C.c_uint32),
+                ("light_ms", C.c_float), ("visible_ms", C.c_float), ("gen_launches", C.c_uint32),
                 ("mesh_launches", C.c_uint32), ("other_launches", C.c_uint32),
-                ("cave_columns", C.c_uint32), ("simplex2_evals", C.c_uint64),
+                ("cave_columns", C.c_uint32), ("reserved", C.c_uint32), ("simplex2_evals", C.c_uint64),
                 ("simplex3_evals", C.c_uint64), ("cave_voxels", C.c_uint64), ("cave_evals", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class View(C.Structure):
+    """vx_view: camera state of one frame (renderer.rs:365-462)."""
+    _fields_ = [("cam_pos", C.c_float * 3), ("cam_target_z", C.c_float), ("look", C.c_float * 3),
+                ("render_size", C.c_uint32), ("head_in_water", C.c_uint32), ("show_map", C.c_uint32)]
+
+
+class VisibleInfo(C.Structure):
+    _fields_ = [("n_visible", C.c_uint64), ("n_faces", C.c_uint64), ("n_areas", C.c_uint32),
+                ("n_lamps", C.c_uint32), ("type_first", C.c_uint32 * 28), ("lamps", C.c_uint32 * 64)]
+
+
+def make_view(cam_pos, cam_target, render_size=8, head_in_water=False, show_map=False) -> View:
+    """Camera3D position / target -> vx_view; look = (target - position).normalize_or_zero() in
+    f32, as render_voxels computes it (renderer.rs:425)."""
+    p = np.asarray(cam_pos, np.float32)
+    t = np.asarray(cam_target, np.float32)
+    d = (t - p).astype(np.float32)
+    length = np.sqrt(np.float32(np.float32(d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]), dtype=np.float32)
+    with np.errstate(divide="ignore"):
+        rcp = np.float32(1.0) / length
+    look = (d * rcp).astype(np.float32) if np.isfinite(rcp) and rcp > 0 else np.zeros(3, np.float32)
+    v = View()
+    v.cam_pos[:] = [float(x) for x in p]
+    v.cam_target_z = float(t[2])
+    v.look[:] = [float(x) for x in look]
+    v.render_size, v.head_in_water, v.show_map = int(render_size), int(bool(head_in_water)), int(bool(show_map))
+    return v
 
 
 def build(verbose: bool = False) -> str:
@@ -123,6 +152,8 @@ def load():
     L.vx_mesh_read.argtypes = [vp, vp, vp, vp, vp, vp]
     L.vx_apply_edits.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int)]
     L.vx_heightmap.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_uint32, vp]
+    L.vx_visible.argtypes = [vp, C.POINTER(View), C.POINTER(VisibleInfo)]
+    L.vx_visible_read.argtypes = [vp, vp, vp]
     L.vx_light.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int)]
     L.vx_diag_fp64_rate.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     for name in ABI_SYMBOLS:
@@ -310,6 +341,23 @@ class Context:
             rgba = np.empty((512, 512, 4), np.uint8)
         self._check(self._lib.vx_heightmap(self._h, xy.ctypes.data, xy.shape[0], cam_ax, cam_ay, rgba.ctypes.data))
         return rgba
+
+    def visible(self, view: View, read: bool = True):
+        """Per-frame visibility over the mesh of the last mesh() call.
+        -> dict(n_visible, n_faces, n_areas, n_lamps, type_first[28], lamps[<=64]) and, if read,
+        (rec_index u32[n_visible], area_visible u8[n areas])."""
+        info = VisibleInfo()
+        self._check(self._lib.vx_visible(self._h, C.byref(view), C.byref(info)))
+        out = dict(n_visible=int(info.n_visible), n_faces=int(info.n_faces), n_areas=int(info.n_areas),
+                   n_lamps=int(info.n_lamps), type_first=np.array(info.type_first[:], np.uint32),
+                   lamps=np.array(info.lamps[: min(64, int(info.n_lamps))], np.uint32))
+        if not read:
+            return out
+        idx = np.empty(out["n_visible"], np.uint32)
+        flags = np.empty(self._mesh_n, np.uint8)
+        self._check(self._lib.vx_visible_read(self._h, idx.ctypes.data if idx.size else None,
+                                              flags.ctypes.data if flags.size else None))
+        return out, idx, flags
 
     def light(self, area_xy):
         xy = _xy(area_xy)

@@ -121,7 +121,7 @@ struct HostAreaMap {
 };
 
 enum TimerId { TM_GEN_COLUMNS, TM_GEN_CAVES, TM_GEN_FINISH, TM_MESH_COUNT, TM_MESH_EMIT, TM_EDIT,
-               TM_HEIGHTMAP, TM_LIGHT, TM_COUNT };
+               TM_HEIGHTMAP, TM_LIGHT, TM_VISIBLE, TM_COUNT };
 
 }  // namespace
 
@@ -163,6 +163,9 @@ struct vx_ctx {
     DevBuf d_jobs, d_gen_jobs, d_list, d_missing, d_cave_items, d_counters, d_rec_count, d_face_count;
     DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
     DevBuf d_heightmap, d_light, d_slot_to_job, d_finished, d_warp_totals, d_mesh_nbr;
+    DevBuf d_mesh_xy, d_frame_flags, d_frame_counts, d_frame_small, d_frame_visible;  // per-frame visibility (K7)
+    bool frame_ready = false;      // d_frame_visible / d_frame_flags hold the result of vx_visible for this mesh
+    uint64_t frame_n_visible = 0;
     bool heightmap_init = false;
 
     // last mesh
@@ -222,7 +225,8 @@ void collect_timers(vx_ctx* c) {
     float* dst[TM_COUNT] = {&c->timings.gen_columns_ms, &c->timings.gen_caves_ms,
                             &c->timings.gen_finish_ms,  &c->timings.mesh_count_ms,
                             &c->timings.mesh_emit_ms,   &c->timings.edit_ms,
-                            &c->timings.heightmap_ms,   &c->timings.light_ms};
+                            &c->timings.heightmap_ms,   &c->timings.light_ms,
+                            &c->timings.visible_ms};
     for (int i = 0; i < TM_COUNT; ++i)
         if (c->ev_used[i]) {
             float ms = 0.f;
@@ -465,7 +469,8 @@ void vx_destroy(vx_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_gen_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters,
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
-                      &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_warp_totals, &ctx->d_mesh_nbr, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
+                      &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_warp_totals, &ctx->d_mesh_nbr, &ctx->d_mesh_xy, &ctx->d_frame_flags,
+                      &ctx->d_frame_counts, &ctx->d_frame_small, &ctx->d_frame_visible, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
                       &ctx->d_vertices, &ctx->d_indices};
     for (DevBuf* b : bufs) b->release();
     ctx->h_stage.release();
@@ -668,6 +673,7 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
     VX_CUDA(cudaSetDevice(ctx->device));
     reset_timers(ctx);
     ctx->mesh_n = -1;
+    ctx->frame_ready = false;
     ctx->mesh_info = vx_mesh_info{};
     int st;
     if (n > 0) {
@@ -694,6 +700,8 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
         if (!jobs_ready) {
             std::memcpy(ctx->h_stage.p, area_xy, xy_bytes);
             VX_CUDA(cudaMemcpyAsync(ctx->d_list.p, ctx->h_stage.p, xy_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            VX_CUDA(ctx->d_mesh_xy.ensure(xy_bytes));  // the list of this mesh, kept for vx_visible
+            VX_CUDA(cudaMemcpyAsync(ctx->d_mesh_xy.p, ctx->d_list.p, xy_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
             ctx->last_mesh_xy.assign(area_xy, area_xy + 2 * (size_t)n);
             ctx->last_mesh_version = ~0ull;
         }
@@ -816,6 +824,78 @@ int vx_mesh_read(vx_ctx* ctx, uint32_t* rec_first, uint32_t* face_first, vx_voxe
     if (recs && mi.rec_bytes) VX_CUDA(cudaMemcpyAsync(recs, ctx->d_recs.p, mi.rec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (vertices && mi.vertex_bytes) VX_CUDA(cudaMemcpyAsync(vertices, ctx->d_vertices.p, mi.vertex_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (indices && mi.index_bytes) VX_CUDA(cudaMemcpyAsync(indices, ctx->d_indices.p, mi.index_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_visible(vx_ctx* ctx, const vx_view* view, vx_visible_info* info) {
+    if (!ctx || !view || !info) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (ctx->mesh_n < 0) return fail(ctx, VX_ERR_NO_MESH, "vx_visible without vx_mesh");
+    VX_CUDA(cudaSetDevice(ctx->device));
+    reset_timers(ctx);
+    *info = vx_visible_info{};
+    ctx->frame_ready = false;
+    ctx->frame_n_visible = 0;
+    const int n = ctx->mesh_n;
+    if (n == 0) {
+        ctx->frame_ready = true;
+        return VX_OK;
+    }
+    const uint64_t n_recs = ctx->mesh_info.n_recs;
+    VX_CUDA(ctx->d_frame_flags.ensure((size_t)n));
+    VX_CUDA(ctx->d_frame_counts.ensure((size_t)28 * n * 4));
+    VX_CUDA(ctx->d_frame_visible.ensure(std::max<size_t>(16, n_recs * 4)));
+    const bool fresh = ctx->d_frame_small.p == nullptr;
+    VX_CUDA(ctx->d_frame_small.ensure(sizeof(FrameTotals) + 32 * 4));
+    VX_CUDA(ctx->h_small.ensure(sizeof(FrameTotals)));
+    FrameTotals* totals = ctx->d_frame_small.as<FrameTotals>();
+    uint32_t* row_total = reinterpret_cast<uint32_t*>(totals + 1);
+    uint32_t* done = row_total + 28;
+    if (fresh) VX_CUDA(cudaMemsetAsync(ctx->d_frame_small.p, 0, sizeof(FrameTotals) + 32 * 4, ctx->stream));
+    VX_CUDA(cudaMemsetAsync(totals, 0, 16, ctx->stream));  // n_faces, n_areas, n_lamps
+    FrameView fv;
+    fv.cx = view->cam_pos[0]; fv.cy = view->cam_pos[1]; fv.cz = view->cam_pos[2];
+    fv.target_z = view->cam_target_z;
+    fv.lx = view->look[0]; fv.ly = view->look[1]; fv.lz = view->look[2];
+    fv.render_size = view->render_size;
+    fv.head_in_water = view->head_in_water;
+    fv.show_map = view->show_map;
+    {
+        ScopedTimer t(ctx, TM_VISIBLE);
+        launch_frame_visible(ctx->d_recs.as<uint4>(), ctx->d_rec_first.as<uint32_t>(), ctx->d_mesh_xy.as<uint2>(), n, fv,
+                             ctx->d_frame_flags.as<uint8_t>(), ctx->d_frame_counts.as<uint32_t>(), row_total, done,
+                             totals, ctx->d_frame_visible.as<uint32_t>(), ctx->stream);
+        ctx->timings.other_launches += 4;
+    }
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaMemcpyAsync(ctx->h_small.p, totals, sizeof(FrameTotals), cudaMemcpyDeviceToHost, ctx->stream));
+    int st;
+    if ((st = sync_stream(ctx)) != VX_OK) return st;
+    collect_timers(ctx);
+    const FrameTotals* h = ctx->h_small.as<FrameTotals>();
+    info->n_visible = h->type_first[27];
+    info->n_faces = h->n_faces;
+    info->n_areas = h->n_areas;
+    info->n_lamps = h->n_lamps;
+    std::memcpy(info->type_first, h->type_first, sizeof info->type_first);
+    const uint32_t nl = std::min<uint32_t>(h->n_lamps, VX_MAX_LIGHTS);
+    std::memcpy(info->lamps, h->lamps, nl * sizeof(uint32_t));
+    ctx->frame_n_visible = info->n_visible;
+    ctx->frame_ready = true;
+    return VX_OK;
+}
+
+int vx_visible_read(vx_ctx* ctx, uint32_t* rec_index, uint8_t* area_visible) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (ctx->mesh_n < 0 || !ctx->frame_ready) return fail(ctx, VX_ERR_NO_MESH, "vx_visible_read without vx_visible");
+    VX_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->mesh_n == 0) return VX_OK;
+    if (rec_index && ctx->frame_n_visible)
+        VX_CUDA(cudaMemcpyAsync(rec_index, ctx->d_frame_visible.p, ctx->frame_n_visible * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (area_visible)
+        VX_CUDA(cudaMemcpyAsync(area_visible, ctx->d_frame_flags.p, (size_t)ctx->mesh_n, cudaMemcpyDeviceToHost, ctx->stream));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }

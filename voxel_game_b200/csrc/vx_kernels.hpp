@@ -52,6 +52,24 @@ void launch_mesh_emit(const uint4* jobs, const uint4* nbr, int n, const uint8_t*
                       uint32_t cap_faces, uint32_t cap_recs /* arena capacity; no-op if exceeded */,
                       cudaStream_t stream);
 
+// ---- per-frame visibility (K7), vx_frame.cu
+constexpr int FRAME_MAX_LAMPS = 64;
+struct FrameView {
+    float cx, cy, cz, target_z;  // camera position, camera target z
+    float lx, ly, lz;            // look direction
+    uint32_t render_size, head_in_water, show_map;
+};
+struct FrameTotals {  // zero n_faces / n_areas before the launch
+    unsigned long long n_faces;
+    uint32_t n_areas, n_lamps;
+    uint32_t type_first[28];
+    uint32_t lamps[FRAME_MAX_LAMPS];
+};
+// counts: 28 * n words; row_total: 28 words; done: one word, zero before the first launch
+void launch_frame_visible(const uint4* recs, const uint32_t* rec_first, const uint2* area_xy, int n,
+                          const FrameView& view, uint8_t* area_flag, uint32_t* counts, uint32_t* row_total,
+                          uint32_t* done, FrameTotals* totals, uint32_t* visible, cudaStream_t stream);
+
 // ---- edits (K5) and height map (K6)
 // hash_keys must be filled with 0xFF bytes, hash_vals / dirty_flags / dirty_count / status with 0
 void launch_apply_edits(const uint4* edits, int n, AreaMap map, uint8_t* pool_voxels,
