@@ -259,6 +259,29 @@ def main():
     value = n_mesh * world * args.steps / (ms * 1e-3)
     kern = {k: v / args.steps for k, v in kern.items()}
 
+    # ---- per-frame visibility over the resident mesh (K7; not part of `value`): a camera on the
+    # spawn surface with a render distance that covers the whole region
+    frame = None
+    if world == 1:
+        view = vg.make_view((8.0, 8.0, 58.0), (9.0, 8.5, 59.0), render_size=REGION // 2)
+        ctx.set_timing(True)
+        for _ in range(3):
+            vis = ctx.visible(view, read=False)
+        f_ms = 0.0
+        for _ in range(10):
+            vis = ctx.visible(view, read=False)
+            f_ms += ctx.timings()["visible_ms"]
+        f_ms /= 10
+        _, _, flags = ctx.visible(view)
+        rf = np.empty(n_mesh + 1, np.uint32)
+        ctx.mesh_read(info, out=(rf, None, None, None, None))
+        recs_in_view = int((np.diff(rf.astype(np.int64)) * flags).sum())
+        frame_bytes = recs_in_view * 16 + vis["n_visible"] * 4
+        frame = {"ms": f_ms, "visible_areas": vis["n_areas"], "records_tested": recs_in_view,
+                 "visible_voxels": vis["n_visible"], "visible_faces": vis["n_faces"],
+                 "records_per_s": recs_in_view / (f_ms * 1e-3), "algorithmic_bytes": frame_bytes,
+                 "note": "vx_visible: areas + count + scan + scatter (4 launches); the records are read twice"}
+
     # ---- end to end through the C ABI with host buffers (`e2e`)
     pin = {
         "vox": vg.PinnedArray((n_gen, 32768), np.uint8), "mh": vg.PinnedArray((n_gen, 256), np.uint8),
@@ -356,8 +379,22 @@ def main():
                           "f64_ops": s2 * F2_OPS + s3 * F3_OPS},
     }
 
+    if frame is not None:
+        frame["roofline"] = hbm_roof(frame["algorithmic_bytes"], frame["ms"])
+        line["frame"] = frame
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
+
+        if frame is not None:  # the same frame on one host thread (the reference: rayon par_iter)
+            import time
+
+            recs_h = np.empty(info["n_recs"], vg.REC_DTYPE)
+            rf_h = np.empty(n_mesh + 1, np.uint32)
+            ctx.mesh_read(info, out=(rf_h, None, recs_h, None, None))
+            oview = oracle.make_view((8.0, 8.0, 58.0), (9.0, 8.5, 59.0), render_size=REGION // 2)
+            t0 = time.perf_counter()
+            oracle.filter_visible(recs_h, rf_h, mesh_xy, oview)
+            frame["cpu_port_ms_1_thread"] = (time.perf_counter() - t0) * 1e3
 
         c = cpu_pass(oracle.hash_world_name(WORLD_NAME), CPU_SAMPLE, faithful=True)
         g = cpu_pass(oracle.hash_world_name(WORLD_NAME), CPU_SAMPLE, faithful=False)

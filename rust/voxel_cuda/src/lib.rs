@@ -49,6 +49,29 @@ pub struct vx_mesh_info {
     pub rec_bytes: u64,
 }
 
+/// Camera state of one frame (`vx_view`), see `Pipeline::visible`.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct vx_view {
+    pub cam_pos: [f32; 3],
+    pub cam_target_z: f32,
+    pub look: [f32; 3],
+    pub render_size: u32,
+    pub head_in_water: u32,
+    pub show_map: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct vx_visible_info {
+    pub n_visible: u64,
+    pub n_faces: u64,
+    pub n_areas: u32,
+    pub n_lamps: u32,
+    pub type_first: [u32; 28],
+    pub lamps: [u32; 64],
+}
+
 /// macroquad::ui::Vertex is `#[repr(C)] { position: Vec3, uv: Vec2, color: [u8; 4], normal: Vec4 }`
 /// with glam's scalar-math feature = 40 bytes; the GPU writes exactly these bytes.
 pub const VERTEX_BYTES: usize = 40;
@@ -82,6 +105,8 @@ extern "C" {
                           n_dirty: *mut c_int) -> c_int;
     pub fn vx_heightmap(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, cam_area_x: u32,
                         cam_area_y: u32, rgba: *mut u8) -> c_int;
+    pub fn vx_visible(ctx: *mut vx_ctx, view: *const vx_view, info: *mut vx_visible_info) -> c_int;
+    pub fn vx_visible_read(ctx: *mut vx_ctx, rec_index: *mut u32, area_visible: *mut u8) -> c_int;
     pub fn vx_light(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, light_out: *mut u8,
                     iterations: *mut c_int) -> c_int;
 }
@@ -197,6 +222,20 @@ impl Pipeline {
         assert_eq!(rgba.len(), 512 * 512 * 4);
         let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
         self.check(unsafe { vx_heightmap(self.ctx, xy.as_ptr(), areas.len() as c_int, cam.0, cam.1, rgba.as_mut_ptr()) })
+    }
+}
+
+impl Pipeline {
+    /// One frame of `set_voxel_shader_and_find_visible_areas` + `render_voxels`
+    /// (graphics/renderer.rs:365-452) over the batch of the last `mesh` call: returns the summary
+    /// and the record indices to draw, already in `optimise_render_order`.
+    pub fn visible(&self, view: &vx_view) -> Result<(vx_visible_info, Vec<u32>), VxError> {
+        let mut info = std::mem::MaybeUninit::<vx_visible_info>::zeroed();
+        self.check(unsafe { vx_visible(self.ctx, view, info.as_mut_ptr()) })?;
+        let info = unsafe { info.assume_init() };
+        let mut idx = vec![0u32; info.n_visible as usize];
+        self.check(unsafe { vx_visible_read(self.ctx, idx.as_mut_ptr(), std::ptr::null_mut()) })?;
+        Ok((info, idx))
     }
 }
 

@@ -4,7 +4,8 @@
 //   generator.rs:155-220   test_generate_area, _different_locations, _different_seeds, _same_area,
 //                          _heights_calculated_correctly
 //   world.rs:288-336       test_get_same_location, test_get_renderable_locations_for_area (structural)
-//   renderer                face count bookkeeping, edits through World::set + update_location
+//   renderer                face count bookkeeping, edits through World::set + update_location,
+//                          one frame of render_voxels (visible areas / voxels, draw order)
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -109,6 +110,26 @@ int main() {
     CHECK(renderer.get_voxel_face_count() == before);
     CHECK(renderer.meshes().at({62500, 62500}).lights.empty());
     CHECK(world.get_height(lamp_at) > 20);
+
+    // one frame (renderer.rs:365-452): everything in the map view, a strict subset when looking +x
+    // from the spawn column, nothing drawn twice, every drawn voxel has a mesh
+    renderer.update_locations(world, inner);  // one batch over the whole zone = the set a frame walks
+    const FrameResult all = renderer.render_voxels(world, Camera3D{{8.f, 8.f, 50.f}, {9.f, 8.f, 50.f}}, 8, false, true);
+    CHECK(all.visible_areas == inner.size() && all.faces_visible == renderer.get_voxel_face_count());
+    const FrameResult some = renderer.render_voxels(world, Camera3D{{8.f, 8.f, 50.f}, {9.f, 8.f, 50.f}}, 8, false, false);
+    CHECK(some.visible_areas > 0 && some.visible_areas < all.visible_areas);
+    CHECK(some.faces_visible > 0 && some.faces_visible < all.faces_visible);
+    size_t some_faces = 0;
+    int last_type = -1;
+    for (const LocKey& k : some.draw_order) {
+        const AreaLocation a{k.x / AREA_SIZE, k.y / AREA_SIZE};
+        const MeshInfo& mi = renderer.meshes().at(a).mesh_map.at(k);
+        some_faces += mi.face_count;
+        CHECK(static_cast<int>(mi.voxel) >= last_type);  // grouped by voxel type
+        last_type = static_cast<int>(mi.voxel);
+        CHECK(static_cast<float>(static_cast<int>(k.x) - LOCATION_OFFSET) > 8.f - 6.f);  // nothing far behind the camera
+    }
+    CHECK(some_faces == some.faces_visible);
 
     // error behaviour: an unknown device has no CPU fallback
     bool threw = false;

@@ -16,6 +16,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <cmath>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -228,8 +229,53 @@ struct RenderArea {  // renderer.rs:48-73
     std::vector<LocKey> lights;  // Lamp voxels with at least one face
 };
 
-class Renderer {  // graphics/renderer.rs:97-322,455-472
+struct Camera3D {  // macroquad::camera::Camera3D, the two fields the visibility pass reads
+    float position[3];
+    float target[3];
+};
+struct FrameResult {  // what one frame draws
+    size_t visible_areas = 0, faces_visible = 0;  // render_voxels' return value (renderer.rs:414-452)
+    std::vector<LocKey> draw_order;                // voxels in draw_mesh order (optimise_render_order)
+    std::vector<LocKey> lights;                    // set_lights input: first <= 64 lamps (voxel_shader.rs:176-200)
+    size_t lamps_in_view = 0;
+};
+
+class Renderer {  // graphics/renderer.rs:97-322,365-472
 public:
+    // set_voxel_shader_and_find_visible_areas + render_voxels (renderer.rs:365-452) over the areas of
+    // the last load_all_blocking / update_locations batch: the per-frame filter runs on the device
+    // over the records kept there, the host only receives the indices of the meshes to draw.
+    FrameResult render_voxels(World& world, const Camera3D& camera, uint32_t render_size, bool head_in_water,
+                              bool show_map) {
+        const Pipeline& p = world.pipeline();
+        vx_view v{};
+        float d[3], len2 = 0.f;
+        for (int k = 0; k < 3; ++k) {
+            v.cam_pos[k] = camera.position[k];
+            d[k] = camera.target[k] - camera.position[k];
+        }
+        len2 = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
+        const float rcp = 1.0f / std::sqrt(len2);  // Vec3::normalize_or_zero
+        const bool ok = std::isfinite(rcp) && rcp > 0.0f;
+        for (int k = 0; k < 3; ++k) v.look[k] = ok ? d[k] * rcp : 0.0f;
+        v.cam_target_z = camera.target[2];
+        v.render_size = render_size;
+        v.head_in_water = head_in_water;
+        v.show_map = show_map;
+        vx_visible_info info{};
+        p.check(vx_visible(p.raw(), &v, &info));
+        std::vector<uint32_t> idx(info.n_visible);
+        p.check(vx_visible_read(p.raw(), idx.data(), nullptr));
+        FrameResult f;
+        f.visible_areas = info.n_areas;
+        f.faces_visible = info.n_faces;
+        f.lamps_in_view = info.n_lamps;
+        f.draw_order.reserve(idx.size());
+        for (uint32_t r : idx) f.draw_order.push_back(last_keys_[r]);
+        for (uint32_t k = 0; k < info.n_lamps && k < VX_MAX_LIGHTS; ++k) f.lights.push_back(last_keys_[info.lamps[k]]);
+        return f;
+    }
+
     // load_all_blocking (renderer.rs:468-472): skips areas already meshed (:311)
     void load_all_blocking(World& world, const std::vector<AreaLocation>& areas) {
         std::vector<AreaLocation> todo;
@@ -265,6 +311,7 @@ private:
         std::vector<Vertex> vertices(info.n_faces * 4);
         std::vector<uint16_t> indices(info.n_faces * 6);
         p.check(vx_mesh_read(p.raw(), rec_first.data(), face_first.data(), recs.data(), vertices.data(), indices.data()));
+        last_keys_.assign(info.n_recs, LocKey{0, 0, 0});
         for (int i = 0; i < n; ++i) {
             RenderArea ra;
             for (uint32_t r = rec_first[i]; r < rec_first[i + 1]; ++r) {
@@ -275,6 +322,7 @@ private:
                 mi.mesh.vertices.assign(vertices.begin() + size_t(rec.first_face) * 4, vertices.begin() + size_t(rec.first_face + nf) * 4);
                 mi.mesh.indices.assign(indices.begin() + size_t(rec.first_face) * 6, indices.begin() + size_t(rec.first_face + nf) * 6);
                 const LocKey key{rec.gx, rec.gy, gz};
+                last_keys_[r] = key;
                 if (voxel == Voxel::Lamp) ra.lights.push_back(key);  // RenderArea::insert, renderer.rs:60-67
                 ra.mesh_map.emplace(key, std::move(mi));
             }
@@ -282,6 +330,7 @@ private:
         }
     }
     std::map<AreaLocation, RenderArea> meshes_;
+    std::vector<LocKey> last_keys_;  // record index of the last batch -> voxel location
 };
 
 }  // namespace voxel_game
