@@ -96,7 +96,7 @@ typedef struct {
     float visible_ms;      /* K7 (vx_visible) */
     uint32_t gen_launches, mesh_launches, other_launches; /* kernels launched by the last call */
     uint32_t cave_columns;                                /* K1b work items of the last generate */
-    uint32_t reserved;
+    float codec_ms;        /* K8 / K9 (vx_encode_areas, vx_decode_areas) */
     /* work accounting of the last vx_generate (roofline numerators): octave-level simplex
      * evaluations executed and voxels that ran the cave noise */
     uint64_t simplex2_evals, simplex3_evals, cave_voxels;
@@ -185,6 +185,26 @@ int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_are
  * areas of the list that are not resident read as an empty area (height 127, world.rs:64-69). */
 int vx_heightmap(vx_ctx* ctx, const uint32_t* area_xy, int n, uint32_t cam_area_x,
                  uint32_t cam_area_y, uint8_t* rgba);
+
+/* ---- area save files: replaces store_blocking / load_blocking
+ * (service/persistence/world_persistence.rs:27-42,62-71) = write/read_binary_object with
+ * compression (generic_persistence.rs:17-103) of AreaDTO (model/area.rs:204-227) for batches of
+ * areas.  A file is  u32 LE 32771 || LZ4 block of [FB 00 80][32768 voxel bytes]  (lz4_flex
+ * compress_prepend_size over bincode config::standard()).  Files written here are plain LZ4
+ * blocks any decoder expands to the same bytes (they are not the byte sequence lz4_flex's
+ * compressor would pick); any valid file is accepted on the way in. */
+#define VX_AREA_FILE_MAX_BYTES 33300
+/* Compresses n resident areas on the device; *total_bytes = size of all files together. */
+int vx_encode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint64_t* total_bytes);
+/* files: total_bytes; offsets: n + 1 (file i = files[offsets[i] .. offsets[i+1])), named
+ * "<world>/area<x>_<y>.dat" by the caller (world_persistence.rs:29-31).  Either may be NULL. */
+int vx_encode_read(vx_ctx* ctx, uint8_t* files, uint64_t* offsets);
+/* Expands n files into resident areas (as vx_upload would) and computes their column heights
+ * (AreaDTO::into_area, area.rs:209-219).  ok[i] = 0 where the reference logs an error and generates
+ * the area instead (world_persistence.rs:66-70): such areas are NOT resident afterwards and their
+ * max_height_out rows are undefined; the caller passes them to vx_generate. */
+int vx_decode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* files,
+                    const uint64_t* offsets, uint8_t* ok, uint8_t* max_height_out);
 
 /* ---- per-frame visibility: replaces, for the mesh of the last vx_mesh call, the work
  * Renderer::set_voxel_shader_and_find_visible_areas and render_voxels do every frame before the

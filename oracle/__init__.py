@@ -148,6 +148,15 @@ def lib():
         L.vgo_filter_visible.restype = C.c_long
         L.vgo_filter_visible.argtypes = [C.c_void_p, u32p, u32p, C.c_int, C.POINTER(View), u8p, u32p, u32p,
                                          C.POINTER(C.c_long), u32p, C.POINTER(C.c_long)]
+        L.vgo_bincode_area.argtypes = [u8p, u8p]
+        L.vgo_lz4_decompress_block.restype = C.c_long
+        L.vgo_lz4_decompress_block.argtypes = [u8p, C.c_long, u8p, C.c_long]
+        L.vgo_lz4_compress_block.restype = C.c_long
+        L.vgo_lz4_compress_block.argtypes = [u8p, C.c_long, u8p]
+        L.vgo_area_file_encode.restype = C.c_long
+        L.vgo_area_file_encode.argtypes = [u8p, u8p]
+        L.vgo_area_file_decode.restype = C.c_int
+        L.vgo_area_file_decode.argtypes = [u8p, C.c_long, u8p]
         L.vgo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -444,3 +453,37 @@ def filter_visible(recs, rec_first, area_xy, view: View):
                                   C.byref(n_lamps))
     return dict(area_visible=area_visible, visible=visible[:nv].copy(), type_first=type_first,
                 n_faces=int(n_faces.value), lamps=lamps[:n_lamps.value].copy())
+
+
+# ------------------------------------------------------------------------------ area save files
+AREA_PAYLOAD_BYTES = 3 + 32768
+AREA_FILE_MAX_BYTES = 33300
+
+
+def lz4_decompress_block(src: bytes, cap: int):
+    """-> bytes, or None for a malformed stream."""
+    a = np.frombuffer(bytes(src), np.uint8) if len(src) else np.zeros(1, np.uint8)
+    out = np.empty(max(cap, 1), np.uint8)
+    n = lib().vgo_lz4_decompress_block(_p(a), len(src), _p(out), cap)
+    return None if n < 0 else out[:n].tobytes()
+
+
+def lz4_compress_block(src: bytes) -> bytes:
+    a = np.frombuffer(bytes(src), np.uint8)
+    out = np.empty(len(src) + len(src) // 255 + 64, np.uint8)
+    n = lib().vgo_lz4_compress_block(_p(a), len(src), _p(out))
+    return out[:n].tobytes()
+
+
+def area_file_encode(voxels: np.ndarray) -> bytes:
+    v = np.ascontiguousarray(voxels, np.uint8).reshape(32768)
+    out = np.empty(AREA_FILE_MAX_BYTES, np.uint8)
+    n = lib().vgo_area_file_encode(_p(v), _p(out))
+    return out[:n].tobytes()
+
+
+def area_file_decode(data: bytes):
+    """-> voxels u8[32768], or None where the reference falls back to generation."""
+    a = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
+    v = np.empty(32768, np.uint8)
+    return v if lib().vgo_area_file_decode(_p(a), len(data), _p(v)) == 0 else None

@@ -219,6 +219,17 @@ long vgo_filter_visible(const vgo_voxel_rec* recs, const uint32_t* rec_first, co
                         int n, const vgo_view* v, uint8_t* area_visible, uint32_t* visible,
                         uint32_t* type_first, long* n_faces, uint32_t* lamps, long* n_lamps);
 
+/* ---------------------------------------------------------------- area save files (codec.c)
+ * file = u32 LE size || LZ4 block of bincode(AreaDTO) (generic_persistence.rs:17-103,
+ * world_persistence.rs:27-71, area.rs:204-227); see codec.c for what is and is not pinned. */
+#define VGO_AREA_PAYLOAD_BYTES (3 + VGO_VOXELS_IN_AREA)
+#define VGO_AREA_FILE_MAX_BYTES 33300
+void vgo_bincode_area(const uint8_t* voxels, uint8_t* out);
+long vgo_lz4_decompress_block(const uint8_t* src, long n, uint8_t* dst, long cap);
+long vgo_lz4_compress_block(const uint8_t* src, long n, uint8_t* dst);
+long vgo_area_file_encode(const uint8_t* voxels, uint8_t* out);
+int vgo_area_file_decode(const uint8_t* file, long n, uint8_t* voxels);
+
 int vgo_max_threads(void);
 
 #ifdef __cplusplus

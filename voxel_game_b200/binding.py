@@ -40,7 +40,8 @@ ABI_SYMBOLS = [
     "vx_sync", "vx_set_timing", "vx_get_timings", "vx_host_alloc", "vx_host_free", "vx_set_seed",
     "vx_hash_world_name", "vx_generate", "vx_upload", "vx_read_areas", "vx_unload",
     "vx_resident_count", "vx_column_heights", "vx_mesh", "vx_mesh_read", "vx_apply_edits",
-    "vx_heightmap", "vx_visible", "vx_visible_read", "vx_light", "vx_diag_fp64_rate",
+    "vx_heightmap", "vx_visible", "vx_visible_read", "vx_encode_areas", "vx_encode_read", "vx_decode_areas",
+    "vx_light", "vx_diag_fp64_rate",
 ]
 
 
@@ -61,7 +62,7 @@ class Timings(C.Structure):
                 ("mesh_emit_ms", C.c_float), ("edit_ms", C.c_float), ("heightmap_ms", C.c_float),
                 ("light_ms", C.c_float), ("visible_ms", C.c_float), ("gen_launches", C.c_uint32),
                 ("mesh_launches", C.c_uint32), ("other_launches", C.c_uint32),
-                ("cave_columns", C.c_uint32), ("reserved", C.c_uint32), ("simplex2_evals", C.c_uint64),
+                ("cave_columns", C.c_uint32), ("codec_ms", C.c_float), ("simplex2_evals", C.c_uint64),
                 ("simplex3_evals", C.c_uint64), ("cave_voxels", C.c_uint64), ("cave_evals", C.c_uint64)]
 
     def as_dict(self):
@@ -152,6 +153,9 @@ def load():
     L.vx_mesh_read.argtypes = [vp, vp, vp, vp, vp, vp]
     L.vx_apply_edits.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int)]
     L.vx_heightmap.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_uint32, vp]
+    L.vx_encode_areas.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_uint64)]
+    L.vx_encode_read.argtypes = [vp, vp, vp]
+    L.vx_decode_areas.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
     L.vx_visible.argtypes = [vp, C.POINTER(View), C.POINTER(VisibleInfo)]
     L.vx_visible_read.argtypes = [vp, vp, vp]
     L.vx_light.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int)]
@@ -341,6 +345,35 @@ class Context:
             rgba = np.empty((512, 512, 4), np.uint8)
         self._check(self._lib.vx_heightmap(self._h, xy.ctypes.data, xy.shape[0], cam_ax, cam_ay, rgba.ctypes.data))
         return rgba
+
+    # -- area save files
+    def encode_areas(self, area_xy, read: bool = True, out=None):
+        """store_blocking for a batch of resident areas -> (files u8[total], offsets u64[n+1]);
+        file i = files[offsets[i]:offsets[i+1]].  read=False leaves them on the device and returns
+        the total size."""
+        xy = _xy(area_xy)
+        total = C.c_uint64(0)
+        self._check(self._lib.vx_encode_areas(self._h, xy.ctypes.data, xy.shape[0], C.byref(total)))
+        if not read:
+            return int(total.value)
+        files = out if out is not None else np.empty(int(total.value), np.uint8)
+        offsets = np.empty(xy.shape[0] + 1, np.uint64)
+        self._check(self._lib.vx_encode_read(self._h, files.ctypes.data if files.size else None, offsets.ctypes.data))
+        return files[: int(total.value)], offsets
+
+    def decode_areas(self, area_xy, files, offsets, read_heights: bool = True):
+        """load_blocking for a batch of files -> (ok u8[n], max_height u8[n,256] or None); areas with
+        ok == 0 are not resident afterwards (the caller generates them)."""
+        xy = _xy(area_xy)
+        n = xy.shape[0]
+        files = np.ascontiguousarray(files, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        assert offsets.shape[0] == n + 1
+        ok = np.zeros(n, np.uint8)
+        mh = np.empty((n, COLUMNS_IN_AREA), np.uint8) if read_heights else None
+        self._check(self._lib.vx_decode_areas(self._h, xy.ctypes.data, n, files.ctypes.data if files.size else None,
+                                              offsets.ctypes.data, ok.ctypes.data, _ptr(mh)))
+        return ok, mh
 
     def visible(self, view: View, read: bool = True):
         """Per-frame visibility over the mesh of the last mesh() call.

@@ -121,7 +121,7 @@ struct HostAreaMap {
 };
 
 enum TimerId { TM_GEN_COLUMNS, TM_GEN_CAVES, TM_GEN_FINISH, TM_MESH_COUNT, TM_MESH_EMIT, TM_EDIT,
-               TM_HEIGHTMAP, TM_LIGHT, TM_VISIBLE, TM_COUNT };
+               TM_HEIGHTMAP, TM_LIGHT, TM_VISIBLE, TM_CODEC, TM_COUNT };
 
 }  // namespace
 
@@ -164,6 +164,9 @@ struct vx_ctx {
     DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
     DevBuf d_heightmap, d_light, d_slot_to_job, d_finished, d_warp_totals, d_mesh_nbr;
     DevBuf d_mesh_xy, d_frame_flags, d_frame_counts, d_frame_small, d_frame_visible;  // per-frame visibility (K7)
+    DevBuf d_codec_sizes, d_codec_offsets, d_codec_bytes, d_codec_status;  // area save files (K8 / K9)
+    int codec_n = -1;              // areas of the last vx_encode_areas
+    uint64_t codec_total = 0;
     bool frame_ready = false;      // d_frame_visible / d_frame_flags hold the result of vx_visible for this mesh
     uint64_t frame_n_visible = 0;
     bool heightmap_init = false;
@@ -226,7 +229,7 @@ void collect_timers(vx_ctx* c) {
                             &c->timings.gen_finish_ms,  &c->timings.mesh_count_ms,
                             &c->timings.mesh_emit_ms,   &c->timings.edit_ms,
                             &c->timings.heightmap_ms,   &c->timings.light_ms,
-                            &c->timings.visible_ms};
+                            &c->timings.visible_ms,     &c->timings.codec_ms};
     for (int i = 0; i < TM_COUNT; ++i)
         if (c->ev_used[i]) {
             float ms = 0.f;
@@ -470,7 +473,8 @@ void vx_destroy(vx_ctx* ctx) {
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
                       &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_warp_totals, &ctx->d_mesh_nbr, &ctx->d_mesh_xy, &ctx->d_frame_flags,
-                      &ctx->d_frame_counts, &ctx->d_frame_small, &ctx->d_frame_visible, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
+                      &ctx->d_frame_counts, &ctx->d_frame_small, &ctx->d_frame_visible, &ctx->d_codec_sizes,
+                      &ctx->d_codec_offsets, &ctx->d_codec_bytes, &ctx->d_codec_status, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
                       &ctx->d_vertices, &ctx->d_indices};
     for (DevBuf* b : bufs) b->release();
     ctx->h_stage.release();
@@ -825,6 +829,125 @@ int vx_mesh_read(vx_ctx* ctx, uint32_t* rec_first, uint32_t* face_first, vx_voxe
     if (vertices && mi.vertex_bytes) VX_CUDA(cudaMemcpyAsync(vertices, ctx->d_vertices.p, mi.vertex_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (indices && mi.index_bytes) VX_CUDA(cudaMemcpyAsync(indices, ctx->d_indices.p, mi.index_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_encode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint64_t* total_bytes) {
+    if (!ctx || n < 0 || (n > 0 && !area_xy) || !total_bytes) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    reset_timers(ctx);
+    *total_bytes = 0;
+    ctx->codec_n = -1;
+    ctx->codec_total = 0;
+    if (n == 0) {
+        ctx->codec_n = 0;
+        return VX_OK;
+    }
+    std::vector<int> slots(n);
+    for (int i = 0; i < n; ++i) {
+        slots[i] = host_slot(ctx, area_xy[2 * i], area_xy[2 * i + 1]);
+        if (slots[i] < 0) return fail(ctx, VX_ERR_NOT_LOADED, "vx_encode_areas: area not resident");
+    }
+    int st;
+    if ((st = upload_jobs(ctx, area_xy, slots, n)) != VX_OK) return st;
+    VX_CUDA(ctx->d_codec_sizes.ensure((size_t)n * 4));
+    VX_CUDA(ctx->d_codec_offsets.ensure((size_t)(n + 1) * 8));
+    VX_CUDA(ctx->h_small.ensure(64));
+    unsigned long long* offsets = ctx->d_codec_offsets.as<unsigned long long>();
+    {
+        ScopedTimer t(ctx, TM_CODEC);
+        launch_codec_sizes(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_codec_sizes.as<uint32_t>(), offsets, ctx->stream);
+    }
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaMemcpyAsync(ctx->h_small.p, offsets + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((st = sync_stream(ctx)) != VX_OK) return st;
+    collect_timers(ctx);
+    const uint64_t total = *ctx->h_small.as<uint64_t>();
+    VX_CUDA(ctx->d_codec_bytes.ensure(std::max<size_t>(16, total)));
+    {
+        ScopedTimer t(ctx, TM_CODEC);
+        launch_codec_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, offsets, ctx->d_codec_bytes.as<uint8_t>(), ctx->stream);
+    }
+    ctx->timings.other_launches += 3;
+    VX_CUDA(cudaGetLastError());
+    if ((st = sync_stream(ctx)) != VX_OK) return st;
+    collect_timers(ctx);
+    ctx->codec_n = n;
+    ctx->codec_total = total;
+    *total_bytes = total;
+    return VX_OK;
+}
+
+int vx_encode_read(vx_ctx* ctx, uint8_t* files, uint64_t* offsets) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (ctx->codec_n < 0) return fail(ctx, VX_ERR_INVALID, "vx_encode_read without vx_encode_areas");
+    VX_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->codec_n == 0) {
+        if (offsets) offsets[0] = 0;
+        return VX_OK;
+    }
+    if (files && ctx->codec_total)
+        VX_CUDA(cudaMemcpyAsync(files, ctx->d_codec_bytes.p, ctx->codec_total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (offsets)
+        VX_CUDA(cudaMemcpyAsync(offsets, ctx->d_codec_offsets.p, (size_t)(ctx->codec_n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_decode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* files,
+                    const uint64_t* offsets, uint8_t* ok, uint8_t* max_height_out) {
+    if (!ctx || n < 0 || (n > 0 && (!area_xy || !offsets || !ok))) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    reset_timers(ctx);
+    if (n == 0) return VX_OK;
+    for (int i = 0; i < n; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, VX_ERR_INVALID, "vx_decode_areas: offsets must not decrease");
+    const uint64_t total = offsets[n] - offsets[0];
+    if (total && !files) return fail(ctx, VX_ERR_INVALID, "vx_decode_areas: files is NULL");
+    std::vector<int> slots;
+    int st = acquire_slots(ctx, area_xy, n, slots);
+    if (st != VX_OK) return st;
+    if ((st = upload_jobs(ctx, area_xy, slots, n)) != VX_OK) return st;
+    VX_CUDA(ctx->d_codec_bytes.ensure(std::max<size_t>(16, total)));
+    VX_CUDA(ctx->d_codec_offsets.ensure((size_t)(n + 1) * 8));
+    VX_CUDA(ctx->d_codec_status.ensure((size_t)n));
+    ctx->codec_n = -1;  // d_codec_bytes no longer holds the result of vx_encode_areas
+    // offsets relative to the first file, as uploaded
+    std::vector<uint64_t> rel(n + 1);
+    for (int i = 0; i <= n; ++i) rel[i] = offsets[i] - offsets[0];
+    if (total) VX_CUDA(cudaMemcpyAsync(ctx->d_codec_bytes.p, files + offsets[0], total, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(cudaMemcpyAsync(ctx->d_codec_offsets.p, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ScopedTimer t(ctx, TM_CODEC);
+        launch_codec_decode(ctx->d_jobs.as<uint4>(), n, ctx->d_codec_bytes.as<uint8_t>(),
+                            ctx->d_codec_offsets.as<unsigned long long>(), ctx->d_voxels,
+                            ctx->d_codec_status.as<uint8_t>(), ctx->stream);
+    }
+    launch_column_heights(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_heights, ctx->d_slot_xy, ctx->d_planes,
+                          ctx->stream);
+    ctx->timings.other_launches += 2;
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaMemcpyAsync(ok, ctx->d_codec_status.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (max_height_out && (st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, max_height_out, true)) != VX_OK) return st;
+    if ((st = sync_stream(ctx)) != VX_OK) return st;  // rel[] was read by the copy above: keep it alive until here
+    collect_timers(ctx);
+    bool any = false;
+    for (int i = 0; i < n; ++i) {
+        if (ok[i]) continue;
+        const int s = ctx->index.erase(area_xy[2 * i], area_xy[2 * i + 1]);  // not resident after all
+        if (s < 0) continue;
+        ctx->slot_key[s] = ~0ull;
+        ctx->free_slots.push_back(s);
+        any = true;
+    }
+    if (any) {
+        ctx->map_dirty = true;
+        ++ctx->index_version;
+        std::sort(ctx->free_slots.begin(), ctx->free_slots.end(), std::greater<int>());
+    }
     return VX_OK;
 }
 

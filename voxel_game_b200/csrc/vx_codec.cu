@@ -1,0 +1,406 @@
+// vx_codec.cu -- area save files on the device (K8 encode, K9 decode).
+//
+// Replaces, for batches of resident areas, store_blocking / load_blocking
+// (service/persistence/world_persistence.rs:27-42,62-71) = write/read_binary_object with
+// compression (generic_persistence.rs:17-103) of AreaDTO { voxels: Box<[Voxel]> } (area.rs:204-227):
+//     file = u32 LE 32771  ||  LZ4 block of  [FB 00 80 (bincode varint 32768)] [32768 voxel bytes]
+// so that world pre-generation ships a few KB per area over PCIe instead of 32 KiB, and saved worlds
+// are expanded where the voxels are needed.
+//
+// Encode is a *row-granular* LZ4 compressor made for this data (index = x + 16 y + 256 z): a
+// 16-byte row either equals the row before it (match, offset 16: air, rock, flat ground), or the
+// row one slab up (match, offset 256: vertical structures), or is sent as 16 literals.  Runs of
+// rows of one kind are one LZ4 match / literal run, so all decisions are per row and independent:
+// kinds, run boundaries and output positions come from block-wide scans, no serial parse.  The
+// stream is a plain LZ4 block (last row always literal: the format wants the last 5 bytes literal
+// and the last match to start 12 bytes before the end), readable by any LZ4 decoder; it is not the
+// byte sequence lz4_flex would write, which no decoder requires.
+// Decode accepts any valid LZ4 block (byte-granular, overlapping matches): one warp per area walks
+// the sequences, the 32 lanes copy.
+#include "vx_kernels.hpp"
+
+namespace vx {
+namespace {
+
+constexpr int ROWS = VOXELS_IN_AREA / 16;
+constexpr uint32_t PAYLOAD = 3 + VOXELS_IN_AREA;  // bincode(AreaDTO)
+enum RowKind : uint8_t { LIT = 0, M16 = 1, M256 = 2 };
+
+__device__ __forceinline__ uint32_t ext_bytes(uint32_t v) { return v >= 15u ? 1u + (v - 15u) / 255u : 0u; }
+
+__device__ __forceinline__ uint8_t* put_ext(uint8_t* p, uint32_t v) {  // v >= 15
+    v -= 15u;
+    while (v >= 255u) {
+        *p++ = 255;
+        v -= 255u;
+    }
+    *p++ = (uint8_t)v;
+    return p;
+}
+
+__device__ __forceinline__ bool same_row(const uint4 a, const uint4 b) {
+    return a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w;
+}
+
+struct EncodeSmem {
+    uint4 rows[ROWS];
+    uint32_t seg_pos[ROWS];   // by segment END row: where the segment's bytes start in the block
+    uint32_t lit_base[ROWS];  // by segment START row: where a literal segment's literals start
+    uint16_t seg_start[ROWS];
+    uint8_t kind[ROWS];
+    uint32_t warp_tmp[8];
+    uint32_t total;
+};
+
+// inclusive max-scan / exclusive sum-scan over 2048 values, 8 consecutive per thread
+__device__ __forceinline__ uint32_t block_carry_max(uint32_t mine, uint32_t* warp_tmp, int tid) {
+    // returns the max over all threads before `tid` (0 if none)
+    const int lane = tid & 31, wid = tid >> 5;
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc = max(inc, o);
+    }
+    if (lane == 31) warp_tmp[wid] = inc;
+    __syncthreads();
+    uint32_t before = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+    if (lane == 0) before = 0;
+    for (int w = 0; w < wid; ++w) before = max(before, warp_tmp[w]);
+    __syncthreads();
+    return before;
+}
+
+__device__ __forceinline__ uint32_t block_carry_sum(uint32_t mine, uint32_t* warp_tmp, int tid, uint32_t* total) {
+    const int lane = tid & 31, wid = tid >> 5;
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_tmp[wid] = inc;
+    __syncthreads();
+    uint32_t before = inc - mine;
+    uint32_t all = 0;
+    for (int w = 0; w < 8; ++w) {
+        if (w < wid) before += warp_tmp[w];
+        all += warp_tmp[w];
+    }
+    *total = all;
+    __syncthreads();
+    return before;
+}
+
+// EMIT = false: sizes[i] = file size of area i.  EMIT = true: write the file at out + offsets[i].
+template <bool EMIT>
+__global__ void __launch_bounds__(256) codec_encode_kernel(const uint4* __restrict__ jobs,
+                                                           const uint8_t* __restrict__ pool_voxels,
+                                                           uint32_t* __restrict__ sizes,
+                                                           const unsigned long long* __restrict__ offsets,
+                                                           uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EncodeSmem& sm = *reinterpret_cast<EncodeSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const uint4 job = jobs[blockIdx.x];
+    const uint4* src = reinterpret_cast<const uint4*>(pool_voxels + (size_t)job.z * VOXELS_IN_AREA);
+    for (int i = tid; i < ROWS; i += 256) sm.rows[i] = src[i];
+    __syncthreads();
+
+    // 1. kind of every row; thread t owns rows 8t .. 8t+7
+    const int r0 = tid * 8;
+    uint8_t kind[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int r = r0 + k;
+        const uint4 v = sm.rows[r];
+        uint8_t c = LIT;
+        if (r > 0 && r < ROWS - 1) {
+            if (same_row(v, sm.rows[r - 1])) c = M16;
+            else if (r >= 16 && same_row(v, sm.rows[r - 16])) c = M256;
+        }
+        kind[k] = c;
+        sm.kind[r] = c;
+    }
+    __syncthreads();
+
+    // 2. start row of the segment (maximal run of one kind) every row belongs to
+    uint32_t last_start = 0;  // row + 1 of the last boundary among my rows, 0 = none
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int r = r0 + k;
+        if (r == 0 || sm.kind[r - 1] != kind[k]) last_start = (uint32_t)r + 1u;
+    }
+    uint32_t run_start = block_carry_max(last_start, sm.warp_tmp, tid);
+    uint16_t start[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int r = r0 + k;
+        if (r == 0 || sm.kind[r - 1] != kind[k]) run_start = (uint32_t)r + 1u;
+        start[k] = (uint16_t)(run_start - 1u);
+        sm.seg_start[r] = start[k];
+    }
+
+    // 3. bytes every segment contributes, accounted to its END row.  A literal segment opens a
+    //    sequence (token + length extension + literals); a match segment adds offset + extension,
+    //    and its own token if no literals precede it.  Row 0 carries the 3 bincode header bytes.
+    uint32_t contrib[8];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int r = r0 + k;
+        contrib[k] = 0;
+        if (r == ROWS - 1 || sm.kind[r + 1] != kind[k]) {  // segment end
+            const uint32_t s = start[k], len_rows = (uint32_t)r - s + 1u;
+            if (kind[k] == LIT) {
+                const uint32_t L = 16u * len_rows + (s == 0 ? 3u : 0u);
+                contrib[k] = 1u + ext_bytes(L) + L;
+            } else {
+                const bool own_token = sm.kind[s - 1] != LIT;  // s >= 1: row 0 is always literal
+                contrib[k] = (own_token ? 1u : 0u) + 2u + ext_bytes(16u * len_rows - 4u);
+            }
+        }
+        mine += contrib[k];
+    }
+    uint32_t block_bytes;
+    uint32_t pos = block_carry_sum(mine, sm.warp_tmp, tid, &block_bytes);
+    if (!EMIT) {
+        if (tid == 0) sizes[blockIdx.x] = 4u + block_bytes;  // compress_prepend_size: u32 LE size first
+        return;
+    }
+
+    uint8_t* file = out + offsets[blockIdx.x];
+    uint8_t* block = file + 4;
+    if (tid == 0) {
+        file[0] = (uint8_t)(PAYLOAD & 0xFF);
+        file[1] = (uint8_t)((PAYLOAD >> 8) & 0xFF);
+        file[2] = (uint8_t)((PAYLOAD >> 16) & 0xFF);
+        file[3] = (uint8_t)(PAYLOAD >> 24);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int r = r0 + k;
+        if (contrib[k]) {
+            sm.seg_pos[r] = pos;
+            if (kind[k] == LIT) {
+                const uint32_t s = start[k];
+                const uint32_t L = 16u * ((uint32_t)r - s + 1u) + (s == 0 ? 3u : 0u);
+                sm.lit_base[s] = pos + 1u + ext_bytes(L);
+            }
+        }
+        pos += contrib[k];
+    }
+    __syncthreads();
+
+    // 4. tokens, extensions, offsets: one thread per sequence (the match segment's end row, or the
+    //    last row for the closing literals-only sequence)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int r = r0 + k;
+        if (!contrib[k]) continue;
+        if (kind[k] != LIT) {
+            const uint32_t s = start[k], ml = 16u * ((uint32_t)r - s + 1u) - 4u;
+            const uint32_t offset = kind[k] == M16 ? 16u : 256u;
+            uint8_t* p;
+            if (sm.kind[s - 1] == LIT) {  // literals, then this match
+                const uint32_t ls = sm.seg_start[s - 1];
+                const uint32_t L = 16u * (s - ls) + (ls == 0 ? 3u : 0u);
+                uint8_t* t = block + sm.seg_pos[s - 1];
+                *t = (uint8_t)((min(L, 15u) << 4) | min(ml, 15u));
+                if (L >= 15u) put_ext(t + 1, L);
+                p = block + sm.seg_pos[r];
+            } else {
+                p = block + sm.seg_pos[r];
+                *p++ = (uint8_t)min(ml, 15u);
+            }
+            *p++ = (uint8_t)(offset & 0xFF);
+            *p++ = (uint8_t)(offset >> 8);
+            if (ml >= 15u) put_ext(p, ml);
+        } else if (r == ROWS - 1) {  // closing sequence: literals only
+            const uint32_t s = start[k];
+            const uint32_t L = 16u * ((uint32_t)r - s + 1u) + (s == 0 ? 3u : 0u);
+            uint8_t* t = block + sm.seg_pos[r];
+            *t = (uint8_t)(min(L, 15u) << 4);
+            if (L >= 15u) put_ext(t + 1, L);
+        }
+    }
+    // 5. literal rows, each by its owner
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (kind[k] != LIT) continue;
+        const int r = r0 + k;
+        const uint32_t s = start[k];
+        uint8_t* p = block + sm.lit_base[s] + 16u * ((uint32_t)r - s) + (s == 0 ? 3u : 0u);
+        if (r == 0) {  // bincode: slice length 32768 as a varint (marker 251 + u16 LE)
+            p[-3] = 251;
+            p[-2] = (uint8_t)(VOXELS_IN_AREA & 0xFF);
+            p[-1] = (uint8_t)(VOXELS_IN_AREA >> 8);
+        }
+        const uint4 v = sm.rows[r];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int b = 0; b < 16; ++b) p[b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+    }
+}
+
+// exclusive scan of the file sizes into 64-bit offsets; offsets[n] = total
+__global__ void __launch_bounds__(1024) codec_offsets_kernel(const uint32_t* __restrict__ sizes, int n,
+                                                             unsigned long long* __restrict__ offsets) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const unsigned long long c = i < n ? sizes[i] : 0ull;
+        unsigned long long inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long w = s_w[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, w, d);
+                if (lane >= d) w += o;
+            }
+            s_w[lane] = w;
+        }
+        __syncthreads();
+        const unsigned long long before = carry + (wid ? s_w[wid - 1] : 0ull) + inc - c;
+        if (i < n) offsets[i] = before;
+        __syncthreads();
+        if (tid == 1023) carry = before + c;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[n] = carry;
+}
+
+// ------------------------------------------------------------------------------------- decode
+constexpr uint32_t STAGE_BYTES = 16384;  // compressed files up to this size are parsed from shared memory
+
+struct DecodeSmem {
+    uint8_t out[PAYLOAD + 13];  // 32784: 16-byte multiple
+    uint8_t in[STAGE_BYTES];
+};
+
+// One warp per file.  status[i] = 1 if the file expands to a well-formed AreaDTO (then the voxels
+// are in the area's pool slot), 0 where the reference logs an error and generates the area instead
+// (world_persistence.rs:66-70): bad size prefix, malformed LZ4 stream, wrong slice length, voxel id
+// >= 27.
+__global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restrict__ jobs,
+                                                          const uint8_t* __restrict__ files,
+                                                          const unsigned long long* __restrict__ offsets,
+                                                          uint8_t* __restrict__ pool_voxels,
+                                                          uint8_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DecodeSmem& sm = *reinterpret_cast<DecodeSmem*>(smem_raw);
+    const int lane = threadIdx.x;
+    const uint4 job = jobs[blockIdx.x];
+    const uint8_t* file = files + offsets[blockIdx.x];
+    const unsigned long long n64 = offsets[blockIdx.x + 1] - offsets[blockIdx.x];
+    bool ok = n64 >= 4 && n64 <= 0x7FFFFFFFull;
+    const uint32_t n = ok ? (uint32_t)n64 : 0u;
+    if (ok) {  // decompress_size_prepended: u32 LE uncompressed size
+        const uint32_t size = file[0] | (file[1] << 8) | (file[2] << 16) | ((uint32_t)file[3] << 24);
+        ok = size == PAYLOAD;
+    }
+    const uint8_t* src = file;
+    if (ok && n <= STAGE_BYTES) {
+        for (uint32_t i = lane; i < n; i += 32) sm.in[i] = file[i];
+        src = sm.in;
+    }
+    __syncwarp();
+    uint32_t ip = 4, op = 0;
+    while (ok && ip < n) {
+        const uint32_t token = src[ip++];
+        uint32_t lit = token >> 4;
+        if (lit == 15u) {
+            uint32_t b;
+            do {
+                if (ip >= n) { ok = false; break; }
+                b = src[ip++];
+                lit += b;
+            } while (b == 255u);
+            if (!ok) break;
+        }
+        if (lit > n - ip || lit > PAYLOAD - op) { ok = false; break; }
+        for (uint32_t k = lane; k < lit; k += 32) sm.out[op + k] = src[ip + k];
+        ip += lit;
+        op += lit;
+        if (ip == n) break;  // last sequence: literals only
+        if (n - ip < 2u) { ok = false; break; }
+        const uint32_t offset = src[ip] | (src[ip + 1] << 8);
+        ip += 2;
+        if (offset == 0u || offset > op) { ok = false; break; }
+        uint32_t len = (token & 15u) + 4u;
+        if ((token & 15u) == 15u) {
+            uint32_t b;
+            do {
+                if (ip >= n) { ok = false; break; }
+                b = src[ip++];
+                len += b;
+            } while (b == 255u);
+            if (!ok) break;
+        }
+        if (len > PAYLOAD - op) { ok = false; break; }
+        __syncwarp();  // the literals are in place
+        // overlapping matches repeat the last `offset` bytes: every byte comes from before `op`
+        const uint8_t* from = sm.out + op - offset;
+        if (offset >= len) {
+            for (uint32_t k = lane; k < len; k += 32) sm.out[op + k] = from[k];
+        } else {
+            for (uint32_t k = lane; k < len; k += 32) sm.out[op + k] = from[k % offset];
+        }
+        __syncwarp();
+        op += len;
+    }
+    __syncwarp();
+    ok = ok && op == PAYLOAD;
+    // bincode: Box<[Voxel]> = varint length (FB 00 80) + one variant byte per voxel, each < 27
+    ok = ok && sm.out[0] == 251 && sm.out[1] == (VOXELS_IN_AREA & 0xFF) && sm.out[2] == (VOXELS_IN_AREA >> 8);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(pool_voxels + (size_t)job.z * VOXELS_IN_AREA);
+    bool valid = true;
+    if (ok) {
+        for (uint32_t w = lane; w < VOXELS_IN_AREA / 4; w += 32) {
+            const uint8_t* b = sm.out + 3 + 4 * w;
+            const uint32_t v0 = b[0], v1 = b[1], v2 = b[2], v3 = b[3];
+            valid = valid && v0 < (uint32_t)V_VARIANTS && v1 < (uint32_t)V_VARIANTS && v2 < (uint32_t)V_VARIANTS &&
+                    v3 < (uint32_t)V_VARIANTS;
+            dst[w] = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+        }
+    }
+    ok = ok && __all_sync(0xFFFFFFFFu, valid);
+    if (lane == 0) status[blockIdx.x] = ok ? 1 : 0;
+}
+
+}  // namespace
+
+void launch_codec_sizes(const uint4* jobs, int n, const uint8_t* pool_voxels, uint32_t* sizes,
+                        unsigned long long* offsets, cudaStream_t stream) {
+    if (n <= 0) return;
+    cudaFuncSetAttribute(codec_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncodeSmem));
+    codec_encode_kernel<false><<<n, 256, sizeof(EncodeSmem), stream>>>(jobs, pool_voxels, sizes, nullptr, nullptr);
+    codec_offsets_kernel<<<1, 1024, 0, stream>>>(sizes, n, offsets);
+}
+
+void launch_codec_emit(const uint4* jobs, int n, const uint8_t* pool_voxels, const unsigned long long* offsets,
+                       uint8_t* out, cudaStream_t stream) {
+    if (n <= 0) return;
+    cudaFuncSetAttribute(codec_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncodeSmem));
+    codec_encode_kernel<true><<<n, 256, sizeof(EncodeSmem), stream>>>(jobs, pool_voxels, nullptr, offsets, out);
+}
+
+void launch_codec_decode(const uint4* jobs, int n, const uint8_t* files, const unsigned long long* offsets,
+                         uint8_t* pool_voxels, uint8_t* status, cudaStream_t stream) {
+    if (n <= 0) return;
+    cudaFuncSetAttribute(codec_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
+    codec_decode_kernel<<<n, 32, sizeof(DecodeSmem), stream>>>(jobs, files, offsets, pool_voxels, status);
+}
+
+}  // namespace vx

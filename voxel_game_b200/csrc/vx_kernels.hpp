@@ -70,6 +70,15 @@ void launch_frame_visible(const uint4* recs, const uint32_t* rec_first, const ui
                           const FrameView& view, uint8_t* area_flag, uint32_t* counts, uint32_t* row_total,
                           uint32_t* done, FrameTotals* totals, uint32_t* visible, cudaStream_t stream);
 
+// ---- area save files (K8 encode, K9 decode), vx_codec.cu; jobs = {ax, ay, slot, 0}
+constexpr uint32_t AREA_FILE_MAX_BYTES = 33300;  // 4 + 3 + 32768 literals + token / length bytes
+void launch_codec_sizes(const uint4* jobs, int n, const uint8_t* pool_voxels, uint32_t* sizes,
+                        unsigned long long* offsets /* n + 1 */, cudaStream_t stream);
+void launch_codec_emit(const uint4* jobs, int n, const uint8_t* pool_voxels, const unsigned long long* offsets,
+                       uint8_t* out, cudaStream_t stream);
+void launch_codec_decode(const uint4* jobs, int n, const uint8_t* files, const unsigned long long* offsets,
+                         uint8_t* pool_voxels, uint8_t* status /* n */, cudaStream_t stream);
+
 // ---- edits (K5) and height map (K6)
 // hash_keys must be filled with 0xFF bytes, hash_vals / dirty_flags / dirty_count / status with 0
 void launch_apply_edits(const uint4* edits, int n, AreaMap map, uint8_t* pool_voxels,
