@@ -282,6 +282,40 @@ def main():
                  "records_per_s": recs_in_view / (f_ms * 1e-3), "algorithmic_bytes": frame_bytes,
                  "note": "vx_visible: areas + count + scan + scatter (4 launches); the records are read twice"}
 
+    # ---- world pre-generation through save files (K8 / K9; not part of `value`): generate, compress
+    # on the device, ship the files to pinned host memory; and the way back (files -> resident areas)
+    codec = None
+    if world == 1:
+        ctx.set_timing(True)
+        total = ctx.encode_areas(gen_xy, read=False)  # first call: sizes the pinned buffer (and loads the kernels)
+        files_pin = vg.PinnedArray((int(total * 1.05) + 4096,), np.uint8)
+        for _ in range(2):
+            ctx.generate(gen_xy, read=False)
+            ctx.encode_areas(gen_xy, out=files_pin.array)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pre_steps = 5
+        torch.cuda.synchronize()
+        p0.record(stream)
+        for _ in range(pre_steps):
+            ctx.generate(gen_xy, read=False)
+            blob, offs = ctx.encode_areas(gen_xy, out=files_pin.array)
+            enc_ms = ctx.timings()["codec_ms"]
+        p1.record(stream)
+        torch.cuda.synchronize()
+        pre_ms = p0.elapsed_time(p1) / pre_steps
+        with vg.Context(local_rank, seed=seed) as other:
+            other.set_timing(True)
+            other.decode_areas(gen_xy, blob, offs, read_heights=False)
+            other.decode_areas(gen_xy, blob, offs, read_heights=False)
+            dec_ms = other.timings()["codec_ms"]
+        codec = {"encode_ms": enc_ms, "decode_ms": dec_ms, "areas": n_gen, "file_bytes_total": int(total),
+                 "file_bytes_per_area": total / n_gen, "ratio_vs_raw": n_gen * 32768 / total,
+                 "pregen_e2e_chunks_per_s": n_gen / (pre_ms * 1e-3), "pregen_e2e_ms": pre_ms,
+                 "pregen_d2h_bytes": int(total) + 8 * (n_gen + 1),
+                 "note": "pregen_e2e = vx_generate + vx_encode_areas + vx_encode_read of every file into pinned host "
+                         "memory (the bytes store_blocking writes to disk); encode reads 32 KiB per area twice"}
+        files_pin.free()
+
     # ---- end to end through the C ABI with host buffers (`e2e`)
     pin = {
         "vox": vg.PinnedArray((n_gen, 32768), np.uint8), "mh": vg.PinnedArray((n_gen, 256), np.uint8),
@@ -382,6 +416,10 @@ def main():
     if frame is not None:
         frame["roofline"] = hbm_roof(frame["algorithmic_bytes"], frame["ms"])
         line["frame"] = frame
+    if codec is not None:
+        codec["encode_roofline"] = hbm_roof(n_gen * 32768 + codec["file_bytes_total"], codec["encode_ms"])
+        codec["decode_roofline"] = hbm_roof(n_gen * (32768 + 8192 + 256) + codec["file_bytes_total"], codec["decode_ms"])
+        line["codec"] = codec
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
 

@@ -164,7 +164,7 @@ struct vx_ctx {
     DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
     DevBuf d_heightmap, d_light, d_slot_to_job, d_finished, d_warp_totals, d_mesh_nbr;
     DevBuf d_mesh_xy, d_frame_flags, d_frame_counts, d_frame_small, d_frame_visible;  // per-frame visibility (K7)
-    DevBuf d_codec_sizes, d_codec_offsets, d_codec_bytes, d_codec_status;  // area save files (K8 / K9)
+    DevBuf d_codec_sizes, d_codec_offsets, d_codec_bytes, d_codec_status, d_codec_kinds;  // area save files (K8 / K9)
     int codec_n = -1;              // areas of the last vx_encode_areas
     uint64_t codec_total = 0;
     bool frame_ready = false;      // d_frame_visible / d_frame_flags hold the result of vx_visible for this mesh
@@ -474,7 +474,7 @@ void vx_destroy(vx_ctx* ctx) {
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
                       &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_warp_totals, &ctx->d_mesh_nbr, &ctx->d_mesh_xy, &ctx->d_frame_flags,
                       &ctx->d_frame_counts, &ctx->d_frame_small, &ctx->d_frame_visible, &ctx->d_codec_sizes,
-                      &ctx->d_codec_offsets, &ctx->d_codec_bytes, &ctx->d_codec_status, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
+                      &ctx->d_codec_offsets, &ctx->d_codec_bytes, &ctx->d_codec_status, &ctx->d_codec_kinds, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
                       &ctx->d_vertices, &ctx->d_indices};
     for (DevBuf* b : bufs) b->release();
     ctx->h_stage.release();
@@ -853,11 +853,13 @@ int vx_encode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint64_t* total
     if ((st = upload_jobs(ctx, area_xy, slots, n)) != VX_OK) return st;
     VX_CUDA(ctx->d_codec_sizes.ensure((size_t)n * 4));
     VX_CUDA(ctx->d_codec_offsets.ensure((size_t)(n + 1) * 8));
+    VX_CUDA(ctx->d_codec_kinds.ensure((size_t)n * (VOXELS_IN_AREA / 16)));
     VX_CUDA(ctx->h_small.ensure(64));
     unsigned long long* offsets = ctx->d_codec_offsets.as<unsigned long long>();
     {
         ScopedTimer t(ctx, TM_CODEC);
-        launch_codec_sizes(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_codec_sizes.as<uint32_t>(), offsets, ctx->stream);
+        launch_codec_sizes(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_codec_kinds.as<uint8_t>(),
+                           ctx->d_codec_sizes.as<uint32_t>(), offsets, ctx->stream);
     }
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaMemcpyAsync(ctx->h_small.p, offsets + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -867,7 +869,8 @@ int vx_encode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint64_t* total
     VX_CUDA(ctx->d_codec_bytes.ensure(std::max<size_t>(16, total)));
     {
         ScopedTimer t(ctx, TM_CODEC);
-        launch_codec_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, offsets, ctx->d_codec_bytes.as<uint8_t>(), ctx->stream);
+        launch_codec_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_codec_kinds.as<uint8_t>(), offsets,
+                          ctx->d_codec_bytes.as<uint8_t>(), ctx->stream);
     }
     ctx->timings.other_launches += 3;
     VX_CUDA(cudaGetLastError());

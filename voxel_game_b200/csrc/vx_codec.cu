@@ -42,14 +42,20 @@ __device__ __forceinline__ bool same_row(const uint4 a, const uint4 b) {
     return a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w;
 }
 
-struct EncodeSmem {
+// The size pass stages the area's rows and classifies them; the kinds (one byte per row) go to a
+// scratch buffer, so the emit pass starts from 2 KiB per area instead of 32 and reads only the
+// literal rows again.
+struct SizeSmem {
     uint4 rows[ROWS];
+    uint8_t kind[ROWS];
+    uint32_t warp_tmp[8];
+};
+struct EmitSmem {
     uint32_t seg_pos[ROWS];   // by segment END row: where the segment's bytes start in the block
     uint32_t lit_base[ROWS];  // by segment START row: where a literal segment's literals start
     uint16_t seg_start[ROWS];
     uint8_t kind[ROWS];
     uint32_t warp_tmp[8];
-    uint32_t total;
 };
 
 // inclusive max-scan / exclusive sum-scan over 2048 values, 8 consecutive per thread
@@ -92,53 +98,73 @@ __device__ __forceinline__ uint32_t block_carry_sum(uint32_t mine, uint32_t* war
     return before;
 }
 
-// EMIT = false: sizes[i] = file size of area i.  EMIT = true: write the file at out + offsets[i].
+// EMIT = false: sizes[i] = file size of area i, kinds[i] = its row kinds.
+// EMIT = true: write the file at out + offsets[i].
 template <bool EMIT>
 __global__ void __launch_bounds__(256) codec_encode_kernel(const uint4* __restrict__ jobs,
                                                            const uint8_t* __restrict__ pool_voxels,
+                                                           uint8_t* __restrict__ kinds,
                                                            uint32_t* __restrict__ sizes,
                                                            const unsigned long long* __restrict__ offsets,
                                                            uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    EncodeSmem& sm = *reinterpret_cast<EncodeSmem*>(smem_raw);
+    SizeSmem& ss = *reinterpret_cast<SizeSmem*>(smem_raw);
+    EmitSmem& sm = *reinterpret_cast<EmitSmem*>(smem_raw);
+    uint8_t* sm_kind = EMIT ? sm.kind : ss.kind;
+    uint32_t* warp_tmp = EMIT ? sm.warp_tmp : ss.warp_tmp;
     const int tid = threadIdx.x;
     const uint4 job = jobs[blockIdx.x];
     const uint4* src = reinterpret_cast<const uint4*>(pool_voxels + (size_t)job.z * VOXELS_IN_AREA);
-    for (int i = tid; i < ROWS; i += 256) sm.rows[i] = src[i];
-    __syncthreads();
-
-    // 1. kind of every row; thread t owns rows 8t .. 8t+7
+    uint4* area_kinds = reinterpret_cast<uint4*>(kinds + (size_t)blockIdx.x * ROWS);
+    if (!EMIT) {
+        for (int i = tid; i < ROWS; i += 256) ss.rows[i] = src[i];
+        __syncthreads();
+        // 1. kind of every row, lanes on consecutive rows (conflict-free 16-byte reads)
+        for (int r = tid; r < ROWS; r += 256) {
+            const uint4 v = ss.rows[r];
+            uint8_t c = LIT;
+            if (r > 0 && r < ROWS - 1) {
+                if (same_row(v, ss.rows[r - 1])) c = M16;
+                else if (r >= 16 && same_row(v, ss.rows[r - 16])) c = M256;
+            }
+            ss.kind[r] = c;
+        }
+        __syncthreads();
+        if (tid < ROWS / 16) area_kinds[tid] = reinterpret_cast<const uint4*>(ss.kind)[tid];
+    } else {
+        if (tid < ROWS / 16) reinterpret_cast<uint4*>(sm.kind)[tid] = area_kinds[tid];
+        __syncthreads();
+    }
+    // everything below works on the kinds only, thread t owning rows 8t .. 8t+7
     const int r0 = tid * 8;
     uint8_t kind[8];
+    {
+        const uint2 k8 = *reinterpret_cast<const uint2*>(&sm_kind[r0]);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int r = r0 + k;
-        const uint4 v = sm.rows[r];
-        uint8_t c = LIT;
-        if (r > 0 && r < ROWS - 1) {
-            if (same_row(v, sm.rows[r - 1])) c = M16;
-            else if (r >= 16 && same_row(v, sm.rows[r - 16])) c = M256;
-        }
-        kind[k] = c;
-        sm.kind[r] = c;
+        for (int k = 0; k < 8; ++k) kind[k] = (uint8_t)((k < 4 ? k8.x >> (8 * k) : k8.y >> (8 * (k - 4))) & 0xFFu);
     }
-    __syncthreads();
+    const uint8_t kind_before = r0 > 0 ? sm_kind[r0 - 1] : (uint8_t)0xFF;
+    const uint8_t kind_after = r0 + 8 < ROWS ? sm_kind[r0 + 8] : (uint8_t)0xFF;
 
     // 2. start row of the segment (maximal run of one kind) every row belongs to
     uint32_t last_start = 0;  // row + 1 of the last boundary among my rows, 0 = none
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int r = r0 + k;
-        if (r == 0 || sm.kind[r - 1] != kind[k]) last_start = (uint32_t)r + 1u;
-    }
-    uint32_t run_start = block_carry_max(last_start, sm.warp_tmp, tid);
+    for (int k = 0; k < 8; ++k)
+        if ((k == 0 ? kind_before : kind[k - 1]) != kind[k]) last_start = (uint32_t)(r0 + k) + 1u;
+    uint32_t run_start = block_carry_max(last_start, warp_tmp, tid);
     uint16_t start[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int r = r0 + k;
-        if (r == 0 || sm.kind[r - 1] != kind[k]) run_start = (uint32_t)r + 1u;
+        if ((k == 0 ? kind_before : kind[k - 1]) != kind[k]) run_start = (uint32_t)(r0 + k) + 1u;
         start[k] = (uint16_t)(run_start - 1u);
-        sm.seg_start[r] = start[k];
+    }
+    if (EMIT) {
+        uint4 packed;
+        packed.x = start[0] | ((uint32_t)start[1] << 16);
+        packed.y = start[2] | ((uint32_t)start[3] << 16);
+        packed.z = start[4] | ((uint32_t)start[5] << 16);
+        packed.w = start[6] | ((uint32_t)start[7] << 16);
+        *reinterpret_cast<uint4*>(&sm.seg_start[r0]) = packed;
     }
 
     // 3. bytes every segment contributes, accounted to its END row.  A literal segment opens a
@@ -150,20 +176,20 @@ __global__ void __launch_bounds__(256) codec_encode_kernel(const uint4* __restri
     for (int k = 0; k < 8; ++k) {
         const int r = r0 + k;
         contrib[k] = 0;
-        if (r == ROWS - 1 || sm.kind[r + 1] != kind[k]) {  // segment end
+        if ((k == 7 ? kind_after : kind[k + 1]) != kind[k]) {  // segment end (0xFF after the last row)
             const uint32_t s = start[k], len_rows = (uint32_t)r - s + 1u;
             if (kind[k] == LIT) {
                 const uint32_t L = 16u * len_rows + (s == 0 ? 3u : 0u);
                 contrib[k] = 1u + ext_bytes(L) + L;
             } else {
-                const bool own_token = sm.kind[s - 1] != LIT;  // s >= 1: row 0 is always literal
+                const bool own_token = sm_kind[s - 1] != LIT;  // s >= 1: row 0 is always literal
                 contrib[k] = (own_token ? 1u : 0u) + 2u + ext_bytes(16u * len_rows - 4u);
             }
         }
         mine += contrib[k];
     }
     uint32_t block_bytes;
-    uint32_t pos = block_carry_sum(mine, sm.warp_tmp, tid, &block_bytes);
+    uint32_t pos = block_carry_sum(mine, warp_tmp, tid, &block_bytes);
     if (!EMIT) {
         if (tid == 0) sizes[blockIdx.x] = 4u + block_bytes;  // compress_prepend_size: u32 LE size first
         return;
@@ -224,22 +250,25 @@ __global__ void __launch_bounds__(256) codec_encode_kernel(const uint4* __restri
             if (L >= 15u) put_ext(t + 1, L);
         }
     }
-    // 5. literal rows, each by its owner
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (kind[k] != LIT) continue;
-        const int r = r0 + k;
-        const uint32_t s = start[k];
+    // 5. literal rows, lanes on consecutive rows
+    for (int r = tid; r < ROWS; r += 256) {
+        if (sm.kind[r] != LIT) continue;
+        const uint32_t s = sm.seg_start[r];
         uint8_t* p = block + sm.lit_base[s] + 16u * ((uint32_t)r - s) + (s == 0 ? 3u : 0u);
         if (r == 0) {  // bincode: slice length 32768 as a varint (marker 251 + u16 LE)
             p[-3] = 251;
             p[-2] = (uint8_t)(VOXELS_IN_AREA & 0xFF);
             p[-1] = (uint8_t)(VOXELS_IN_AREA >> 8);
         }
-        const uint4 v = sm.rows[r];
+        const uint4 v = src[r];
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0) {
 #pragma unroll
-        for (int b = 0; b < 16; ++b) p[b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+            for (int q = 0; q < 4; ++q) reinterpret_cast<uint32_t*>(p)[q] = w[q];
+        } else {
+#pragma unroll
+            for (int b = 0; b < 16; ++b) p[b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+        }
     }
 }
 
@@ -282,10 +311,10 @@ __global__ void __launch_bounds__(1024) codec_offsets_kernel(const uint32_t* __r
 }
 
 // ------------------------------------------------------------------------------------- decode
-constexpr uint32_t STAGE_BYTES = 16384;  // compressed files up to this size are parsed from shared memory
+constexpr uint32_t STAGE_BYTES = 4096;  // compressed files up to this size are parsed from shared memory
 
 struct DecodeSmem {
-    uint8_t out[PAYLOAD + 13];  // 32784: 16-byte multiple
+    uint8_t raw[16 + VOXELS_IN_AREA];  // payload at raw + 13: its 32768 voxel bytes are 16-byte aligned
     uint8_t in[STAGE_BYTES];
 };
 
@@ -316,6 +345,7 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
         src = sm.in;
     }
     __syncwarp();
+    uint8_t* out = sm.raw + 13;
     uint32_t ip = 4, op = 0;
     while (ok && ip < n) {
         const uint32_t token = src[ip++];
@@ -330,7 +360,7 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
             if (!ok) break;
         }
         if (lit > n - ip || lit > PAYLOAD - op) { ok = false; break; }
-        for (uint32_t k = lane; k < lit; k += 32) sm.out[op + k] = src[ip + k];
+        for (uint32_t k = lane; k < lit; k += 32) out[op + k] = src[ip + k];
         ip += lit;
         op += lit;
         if (ip == n) break;  // last sequence: literals only
@@ -350,29 +380,34 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
         }
         if (len > PAYLOAD - op) { ok = false; break; }
         __syncwarp();  // the literals are in place
-        // overlapping matches repeat the last `offset` bytes: every byte comes from before `op`
-        const uint8_t* from = sm.out + op - offset;
-        if (offset >= len) {
-            for (uint32_t k = lane; k < len; k += 32) sm.out[op + k] = from[k];
-        } else {
-            for (uint32_t k = lane; k < len; k += 32) sm.out[op + k] = from[k % offset];
+        // An overlapping match repeats the last `offset` bytes.  Copy in rounds: each round copies
+        // from the start of the pattern as much as is already final (offset, then twice that, ...),
+        // so every round is a plain non-overlapping copy.
+        const uint8_t* from = out + op - offset;
+        uint32_t done = 0;
+        while (done < len) {
+            const uint32_t chunk = min(len - done, offset + done);
+            for (uint32_t k = lane; k < chunk; k += 32) out[op + done + k] = from[k];
+            done += chunk;
+            __syncwarp();
         }
-        __syncwarp();
         op += len;
     }
     __syncwarp();
     ok = ok && op == PAYLOAD;
     // bincode: Box<[Voxel]> = varint length (FB 00 80) + one variant byte per voxel, each < 27
-    ok = ok && sm.out[0] == 251 && sm.out[1] == (VOXELS_IN_AREA & 0xFF) && sm.out[2] == (VOXELS_IN_AREA >> 8);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(pool_voxels + (size_t)job.z * VOXELS_IN_AREA);
+    ok = ok && out[0] == 251 && out[1] == (VOXELS_IN_AREA & 0xFF) && out[2] == (VOXELS_IN_AREA >> 8);
+    uint4* dst = reinterpret_cast<uint4*>(pool_voxels + (size_t)job.z * VOXELS_IN_AREA);
+    const uint4* voxels = reinterpret_cast<const uint4*>(sm.raw + 16);
     bool valid = true;
     if (ok) {
-        for (uint32_t w = lane; w < VOXELS_IN_AREA / 4; w += 32) {
-            const uint8_t* b = sm.out + 3 + 4 * w;
-            const uint32_t v0 = b[0], v1 = b[1], v2 = b[2], v3 = b[3];
-            valid = valid && v0 < (uint32_t)V_VARIANTS && v1 < (uint32_t)V_VARIANTS && v2 < (uint32_t)V_VARIANTS &&
-                    v3 < (uint32_t)V_VARIANTS;
-            dst[w] = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+        const uint32_t limit = 0x01010101u * (uint32_t)(V_VARIANTS - 1);
+        for (uint32_t w = lane; w < VOXELS_IN_AREA / 16; w += 32) {
+            const uint4 v = voxels[w];
+            // any byte > 26 is not a Voxel variant (per-byte unsigned compare)
+            valid = valid && (__vcmpgtu4(v.x, limit) | __vcmpgtu4(v.y, limit) | __vcmpgtu4(v.z, limit) |
+                              __vcmpgtu4(v.w, limit)) == 0u;
+            dst[w] = v;
         }
     }
     ok = ok && __all_sync(0xFFFFFFFFu, valid);
@@ -381,19 +416,18 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
 
 }  // namespace
 
-void launch_codec_sizes(const uint4* jobs, int n, const uint8_t* pool_voxels, uint32_t* sizes,
+void launch_codec_sizes(const uint4* jobs, int n, const uint8_t* pool_voxels, uint8_t* kinds, uint32_t* sizes,
                         unsigned long long* offsets, cudaStream_t stream) {
     if (n <= 0) return;
-    cudaFuncSetAttribute(codec_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncodeSmem));
-    codec_encode_kernel<false><<<n, 256, sizeof(EncodeSmem), stream>>>(jobs, pool_voxels, sizes, nullptr, nullptr);
+    cudaFuncSetAttribute(codec_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SizeSmem));
+    codec_encode_kernel<false><<<n, 256, sizeof(SizeSmem), stream>>>(jobs, pool_voxels, kinds, sizes, nullptr, nullptr);
     codec_offsets_kernel<<<1, 1024, 0, stream>>>(sizes, n, offsets);
 }
 
-void launch_codec_emit(const uint4* jobs, int n, const uint8_t* pool_voxels, const unsigned long long* offsets,
-                       uint8_t* out, cudaStream_t stream) {
+void launch_codec_emit(const uint4* jobs, int n, const uint8_t* pool_voxels, uint8_t* kinds,
+                       const unsigned long long* offsets, uint8_t* out, cudaStream_t stream) {
     if (n <= 0) return;
-    cudaFuncSetAttribute(codec_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncodeSmem));
-    codec_encode_kernel<true><<<n, 256, sizeof(EncodeSmem), stream>>>(jobs, pool_voxels, nullptr, offsets, out);
+    codec_encode_kernel<true><<<n, 256, sizeof(EmitSmem), stream>>>(jobs, pool_voxels, kinds, nullptr, offsets, out);
 }
 
 void launch_codec_decode(const uint4* jobs, int n, const uint8_t* files, const unsigned long long* offsets,

@@ -72,10 +72,11 @@ void launch_frame_visible(const uint4* recs, const uint32_t* rec_first, const ui
 
 // ---- area save files (K8 encode, K9 decode), vx_codec.cu; jobs = {ax, ay, slot, 0}
 constexpr uint32_t AREA_FILE_MAX_BYTES = 33300;  // 4 + 3 + 32768 literals + token / length bytes
-void launch_codec_sizes(const uint4* jobs, int n, const uint8_t* pool_voxels, uint32_t* sizes,
+// kinds: n * 2048 bytes of scratch written by the size pass and read by the emit pass
+void launch_codec_sizes(const uint4* jobs, int n, const uint8_t* pool_voxels, uint8_t* kinds, uint32_t* sizes,
                         unsigned long long* offsets /* n + 1 */, cudaStream_t stream);
-void launch_codec_emit(const uint4* jobs, int n, const uint8_t* pool_voxels, const unsigned long long* offsets,
-                       uint8_t* out, cudaStream_t stream);
+void launch_codec_emit(const uint4* jobs, int n, const uint8_t* pool_voxels, uint8_t* kinds,
+                       const unsigned long long* offsets, uint8_t* out, cudaStream_t stream);
 void launch_codec_decode(const uint4* jobs, int n, const uint8_t* files, const unsigned long long* offsets,
                          uint8_t* pool_voxels, uint8_t* status /* n */, cudaStream_t stream);
 
