@@ -105,6 +105,10 @@ extern "C" {
                           n_dirty: *mut c_int) -> c_int;
     pub fn vx_heightmap(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, cam_area_x: u32,
                         cam_area_y: u32, rgba: *mut u8) -> c_int;
+    pub fn vx_encode_areas(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, total_bytes: *mut u64) -> c_int;
+    pub fn vx_encode_read(ctx: *mut vx_ctx, files: *mut u8, offsets: *mut u64) -> c_int;
+    pub fn vx_decode_areas(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, files: *const u8,
+                           offsets: *const u64, ok: *mut u8, max_height_out: *mut u8) -> c_int;
     pub fn vx_visible(ctx: *mut vx_ctx, view: *const vx_view, info: *mut vx_visible_info) -> c_int;
     pub fn vx_visible_read(ctx: *mut vx_ctx, rec_index: *mut u32, area_visible: *mut u8) -> c_int;
     pub fn vx_light(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, light_out: *mut u8,
@@ -226,6 +230,37 @@ impl Pipeline {
 }
 
 impl Pipeline {
+    /// `store_all_blocking` (world_persistence.rs:55-59) for resident areas: the bytes of every
+    /// `saves/<world>/area<x>_<y>.dat`, compressed on the device.
+    pub fn encode_areas(&self, areas: &[(u32, u32)]) -> Result<Vec<Vec<u8>>, VxError> {
+        let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
+        let mut total = 0u64;
+        self.check(unsafe { vx_encode_areas(self.ctx, xy.as_ptr(), areas.len() as c_int, &mut total) })?;
+        let mut blob = vec![0u8; total as usize];
+        let mut offsets = vec![0u64; areas.len() + 1];
+        self.check(unsafe { vx_encode_read(self.ctx, blob.as_mut_ptr(), offsets.as_mut_ptr()) })?;
+        Ok(offsets.windows(2).map(|w| blob[w[0] as usize..w[1] as usize].to_vec()).collect())
+    }
+
+    /// `load_blocking` (world_persistence.rs:62-71) for a batch of files read from disk: returns
+    /// which files were well-formed; the others are generated by the caller, as the reference does.
+    pub fn decode_areas(&self, areas: &[(u32, u32)], files: &[Vec<u8>]) -> Result<(Vec<bool>, Vec<u8>), VxError> {
+        assert_eq!(areas.len(), files.len());
+        let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
+        let mut offsets = vec![0u64; files.len() + 1];
+        for (i, f) in files.iter().enumerate() {
+            offsets[i + 1] = offsets[i] + f.len() as u64;
+        }
+        let blob: Vec<u8> = files.concat();
+        let mut ok = vec![0u8; files.len()];
+        let mut max_height = vec![0u8; files.len() * 256];
+        self.check(unsafe {
+            vx_decode_areas(self.ctx, xy.as_ptr(), areas.len() as c_int, blob.as_ptr(), offsets.as_ptr(),
+                            ok.as_mut_ptr(), max_height.as_mut_ptr())
+        })?;
+        Ok((ok.into_iter().map(|b| b != 0).collect(), max_height))
+    }
+
     /// One frame of `set_voxel_shader_and_find_visible_areas` + `render_voxels`
     /// (graphics/renderer.rs:365-452) over the batch of the last `mesh` call: returns the summary
     /// and the record indices to draw, already in `optimise_render_order`.
