@@ -114,9 +114,10 @@ int main() {
     // one frame (renderer.rs:365-452): everything in the map view, a strict subset when looking +x
     // from the spawn column, nothing drawn twice, every drawn voxel has a mesh
     renderer.update_locations(world, inner);  // one batch over the whole zone = the set a frame walks
-    const FrameResult all = renderer.render_voxels(world, Camera3D{{8.f, 8.f, 50.f}, {9.f, 8.f, 50.f}}, 8, false, true);
+    const float eye = static_cast<float>(world.get_height(Location{8, 8, 0}.to_internal())) - 3.f;  // above the ground
+    const FrameResult all = renderer.render_voxels(world, Camera3D{{8.f, 8.f, eye}, {9.f, 8.f, eye}}, 8, false, true);
     CHECK(all.visible_areas == inner.size() && all.faces_visible == renderer.get_voxel_face_count());
-    const FrameResult some = renderer.render_voxels(world, Camera3D{{8.f, 8.f, 50.f}, {9.f, 8.f, 50.f}}, 8, false, false);
+    const FrameResult some = renderer.render_voxels(world, Camera3D{{8.f, 8.f, eye}, {9.f, 8.f, eye}}, 8, false, false);
     CHECK(some.visible_areas > 0 && some.visible_areas < all.visible_areas);
     CHECK(some.faces_visible > 0 && some.faces_visible < all.faces_visible);
     size_t some_faces = 0;
