@@ -153,3 +153,27 @@ def test_codec_round_trip_full_region(ctx, seed):
         assert ok.all() and np.array_equal(mh2, mh)
         v2, _ = d.read_areas(xy)
         assert np.array_equal(v2, vox)
+
+
+@pytest.mark.parametrize("world_name,locations", [
+    ("test_world_persistence_load_temp_test_world", [(0, 0)]),
+    ("test_world_persistence_area_loader_batch_load", [(0, 0), (1, 0), (0, 1), (1, 1)]),
+])
+def test_reference_persistence_tests(world_name, locations):
+    """world_persistence.rs:183-238 (test_world_persistence_load, ..._area_loader_batch_load):
+    generate, store, load again, areas equal -- at the reference's own world names and locations
+    (the corner of the coordinate space)."""
+    seed = vg.hash_world_name(world_name)
+    assert seed == oracle.hash_world_name(world_name)
+    xy = np.array(locations, np.uint32)
+    with vg.Context(0, seed=seed) as c:
+        vox, mh = c.generate(xy)
+        ovox, omh, _, _ = oracle.generate_areas(seed, xy)
+        assert np.array_equal(vox, ovox) and np.array_equal(mh, omh)
+        blob, offsets = c.encode_areas(xy)                       # store_all_blocking
+        c.unload(xy)
+        assert c.resident_count() == 0
+        ok, mh2 = c.decode_areas(xy, blob, offsets)              # load_blocking / batch_load
+        assert ok.all()
+        v2, _ = c.read_areas(xy)
+        assert np.array_equal(v2, vox) and np.array_equal(mh2, mh)   # assert_areas_equal
