@@ -80,7 +80,7 @@ struct RowMasks {
 // T (2 x 4 KiB), per row the two x-halo bits (T of the +x neighbour's x = 0 and of the -x
 // neighbour's x = 15), and the y-halo rows (T of the +y neighbour's y = 0 row and of the -y
 // neighbour's y = 15 row, per z).
-struct PlaneTile {
+struct alignas(16) PlaneTile {
     uint16_t S[ROWS];
     uint16_t T[ROWS];
     uint8_t hx[ROWS];              // bit0: T(+x neighbour, x = 0), bit1: T(-x neighbour, x = 15)
@@ -263,19 +263,28 @@ __global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict
                                                          uint32_t* __restrict__ face_count,
                                                          uint32_t* __restrict__ warp_totals) {
     __shared__ uint32_t s_faces[8], s_recs[8];
+    __shared__ uint32_t s_busy[2];  // bit c * 8 + w: (chunk c, warp w) may have faces
     __shared__ PlaneTile tile;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const AreaView a = make_view(jobs[blockIdx.x], nbr[blockIdx.x], pool_voxels, pool_planes);
     load_plane_tile(tile, a, tid);
     __syncthreads();
-    uint32_t faces = 0, recs = 0;
     uint32_t* wt = warp_totals + (size_t)blockIdx.x * 64;
-#pragma unroll 1
-    for (int c = 0; c < ROWS / 256; ++c) {
-        if (slab_pair_empty(tile, 16 * c + 2 * wid)) {  // uniform across the warp (rows of 2 slabs)
-            if (lane == 0) wt[c * 8 + wid] = 0u;
-            continue;
-        }
+    if (tid < 64) {  // one thread per (chunk, warp): rows of two slabs
+        const bool empty = slab_pair_empty(tile, 16 * (tid >> 3) + 2 * (tid & 7));
+        if (empty) wt[tid] = 0u;
+        const uint32_t busy = __ballot_sync(0xFFFFFFFFu, !empty);
+        if (lane == 0) s_busy[wid] = busy;
+    }
+    __syncthreads();
+    // this warp's chunks: bits wid, 8 + wid, ... of the 64-bit mask
+    uint32_t mine = 0;
+#pragma unroll
+    for (int c = 0; c < ROWS / 256; ++c) mine |= ((s_busy[c >> 2] >> ((c & 3) * 8 + wid)) & 1u) << c;
+    uint32_t faces = 0, recs = 0;
+    while (mine) {
+        const int c = __ffs(mine) - 1;
+        mine &= mine - 1;
         const uint32_t v = row_counts(row_masks(tile, a, c * 256 + tid));
         const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, v);  // <= 32 * 96 faces, 32 * 16 voxels
         const uint32_t rows = __popc(__ballot_sync(0xFFFFFFFFu, v != 0u));
