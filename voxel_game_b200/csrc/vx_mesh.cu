@@ -545,9 +545,10 @@ __device__ __forceinline__ void flush_faces(EmitSmem& sm, uint32_t count, uint32
 //      the row's faces / records from the count kernel's (chunk, warp) totals and a warp scan; rows
 //      that have faces are staged in shared memory with their 16 voxel bytes.  (chunk, warp) pairs
 //      whose total is 0 -- all air or all buried, most of them -- are skipped.
-//   B  one thread per (staged row, x): visible voxels write their record and push their face
-//      descriptors.  The faces cluster in a few z levels, i.e. in a few warps of phase A; spreading
-//      them over the CTA by voxel is what keeps the warps evenly busy.
+//   B  one thread per visible voxel of the staged rows (binary search over the rows' record
+//      prefixes): it writes its record and pushes its face descriptors.  The faces cluster in a few
+//      z levels, i.e. in a few warps of phase A; spreading them over the CTA by voxel is what keeps
+//      the warps evenly busy.
 //   C  flush: lane pairs expand descriptors into 160-byte vertex blocks (flush_faces).
 __global__ void __launch_bounds__(256, 5) mesh_emit_kernel(const uint4* __restrict__ jobs,
                                                         const uint4* __restrict__ nbr,
@@ -584,8 +585,6 @@ __global__ void __launch_bounds__(256, 5) mesh_emit_kernel(const uint4* __restri
     }
     __syncthreads();
 
-    const int x = tid & 15;
-    const uint32_t below = (1u << x) - 1u, below2 = below | (below << 16);
     const unsigned long long area_total = sm.part[CHUNKS * 8];
     const bool one_pass = rows_of(area_total) <= ROW_CAP && faces_of(area_total) <= LIST_FACES;
     int c0 = 0;
@@ -626,20 +625,30 @@ __global__ void __launch_bounds__(256, 5) mesh_emit_kernel(const uint4* __restri
                 }
             }
             __syncthreads();
-            // ---- B
+            // ---- B: one thread per visible voxel of the pass (the record index), found in the staged
+            //      rows by binary search over their record prefixes -- every lane has work, and the
+            //      records leave as consecutive 16-byte stores
+            const uint32_t rec0 = recs_of(p0), nrecs = recs_of(p1) - rec0;
 #pragma unroll 1
-            for (int e = tid >> 4; e < nrows; e += 16) {
-                const uint4 m = sm.u.rows.masks[e];
+            for (uint32_t q = tid; q < nrecs; q += 256) {
+                const uint32_t target = rec0 + q;
+                int elo = 0, ehi = nrows;  // largest entry whose first record is <= target
+                while (ehi - elo > 1) {
+                    const int mid = (elo + ehi) >> 1;
+                    if (sm.u.rows.first[mid].y <= target) elo = mid; else ehi = mid;
+                }
+                const uint2 fq = sm.u.rows.first[elo];
+                const uint4 m = sm.u.rows.masks[elo];
+                const uint32_t vis = (m.x | (m.x >> 16) | m.y | (m.y >> 16) | m.z | (m.z >> 16)) & 0xFFFFu;
+                const int x = (int)__fns(vis, 0, (int)(target - fq.y) + 1);  // the (k+1)-th visible voxel of the row
+                const uint32_t below = (1u << x) - 1u, below2 = below | (below << 16);
                 const uint32_t t0 = (m.x >> x) & 0x10001u, t1 = (m.y >> x) & 0x10001u, t2 = (m.z >> x) & 0x10001u;
                 const uint32_t m6 = (t0 & 1u) | (t0 >> 15) | ((t1 & 1u) << 2) | (t1 >> 13) | ((t2 & 1u) << 4) | (t2 >> 11);
-                if (m6 == 0u) continue;
-                const uint2 fq = sm.u.rows.first[e];
-                const uint32_t vis = (m.x | (m.x >> 16) | m.y | (m.y >> 16) | m.z | (m.z >> 16)) & 0xFFFFu;
                 const uint32_t f = fq.x + __popc(m.x & below2) + __popc(m.y & below2) + __popc(m.z & below2);
-                const uint32_t voxel = reinterpret_cast<const uint8_t*>(&sm.u.rows.vox[e])[x];
+                const uint32_t voxel = reinterpret_cast<const uint8_t*>(&sm.u.rows.vox[elo])[x];
                 const uint32_t r = m.w;
                 if (!windowed || (f >= lo && f < hi))  // the window of the voxel's first face writes its record
-                    out.recs[rec_base + fq.y + __popc(vis & below)] =
+                    out.recs[rec_base + target] =
                         make_uint4(gx0 + x, gy0 + (r & 15u), (r >> 4) | (voxel << 8) | (m6 << 16) | ((uint32_t)__popc(m6) << 24),
                                    face_base + f);
                 const uint32_t desc0 = make_desc((int)r, x, 0, 0, voxel);
