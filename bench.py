@@ -419,6 +419,12 @@ def main():
         "roofline": roofline,
         "rooflines": rooflines,
         "kernel_ms_per_step": kern,
+        # the stages separately (device time of their kernels; column heights and bit
+        # planes are fused into generation, so LIGHT L1 has no time of its own)
+        "stage_chunks_per_s": {
+            "gen_plus_light": n_gen * world / ((kern["gen_columns_ms"] + kern["gen_caves_ms"] + kern["gen_finish_ms"]) * 1e-3),
+            "mesh": n_mesh * world / ((kern["mesh_count_ms"] + kern["mesh_emit_ms"]) * 1e-3),
+        },
         "work_per_step": {"simplex2_octave_evals": s2, "simplex3_octave_evals": s3, "cave_voxels": cave_vox,
                           "cave_octave_evals": cave3, "cave_octave_evals_without_early_exit": 14 * cave_vox,
                           "f64_ops": s2 * F2_OPS + s3 * F3_OPS},
