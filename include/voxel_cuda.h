@@ -179,6 +179,22 @@ int vx_mesh_read(vx_ctx* ctx, uint32_t* rec_first, uint32_t* face_first, vx_voxe
 int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_area_xy,
                    int* n_dirty);
 
+/* ---- explosions: replaces the voxel loop of BombSimulator::handle_explosions / explode_at
+ * (service/physics/bomb_simulator.rs:191-262) for the explosions of one tick (n <= 32; the
+ * reference caps active bombs at 10): every solid voxel (voxel.rs:117-128) whose centre is within
+ * 4.5 of a position becomes None (world.set + renderer.update_location).  positions: n Vec3 in
+ * player coordinates, processed like the reference from the last to the first.
+ *   removed_xyz  internal x, y, z of the removed voxels in the reference's visiting order
+ *                (room for 3 * 1331 * n words): the `locations_to_update` the water and
+ *                falling-voxel simulators are told about (bomb_simulator.rs:108-116)
+ *   bomb_xyz     voxels that were Voxel::Bomb when visited (add_active_bomb_from_explosion), same
+ *                order and room
+ *   dirty_area_xy as vx_apply_edits (room for 9 * n pairs); the caller re-runs vx_mesh on them
+ * All areas an explosion can reach (x, y within 5 voxels of it) must be resident. */
+#define VX_EXPLOSION_CANDIDATES 1331
+int vx_explode(vx_ctx* ctx, const float* positions, int n, uint32_t* removed_xyz, int* n_removed,
+               uint32_t* bomb_xyz, int* n_bombs, uint32_t* dirty_area_xy, int* n_dirty);
+
 /* ---- height map: replaces HeightMap::generate_height_map's pixel loop (height_map.rs:41-85).
  * rgba is the persistent 512*512*4 pixel buffer (stale pixels persist, as in the reference);
  * areas with |dx| or |dy| >= 16 from the camera area are skipped (height_map.rs:90-101);

@@ -157,6 +157,9 @@ def lib():
         L.vgo_area_file_encode.argtypes = [u8p, u8p]
         L.vgo_area_file_decode.restype = C.c_int
         L.vgo_area_file_decode.argtypes = [u8p, C.c_long, u8p]
+        L.vgo_explode.restype = C.c_int
+        L.vgo_explode.argtypes = [C.POINTER(_World), C.POINTER(C.c_float), C.c_int, u32p, C.POINTER(C.c_long),
+                                  u32p, C.POINTER(C.c_long)]
         L.vgo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -377,6 +380,19 @@ class World:
         """world.set + renderer.update_location."""
         if lib().vgo_apply_edit(C.byref(self._w), gx, gy, gz, voxel) != 0:
             raise ValueError("edit outside the loaded grid")
+
+    def explode(self, positions):
+        """BombSimulator::handle_explosions for one tick -> (removed [k,3] u32, bombs [m,3] u32), internal
+        coordinates in the reference's visiting order."""
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        n = len(pos)
+        removed = np.zeros((max(1331 * n, 1), 3), np.uint32)
+        bombs = np.zeros((max(1331 * n, 1), 3), np.uint32)
+        nr, nb = C.c_long(0), C.c_long(0)
+        if lib().vgo_explode(C.byref(self._w), pos.ctypes.data_as(C.POINTER(C.c_float)), n, _p(removed, C.c_uint32),
+                             C.byref(nr), _p(bombs, C.c_uint32), C.byref(nb)) != 0:
+            raise ValueError("explosion reaches outside the loaded grid")
+        return removed[: nr.value].copy(), bombs[: nb.value].copy()
 
     def light_flood(self) -> np.ndarray:
         light = np.zeros_like(self.voxels)

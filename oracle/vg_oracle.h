@@ -230,6 +230,13 @@ long vgo_lz4_compress_block(const uint8_t* src, long n, uint8_t* dst);
 long vgo_area_file_encode(const uint8_t* voxels, uint8_t* out);
 int vgo_area_file_decode(const uint8_t* file, long n, uint8_t* voxels);
 
+/* ---------------------------------------------------------------- bomb explosions (physics.c)
+ * BombSimulator::handle_explosions / explode_at (bomb_simulator.rs:191-262).  removed / bombs need
+ * room for 3 * 1331 * n words. */
+#define VGO_EXPLOSION_CANDIDATES 1331 /* (2 * ceil(4.5) + 1)^3 */
+int vgo_explode(vgo_world* w, const float* positions, int n, uint32_t* removed, long* n_removed,
+                uint32_t* bombs, long* n_bombs);
+
 int vgo_max_threads(void);
 
 #ifdef __cplusplus

@@ -109,6 +109,9 @@ extern "C" {
     pub fn vx_encode_read(ctx: *mut vx_ctx, files: *mut u8, offsets: *mut u64) -> c_int;
     pub fn vx_decode_areas(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, files: *const u8,
                            offsets: *const u64, ok: *mut u8, max_height_out: *mut u8) -> c_int;
+    pub fn vx_explode(ctx: *mut vx_ctx, positions: *const f32, n: c_int, removed_xyz: *mut u32,
+                      n_removed: *mut c_int, bomb_xyz: *mut u32, n_bombs: *mut c_int,
+                      dirty_area_xy: *mut u32, n_dirty: *mut c_int) -> c_int;
     pub fn vx_visible(ctx: *mut vx_ctx, view: *const vx_view, info: *mut vx_visible_info) -> c_int;
     pub fn vx_visible_read(ctx: *mut vx_ctx, rec_index: *mut u32, area_visible: *mut u8) -> c_int;
     pub fn vx_light(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, light_out: *mut u8,
@@ -259,6 +262,26 @@ impl Pipeline {
                             ok.as_mut_ptr(), max_height.as_mut_ptr())
         })?;
         Ok((ok.into_iter().map(|b| b != 0).collect(), max_height))
+    }
+
+    /// The voxel loops of `BombSimulator::handle_explosions` for one tick (at most 32 positions):
+    /// removed voxels and found bombs as internal (x, y, z), in the reference's visiting order, and
+    /// the areas to re-mesh.
+    #[allow(clippy::type_complexity)]
+    pub fn explode(&self, positions: &[[f32; 3]]) -> Result<(Vec<[u32; 3]>, Vec<[u32; 3]>, Vec<(u32, u32)>), VxError> {
+        let n = positions.len();
+        let flat: Vec<f32> = positions.iter().flatten().copied().collect();
+        let mut removed = vec![0u32; 3 * 1331 * n.max(1)];
+        let mut bombs = vec![0u32; 3 * 1331 * n.max(1)];
+        let mut dirty = vec![0u32; 2 * 9 * n.max(1)];
+        let (mut nr, mut nb, mut nd) = (0 as c_int, 0 as c_int, 0 as c_int);
+        self.check(unsafe {
+            vx_explode(self.ctx, flat.as_ptr(), n as c_int, removed.as_mut_ptr(), &mut nr, bombs.as_mut_ptr(),
+                       &mut nb, dirty.as_mut_ptr(), &mut nd)
+        })?;
+        let triples = |v: &[u32], k: c_int| v.chunks(3).take(k as usize).map(|c| [c[0], c[1], c[2]]).collect();
+        Ok((triples(&removed, nr), triples(&bombs, nb),
+            dirty.chunks(2).take(nd as usize).map(|c| (c[0], c[1])).collect()))
     }
 
     /// One frame of `set_voxel_shader_and_find_visible_areas` + `render_voxels`

@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "vx_hash_world_name", "vx_generate", "vx_upload", "vx_read_areas", "vx_unload",
     "vx_resident_count", "vx_column_heights", "vx_mesh", "vx_mesh_read", "vx_apply_edits",
     "vx_heightmap", "vx_visible", "vx_visible_read", "vx_encode_areas", "vx_encode_read", "vx_decode_areas",
-    "vx_light", "vx_diag_fp64_rate",
+    "vx_explode", "vx_light", "vx_diag_fp64_rate",
 ]
 
 
@@ -153,6 +153,7 @@ def load():
     L.vx_mesh_read.argtypes = [vp, vp, vp, vp, vp, vp]
     L.vx_apply_edits.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int)]
     L.vx_heightmap.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_uint32, vp]
+    L.vx_explode.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int), vp, C.POINTER(C.c_int), vp, C.POINTER(C.c_int)]
     L.vx_encode_areas.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_uint64)]
     L.vx_encode_read.argtypes = [vp, vp, vp]
     L.vx_decode_areas.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
@@ -338,6 +339,19 @@ class Context:
         nd = C.c_int(0)
         self._check(self._lib.vx_apply_edits(self._h, e.ctypes.data, n, dirty.ctypes.data, C.byref(nd)))
         return dirty[: nd.value].copy()
+
+    def explode(self, positions):
+        """BombSimulator::handle_explosions for one tick -> (removed [k,3] u32, bombs [m,3] u32,
+        dirty areas [d,2] u32); positions are Vec3 in player coordinates."""
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        n = pos.shape[0]
+        removed = np.empty((max(1331 * n, 1), 3), np.uint32)
+        bombs = np.empty((max(1331 * n, 1), 3), np.uint32)
+        dirty = np.empty((max(9 * n, 1), 2), np.uint32)
+        nr, nb, nd = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(self._lib.vx_explode(self._h, pos.ctypes.data, n, removed.ctypes.data, C.byref(nr),
+                                         bombs.ctypes.data, C.byref(nb), dirty.ctypes.data, C.byref(nd)))
+        return removed[: nr.value].copy(), bombs[: nb.value].copy(), dirty[: nd.value].copy()
 
     def heightmap(self, area_xy, cam_ax: int, cam_ay: int, rgba=None) -> np.ndarray:
         xy = _xy(area_xy)

@@ -2,6 +2,7 @@
 // kernel sequencing, host<->device copies.  No torch, no CPU compute path: a context cannot be
 // created without a CUDA device, and every voxel / height / vertex is produced by a kernel.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -1082,6 +1083,84 @@ int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_are
         dirty_area_xy[2 * i + 1] = (uint32_t)key;
     }
     *n_dirty = (int)nd;
+    return VX_OK;
+}
+
+int vx_explode(vx_ctx* ctx, const float* positions, int n, uint32_t* removed_xyz, int* n_removed,
+               uint32_t* bomb_xyz, int* n_bombs, uint32_t* dirty_area_xy, int* n_dirty) {
+    if (!ctx || n < 0 || n > 32 || !n_removed || !n_bombs || !n_dirty ||
+        (n > 0 && (!positions || !removed_xyz || !bomb_xyz || !dirty_area_xy)))
+        return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    reset_timers(ctx);
+    *n_removed = *n_bombs = *n_dirty = 0;
+    if (n == 0) return VX_OK;
+    for (int i = 0; i < n; ++i) {  // all-or-nothing: every area a sphere can reach is resident
+        const float px = positions[3 * i], py = positions[3 * i + 1], pz = positions[3 * i + 2];
+        if (!(std::fabs(px) < 1.0e6f && std::fabs(py) < 1.0e6f && std::fabs(pz) < 1.0e6f))
+            return fail(ctx, VX_ERR_INVALID, "vx_explode: position out of range");
+        const int cx = (int)std::floor(px), cy = (int)std::floor(py);
+        for (int dx = -5; dx <= 5; dx += 10)
+            for (int dy = -5; dy <= 5; dy += 10) {
+                const uint32_t gx = (uint32_t)(cx + dx + LOCATION_OFFSET), gy = (uint32_t)(cy + dy + LOCATION_OFFSET);
+                if (host_slot(ctx, gx / AREA_SIZE, gy / AREA_SIZE) < 0)
+                    return fail(ctx, VX_ERR_NOT_LOADED, "vx_explode: an area within reach of an explosion is not resident");
+            }
+    }
+    int st;
+    if ((st = upload_map(ctx)) != VX_OK) return st;
+    const size_t cand = (size_t)n * EXPLOSION_CANDIDATES;
+    uint32_t cap = 1024;
+    while (cap < cand * 2u) cap <<= 1;
+    VX_CUDA(ctx->d_hash_keys.ensure((size_t)cap * 8));
+    VX_CUDA(ctx->d_hash_vals.ensure((size_t)cap * 4));
+    VX_CUDA(ctx->d_dirty_flags.ensure((size_t)ctx->capacity * 4));
+    VX_CUDA(ctx->d_dirty_slots.ensure((size_t)ctx->capacity * 4));
+    VX_CUDA(ctx->d_counters.ensure(64));
+    // scratch: positions | flags | removed | bombs
+    const size_t pos_bytes = ((size_t)n * 12 + 15) & ~(size_t)15, flag_bytes = (cand + 15) & ~(size_t)15;
+    VX_CUDA(ctx->d_edits.ensure(pos_bytes + flag_bytes + 2 * cand * 12));
+    uint8_t* base = ctx->d_edits.as<uint8_t>();
+    float* d_pos = reinterpret_cast<float*>(base);
+    uint8_t* d_flags = base + pos_bytes;
+    uint32_t* d_removed = reinterpret_cast<uint32_t*>(base + pos_bytes + flag_bytes);
+    uint32_t* d_bombs = d_removed + 3 * cand;
+    VX_CUDA(cudaMemsetAsync(ctx->d_hash_keys.p, 0xFF, (size_t)cap * 8, ctx->stream));
+    VX_CUDA(cudaMemsetAsync(ctx->d_hash_vals.p, 0, (size_t)cap * 4, ctx->stream));
+    VX_CUDA(cudaMemsetAsync(ctx->d_dirty_flags.p, 0, (size_t)ctx->capacity * 4, ctx->stream));
+    VX_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
+    VX_CUDA(cudaMemcpyAsync(d_pos, positions, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t* counters = ctx->d_counters.as<uint32_t>();  // [0] dirty, [1] status, [2] removed, [3] bombs
+    {
+        ScopedTimer t(ctx, TM_EDIT);
+        launch_explode(d_pos, n, device_map(ctx), ctx->d_voxels, ctx->d_heights, ctx->d_planes,
+                       ctx->d_hash_keys.as<unsigned long long>(), ctx->d_hash_vals.as<uint32_t>(), cap,
+                       ctx->d_dirty_flags.as<uint32_t>(), ctx->d_dirty_slots.as<uint32_t>(), counters,
+                       reinterpret_cast<int32_t*>(counters + 1), d_flags, d_removed, d_bombs, counters + 2, ctx->stream);
+    }
+    ctx->timings.other_launches += 3;
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(ctx->h_small.ensure(16 + (size_t)ctx->capacity * 4));
+    uint32_t* hs = ctx->h_small.as<uint32_t>();
+    VX_CUDA(cudaMemcpyAsync(hs, counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint32_t nd = hs[0], nr = hs[2], nb = hs[3];
+    if (nd) VX_CUDA(cudaMemcpyAsync(hs + 4, ctx->d_dirty_slots.p, (size_t)nd * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nr) VX_CUDA(cudaMemcpyAsync(removed_xyz, d_removed, (size_t)nr * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nb) VX_CUDA(cudaMemcpyAsync(bomb_xyz, d_bombs, (size_t)nb * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((st = sync_stream(ctx)) != VX_OK) return st;
+    collect_timers(ctx);
+    std::vector<uint32_t> ds(hs + 4, hs + 4 + nd);
+    std::sort(ds.begin(), ds.end());  // deterministic order
+    for (uint32_t i = 0; i < nd; ++i) {
+        const uint64_t key = ctx->slot_key[ds[i]];
+        dirty_area_xy[2 * i] = (uint32_t)(key >> 32);
+        dirty_area_xy[2 * i + 1] = (uint32_t)key;
+    }
+    *n_dirty = (int)nd;
+    *n_removed = (int)nr;
+    *n_bombs = (int)nb;
     return VX_OK;
 }
 

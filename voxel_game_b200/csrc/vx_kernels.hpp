@@ -87,6 +87,13 @@ void launch_apply_edits(const uint4* edits, int n, AreaMap map, uint8_t* pool_vo
                         uint32_t hash_cap, uint32_t* dirty_flags /* per slot */,
                         uint32_t* dirty_slots, uint32_t* dirty_count, int32_t* status,
                         cudaStream_t stream);
+// explosions of one tick (bomb_simulator.rs:191-262); buffers as for launch_apply_edits, plus
+// flags: n * 1331 bytes, removed / bombs: 3 * n * 1331 words each, counts: 2 words
+constexpr uint32_t EXPLOSION_CANDIDATES = 1331;  // (2 * ceil(4.5) + 1)^3 voxels visited per explosion
+void launch_explode(const float* positions, int n, AreaMap map, uint8_t* pool_voxels, uint8_t* pool_heights,
+                    uint16_t* pool_planes, unsigned long long* hash_keys, uint32_t* hash_vals, uint32_t hash_cap,
+                    uint32_t* dirty_flags, uint32_t* dirty_slots, uint32_t* dirty_count, int32_t* status,
+                    uint8_t* flags, uint32_t* removed, uint32_t* bombs, uint32_t* counts, cudaStream_t stream);
 void launch_heightmap(const uint2* area_xy, int n, AreaMap map, const uint8_t* pool_heights,
                       uint32_t cam_ax, uint32_t cam_ay, uint32_t* rgba, cudaStream_t stream);
 
