@@ -122,7 +122,10 @@ def test_work_counters_match_oracle(ctx, seed):
     t = ctx.timings()
     ctx.set_timing(False)
     _, _, stats, _ = oracle.generate_areas(seed, xy)
-    assert t["simplex2_evals"] == stats["simplex2_evals"]
+    # 2-D evaluations: the cave-zone and biome noises skip their second octave where it cannot
+    # change the verdict (at most 2 of the reference's evaluations per column)
+    columns = len(xy) * 256
+    assert stats["simplex2_evals"] - 2 * columns <= t["simplex2_evals"] < stats["simplex2_evals"]
     assert t["cave_voxels"] == stats["cave_voxels"]
     assert t["cave_columns"] == stats["cave_columns"]
     # 3-D evaluations: the kernel skips the alternative-voxel noise where a lake overrides the voxel

@@ -236,6 +236,38 @@ struct __align__(16) GenSmem {
     uint16_t tree[COLUMNS_IN_AREA];  // tree candidates, indexed x * 16 + y
 };
 
+// A two-octave Fbm that the reference only ever compares with integer cuts of
+// `normalise(v) as i32` (cave zone: >= 80; biome: 0, 20, 80).  The second octave is bounded by
+// |simplex| <= SIMPLEX_BOUND, and normalise / the cast are monotone, so it is evaluated only if it
+// can still move the value across a cut.  Returns the number of cuts <= the value.  These noises
+// have wavelengths of hundreds of voxels: the 32 columns of a warp nearly always agree.
+template <int ID, int NCUTS>
+__device__ __forceinline__ int fbm2_region(const NoiseTables& nt, const NoiseShared* s, double x, double y,
+                                           const int (&cuts)[NCUTS], unsigned& evals) {
+    const FbmParams& q = nt.fbm[ID];
+    const unsigned p = (unsigned)q.table * 256u;
+    auto region = [&](double v) {
+        const int b = f64_as_i32(normalise(v));
+        int r = 0;
+#pragma unroll
+        for (int i = 0; i < NCUTS; ++i) r += b >= cuts[i] ? 1 : 0;
+        return r;
+    };
+    x *= q.frequency;
+    y *= q.frequency;
+    double acc = 0.0;
+    acc += q.amp[0] * simplex2(s, p, x, y);
+    ++evals;
+    const double mid = acc * q.norm, rest = SIMPLEX_BOUND * q.amp[1] * q.norm + 1e-9;
+    const int r_lo = region(mid - rest), r_hi = region(mid + rest);
+    if (r_lo == r_hi) return r_lo;
+    x *= q.lacunarity;
+    y *= q.lacunarity;
+    acc += q.amp[1] * simplex2(s, p, x, y);
+    ++evals;
+    return region(acc * q.norm);
+}
+
 __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_constant__ NoiseTables nt,
                                                           const uint4* __restrict__ jobs,
                                                           uint8_t* __restrict__ pool_voxels,
@@ -272,19 +304,22 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
     value = value < 0.1 ? 0.1 : (value > 1.0 ? 1.0 : value);
     const double height_mod = 1.0 - (fbm2<FBM_HEIGHT_MOD>(nt, s, px, py) + 1.0) / 2.0;
     const unsigned H = f64_as_u32(height_mod * value * 0.55 * 128.0) + 32u;
-    // CaveGenerator::is_cave_zone (cave_generator.rs:36-41)
-    const bool cave_zone = f64_as_i32(normalise(fbm2<FBM_CAVE_CHECK>(nt, s, px, py))) >= 80;
+    unsigned evals2 = 12, evals3 = 0;  // simplex evaluations of this column (work accounting)
+    // CaveGenerator::is_cave_zone (cave_generator.rs:36-41): normalise(v) as i32 >= 80
+    const int cave_cuts[1] = {80};
+    const bool cave_zone = fbm2_region<FBM_CAVE_CHECK>(nt, s, px, py, cave_cuts, evals2) == 1;
     // LakeGenerator::sample_lake_depth (lake_generator.rs:27-52)
     unsigned lake_depth = 0;
-    unsigned evals2 = 16, evals3 = 0;  // simplex evaluations of this column (work accounting)
     if (!cave_zone && H <= LAKE_MAX_TERRAIN && H > LAKE_TOP_ZI) {
         evals2 += 2;
         const int d = (f64_as_i32(normalise(fbm2<FBM_LAKE>(nt, s, px, py))) - 70) / 3;
         lake_depth = d < 2 ? 0u : (unsigned)d;
     }
     // BiomeTypeGenerator::sample (biome_type.rs:25-34)
-    const int b = f64_as_i32(normalise(fbm2<FBM_BIOME>(nt, s, px, py)));
-    const int biome = (b >= 0 && b < 20) ? DRY : ((b >= 20 && b < 80) ? WET : COLD);
+    //   0..20 Dry, 20..80 Wet, everything else (below 0 too) Cold
+    const int biome_cuts[3] = {0, 20, 80};
+    const int biome_region = fbm2_region<FBM_BIOME>(nt, s, px, py, biome_cuts, evals2);
+    const int biome = biome_region == 1 ? DRY : (biome_region == 2 ? WET : COLD);
 
     // The four topmost voxels first, in a loop all lanes walk together (k-th voxel from H - 3).
     // A lake column never consults the noise where the lake overrides the voxel
