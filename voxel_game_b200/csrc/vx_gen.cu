@@ -630,18 +630,23 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
                                                          uint8_t* __restrict__ pool_heights,
                                                          uint16_t* __restrict__ pool_planes,
                                                          uint64_t seed) {
+    __shared__ uint4 s_vox[VOXELS_IN_AREA / 16];
     __shared__ uint16_t s_tree[COLUMNS_IN_AREA];  // indexed x*16 + y (generator.rs:54-58 order)
     __shared__ int s_min_z;
     if (finished[blockIdx.x]) return;
     const int tid = threadIdx.x;
     const uint4 job = jobs[blockIdx.x];
     const uint32_t ax = job.x, ay = job.y, slot = job.z;
-    uint8_t* vox = pool_voxels + (size_t)slot * VOXELS_IN_AREA;
+    uint4* area = reinterpret_cast<uint4*>(pool_voxels + (size_t)slot * VOXELS_IN_AREA);
     uint8_t* heights = pool_heights + (size_t)slot * COLUMNS_IN_AREA;
     const unsigned x = tid & 15, y = tid >> 4;
 
+    // the carved area comes into shared memory in one sweep; the column walks below would
+    // otherwise be chains of dependent HBM reads
+    for (int i = tid; i < VOXELS_IN_AREA / 16; i += 256) s_vox[i] = area[i];
     if (tid == 0) s_min_z = AREA_HEIGHT;
     __syncthreads();
+    uint8_t* vox = reinterpret_cast<uint8_t*>(s_vox);
 
     // max_generated_height = topmost generated non-None voxel (generator.rs:91-93,100)
     const unsigned H = heights[tid] & 0x7Fu;
@@ -664,6 +669,9 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
     while (zz < AREA_HEIGHT && is_transparent(vox[tid + 256 * zz])) ++zz;
     heights[tid] = (uint8_t)(zz < AREA_HEIGHT ? zz : AREA_HEIGHT - 1);
     planes_of_area(vox, pool_planes + (size_t)slot * (VOXELS_IN_AREA / 8), tid);
+    // trees only touch the slabs from min_z - 8 down to the surface; write those back
+    const int first_row = max(s_min_z - 8, 0) * 16;
+    for (int i = first_row + tid; i < VOXELS_IN_AREA / 16; i += 256) area[i] = s_vox[i];
 }
 
 // ------------------------------------------------------------------------------------------- L1
