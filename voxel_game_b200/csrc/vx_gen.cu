@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
                                                         const uint8_t* __restrict__ pool_heights,
                                                         const uint2* __restrict__ slot_xy,
                                                         unsigned long long* __restrict__ stats) {
-    __shared__ CaveSmem sm;
+    __shared__ __align__(256) CaveSmem sm;  // tables at the start: 256-byte aligned for simplex3_sa
     const int tid = threadIdx.x, lane = tid & 31;
     const FbmParams& q1 = nt.fbm[FBM_CAVE1];
     const FbmParams& q2 = nt.fbm[FBM_CAVE2];
@@ -505,7 +505,8 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
     if (tid < 18) (&sm.rest[0][0])[tid] = (&nt.cave_rest[0][0])[tid] + 1e-9;
     __syncthreads();
     const uint32_t n_items = *cave_count;
-    const unsigned t1 = (unsigned)q1.table * 256u, t2 = (unsigned)q2.table * 256u;  // table offsets
+    // shared-memory addresses of the two permutation tables
+    const unsigned t1 = smem_address(sm.bytes) + (unsigned)q1.table * 256u, t2 = smem_address(sm.bytes) + (unsigned)q2.table * 256u;
     const double f1 = q1.frequency, f2 = q2.frequency, l1 = q1.lacunarity, l2 = q2.lacunarity;
     const double n1 = q1.norm, n2 = q2.norm;
     CaveWarp& cw = sm.warp[tid >> 5];
@@ -591,12 +592,12 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
             // one octave of each Fbm per round (noise1 has 6, noise2 has 8): no per-lane selection
             // of coordinates, and two independent evaluations in flight
             const unsigned k = step;
-            const double svb = simplex3(sm.bytes, t2, xb, yb, zb);
+            const double svb = simplex3_sa(t2, xb, yb, zb);
             bsum += sm.amp[1][k] * svb;
             xb *= l2; yb *= l2; zb *= l2;
             ++my_evals;
             if (k < 6) {
-                const double sva = simplex3(sm.bytes, t1, xa, ya, za);
+                const double sva = simplex3_sa(t1, xa, ya, za);
                 a += sm.amp[0][k] * sva;
                 xa *= l1; ya *= l1; za *= l1;
                 ++my_evals;

@@ -109,8 +109,48 @@ __device__ __forceinline__ void corner3(double x, double y, double z, unsigned g
     if (t > 0.0) sum += v;
 }
 
+// Table bytes through explicit shared-memory addresses.  With the tables 256-byte aligned,
+// "table address | (index & 255)" is one logic instruction and the % 12 copy sits at a fixed
+// +2048 that folds into the load: two instructions per lookup.
+__device__ __forceinline__ unsigned smem_address(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u8_p12(unsigned addr) {  // same index in the % 12 copy
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1+2048];" : "=r"(v) : "r"(addr));
+    return v;
+}
+static_assert(OFF_P12 == 2048, "lds_u8_p12 hard-codes the offset");
+
+template <class Lookup>
+__device__ __forceinline__ double simplex3_body(double x, double y, double z, Lookup look);
+
 // b = shared-memory base of the table bytes, p = byte offset of the permutation table in it
 __device__ __forceinline__ double simplex3(const uint8_t* b, unsigned p, double x, double y, double z) {
+    struct {
+        const uint8_t* b;
+        unsigned p;
+        __device__ __forceinline__ unsigned perm(unsigned idx) const { return b[p + (idx & 255u)]; }
+        __device__ __forceinline__ unsigned perm12(unsigned idx) const { return b[p + OFF_P12 + (idx & 255u)]; }
+    } look{b, p};
+    return simplex3_body(x, y, z, look);
+}
+
+// sp = shared-memory address of the permutation table, a multiple of 256
+__device__ __forceinline__ double simplex3_sa(unsigned sp, double x, double y, double z) {
+    struct {
+        unsigned sp;
+        __device__ __forceinline__ unsigned perm(unsigned idx) const { return lds_u8(sp | (idx & 255u)); }
+        __device__ __forceinline__ unsigned perm12(unsigned idx) const { return lds_u8_p12(sp | (idx & 255u)); }
+    } look{sp};
+    return simplex3_body(x, y, z, look);
+}
+
+template <class Lookup>
+__device__ __forceinline__ double simplex3_body(double x, double y, double z, Lookup look) {
     const double SKEW = 1.0 / 3.0, UNSKEW = 1.0 / 6.0;
     const double sk = (x + y + z) * SKEW;
     int i, j, k;
@@ -130,12 +170,11 @@ __device__ __forceinline__ double simplex3(const uint8_t* b, unsigned p, double 
                  z2 = z0 - (k2 ? 1.0 : 0.0) + 2.0 * UNSKEW;
     const double x3 = x0 - 1.0 + 3.0 * UNSKEW, y3 = y0 - 1.0 + 3.0 * UNSKEW,
                  z3 = z0 - 1.0 + 3.0 * UNSKEW;
-    const unsigned g = p + OFF_P12;
-    const unsigned pi0 = b[p + (i & 255)], pi1 = b[p + ((i + 1) & 255)];
-    const unsigned h0 = b[g + ((b[p + ((pi0 + j) & 255)] + k) & 255)];
-    const unsigned h1 = b[g + ((b[p + (((i1 ? pi1 : pi0) + j + (int)j1) & 255)] + k + (int)k1) & 255)];
-    const unsigned h2 = b[g + ((b[p + (((i2 ? pi1 : pi0) + j + (int)j2) & 255)] + k + (int)k2) & 255)];
-    const unsigned h3 = b[g + ((b[p + ((pi1 + j + 1) & 255)] + k + 1) & 255)];
+    const unsigned pi0 = look.perm((unsigned)i), pi1 = look.perm((unsigned)(i + 1));
+    const unsigned h0 = look.perm12(look.perm(pi0 + j) + k);
+    const unsigned h1 = look.perm12(look.perm((i1 ? pi1 : pi0) + j + (int)j1) + k + (int)k1);
+    const unsigned h2 = look.perm12(look.perm((i2 ? pi1 : pi0) + j + (int)j2) + k + (int)k2);
+    const unsigned h3 = look.perm12(look.perm(pi1 + j + 1) + k + 1);
     double sum = 0.0;
     corner3(x0, y0, z0, h0, sum);
     corner3(x1, y1, z1, h1, sum);
