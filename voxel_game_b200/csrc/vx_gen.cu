@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
                                                           unsigned long long* __restrict__ stats,
                                                           uint16_t* __restrict__ pool_planes,
                                                           uint8_t* __restrict__ finished) {
-    __shared__ GenSmem sm;
+    __shared__ __align__(256) GenSmem sm;  // vox is 32 KiB, so the noise tables behind it are 256-byte aligned
     const int tid = threadIdx.x;
     const uint4 job = jobs[blockIdx.x];
     const uint32_t ax = job.x, ay = job.y, slot = job.z;
@@ -338,10 +338,10 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
             // |simplex| <= SIMPLEX_BOUND, so it is evaluated only when it can still change the
             // verdict; normalise() is monotone, so testing it at the bounds is exact.
             const FbmParams& q = nt.fbm[FBM_ALT];
-            const unsigned tab = (unsigned)q.table * 256u;
+            const unsigned tab = smem_address(s->bytes) + (unsigned)q.table * 256u;
             double x3 = px * q.frequency, y3 = py * q.frequency, z3 = (double)zi * q.frequency;
             double acc = 0.0;
-            acc += q.amp[0] * simplex3(s->bytes, tab, x3, y3, z3);
+            acc += q.amp[0] * simplex3_sa(tab, x3, y3, z3);
             evals3 += 1;
             const double mid = acc * q.norm, rest = SIMPLEX_BOUND * q.amp[1] * q.norm + 1e-9;
             if (normalise(mid - rest) - 1e-9 >= threshold) {
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
                 alt = false;
             } else {
                 x3 *= q.lacunarity; y3 *= q.lacunarity; z3 *= q.lacunarity;
-                acc += q.amp[1] * simplex3(s->bytes, tab, x3, y3, z3);
+                acc += q.amp[1] * simplex3_sa(tab, x3, y3, z3);
                 evals3 += 1;
                 alt = normalise(acc * q.norm) >= threshold;
             }
