@@ -245,7 +245,6 @@ template <int ID, int NCUTS>
 __device__ __forceinline__ int fbm2_region(const NoiseTables& nt, const NoiseShared* s, double x, double y,
                                            const int (&cuts)[NCUTS], unsigned& evals) {
     const FbmParams& q = nt.fbm[ID];
-    const unsigned p = (unsigned)q.table * 256u;
     auto region = [&](double v) {
         const int b = f64_as_i32(normalise(v));
         int r = 0;
@@ -256,14 +255,14 @@ __device__ __forceinline__ int fbm2_region(const NoiseTables& nt, const NoiseSha
     x *= q.frequency;
     y *= q.frequency;
     double acc = 0.0;
-    acc += q.amp[0] * simplex2(s, p, x, y);
+    acc += q.amp[0] * simplex2<FBM_TABLE<ID>>(s, x, y);
     ++evals;
     const double mid = acc * q.norm, rest = SIMPLEX_BOUND * q.amp[1] * q.norm + 1e-9;
     const int r_lo = region(mid - rest), r_hi = region(mid + rest);
     if (r_lo == r_hi) return r_lo;
     x *= q.lacunarity;
     y *= q.lacunarity;
-    acc += q.amp[1] * simplex2(s, p, x, y);
+    acc += q.amp[1] * simplex2<FBM_TABLE<ID>>(s, x, y);
     ++evals;
     return region(acc * q.norm);
 }
@@ -278,7 +277,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
                                                           unsigned long long* __restrict__ stats,
                                                           uint16_t* __restrict__ pool_planes,
                                                           uint8_t* __restrict__ finished) {
-    __shared__ __align__(256) GenSmem sm;  // vox is 32 KiB, so the noise tables behind it are 256-byte aligned
+    __shared__ GenSmem sm;
     const int tid = threadIdx.x;
     const uint4 job = jobs[blockIdx.x];
     const uint32_t ax = job.x, ay = job.y, slot = job.z;
@@ -338,10 +337,9 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
             // |simplex| <= SIMPLEX_BOUND, so it is evaluated only when it can still change the
             // verdict; normalise() is monotone, so testing it at the bounds is exact.
             const FbmParams& q = nt.fbm[FBM_ALT];
-            const unsigned tab = smem_address(s->bytes) + (unsigned)q.table * 256u;
             double x3 = px * q.frequency, y3 = py * q.frequency, z3 = (double)zi * q.frequency;
             double acc = 0.0;
-            acc += q.amp[0] * simplex3_sa(tab, x3, y3, z3);
+            acc += q.amp[0] * simplex3<FBM_TABLE<FBM_ALT>>(s->bytes, x3, y3, z3);
             evals3 += 1;
             const double mid = acc * q.norm, rest = SIMPLEX_BOUND * q.amp[1] * q.norm + 1e-9;
             if (normalise(mid - rest) - 1e-9 >= threshold) {
@@ -350,7 +348,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
                 alt = false;
             } else {
                 x3 *= q.lacunarity; y3 *= q.lacunarity; z3 *= q.lacunarity;
-                acc += q.amp[1] * simplex3_sa(tab, x3, y3, z3);
+                acc += q.amp[1] * simplex3<FBM_TABLE<FBM_ALT>>(s->bytes, x3, y3, z3);
                 evals3 += 1;
                 alt = normalise(acc * q.norm) >= threshold;
             }
@@ -486,14 +484,17 @@ struct CaveSmem {
 //     one at once (ballot + popc, no atomics, no CTA barrier) instead of idling until the slowest
 //     lane is done.  Lanes of a warp sit at different octaves of different voxels, which costs
 //     nothing because the octave index only selects table rows.
-__global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ NoiseTables nt,
+#ifndef VX_CAVE_CTAS_PER_SM
+#define VX_CAVE_CTAS_PER_SM 3
+#endif
+__global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(const __grid_constant__ NoiseTables nt,
                                                         const uint32_t* __restrict__ cave_items,
                                                         const uint32_t* __restrict__ cave_count,
                                                         uint8_t* __restrict__ pool_voxels,
                                                         const uint8_t* __restrict__ pool_heights,
                                                         const uint2* __restrict__ slot_xy,
                                                         unsigned long long* __restrict__ stats) {
-    __shared__ __align__(256) CaveSmem sm;  // tables at the start: 256-byte aligned for simplex3_sa
+    __shared__ CaveSmem sm;
     const int tid = threadIdx.x, lane = tid & 31;
     const FbmParams& q1 = nt.fbm[FBM_CAVE1];
     const FbmParams& q2 = nt.fbm[FBM_CAVE2];
@@ -505,8 +506,6 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
     if (tid < 18) (&sm.rest[0][0])[tid] = (&nt.cave_rest[0][0])[tid] + 1e-9;
     __syncthreads();
     const uint32_t n_items = *cave_count;
-    // shared-memory addresses of the two permutation tables
-    const unsigned t1 = smem_address(sm.bytes) + (unsigned)q1.table * 256u, t2 = smem_address(sm.bytes) + (unsigned)q2.table * 256u;
     const double f1 = q1.frequency, f2 = q2.frequency, l1 = q1.lacunarity, l2 = q2.lacunarity;
     const double n1 = q1.norm, n2 = q2.norm;
     CaveWarp& cw = sm.warp[tid >> 5];
@@ -592,12 +591,12 @@ __global__ void __launch_bounds__(256) gen_caves_kernel(const __grid_constant__ 
             // one octave of each Fbm per round (noise1 has 6, noise2 has 8): no per-lane selection
             // of coordinates, and two independent evaluations in flight
             const unsigned k = step;
-            const double svb = simplex3_sa(t2, xb, yb, zb);
+            const double svb = simplex3<FBM_TABLE<FBM_CAVE2>>(sm.bytes, xb, yb, zb);
             bsum += sm.amp[1][k] * svb;
             xb *= l2; yb *= l2; zb *= l2;
             ++my_evals;
             if (k < 6) {
-                const double sva = simplex3_sa(t1, xa, ya, za);
+                const double sva = simplex3<FBM_TABLE<FBM_CAVE1>>(sm.bytes, xa, ya, za);
                 a += sm.amp[0][k] * sva;
                 xa *= l1; ya *= l1; za *= l1;
                 ++my_evals;
@@ -723,7 +722,7 @@ void launch_gen_columns(const NoiseTables& nt, const uint4* jobs, int n, uint8_t
 void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const uint32_t* cave_count, uint8_t* pool_voxels,
                       const uint8_t* pool_heights, const uint2* slot_xy, unsigned long long* stats,
                       int sm_count, cudaStream_t stream) {
-    gen_caves_kernel<<<sm_count * 4, 256, 0, stream>>>(nt, cave_items, cave_count, pool_voxels,
+    gen_caves_kernel<<<sm_count * VX_CAVE_CTAS_PER_SM, 256, 0, stream>>>(nt, cave_items, cave_count, pool_voxels,
                                                        pool_heights, slot_xy, stats);
 }
 

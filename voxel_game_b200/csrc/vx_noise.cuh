@@ -7,15 +7,21 @@
 // evaluation.  What is *re-organised* for the GPU, all value-preserving:
 //   * floor + integer cast are two FP64 adds (round-down add of 2^52 + 2^51, then subtract)
 //     instead of FRND/F2I on the conversion pipe;
-//   * the permutation table is kept un-doubled (256 B, at most 2-way bank conflicts) and indexed
-//     modulo 256, which equals indexing the crate's doubled 512-entry table;
+//   * the permutation table is doubled (512 B) like the crate's, and the integer lattice
+//     coordinates are reduced modulo 256 once per evaluation, so no lookup needs a mask;
 //   * the 3-D gradient dot product g.x (components 0/+-1) is one signed add instead of
 //     3 multiplies + 2 adds (x*1 = x, x*0 = +-0, y + +-0 = y);
 //   * Fbm amplitudes amp_k are precomputed on the host with the same running product;
 //   * the last permutation lookup only feeds "% 12" / "% 24", so it reads pre-reduced copies of
-//     the table; a corner with t <= 0 contributes 0, i.e. leaves the running sum unchanged.
-// Tables are addressed as (shared-memory base, byte offset) and never through a selected pointer,
-// so every lookup stays an LDS even when the table is chosen per lane.
+//     the table;
+//   * a corner with t <= 0 contributes 0 in the crate, i.e. leaves the running sum unchanged.  Here
+//     the high word of t is clamped with one signed integer max (a negative or -0 t becomes a
+//     number below 2^-1022 whose square is exactly +0), so t^4 * d = +-0 is added unconditionally:
+//     no FP64 compare and no selects (sum is never -0: it starts at +0.0, and x + (-x) = +0);
+//   * "c - (step ? 1.0 : 0.0)" is a select between c - 1.0 and c (c - 0.0 == c bit for bit), and
+//     c - 1.0 is shared with the last corner.
+// Tables are addressed as uniform shared-memory pointer + per-lane index, never through a
+// selected pointer, so every lookup is one LDS with the table base in a uniform register.
 #pragma once
 #include <cstdint>
 
@@ -28,10 +34,24 @@ namespace vx {
 // each other, which a module-wide __constant__ symbol would allow.  Lookups are random per lane,
 // so the tables are read from a shared-memory copy (the constant cache would serialise them); the
 // copy is 216 coalesced 16-byte loads per CTA.
-constexpr unsigned TAB_BYTES = TAB_COUNT * 256;
+constexpr unsigned TAB_BYTES = TAB_COUNT * TAB_STRIDE;
 constexpr unsigned OFF_P24 = TAB_BYTES;      // byte offset of the % 24 copies
 constexpr unsigned OFF_P12 = 2 * TAB_BYTES;  // byte offset of the % 12 copies
 using NoiseShared = NoiseImage;
+
+// Numeric constants whose low word is not zero cannot be FP64 immediates; as literals ptxas
+// re-materialises each of them with two moves per use.  From the constant bank they are plain
+// instruction operands.
+__constant__ double c_noise_k[8] = {
+    0.366025403784439,        // 0: 2-D skew
+    0.211324865405187,        // 1: 2-D unskew
+    2.0 * 0.211324865405187,  // 2
+    99.83685446303647,        // 3: 2-D normalisation
+    1.0 / 3.0,                // 4: 3-D skew
+    1.0 / 6.0,                // 5: 3-D unskew
+    2.0 * (1.0 / 6.0),        // 6
+    76.88375854620836,        // 7: 3-D normalisation
+};
 
 // first `bytes` bytes of the image (a multiple of 16): the cave kernel only needs the tables
 __device__ __forceinline__ void load_noise_image(void* dst, const NoiseTables& nt, unsigned bytes, int tid,
@@ -55,41 +75,49 @@ __device__ __forceinline__ double floor_split(double x, int& i) {
     return t - MAGIC;
 }
 
+// t for t > 0; for t <= 0 (sign bit set, or +0) a value whose square is exactly +0.0: the high
+// word becomes 0, which leaves either +0 or a subnormal below 2^-1022.
+__device__ __forceinline__ double clamp_radius(double t) {
+    return __hiloint2double(max(__double2hiint(t), 0), __double2loint(t));
+}
+
 // contribution of one simplex corner, added to `sum`; gi = gradient index.  A corner outside its
-// radius (t <= 0) contributes 0 in the crate, i.e. leaves the running sum unchanged (sum starts at
-// +0.0 and 0.0 + v == v).
-__device__ __forceinline__ void corner2(const NoiseShared* s, double x, double y, unsigned gi,
-                                        double& sum) {
-    const double t = 0.5 - x * x - y * y;
+// radius (t <= 0) contributes 0 in the crate, i.e. leaves the running sum unchanged: here it adds
+// (+0 * +0) * d = +-0 (d is finite), and sum + +-0 == sum because sum is never -0.
+__device__ __forceinline__ void corner2(const NoiseShared* s, double x, double y, unsigned gi, double& sum) {
+    const double t = clamp_radius(0.5 - x * x - y * y);
     const double2 g = *reinterpret_cast<const double2*>(&s->grad2[gi][0]);
     const double d = g.x * x + g.y * y;
     const double t2 = t * t;
-    const double v = t2 * t2 * d;
-    if (t > 0.0) sum += v;
+    sum += t2 * t2 * d;
 }
 
-// p = byte offset of the permutation table inside s->bytes
-__device__ __forceinline__ double simplex2(const NoiseShared* s, unsigned p, double x, double y) {
-    const double SKEW = 0.366025403784439, UNSKEW = 0.211324865405187;
-    const uint8_t* b = s->bytes;
+// TABLE = which (doubled) permutation table of s->bytes; its % 24 copy sits OFF_P24 bytes further.
+// The table is a template argument so that its base is part of each load's constant offset.
+template <int TABLE>
+__device__ __forceinline__ double simplex2(const NoiseShared* s, double x, double y) {
+    const uint8_t* tb = s->bytes + TABLE * TAB_STRIDE;
+    const double SKEW = c_noise_k[0], UNSKEW = c_noise_k[1], UNSKEW_2 = c_noise_k[2];
     const double sk = (x + y) * SKEW;
     int i, j;
     const double fx = floor_split(x + sk, i), fy = floor_split(y + sk, j);
     const double un = (fx + fy) * UNSKEW;
     const double x0 = x - fx + un, y0 = y - fy + un;
     const bool lower = !(x0 < y0);  // middle corner (1,0) unless x0 < y0
-    const double x1 = x0 - (lower ? 1.0 : 0.0) + UNSKEW, y1 = y0 - (lower ? 0.0 : 1.0) + UNSKEW;
-    const double x2 = x0 - 1.0 + 2.0 * UNSKEW, y2 = y0 - 1.0 + 2.0 * UNSKEW;
-    const unsigned pi0 = b[p + (i & 255)], pi1 = b[p + ((i + 1) & 255)];
-    const unsigned g = p + OFF_P24;
-    const unsigned h0 = b[g + ((pi0 + j) & 255)];
-    const unsigned h1 = b[g + (((lower ? pi1 : pi0) + j + (lower ? 0 : 1)) & 255)];
-    const unsigned h2 = b[g + ((pi1 + j + 1) & 255)];
+    const double xm = x0 - 1.0, ym = y0 - 1.0;
+    const double x1 = (lower ? xm : x0) + UNSKEW, y1 = (lower ? y0 : ym) + UNSKEW;
+    const double x2 = xm + UNSKEW_2, y2 = ym + UNSKEW_2;
+    const unsigned im = (unsigned)i & 255u, jm = (unsigned)j & 255u;
+    const unsigned pi0 = tb[im], pi1 = tb[im + 1];
+    const uint8_t* tg = tb + OFF_P24;
+    const unsigned h0 = tg[pi0 + jm];
+    const unsigned h1 = lower ? tg[pi1 + jm] : tg[pi0 + jm + 1];
+    const unsigned h2 = tg[pi1 + jm + 1];
     double sum = 0.0;
     corner2(s, x0, y0, h0, sum);
     corner2(s, x1, y1, h1, sum);
     corner2(s, x2, y2, h2, sum);
-    return sum * 99.83685446303647;
+    return sum * c_noise_k[3];
 }
 
 // gradient gi (0..11) of the edge-midpoint set
@@ -99,59 +127,24 @@ __device__ __forceinline__ double flip_sign(double v, unsigned sign_bit31) {
     return __hiloint2double(__double2hiint(v) ^ (int)sign_bit31, __double2loint(v));
 }
 __device__ __forceinline__ void corner3(double x, double y, double z, unsigned gi, double& sum) {
-    const double t = 0.5 - x * x - y * y - z * z;
+    const double t = clamp_radius(0.5 - x * x - y * y - z * z);
     const unsigned grp = gi >> 2;
     const double a = flip_sign(grp == 2u ? y : x, gi << 31);
     const double b = flip_sign(grp == 0u ? y : z, (gi << 30) & 0x80000000u);
     const double d = a + b;
     const double t2 = t * t;
-    const double v = t2 * t2 * d;
-    if (t > 0.0) sum += v;
+    sum += t2 * t2 * d;
 }
 
-// Table bytes through explicit shared-memory addresses.  With the tables 256-byte aligned,
-// "table address | (index & 255)" is one logic instruction and the % 12 copy sits at a fixed
-// +2048 that folds into the load: two instructions per lookup.
-__device__ __forceinline__ unsigned smem_address(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
-    unsigned v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ unsigned lds_u8_p12(unsigned addr) {  // same index in the % 12 copy
-    unsigned v;
-    asm volatile("ld.shared.u8 %0, [%1+2048];" : "=r"(v) : "r"(addr));
-    return v;
-}
-static_assert(OFF_P12 == 2048, "lds_u8_p12 hard-codes the offset");
-
-template <class Lookup>
-__device__ __forceinline__ double simplex3_body(double x, double y, double z, Lookup look);
-
-// b = shared-memory base of the table bytes, p = byte offset of the permutation table in it
-__device__ __forceinline__ double simplex3(const uint8_t* b, unsigned p, double x, double y, double z) {
-    struct {
-        const uint8_t* b;
-        unsigned p;
-        __device__ __forceinline__ unsigned perm(unsigned idx) const { return b[p + (idx & 255u)]; }
-        __device__ __forceinline__ unsigned perm12(unsigned idx) const { return b[p + OFF_P12 + (idx & 255u)]; }
-    } look{b, p};
-    return simplex3_body(x, y, z, look);
-}
-
-// sp = shared-memory address of the permutation table, a multiple of 256
-__device__ __forceinline__ double simplex3_sa(unsigned sp, double x, double y, double z) {
-    struct {
-        unsigned sp;
-        __device__ __forceinline__ unsigned perm(unsigned idx) const { return lds_u8(sp | (idx & 255u)); }
-        __device__ __forceinline__ unsigned perm12(unsigned idx) const { return lds_u8_p12(sp | (idx & 255u)); }
-    } look{sp};
-    return simplex3_body(x, y, z, look);
-}
-
-template <class Lookup>
-__device__ __forceinline__ double simplex3_body(double x, double y, double z, Lookup look) {
-    const double SKEW = 1.0 / 3.0, UNSKEW = 1.0 / 6.0;
+// bytes = the table image in shared memory, TABLE = which (doubled) permutation table of it; the
+// % 12 copy sits OFF_P12 bytes further.
+// Indices are sums of table bytes and coordinates reduced to 8 bits (at most 255 + 255 + 1), which
+// the doubled table serves without masking -- the crate's own arrangement; constant offsets fold
+// into the loads.
+template <int TABLE>
+__device__ __forceinline__ double simplex3(const uint8_t* bytes, double x, double y, double z) {
+    const uint8_t* tb = bytes + TABLE * TAB_STRIDE;
+    const double SKEW = c_noise_k[4], UNSKEW = c_noise_k[5], UNSKEW_2 = c_noise_k[6];
     const double sk = (x + y + z) * SKEW;
     int i, j, k;
     const double fx = floor_split(x + sk, i), fy = floor_split(y + sk, j),
@@ -163,36 +156,35 @@ __device__ __forceinline__ double simplex3_body(double x, double y, double z, Lo
     const bool xy = x0 >= y0, yz = y0 >= z0, xz = x0 >= z0;
     const bool i1 = xy && xz, j1 = !xy && yz, k1 = !xz && !yz;
     const bool i2 = xy || xz, j2 = !xy || yz, k2 = !(xz && yz);
-    // selects, not int->double conversions (those run on the slow conversion pipe)
-    const double x1 = x0 - (i1 ? 1.0 : 0.0) + UNSKEW, y1 = y0 - (j1 ? 1.0 : 0.0) + UNSKEW,
-                 z1 = z0 - (k1 ? 1.0 : 0.0) + UNSKEW;
-    const double x2 = x0 - (i2 ? 1.0 : 0.0) + 2.0 * UNSKEW, y2 = y0 - (j2 ? 1.0 : 0.0) + 2.0 * UNSKEW,
-                 z2 = z0 - (k2 ? 1.0 : 0.0) + 2.0 * UNSKEW;
-    const double x3 = x0 - 1.0 + 3.0 * UNSKEW, y3 = y0 - 1.0 + 3.0 * UNSKEW,
-                 z3 = z0 - 1.0 + 3.0 * UNSKEW;
-    const unsigned pi0 = look.perm((unsigned)i), pi1 = look.perm((unsigned)(i + 1));
-    const unsigned h0 = look.perm12(look.perm(pi0 + j) + k);
-    const unsigned h1 = look.perm12(look.perm((i1 ? pi1 : pi0) + j + (int)j1) + k + (int)k1);
-    const unsigned h2 = look.perm12(look.perm((i2 ? pi1 : pi0) + j + (int)j2) + k + (int)k2);
-    const unsigned h3 = look.perm12(look.perm(pi1 + j + 1) + k + 1);
+    // "c - step" as a select between c - 1.0 and c (c - 0.0 == c); c - 1.0 also serves corner 3
+    const double xm = x0 - 1.0, ym = y0 - 1.0, zm = z0 - 1.0;
+    const double x1 = (i1 ? xm : x0) + UNSKEW, y1 = (j1 ? ym : y0) + UNSKEW, z1 = (k1 ? zm : z0) + UNSKEW;
+    const double x2 = (i2 ? xm : x0) + UNSKEW_2, y2 = (j2 ? ym : y0) + UNSKEW_2, z2 = (k2 ? zm : z0) + UNSKEW_2;
+    const double x3 = xm + 0.5, y3 = ym + 0.5, z3 = zm + 0.5;  // 3.0 * UNSKEW == 0.5 exactly
+    const unsigned im = (unsigned)i & 255u, jm = (unsigned)j & 255u, km = (unsigned)k & 255u;
+    const unsigned pi0 = tb[im], pi1 = tb[im + 1];
+    const uint8_t* tg = tb + OFF_P12;
+    const unsigned h0 = tg[tb[pi0 + jm] + km];
+    const unsigned h1 = tg[tb[(i1 ? pi1 : pi0) + jm + (j1 ? 1u : 0u)] + km + (k1 ? 1u : 0u)];
+    const unsigned h2 = tg[tb[(i2 ? pi1 : pi0) + jm + (j2 ? 1u : 0u)] + km + (k2 ? 1u : 0u)];
+    const unsigned h3 = tg[tb[pi1 + jm + 1] + km + 1];
     double sum = 0.0;
     corner3(x0, y0, z0, h0, sum);
     corner3(x1, y1, z1, h1, sum);
     corner3(x2, y2, z2, h2, sum);
     corner3(x3, y3, z3, h3, sum);
-    return sum * 76.88375854620836;
+    return sum * c_noise_k[7];
 }
 
 template <int ID>
 __device__ __forceinline__ double fbm2(const NoiseTables& nt, const NoiseShared* s, double x, double y) {
     const FbmParams& q = nt.fbm[ID];
-    const unsigned p = (unsigned)q.table * 256u;
     x *= q.frequency;
     y *= q.frequency;
     double acc = 0.0;
 #pragma unroll 1
     for (int o = 0; o < q.octaves; ++o) {
-        acc += q.amp[o] * simplex2(s, p, x, y);
+        acc += q.amp[o] * simplex2<FBM_TABLE<ID>>(s, x, y);
         x *= q.lacunarity;
         y *= q.lacunarity;
     }
@@ -203,14 +195,13 @@ template <int ID>
 __device__ __forceinline__ double fbm3(const NoiseTables& nt, const NoiseShared* s, double x, double y,
                                        double z) {
     const FbmParams& q = nt.fbm[ID];
-    const unsigned p = (unsigned)q.table * 256u;
     x *= q.frequency;
     y *= q.frequency;
     z *= q.frequency;
     double acc = 0.0;
 #pragma unroll 1
     for (int o = 0; o < q.octaves; ++o) {
-        acc += q.amp[o] * simplex3(s->bytes, p, x, y, z);
+        acc += q.amp[o] * simplex3<FBM_TABLE<ID>>(s->bytes, x, y, z);
         x *= q.lacunarity;
         y *= q.lacunarity;
         z *= q.lacunarity;

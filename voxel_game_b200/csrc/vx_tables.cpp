@@ -121,15 +121,15 @@ void build_noise_tables(uint64_t seed, NoiseTables* out) {
     shuffled_identity(~seed, out->perm[TAB_NOT_SEED]);  // seed ^ u64::MAX
     shuffled_identity(seed + 1, out->perm[TAB_SEED_PLUS_1]);
     shuffled_identity(seed + 10, out->perm[TAB_SEED_PLUS_10]);
-    out->fbm[FBM_HEIGHT1] = make_fbm(TAB_SEED, 6, 0.008, 1.8, 0.45);
-    out->fbm[FBM_HEIGHT2] = make_fbm(TAB_NOT_SEED, 4, 0.004, 1.8, 0.45);
-    out->fbm[FBM_HEIGHT_MOD] = make_fbm(TAB_SEED_PLUS_1, 2, 0.004, 0.004, 0.2);
-    out->fbm[FBM_BIOME] = make_fbm(TAB_SEED, 2, 0.0015, 1.5, 0.3);
-    out->fbm[FBM_CAVE1] = make_fbm(TAB_SEED, 6, 0.08, 1.3, 0.45);
-    out->fbm[FBM_CAVE2] = make_fbm(TAB_NOT_SEED, 8, 0.04, 1.2, 0.35);
-    out->fbm[FBM_CAVE_CHECK] = make_fbm(TAB_SEED, 2, 0.003, 1.3, 0.3);
-    out->fbm[FBM_ALT] = make_fbm(TAB_SEED_PLUS_1, 2, 0.07, 2.0, 0.3);
-    out->fbm[FBM_LAKE] = make_fbm(TAB_SEED_PLUS_10, 2, 0.004, 1.3, 0.35);
+    out->fbm[FBM_HEIGHT1] = make_fbm(FBM_TABLE<FBM_HEIGHT1>, 6, 0.008, 1.8, 0.45);
+    out->fbm[FBM_HEIGHT2] = make_fbm(FBM_TABLE<FBM_HEIGHT2>, 4, 0.004, 1.8, 0.45);
+    out->fbm[FBM_HEIGHT_MOD] = make_fbm(FBM_TABLE<FBM_HEIGHT_MOD>, 2, 0.004, 0.004, 0.2);
+    out->fbm[FBM_BIOME] = make_fbm(FBM_TABLE<FBM_BIOME>, 2, 0.0015, 1.5, 0.3);
+    out->fbm[FBM_CAVE1] = make_fbm(FBM_TABLE<FBM_CAVE1>, 6, 0.08, 1.3, 0.45);
+    out->fbm[FBM_CAVE2] = make_fbm(FBM_TABLE<FBM_CAVE2>, 8, 0.04, 1.2, 0.35);
+    out->fbm[FBM_CAVE_CHECK] = make_fbm(FBM_TABLE<FBM_CAVE_CHECK>, 2, 0.003, 1.3, 0.3);
+    out->fbm[FBM_ALT] = make_fbm(FBM_TABLE<FBM_ALT>, 2, 0.07, 2.0, 0.3);
+    out->fbm[FBM_LAKE] = make_fbm(FBM_TABLE<FBM_LAKE>, 2, 0.004, 1.3, 0.35);
     const int cave_ids[2] = {FBM_CAVE1, FBM_CAVE2};
     for (int f = 0; f < 2; ++f) {
         const FbmParams& q = out->fbm[cave_ids[f]];
@@ -157,9 +157,9 @@ static const double GRAD2[24][2] = {
     {-0.38268343236509, 0.923879532511287},   {-0.130526192220052, 0.99144486137381}};
 
 void build_noise_image(const NoiseTables& tables, NoiseImage* out) {
-    const unsigned n = TAB_COUNT * 256;
+    const unsigned n = TAB_COUNT * TAB_STRIDE;
     for (unsigned i = 0; i < n; ++i) {
-        const unsigned v = (&tables.perm[0][0])[i];
+        const unsigned v = tables.perm[i / TAB_STRIDE][i & 255u];
         out->bytes[i] = (uint8_t)v;
         out->bytes[n + i] = (uint8_t)(v % 24u);
         out->bytes[2 * n + i] = (uint8_t)(v % 12u);

@@ -35,6 +35,15 @@ enum FbmId {
 
 enum TableId { TAB_SEED = 0, TAB_NOT_SEED, TAB_SEED_PLUS_1, TAB_SEED_PLUS_10, TAB_COUNT };
 
+// Which permutation table an Fbm reads (the seed its Simplex::new got).  Fixed by the reference's
+// constructors, so the kernels use it as a compile-time constant: the table base folds into the
+// address of every lookup.
+template <int ID>
+constexpr int FBM_TABLE = ID == FBM_HEIGHT1 || ID == FBM_BIOME || ID == FBM_CAVE1 || ID == FBM_CAVE_CHECK ? TAB_SEED
+                          : ID == FBM_HEIGHT2 || ID == FBM_CAVE2                                         ? TAB_NOT_SEED
+                          : ID == FBM_HEIGHT_MOD || ID == FBM_ALT                                        ? TAB_SEED_PLUS_1
+                                                                                                          : TAB_SEED_PLUS_10;
+
 struct NoiseTables {
     uint64_t seed;
     uint8_t perm[TAB_COUNT][256];  // un-doubled; kernels index with (a + b) & 255
@@ -45,11 +54,13 @@ struct NoiseTables {
     const void* image;  // device copy of the NoiseImage of this seed (set by the owner of the tables)
 };
 
-// What the kernels keep in shared memory, byte for byte: the four permutation tables, their
-// "% 24" and "% 12" copies (the last lookup of a 2-D / 3-D corner only feeds that remainder), and
-// the 24 2-D gradients.  bytes = perm (4 x 256) | perm % 24 (4 x 256) | perm % 12 (4 x 256).
+// What the kernels keep in shared memory, byte for byte: the four permutation tables, doubled to
+// 512 entries (entry i = perm[i & 255], the crate's arrangement), their "% 24" and "% 12" copies
+// (the last lookup of a 2-D / 3-D corner only feeds that remainder), and the 24 2-D gradients.
+// bytes = perm (4 x 512) | perm % 24 (4 x 512) | perm % 12 (4 x 512).
+constexpr unsigned TAB_STRIDE = 512;
 struct alignas(16) NoiseImage {
-    uint8_t bytes[3 * TAB_COUNT * 256];
+    uint8_t bytes[3 * TAB_COUNT * TAB_STRIDE];
     double grad2[24][2];
 };
 
