@@ -35,8 +35,8 @@ REF_SAMPLE = 32        # --impl reference: 32x32 areas per step
 WORLD_NAME = "test"    # the reference's own test seed (generator.rs:157)
 
 # algorithmic work per unit (DESIGN.md "Roofline accounting")
-F2_OPS = 60            # f64 add/mul issued per 2-D simplex octave incl. the Fbm accumulate
-F3_OPS = 89            # f64 add/mul issued per 3-D simplex octave incl. the Fbm accumulate
+F2_OPS = 58            # f64 add/mul issued per 2-D simplex octave incl. the Fbm accumulate
+F3_OPS = 83            # f64 add/mul issued per 3-D simplex octave incl. the Fbm accumulate
 AREA_BYTES = 32768 + 256
 
 
@@ -237,6 +237,7 @@ def main():
     info = None
     for _ in range(args.warmup):
         info = step()
+    ctx.timings()  # clears the accumulators: the kernel times below cover the timed steps only
     kern = {}
     work = {}
     launches = 0
@@ -247,17 +248,13 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        ctx.generate(gen_xy, read=False)
-        t = ctx.timings()
-        for k in ("gen_columns_ms", "gen_caves_ms", "gen_finish_ms"):
-            kern[k] = kern.get(k, 0.0) + t[k]
-        launches += t["gen_launches"]
-        work = {k: t[k] for k in ("simplex2_evals", "simplex3_evals", "cave_voxels", "cave_columns", "cave_evals")}
+        ctx.generate(gen_xy, read=False)  # enqueued; vx_mesh is ordered behind it and waits for the totals
         info = ctx.mesh(mesh_xy)
-        t = ctx.timings()
-        for k in ("mesh_count_ms", "mesh_emit_ms"):
+        t = ctx.timings()                 # kernel times and work counters since the previous read
+        for k in ("gen_columns_ms", "gen_caves_ms", "gen_finish_ms", "mesh_count_ms", "mesh_emit_ms"):
             kern[k] = kern.get(k, 0.0) + t[k]
         launches += t["mesh_launches"] + t["gen_launches"]
+        work = {k: t[k] for k in ("simplex2_evals", "simplex3_evals", "cave_voxels", "cave_columns", "cave_evals")}
     e1.record(stream)
     torch.cuda.synchronize()
     clocks = sampler.stop()
@@ -317,6 +314,7 @@ def main():
         with vg.Context(local_rank, seed=seed) as other:
             other.set_timing(True)
             other.decode_areas(gen_xy, blob, offs, read_heights=False)
+            other.timings()  # clears the accumulators: the first call also loaded the kernels
             other.decode_areas(gen_xy, blob, offs, read_heights=False)
             dec_ms = other.timings()["codec_ms"]
         codec = {"encode_ms": enc_ms, "decode_ms": dec_ms, "areas": n_gen, "file_bytes_total": int(total),

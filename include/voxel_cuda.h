@@ -82,8 +82,9 @@ typedef struct {
     uint64_t vertex_bytes, index_bytes, rec_bytes;
 } vx_mesh_info;
 
-/* Device time of the kernels of the most recent vx_generate / vx_mesh / vx_apply_edits / ... call,
- * CUDA events on the context's stream.  Only filled while vx_set_timing(ctx, 1). */
+/* Device time of the kernels launched since the previous vx_get_timings (which clears the
+ * accumulators), CUDA events on the context's stream.  Only filled while vx_set_timing(ctx, 1).
+ * vx_get_timings waits for a vx_generate that returned without waiting (see there). */
 typedef struct {
     float gen_columns_ms;  /* K1 */
     float gen_caves_ms;    /* K1b */
@@ -94,7 +95,7 @@ typedef struct {
     float heightmap_ms;    /* K6 */
     float light_ms;        /* L-ext */
     float visible_ms;      /* K7 (vx_visible) */
-    uint32_t gen_launches, mesh_launches, other_launches; /* kernels launched by the last call */
+    uint32_t gen_launches, mesh_launches, other_launches; /* kernels launched */
     uint32_t cave_columns;                                /* K1b work items of the last generate */
     float codec_ms;        /* K8 / K9 (vx_encode_areas, vx_decode_areas) */
     /* work accounting of the last vx_generate (roofline numerators): octave-level simplex
@@ -133,7 +134,10 @@ uint64_t vx_hash_world_name(const char* world_name);
  * which ends in Area::update_all_column_heights, area.rs:34-44) for a whole batch, i.e. the body
  * of AreaLoader::load_all_blocking / batch_load (world_persistence.rs:85-110) for disk misses.
  * Areas become resident in the context.  voxels_out (n*32768) / max_height_out (n*256) are host
- * buffers, either may be NULL to leave the result on the device only. */
+ * buffers, either may be NULL to leave the result on the device only.  With both NULL the call
+ * returns as soon as the kernels are enqueued on the context's stream (world pre-generation keeps
+ * the device busy while the host prepares the next call); every later call on the context is
+ * ordered behind them, and a failure of the kernels is reported by that call or by vx_sync. */
 int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out,
                 uint8_t* max_height_out);
 

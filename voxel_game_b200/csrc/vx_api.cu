@@ -161,6 +161,10 @@ struct vx_ctx {
     // scratch
     PinnedBuf h_stage;   // jobs / lists going to the device
     PinnedBuf h_small;   // small results coming back
+    PinnedBuf h_gen_counters;  // work counters of a vx_generate that returned without waiting
+    bool gen_counters_pending = false;
+    cudaEvent_t stage_ev = nullptr;  // h_stage has been consumed by the copy enqueued from it
+    bool stage_pending = false;
     DevBuf d_jobs, d_gen_jobs, d_list, d_missing, d_cave_items, d_counters, d_rec_count, d_face_count;
     DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
     DevBuf d_heightmap, d_light, d_slot_to_job, d_finished, d_warp_totals, d_mesh_nbr;
@@ -204,11 +208,33 @@ int fail(vx_ctx* c, int status, const char* what) {
         if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call);   \
     } while (0)
 
+float* timer_slot(vx_ctx* c, int id) {
+    float* dst[TM_COUNT] = {&c->timings.gen_columns_ms, &c->timings.gen_caves_ms,
+                            &c->timings.gen_finish_ms,  &c->timings.mesh_count_ms,
+                            &c->timings.mesh_emit_ms,   &c->timings.edit_ms,
+                            &c->timings.heightmap_ms,   &c->timings.light_ms,
+                            &c->timings.visible_ms,     &c->timings.codec_ms};
+    return dst[id];
+}
+
+// adds the elapsed time of a recorded pair to the accumulators (the pair must have completed)
+void collect_timer(vx_ctx* c, int id) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev[id][0], c->ev[id][1]) == cudaSuccess) *timer_slot(c, id) += ms;
+    c->ev_used[id] = false;
+}
+
+// Timings accumulate from one vx_get_timings to the next.  A pair recorded by a call that returned
+// without waiting (vx_generate without host outputs) stays pending until the next synchronisation.
 struct ScopedTimer {
     vx_ctx* c;
     int id;
     ScopedTimer(vx_ctx* ctx, int which) : c(ctx), id(which) {
         if (c->timing) {
+            if (c->ev_used[id]) {  // still pending from an earlier call: settle it before reuse
+                cudaEventSynchronize(c->ev[id][1]);
+                collect_timer(c, id);
+            }
             cudaEventRecord(c->ev[id][0], c->stream);
             c->ev_used[id] = true;
         }
@@ -218,30 +244,36 @@ struct ScopedTimer {
     }
 };
 
-void reset_timers(vx_ctx* c) {
-    std::memset(c->ev_used, 0, sizeof c->ev_used);
-    std::memset(&c->timings, 0, sizeof c->timings);
-}
+void reset_timers(vx_ctx*) {}  // accumulators are cleared by vx_get_timings
 
 // call after the stream has been synchronised
 void collect_timers(vx_ctx* c) {
-    if (!c->timing) return;
-    float* dst[TM_COUNT] = {&c->timings.gen_columns_ms, &c->timings.gen_caves_ms,
-                            &c->timings.gen_finish_ms,  &c->timings.mesh_count_ms,
-                            &c->timings.mesh_emit_ms,   &c->timings.edit_ms,
-                            &c->timings.heightmap_ms,   &c->timings.light_ms,
-                            &c->timings.visible_ms,     &c->timings.codec_ms};
     for (int i = 0; i < TM_COUNT; ++i)
-        if (c->ev_used[i]) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, c->ev[i][0], c->ev[i][1]) == cudaSuccess) *dst[i] += ms;
-            c->ev_used[i] = false;
-        }
+        if (c->ev_used[i]) collect_timer(c, i);
+    if (c->gen_counters_pending) {
+        const unsigned long long* n = c->h_gen_counters.as<unsigned long long>();
+        c->timings.cave_columns = (uint32_t)n[0];
+        c->timings.simplex2_evals = n[2];
+        c->timings.cave_voxels = n[4];
+        c->timings.simplex3_evals = n[3] + n[5];  // surface noise + cave octaves actually evaluated
+        c->timings.cave_evals = n[5];
+        c->gen_counters_pending = false;
+    }
+}
+
+// h_stage may still be the source of a copy enqueued by a call that did not wait
+int stage_ready(vx_ctx* ctx) {
+    if (ctx->stage_pending) {
+        VX_CUDA(cudaEventSynchronize(ctx->stage_ev));
+        ctx->stage_pending = false;
+    }
+    return VX_OK;
 }
 
 int sync_stream(vx_ctx* ctx) {
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     VX_CUDA(cudaGetLastError());
+    ctx->stage_pending = false;
     collect_timers(ctx);
     return VX_OK;
 }
@@ -342,6 +374,7 @@ int host_slot(const vx_ctx* ctx, uint32_t ax, uint32_t ay) { return ctx->index.f
 // jobs {ax, ay, slot, 0} -> device (through pinned staging; the stream is idle between calls)
 int upload_jobs(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>& slots, int n) {
     ctx->last_mesh_version = ~0ull;  // d_jobs no longer holds the list of the last vx_mesh
+    if (int st = stage_ready(ctx)) return st;
     VX_CUDA(ctx->h_stage.ensure((size_t)n * sizeof(uint4)));
     VX_CUDA(ctx->d_jobs.ensure((size_t)n * sizeof(uint4)));
     uint4* j = ctx->h_stage.as<uint4>();
@@ -372,11 +405,15 @@ int copy_slots(vx_ctx* ctx, const std::vector<int>& slots, int n, uint8_t* dev_b
 int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>& slots, int n,
                    bool jobs_on_device = false) {
     if (!jobs_on_device) {  // jobs {ax, ay, slot, 0} -> d_gen_jobs through pinned staging
+        int st = stage_ready(ctx);
+        if (st != VX_OK) return st;
         VX_CUDA(ctx->h_stage.ensure((size_t)n * sizeof(uint4)));
         VX_CUDA(ctx->d_gen_jobs.ensure((size_t)n * sizeof(uint4)));
         uint4* j = ctx->h_stage.as<uint4>();
         for (int i = 0; i < n; ++i) j[i] = make_uint4(area_xy[2 * i], area_xy[2 * i + 1], (uint32_t)slots[i], 0u);
         VX_CUDA(cudaMemcpyAsync(ctx->d_gen_jobs.p, j, (size_t)n * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+        VX_CUDA(cudaEventRecord(ctx->stage_ev, ctx->stream));
+        ctx->stage_pending = true;
         ctx->last_gen_version = ~0ull;  // whatever list d_gen_jobs held before is gone
     }
     VX_CUDA(ctx->d_cave_items.ensure((size_t)n * COLUMNS_IN_AREA * sizeof(uint32_t)));
@@ -460,6 +497,7 @@ int vx_create(int device, vx_ctx** out) {
     ctx->stream = ctx->own_stream;
     for (int i = 0; i < TM_COUNT; ++i)
         for (int k = 0; k < 2; ++k) cudaEventCreate(&ctx->ev[i][k]);
+    cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming);
     *out = ctx;
     return VX_OK;
 }
@@ -480,6 +518,8 @@ void vx_destroy(vx_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     ctx->h_stage.release();
     ctx->h_small.release();
+    ctx->h_gen_counters.release();
+    cudaEventDestroy(ctx->stage_ev);
     for (int i = 0; i < TM_COUNT; ++i)
         for (int k = 0; k < 2; ++k) cudaEventDestroy(ctx->ev[i][k]);
     cudaStreamDestroy(ctx->own_stream);
@@ -514,7 +554,15 @@ int vx_set_timing(vx_ctx* ctx, int enabled) {
 int vx_get_timings(vx_ctx* ctx, vx_timings* out) {
     if (!ctx || !out) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    bool pending = ctx->gen_counters_pending;
+    for (int i = 0; i < TM_COUNT; ++i) pending = pending || ctx->ev_used[i];
+    if (pending) {  // a call that did not wait (vx_generate without host outputs) is still in flight
+        VX_CUDA(cudaSetDevice(ctx->device));
+        int st = sync_stream(ctx);
+        if (st != VX_OK) return st;
+    }
     *out = ctx->timings;
+    ctx->timings = vx_timings{};
     return VX_OK;
 }
 
@@ -571,21 +619,16 @@ int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out
     ctx->last_gen_version = ctx->index_version;  // d_gen_jobs now holds exactly this list
     if (voxels_out && (st = copy_slots(ctx, slots, n, ctx->d_voxels, VOXELS_IN_AREA, voxels_out, true)) != VX_OK) return st;
     if (max_height_out && (st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, max_height_out, true)) != VX_OK) return st;
-    unsigned long long* c = nullptr;
     if (ctx->timing) {  // work accounting of this call (the roofline numerators)
-        VX_CUDA(ctx->h_small.ensure(64));
-        c = ctx->h_small.as<unsigned long long>();
-        VX_CUDA(cudaMemcpyAsync(c, ctx->d_counters.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
+        VX_CUDA(ctx->h_gen_counters.ensure(64));
+        VX_CUDA(cudaMemcpyAsync(ctx->h_gen_counters.p, ctx->d_counters.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->gen_counters_pending = true;
     }
-    if ((st = sync_stream(ctx)) != VX_OK) return st;
-    if (c) {
-        ctx->timings.cave_columns = (uint32_t)c[0];
-        ctx->timings.simplex2_evals = c[2];
-        ctx->timings.cave_voxels = c[4];
-        ctx->timings.simplex3_evals = c[3] + c[5];  // surface noise + cave octaves actually evaluated
-        ctx->timings.cave_evals = c[5];
-    }
-    return VX_OK;
+    // Without host outputs there is nothing to wait for: the areas are resident in stream order,
+    // and whatever reads or changes them next is enqueued behind the kernels.  Errors of the
+    // kernels then surface in that later call (or in vx_sync).
+    if (!voxels_out && !max_height_out) return VX_OK;
+    return sync_stream(ctx);
 }
 
 int vx_upload(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* voxels,
@@ -661,6 +704,7 @@ int vx_column_heights(vx_ctx* ctx, const uint8_t* voxels, int n, uint8_t* max_he
     uint8_t* dv = ctx->d_tmp.as<uint8_t>();
     uint8_t* dh = dv + vbytes;
     VX_CUDA(cudaMemcpyAsync(dv, voxels, vbytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (int st = stage_ready(ctx)) return st;
     VX_CUDA(ctx->h_stage.ensure((size_t)n * sizeof(uint4)));
     VX_CUDA(ctx->d_jobs.ensure((size_t)n * sizeof(uint4)));
     uint4* j = ctx->h_stage.as<uint4>();
@@ -686,6 +730,7 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
         // the area list goes to the device as is; slots, neighbour residency and the set of bit
         // planes to refresh are resolved there (mesh_prepare_kernel), not in a host loop
         const size_t xy_bytes = (size_t)n * sizeof(uint2);
+        if ((st = stage_ready(ctx)) != VX_OK) return st;
         VX_CUDA(ctx->h_stage.ensure(xy_bytes));
         VX_CUDA(ctx->h_small.ensure(64 + (size_t)4 * n * sizeof(uint2)));
         VX_CUDA(ctx->d_list.ensure(xy_bytes));
@@ -1179,6 +1224,7 @@ int vx_heightmap(vx_ctx* ctx, const uint32_t* area_xy, int n, uint32_t cam_area_
         ctx->heightmap_init = true;
     }
     if (n > 0) {
+        if (int st = stage_ready(ctx)) return st;
         VX_CUDA(ctx->h_stage.ensure((size_t)n * 8));
         VX_CUDA(ctx->d_list.ensure((size_t)n * 8));
         std::memcpy(ctx->h_stage.p, area_xy, (size_t)n * 8);

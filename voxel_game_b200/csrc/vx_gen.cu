@@ -231,6 +231,7 @@ struct __align__(16) GenSmem {
     NoiseShared noise;
     unsigned cave_n;
     unsigned cave_base;
+    unsigned evals[2];    // 2-D / 3-D octave evaluations of the CTA
     unsigned stone_rows;  // zi <= stone_rows is Stone in every column of the area
     int min_z;            // smallest z holding generated terrain (= 128 - max H)
     uint16_t tree[COLUMNS_IN_AREA];  // tree candidates, indexed x * 16 + y
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
                                                           unsigned long long* __restrict__ stats,
                                                           uint16_t* __restrict__ pool_planes,
                                                           uint8_t* __restrict__ finished) {
-    __shared__ GenSmem sm;
+    __shared__ __align__(256) GenSmem sm;  // vox is 32 KiB, so the table image behind it is 256-byte aligned
     const int tid = threadIdx.x;
     const uint4 job = jobs[blockIdx.x];
     const uint32_t ax = job.x, ay = job.y, slot = job.z;
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
     load_noise_shared(&sm.noise, nt, tid, 256);
     if (tid == 0) {
         sm.cave_n = 0;
+        sm.evals[0] = sm.evals[1] = 0;
         sm.stone_rows = AREA_HEIGHT;
         sm.min_z = AREA_HEIGHT;
         slot_xy[slot] = make_uint2(ax, ay);
@@ -292,6 +294,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
     __syncthreads();
 
     const NoiseShared* s = &sm.noise;
+    const unsigned sb = smem_address(sm.noise.bytes);
     uint8_t* vox = reinterpret_cast<uint8_t*>(sm.vox);
     const unsigned x = tid & 15, y = tid >> 4;
     // algorithms.rs:12-17: u32 sum, then cast
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
             const FbmParams& q = nt.fbm[FBM_ALT];
             double x3 = px * q.frequency, y3 = py * q.frequency, z3 = (double)zi * q.frequency;
             double acc = 0.0;
-            acc += q.amp[0] * simplex3<FBM_TABLE<FBM_ALT>>(s->bytes, x3, y3, z3);
+            acc += q.amp[0] * simplex3<FBM_TABLE<FBM_ALT>>(sb, x3, y3, z3);
             evals3 += 1;
             const double mid = acc * q.norm, rest = SIMPLEX_BOUND * q.amp[1] * q.norm + 1e-9;
             if (normalise(mid - rest) - 1e-9 >= threshold) {
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
                 alt = false;
             } else {
                 x3 *= q.lacunarity; y3 *= q.lacunarity; z3 *= q.lacunarity;
-                acc += q.amp[1] * simplex3<FBM_TABLE<FBM_ALT>>(s->bytes, x3, y3, z3);
+                acc += q.amp[1] * simplex3<FBM_TABLE<FBM_ALT>>(sb, x3, y3, z3);
                 evals3 += 1;
                 alt = normalise(acc * q.norm) >= threshold;
             }
@@ -365,37 +368,55 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
     __syncthreads();
     const unsigned stone_rows = sm.stone_rows;
     {
-        const unsigned s4 = V_STONE * 0x01010101u;
+        const unsigned s4 = V_STONE * 0x01010101u, first_stone_z = AREA_HEIGHT - stone_rows;
         const uint4 stone = make_uint4(s4, s4, s4, s4), none = make_uint4(0, 0, 0, 0);
-        for (unsigned i = tid; i < VOXELS_IN_AREA / 16; i += 256)  // i / 16 = z of the 16-byte row
-            sm.vox[i] = (i >> 4) >= AREA_HEIGHT - stone_rows ? stone : none;
+#pragma unroll
+        for (unsigned k = 0; k < VOXELS_IN_AREA / 16 / 256; ++k) {  // i / 16 = z of the 16-byte row
+            const unsigned i = tid + 256 * k;
+            if ((i >> 4) >= first_stone_z) sm.vox[i] = stone;
+            else sm.vox[i] = none;
+        }
     }
     __syncthreads();
 
-    // generate_column (generator.rs:70-98) without the cave test; bottom -> top
-    for (unsigned zi = stone_rows + 1; zi <= H; ++zi) {
-        uint8_t v;
-        if (lake_depth != 0 && zi > LAKE_TOP_ZI) {
-            v = V_NONE;  // lake_generator.rs:59-61
-        } else if (lake_depth != 0 && zi >= LAKE_TOP_ZI - lake_depth) {
-            v = (biome == COLD && zi == LAKE_TOP_ZI) ? V_ICE : V_WATER_SOURCE;
-        } else if (zi + 3 < H) {
-            v = V_STONE;
-        } else {
-            v = (uint8_t)(tops >> (8 * (zi + 3 - H)));
+    // generate_column (generator.rs:70-98) without the cave test; bottom -> top, above the slabs
+    // filled already
+    if (lake_depth == 0) {
+        // Stone up to four below the surface (voxel_type_generator.rs:64-174), then the surface voxels
+        uint8_t* col = vox + tid + 256 * AREA_HEIGHT;  // col[-256 * zi] is the voxel at zi
+        for (unsigned zi = stone_rows + 1; zi + 3 < H; ++zi) col[-256 * (int)zi] = V_STONE;
+#pragma unroll
+        for (unsigned k = 0; k < 4; ++k) col[-256 * (int)(H - 3 + k)] = (uint8_t)(tops >> (8 * k));
+    } else {
+        for (unsigned zi = stone_rows + 1; zi <= H; ++zi) {
+            uint8_t v;
+            if (zi > LAKE_TOP_ZI) {
+                v = V_NONE;  // lake_generator.rs:59-61
+            } else if (zi >= LAKE_TOP_ZI - lake_depth) {
+                v = (biome == COLD && zi == LAKE_TOP_ZI) ? V_ICE : V_WATER_SOURCE;
+            } else if (zi + 3 < H) {
+                v = V_STONE;
+            } else {
+                v = (uint8_t)(tops >> (8 * (zi + 3 - H)));
+            }
+            vox[tid + 256 * (AREA_HEIGHT - zi)] = v;
         }
-        vox[tid + 256 * (AREA_HEIGHT - zi)] = v;
     }
 
+    // work accounting: one pair of global atomics per CTA
     evals2 = __reduce_add_sync(0xFFFFFFFFu, evals2);
     evals3 = __reduce_add_sync(0xFFFFFFFFu, evals3);
     if ((tid & 31) == 0) {
-        atomicAdd(&stats[0], (unsigned long long)evals2);
-        atomicAdd(&stats[1], (unsigned long long)evals3);
+        atomicAdd(&sm.evals[0], evals2);
+        atomicAdd(&sm.evals[1], evals3);
     }
     uint8_t* heights = pool_heights + (size_t)slot * COLUMNS_IN_AREA;
     __syncthreads();  // the area is complete in shared memory
     const unsigned n_cave = sm.cave_n;  // final since the barrier before the fill
+    if (tid == 0) {
+        atomicAdd(&stats[0], (unsigned long long)sm.evals[0]);
+        atomicAdd(&stats[1], (unsigned long long)sm.evals[1]);
+    }
     __syncthreads();                    // everyone has read it before it is reused as a cursor
 
     if (n_cave != 0) {
@@ -419,15 +440,13 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
         __syncthreads();
         if (tid < 32) place_trees(vox, sm.tree, tid);
         __syncthreads();
-        // update_all_column_heights (area.rs:34-56); everything above min_z - 7 is still None
-        const int z_lo = max(sm.min_z - 8, 0);
-        int zz = z_lo;
-        while (zz < AREA_HEIGHT && is_transparent(vox[tid + 256 * zz])) ++zz;
-        heights[tid] = (uint8_t)(zz < AREA_HEIGHT ? zz : AREA_HEIGHT - 1);
-        // planes: slabs above z_lo are all None, slabs from z_hi on are all Stone; in between one
-        // ballot per slab and warp gives the two rows (y = 2 * warp, 2 * warp + 1) of both planes
+        // Column heights (update_all_column_heights, area.rs:34-56) and the bit planes in one walk.
+        // Slabs above z_lo are all None (trees reach at most 7 above the surface), slabs from z_hi
+        // on are all Stone -- so a column's height is z_hi unless something opaque lies above it.
+        // In between one ballot per slab and warp gives the two rows (y = 2 * warp, 2 * warp + 1)
+        // of both planes.
+        const int z_lo = max(sm.min_z - 8, 0), z_hi = AREA_HEIGHT - (int)stone_rows;
         uint16_t* planes = pool_planes + (size_t)slot * (VOXELS_IN_AREA / 8);
-        const int z_hi = AREA_HEIGHT - (int)stone_rows;
         {
             const int z = tid >> 1;  // thread i owns rows 8i .. 8i+7 = half of slab z = i / 2
             if (z < z_lo || z >= z_hi) {
@@ -437,15 +456,21 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
             }
         }
         const int wid = tid >> 5;
-        for (int z = z_lo; z < z_hi; ++z) {
+        uint32_t* s_words = reinterpret_cast<uint32_t*>(planes) + wid;
+        uint32_t* t_words = reinterpret_cast<uint32_t*>(planes + VOXELS_IN_AREA / 16) + wid;
+        int top = z_hi;  // first z from the top that is not transparent
+        for (int z = z_hi - 1; z >= z_lo; --z) {
             const unsigned v = vox[tid + 256 * z];
+            const bool transparent = is_transparent(v);
             const unsigned sb = __ballot_sync(0xFFFFFFFFu, v != 0u);
-            const unsigned tb = __ballot_sync(0xFFFFFFFFu, is_transparent(v));
+            const unsigned tb = __ballot_sync(0xFFFFFFFFu, transparent);
+            if (!transparent) top = z;
             if ((tid & 31) == 0) {  // rows r = 16 z + 2 wid and r + 1 are one 32-bit word
-                reinterpret_cast<uint32_t*>(planes)[8 * z + wid] = sb;
-                reinterpret_cast<uint32_t*>(planes + VOXELS_IN_AREA / 16)[8 * z + wid] = tb;
+                s_words[8 * z] = sb;
+                t_words[8 * z] = tb;
             }
         }
+        heights[tid] = (uint8_t)top;
         if (tid == 0) finished[blockIdx.x] = 1;
     }
 
@@ -494,7 +519,7 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
                                                         const uint8_t* __restrict__ pool_heights,
                                                         const uint2* __restrict__ slot_xy,
                                                         unsigned long long* __restrict__ stats) {
-    __shared__ CaveSmem sm;
+    __shared__ __align__(256) CaveSmem sm;  // table image first: 256-byte aligned for simplex3
     const int tid = threadIdx.x, lane = tid & 31;
     const FbmParams& q1 = nt.fbm[FBM_CAVE1];
     const FbmParams& q2 = nt.fbm[FBM_CAVE2];
@@ -508,6 +533,7 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
     const uint32_t n_items = *cave_count;
     const double f1 = q1.frequency, f2 = q2.frequency, l1 = q1.lacunarity, l2 = q2.lacunarity;
     const double n1 = q1.norm, n2 = q2.norm;
+    const unsigned sb = smem_address(sm.bytes);
     CaveWarp& cw = sm.warp[tid >> 5];
     unsigned* chunk_counter = reinterpret_cast<unsigned*>(&stats[4]);
     const unsigned lanes_below = (1u << lane) - 1u;
@@ -591,12 +617,12 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
             // one octave of each Fbm per round (noise1 has 6, noise2 has 8): no per-lane selection
             // of coordinates, and two independent evaluations in flight
             const unsigned k = step;
-            const double svb = simplex3<FBM_TABLE<FBM_CAVE2>>(sm.bytes, xb, yb, zb);
+            const double svb = simplex3<FBM_TABLE<FBM_CAVE2>>(sb, xb, yb, zb);
             bsum += sm.amp[1][k] * svb;
             xb *= l2; yb *= l2; zb *= l2;
             ++my_evals;
             if (k < 6) {
-                const double sva = simplex3<FBM_TABLE<FBM_CAVE1>>(sm.bytes, xa, ya, za);
+                const double sva = simplex3<FBM_TABLE<FBM_CAVE1>>(sb, xa, ya, za);
                 a += sm.amp[0][k] * sva;
                 xa *= l1; ya *= l1; za *= l1;
                 ++my_evals;

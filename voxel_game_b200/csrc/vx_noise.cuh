@@ -136,14 +136,24 @@ __device__ __forceinline__ void corner3(double x, double y, double z, unsigned g
     sum += t2 * t2 * d;
 }
 
-// bytes = the table image in shared memory, TABLE = which (doubled) permutation table of it; the
-// % 12 copy sits OFF_P12 bytes further.
-// Indices are sums of table bytes and coordinates reduced to 8 bits (at most 255 + 255 + 1), which
-// the doubled table serves without masking -- the crate's own arrangement; constant offsets fold
-// into the loads.
+// One table byte through an explicit shared-memory address: `addr` already holds table image +
+// index, the table and the copy are the constant OFF that folds into the load.
+template <int OFF>
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ unsigned smem_address(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// sb = shared-memory address of the table image (256-byte aligned, so that "sb | coordinate & 255"
+// is one logic instruction), TABLE = which (doubled) permutation table of it; the % 12 copy sits
+// OFF_P12 bytes further.  Indices are sums of table bytes and coordinates reduced to 8 bits (at
+// most 255 + 255 + 1), which the doubled table serves without masking -- the crate's own
+// arrangement: one add and one load per lookup.
 template <int TABLE>
-__device__ __forceinline__ double simplex3(const uint8_t* bytes, double x, double y, double z) {
-    const uint8_t* tb = bytes + TABLE * TAB_STRIDE;
+__device__ __forceinline__ double simplex3(unsigned sb, double x, double y, double z) {
+    constexpr int T = TABLE * (int)TAB_STRIDE, G = T + (int)OFF_P12;
     const double SKEW = c_noise_k[4], UNSKEW = c_noise_k[5], UNSKEW_2 = c_noise_k[6];
     const double sk = (x + y + z) * SKEW;
     int i, j, k;
@@ -161,13 +171,12 @@ __device__ __forceinline__ double simplex3(const uint8_t* bytes, double x, doubl
     const double x1 = (i1 ? xm : x0) + UNSKEW, y1 = (j1 ? ym : y0) + UNSKEW, z1 = (k1 ? zm : z0) + UNSKEW;
     const double x2 = (i2 ? xm : x0) + UNSKEW_2, y2 = (j2 ? ym : y0) + UNSKEW_2, z2 = (k2 ? zm : z0) + UNSKEW_2;
     const double x3 = xm + 0.5, y3 = ym + 0.5, z3 = zm + 0.5;  // 3.0 * UNSKEW == 0.5 exactly
-    const unsigned im = (unsigned)i & 255u, jm = (unsigned)j & 255u, km = (unsigned)k & 255u;
-    const unsigned pi0 = tb[im], pi1 = tb[im + 1];
-    const uint8_t* tg = tb + OFF_P12;
-    const unsigned h0 = tg[tb[pi0 + jm] + km];
-    const unsigned h1 = tg[tb[(i1 ? pi1 : pi0) + jm + (j1 ? 1u : 0u)] + km + (k1 ? 1u : 0u)];
-    const unsigned h2 = tg[tb[(i2 ? pi1 : pi0) + jm + (j2 ? 1u : 0u)] + km + (k2 ? 1u : 0u)];
-    const unsigned h3 = tg[tb[pi1 + jm + 1] + km + 1];
+    const unsigned ib = sb | ((unsigned)i & 255u), jb = sb | ((unsigned)j & 255u), kb = sb | ((unsigned)k & 255u);
+    const unsigned pi0 = lds_u8<T>(ib), pi1 = lds_u8<T + 1>(ib);
+    const unsigned h0 = lds_u8<G>(kb + lds_u8<T>(jb + pi0));
+    const unsigned h1 = lds_u8<G>(kb + lds_u8<T>(jb + (i1 ? pi1 : pi0) + (j1 ? 1u : 0u)) + (k1 ? 1u : 0u));
+    const unsigned h2 = lds_u8<G>(kb + lds_u8<T>(jb + (i2 ? pi1 : pi0) + (j2 ? 1u : 0u)) + (k2 ? 1u : 0u));
+    const unsigned h3 = lds_u8<G + 1>(kb + lds_u8<T + 1>(jb + pi1));
     double sum = 0.0;
     corner3(x0, y0, z0, h0, sum);
     corner3(x1, y1, z1, h1, sum);
@@ -201,7 +210,7 @@ __device__ __forceinline__ double fbm3(const NoiseTables& nt, const NoiseShared*
     double acc = 0.0;
 #pragma unroll 1
     for (int o = 0; o < q.octaves; ++o) {
-        acc += q.amp[o] * simplex3<FBM_TABLE<ID>>(s->bytes, x, y, z);
+        acc += q.amp[o] * simplex3<FBM_TABLE<ID>>(smem_address(s->bytes), x, y, z);
         x *= q.lacunarity;
         y *= q.lacunarity;
         z *= q.lacunarity;
