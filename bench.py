@@ -219,7 +219,10 @@ def main():
 
     seed = vg.hash_world_name(WORLD_NAME)
     ctx = vg.Context(local_rank, seed=seed)
-    stream = torch.cuda.current_stream()
+    # a stream of our own: torch's default stream is the NULL stream, which vx_set_stream reads as
+    # "use the context's own stream" -- the events below must sit on the stream the kernels run on
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     ax0, ay0, nx, ny = vg.spawn_region(REGION)
@@ -250,11 +253,6 @@ def main():
     for _ in range(args.steps):
         ctx.generate(gen_xy, read=False)  # enqueued; vx_mesh is ordered behind it and waits for the totals
         info = ctx.mesh(mesh_xy)
-        t = ctx.timings()                 # kernel times and work counters since the previous read
-        for k in ("gen_columns_ms", "gen_caves_ms", "gen_finish_ms", "mesh_count_ms", "mesh_emit_ms"):
-            kern[k] = kern.get(k, 0.0) + t[k]
-        launches += t["mesh_launches"] + t["gen_launches"]
-        work = {k: t[k] for k in ("simplex2_evals", "simplex3_evals", "cave_voxels", "cave_columns", "cave_evals")}
     e1.record(stream)
     torch.cuda.synchronize()
     clocks = sampler.stop()
@@ -265,7 +263,10 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
     value = n_mesh * world * args.steps / (ms * 1e-3)
-    kern = {k: v / args.steps for k, v in kern.items()}
+    t = ctx.timings()  # kernel times (CUDA events around every launch) accumulated over the timed steps
+    kern = {k: t[k] / args.steps for k in ("gen_columns_ms", "gen_caves_ms", "gen_finish_ms", "mesh_count_ms", "mesh_emit_ms")}
+    launches = t["mesh_launches"] + t["gen_launches"]
+    work = {k: t[k] for k in ("simplex2_evals", "simplex3_evals", "cave_voxels", "cave_columns", "cave_evals")}
 
     # ---- per-frame visibility over the resident mesh (K7; not part of `value`): a camera on the
     # spawn surface with a render distance that covers the whole region

@@ -161,11 +161,11 @@ struct vx_ctx {
     // scratch
     PinnedBuf h_stage;   // jobs / lists going to the device
     PinnedBuf h_small;   // small results coming back
-    PinnedBuf h_gen_counters;  // work counters of a vx_generate that returned without waiting
-    bool gen_counters_pending = false;
+    bool gen_counters_pending = false;  // d_counters holds the work counters of a timed vx_generate
     cudaEvent_t stage_ev = nullptr;  // h_stage has been consumed by the copy enqueued from it
     bool stage_pending = false;
     DevBuf d_jobs, d_gen_jobs, d_list, d_missing, d_cave_items, d_counters, d_rec_count, d_face_count;
+    DevBuf d_gen_counters;  // cave work list size + work accounting of vx_generate; no other call touches it
     DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
     DevBuf d_heightmap, d_light, d_slot_to_job, d_finished, d_warp_totals, d_mesh_nbr;
     DevBuf d_mesh_xy, d_frame_flags, d_frame_counts, d_frame_small, d_frame_visible;  // per-frame visibility (K7)
@@ -184,6 +184,7 @@ struct vx_ctx {
     // timing
     bool timing = false;
     cudaEvent_t ev[TM_COUNT][2] = {};
+    cudaEvent_t ev_start[TM_COUNT] = {};  // ev[id][0], or the end event of the timer it follows directly
     bool ev_used[TM_COUNT] = {};
     vx_timings timings{};
 };
@@ -220,22 +221,30 @@ float* timer_slot(vx_ctx* c, int id) {
 // adds the elapsed time of a recorded pair to the accumulators (the pair must have completed)
 void collect_timer(vx_ctx* c, int id) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, c->ev[id][0], c->ev[id][1]) == cudaSuccess) *timer_slot(c, id) += ms;
+    if (cudaEventElapsedTime(&ms, c->ev_start[id], c->ev[id][1]) == cudaSuccess) *timer_slot(c, id) += ms;
     c->ev_used[id] = false;
 }
 
 // Timings accumulate from one vx_get_timings to the next.  A pair recorded by a call that returned
 // without waiting (vx_generate without host outputs) stays pending until the next synchronisation.
+// `follows` = a timer whose scope closed immediately before this one opens (nothing else went
+// into the stream in between): its end event is this timer's start, one record instead of two --
+// every record between two kernels keeps the second from being launched ahead.
 struct ScopedTimer {
     vx_ctx* c;
     int id;
-    ScopedTimer(vx_ctx* ctx, int which) : c(ctx), id(which) {
+    ScopedTimer(vx_ctx* ctx, int which, int follows = -1) : c(ctx), id(which) {
         if (c->timing) {
             if (c->ev_used[id]) {  // still pending from an earlier call: settle it before reuse
                 cudaEventSynchronize(c->ev[id][1]);
                 collect_timer(c, id);
             }
-            cudaEventRecord(c->ev[id][0], c->stream);
+            if (follows >= 0 && c->ev_used[follows]) {
+                c->ev_start[id] = c->ev[follows][1];
+            } else {
+                cudaEventRecord(c->ev[id][0], c->stream);
+                c->ev_start[id] = c->ev[id][0];
+            }
             c->ev_used[id] = true;
         }
     }
@@ -250,15 +259,6 @@ void reset_timers(vx_ctx*) {}  // accumulators are cleared by vx_get_timings
 void collect_timers(vx_ctx* c) {
     for (int i = 0; i < TM_COUNT; ++i)
         if (c->ev_used[i]) collect_timer(c, i);
-    if (c->gen_counters_pending) {
-        const unsigned long long* n = c->h_gen_counters.as<unsigned long long>();
-        c->timings.cave_columns = (uint32_t)n[0];
-        c->timings.simplex2_evals = n[2];
-        c->timings.cave_voxels = n[4];
-        c->timings.simplex3_evals = n[3] + n[5];  // surface noise + cave octaves actually evaluated
-        c->timings.cave_evals = n[5];
-        c->gen_counters_pending = false;
-    }
 }
 
 // h_stage may still be the source of a copy enqueued by a call that did not wait
@@ -418,11 +418,11 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
     }
     VX_CUDA(ctx->d_cave_items.ensure((size_t)n * COLUMNS_IN_AREA * sizeof(uint32_t)));
     VX_CUDA(ctx->d_finished.ensure((size_t)n));
-    VX_CUDA(ctx->d_counters.ensure(64));
-    VX_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
+    VX_CUDA(ctx->d_gen_counters.ensure(64));
+    VX_CUDA(cudaMemsetAsync(ctx->d_gen_counters.p, 0, 64, ctx->stream));
     const uint4* jobs = ctx->d_gen_jobs.as<uint4>();
-    uint32_t* cave_count = ctx->d_counters.as<uint32_t>();
-    unsigned long long* stats = ctx->d_counters.as<unsigned long long>() + 2;  // bytes 16..39
+    uint32_t* cave_count = ctx->d_gen_counters.as<uint32_t>();
+    unsigned long long* stats = ctx->d_gen_counters.as<unsigned long long>() + 2;  // bytes 16..55
     {
         ScopedTimer t(ctx, TM_GEN_COLUMNS);
         launch_gen_columns(ctx->tables, jobs, n, ctx->d_voxels, ctx->d_heights, ctx->d_slot_xy,
@@ -430,12 +430,12 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
                            ctx->d_finished.as<uint8_t>(), ctx->stream);
     }
     {
-        ScopedTimer t(ctx, TM_GEN_CAVES);
+        ScopedTimer t(ctx, TM_GEN_CAVES, TM_GEN_COLUMNS);
         launch_gen_caves(ctx->tables, ctx->d_cave_items.as<uint32_t>(), cave_count, ctx->d_voxels, ctx->d_heights,
                          ctx->d_slot_xy, stats, ctx->sm_count, ctx->stream);
     }
     {
-        ScopedTimer t(ctx, TM_GEN_FINISH);
+        ScopedTimer t(ctx, TM_GEN_FINISH, TM_GEN_CAVES);
         launch_gen_finish(jobs, ctx->d_finished.as<uint8_t>(), n, ctx->d_voxels, ctx->d_heights, ctx->d_planes,
                           ctx->tables.seed, ctx->stream);
     }
@@ -508,7 +508,7 @@ void vx_destroy(vx_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
     cudaFree(ctx->d_noise_image);
-    DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_gen_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters,
+    DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_gen_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters, &ctx->d_gen_counters,
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
                       &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_warp_totals, &ctx->d_mesh_nbr, &ctx->d_mesh_xy, &ctx->d_frame_flags,
@@ -518,7 +518,6 @@ void vx_destroy(vx_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     ctx->h_stage.release();
     ctx->h_small.release();
-    ctx->h_gen_counters.release();
     cudaEventDestroy(ctx->stage_ev);
     for (int i = 0; i < TM_COUNT; ++i)
         for (int k = 0; k < 2; ++k) cudaEventDestroy(ctx->ev[i][k]);
@@ -560,6 +559,16 @@ int vx_get_timings(vx_ctx* ctx, vx_timings* out) {
         VX_CUDA(cudaSetDevice(ctx->device));
         int st = sync_stream(ctx);
         if (st != VX_OK) return st;
+    }
+    if (ctx->gen_counters_pending) {  // of the most recent vx_generate
+        unsigned long long n[6];
+        VX_CUDA(cudaMemcpy(n, ctx->d_gen_counters.p, sizeof n, cudaMemcpyDeviceToHost));
+        ctx->timings.cave_columns = (uint32_t)n[0];
+        ctx->timings.simplex2_evals = n[2];
+        ctx->timings.cave_voxels = n[4];
+        ctx->timings.simplex3_evals = n[3] + n[5];  // surface noise + cave octaves actually evaluated
+        ctx->timings.cave_evals = n[5];
+        ctx->gen_counters_pending = false;
     }
     *out = ctx->timings;
     ctx->timings = vx_timings{};
@@ -619,11 +628,8 @@ int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out
     ctx->last_gen_version = ctx->index_version;  // d_gen_jobs now holds exactly this list
     if (voxels_out && (st = copy_slots(ctx, slots, n, ctx->d_voxels, VOXELS_IN_AREA, voxels_out, true)) != VX_OK) return st;
     if (max_height_out && (st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, max_height_out, true)) != VX_OK) return st;
-    if (ctx->timing) {  // work accounting of this call (the roofline numerators)
-        VX_CUDA(ctx->h_gen_counters.ensure(64));
-        VX_CUDA(cudaMemcpyAsync(ctx->h_gen_counters.p, ctx->d_counters.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->gen_counters_pending = true;
-    }
+    // work accounting of this call (the roofline numerators): fetched when the timings are read
+    if (ctx->timing) ctx->gen_counters_pending = true;
     // Without host outputs there is nothing to wait for: the areas are resident in stream order,
     // and whatever reads or changes them next is enqueued behind the kernels.  Errors of the
     // kernels then surface in that later call (or in vx_sync).
@@ -769,7 +775,7 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
             out.recs = ctx->d_recs.as<uint4>();
             out.vertices = ctx->d_vertices.as<uint4>();
             out.indices = ctx->d_indices.as<uint32_t>();
-            ScopedTimer t(ctx, TM_MESH_EMIT);
+            ScopedTimer t(ctx, TM_MESH_EMIT, TM_MESH_COUNT);
             launch_mesh_emit(ctx->d_jobs.as<uint4>(), ctx->d_mesh_nbr.as<uint4>(), n, ctx->d_voxels, ctx->d_planes,
                              ctx->d_warp_totals.as<uint32_t>(), out, cap_faces, cap_recs, ctx->stream);
             ctx->timings.mesh_launches += 1;
@@ -790,7 +796,8 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
                                   ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(),
                                   ctx->d_warp_totals.as<uint32_t>(), ctx->stream);
                 launch_mesh_offsets(ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), n,
-                                    ctx->d_rec_first.as<uint32_t>(), ctx->d_face_first.as<uint32_t>(), ctx->stream);
+                                    ctx->d_rec_first.as<uint32_t>(), ctx->d_face_first.as<uint32_t>(), counters + 2,
+                                    ctx->stream);
             }
             ctx->timings.mesh_launches += 2;
             // Emit goes out right behind the scan, before the host knows the totals: it backs off
@@ -799,9 +806,7 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
             arena_caps(cap_faces, cap_recs);
             if (cap_faces && cap_recs) launch_emit(cap_faces, cap_recs);
             VX_CUDA(cudaGetLastError());
-            VX_CUDA(cudaMemcpyAsync(&back[0], counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            VX_CUDA(cudaMemcpyAsync(&back[2], ctx->d_rec_first.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-            VX_CUDA(cudaMemcpyAsync(&back[3], ctx->d_face_first.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            VX_CUDA(cudaMemcpyAsync(&back[0], counters, 16, cudaMemcpyDeviceToHost, ctx->stream));  // + the scan's totals
             VX_CUDA(cudaStreamSynchronize(ctx->stream));
             VX_CUDA(cudaGetLastError());
             collect_timers(ctx);

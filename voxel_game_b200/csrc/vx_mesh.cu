@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict
 __global__ void __launch_bounds__(1024) mesh_offsets_kernel(const uint32_t* __restrict__ rec_count,
                                                             const uint32_t* __restrict__ face_count,
                                                             int n, uint32_t* __restrict__ rec_first,
-                                                            uint32_t* __restrict__ face_first) {
+                                                            uint32_t* __restrict__ face_first,
+                                                            uint32_t* __restrict__ totals) {
     __shared__ uint32_t s_r[32], s_f[32];
     __shared__ uint32_t carry_r, carry_f;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -368,6 +369,8 @@ __global__ void __launch_bounds__(1024) mesh_offsets_kernel(const uint32_t* __re
     if (tid == 0) {
         rec_first[n] = carry_r;
         face_first[n] = carry_f;
+        totals[0] = carry_r;  // next to the host's other counters: one copy brings everything back
+        totals[1] = carry_f;
     }
 }
 
@@ -688,9 +691,9 @@ void launch_mesh_count(const uint4* jobs, const uint4* nbr, int n, const uint8_t
                                              face_count, warp_totals);
 }
 
-void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, int n,
-                         uint32_t* rec_first, uint32_t* face_first, cudaStream_t stream) {
-    mesh_offsets_kernel<<<1, 1024, 0, stream>>>(rec_count, face_count, n, rec_first, face_first);
+void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, int n, uint32_t* rec_first,
+                         uint32_t* face_first, uint32_t* totals, cudaStream_t stream) {
+    mesh_offsets_kernel<<<1, 1024, 0, stream>>>(rec_count, face_count, n, rec_first, face_first, totals);
 }
 
 void launch_mesh_emit(const uint4* jobs, const uint4* nbr, int n, const uint8_t* pool_voxels,
