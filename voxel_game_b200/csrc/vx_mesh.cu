@@ -508,8 +508,8 @@ __device__ __forceinline__ void build_half_face(uint4* dst, const FaceParts& p, 
 
 // Write `count` buffered faces (descriptors sm.list[0..count)) starting at stream face `first`.
 // Each warp works on its own: 16 faces are assembled in the warp's staging tile by lane pairs, then
-// the tile leaves as 160 consecutive 16-byte pieces; no CTA barrier is involved.  (One lane per
-// face with 80-byte half tiles needs fewer instructions but writes partial sectors: measured slower.)
+// the tile leaves as one TMA bulk copy; no CTA barrier is involved.  (One lane per face with
+// 80-byte half tiles needs fewer instructions but writes partial sectors: measured slower.)
 __device__ __forceinline__ void flush_faces(EmitSmem& sm, uint32_t count, uint32_t first,
                                             const MeshOut& out, uint32_t gx0, uint32_t gy0, int tid) {
     const int lane = tid & 31, wid = tid >> 5;
@@ -522,13 +522,19 @@ __device__ __forceinline__ void flush_faces(EmitSmem& sm, uint32_t count, uint32
             const FaceParts p = decode_face(sm.list[base + f], gx0, gy0);
             build_half_face(&tile[f * FACE_U4 + (lane & 1) * HALF_U4], p, lane & 1);
         }
+        // The tile leaves through the TMA unit as one bulk copy (shared -> global, up to 2 560 B):
+        // the writers make their shared-memory stores visible to the async proxy, one lane issues
+        // the copy and waits only until the tile has been READ -- the global writes drain behind
+        // the warp's back while it assembles the next 16 faces.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        uint4* vdst = out.vertices + (size_t)(first + base) * FACE_U4;
-        if (nfaces == WARP_FACES) {
-#pragma unroll
-            for (int it = 0; it < WARP_FACES * FACE_U4 / 32; ++it) vdst[it * 32 + lane] = tile[it * 32 + lane];
-        } else {
-            for (uint32_t w = lane; w < nfaces * FACE_U4; w += 32) vdst[w] = tile[w];
+        if (lane == 0) {
+            const uint4* vdst = out.vertices + (size_t)(first + base) * FACE_U4;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(vdst), "r"((uint32_t)__cvta_generic_to_shared(tile)), "r"(nfaces * (FACE_U4 * 16u))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         __syncwarp();
     }
