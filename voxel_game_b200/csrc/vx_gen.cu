@@ -689,12 +689,37 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
     if (tid < 32) place_trees(vox, s_tree, tid);
     __syncthreads();
 
-    // update_all_column_heights (area.rs:34-56). Everything above min_z - 7 is still None.
-    int zz = s_min_z - 8;
-    if (zz < 0) zz = 0;
-    while (zz < AREA_HEIGHT && is_transparent(vox[tid + 256 * zz])) ++zz;
-    heights[tid] = (uint8_t)(zz < AREA_HEIGHT ? zz : AREA_HEIGHT - 1);
-    planes_of_area(vox, pool_planes + (size_t)slot * (VOXELS_IN_AREA / 8), tid);
+    // Column heights (update_all_column_heights, area.rs:34-56) and bit planes in one walk, as in K1.
+    // Everything above min_z - 7 is still None; zi <= ALWAYS_STONE_ZI is Stone in every column of
+    // every area (the lowest surface is 32, the deepest lake bed 34 - 10; caves start at zi = 25).
+    constexpr int ALWAYS_STONE_ZI = 23;
+    static_assert(ALWAYS_STONE_ZI < (int)CAVE_MIN_ZI && ALWAYS_STONE_ZI <= 32 - 4 && ALWAYS_STONE_ZI <= (int)LAKE_TOP_ZI - 10 - 1, "");
+    const int z_lo = max(s_min_z - 8, 0), z_hi = AREA_HEIGHT - ALWAYS_STONE_ZI;
+    uint16_t* planes = pool_planes + (size_t)slot * (VOXELS_IN_AREA / 8);
+    {
+        const int zt = tid >> 1;  // thread i owns rows 8i .. 8i+7 = half of slab z = i / 2
+        if (zt < z_lo || zt >= z_hi) {
+            const uint32_t sv = zt < z_lo ? 0u : 0xFFFFFFFFu;
+            reinterpret_cast<uint4*>(planes)[tid] = make_uint4(sv, sv, sv, sv);
+            reinterpret_cast<uint4*>(planes + VOXELS_IN_AREA / 16)[tid] = make_uint4(~sv, ~sv, ~sv, ~sv);
+        }
+    }
+    const int wid = tid >> 5;
+    uint32_t* s_words = reinterpret_cast<uint32_t*>(planes) + wid;
+    uint32_t* t_words = reinterpret_cast<uint32_t*>(planes + VOXELS_IN_AREA / 16) + wid;
+    int top = z_hi;  // first z from the top that is not transparent
+    for (int zz = z_hi - 1; zz >= z_lo; --zz) {
+        const unsigned vv = vox[tid + 256 * zz];
+        const bool transparent = is_transparent(vv);
+        const unsigned sb = __ballot_sync(0xFFFFFFFFu, vv != 0u);
+        const unsigned tb = __ballot_sync(0xFFFFFFFFu, transparent);
+        if (!transparent) top = zz;
+        if ((tid & 31) == 0) {  // rows r = 16 z + 2 wid and r + 1 are one 32-bit word
+            s_words[8 * zz] = sb;
+            t_words[8 * zz] = tb;
+        }
+    }
+    heights[tid] = (uint8_t)top;
     // trees only touch the slabs from min_z - 8 down to the surface; write those back
     const int first_row = max(s_min_z - 8, 0) * 16;
     for (int i = first_row + tid; i < VOXELS_IN_AREA / 16; i += 256) area[i] = s_vox[i];

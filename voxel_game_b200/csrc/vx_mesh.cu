@@ -576,12 +576,24 @@ __global__ void __launch_bounds__(256, 5) mesh_emit_kernel(const uint4* __restri
     const uint32_t rec_base = out.rec_first[blockIdx.x];
     uint2 w2 = make_uint2(0u, 0u);
     if (wid == 0) w2 = reinterpret_cast<const uint2*>(warp_totals + (size_t)blockIdx.x * (CHUNKS * 8))[lane];
+    // this warp's own (chunk, warp) totals, lane c = chunk c: which voxel rows phase A will read
+    const uint32_t my_total = lane < CHUNKS ? warp_totals[(size_t)blockIdx.x * (CHUNKS * 8) + lane * 8 + wid] : 0u;
     // launched speculatively right behind the offsets scan: if the stream does not fit the arena
     // the whole grid backs off and the host, which sees the totals afterwards, enlarges it and
     // launches again
     if (stream_faces > cap_faces || stream_recs > cap_recs) return;
     const AreaView a = make_view(job, nb, pool_voxels, pool_planes);
     const uint32_t gx0 = job.x * AREA_SIZE, gy0 = job.y * AREA_SIZE;
+    {   // The voxel rows of the busy groups are requested into L2 together with the planes: phase A
+        // would otherwise start a third dependent round trip to HBM (32 rows = four 128-byte lines).
+        uint32_t busy = __ballot_sync(0xFFFFFFFFu, my_total != 0u);
+        while (busy) {
+            const int c = __ffs(busy) - 1;
+            busy &= busy - 1;
+            if ((lane & 7) == 0)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(a.vox + (size_t)(c * 256 + tid) * 16));
+        }
+    }
     load_plane_tile(sm.planes, a, tid);
     if (wid == 0) {  // running sums of the 64 (chunk, warp) totals, two per lane
         const unsigned long long t0 = widen(w2.x), t1 = widen(w2.y);
