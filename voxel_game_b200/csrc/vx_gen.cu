@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
     const uint4 job = jobs[blockIdx.x];
     const uint32_t ax = job.x, ay = job.y, slot = job.z;
 
-    load_noise_shared(&sm.noise, nt, tid, 256);
+    load_noise_shared<FBM_TABLE<FBM_ALT>>(&sm.noise, nt, tid, 256);
     if (tid == 0) {
         sm.cave_n = 0;
         sm.evals[0] = sm.evals[1] = 0;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
     __syncthreads();
 
     const NoiseShared* s = &sm.noise;
-    const unsigned sb = smem_address(sm.noise.bytes);
+    const unsigned sb = smem_address(sm.noise.bytes), sg = smem_address(sm.noise.grad3);
     uint8_t* vox = reinterpret_cast<uint8_t*>(sm.vox);
     const unsigned x = tid & 15, y = tid >> 4;
     // algorithms.rs:12-17: u32 sum, then cast
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
             const FbmParams& q = nt.fbm[FBM_ALT];
             double x3 = px * q.frequency, y3 = py * q.frequency, z3 = (double)zi * q.frequency;
             double acc = 0.0;
-            acc += q.amp[0] * simplex3<FBM_TABLE<FBM_ALT>>(sb, x3, y3, z3);
+            acc += q.amp[0] * simplex3<FBM_TABLE<FBM_ALT>>(sb, sg, x3, y3, z3);
             evals3 += 1;
             const double mid = acc * q.norm, rest = SIMPLEX_BOUND * q.amp[1] * q.norm + 1e-9;
             if (normalise(mid - rest) - 1e-9 >= threshold) {
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
                 alt = false;
             } else {
                 x3 *= q.lacunarity; y3 *= q.lacunarity; z3 *= q.lacunarity;
-                acc += q.amp[1] * simplex3<FBM_TABLE<FBM_ALT>>(sb, x3, y3, z3);
+                acc += q.amp[1] * simplex3<FBM_TABLE<FBM_ALT>>(sb, sg, x3, y3, z3);
                 evals3 += 1;
                 alt = normalise(acc * q.norm) >= threshold;
             }
@@ -489,7 +489,8 @@ struct CaveWarp {  // per-warp description of the claimed chunk
     uint2 origin[CAVE_CHUNK];        // global x, y of the column
 };
 struct CaveSmem {
-    alignas(16) uint8_t bytes[3 * TAB_BYTES];  // permutation tables and their reduced copies (vx_noise.cuh)
+    alignas(16) uint8_t bytes[TAB_BYTES];       // the (doubled) permutation tables (vx_noise.cuh)
+    NoiseImage::Code grad3[2][TAB_STRIDE];      // 3-D gradient codes of the two cave tables
     double amp[2][8];              // [0] = noise1, [1] = noise2: running amplitudes
     double rest[2][9];             // bound of the octaves not yet evaluated (cave_rest) + slack
     CaveWarp warp[8];
@@ -523,7 +524,9 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
     const int tid = threadIdx.x, lane = tid & 31;
     const FbmParams& q1 = nt.fbm[FBM_CAVE1];
     const FbmParams& q2 = nt.fbm[FBM_CAVE2];
-    load_noise_image(sm.bytes, nt, 3 * TAB_BYTES, tid, 256);
+    static_assert(FBM_TABLE<FBM_CAVE1> == 0 && FBM_TABLE<FBM_CAVE2> == 1, "grad3[0..1] are the cave tables");
+    load_noise_image(sm.bytes, nt, 0, TAB_BYTES, tid, 256);
+    load_noise_image(sm.grad3, nt, (unsigned)offsetof(NoiseImage, grad3), (unsigned)sizeof(sm.grad3), tid, 256);
     if (tid < 8) {
         sm.amp[0][tid] = tid < 6 ? q1.amp[tid] : 0.0;
         sm.amp[1][tid] = q2.amp[tid];
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
     const uint32_t n_items = *cave_count;
     const double f1 = q1.frequency, f2 = q2.frequency, l1 = q1.lacunarity, l2 = q2.lacunarity;
     const double n1 = q1.norm, n2 = q2.norm;
-    const unsigned sb = smem_address(sm.bytes);
+    const unsigned sb = smem_address(sm.bytes), sg1 = smem_address(sm.grad3[0]), sg2 = smem_address(sm.grad3[1]);
     CaveWarp& cw = sm.warp[tid >> 5];
     unsigned* chunk_counter = reinterpret_cast<unsigned*>(&stats[4]);
     const unsigned lanes_below = (1u << lane) - 1u;
@@ -617,12 +620,12 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
             // one octave of each Fbm per round (noise1 has 6, noise2 has 8): no per-lane selection
             // of coordinates, and two independent evaluations in flight
             const unsigned k = step;
-            const double svb = simplex3<FBM_TABLE<FBM_CAVE2>>(sb, xb, yb, zb);
+            const double svb = simplex3<FBM_TABLE<FBM_CAVE2>>(sb, sg2, xb, yb, zb);
             bsum += sm.amp[1][k] * svb;
             xb *= l2; yb *= l2; zb *= l2;
             ++my_evals;
             if (k < 6) {
-                const double sva = simplex3<FBM_TABLE<FBM_CAVE1>>(sb, xa, ya, za);
+                const double sva = simplex3<FBM_TABLE<FBM_CAVE1>>(sb, sg1, xa, ya, za);
                 a += sm.amp[0][k] * sva;
                 xa *= l1; ya *= l1; za *= l1;
                 ++my_evals;

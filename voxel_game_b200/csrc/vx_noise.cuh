@@ -23,6 +23,7 @@
 // Tables are addressed as uniform shared-memory pointer + per-lane index, never through a
 // selected pointer, so every lookup is one LDS with the table base in a uniform register.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 #include "vx_tables.hpp"
@@ -36,8 +37,14 @@ namespace vx {
 // copy is 216 coalesced 16-byte loads per CTA.
 constexpr unsigned TAB_BYTES = TAB_COUNT * TAB_STRIDE;
 constexpr unsigned OFF_P24 = TAB_BYTES;      // byte offset of the % 24 copies
-constexpr unsigned OFF_P12 = 2 * TAB_BYTES;  // byte offset of the % 12 copies
-using NoiseShared = NoiseImage;
+// K1's copy: everything 2-D noise reads plus the 3-D gradient codes of ONE table (the surface
+// noise's); the leading members mirror NoiseImage
+struct alignas(16) NoiseShared {
+    uint8_t bytes[2 * TAB_BYTES];
+    double grad2[24][2];
+    NoiseImage::Code grad3[TAB_STRIDE];
+};
+static_assert(offsetof(NoiseImage, grad3) == offsetof(NoiseShared, grad3), "image and shared copy share the 2-D part");
 
 // Numeric constants whose low word is not zero cannot be FP64 immediates; as literals ptxas
 // re-materialises each of them with two moves per use.  From the constant bank they are plain
@@ -53,16 +60,19 @@ __constant__ double c_noise_k[8] = {
     76.88375854620836,        // 7: 3-D normalisation
 };
 
-// first `bytes` bytes of the image (a multiple of 16): the cave kernel only needs the tables
-__device__ __forceinline__ void load_noise_image(void* dst, const NoiseTables& nt, unsigned bytes, int tid,
-                                                 int nthreads) {
-    const uint4* src = static_cast<const uint4*>(nt.image);
+// `bytes` bytes (a multiple of 16) of the image, from byte `offset` on
+__device__ __forceinline__ void load_noise_image(void* dst, const NoiseTables& nt, unsigned offset, unsigned bytes,
+                                                 int tid, int nthreads) {
+    const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(nt.image) + offset);
     for (unsigned i = tid; i < bytes / 16u; i += nthreads) static_cast<uint4*>(dst)[i] = __ldg(src + i);
 }
 
-__device__ __forceinline__ void load_noise_shared(NoiseShared* s, const NoiseTables& nt, int tid,
-                                                  int nthreads) {
-    load_noise_image(s, nt, (unsigned)sizeof(NoiseImage), tid, nthreads);
+// GRAD3_TABLE = the table whose 3-D gradient codes the kernel needs
+template <int GRAD3_TABLE>
+__device__ __forceinline__ void load_noise_shared(NoiseShared* s, const NoiseTables& nt, int tid, int nthreads) {
+    load_noise_image(s, nt, 0, (unsigned)offsetof(NoiseShared, grad3), tid, nthreads);
+    load_noise_image(s->grad3, nt, (unsigned)(offsetof(NoiseImage, grad3) + GRAD3_TABLE * sizeof(s->grad3)),
+                     (unsigned)sizeof(s->grad3), tid, nthreads);
 }
 
 // floor(x) as a double and as an int, |x| < 2^31, in two FP64 adds and nothing else: adding
@@ -120,17 +130,22 @@ __device__ __forceinline__ double simplex2(const NoiseShared* s, double x, doubl
     return sum * c_noise_k[3];
 }
 
-// gradient gi (0..11) of the edge-midpoint set
-//   0..3: (+-1,+-1,0)   4..7: (+-1,0,+-1)   8..11: (0,+-1,+-1); bit0 negates the first non-zero
-//   component, bit1 the second
-__device__ __forceinline__ double flip_sign(double v, unsigned sign_bit31) {
-    return __hiloint2double(__double2hiint(v) ^ (int)sign_bit31, __double2loint(v));
+// prmt.b32 in its default mode reads selector bits 0..15 only (__byte_perm would mask them first)
+__device__ __forceinline__ unsigned prmt(int lo, int hi, unsigned selector) {
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(selector));
+    return d;
 }
-__device__ __forceinline__ void corner3(double x, double y, double z, unsigned gi, double& sum) {
+
+// One corner of the 3-D simplex; e = gradient code of the corner's hash (vx_tables.hpp): the dot
+// product with an edge-midpoint gradient is +-a +-b, a in {x, y}, b in {y, z}, picked word by word
+// with the code's byte-permute selector and signed with its top bit.
+__device__ __forceinline__ void corner3(double x, double y, double z, uint2 e, double& sum) {
     const double t = clamp_radius(0.5 - x * x - y * y - z * z);
-    const unsigned grp = gi >> 2;
-    const double a = flip_sign(grp == 2u ? y : x, gi << 31);
-    const double b = flip_sign(grp == 0u ? y : z, (gi << 30) & 0x80000000u);
+    const double a = __hiloint2double((int)(prmt(__double2hiint(x), __double2hiint(y), e.x) ^ (e.x & 0x80000000u)),
+                                      (int)prmt(__double2loint(x), __double2loint(y), e.x));
+    const double b = __hiloint2double((int)(prmt(__double2hiint(y), __double2hiint(z), e.y) ^ (e.y & 0x80000000u)),
+                                      (int)prmt(__double2loint(y), __double2loint(z), e.y));
     const double d = a + b;
     const double t2 = t * t;
     sum += t2 * t2 * d;
@@ -144,16 +159,22 @@ __device__ __forceinline__ unsigned lds_u8(unsigned addr) {
     asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
     return v;
 }
+template <int OFF>
+__device__ __forceinline__ uint2 lds_u32x2(unsigned addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(OFF));
+    return v;
+}
 __device__ __forceinline__ unsigned smem_address(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// sb = shared-memory address of the table image (256-byte aligned, so that "sb | coordinate & 255"
-// is one logic instruction), TABLE = which (doubled) permutation table of it; the % 12 copy sits
-// OFF_P12 bytes further.  Indices are sums of table bytes and coordinates reduced to 8 bits (at
-// most 255 + 255 + 1), which the doubled table serves without masking -- the crate's own
+// sb = shared-memory address of the permutation tables (256-byte aligned, so that
+// "sb | coordinate & 255" is one logic instruction), TABLE = which (doubled) table; sg = address of
+// that table's 3-D gradient codes.  Indices are sums of table bytes and coordinates reduced to 8
+// bits (at most 255 + 255 + 1), which the doubled tables serve without masking -- the crate's own
 // arrangement: one add and one load per lookup.
 template <int TABLE>
-__device__ __forceinline__ double simplex3(unsigned sb, double x, double y, double z) {
-    constexpr int T = TABLE * (int)TAB_STRIDE, G = T + (int)OFF_P12;
+__device__ __forceinline__ double simplex3(unsigned sb, unsigned sg, double x, double y, double z) {
+    constexpr int T = TABLE * (int)TAB_STRIDE;
     const double SKEW = c_noise_k[4], UNSKEW = c_noise_k[5], UNSKEW_2 = c_noise_k[6];
     const double sk = (x + y + z) * SKEW;
     int i, j, k;
@@ -171,12 +192,19 @@ __device__ __forceinline__ double simplex3(unsigned sb, double x, double y, doub
     const double x1 = (i1 ? xm : x0) + UNSKEW, y1 = (j1 ? ym : y0) + UNSKEW, z1 = (k1 ? zm : z0) + UNSKEW;
     const double x2 = (i2 ? xm : x0) + UNSKEW_2, y2 = (j2 ? ym : y0) + UNSKEW_2, z2 = (k2 ? zm : z0) + UNSKEW_2;
     const double x3 = xm + 0.5, y3 = ym + 0.5, z3 = zm + 0.5;  // 3.0 * UNSKEW == 0.5 exactly
-    const unsigned ib = sb | ((unsigned)i & 255u), jb = sb | ((unsigned)j & 255u), kb = sb | ((unsigned)k & 255u);
+    const unsigned ib = sb | ((unsigned)i & 255u), jb = sb | ((unsigned)j & 255u);
+    unsigned kg = sg + ((unsigned)k & 255u) * 8u;  // 8-byte codes
+    asm("" : "+r"(kg));                            // kept as one value: "kg + 8 * hash" is one shift-add
     const unsigned pi0 = lds_u8<T>(ib), pi1 = lds_u8<T + 1>(ib);
-    const unsigned h0 = lds_u8<G>(kb + lds_u8<T>(jb + pi0));
-    const unsigned h1 = lds_u8<G>(kb + lds_u8<T>(jb + (i1 ? pi1 : pi0) + (j1 ? 1u : 0u)) + (k1 ? 1u : 0u));
-    const unsigned h2 = lds_u8<G>(kb + lds_u8<T>(jb + (i2 ? pi1 : pi0) + (j2 ? 1u : 0u)) + (k2 ? 1u : 0u));
-    const unsigned h3 = lds_u8<G + 1>(kb + lds_u8<T + 1>(jb + pi1));
+    // a step along j or k is the load's constant offset, chosen by predicate
+    const unsigned a1 = jb + (i1 ? pi1 : pi0), a2 = jb + (i2 ? pi1 : pi0);
+    const unsigned q0 = lds_u8<T>(jb + pi0), q1 = j1 ? lds_u8<T + 1>(a1) : lds_u8<T>(a1);
+    const unsigned q2 = j2 ? lds_u8<T + 1>(a2) : lds_u8<T>(a2), q3 = lds_u8<T + 1>(jb + pi1);
+    const unsigned g1 = kg + q1 * 8u, g2 = kg + q2 * 8u;
+    const uint2 h0 = lds_u32x2<0>(kg + q0 * 8u);
+    const uint2 h1 = k1 ? lds_u32x2<8>(g1) : lds_u32x2<0>(g1);
+    const uint2 h2 = k2 ? lds_u32x2<8>(g2) : lds_u32x2<0>(g2);
+    const uint2 h3 = lds_u32x2<8>(kg + q3 * 8u);
     double sum = 0.0;
     corner3(x0, y0, z0, h0, sum);
     corner3(x1, y1, z1, h1, sum);
@@ -210,7 +238,7 @@ __device__ __forceinline__ double fbm3(const NoiseTables& nt, const NoiseShared*
     double acc = 0.0;
 #pragma unroll 1
     for (int o = 0; o < q.octaves; ++o) {
-        acc += q.amp[o] * simplex3<FBM_TABLE<ID>>(smem_address(s->bytes), x, y, z);
+        acc += q.amp[o] * simplex3<FBM_TABLE<ID>>(smem_address(s->bytes), smem_address(s->grad3), x, y, z);
         x *= q.lacunarity;
         y *= q.lacunarity;
         z *= q.lacunarity;

@@ -162,9 +162,16 @@ void build_noise_image(const NoiseTables& tables, NoiseImage* out) {
         const unsigned v = tables.perm[i / TAB_STRIDE][i & 255u];
         out->bytes[i] = (uint8_t)v;
         out->bytes[n + i] = (uint8_t)(v % 24u);
-        out->bytes[2 * n + i] = (uint8_t)(v % 12u);
     }
     std::memcpy(out->grad2, GRAD2, sizeof GRAD2);
+    // gradient gi = perm % 12 of the edge-midpoint set: 0..3 (+-1,+-1,0), 4..7 (+-1,0,+-1),
+    // 8..11 (0,+-1,+-1); bit 0 negates the first non-zero component, bit 1 the second
+    for (int t = 0; t < GRAD3_TABLES; ++t)
+        for (unsigned i = 0; i < TAB_STRIDE; ++i) {
+            const unsigned gi = tables.perm[t][i & 255u] % 12u, grp = gi >> 2;
+            out->grad3[t][i].x = (grp == 2u ? 0x7654u : 0x3210u) | ((gi & 1u) << 31);
+            out->grad3[t][i].y = (grp == 0u ? 0x3210u : 0x7654u) | (((gi >> 1) & 1u) << 31);
+        }
 }
 
 uint64_t hash_world_name(const char* name) {

@@ -55,13 +55,20 @@ struct NoiseTables {
 };
 
 // What the kernels keep in shared memory, byte for byte: the four permutation tables, doubled to
-// 512 entries (entry i = perm[i & 255], the crate's arrangement), their "% 24" and "% 12" copies
-// (the last lookup of a 2-D / 3-D corner only feeds that remainder), and the 24 2-D gradients.
-// bytes = perm (4 x 512) | perm % 24 (4 x 512) | perm % 12 (4 x 512).
+// 512 entries (entry i = perm[i & 255], the crate's arrangement), their "% 24" copies (the last
+// lookup of a 2-D corner only feeds that remainder), the 24 2-D gradients, and for the three
+// tables that 3-D noise reads the 3-D gradient CODE of every entry: the last lookup of a 3-D
+// corner only feeds "% 12", i.e. one of the 12 edge-midpoint gradients, and g . (x, y, z) for such
+// a gradient is +-a +-b with a in {x, y}, b in {y, z}.  A code is two words
+//   .x = byte-permute selector of a (0x3210: x, 0x7654: y) | sign of a << 31
+//   .y = byte-permute selector of b (0x3210: y, 0x7654: z) | sign of b << 31
+// so a corner picks and signs its two terms without a compare.
 constexpr unsigned TAB_STRIDE = 512;
+constexpr int GRAD3_TABLES = 3;  // TAB_SEED, TAB_NOT_SEED, TAB_SEED_PLUS_1
 struct alignas(16) NoiseImage {
-    uint8_t bytes[3 * TAB_COUNT * TAB_STRIDE];
+    uint8_t bytes[2 * TAB_COUNT * TAB_STRIDE];  // perm (4 x 512) | perm % 24 (4 x 512)
     double grad2[24][2];
+    struct Code { uint32_t x, y; } grad3[GRAD3_TABLES][TAB_STRIDE];
 };
 
 // |simplex3| <= 1.00004 for this gradient set and normalisation constant (1/76.8808 is the true
