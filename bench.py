@@ -276,6 +276,7 @@ def main():
         ctx.set_timing(True)
         for _ in range(3):
             vis = ctx.visible(view, read=False)
+        ctx.timings()  # clears the accumulators
         f_ms = 0.0
         for _ in range(10):
             vis = ctx.visible(view, read=False)

@@ -13,7 +13,7 @@ for l in sys.stdin:
     if l.startswith('{'):
         d = json.loads(l)
         k = d['kernel_ms_per_step']
-        print('$v', 'ms/step %.4f' % d['ms_per_step'], ' '.join('%s=%.4f' % (a.replace('_ms', ''), b) for a, b in k.items()), 'clk', d['clocks']['sm_mhz'])
+        print('$v', 'e2e %.0f (%.2f ms)' % (d['e2e']['value'], d['e2e']['ms_per_step']), 'ms/step %.4f' % d['ms_per_step'], ' '.join('%s=%.4f' % (a.replace('_ms', ''), b) for a, b in k.items()), 'clk', d['clocks']['sm_mhz'])
 "
   done
 done | tee gpurun_out/ab.log

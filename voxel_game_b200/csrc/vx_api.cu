@@ -163,6 +163,8 @@ struct vx_ctx {
     PinnedBuf h_small;   // small results coming back
     bool gen_counters_pending = false;  // d_counters holds the work counters of a timed vx_generate
     cudaEvent_t stage_ev = nullptr;  // h_stage has been consumed by the copy enqueued from it
+    uint32_t* h_totals = nullptr;    // mapped pinned words the mesh scan writes for the host (vx_mesh)
+    cudaEvent_t totals_ev = nullptr;
     bool stage_pending = false;
     DevBuf d_jobs, d_gen_jobs, d_list, d_missing, d_cave_items, d_counters, d_rec_count, d_face_count;
     DevBuf d_gen_counters;  // cave work list size + work accounting of vx_generate; no other call touches it
@@ -185,6 +187,7 @@ struct vx_ctx {
     bool timing = false;
     cudaEvent_t ev[TM_COUNT][2] = {};
     cudaEvent_t ev_start[TM_COUNT] = {};  // ev[id][0], or the end event of the timer it follows directly
+    int ev_parent[TM_COUNT] = {};         // that timer (-1: none)
     bool ev_used[TM_COUNT] = {};
     vx_timings timings{};
 };
@@ -225,6 +228,17 @@ void collect_timer(vx_ctx* c, int id) {
     c->ev_used[id] = false;
 }
 
+// Before the events of timer `id` are recorded again: wait for its pending measurement and for the
+// pending measurements that start at its end event, and add them to the accumulators.
+void settle_timer(vx_ctx* c, int id) {
+    for (int j = 0; j < TM_COUNT; ++j)
+        if (j != id && c->ev_used[j] && c->ev_parent[j] == id) settle_timer(c, j);
+    if (c->ev_used[id]) {
+        cudaEventSynchronize(c->ev[id][1]);
+        collect_timer(c, id);
+    }
+}
+
 // Timings accumulate from one vx_get_timings to the next.  A pair recorded by a call that returned
 // without waiting (vx_generate without host outputs) stays pending until the next synchronisation.
 // `follows` = a timer whose scope closed immediately before this one opens (nothing else went
@@ -235,15 +249,14 @@ struct ScopedTimer {
     int id;
     ScopedTimer(vx_ctx* ctx, int which, int follows = -1) : c(ctx), id(which) {
         if (c->timing) {
-            if (c->ev_used[id]) {  // still pending from an earlier call: settle it before reuse
-                cudaEventSynchronize(c->ev[id][1]);
-                collect_timer(c, id);
-            }
+            settle_timer(c, id);  // whatever is still pending from a call that did not wait
             if (follows >= 0 && c->ev_used[follows]) {
                 c->ev_start[id] = c->ev[follows][1];
+                c->ev_parent[id] = follows;
             } else {
                 cudaEventRecord(c->ev[id][0], c->stream);
                 c->ev_start[id] = c->ev[id][0];
+                c->ev_parent[id] = -1;
             }
             c->ev_used[id] = true;
         }
@@ -498,6 +511,12 @@ int vx_create(int device, vx_ctx** out) {
     for (int i = 0; i < TM_COUNT; ++i)
         for (int k = 0; k < 2; ++k) cudaEventCreate(&ctx->ev[i][k]);
     cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->totals_ev, cudaEventDisableTiming);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_totals), 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        vx_destroy(ctx);
+        return VX_ERR_CUDA;
+    }
     *out = ctx;
     return VX_OK;
 }
@@ -519,6 +538,8 @@ void vx_destroy(vx_ctx* ctx) {
     ctx->h_stage.release();
     ctx->h_small.release();
     cudaEventDestroy(ctx->stage_ev);
+    cudaEventDestroy(ctx->totals_ev);
+    if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     for (int i = 0; i < TM_COUNT; ++i)
         for (int k = 0; k < 2; ++k) cudaEventDestroy(ctx->ev[i][k]);
     cudaStreamDestroy(ctx->own_stream);
@@ -762,7 +783,7 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
             ctx->last_mesh_version = ~0ull;
         }
         uint32_t* counters = ctx->d_counters.as<uint32_t>();
-        uint32_t* back = ctx->h_small.as<uint32_t>();  // [0] missing self, [1] missing nbrs, [2] recs, [3] faces
+        const volatile uint32_t* back = ctx->h_totals;  // [0] missing self, [1] missing nbrs, [2] recs, [3] faces
         uint64_t n_recs = 0, n_faces = 0;
         auto arena_caps = [&](uint32_t& cap_faces, uint32_t& cap_recs) {
             cap_faces = (uint32_t)std::min<uint64_t>(std::min(ctx->d_vertices.cap / 160, ctx->d_indices.cap / 12), 0xFFFFFFFFull);
@@ -796,26 +817,30 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
                                   ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(),
                                   ctx->d_warp_totals.as<uint32_t>(), ctx->stream);
                 launch_mesh_offsets(ctx->d_rec_count.as<uint32_t>(), ctx->d_face_count.as<uint32_t>(), n,
-                                    ctx->d_rec_first.as<uint32_t>(), ctx->d_face_first.as<uint32_t>(), counters + 2,
-                                    ctx->stream);
+                                    ctx->d_rec_first.as<uint32_t>(), ctx->d_face_first.as<uint32_t>(), counters,
+                                    ctx->h_totals, ctx->stream);
             }
             ctx->timings.mesh_launches += 2;
             // Emit goes out right behind the scan, before the host knows the totals: it backs off
-            // by itself if the stream does not fit the arena kept from earlier calls.
+            // by itself if the stream does not fit the arena kept from earlier calls.  The host waits
+            // for the scan only; in the common case it returns while emit is still running, and
+            // whatever the caller enqueues next (vx_mesh_read, the next vx_generate) lines up behind it.
+            VX_CUDA(cudaEventRecord(ctx->totals_ev, ctx->stream));
             uint32_t cap_faces, cap_recs;
             arena_caps(cap_faces, cap_recs);
             if (cap_faces && cap_recs) launch_emit(cap_faces, cap_recs);
             VX_CUDA(cudaGetLastError());
-            VX_CUDA(cudaMemcpyAsync(&back[0], counters, 16, cudaMemcpyDeviceToHost, ctx->stream));  // + the scan's totals
-            VX_CUDA(cudaStreamSynchronize(ctx->stream));
-            VX_CUDA(cudaGetLastError());
-            collect_timers(ctx);
-            if (back[0] != 0) return fail(ctx, VX_ERR_NOT_LOADED, "vx_mesh: area not resident");
+            VX_CUDA(cudaEventSynchronize(ctx->totals_ev));
+            if (back[0] != 0) {
+                sync_stream(ctx);
+                return fail(ctx, VX_ERR_NOT_LOADED, "vx_mesh: area not resident");
+            }
             if (back[1] == 0) {
                 ctx->last_mesh_version = ctx->index_version;  // d_jobs resolves exactly this list
                 n_recs = back[2];
                 n_faces = back[3];
                 if (n_faces > cap_faces || n_recs > cap_recs || !(cap_faces && cap_recs)) {
+                    if ((st = sync_stream(ctx)) != VX_OK) return st;  // the arena is about to be replaced
                     VX_CUDA(ctx->d_recs.ensure(std::max<size_t>(16, n_recs * 16)));
                     VX_CUDA(ctx->d_vertices.ensure(std::max<size_t>(16, n_faces * 160)));
                     VX_CUDA(ctx->d_indices.ensure(std::max<size_t>(16, n_faces * 12)));
@@ -826,12 +851,16 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
                 }
                 break;
             }
+            VX_CUDA(cudaStreamSynchronize(ctx->stream));
+            VX_CUDA(cudaGetLastError());
+            collect_timers(ctx);
             // edge neighbours that are not resident are generated, like world.get_with_cache ->
             // load_area (world.rs:157-174), then the pass above is repeated
             if (attempt > 0) return fail(ctx, VX_ERR_CUDA, "vx_mesh: neighbours still missing after generation");
             if (!ctx->has_seed) return fail(ctx, VX_ERR_NO_SEED, "vx_mesh needs to generate edge neighbours but no seed is set");
-            const uint32_t nm = std::min<uint32_t>(back[1], 4u * (uint32_t)n);
-            uint2* miss = reinterpret_cast<uint2*>(back + 16);
+            const uint32_t n_missing = back[1];
+            const uint32_t nm = std::min<uint32_t>(n_missing, 4u * (uint32_t)n);
+            uint2* miss = reinterpret_cast<uint2*>(ctx->h_small.as<uint32_t>() + 16);
             VX_CUDA(cudaMemcpyAsync(miss, ctx->d_missing.p, (size_t)nm * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
             VX_CUDA(cudaStreamSynchronize(ctx->stream));
             std::vector<uint64_t> keys(nm);

@@ -46,7 +46,7 @@ void launch_mesh_count(const uint4* jobs, const uint4* nbr, int n, const uint8_t
                        const uint16_t* pool_planes, uint32_t* rec_count,
                        uint32_t* face_count, uint32_t* warp_totals /* 64 per area */, cudaStream_t stream);
 void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, int n, uint32_t* rec_first,
-                         uint32_t* face_first, uint32_t* totals, cudaStream_t stream);
+                         uint32_t* face_first, const uint32_t* counters, uint32_t* host_totals, cudaStream_t stream);
 void launch_mesh_emit(const uint4* jobs, const uint4* nbr, int n, const uint8_t* pool_voxels,
                       const uint16_t* pool_planes, const uint32_t* warp_totals, MeshOut out,
                       uint32_t cap_faces, uint32_t cap_recs /* arena capacity; no-op if exceeded */,

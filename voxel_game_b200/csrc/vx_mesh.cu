@@ -315,28 +315,38 @@ __global__ void __launch_bounds__(1024) mesh_offsets_kernel(const uint32_t* __re
                                                             const uint32_t* __restrict__ face_count,
                                                             int n, uint32_t* __restrict__ rec_first,
                                                             uint32_t* __restrict__ face_first,
-                                                            uint32_t* __restrict__ totals) {
+                                                            const uint32_t* __restrict__ counters,
+                                                            uint32_t* __restrict__ host_totals) {
     __shared__ uint32_t s_r[32], s_f[32];
     __shared__ uint32_t carry_r, carry_f;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) carry_r = carry_f = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 4096) {
-        const int i = base + 4 * tid;
-        uint32_t r[4], f[4];
-        if (i + 3 < n) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(rec_count + i);
-            const uint4 fv = *reinterpret_cast<const uint4*>(face_count + i);
-            r[0] = rv.x; r[1] = rv.y; r[2] = rv.z; r[3] = rv.w;
-            f[0] = fv.x; f[1] = fv.y; f[2] = fv.z; f[3] = fv.w;
+    constexpr int PER = 16;  // areas per thread and round: four 16-byte loads of each array in flight
+    for (int base = 0; base < n; base += 1024 * PER) {
+        const int i = base + PER * tid;
+        uint32_t r[PER], f[PER];
+        if (i + PER <= n) {
+#pragma unroll
+            for (int q = 0; q < PER / 4; ++q) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(rec_count + i + 4 * q);
+                const uint4 fv = *reinterpret_cast<const uint4*>(face_count + i + 4 * q);
+                r[4 * q] = rv.x; r[4 * q + 1] = rv.y; r[4 * q + 2] = rv.z; r[4 * q + 3] = rv.w;
+                f[4 * q] = fv.x; f[4 * q + 1] = fv.y; f[4 * q + 2] = fv.z; f[4 * q + 3] = fv.w;
+            }
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < PER; ++k) {
                 r[k] = i + k < n ? rec_count[i + k] : 0u;
                 f[k] = i + k < n ? face_count[i + k] : 0u;
             }
         }
-        const uint32_t sr = r[0] + r[1] + r[2] + r[3], sf = f[0] + f[1] + f[2] + f[3];
+        uint32_t sr = 0, sf = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            sr += r[k];
+            sf += f[k];
+        }
         const uint32_t ir = warp_inclusive_scan(sr, lane), jf = warp_inclusive_scan(sf, lane);
         if (lane == 31) {
             s_r[wid] = ir;
@@ -350,14 +360,25 @@ __global__ void __launch_bounds__(1024) mesh_offsets_kernel(const uint32_t* __re
         }
         __syncthreads();
         uint32_t pr = carry_r + (wid ? s_r[wid - 1] : 0u) + ir - sr, pf = carry_f + (wid ? s_f[wid - 1] : 0u) + jf - sf;
+        if (i + PER <= n) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i + k < n) {
-                rec_first[i + k] = pr;
-                face_first[i + k] = pf;
+            for (int q = 0; q < PER / 4; ++q) {
+                uint4 ro, fo;
+                ro.x = pr; pr += r[4 * q]; ro.y = pr; pr += r[4 * q + 1]; ro.z = pr; pr += r[4 * q + 2]; ro.w = pr; pr += r[4 * q + 3];
+                fo.x = pf; pf += f[4 * q]; fo.y = pf; pf += f[4 * q + 1]; fo.z = pf; pf += f[4 * q + 2]; fo.w = pf; pf += f[4 * q + 3];
+                *reinterpret_cast<uint4*>(rec_first + i + 4 * q) = ro;
+                *reinterpret_cast<uint4*>(face_first + i + 4 * q) = fo;
             }
-            pr += r[k];
-            pf += f[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                if (i + k < n) {
+                    rec_first[i + k] = pr;
+                    face_first[i + k] = pf;
+                }
+                pr += r[k];
+                pf += f[k];
+            }
         }
         __syncthreads();
         if (tid == 1023) {
@@ -369,8 +390,12 @@ __global__ void __launch_bounds__(1024) mesh_offsets_kernel(const uint32_t* __re
     if (tid == 0) {
         rec_first[n] = carry_r;
         face_first[n] = carry_f;
-        totals[0] = carry_r;  // next to the host's other counters: one copy brings everything back
-        totals[1] = carry_f;
+        // what the host waits for, written straight into its (mapped, pinned) memory: it reads them
+        // as soon as this kernel is done, while emit is already running
+        host_totals[0] = counters[0];  // listed areas that are not resident (mesh_prepare)
+        host_totals[1] = counters[1];  // edge neighbours that are not resident
+        host_totals[2] = carry_r;
+        host_totals[3] = carry_f;
     }
 }
 
@@ -710,8 +735,8 @@ void launch_mesh_count(const uint4* jobs, const uint4* nbr, int n, const uint8_t
 }
 
 void launch_mesh_offsets(const uint32_t* rec_count, const uint32_t* face_count, int n, uint32_t* rec_first,
-                         uint32_t* face_first, uint32_t* totals, cudaStream_t stream) {
-    mesh_offsets_kernel<<<1, 1024, 0, stream>>>(rec_count, face_count, n, rec_first, face_first, totals);
+                         uint32_t* face_first, const uint32_t* counters, uint32_t* host_totals, cudaStream_t stream) {
+    mesh_offsets_kernel<<<1, 1024, 0, stream>>>(rec_count, face_count, n, rec_first, face_first, counters, host_totals);
 }
 
 void launch_mesh_emit(const uint4* jobs, const uint4* nbr, int n, const uint8_t* pool_voxels,
