@@ -24,8 +24,12 @@ with open(out_csv, "w", newline="") as f:
     w = csv.writer(f)
     w.writerow(cols)
     w.writerow([units[i] for i in idx])
+    seen = set()
     for d in data:
         name = d[idx[0]].split("(")[0].split("::")[-1]
+        if name in seen:  # one row per kernel: the first captured launch
+            continue
+        seen.add(name)
         w.writerow([name] + [d[i] for i in idx[1:]])
         rd = float(d[hdr.index("dram__bytes_read.sum")]) * scale[units[hdr.index("dram__bytes_read.sum")]]
         wr = float(d[hdr.index("dram__bytes_write.sum")]) * scale[units[hdr.index("dram__bytes_write.sum")]]

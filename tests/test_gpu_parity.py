@@ -587,3 +587,32 @@ def test_config1_spawn_area_at_shipped_render_distance(seed):
         faces = _compare_mesh(c, world, render)
         assert c.resident_count() == 361        # the render zone's neighbours were all loaded already
         assert faces > 50_000
+
+
+@pytest.mark.gpu
+def test_generate_without_outputs_is_stream_ordered(seed):
+    """vx_generate with no host buffers returns once the kernels are enqueued; whatever reads the
+    areas next sees them complete, and the timings accumulate until they are read."""
+    xy = vg.region_xy(SPAWN - 3, SPAWN - 3, 6, 6)
+    with vg.Context(0, seed=seed) as c:
+        c.set_timing(True)
+        c.generate(xy, read=False)
+        c.generate(xy, read=False)           # a second call before anything waited for the first
+        vox, mh = c.read_areas(xy)
+        t = c.timings()
+        assert t["gen_launches"] == 6 and t["gen_columns_ms"] > 0 and t["gen_caves_ms"] >= 0
+        assert t["simplex2_evals"] > 0
+        again = c.timings()                  # reading clears the accumulators
+        assert again["gen_launches"] == 0 and again["gen_columns_ms"] == 0
+        ovox, omh, _, _ = oracle.generate_areas(seed, xy)
+        assert np.array_equal(vox, ovox) and np.array_equal(mh, omh)
+        # mesh returns when the totals are known, emit may still be running: the reads line up behind it
+        inner = vg.region_xy(SPAWN - 2, SPAWN - 2, 4, 4)
+        info = c.mesh(inner)
+        first = c.mesh_read(info)
+        c.generate(xy, read=False)           # regenerating right behind a mesh in flight changes nothing
+        info2 = c.mesh(inner)
+        second = c.mesh_read(info2)
+        assert info == info2
+        for a, b in zip(first, second):
+            assert np.array_equal(a, b)

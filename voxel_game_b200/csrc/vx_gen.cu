@@ -226,12 +226,22 @@ __device__ __forceinline__ void planes_of_area(const uint8_t* vox, uint16_t* pla
     }
 }
 
+// Surface voxels whose second noise octave has to be evaluated; lives where the area is assembled
+// afterwards (GenSmem::vox).
+struct SurfaceQueue {
+    double2 acc[4 * COLUMNS_IN_AREA];  // first octave's weighted value, threshold
+    uint32_t who[4 * COLUMNS_IN_AREA]; // column | k << 8 | zi << 16
+    uint32_t alt[COLUMNS_IN_AREA];     // verdicts coming back: bit k per column
+};
+static_assert(sizeof(SurfaceQueue) <= VOXELS_IN_AREA, "the queue aliases the voxel buffer");
+
 struct __align__(16) GenSmem {
     uint4 vox[VOXELS_IN_AREA / 16];
     NoiseShared noise;
     unsigned cave_n;
     unsigned cave_base;
     unsigned evals[2];    // 2-D / 3-D octave evaluations of the CTA
+    unsigned queue_n;     // entries of the SurfaceQueue
     unsigned stone_rows;  // zi <= stone_rows is Stone in every column of the area
     int min_z;            // smallest z holding generated terrain (= 128 - max H)
     uint16_t tree[COLUMNS_IN_AREA];  // tree candidates, indexed x * 16 + y
@@ -287,6 +297,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
     if (tid == 0) {
         sm.cave_n = 0;
         sm.evals[0] = sm.evals[1] = 0;
+        sm.queue_n = 0;
         sm.stone_rows = AREA_HEIGHT;
         sm.min_z = AREA_HEIGHT;
         slot_xy[slot] = make_uint2(ax, ay);
@@ -323,41 +334,65 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
     const int biome_region = fbm2_region<FBM_BIOME>(nt, s, px, py, biome_cuts, evals2);
     const int biome = biome_region == 1 ? DRY : (biome_region == 2 ? WET : COLD);
 
-    // The four topmost voxels first, in a loop all lanes walk together (k-th voxel from H - 3).
+    // The four topmost voxels first (k-th voxel from H - 3): should_generate_alternative_voxel
+    // (voxel_type_generator.rs:176-188) is a 2-octave Fbm (weights 1/1.3 and 0.3/1.3) against a
+    // threshold.  The second octave is bounded by |simplex| <= SIMPLEX_BOUND, so it is needed only
+    // where it can still change the verdict (normalise() is monotone: testing it at the bounds is
+    // exact) -- about a quarter of the evaluations, scattered over the lanes.  Those are queued and
+    // evaluated densely by the whole CTA instead of by half-empty warps.
     // A lake column never consults the noise where the lake overrides the voxel
     // (lake_generator.rs:54-74 replaces the value; the reference computes it and throws it away).
-    unsigned tops = 0;  // voxel of zi = H - 3 + k in byte k
+    SurfaceQueue& sq = *reinterpret_cast<SurfaceQueue*>(sm.vox);  // the area is assembled there afterwards
+    const FbmParams& qa = nt.fbm[FBM_ALT];
+    const double alt_rest = SIMPLEX_BOUND * qa.amp[1] * qa.norm + 1e-9;
+    unsigned alt_bits = 0;  // bit k: the voxel at zi = H - 3 + k takes its alternative type
+    sq.alt[tid] = 0;
 #pragma unroll 1
     for (unsigned k = 0; k < 4; ++k) {
         const unsigned zi = H - 3 + k;
         double threshold;
         bool need = surface_query(biome, zi, H, threshold);
         if (lake_depth != 0 && zi >= LAKE_TOP_ZI - lake_depth) need = false;
-        bool alt = false;
+        bool undecided = false;
+        double acc = 0.0;
         if (need) {
-            // should_generate_alternative_voxel (voxel_type_generator.rs:176-188): a 2-octave Fbm
-            // (weights 1/1.3 and 0.3/1.3) against a threshold.  The second octave is bounded by
-            // |simplex| <= SIMPLEX_BOUND, so it is evaluated only when it can still change the
-            // verdict; normalise() is monotone, so testing it at the bounds is exact.
-            const FbmParams& q = nt.fbm[FBM_ALT];
-            double x3 = px * q.frequency, y3 = py * q.frequency, z3 = (double)zi * q.frequency;
-            double acc = 0.0;
-            acc += q.amp[0] * simplex3<FBM_TABLE<FBM_ALT>>(sb, sg, x3, y3, z3);
+            const double x3 = px * qa.frequency, y3 = py * qa.frequency, z3 = (double)zi * qa.frequency;
+            acc += qa.amp[0] * simplex3<FBM_TABLE<FBM_ALT>>(sb, sg, x3, y3, z3);
             evals3 += 1;
-            const double mid = acc * q.norm, rest = SIMPLEX_BOUND * q.amp[1] * q.norm + 1e-9;
-            if (normalise(mid - rest) - 1e-9 >= threshold) {
-                alt = true;
-            } else if (normalise(mid + rest) + 1e-9 < threshold) {
-                alt = false;
-            } else {
-                x3 *= q.lacunarity; y3 *= q.lacunarity; z3 *= q.lacunarity;
-                acc += q.amp[1] * simplex3<FBM_TABLE<FBM_ALT>>(sb, sg, x3, y3, z3);
-                evals3 += 1;
-                alt = normalise(acc * q.norm) >= threshold;
+            const double mid = acc * qa.norm;
+            if (normalise(mid - alt_rest) - 1e-9 >= threshold) alt_bits |= 1u << k;
+            else if (!(normalise(mid + alt_rest) + 1e-9 < threshold)) undecided = true;
+        }
+        const unsigned und = __ballot_sync(0xFFFFFFFFu, undecided);
+        if (und) {  // warp-aggregated push
+            unsigned base = 0;
+            if ((tid & 31) == 0) base = atomicAdd(&sm.queue_n, (unsigned)__popc(und));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (undecided) {
+                const unsigned slot = base + __popc(und & ((1u << (tid & 31)) - 1u));
+                sq.acc[slot] = make_double2(acc, threshold);
+                sq.who[slot] = (unsigned)tid | (k << 8) | (zi << 16);
             }
         }
-        tops |= (unsigned)surface_pick(biome, zi, H, alt) << (8 * k);
     }
+    __syncthreads();
+    for (unsigned i = tid; i < sm.queue_n; i += 256) {
+        const unsigned who = sq.who[i], c = who & 255u, k = (who >> 8) & 3u, zi = who >> 16;
+        const double2 d = sq.acc[i];  // first octave's weighted value, threshold
+        // the column's coordinates as its own thread computed them; octave 1 = octave 0 * lacunarity
+        const double cx = (double)((c & 15u) + ax * AREA_SIZE), cy = (double)((c >> 4) + ay * AREA_SIZE);
+        double x3 = cx * qa.frequency, y3 = cy * qa.frequency, z3 = (double)zi * qa.frequency;
+        x3 *= qa.lacunarity; y3 *= qa.lacunarity; z3 *= qa.lacunarity;
+        double acc = d.x;
+        acc += qa.amp[1] * simplex3<FBM_TABLE<FBM_ALT>>(sb, sg, x3, y3, z3);
+        evals3 += 1;
+        if (normalise(acc * qa.norm) >= d.y) atomicOr(&sq.alt[c], 1u << k);
+    }
+    __syncthreads();
+    alt_bits |= sq.alt[tid];
+    unsigned tops = 0;  // voxel of zi = H - 3 + k in byte k
+#pragma unroll
+    for (unsigned k = 0; k < 4; ++k) tops |= (unsigned)surface_pick(biome, H - 3 + k, H, (alt_bits >> k) & 1u) << (8 * k);
 
     // Deep down every column of the area is Stone: the lowest `stone_rows` slabs are filled by the
     // whole CTA with 16-byte stores (and everything above with None) before the per-column loop
