@@ -328,6 +328,17 @@ def main():
         files_pin.free()
 
     # ---- end to end through the C ABI with host buffers (`e2e`)
+    # The pinned buffers are placed when they are allocated: do that from a core next to the GPU
+    # (at N = 1 the process is otherwise free to roam, the CPU baseline needs every core), or the
+    # copies cross the socket link and the number depends on where the scheduler had put us.
+    saved_affinity = os.sched_getaffinity(0)
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     pin = {
         "vox": vg.PinnedArray((n_gen, 32768), np.uint8), "mh": vg.PinnedArray((n_gen, 256), np.uint8),
         "rf": vg.PinnedArray((n_mesh + 1,), np.uint32), "ff": vg.PinnedArray((n_mesh + 1,), np.uint32),
@@ -336,6 +347,10 @@ def main():
         "idx": vg.PinnedArray((info["n_faces"] * 6,), np.uint16),
     }
     mesh_out = (pin["rf"].array, pin["ff"].array, pin["recs"].array, pin["verts"].array, pin["idx"].array)
+    for p_ in pin.values():
+        p_.array.view(np.uint8).reshape(-1)[::4096] = 0  # touch every page while still next to the GPU
+    if world == 1:
+        os.sched_setaffinity(0, saved_affinity)
 
     def e2e_step():
         ctx.generate(gen_xy, voxels_out=pin["vox"].array, max_height_out=pin["mh"].array)
