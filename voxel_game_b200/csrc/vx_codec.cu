@@ -318,6 +318,21 @@ struct DecodeSmem {
     uint8_t in[STAGE_BYTES];
 };
 
+// dst[0..n) = src[0..n), non-overlapping, by the whole warp; both in shared memory (or src in
+// global memory for a file that was not staged).  16 bytes per lane where both ends are 16-byte
+// aligned -- the files this library writes are row-granular, so nearly every match is -- else
+// byte by byte.
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+    uint32_t done = 0;
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15u) == 0u) {
+        const uint32_t n16 = n >> 4;
+        for (uint32_t k = lane; k < n16; k += 32)
+            reinterpret_cast<uint4*>(dst)[k] = reinterpret_cast<const uint4*>(src)[k];
+        done = n16 << 4;
+    }
+    for (uint32_t k = done + lane; k < n; k += 32) dst[k] = src[k];
+}
+
 // One warp per file.  status[i] = 1 if the file expands to a well-formed AreaDTO (then the voxels
 // are in the area's pool slot), 0 where the reference logs an error and generates the area instead
 // (world_persistence.rs:66-70): bad size prefix, malformed LZ4 stream, wrong slice length, voxel id
@@ -360,7 +375,7 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
             if (!ok) break;
         }
         if (lit > n - ip || lit > PAYLOAD - op) { ok = false; break; }
-        for (uint32_t k = lane; k < lit; k += 32) out[op + k] = src[ip + k];
+        warp_copy(out + op, src + ip, lit, lane);
         ip += lit;
         op += lit;
         if (ip == n) break;  // last sequence: literals only
@@ -387,7 +402,7 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
         uint32_t done = 0;
         while (done < len) {
             const uint32_t chunk = min(len - done, offset + done);
-            for (uint32_t k = lane; k < chunk; k += 32) out[op + done + k] = from[k];
+            warp_copy(out + op + done, from, chunk, lane);
             done += chunk;
             __syncwarp();
         }
