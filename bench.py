@@ -327,6 +327,49 @@ def main():
                          "memory (the bytes store_blocking writes to disk); encode reads 32 KiB per area twice"}
         files_pin.free()
 
+    # ---- edit storm (BASELINE.json configs[3]; not part of `value`): 100 000 place/break events over a
+    # loaded 64x64 region in batches of 1 000 -- vx_apply_edits (World::set + column heights) and a
+    # remesh of the dirty areas per batch, as a simulator tick would issue them
+    edit_storm = None
+    if world == 1:
+        with vg.Context(local_rank, seed=seed) as ec:
+            n_side = 64
+            ex0, ey0, _, _ = vg.spawn_region(n_side)
+            ec.generate(vg.region_xy(ex0 - 1, ey0 - 1, n_side + 2, n_side + 2), read=False)
+            ec.mesh(vg.region_xy(ex0, ey0, n_side, n_side))
+            vox0, _ = ec.read_areas(vg.region_xy(ex0, ey0, n_side, n_side))
+            rng = np.random.default_rng(0x5EEDED17)
+            n_edits, batch = 100_000, 1000
+            gx = rng.integers(0, n_side * 16, n_edits)
+            gy = rng.integers(0, n_side * 16, n_edits)
+            gz = rng.integers(1, 127, n_edits)
+            area = (gx // 16) + n_side * (gy // 16)  # region_xy order: index = ix + nx * iy
+            cur = vox0[area, (gx % 16) + 16 * (gy % 16) + 256 * gz]
+            palette = np.array([1, 6, 8, 9, 11, 26], np.uint32)  # Cobblestone Brick Boards Stone Lamp Glass
+            edits = np.zeros(n_edits, vg.EDIT_DTYPE)
+            edits["gx"] = ex0 * 16 + gx
+            edits["gy"] = ey0 * 16 + gy
+            edits["gz"] = gz
+            edits["voxel"] = np.where(cur != 0, 0, palette[rng.integers(0, 6, n_edits)])
+            for lo in range(0, 3 * batch, batch):  # warm-up
+                d = ec.apply_edits(edits[lo:lo + batch])
+                ec.mesh(d)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dirty_total = faces_total = 0
+            for lo in range(0, n_edits, batch):
+                d = ec.apply_edits(edits[lo:lo + batch])
+                inf = ec.mesh(d)
+                dirty_total += len(d)
+                faces_total += inf["n_faces"]
+            ec.sync()
+            wall = time.perf_counter() - t0
+            edit_storm = {"edits": n_edits, "batch": batch, "region": "64x64 areas", "ms_per_batch": wall * 1e3 / (n_edits // batch),
+                          "edits_per_s": n_edits / wall, "dirty_areas_remeshed": dirty_total,
+                          "areas_remeshed_per_s": dirty_total / wall, "faces_emitted": int(faces_total),
+                          "note": "wall clock over 100 batches: vx_apply_edits + vx_mesh of the dirty areas (edited area, "
+                                  "plus the neighbour for border columns); meshes stay on the device"}
+
     # ---- end to end through the C ABI with host buffers (`e2e`)
     # The pinned buffers are placed when they are allocated: do that from a core next to the GPU
     # (at N = 1 the process is otherwise free to roam, the CPU baseline needs every core), or the
@@ -448,6 +491,8 @@ def main():
     if frame is not None:
         frame["roofline"] = hbm_roof(frame["algorithmic_bytes"], frame["ms"])
         line["frame"] = frame
+    if edit_storm is not None:
+        line["edit_storm"] = edit_storm
     if codec is not None:
         codec["encode_roofline"] = hbm_roof(n_gen * 32768 + codec["file_bytes_total"], codec["encode_ms"])
         codec["decode_roofline"] = hbm_roof(n_gen * (32768 + 8192 + 256) + codec["file_bytes_total"], codec["decode_ms"])
@@ -456,7 +501,6 @@ def main():
         import oracle
 
         if frame is not None:  # the same frame on one host thread (the reference: rayon par_iter)
-            import time
 
             recs_h = np.empty(info["n_recs"], vg.REC_DTYPE)
             rf_h = np.empty(n_mesh + 1, np.uint32)
