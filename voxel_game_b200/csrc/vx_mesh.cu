@@ -113,14 +113,17 @@ __device__ __forceinline__ void load_plane_tile(PlaneTile& p, const AreaView& a,
         }
         ds[i] = sv;
         dt[i] = tv;
+        // per row one byte: bit0 = T(+x neighbour, x = 0), bit1 = T(-x neighbour, x = 15); a 32-bit
+        // word holds two rows, so both bits of both rows are gathered with a mask, a shift and one
+        // byte permute (bytes 0 and 2 of the gathered word)
         const uint32_t wp[4] = {xp.x, xp.y, xp.z, xp.w}, wm[4] = {xm.x, xm.y, xm.z, xm.w};
-        uint32_t h[2] = {0, 0};
+        uint32_t pair[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t vp = (wp[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-            const uint32_t vm = (wm[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-            h[k >> 2] |= ((vp & 1u) | ((vm >> 15) << 1)) << (8 * (k & 3));
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t g = (wp[k] & 0x00010001u) | ((wm[k] >> 14) & 0x00020002u);
+            pair[k] = __byte_perm(g, 0u, 0x4420);  // rows 2k, 2k + 1 -> bytes 0, 1
         }
+        const uint32_t h[2] = {pair[0] | (pair[1] << 16), pair[2] | (pair[3] << 16)};
         dh[i] = make_uint2(h[0], h[1]);
         uint32_t any_s = sv.x | sv.y | sv.z | sv.w;
         uint32_t any_t = tv.x | tv.y | tv.z | tv.w | h[0] | h[1] | ty_or;
@@ -278,9 +281,12 @@ __global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict
     }
     __syncthreads();
     // this warp's chunks: bits wid, 8 + wid, ... of the 64-bit mask
-    uint32_t mine = 0;
-#pragma unroll
-    for (int c = 0; c < ROWS / 256; ++c) mine |= ((s_busy[c >> 2] >> ((c & 3) * 8 + wid)) & 1u) << c;
+    // (bit wid of each byte, gathered into a nibble by a multiply: the partial products land on
+    // distinct bits, the wanted ones on bits 24..27)
+    static_assert(ROWS / 256 == 8, "two words of four chunks each");
+    const uint32_t mine_lo = ((((s_busy[0] >> wid) & 0x01010101u) * 0x01020408u) >> 24) & 15u;
+    const uint32_t mine_hi = ((((s_busy[1] >> wid) & 0x01010101u) * 0x01020408u) >> 24) & 15u;
+    uint32_t mine = mine_lo | (mine_hi << 4);
     uint32_t faces = 0, recs = 0;
     while (mine) {
         const int c = __ffs(mine) - 1;
