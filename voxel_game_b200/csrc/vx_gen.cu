@@ -1,14 +1,16 @@
 // vx_gen.cu -- terrain generation kernels (sm_100a).
 //
 //   K1  gen_columns : one CTA per area, one thread per voxel column.  Column samples
-//                     (generator.rs:108-132), voxel types (voxel_type_generator.rs:31-174), lake
-//                     override (lake_generator.rs:54-74).  The 32 KiB area is assembled in shared
+//                     (generator.rs:108-132), voxel types (voxel_type_generator.rs:31-174; the second
+//                     octave of the surface noise, needed by a quarter of the evaluations, is
+//                     queued and evaluated densely by the CTA), lake override
+//                     (lake_generator.rs:54-74).  The 32 KiB area is assembled in shared
 //                     memory and written to HBM with 16-byte coalesced stores.  An area without
 //                     cave-zone columns (most) is FINISHED here, still in shared memory: tree
 //                     candidates and ordered placement (trees.rs:142-241), column heights
 //                     (area.rs:34-56) and the S/T bit planes the mesher reads.  Cave-zone columns
 //                     are appended to a work list instead of being carved in place.
-//   K1b gen_caves   : persistent, warp-autonomous lanes over the list of cave-zone columns
+//   K1b gen_caves   : persistent (3 CTAs per SM), warp-autonomous lanes over the list of cave-zone columns
 //                     (cave_generator.rs:43-64): exact early exit on octave bounds, lanes refill
 //                     themselves, warps claim the next chunk while still busy.  FP64-bound part.
 //   K2  gen_finish  : areas with cave columns only: trees, heights, planes from HBM after carving.

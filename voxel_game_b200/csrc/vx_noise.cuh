@@ -10,18 +10,19 @@
 //   * the permutation table is doubled (512 B) like the crate's, and the integer lattice
 //     coordinates are reduced modulo 256 once per evaluation, so no lookup needs a mask;
 //   * the 3-D gradient dot product g.x (components 0/+-1) is one signed add instead of
-//     3 multiplies + 2 adds (x*1 = x, x*0 = +-0, y + +-0 = y);
+//     3 multiplies + 2 adds (x*1 = x, x*0 = +-0, y + +-0 = y); which two coordinates and which
+//     signs comes from the table as a code (vx_tables.hpp) applied with byte permutes;
 //   * Fbm amplitudes amp_k are precomputed on the host with the same running product;
-//   * the last permutation lookup only feeds "% 12" / "% 24", so it reads pre-reduced copies of
-//     the table;
+//   * the last permutation lookup of a corner only feeds "% 24" (2-D) or "% 12" (3-D), so it reads
+//     a pre-reduced copy of the table, or the gradient code directly;
 //   * a corner with t <= 0 contributes 0 in the crate, i.e. leaves the running sum unchanged.  Here
 //     the high word of t is clamped with one signed integer max (a negative or -0 t becomes a
 //     number below 2^-1022 whose square is exactly +0), so t^4 * d = +-0 is added unconditionally:
 //     no FP64 compare and no selects (sum is never -0: it starts at +0.0, and x + (-x) = +0);
 //   * "c - (step ? 1.0 : 0.0)" is a select between c - 1.0 and c (c - 0.0 == c bit for bit), and
 //     c - 1.0 is shared with the last corner.
-// Tables are addressed as uniform shared-memory pointer + per-lane index, never through a
-// selected pointer, so every lookup is one LDS with the table base in a uniform register.
+// Which table an Fbm reads is a template argument, so the table base is part of each load's
+// constant offset; a lookup is one add and one LDS.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -34,7 +35,7 @@ namespace vx {
 // per-context image in device memory: contexts with different seeds in one process cannot disturb
 // each other, which a module-wide __constant__ symbol would allow.  Lookups are random per lane,
 // so the tables are read from a shared-memory copy (the constant cache would serialise them); the
-// copy is 216 coalesced 16-byte loads per CTA.
+// copy is 536 (K1) / 640 (K1b) coalesced 16-byte loads per CTA.
 constexpr unsigned TAB_BYTES = TAB_COUNT * TAB_STRIDE;
 constexpr unsigned OFF_P24 = TAB_BYTES;      // byte offset of the % 24 copies
 // K1's copy: everything 2-D noise reads plus the 3-D gradient codes of ONE table (the surface

@@ -46,7 +46,7 @@ constexpr int FBM_TABLE = ID == FBM_HEIGHT1 || ID == FBM_BIOME || ID == FBM_CAVE
 
 struct NoiseTables {
     uint64_t seed;
-    uint8_t perm[TAB_COUNT][256];  // un-doubled; kernels index with (a + b) & 255
+    uint8_t perm[TAB_COUNT][256];  // the shuffled identity tables; NoiseImage holds what the kernels read
     FbmParams fbm[FBM_COUNT];
     // cave_rest[f][k]: upper bound of |norm * sum_{i >= k} amp_i * simplex_i| for the two cave
     // Fbms after k evaluated octaves (SIMPLEX_BOUND * norm * sum of the remaining amplitudes)
