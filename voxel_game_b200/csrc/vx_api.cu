@@ -552,7 +552,7 @@ int vx_set_stream(vx_ctx* ctx, void* cuda_stream) {
     if (!ctx) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    sync_stream(ctx);  // nothing stays in flight (or pending in the timers) on the stream being left
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return VX_OK;
 }
