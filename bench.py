@@ -241,9 +241,6 @@ def main():
     for _ in range(args.warmup):
         info = step()
     ctx.timings()  # clears the accumulators: the kernel times below cover the timed steps only
-    kern = {}
-    work = {}
-    launches = 0
     sampler = ClockSampler(local_rank)
     barrier()
     torch.cuda.synchronize()

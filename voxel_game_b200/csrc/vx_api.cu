@@ -266,8 +266,6 @@ struct ScopedTimer {
     }
 };
 
-void reset_timers(vx_ctx*) {}  // accumulators are cleared by vx_get_timings
-
 // call after the stream has been synchronised
 void collect_timers(vx_ctx* c) {
     for (int i = 0; i < TM_COUNT; ++i)
@@ -633,7 +631,6 @@ int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (!ctx->has_seed) return fail(ctx, VX_ERR_NO_SEED, "vx_generate before vx_set_seed");
     VX_CUDA(cudaSetDevice(ctx->device));
-    reset_timers(ctx);
     if (n == 0) return VX_OK;
     // Regenerating the list of the previous call with an unchanged resident set (world
     // pre-generation sweeps, benchmarks) reuses its slot assignment: no hashing on the host.
@@ -663,7 +660,6 @@ int vx_upload(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* voxels
     if (!ctx || n < 0 || (n > 0 && (!area_xy || !voxels))) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
-    reset_timers(ctx);
     if (n == 0) return VX_OK;
     std::vector<int> slots;
     int st = acquire_slots(ctx, area_xy, n, slots);
@@ -747,7 +743,6 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
     if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
-    reset_timers(ctx);
     ctx->mesh_n = -1;
     ctx->frame_ready = false;
     ctx->mesh_info = vx_mesh_info{};
@@ -916,7 +911,6 @@ int vx_encode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint64_t* total
     if (!ctx || n < 0 || (n > 0 && !area_xy) || !total_bytes) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
-    reset_timers(ctx);
     *total_bytes = 0;
     ctx->codec_n = -1;
     ctx->codec_total = 0;
@@ -984,7 +978,6 @@ int vx_decode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* 
     if (!ctx || n < 0 || (n > 0 && (!area_xy || !offsets || !ok))) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
-    reset_timers(ctx);
     if (n == 0) return VX_OK;
     for (int i = 0; i < n; ++i)
         if (offsets[i + 1] < offsets[i]) return fail(ctx, VX_ERR_INVALID, "vx_decode_areas: offsets must not decrease");
@@ -1039,7 +1032,6 @@ int vx_visible(vx_ctx* ctx, const vx_view* view, vx_visible_info* info) {
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (ctx->mesh_n < 0) return fail(ctx, VX_ERR_NO_MESH, "vx_visible without vx_mesh");
     VX_CUDA(cudaSetDevice(ctx->device));
-    reset_timers(ctx);
     *info = vx_visible_info{};
     ctx->frame_ready = false;
     ctx->frame_n_visible = 0;
@@ -1110,7 +1102,6 @@ int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_are
     if (!ctx || n < 0 || (n > 0 && (!edits || !dirty_area_xy)) || !n_dirty) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
-    reset_timers(ctx);
     *n_dirty = 0;
     if (n == 0) return VX_OK;
     for (int i = 0; i < n; ++i) {  // all-or-nothing validation (reference: world_actions.rs guards)
@@ -1172,7 +1163,6 @@ int vx_explode(vx_ctx* ctx, const float* positions, int n, uint32_t* removed_xyz
         return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
-    reset_timers(ctx);
     *n_removed = *n_bombs = *n_dirty = 0;
     if (n == 0) return VX_OK;
     for (int i = 0; i < n; ++i) {  // all-or-nothing: every area a sphere can reach is resident
@@ -1248,7 +1238,6 @@ int vx_heightmap(vx_ctx* ctx, const uint32_t* area_xy, int n, uint32_t cam_area_
     if (!ctx || n < 0 || (n > 0 && !area_xy) || !rgba) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
-    reset_timers(ctx);
     const size_t img_bytes = (size_t)VX_HEIGHTMAP_SIZE * VX_HEIGHTMAP_SIZE * 4;
     int st;
     if ((st = upload_map(ctx)) != VX_OK) return st;
@@ -1277,7 +1266,6 @@ int vx_light(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* light_out, in
     if (!ctx || n < 0 || (n > 0 && (!area_xy || !light_out))) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
-    reset_timers(ctx);
     if (iterations) *iterations = 0;
     if (n == 0) return VX_OK;
     std::vector<int> slots(n);
