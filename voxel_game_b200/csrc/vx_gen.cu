@@ -516,14 +516,23 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------- K1b
-constexpr int CAVE_CHUNK = 32;  // cave columns claimed by a warp at a time (one per lane)
+#ifndef VX_CAVE_CHUNK
+#define VX_CAVE_CHUNK 8
+#endif
+// Cave columns a warp claims at a time (lane c < CAVE_CHUNK describes column c).  A column is 8..78
+// voxels and a region has ~87 000 cave columns for 3 552 warps: with 32 columns per claim most
+// warps got exactly one chunk (a quarter of them none) and the kernel lasted as long as the
+// heaviest chunk; small chunks let the global counter even the warps out.
+constexpr int CAVE_CHUNK = VX_CAVE_CHUNK;
+constexpr int CAVE_SLOTS = 32;  // table entries per warp (one per lane; those past CAVE_CHUNK stay empty)
+static_assert(CAVE_CHUNK >= 1 && CAVE_CHUNK <= CAVE_SLOTS, "one column per lane");
 // The 14 cave octaves are evaluated in rounds: round k = octave k of noise2 (8 octaves, weights
 // .650 .228 .080 .028 ...) and, for k < 6, octave k of noise1 (6 octaves, .553 .249 .112 .050 ...).
 
 struct CaveWarp {  // per-warp description of the claimed chunk
-    uint32_t first[CAVE_CHUNK + 1];  // exclusive prefix of per-column voxel counts
-    uint32_t item[CAVE_CHUNK];       // slot * 256 + column
-    uint2 origin[CAVE_CHUNK];        // global x, y of the column
+    uint32_t first[CAVE_SLOTS + 1];  // exclusive prefix of per-column voxel counts
+    uint32_t item[CAVE_SLOTS];       // slot * 256 + column
+    uint2 origin[CAVE_SLOTS];        // global x, y of the column
 };
 struct CaveSmem {
     alignas(16) uint8_t bytes[TAB_BYTES];       // the (doubled) permutation tables (vx_noise.cuh)
@@ -588,7 +597,7 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
     while (true) {
         const unsigned want = __ballot_sync(0xFFFFFFFFu, !busy);
         if (want != 0 && next >= total && more) {
-            // The current chunk is used up: claim the next 32 columns right away.  Lanes that are
+            // The current chunk is used up: claim the next columns right away.  Lanes that are
             // still evaluating keep their state in registers, so the warp never drains.
             unsigned chunk = 0;
             if (lane == 0) chunk = atomicAdd(chunk_counter, 1u);
@@ -599,7 +608,7 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
                 const uint32_t idx = chunk * CAVE_CHUNK + lane;
                 uint32_t item = 0, cnt = 0;
                 uint2 org = make_uint2(0, 0);
-                if (idx < n_items) {
+                if (lane < CAVE_CHUNK && idx < n_items) {
                     item = cave_items[idx];
                     const unsigned H = pool_heights[item] & 0x7Fu;
                     // should_be_cave evaluates the noise for CAVE_MIN_ZI <= zi < CAVE_MAX_ZI, zi <= H
@@ -621,7 +630,7 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
                 cw.first[lane + 1] = v;
                 if (lane == 0) cw.first[0] = 0;
                 __syncwarp();
-                total = cw.first[CAVE_CHUNK];
+                total = cw.first[CAVE_SLOTS];
                 next = 0;
                 if (lane == 0) atomicAdd(&stats[2], (unsigned long long)total);  // cave voxels evaluated
             }
@@ -630,7 +639,7 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
         if (!busy) {
             const uint32_t w = next + __popc(want & lanes_below);
             if (w < total) {
-                int lo = 0, hi = CAVE_CHUNK;  // column with first[lo] <= w < first[lo + 1]
+                int lo = 0, hi = CAVE_SLOTS;  // column with first[lo] <= w < first[lo + 1]
 #pragma unroll
                 for (int s = 0; s < 5; ++s) {
                     const int mid = (lo + hi) >> 1;
