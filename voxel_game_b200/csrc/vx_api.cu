@@ -428,7 +428,7 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
         ctx->last_gen_version = ~0ull;  // whatever list d_gen_jobs held before is gone
     }
     VX_CUDA(ctx->d_cave_items.ensure((size_t)n * COLUMNS_IN_AREA * sizeof(uint32_t)));
-    VX_CUDA(ctx->d_finished.ensure((size_t)n));
+    VX_CUDA(ctx->d_finished.ensure((size_t)n * sizeof(uint32_t)));  // K2 work list
     VX_CUDA(ctx->d_gen_counters.ensure(64));
     VX_CUDA(cudaMemsetAsync(ctx->d_gen_counters.p, 0, 64, ctx->stream));
     const uint4* jobs = ctx->d_gen_jobs.as<uint4>();
@@ -438,7 +438,7 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
         ScopedTimer t(ctx, TM_GEN_COLUMNS);
         launch_gen_columns(ctx->tables, jobs, n, ctx->d_voxels, ctx->d_heights, ctx->d_slot_xy,
                            ctx->d_cave_items.as<uint32_t>(), cave_count, stats, ctx->d_planes,
-                           ctx->d_finished.as<uint8_t>(), ctx->stream);
+                           ctx->d_finished.as<uint32_t>(), ctx->stream);
     }
     {
         ScopedTimer t(ctx, TM_GEN_CAVES, TM_GEN_COLUMNS);
@@ -447,8 +447,8 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
     }
     {
         ScopedTimer t(ctx, TM_GEN_FINISH, TM_GEN_CAVES);
-        launch_gen_finish(jobs, ctx->d_finished.as<uint8_t>(), n, ctx->d_voxels, ctx->d_heights, ctx->d_planes,
-                          ctx->tables.seed, ctx->stream);
+        launch_gen_finish(jobs, ctx->d_finished.as<uint32_t>(), cave_count + 1, n, ctx->d_voxels, ctx->d_heights,
+                          ctx->d_planes, ctx->tables.seed, ctx->sm_count, ctx->stream);
     }
     ctx->timings.gen_launches += 3;
     VX_CUDA(cudaGetLastError());

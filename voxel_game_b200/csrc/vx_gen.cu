@@ -13,7 +13,8 @@
 //   K1b gen_caves   : persistent (3 CTAs per SM), warp-autonomous lanes over the list of cave-zone columns
 //                     (cave_generator.rs:43-64): exact early exit on octave bounds, lanes refill
 //                     themselves, warps claim the next chunk while still busy.  FP64-bound part.
-//   K2  gen_finish  : areas with cave columns only: trees, heights, planes from HBM after carving.
+//   K2  gen_finish  : persistent CTAs over the areas with cave columns (listed by K1): trees, heights,
+//                     planes from HBM after carving.
 //   L1  column_heights : Area::update_all_column_heights (+ planes) for uploaded areas.
 //
 // FP64 only (the reference's libnoise is f64 throughout), no FMA contraction (-fmad=false).
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
                                                           uint32_t* __restrict__ cave_count,
                                                           unsigned long long* __restrict__ stats,
                                                           uint16_t* __restrict__ pool_planes,
-                                                          uint8_t* __restrict__ finished) {
+                                                          uint32_t* __restrict__ cave_areas) {
     __shared__ __align__(256) GenSmem sm;  // vox is 32 KiB, so the table image behind it is 256-byte aligned
     const int tid = threadIdx.x;
     const uint4 job = jobs[blockIdx.x];
@@ -463,7 +464,8 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
         if (tid == 0) {
             sm.cave_base = atomicAdd(cave_count, n_cave);
             sm.cave_n = 0;
-            finished[blockIdx.x] = 0;
+            // K2's work list: the jobs that still need finishing (cave_count + 1 counts them)
+            cave_areas[atomicAdd(cave_count + 1, 1u)] = blockIdx.x;
         }
         __syncthreads();
         if (cave_zone) cave_items[sm.cave_base + atomicAdd(&sm.cave_n, 1u)] = slot * COLUMNS_IN_AREA + tid;
@@ -508,7 +510,6 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
             }
         }
         heights[tid] = (uint8_t)top;
-        if (tid == 0) finished[blockIdx.x] = 1;
     }
 
     uint4* dst = reinterpret_cast<uint4*>(pool_voxels + (size_t)slot * VOXELS_IN_AREA);
@@ -698,9 +699,11 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
 }
 
 // ------------------------------------------------------------------------------------------- K2
-// K2: areas that contain cave-zone columns (K1 finished all others in shared memory).
+// K2: areas that contain cave-zone columns (K1 finished all others in shared memory), from the
+// list K1 wrote.  Persistent CTAs: one launch wave instead of one (mostly empty) CTA per area.
 __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict__ jobs,
-                                                         const uint8_t* __restrict__ finished,
+                                                         const uint32_t* __restrict__ cave_areas,
+                                                         const uint32_t* __restrict__ cave_area_count,
                                                          uint8_t* __restrict__ pool_voxels,
                                                          uint8_t* __restrict__ pool_heights,
                                                          uint16_t* __restrict__ pool_planes,
@@ -708,9 +711,10 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
     __shared__ uint4 s_vox[VOXELS_IN_AREA / 16];
     __shared__ uint16_t s_tree[COLUMNS_IN_AREA];  // indexed x*16 + y (generator.rs:54-58 order)
     __shared__ int s_min_z;
-    if (finished[blockIdx.x]) return;
     const int tid = threadIdx.x;
-    const uint4 job = jobs[blockIdx.x];
+    const uint32_t n_list = *cave_area_count;
+    for (uint32_t item = blockIdx.x; item < n_list; item += gridDim.x) {
+    const uint4 job = jobs[cave_areas[item]];
     const uint32_t ax = job.x, ay = job.y, slot = job.z;
     uint4* area = reinterpret_cast<uint4*>(pool_voxels + (size_t)slot * VOXELS_IN_AREA);
     uint8_t* heights = pool_heights + (size_t)slot * COLUMNS_IN_AREA;
@@ -772,6 +776,8 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
     // trees only touch the slabs from min_z - 8 down to the surface; write those back
     const int first_row = max(s_min_z - 8, 0) * 16;
     for (int i = first_row + tid; i < VOXELS_IN_AREA / 16; i += 256) area[i] = s_vox[i];
+    __syncthreads();  // shared memory is reused by the next area of this CTA
+    }
 }
 
 // ------------------------------------------------------------------------------------------- L1
@@ -812,11 +818,11 @@ __global__ void __launch_bounds__(256) fp64_rate_kernel(double* sink, int iters)
 
 void launch_gen_columns(const NoiseTables& nt, const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
                         uint2* slot_xy, uint32_t* cave_items, uint32_t* cave_count,
-                        unsigned long long* stats, uint16_t* pool_planes, uint8_t* finished,
+                        unsigned long long* stats, uint16_t* pool_planes, uint32_t* cave_areas,
                         cudaStream_t stream) {
     if (n <= 0) return;
     gen_columns_kernel<<<n, 256, 0, stream>>>(nt, jobs, pool_voxels, pool_heights, slot_xy, cave_items,
-                                              cave_count, stats, pool_planes, finished);
+                                              cave_count, stats, pool_planes, cave_areas);
 }
 
 void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const uint32_t* cave_count, uint8_t* pool_voxels,
@@ -826,10 +832,13 @@ void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const u
                                                        pool_heights, slot_xy, stats);
 }
 
-void launch_gen_finish(const uint4* jobs, const uint8_t* finished, int n, uint8_t* pool_voxels,
-                       uint8_t* pool_heights, uint16_t* pool_planes, uint64_t seed, cudaStream_t stream) {
+void launch_gen_finish(const uint4* jobs, const uint32_t* cave_areas, const uint32_t* cave_area_count, int n,
+                       uint8_t* pool_voxels, uint8_t* pool_heights, uint16_t* pool_planes, uint64_t seed,
+                       int sm_count, cudaStream_t stream) {
     if (n <= 0) return;
-    gen_finish_kernel<<<n, 256, 0, stream>>>(jobs, finished, pool_voxels, pool_heights, pool_planes, seed);
+    const int grid = n < sm_count * 6 ? n : sm_count * 6;  // 33 KiB of shared memory each: 6 per SM
+    gen_finish_kernel<<<grid, 256, 0, stream>>>(jobs, cave_areas, cave_area_count, pool_voxels, pool_heights,
+                                                pool_planes, seed);
 }
 
 void launch_column_heights(const uint4* jobs, int n, const uint8_t* pool_voxels,

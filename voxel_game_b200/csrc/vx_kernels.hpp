@@ -15,13 +15,14 @@ namespace vx {
 void launch_gen_columns(const NoiseTables& nt, const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
                         uint2* slot_xy, uint32_t* cave_items, uint32_t* cave_count,
                         unsigned long long* stats /* [5]: simplex2, alt simplex3, cave voxels, cave evals, cursor */,
-                        uint16_t* pool_planes, uint8_t* finished /* per job: 1 = K1 completed the area */,
+                        uint16_t* pool_planes, uint32_t* cave_areas /* jobs K2 has to finish; counted at cave_count[1] */,
                         cudaStream_t stream);
 void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const uint32_t* cave_count,
                       uint8_t* pool_voxels, const uint8_t* pool_heights, const uint2* slot_xy,
                       unsigned long long* stats, int sm_count, cudaStream_t stream);
-void launch_gen_finish(const uint4* jobs, const uint8_t* finished, int n, uint8_t* pool_voxels,
-                       uint8_t* pool_heights, uint16_t* pool_planes, uint64_t seed, cudaStream_t stream);
+void launch_gen_finish(const uint4* jobs, const uint32_t* cave_areas, const uint32_t* cave_area_count, int n,
+                       uint8_t* pool_voxels, uint8_t* pool_heights, uint16_t* pool_planes, uint64_t seed,
+                       int sm_count, cudaStream_t stream);
 // pool_planes may be null (temporary areas that are never meshed)
 void launch_column_heights(const uint4* jobs, int n, const uint8_t* pool_voxels,
                            uint8_t* pool_heights, uint2* slot_xy, uint16_t* pool_planes,
