@@ -461,7 +461,6 @@ struct EmitSmem {
         uint4 stage[8][WARP_FACES * FACE_U4];  // one staging tile per warp
     } u;
     unsigned long long part[CHUNKS * 8 + 1];  // running sums before (chunk, warp); [64] = area totals
-    uint32_t tot[CHUNKS * 8];                 // the packed totals themselves; 0 = nothing to do
 };
 static_assert(sizeof(RowEntries) <= sizeof(uint4) * 8 * WARP_FACES * FACE_U4, "row entries alias the staging tiles");
 
@@ -569,14 +568,15 @@ __device__ __forceinline__ void flush_faces(EmitSmem& sm, uint32_t count, uint32
         }
         __syncwarp();
     }
-    // indices: [0,1,2,0,2,3] + 4*ord as three u32 words per face (mesh_generator.rs:44,131-139)
+    // indices: [0,1,2,0,2,3] + 4*ord as three u32 words per face (mesh_generator.rs:44,131-139);
+    // one thread per face, a warp covers 384 consecutive bytes with its three stores
     uint32_t* idst = out.indices + (size_t)first * 3;
-    for (uint32_t w = tid; w < count * 3; w += 256) {
-        const uint32_t fi = w / 3, part = w - fi * 3;
+    for (uint32_t fi = tid; fi < count; fi += 256) {
         const uint32_t b = ((sm.list[fi] >> 18) & 7u) * 4u;
-        const uint32_t lo16 = part == 0 ? b : b + 2u;
-        const uint32_t hi16 = part == 0 ? b + 1u : (part == 1 ? b : b + 3u);
-        idst[w] = lo16 | (hi16 << 16);
+        uint32_t* w = idst + 3 * fi;
+        w[0] = b | ((b + 1u) << 16);
+        w[1] = (b + 2u) | (b << 16);
+        w[2] = (b + 2u) | ((b + 3u) << 16);
     }
 }
 
@@ -615,9 +615,11 @@ __global__ void __launch_bounds__(256, 5) mesh_emit_kernel(const uint4* __restri
     if (stream_faces > cap_faces || stream_recs > cap_recs) return;
     const AreaView a = make_view(job, nb, pool_voxels, pool_planes);
     const uint32_t gx0 = job.x * AREA_SIZE, gy0 = job.y * AREA_SIZE;
+    // bit c: this warp's group of chunk c has faces (lane c holds its total)
+    const uint32_t busy_chunks = __ballot_sync(0xFFFFFFFFu, my_total != 0u);
     {   // The voxel rows of the busy groups are requested into L2 together with the planes: phase A
         // would otherwise start a third dependent round trip to HBM (32 rows = four 128-byte lines).
-        uint32_t busy = __ballot_sync(0xFFFFFFFFu, my_total != 0u);
+        uint32_t busy = busy_chunks;
         while (busy) {
             const int c = __ffs(busy) - 1;
             busy &= busy - 1;
@@ -631,8 +633,6 @@ __global__ void __launch_bounds__(256, 5) mesh_emit_kernel(const uint4* __restri
         const unsigned long long inc = warp_inclusive_scan64(t0 + t1, lane);
         sm.part[2 * lane] = inc - t0 - t1;
         sm.part[2 * lane + 1] = inc - t1;
-        sm.tot[2 * lane] = w2.x;
-        sm.tot[2 * lane + 1] = w2.y;
         if (lane == 31) sm.part[CHUNKS * 8] = inc;
     }
     __syncthreads();
@@ -659,9 +659,8 @@ __global__ void __launch_bounds__(256, 5) mesh_emit_kernel(const uint4* __restri
             const uint32_t hi = min(pass_hi, lo + LIST_FACES);
             // ---- A
 #pragma unroll 1
-            for (int c = c0; c < c1; ++c) {
-                const uint32_t w = sm.tot[c * 8 + wid];
-                if (w == 0) continue;  // uniform across the warp
+            for (uint32_t todo = busy_chunks & ((1u << c1) - (1u << c0)); todo; todo &= todo - 1) {
+                const int c = __ffs(todo) - 1;  // busy chunks of the pass only (uniform across the warp)
                 const unsigned long long before = sm.part[c * 8 + wid];
                 const int r = c * 256 + tid;
                 const RowMasks k = row_masks(sm.planes, a, r);
