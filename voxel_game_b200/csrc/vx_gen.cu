@@ -176,8 +176,11 @@ __device__ int pick_tree(uint8_t base, uint64_t seed, uint32_t ax, uint32_t ay, 
 // generate_trees (trees.rs:198-241): candidates in push order (s_tree indexed x * 16 + y, the
 // column order of generator.rs:54-58; entry = tree type | base z << 8, 0 = none), each checked
 // against the voxels as modified by the trees before it.  Run by ONE warp; lanes = template cells.
-// `vox` may point to shared memory (K1) or to the area in HBM (K2).
-__device__ __forceinline__ void place_trees(uint8_t* vox, const uint16_t* s_tree, unsigned lane) {
+// `vox` may point to shared memory (K1) or to the area in HBM (K2).  Returns (to every lane) the
+// smallest z a placed tree reaches, AREA_HEIGHT if none was placed: above it, and above the
+// terrain, everything is still None.
+__device__ __forceinline__ int place_trees(uint8_t* vox, const uint16_t* s_tree, unsigned lane) {
+    int top = AREA_HEIGHT;
     for (int chunk = 0; chunk < COLUMNS_IN_AREA / 32; ++chunk) {
         const unsigned mine = s_tree[chunk * 32 + lane];
         unsigned pending = __ballot_sync(0xFFFFFFFFu, mine != 0);
@@ -199,10 +202,14 @@ __device__ __forceinline__ void place_trees(uint8_t* vox, const uint16_t* s_tree
                 ok = cx >= 0 && cx < AREA_SIZE && cy >= 0 && cy < AREA_SIZE && cz >= 0 && cz < AREA_HEIGHT;
                 if (ok) ok = vox[idx] == V_NONE;
             }
-            if (__all_sync(0xFFFFFFFFu, ok) && (int)lane < ncell) vox[idx] = cell_voxel;
+            if (__all_sync(0xFFFFFFFFu, ok) && (int)lane < ncell) {
+                vox[idx] = cell_voxel;
+                top = min(top, idx >> 8);
+            }
             __syncwarp();  // placed cells are visible to the next candidate's check
         }
     }
+    return __reduce_min_sync(0xFFFFFFFFu, top);
 }
 
 // S ("voxel != None") and T ("voxel in Voxel::TRANSPARENT") bit planes of 16-voxel rows from the
@@ -477,14 +484,17 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
         const int tree = pick_tree(vox[tid + 256u * z_top], nt.seed, ax, ay, x, y, z_top);
         sm.tree[x * 16 + y] = tree ? (uint16_t)(tree | (z_top << 8)) : (uint16_t)0;
         __syncthreads();
-        if (tid < 32) place_trees(vox, sm.tree, tid);
+        if (tid < 32) {
+            const int tree_top = place_trees(vox, sm.tree, tid);
+            if (tid == 0) sm.min_z = min(sm.min_z, tree_top);  // topmost slab that holds anything
+        }
         __syncthreads();
         // Column heights (update_all_column_heights, area.rs:34-56) and the bit planes in one walk.
-        // Slabs above z_lo are all None (trees reach at most 7 above the surface), slabs from z_hi
+        // Slabs above z_lo (the highest terrain or tree voxel) are all None, slabs from z_hi
         // on are all Stone -- so a column's height is z_hi unless something opaque lies above it.
         // In between one ballot per slab and warp gives the two rows (y = 2 * warp, 2 * warp + 1)
         // of both planes.
-        const int z_lo = max(sm.min_z - 8, 0), z_hi = AREA_HEIGHT - (int)stone_rows;
+        const int z_lo = sm.min_z, z_hi = AREA_HEIGHT - (int)stone_rows;
         uint16_t* planes = pool_planes + (size_t)slot * (VOXELS_IN_AREA / 8);
         {
             const int z = tid >> 1;  // thread i owns rows 8i .. 8i+7 = half of slab z = i / 2
@@ -739,15 +749,18 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
     const int tree = pick_tree(v, seed, ax, ay, x, y, z);
     s_tree[x * 16 + y] = tree ? (uint16_t)(tree | (z << 8)) : (uint16_t)0;
     __syncthreads();
-    if (tid < 32) place_trees(vox, s_tree, tid);
+    if (tid < 32) {
+        const int tree_top = place_trees(vox, s_tree, tid);
+        if (tid == 0) s_min_z = min(s_min_z, tree_top);  // topmost slab that holds anything
+    }
     __syncthreads();
 
     // Column heights (update_all_column_heights, area.rs:34-56) and bit planes in one walk, as in K1.
-    // Everything above min_z - 7 is still None; zi <= ALWAYS_STONE_ZI is Stone in every column of
+    // Everything above s_min_z is None; zi <= ALWAYS_STONE_ZI is Stone in every column of
     // every area (the lowest surface is 32, the deepest lake bed 34 - 10; caves start at zi = 25).
     constexpr int ALWAYS_STONE_ZI = 23;
     static_assert(ALWAYS_STONE_ZI < (int)CAVE_MIN_ZI && ALWAYS_STONE_ZI <= 32 - 4 && ALWAYS_STONE_ZI <= (int)LAKE_TOP_ZI - 10 - 1, "");
-    const int z_lo = max(s_min_z - 8, 0), z_hi = AREA_HEIGHT - ALWAYS_STONE_ZI;
+    const int z_lo = s_min_z, z_hi = AREA_HEIGHT - ALWAYS_STONE_ZI;
     uint16_t* planes = pool_planes + (size_t)slot * (VOXELS_IN_AREA / 8);
     {
         const int zt = tid >> 1;  // thread i owns rows 8i .. 8i+7 = half of slab z = i / 2
@@ -773,8 +786,8 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
         }
     }
     heights[tid] = (uint8_t)top;
-    // trees only touch the slabs from min_z - 8 down to the surface; write those back
-    const int first_row = max(s_min_z - 8, 0) * 16;
+    // trees only touch the slabs from s_min_z down to the surface; write those back
+    const int first_row = s_min_z * 16;
     for (int i = first_row + tid; i < VOXELS_IN_AREA / 16; i += 256) area[i] = s_vox[i];
     __syncthreads();  // shared memory is reused by the next area of this CTA
     }
