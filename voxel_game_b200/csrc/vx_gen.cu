@@ -522,8 +522,19 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
         heights[tid] = (uint8_t)top;
     }
 
-    uint4* dst = reinterpret_cast<uint4*>(pool_voxels + (size_t)slot * VOXELS_IN_AREA);
-    for (int i = tid; i < VOXELS_IN_AREA / 16; i += 256) dst[i] = sm.vox[i];
+    // The 32 KiB area leaves as ONE TMA bulk copy (shared -> global): every thread publishes its
+    // shared-memory writes to the async proxy, one thread issues the copy and stays until the
+    // area has been read; the other warps are done.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        uint8_t* dst = pool_voxels + (size_t)slot * VOXELS_IN_AREA;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(sm.vox)), "r"((uint32_t)VOXELS_IN_AREA)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
 }
 
 // ------------------------------------------------------------------------------------------- K1b
