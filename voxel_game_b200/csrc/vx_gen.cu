@@ -547,7 +547,8 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
 // heaviest chunk; small chunks let the global counter even the warps out.
 constexpr int CAVE_CHUNK = VX_CAVE_CHUNK;
 constexpr int CAVE_SLOTS = 32;  // table entries per warp (one per lane; those past CAVE_CHUNK stay empty)
-static_assert(CAVE_CHUNK >= 1 && CAVE_CHUNK <= CAVE_SLOTS, "one column per lane");
+static_assert(CAVE_CHUNK >= 1 && CAVE_CHUNK <= CAVE_SLOTS && (CAVE_CHUNK & (CAVE_CHUNK - 1)) == 0,
+              "one column per lane; a power of two for the column search");
 // The 14 cave octaves are evaluated in rounds: round k = octave k of noise2 (8 octaves, weights
 // .650 .228 .080 .028 ...) and, for k < 6, octave k of noise1 (6 octaves, .553 .249 .112 .050 ...).
 
@@ -661,9 +662,9 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
         if (!busy) {
             const uint32_t w = next + __popc(want & lanes_below);
             if (w < total) {
-                int lo = 0, hi = CAVE_SLOTS;  // column with first[lo] <= w < first[lo + 1]
+                int lo = 0, hi = CAVE_CHUNK;  // column with first[lo] <= w < first[lo + 1]
 #pragma unroll
-                for (int s = 0; s < 5; ++s) {
+                for (int s = 0; (1 << s) < CAVE_CHUNK; ++s) {
                     const int mid = (lo + hi) >> 1;
                     if (cw.first[mid] <= w) lo = mid; else hi = mid;
                 }
