@@ -555,7 +555,8 @@ static_assert(CAVE_CHUNK >= 1 && CAVE_CHUNK <= CAVE_SLOTS && (CAVE_CHUNK & (CAVE
 struct CaveWarp {  // per-warp description of the claimed chunk
     uint32_t first[CAVE_SLOTS + 1];  // exclusive prefix of per-column voxel counts
     uint32_t item[CAVE_SLOTS];       // slot * 256 + column
-    uint2 origin[CAVE_SLOTS];        // global x, y of the column
+    double2 oa[CAVE_CHUNK];          // the column's x, y scaled by the base frequency of noise1 ...
+    double2 ob[CAVE_CHUNK];          // ... and of noise2 (octave 0 coordinates)
 };
 struct CaveSmem {
     alignas(16) uint8_t bytes[TAB_BYTES];       // the (doubled) permutation tables (vx_noise.cuh)
@@ -630,7 +631,7 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
             } else {
                 const uint32_t idx = chunk * CAVE_CHUNK + lane;
                 uint32_t item = 0, cnt = 0;
-                uint2 org = make_uint2(0, 0);
+                double px = 0.0, py = 0.0;
                 if (lane < CAVE_CHUNK && idx < n_items) {
                     item = cave_items[idx];
                     const unsigned H = pool_heights[item] & 0x7Fu;
@@ -639,7 +640,9 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
                     const unsigned top = H < CAVE_MAX_ZI - 1 ? H : CAVE_MAX_ZI - 1;
                     cnt = top >= CAVE_MIN_ZI ? top - CAVE_MIN_ZI + 1 : 0;
                     const uint2 axy = slot_xy[item >> 8];
-                    org = make_uint2((item & 15u) + axy.x * AREA_SIZE, ((item >> 4) & 15u) + axy.y * AREA_SIZE);
+                    // algorithms.rs:19-26: u32 sum, then cast
+                    px = (double)((item & 15u) + axy.x * AREA_SIZE);
+                    py = (double)(((item >> 4) & 15u) + axy.y * AREA_SIZE);
                 }
                 uint32_t v = cnt;
 #pragma unroll
@@ -649,7 +652,10 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
                 }
                 __syncwarp();  // nobody is still reading the previous chunk's tables
                 cw.item[lane] = item;
-                cw.origin[lane] = org;
+                if (lane < CAVE_CHUNK) {
+                    cw.oa[lane] = make_double2(px * f1, py * f1);
+                    cw.ob[lane] = make_double2(px * f2, py * f2);
+                }
                 cw.first[lane + 1] = v;
                 if (lane == 0) cw.first[0] = 0;
                 __syncwarp();
@@ -670,10 +676,10 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
                 }
                 const uint32_t item = cw.item[lo];
                 const unsigned zi = CAVE_MIN_ZI + (w - cw.first[lo]);
-                const uint2 gxy = cw.origin[lo];
-                const double px = (double)gxy.x, py = (double)gxy.y, pz = (double)zi;
-                xa = px * f1; ya = py * f1; za = pz * f1;
-                xb = px * f2; yb = py * f2; zb = pz * f2;
+                const double2 oa = cw.oa[lo], ob = cw.ob[lo];
+                const double pz = (double)zi;
+                xa = oa.x; ya = oa.y; za = pz * f1;
+                xb = ob.x; yb = ob.y; zb = pz * f2;
                 a = 0.0; bsum = 0.0;
                 step = 0;
                 out_index = (size_t)(item >> 8) * VOXELS_IN_AREA + (item & 255u) + 256u * (AREA_HEIGHT - zi);
