@@ -95,6 +95,39 @@ def test_product_tree_never_references_the_oracle():
     assert "oracle" not in out
 
 
+def _make_words(text, name):
+    """Words of `NAME := ...` in a Makefile, continuation lines included."""
+    m = re.search(rf"^{name}\s*[:?]?=\s*((?:.*\\\n)*.*)$", text, flags=re.M)
+    assert m, name
+    return m.group(1).replace("\\\n", " ").split()
+
+
+def test_source_lists_agree():
+    """One list of translation units: csrc/Makefile.  rust/voxel_cuda/build.rs drives that Makefile
+    (it must not carry a list of its own), and the nvcc line INTEGRATION.md shows names exactly the
+    Makefile's sources -- a unit missing from either used to leave the documented build unlinkable."""
+    csrc = os.path.join(ROOT, "voxel_game_b200", "csrc")
+    mk = open(os.path.join(csrc, "Makefile")).read()
+    src = _make_words(mk, "SRC")
+    on_disk = sorted(f for f in os.listdir(csrc) if f.endswith((".cu", ".cpp")))
+    assert sorted(src) == on_disk, "csrc/Makefile SRC does not list every .cu/.cpp in csrc/"
+    hdr = _make_words(mk, "HDR")
+    hdr_on_disk = sorted(f for f in os.listdir(csrc) if f.endswith((".cuh", ".hpp")))
+    assert sorted(h for h in hdr if not h.startswith("..")) == hdr_on_disk
+    assert "--no-undefined" in mk
+    build_rs = open(os.path.join(ROOT, "rust", "voxel_cuda", "build.rs")).read()
+    assert 'Command::new("make")' in build_rs and "voxel_game_b200/csrc" in build_rs
+    assert not re.findall(r"vx_[a-z_]+\.(?:cu|cpp)\b", build_rs), "build.rs must not keep its own source list"
+    integ = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```\nnvcc .*?```", integ, flags=re.S)
+    assert block, "INTEGRATION.md no longer shows the nvcc command"
+    assert sorted(re.findall(r"vx_[a-z_]+\.(?:cu|cpp)\b", block.group(0))) == sorted(src)
+    # every extern "C" function of the Rust shim is declared in the header
+    lib_rs = open(os.path.join(ROOT, "rust", "voxel_cuda", "src", "lib.rs")).read()
+    rust_fns = set(re.findall(r"pub fn (vx_[a-z0-9_]+)\s*\(", lib_rs))
+    assert rust_fns <= set(_header_functions()), rust_fns - set(_header_functions())
+
+
 # ------------------------------------------------------------------------------ golden fixtures
 GOLDEN = ["spawn_8x8_test.npz", "caves_6x6_test.npz", "far_4x4_seed2.npz", "lake_4x4_test.npz", "cold_4x4_test.npz"]
 

@@ -317,11 +317,15 @@ int grow_pool(vx_ctx* ctx, int min_capacity) {
     }
     if (ctx->capacity > 0) {
         const size_t c = (size_t)ctx->capacity;
-        VX_CUDA(cudaMemcpyAsync(nv, ctx->d_voxels, c * VOXELS_IN_AREA, cudaMemcpyDeviceToDevice, ctx->stream));
-        VX_CUDA(cudaMemcpyAsync(nh, ctx->d_heights, c * COLUMNS_IN_AREA, cudaMemcpyDeviceToDevice, ctx->stream));
-        VX_CUDA(cudaMemcpyAsync(np, ctx->d_planes, c * 4096 * sizeof(uint16_t), cudaMemcpyDeviceToDevice, ctx->stream));
-        VX_CUDA(cudaMemcpyAsync(nxy, ctx->d_slot_xy, c * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
-        VX_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaError_t ce = cudaMemcpyAsync(nv, ctx->d_voxels, c * VOXELS_IN_AREA, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(nh, ctx->d_heights, c * COLUMNS_IN_AREA, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(np, ctx->d_planes, c * 4096 * sizeof(uint16_t), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(nxy, ctx->d_slot_xy, c * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+        if (ce != cudaSuccess) {  // the old pool stays in place
+            cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy);
+            return fail_cuda(ctx, ce, "pool growth copy");
+        }
         cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
     }
     ctx->d_voxels = nv; ctx->d_heights = nh; ctx->d_planes = np; ctx->d_slot_xy = nxy;
@@ -639,10 +643,14 @@ int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out
                            std::memcmp(ctx->last_gen_xy.data(), area_xy, (size_t)n * 8) == 0;
     int st;
     if (!same_list) {
+        ctx->last_gen_version = ~0ull;  // the cache describes nothing until this call has succeeded
         if ((st = acquire_slots(ctx, area_xy, n, slots)) != VX_OK) return st;
         ctx->last_gen_xy.assign(area_xy, area_xy + 2 * (size_t)n);
     }
-    if ((st = generate_async(ctx, area_xy, slots, n, same_list)) != VX_OK) return st;
+    if ((st = generate_async(ctx, area_xy, slots, n, same_list)) != VX_OK) {
+        ctx->last_gen_version = ~0ull;
+        return st;
+    }
     ctx->last_gen_version = ctx->index_version;  // d_gen_jobs now holds exactly this list
     if (voxels_out && (st = copy_slots(ctx, slots, n, ctx->d_voxels, VOXELS_IN_AREA, voxels_out, true)) != VX_OK) return st;
     if (max_height_out && (st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, max_height_out, true)) != VX_OK) return st;
@@ -728,6 +736,7 @@ int vx_column_heights(vx_ctx* ctx, const uint8_t* voxels, int n, uint8_t* max_he
     uint8_t* dh = dv + vbytes;
     VX_CUDA(cudaMemcpyAsync(dv, voxels, vbytes, cudaMemcpyHostToDevice, ctx->stream));
     if (int st = stage_ready(ctx)) return st;
+    ctx->last_mesh_version = ~0ull;  // d_jobs is overwritten: it no longer resolves the list of the last vx_mesh
     VX_CUDA(ctx->h_stage.ensure((size_t)n * sizeof(uint4)));
     VX_CUDA(ctx->d_jobs.ensure((size_t)n * sizeof(uint4)));
     uint4* j = ctx->h_stage.as<uint4>();
