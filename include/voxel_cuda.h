@@ -257,6 +257,54 @@ int vx_visible(vx_ctx* ctx, const vx_view* view, vx_visible_info* info);
  * the vx_mesh list.  Either pointer may be NULL. */
 int vx_visible_read(vx_ctx* ctx, uint32_t* rec_index, uint8_t* area_visible);
 
+/* ---- incremental re-meshing: replaces Renderer::update_location (renderer.rs:239-286) for a batch
+ * of locations (the voxels world.set has just changed -- call vx_apply_edits / vx_explode first):
+ * the voxel at each location and its <= 6 neighbours are re-meshed with generate_mesh_for_voxel
+ * (renderer.rs:126-195) on the current voxels, i.e. WITHOUT the enclosed-voxel pre-filter of a
+ * full-area load (world.rs:137-139) and with should_generate_top_face for the Up face, exactly what
+ * applying the locations one by one leaves behind.  Voxels in areas that are not resident are
+ * skipped (get_without_loading -> None, renderer.rs:241,281); an area one voxel further that a face
+ * test reads is generated first (world.get_with_cache -> load_area, world.rs:157-174).
+ * xyz: n triples of internal coordinates (z < 128).  The result is one record per touched voxel
+ * (each voxel once, in the order the reference first touches it) with its vertices and indices;
+ * a record with n_faces == 0 is RenderArea::remove (set_voxel_mesh with mesh = None,
+ * renderer.rs:214-218).  Read it with vx_update_read; it stays valid until the next
+ * vx_update_locations.  The mesh of vx_mesh is not disturbed. */
+int vx_update_locations(vx_ctx* ctx, const uint32_t* xyz, int n, vx_mesh_info* info);
+int vx_update_read(vx_ctx* ctx, vx_voxel_rec* recs, void* vertices, uint16_t* indices);
+
+/* ---- compact transport of the last vx_mesh: 4 bytes per visible voxel instead of 16 + 172 per
+ * face.  packed = (x + 16*y + 256*z) | voxel << 15 | face_mask << 20 with x, y area-local; the
+ * 16-byte record, the vertices and the indices are a pure function of it and of the area's
+ * location (host expander: voxel_game_b200/host/voxel_game.hpp `expand_records`, byte-identical
+ * to vx_mesh_read by test).  rec_first: n + 1 entries as in vx_mesh_read.  Either may be NULL. */
+#define VX_PACKED_LOCAL(p) ((p) & 0x7FFFu)
+#define VX_PACKED_VOXEL(p) (((p) >> 15) & 0x1Fu)
+#define VX_PACKED_MASK(p) (((p) >> 20) & 0x3Fu)
+int vx_mesh_read_compact(vx_ctx* ctx, uint32_t* rec_first, uint32_t* packed_recs);
+
+/* ---- mesh retention: a device-resident mirror of `Renderer.meshes: HashMap<AreaLocation,
+ * RenderArea>` (renderer.rs:97-101), so that the per-frame pass runs over the whole render zone
+ * without re-meshing anything when the zone slides or an edit lands.  While it is on, vx_mesh makes
+ * every listed area "meshed" (load_full_area) and keeps its per-voxel face masks; vx_update_locations
+ * patches them (creating the RenderArea if the area had none, renderer.rs:208-212);
+ * vx_mesh_unload is Renderer::unload_area (renderer.rs:111-117); vx_unload also drops the mesh.
+ * Costs 32 KiB + 1 byte of device memory per pool slot.  Off by default (world pre-generation and
+ * bulk loads do not need it). */
+int vx_set_mesh_retention(vx_ctx* ctx, int enabled);
+int vx_mesh_unload(vx_ctx* ctx, const uint32_t* area_xy, int n);
+/* The resident RenderArea.mesh_map of n resident areas as dense volumes: masks_out n*32768 bytes,
+ * byte x + 16*y + 256*z = face mask of that voxel's mesh, 0 = no entry; meshed_out n bytes,
+ * 1 = the area has a RenderArea.  Either may be NULL. */
+int vx_read_face_masks(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* masks_out, uint8_t* meshed_out);
+/* vx_visible over the resident meshes of the listed areas (the render zone, n <= 131072) instead
+ * of the last vx_mesh batch; areas that are not resident or not meshed draw nothing and do not
+ * count as visible (prepare_visible_areas iterates over `meshes`, renderer.rs:507-519).
+ * vx_visible_read then returns, per drawn voxel, zone index << 15 | (x + 16*y + 256*z) in
+ * rec_index (same grouping and order), info.lamps holds the same codes, and area_visible has n
+ * entries. */
+int vx_visible_zone(vx_ctx* ctx, const uint32_t* area_xy, int n, const vx_view* view, vx_visible_info* info);
+
 /* ---- L-ext (north star only; the reference has no voxel light): light levels
  * 0..15 per voxel over the resident areas listed, see DESIGN.md "L-ext". light_out n*32768. */
 int vx_light(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* light_out, int* iterations);

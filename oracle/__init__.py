@@ -137,6 +137,8 @@ def lib():
         L.vgo_mesh_areas.argtypes = [C.POINTER(_World), u32p, C.c_int, C.c_int, C.POINTER(C.c_long)]
         L.vgo_apply_edit.restype = C.c_int
         L.vgo_apply_edit.argtypes = [C.POINTER(_World), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8]
+        L.vgo_update_location.restype = None
+        L.vgo_update_location.argtypes = [C.POINTER(_World), C.c_uint32, C.c_uint32, C.c_uint32]
         L.vgo_light_flood_world.argtypes = [C.POINTER(_World), u8p]
         L.vgo_area_render_distance.restype = C.c_float
         L.vgo_area_render_distance.argtypes = [C.POINTER(C.c_float), C.c_uint32]
@@ -380,6 +382,26 @@ class World:
         """world.set + renderer.update_location."""
         if lib().vgo_apply_edit(C.byref(self._w), gx, gy, gz, voxel) != 0:
             raise ValueError("edit outside the loaded grid")
+
+    def update_location(self, gx, gy, gz):
+        """renderer.update_location alone."""
+        lib().vgo_update_location(C.byref(self._w), int(gx), int(gy), int(gz))
+
+    def area_xy(self) -> np.ndarray:
+        return region_xy(self.ax0, self.ay0, self.nx, self.ny)
+
+    def records(self, area_xy):
+        """The current meshes (face masks) of the listed areas as a record stream in index order:
+        (rec_first u32[n+1], recs) -- what Renderer.meshes holds, flattened."""
+        area_xy = np.ascontiguousarray(area_xy, np.uint32).reshape(-1, 2)
+        rec_first = np.zeros(len(area_xy) + 1, np.uint32)
+        out, base = [], 0
+        for i, (ax, ay) in enumerate(area_xy):
+            recs, _, _ = self.emit_area(int(ax), int(ay), first_face_base=base)
+            out.append(recs)
+            base += int(np.unpackbits(self.face_mask[self.slot(int(ax), int(ay))]).sum())
+            rec_first[i + 1] = rec_first[i] + len(recs)
+        return rec_first, (np.concatenate(out) if out else np.zeros(0, REC_DTYPE))
 
     def explode(self, positions):
         """BombSimulator::handle_explosions for one tick -> (removed [k,3] u32, bombs [m,3] u32), internal

@@ -282,14 +282,8 @@ static void update_meshes_for_voxel(vgo_world* w, uint32_t gx, uint32_t gy, uint
     w->face_mask[i] = (uint8_t)m; /* set_voxel_mesh: insert or remove (renderer.rs:197-219) */
 }
 
-int vgo_apply_edit(vgo_world* w, uint32_t gx, uint32_t gy, uint32_t gz, uint8_t voxel) {
-    long slot = area_slot(w, gx / VGO_AREA_SIZE, gy / VGO_AREA_SIZE);
-    if (slot < 0 || gz >= VGO_AREA_HEIGHT || voxel >= VGO_VOXEL_VARIANTS) return -1;
-    /* World::set (world.rs:184-191) -> Area::set (area.rs:99-111) */
-    vgo_area_set(w->voxels + (size_t)slot * VGO_VOXELS_IN_AREA,
-                 w->max_height + (size_t)slot * VGO_COLUMNS_IN_AREA, gx % VGO_AREA_SIZE,
-                 gy % VGO_AREA_SIZE, gz, voxel);
-    /* Renderer::update_location (renderer.rs:239-286) */
+/* Renderer::update_location (renderer.rs:239-286): the voxel, then x+1, x-1, y+1, y-1, z-1, z+1 */
+void vgo_update_location(vgo_world* w, uint32_t gx, uint32_t gy, uint32_t gz) {
     update_meshes_for_voxel(w, gx, gy, gz);
     update_meshes_for_voxel(w, gx + 1, gy, gz);
     update_meshes_for_voxel(w, gx - 1, gy, gz);
@@ -297,6 +291,16 @@ int vgo_apply_edit(vgo_world* w, uint32_t gx, uint32_t gy, uint32_t gz, uint8_t 
     update_meshes_for_voxel(w, gx, gy - 1, gz);
     if (gz > 0) update_meshes_for_voxel(w, gx, gy, gz - 1);
     if (gz < VGO_AREA_HEIGHT - 1) update_meshes_for_voxel(w, gx, gy, gz + 1);
+}
+
+int vgo_apply_edit(vgo_world* w, uint32_t gx, uint32_t gy, uint32_t gz, uint8_t voxel) {
+    long slot = area_slot(w, gx / VGO_AREA_SIZE, gy / VGO_AREA_SIZE);
+    if (slot < 0 || gz >= VGO_AREA_HEIGHT || voxel >= VGO_VOXEL_VARIANTS) return -1;
+    /* World::set (world.rs:184-191) -> Area::set (area.rs:99-111) */
+    vgo_area_set(w->voxels + (size_t)slot * VGO_VOXELS_IN_AREA,
+                 w->max_height + (size_t)slot * VGO_COLUMNS_IN_AREA, gx % VGO_AREA_SIZE,
+                 gy % VGO_AREA_SIZE, gz, voxel);
+    vgo_update_location(w, gx, gy, gz);
     return 0;
 }
 

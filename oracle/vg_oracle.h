@@ -178,6 +178,8 @@ long vgo_mesh_areas(vgo_world* w, const uint32_t* area_xy, int n, int threads, l
 /* world.set (world.rs:184-191) + renderer.update_location (renderer.rs:239-286).
  * Locations whose area is outside the grid are treated as unloaded (skipped). Returns 0 or -1. */
 int vgo_apply_edit(vgo_world* w, uint32_t gx, uint32_t gy, uint32_t gz, uint8_t voxel);
+/* renderer.update_location alone (the voxel and its <= 6 neighbours re-meshed, no pre-filter) */
+void vgo_update_location(vgo_world* w, uint32_t gx, uint32_t gy, uint32_t gz);
 
 /* ---------------------------------------------------------------- L-ext (no reference counterpart)
  * Self-specified voxel light field over the whole loaded grid, see DESIGN.md "L-ext".

@@ -102,18 +102,18 @@ int main() {
     CHECK(dirty.size() == 1 && dirty[0] == (AreaLocation{62500, 62500}));
     CHECK(world.get(lamp_at) == Voxel::Lamp);
     CHECK(world.get_height(lamp_at) == 20);
-    renderer.update_locations(world, dirty);
+    renderer.update_location(world, lamp_at);
     CHECK(renderer.get_voxel_face_count() == before + 6);  // a lone block has six faces
     CHECK(renderer.meshes().at({62500, 62500}).lights.size() == 1);
     dirty = world.set_batch({{lamp_at, Voxel::None}});
-    renderer.update_locations(world, dirty);
+    renderer.update_location(world, lamp_at);
     CHECK(renderer.get_voxel_face_count() == before);
     CHECK(renderer.meshes().at({62500, 62500}).lights.empty());
     CHECK(world.get_height(lamp_at) > 20);
 
     // one frame (renderer.rs:365-452): everything in the map view, a strict subset when looking +x
     // from the spawn column, nothing drawn twice, every drawn voxel has a mesh
-    renderer.update_locations(world, inner);  // one batch over the whole zone = the set a frame walks
+    // (the frame runs over the resident meshes of the whole zone; nothing is re-meshed for it)
     const float eye = static_cast<float>(world.get_height(Location{8, 8, 0}.to_internal())) - 3.f;  // above the ground
     const FrameResult all = renderer.render_voxels(world, Camera3D{{8.f, 8.f, eye}, {9.f, 8.f, eye}}, 8, false, true);
     CHECK(all.visible_areas == inner.size() && all.faces_visible == renderer.get_voxel_face_count());
@@ -140,6 +140,29 @@ int main() {
         threw = e.status == VX_ERR_INVALID || e.status == VX_ERR_NO_DEVICE;
     }
     CHECK(threw);
+
+    // both transports build the same Renderer.meshes: vertices rebuilt on the host from the 4-byte
+    // records (expand_voxel) equal the device's vertex stream, voxel by voxel
+    {
+        Renderer raw;
+        raw.transport = Transport::Raw;
+        raw.load_all_blocking(world, inner);
+        Renderer compact;
+        compact.threads = 3;
+        compact.load_all_blocking(world, inner);
+        CHECK(raw.get_voxel_face_count() == compact.get_voxel_face_count() && raw.get_voxel_count() == compact.get_voxel_count());
+        for (const auto& kv : raw.meshes()) {
+            const RenderArea& other = compact.meshes().at(kv.first);
+            CHECK(other.mesh_map.size() == kv.second.mesh_map.size() && other.lights.size() == kv.second.lights.size());
+            for (const auto& m : kv.second.mesh_map) {
+                const MeshInfo& a = m.second;
+                const MeshInfo& b = other.mesh_map.at(m.first);
+                CHECK(a.face_count == b.face_count && a.voxel == b.voxel && a.mesh.indices == b.mesh.indices);
+                CHECK(a.mesh.vertices.size() == b.mesh.vertices.size());
+                CHECK(std::memcmp(a.mesh.vertices.data(), b.mesh.vertices.data(), a.mesh.vertices.size() * sizeof(Vertex)) == 0);
+            }
+        }
+    }
     std::printf("test_host: all checks passed (%zu faces over %zu areas)\n", before, inner.size());
     return 0;
 }

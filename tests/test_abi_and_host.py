@@ -224,3 +224,59 @@ def test_sharded_strips_with_regenerated_halo_equal_unsharded(tmp_path):
     dig = [int(world.voxels[world.slot(int(ax), int(ay))].astype(np.uint64).sum()) for ax, ay in xy]
     assert got.shape == (2, n * n)
     assert got[0].tolist() == faces and got[1].tolist() == dig
+
+
+# ------------------------------------------------------------------------------ host expander
+def test_host_library_exports_and_links_the_cuda_library():
+    L = vg.load_host()
+    for name in vg.HOST_SYMBOLS:
+        assert hasattr(L, name), name
+    out = subprocess.run(["ldd", vg.HOST_LIB_PATH], capture_output=True, text=True).stdout
+    assert "libvoxel_cuda.so" in out and "oracle" not in out
+
+
+def _compact_from_oracle(world, xy):
+    """Face masks of the oracle's meshes -> the 4-byte records vx_mesh_read_compact would deliver."""
+    rec_first = np.zeros(len(xy) + 1, np.uint32)
+    packed = []
+    for i, (ax, ay) in enumerate(xy):
+        s = world.slot(int(ax), int(ay))
+        local = np.flatnonzero(world.face_mask[s]).astype(np.uint32)
+        packed.append(local | (world.voxels[s][local].astype(np.uint32) << 15) | (world.face_mask[s][local].astype(np.uint32) << 20))
+        rec_first[i + 1] = rec_first[i] + len(local)
+    return rec_first, np.concatenate(packed)
+
+
+@pytest.mark.parametrize("case", ["terrain", "all_types"])
+def test_host_expander_equals_oracle_emission(case):
+    """The C++ expander of the compact transport (host/voxel_game.hpp expand_voxel) against the
+    oracle's get_verticies_for_voxel restatement (oracle/mesh.c, mesh_generator.rs:200-498): records,
+    vertices and indices byte for byte -- generated terrain, and random areas with all 27 voxel types
+    (partial-height water offsets, voxels with different faces)."""
+    if case == "terrain":
+        world = oracle.World.generate(oracle.hash_world_name("test"), 62499, 62499, 4, 4)
+        xy = oracle.region_xy(62500, 62500, 2, 2)
+    else:
+        rng = np.random.default_rng(9)
+        vox = rng.integers(0, 27, (9, 32768)).astype(np.uint8)
+        vox[rng.random(vox.shape) < 0.7] = 0
+        mh = np.stack([oracle.update_all_column_heights(v) for v in vox])
+        world = oracle.World(70000, 123, 3, 3, vox, mh)
+        xy = np.array([[70001, 124]], np.uint32)
+    base, orecs, overts, oidx = 0, [], [], []
+    for ax, ay in xy:
+        nf = world.mesh_area(int(ax), int(ay))
+        r, v, i = world.emit_area(int(ax), int(ay), first_face_base=base)
+        orecs.append(r), overts.append(v), oidx.append(i)
+        base += nf
+    rec_first, packed = _compact_from_oracle(world, xy)
+    for threads in (1, 3):
+        ff, recs, verts, idx = vg.expand_records(xy, rec_first, packed, threads=threads)
+        assert ff[-1] == base
+        assert recs.tobytes() == np.concatenate(orecs).tobytes()
+        assert verts.tobytes() == np.concatenate(overts).tobytes()
+        assert np.array_equal(idx, np.concatenate(oidx))
+    assert vg.unpack_records(xy, rec_first, packed).tobytes() == recs.tobytes()
+    if case == "all_types":
+        kinds = set(np.unique((packed >> 15) & 0x1F).tolist())
+        assert kinds == set(range(1, 27)) and base > 20000

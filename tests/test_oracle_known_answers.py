@@ -358,3 +358,38 @@ def test_apply_edit_updates_six_neighbours_and_heights():
     assert w.face_mask[4][col + 256 * (top + 1)] & 32                 # voxel below gains Up
     changed = np.flatnonzero(before != w.face_mask[4])
     assert 1 <= changed.size <= 7
+
+
+def test_batched_updates_equal_sequential_updates():
+    """The batching rule vx_update_locations relies on (csrc/vx_update.cu header): after a batch of
+    world.set + update_location pairs applied one by one (renderer.rs:239-286), every touched voxel
+    holds generate_mesh_for_voxel of the FINAL voxels, so "all sets first, then all updates" leaves
+    the same Renderer.meshes -- including enclosed partial-height water that only an update gives
+    an Up face.  Checked on the oracle alone, with all 27 voxel types and duplicate locations."""
+    rng = np.random.default_rng(21)
+    n = 3
+    vox = rng.integers(0, 27, (n * n, 32768)).astype(np.uint8)
+    vox[rng.random(vox.shape) < 0.4] = 0
+    vox.reshape(n * n, 128, 16, 16)[:, 60:70] = rng.integers(16, 20, (n * n, 10, 16, 16))  # a water slab
+    mh = np.stack([oracle.update_all_column_heights(v) for v in vox])
+    seq = oracle.World(10, 20, n, n, vox.copy(), mh.copy())
+    bat = oracle.World(10, 20, n, n, vox.copy(), mh.copy())
+    for w in (seq, bat):
+        w.mesh_area(11, 21)
+    k = 4000
+    gx = rng.integers(11 * 16 - 1, 12 * 16 + 1, k)
+    gy = rng.integers(21 * 16 - 1, 22 * 16 + 1, k)
+    gz = rng.integers(0, 128, k)
+    gx[-50:], gy[-50:], gz[-50:] = gx[:50], gy[:50], gz[:50]
+    new = rng.integers(0, 27, k)
+    for i in range(k):
+        seq.apply_edit(int(gx[i]), int(gy[i]), int(gz[i]), int(new[i]))
+    for i in range(k):  # all sets (array order: the last writer wins) ...
+        slot = bat.slot(int(gx[i]) // 16, int(gy[i]) // 16)
+        bat.voxels[slot][(gx[i] % 16) + 16 * (gy[i] % 16) + 256 * gz[i]] = new[i]
+    for i in rng.permutation(k):  # ... then all updates, in any order
+        bat.update_location(int(gx[i]), int(gy[i]), int(gz[i]))
+    assert np.array_equal(seq.voxels, bat.voxels)
+    assert np.array_equal(seq.face_mask, bat.face_mask)
+    water = (seq.voxels >= V["Water1"]) & (seq.voxels <= V["Water4"])
+    assert ((seq.face_mask == 32) & water).sum() > 0

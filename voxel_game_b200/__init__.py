@@ -6,10 +6,11 @@ this package is the thin Python plumbing used by tests and bench.py.  No CPU fal
 """
 from .binding import (  # noqa: F401
     ABI_SYMBOLS, EDIT_DTYPE, LIB_PATH, REC_DTYPE, VERTEX_DTYPE, Context, PinnedArray, View, VxError,
-    build, hash_world_name, load, make_view,
+    build, hash_world_name, load, make_view, unpack_records,
 )
-from .world import region_xy, shard_rows, spawn_region  # noqa: F401
+from .host import HOST_LIB_PATH, HOST_SYMBOLS, HostRenderer, expand_records, load_host  # noqa: F401
+from .world import region_xy, render_zone, shard_rows, spawn_region  # noqa: F401
 
 __all__ = ["Context", "PinnedArray", "VxError", "build", "load", "hash_world_name", "region_xy",
            "shard_rows", "spawn_region", "ABI_SYMBOLS", "REC_DTYPE", "VERTEX_DTYPE", "EDIT_DTYPE",
-           "LIB_PATH", "View", "make_view"]
+           "LIB_PATH", "View", "make_view", "unpack_records", "render_zone"]

@@ -41,7 +41,8 @@ ABI_SYMBOLS = [
     "vx_hash_world_name", "vx_generate", "vx_upload", "vx_read_areas", "vx_unload",
     "vx_resident_count", "vx_column_heights", "vx_mesh", "vx_mesh_read", "vx_apply_edits",
     "vx_heightmap", "vx_visible", "vx_visible_read", "vx_encode_areas", "vx_encode_read", "vx_decode_areas",
-    "vx_explode", "vx_light", "vx_diag_fp64_rate",
+    "vx_explode", "vx_light", "vx_diag_fp64_rate", "vx_update_locations", "vx_update_read",
+    "vx_mesh_read_compact", "vx_set_mesh_retention", "vx_mesh_unload", "vx_read_face_masks", "vx_visible_zone",
 ]
 
 
@@ -105,6 +106,9 @@ def build(verbose: bool = False) -> str:
         raise RuntimeError("building libvoxel_cuda.so failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stdout)
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "host")], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libvoxel_host.so failed:\n" + r.stdout + r.stderr)
     return LIB_PATH
 
 
@@ -161,6 +165,13 @@ def load():
     L.vx_visible_read.argtypes = [vp, vp, vp]
     L.vx_light.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int)]
     L.vx_diag_fp64_rate.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    L.vx_update_locations.argtypes = [vp, vp, C.c_int, C.POINTER(MeshInfo)]
+    L.vx_update_read.argtypes = [vp, vp, vp, vp]
+    L.vx_mesh_read_compact.argtypes = [vp, vp, vp]
+    L.vx_set_mesh_retention.argtypes = [vp, C.c_int]
+    L.vx_mesh_unload.argtypes = [vp, vp, C.c_int]
+    L.vx_read_face_masks.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.vx_visible_zone.argtypes = [vp, vp, C.c_int, C.POINTER(View), C.POINTER(VisibleInfo)]
     for name in ABI_SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("vx_device_count",):
@@ -198,6 +209,31 @@ class PinnedArray:
             self.free()
         except Exception:
             pass
+
+
+def unpack_records(area_xy, rec_first, packed) -> np.ndarray:
+    """4-byte records of mesh_read_compact -> the 16-byte records of mesh_read (numpy; tests and
+    tools -- the product-side expander is the C++ one in host/voxel_game.hpp)."""
+    xy = _xy(area_xy).astype(np.uint64)
+    rec_first = np.asarray(rec_first, np.int64)
+    packed = np.asarray(packed, np.uint32)
+    area = np.repeat(np.arange(len(xy)), np.diff(rec_first))
+    local = packed & 0x7FFF
+    voxel = (packed >> 15) & 0x1F
+    mask = (packed >> 20) & 0x3F
+    nf = np.zeros_like(mask)
+    for b in range(6):
+        nf += (mask >> b) & 1
+    recs = np.zeros(len(packed), REC_DTYPE)
+    recs["gx"] = (xy[area, 0] * 16 + (local & 15)).astype(np.uint32)
+    recs["gy"] = (xy[area, 1] * 16 + ((local >> 4) & 15)).astype(np.uint32)
+    recs["packed"] = (local >> 8) | (voxel << 8) | (mask << 16) | (nf << 24)
+    # first_face: running face count over the whole stream (areas in call order)
+    first = np.zeros(len(packed), np.uint64)
+    if len(packed):
+        first[1:] = np.cumsum(nf.astype(np.uint64))[:-1]
+    recs["first_face"] = first.astype(np.uint32)
+    return recs
 
 
 def _xy(area_xy) -> np.ndarray:
@@ -329,6 +365,66 @@ class Context:
         rf, ff, recs, verts, idx = out
         self._check(self._lib.vx_mesh_read(self._h, _ptr(rf), _ptr(ff), _ptr(recs), _ptr(verts), _ptr(idx)))
         return out
+
+    def mesh_read_compact(self, info: dict, out=None):
+        """The last mesh as 4-byte records: (rec_first u32[n+1], packed u32[n_recs]); see
+        unpack_records / the C++ expander for the way back."""
+        n = self._mesh_n
+        if out is None:
+            out = (np.empty(n + 1, np.uint32), np.empty(info["n_recs"], np.uint32))
+        rf, packed = out
+        self._check(self._lib.vx_mesh_read_compact(self._h, _ptr(rf), _ptr(packed)))
+        return out
+
+    # -- Renderer.meshes on the device
+    def set_mesh_retention(self, enabled: bool):
+        self._check(self._lib.vx_set_mesh_retention(self._h, int(enabled)))
+
+    def mesh_unload(self, area_xy):
+        xy = _xy(area_xy)
+        self._check(self._lib.vx_mesh_unload(self._h, xy.ctypes.data, xy.shape[0]))
+
+    def read_face_masks(self, area_xy):
+        """-> (face masks u8[n,32768], meshed u8[n]) of resident areas (mesh retention must be on)."""
+        xy = _xy(area_xy)
+        n = xy.shape[0]
+        masks = np.empty((n, VOXELS_IN_AREA), np.uint8)
+        meshed = np.empty(n, np.uint8)
+        self._check(self._lib.vx_read_face_masks(self._h, xy.ctypes.data, n, masks.ctypes.data, meshed.ctypes.data))
+        return masks, meshed
+
+    def update_locations(self, xyz, read: bool = True):
+        """Renderer::update_location for a batch of internal locations [k,3] -> info dict and, if
+        read, (recs, vertices, indices); records with n_faces == 0 are removals."""
+        loc = np.ascontiguousarray(xyz, np.uint32).reshape(-1, 3)
+        info = MeshInfo()
+        self._check(self._lib.vx_update_locations(self._h, loc.ctypes.data, loc.shape[0], C.byref(info)))
+        d = {k: int(getattr(info, k)) for k, _ in info._fields_}
+        if not read:
+            return d
+        recs = np.empty(d["n_recs"], REC_DTYPE)
+        verts = np.empty(d["n_faces"] * 4, VERTEX_DTYPE)
+        idx = np.empty(d["n_faces"] * 6, np.uint16)
+        self._check(self._lib.vx_update_read(self._h, _ptr(recs) if recs.size else None,
+                                             _ptr(verts) if verts.size else None, _ptr(idx) if idx.size else None))
+        return d, recs, verts, idx
+
+    def visible_zone(self, area_xy, view: View, read: bool = True):
+        """Per-frame visibility over the resident meshes of a render zone -> dict and, if read,
+        (codes u32[n_visible] = zone index << 15 | local voxel index, area_visible u8[n])."""
+        xy = _xy(area_xy)
+        info = VisibleInfo()
+        self._check(self._lib.vx_visible_zone(self._h, xy.ctypes.data, xy.shape[0], C.byref(view), C.byref(info)))
+        out = dict(n_visible=int(info.n_visible), n_faces=int(info.n_faces), n_areas=int(info.n_areas),
+                   n_lamps=int(info.n_lamps), type_first=np.array(info.type_first[:], np.uint32),
+                   lamps=np.array(info.lamps[: min(64, int(info.n_lamps))], np.uint32))
+        if not read:
+            return out
+        idx = np.empty(out["n_visible"], np.uint32)
+        flags = np.empty(xy.shape[0], np.uint8)
+        self._check(self._lib.vx_visible_read(self._h, idx.ctypes.data if idx.size else None,
+                                              flags.ctypes.data if flags.size else None))
+        return out, idx, flags
 
     # -- edits
     def apply_edits(self, edits) -> np.ndarray:

@@ -72,6 +72,19 @@ struct HostAreaMap {
     std::vector<uint4> e;
     uint32_t mask = 0;
     size_t count = 0;
+    // entries written since the device copy was last brought up to date (upload_map): a handful of
+    // changes travel as {index, entry} patches, a rebuilt or heavily changed table as a whole
+    std::vector<uint32_t> touched;
+    bool all_touched = true;
+    void touch(uint32_t h) {
+        if (all_touched) return;
+        if (touched.size() >= 4096) {
+            all_touched = true;
+            touched.clear();
+        } else {
+            touched.push_back(h);
+        }
+    }
 
     HostAreaMap() { e.assign(64, make_uint4(0, 0, 0, 0)); mask = 63; }
     int find(uint32_t ax, uint32_t ay) const {
@@ -87,6 +100,8 @@ struct HostAreaMap {
         old.swap(e);
         e.assign(old.size() * 2, make_uint4(0, 0, 0, 0));
         mask = (uint32_t)e.size() - 1;
+        all_touched = true;
+        touched.clear();
         for (const uint4& v : old)
             if (v.w) place(v.x, v.y, v.z);
     }
@@ -94,6 +109,7 @@ struct HostAreaMap {
         uint32_t h = area_hash(ax, ay) & mask;
         while (e[h].w) h = (h + 1) & mask;
         e[h] = make_uint4(ax, ay, slot, 1u);
+        touch(h);
     }
     void insert(uint32_t ax, uint32_t ay, int slot) {  // key must be absent
         if (2 * (count + 1) > e.size()) grow();
@@ -112,10 +128,12 @@ struct HostAreaMap {
             const uint32_t home = area_hash(e[j].x, e[j].y) & mask;
             if (((j - home) & mask) >= ((j - hole) & mask)) {
                 e[hole] = e[j];
+                touch(hole);
                 hole = j;
             }
         }
         e[hole] = make_uint4(0, 0, 0, 0);
+        touch(hole);
         --count;
         return slot;
     }
@@ -143,6 +161,12 @@ struct vx_ctx {
     uint8_t* d_heights = nullptr;
     uint16_t* d_planes = nullptr;
     uint2* d_slot_xy = nullptr;
+    // device mirror of Renderer.meshes (only while mesh retention is on, vx_update.cu): per slot one
+    // face-mask byte per voxel (0 = no mesh entry) and a "has a RenderArea" flag; the volume of a slot
+    // that is not meshed is all zero
+    bool retention = false;
+    uint8_t* d_face = nullptr;
+    uint8_t* d_meshed = nullptr;
     std::vector<uint64_t> slot_key;    // per slot; ~0 = free
     std::vector<int> free_slots;
     HostAreaMap index;
@@ -155,7 +179,10 @@ struct vx_ctx {
 
     // device copy of `index` (see AreaMap)
     uint32_t map_mask = 0;
-    DevBuf d_map;
+    DevBuf d_map, d_map_patch;
+    PinnedBuf h_map;             // staging of the table / of the patches on their way to the device
+    cudaEvent_t map_ev = nullptr;
+    bool map_pending = false;
     bool map_dirty = true;
 
     // scratch
@@ -172,6 +199,12 @@ struct vx_ctx {
     DevBuf d_heightmap, d_light, d_slot_to_job, d_finished, d_warp_totals, d_mesh_nbr;
     DevBuf d_mesh_xy, d_frame_flags, d_frame_counts, d_frame_small, d_frame_visible;  // per-frame visibility (K7)
     DevBuf d_codec_sizes, d_codec_offsets, d_codec_bytes, d_codec_status, d_codec_kinds;  // area save files (K8 / K9)
+    // incremental updates (vx_update_locations) and the compact record transport
+    DevBuf d_upd_xyz, d_upd_slot, d_upd_info, d_upd_rec_count, d_upd_face_count, d_upd_rec_first, d_upd_face_first;
+    DevBuf d_upd_recs, d_upd_vertices, d_upd_indices, d_packed, d_zone_xy, d_zone_slot;
+    int upd_n = -1;                // locations of the last vx_update_locations
+    vx_mesh_info upd_info{};
+    int frame_areas = 0;           // areas the result of the last vx_visible / vx_visible_zone covers
     int codec_n = -1;              // areas of the last vx_encode_areas
     uint64_t codec_total = 0;
     bool frame_ready = false;      // d_frame_visible / d_frame_flags hold the result of vx_visible for this mesh
@@ -285,6 +318,7 @@ int sync_stream(vx_ctx* ctx) {
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     VX_CUDA(cudaGetLastError());
     ctx->stage_pending = false;
+    ctx->map_pending = false;
     collect_timers(ctx);
     return VX_OK;
 }
@@ -293,27 +327,42 @@ int sync_stream(vx_ctx* ctx) {
 int grow_pool(vx_ctx* ctx, int min_capacity) {
     if (min_capacity <= ctx->capacity) return VX_OK;
     int new_cap = std::max({min_capacity, ctx->capacity * 2, 256});
-    uint8_t *nv = nullptr, *nh = nullptr;
+    uint8_t *nv = nullptr, *nh = nullptr, *nf = nullptr, *nm = nullptr;
     uint16_t* np = nullptr;
     uint2* nxy = nullptr;
+    auto free_new = [&]() {
+        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy); cudaFree(nf); cudaFree(nm);
+        nv = nh = nf = nm = nullptr; np = nullptr; nxy = nullptr;
+    };
     auto alloc_all = [&](int cap) -> cudaError_t {
         cudaError_t e;
         if ((e = cudaMalloc(&nv, (size_t)cap * VOXELS_IN_AREA)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&nh, (size_t)cap * COLUMNS_IN_AREA)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&np, (size_t)cap * 4096 * sizeof(uint16_t))) != cudaSuccess) return e;
+        if (ctx->retention) {
+            if ((e = cudaMalloc(&nf, (size_t)cap * VOXELS_IN_AREA)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&nm, (size_t)cap)) != cudaSuccess) return e;
+        }
         return cudaMalloc(&nxy, (size_t)cap * sizeof(uint2));
     };
     cudaError_t e = alloc_all(new_cap);
     if (e != cudaSuccess && new_cap > min_capacity) {
         cudaGetLastError();
-        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy);
-        nv = nh = nullptr; np = nullptr; nxy = nullptr;
+        free_new();
         new_cap = min_capacity;
         e = alloc_all(new_cap);
     }
     if (e != cudaSuccess) {
-        cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy);
+        free_new();
         return fail_cuda(ctx, e, "pool allocation");
+    }
+    if (ctx->retention) {  // slots that have never been meshed hold an empty mesh
+        cudaError_t ce = cudaMemsetAsync(nf, 0, (size_t)new_cap * VOXELS_IN_AREA, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(nm, 0, (size_t)new_cap, ctx->stream);
+        if (ce != cudaSuccess) {
+            free_new();
+            return fail_cuda(ctx, ce, "pool allocation (mesh retention)");
+        }
     }
     if (ctx->capacity > 0) {
         const size_t c = (size_t)ctx->capacity;
@@ -321,14 +370,18 @@ int grow_pool(vx_ctx* ctx, int min_capacity) {
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(nh, ctx->d_heights, c * COLUMNS_IN_AREA, cudaMemcpyDeviceToDevice, ctx->stream);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(np, ctx->d_planes, c * 4096 * sizeof(uint16_t), cudaMemcpyDeviceToDevice, ctx->stream);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(nxy, ctx->d_slot_xy, c * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (ce == cudaSuccess && ctx->retention) ce = cudaMemcpyAsync(nf, ctx->d_face, c * VOXELS_IN_AREA, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (ce == cudaSuccess && ctx->retention) ce = cudaMemcpyAsync(nm, ctx->d_meshed, c, cudaMemcpyDeviceToDevice, ctx->stream);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
         if (ce != cudaSuccess) {  // the old pool stays in place
-            cudaFree(nv); cudaFree(nh); cudaFree(np); cudaFree(nxy);
+            free_new();
             return fail_cuda(ctx, ce, "pool growth copy");
         }
         cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
+        cudaFree(ctx->d_face); cudaFree(ctx->d_meshed);
     }
     ctx->d_voxels = nv; ctx->d_heights = nh; ctx->d_planes = np; ctx->d_slot_xy = nxy;
+    ctx->d_face = nf; ctx->d_meshed = nm;
     ctx->slot_key.resize(new_cap, ~0ull);
     for (int s = new_cap - 1; s >= ctx->capacity; --s) ctx->free_slots.push_back(s);  // pop -> ascending
     ctx->capacity = new_cap;
@@ -366,13 +419,44 @@ int acquire_slots(vx_ctx* ctx, const uint32_t* area_xy, int n, std::vector<int>&
     return VX_OK;
 }
 
+// Brings the device copy of the area map up to date, in stream order and without waiting: the table
+// (or, after a few changes, just the changed entries) goes through a pinned staging buffer of its
+// own; map_ev tells when the previous upload has finished reading that buffer.
 int upload_map(vx_ctx* ctx) {
     if (!ctx->map_dirty) return VX_OK;
-    const size_t bytes = ctx->index.e.size() * sizeof(uint4);
-    VX_CUDA(ctx->d_map.ensure(bytes));
-    VX_CUDA(cudaMemcpyAsync(ctx->d_map.p, ctx->index.e.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-    VX_CUDA(cudaStreamSynchronize(ctx->stream));  // the table is pageable and changes later
-    ctx->map_mask = ctx->index.mask;
+    HostAreaMap& m = ctx->index;
+    const size_t bytes = m.e.size() * sizeof(uint4);
+    const bool whole = m.all_touched || ctx->d_map.cap < bytes || ctx->map_mask != m.mask;
+    if (ctx->map_pending) {
+        VX_CUDA(cudaEventSynchronize(ctx->map_ev));
+        ctx->map_pending = false;
+    }
+    if (whole) {
+        if (ctx->d_map.cap < bytes) {  // the old table may still be read by kernels in flight
+            VX_CUDA(cudaStreamSynchronize(ctx->stream));
+            VX_CUDA(ctx->d_map.ensure(bytes));
+        }
+        VX_CUDA(ctx->h_map.ensure(bytes));
+        std::memcpy(ctx->h_map.p, m.e.data(), bytes);
+        VX_CUDA(cudaMemcpyAsync(ctx->d_map.p, ctx->h_map.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else if (!m.touched.empty()) {
+        const size_t k = m.touched.size();
+        VX_CUDA(ctx->h_map.ensure(k * 32));
+        VX_CUDA(ctx->d_map_patch.ensure(k * 32));
+        uint4* stage = ctx->h_map.as<uint4>();
+        for (size_t i = 0; i < k; ++i) {  // {index, -, -, -}, {entry}: later patches of one entry repeat its final value
+            stage[2 * i] = make_uint4(m.touched[i], 0u, 0u, 0u);
+            stage[2 * i + 1] = m.e[m.touched[i]];
+        }
+        VX_CUDA(cudaMemcpyAsync(ctx->d_map_patch.p, stage, k * 32, cudaMemcpyHostToDevice, ctx->stream));
+        launch_map_patch(ctx->d_map_patch.as<uint4>(), (int)k, ctx->d_map.as<uint4>(), ctx->stream);
+        VX_CUDA(cudaGetLastError());
+    }
+    VX_CUDA(cudaEventRecord(ctx->map_ev, ctx->stream));
+    ctx->map_pending = true;
+    m.touched.clear();
+    m.all_touched = false;
+    ctx->map_mask = m.mask;
     ctx->map_dirty = false;
     return VX_OK;
 }
@@ -459,6 +543,21 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
     return VX_OK;
 }
 
+// mesh retention: the listed slots lose their RenderArea (face volume zero, flag cleared); one
+// memset per run of consecutive slots, in stream order
+int clear_mesh_slots(vx_ctx* ctx, std::vector<int>& slots) {
+    std::sort(slots.begin(), slots.end());
+    size_t i = 0;
+    while (i < slots.size()) {
+        size_t j = i + 1;
+        while (j < slots.size() && slots[j] == slots[j - 1] + 1) ++j;
+        VX_CUDA(cudaMemsetAsync(ctx->d_face + (size_t)slots[i] * VOXELS_IN_AREA, 0, (j - i) * VOXELS_IN_AREA, ctx->stream));
+        VX_CUDA(cudaMemsetAsync(ctx->d_meshed + slots[i], 0, j - i, ctx->stream));
+        i = j;
+    }
+    return VX_OK;
+}
+
 }  // namespace
 
 // =========================================================================================== ABI
@@ -514,6 +613,7 @@ int vx_create(int device, vx_ctx** out) {
         for (int k = 0; k < 2; ++k) cudaEventCreate(&ctx->ev[i][k]);
     cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->totals_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->map_ev, cudaEventDisableTiming);
     if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_totals), 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
         cudaGetLastError();
         vx_destroy(ctx);
@@ -528,19 +628,25 @@ void vx_destroy(vx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
+    cudaFree(ctx->d_face); cudaFree(ctx->d_meshed);
     cudaFree(ctx->d_noise_image);
-    DevBuf* bufs[] = {&ctx->d_map, &ctx->d_jobs, &ctx->d_gen_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters, &ctx->d_gen_counters,
+    DevBuf* bufs[] = {&ctx->d_map, &ctx->d_map_patch, &ctx->d_jobs, &ctx->d_gen_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters, &ctx->d_gen_counters,
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
                       &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_warp_totals, &ctx->d_mesh_nbr, &ctx->d_mesh_xy, &ctx->d_frame_flags,
                       &ctx->d_frame_counts, &ctx->d_frame_small, &ctx->d_frame_visible, &ctx->d_codec_sizes,
                       &ctx->d_codec_offsets, &ctx->d_codec_bytes, &ctx->d_codec_status, &ctx->d_codec_kinds, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
-                      &ctx->d_vertices, &ctx->d_indices};
+                      &ctx->d_vertices, &ctx->d_indices, &ctx->d_upd_xyz, &ctx->d_upd_slot, &ctx->d_upd_info,
+                      &ctx->d_upd_rec_count, &ctx->d_upd_face_count, &ctx->d_upd_rec_first, &ctx->d_upd_face_first,
+                      &ctx->d_upd_recs, &ctx->d_upd_vertices, &ctx->d_upd_indices, &ctx->d_packed, &ctx->d_zone_xy,
+                      &ctx->d_zone_slot};
     for (DevBuf* b : bufs) b->release();
     ctx->h_stage.release();
     ctx->h_small.release();
     cudaEventDestroy(ctx->stage_ev);
     cudaEventDestroy(ctx->totals_ev);
+    cudaEventDestroy(ctx->map_ev);
+    ctx->h_map.release();
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     for (int i = 0; i < TM_COUNT; ++i)
         for (int k = 0; k < 2; ++k) cudaEventDestroy(ctx->ev[i][k]);
@@ -702,14 +808,20 @@ int vx_unload(vx_ctx* ctx, const uint32_t* area_xy, int n) {
     if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     bool any = false;
+    std::vector<int> freed;
     for (int i = 0; i < n; ++i) {
         const int s = ctx->index.erase(area_xy[2 * i], area_xy[2 * i + 1]);
         if (s < 0) continue;
         ctx->slot_key[s] = ~0ull;
         ctx->free_slots.push_back(s);
+        freed.push_back(s);
         any = true;
     }
     if (any) {
+        if (ctx->retention) {  // a slot that is handed out again starts without a mesh
+            VX_CUDA(cudaSetDevice(ctx->device));
+            if (int st = clear_mesh_slots(ctx, freed)) return st;
+        }
         ctx->map_dirty = true;
         ++ctx->index_version;
         // keep hand-out order ascending so later batches stay contiguous where possible
@@ -885,6 +997,12 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
         }
         ctx->mesh_info.n_faces = n_faces;
         ctx->mesh_info.n_recs = n_recs;
+        if (ctx->retention) {  // RenderArea of every listed area := the records just emitted
+            launch_mesh_retain(ctx->d_jobs.as<uint4>(), n, ctx->d_rec_first.as<uint32_t>(), ctx->d_recs.as<uint4>(),
+                               ctx->d_face, ctx->d_meshed, ctx->stream);
+            ctx->timings.mesh_launches += 1;
+            VX_CUDA(cudaGetLastError());
+        }
     }
     ctx->mesh_info.vertex_bytes = ctx->mesh_info.n_faces * 160;
     ctx->mesh_info.index_bytes = ctx->mesh_info.n_faces * 12;
@@ -1046,6 +1164,7 @@ int vx_visible(vx_ctx* ctx, const vx_view* view, vx_visible_info* info) {
     ctx->frame_n_visible = 0;
     const int n = ctx->mesh_n;
     if (n == 0) {
+        ctx->frame_areas = 0;
         ctx->frame_ready = true;
         return VX_OK;
     }
@@ -1089,6 +1208,7 @@ int vx_visible(vx_ctx* ctx, const vx_view* view, vx_visible_info* info) {
     const uint32_t nl = std::min<uint32_t>(h->n_lamps, VX_MAX_LIGHTS);
     std::memcpy(info->lamps, h->lamps, nl * sizeof(uint32_t));
     ctx->frame_n_visible = info->n_visible;
+    ctx->frame_areas = n;
     ctx->frame_ready = true;
     return VX_OK;
 }
@@ -1096,13 +1216,13 @@ int vx_visible(vx_ctx* ctx, const vx_view* view, vx_visible_info* info) {
 int vx_visible_read(vx_ctx* ctx, uint32_t* rec_index, uint8_t* area_visible) {
     if (!ctx) return VX_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    if (ctx->mesh_n < 0 || !ctx->frame_ready) return fail(ctx, VX_ERR_NO_MESH, "vx_visible_read without vx_visible");
+    if (!ctx->frame_ready) return fail(ctx, VX_ERR_NO_MESH, "vx_visible_read without vx_visible");
     VX_CUDA(cudaSetDevice(ctx->device));
-    if (ctx->mesh_n == 0) return VX_OK;
+    if (ctx->frame_areas == 0) return VX_OK;
     if (rec_index && ctx->frame_n_visible)
         VX_CUDA(cudaMemcpyAsync(rec_index, ctx->d_frame_visible.p, ctx->frame_n_visible * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (area_visible)
-        VX_CUDA(cudaMemcpyAsync(area_visible, ctx->d_frame_flags.p, (size_t)ctx->mesh_n, cudaMemcpyDeviceToHost, ctx->stream));
+        VX_CUDA(cudaMemcpyAsync(area_visible, ctx->d_frame_flags.p, (size_t)ctx->frame_areas, cudaMemcpyDeviceToHost, ctx->stream));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }
@@ -1319,6 +1439,303 @@ int vx_light(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* light_out, in
     VX_CUDA(cudaMemcpyAsync(light_out, ctx->d_light.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (iterations) *iterations = iters;
     return sync_stream(ctx);
+}
+
+int vx_set_mesh_retention(vx_ctx* ctx, int enabled) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    const bool on = enabled != 0;
+    if (on == ctx->retention) return VX_OK;
+    int st;
+    if ((st = sync_stream(ctx)) != VX_OK) return st;
+    if (on) {
+        if (ctx->capacity > 0) {
+            VX_CUDA(cudaMalloc(&ctx->d_face, (size_t)ctx->capacity * VOXELS_IN_AREA));
+            cudaError_t e = cudaMalloc(&ctx->d_meshed, (size_t)ctx->capacity);
+            if (e != cudaSuccess) {
+                cudaFree(ctx->d_face);
+                ctx->d_face = nullptr;
+                return fail_cuda(ctx, e, "mesh retention allocation");
+            }
+            VX_CUDA(cudaMemsetAsync(ctx->d_face, 0, (size_t)ctx->capacity * VOXELS_IN_AREA, ctx->stream));
+            VX_CUDA(cudaMemsetAsync(ctx->d_meshed, 0, (size_t)ctx->capacity, ctx->stream));
+        }
+    } else {
+        cudaFree(ctx->d_face);
+        cudaFree(ctx->d_meshed);
+        ctx->d_face = ctx->d_meshed = nullptr;
+    }
+    ctx->retention = on;
+    return VX_OK;
+}
+
+int vx_mesh_unload(vx_ctx* ctx, const uint32_t* area_xy, int n) {
+    if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->retention || n == 0) return VX_OK;  // nothing is kept on the device
+    VX_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int> slots;
+    for (int i = 0; i < n; ++i) {
+        const int s = host_slot(ctx, area_xy[2 * i], area_xy[2 * i + 1]);
+        if (s >= 0) slots.push_back(s);
+    }
+    return clear_mesh_slots(ctx, slots);
+}
+
+int vx_read_face_masks(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* masks_out, uint8_t* meshed_out) {
+    if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->retention) return fail(ctx, VX_ERR_NO_MESH, "vx_read_face_masks: mesh retention is off");
+    VX_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int> slots(n);
+    for (int i = 0; i < n; ++i) {
+        slots[i] = host_slot(ctx, area_xy[2 * i], area_xy[2 * i + 1]);
+        if (slots[i] < 0) return fail(ctx, VX_ERR_NOT_LOADED, "vx_read_face_masks: area not resident");
+    }
+    int st;
+    if (masks_out && (st = copy_slots(ctx, slots, n, ctx->d_face, VOXELS_IN_AREA, masks_out, true)) != VX_OK) return st;
+    if (meshed_out && (st = copy_slots(ctx, slots, n, ctx->d_meshed, 1, meshed_out, true)) != VX_OK) return st;
+    return sync_stream(ctx);
+}
+
+int vx_update_locations(vx_ctx* ctx, const uint32_t* xyz, int n, vx_mesh_info* info) {
+    if (!ctx || n < 0 || (n > 0 && !xyz)) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    ctx->upd_n = -1;
+    ctx->upd_info = vx_mesh_info{};
+    if (info) *info = ctx->upd_info;
+    if (n == 0) {
+        ctx->upd_n = 0;
+        return VX_OK;
+    }
+    for (int i = 0; i < n; ++i)
+        if (xyz[3 * i + 2] >= (uint32_t)AREA_HEIGHT) return fail(ctx, VX_ERR_INVALID, "vx_update_locations: z >= 128");
+    if (ctx->capacity == 0) {  // nothing is loaded: get_without_loading -> None for every location
+        ctx->upd_n = n;
+        return VX_OK;
+    }
+    int st;
+    const uint32_t n_cand = 7u * (uint32_t)n, n_blocks = (n_cand + 255u) / 256u;
+    uint32_t cap = 1024;
+    while (cap < n_cand * 2u) cap <<= 1;
+    VX_CUDA(ctx->d_hash_keys.ensure((size_t)cap * 8));
+    VX_CUDA(ctx->d_hash_vals.ensure((size_t)cap * 4));
+    VX_CUDA(ctx->d_counters.ensure(64));
+    VX_CUDA(ctx->d_upd_xyz.ensure((size_t)n * 12));
+    VX_CUDA(ctx->d_upd_slot.ensure((size_t)n_cand * 4));
+    VX_CUDA(ctx->d_upd_info.ensure((size_t)n_cand * 2));
+    VX_CUDA(ctx->d_upd_rec_count.ensure((size_t)(n_blocks + 16) * 4));
+    VX_CUDA(ctx->d_upd_face_count.ensure((size_t)(n_blocks + 16) * 4));
+    VX_CUDA(ctx->d_upd_rec_first.ensure((size_t)(n_blocks + 17) * 4));
+    VX_CUDA(ctx->d_upd_face_first.ensure((size_t)(n_blocks + 17) * 4));
+    if ((st = upload_map(ctx)) != VX_OK) return st;
+    VX_CUDA(cudaMemsetAsync(ctx->d_hash_keys.p, 0xFF, (size_t)cap * 8, ctx->stream));
+    VX_CUDA(cudaMemsetAsync(ctx->d_hash_vals.p, 0xFF, (size_t)cap * 4, ctx->stream));
+    VX_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
+    VX_CUDA(cudaMemcpyAsync(ctx->d_upd_xyz.p, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t* d_xyz = ctx->d_upd_xyz.as<uint32_t>();
+    uint32_t* counters = ctx->d_counters.as<uint32_t>();
+    ScopedTimer t(ctx, TM_EDIT);
+    // which voxels get re-meshed is decided on the areas resident NOW (get_without_loading) ...
+    launch_update_claim(d_xyz, n, device_map(ctx), ctx->d_hash_keys.as<unsigned long long>(),
+                        ctx->d_hash_vals.as<uint32_t>(), cap, ctx->d_upd_slot.as<int32_t>(), ctx->stream);
+    // ... while their face tests may reach one voxel further into areas that are not resident: those
+    // are generated first, as world.get_with_cache -> load_area does (world.rs:157-174).  Only
+    // locations within two voxels of an area border can need that.
+    {
+        std::vector<uint64_t> missing;
+        uint64_t last_key = ~0ull;
+        bool last_resident = false;
+        auto resident = [&](uint32_t ax, uint32_t ay) {
+            const uint64_t k = area_key(ax, ay);
+            if (k != last_key) {
+                last_key = k;
+                last_resident = host_slot(ctx, ax, ay) >= 0;
+            }
+            return last_resident;
+        };
+        static const int CAND[5][2] = {{0, 0}, {1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+        for (int i = 0; i < n; ++i) {
+            const uint32_t gx = xyz[3 * i], gy = xyz[3 * i + 1];
+            const uint32_t lx = gx % AREA_SIZE, ly = gy % AREA_SIZE;
+            if (lx >= 2 && lx <= 13 && ly >= 2 && ly <= 13) continue;
+            for (const auto& c : CAND) {
+                const uint32_t vx_ = gx + (uint32_t)c[0], vy_ = gy + (uint32_t)c[1];
+                if (!resident(vx_ / AREA_SIZE, vy_ / AREA_SIZE)) continue;  // the candidate itself is skipped
+                for (const auto& d : CAND) {
+                    if (d[0] == 0 && d[1] == 0) continue;
+                    const uint32_t ax = (vx_ + (uint32_t)d[0]) / AREA_SIZE, ay = (vy_ + (uint32_t)d[1]) / AREA_SIZE;
+                    if (!resident(ax, ay)) missing.push_back(area_key(ax, ay));
+                }
+            }
+        }
+        if (!missing.empty()) {
+            if (!ctx->has_seed) return fail(ctx, VX_ERR_NO_SEED, "vx_update_locations needs to generate a neighbouring area but no seed is set");
+            std::sort(missing.begin(), missing.end());
+            missing.erase(std::unique(missing.begin(), missing.end()), missing.end());
+            std::vector<uint32_t> mxy(2 * missing.size());
+            for (size_t i = 0; i < missing.size(); ++i) {
+                mxy[2 * i] = (uint32_t)(missing[i] >> 32);
+                mxy[2 * i + 1] = (uint32_t)missing[i];
+            }
+            std::vector<int> mslots;
+            if ((st = acquire_slots(ctx, mxy.data(), (int)missing.size(), mslots)) != VX_OK) return st;
+            if ((st = generate_async(ctx, mxy.data(), mslots, (int)missing.size())) != VX_OK) return st;
+            if ((st = upload_map(ctx)) != VX_OK) return st;
+        }
+    }
+    launch_update_count(d_xyz, n, device_map(ctx), ctx->d_voxels, ctx->d_hash_keys.as<unsigned long long>(),
+                        ctx->d_hash_vals.as<uint32_t>(), cap, ctx->d_upd_slot.as<int32_t>(),
+                        ctx->d_upd_info.as<uint16_t>(), ctx->d_upd_rec_count.as<uint32_t>(),
+                        ctx->d_upd_face_count.as<uint32_t>(), reinterpret_cast<int32_t*>(counters + 1), ctx->stream);
+    launch_mesh_offsets(ctx->d_upd_rec_count.as<uint32_t>(), ctx->d_upd_face_count.as<uint32_t>(), (int)n_blocks,
+                        ctx->d_upd_rec_first.as<uint32_t>(), ctx->d_upd_face_first.as<uint32_t>(), counters,
+                        ctx->h_totals, ctx->stream);
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaEventRecord(ctx->totals_ev, ctx->stream));
+    VX_CUDA(cudaEventSynchronize(ctx->totals_ev));
+    const volatile uint32_t* back = ctx->h_totals;  // [1] status, [2] records, [3] faces
+    if (back[1] != 0) {
+        sync_stream(ctx);
+        return fail(ctx, VX_ERR_NOT_LOADED, "vx_update_locations: a neighbouring area is not resident");
+    }
+    const uint64_t n_recs = back[2], n_faces = back[3];
+    VX_CUDA(ctx->d_upd_recs.ensure(std::max<size_t>(16, n_recs * 16)));
+    VX_CUDA(ctx->d_upd_vertices.ensure(std::max<size_t>(16, n_faces * 160)));
+    VX_CUDA(ctx->d_upd_indices.ensure(std::max<size_t>(16, n_faces * 12)));
+    MeshOut out;
+    out.rec_first = ctx->d_upd_rec_first.as<uint32_t>();
+    out.face_first = ctx->d_upd_face_first.as<uint32_t>();
+    out.recs = ctx->d_upd_recs.as<uint4>();
+    out.vertices = ctx->d_upd_vertices.as<uint4>();
+    out.indices = ctx->d_upd_indices.as<uint32_t>();
+    launch_update_emit(d_xyz, n, ctx->d_upd_slot.as<int32_t>(), ctx->d_upd_info.as<uint16_t>(), out.rec_first,
+                       out.face_first, out, ctx->retention ? ctx->d_face : nullptr, ctx->d_meshed, ctx->stream);
+    ctx->timings.other_launches += 4;
+    VX_CUDA(cudaGetLastError());
+    ctx->upd_info.n_recs = n_recs;
+    ctx->upd_info.n_faces = n_faces;
+    ctx->upd_info.rec_bytes = n_recs * 16;
+    ctx->upd_info.vertex_bytes = n_faces * 160;
+    ctx->upd_info.index_bytes = n_faces * 12;
+    ctx->upd_n = n;
+    if (info) *info = ctx->upd_info;
+    return VX_OK;
+}
+
+int vx_update_read(vx_ctx* ctx, vx_voxel_rec* recs, void* vertices, uint16_t* indices) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (ctx->upd_n < 0) return fail(ctx, VX_ERR_NO_MESH, "vx_update_read without vx_update_locations");
+    VX_CUDA(cudaSetDevice(ctx->device));
+    const vx_mesh_info& mi = ctx->upd_info;
+    if (recs && mi.rec_bytes) VX_CUDA(cudaMemcpyAsync(recs, ctx->d_upd_recs.p, mi.rec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (vertices && mi.vertex_bytes) VX_CUDA(cudaMemcpyAsync(vertices, ctx->d_upd_vertices.p, mi.vertex_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (indices && mi.index_bytes) VX_CUDA(cudaMemcpyAsync(indices, ctx->d_upd_indices.p, mi.index_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_stream(ctx);
+}
+
+int vx_mesh_read_compact(vx_ctx* ctx, uint32_t* rec_first, uint32_t* packed_recs) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (ctx->mesh_n < 0) return fail(ctx, VX_ERR_NO_MESH, "vx_mesh_read_compact without vx_mesh");
+    VX_CUDA(cudaSetDevice(ctx->device));
+    const int n = ctx->mesh_n;
+    if (n == 0) {
+        if (rec_first) rec_first[0] = 0;
+        return VX_OK;
+    }
+    const uint64_t n_recs = ctx->mesh_info.n_recs;
+    if (rec_first) VX_CUDA(cudaMemcpyAsync(rec_first, ctx->d_rec_first.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (packed_recs && n_recs) {
+        VX_CUDA(ctx->d_packed.ensure(n_recs * 4));
+        launch_mesh_pack(ctx->d_recs.as<uint4>(), n_recs, ctx->d_packed.as<uint32_t>(), ctx->stream);
+        ctx->timings.mesh_launches += 1;
+        VX_CUDA(cudaGetLastError());
+        VX_CUDA(cudaMemcpyAsync(packed_recs, ctx->d_packed.p, n_recs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_visible_zone(vx_ctx* ctx, const uint32_t* area_xy, int n, const vx_view* view, vx_visible_info* info) {
+    if (!ctx || !view || !info || n < 0 || (n > 0 && !area_xy) || n > (1 << 17)) return VX_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->retention) return fail(ctx, VX_ERR_NO_MESH, "vx_visible_zone: mesh retention is off");
+    VX_CUDA(cudaSetDevice(ctx->device));
+    *info = vx_visible_info{};
+    ctx->frame_ready = false;
+    ctx->frame_n_visible = 0;
+    ctx->frame_areas = n;
+    if (n == 0 || ctx->capacity == 0) {
+        ctx->frame_areas = 0;
+        ctx->frame_ready = true;
+        return VX_OK;
+    }
+    int st;
+    if ((st = upload_map(ctx)) != VX_OK) return st;
+    if ((st = stage_ready(ctx)) != VX_OK) return st;
+    const size_t xy_bytes = (size_t)n * sizeof(uint2);
+    VX_CUDA(ctx->h_stage.ensure(xy_bytes));
+    VX_CUDA(ctx->d_zone_xy.ensure(xy_bytes));
+    VX_CUDA(ctx->d_zone_slot.ensure((size_t)n * 4));
+    VX_CUDA(ctx->d_frame_flags.ensure((size_t)n));
+    VX_CUDA(ctx->d_frame_counts.ensure((size_t)28 * n * 4));
+    // every meshed voxel of every listed area may be drawn (map view): 4 B each; grown on demand below
+    const bool fresh = ctx->d_frame_small.p == nullptr;
+    VX_CUDA(ctx->d_frame_small.ensure(sizeof(FrameTotals) + 32 * 4));
+    VX_CUDA(ctx->h_small.ensure(sizeof(FrameTotals)));
+    FrameTotals* totals = ctx->d_frame_small.as<FrameTotals>();
+    uint32_t* row_total = reinterpret_cast<uint32_t*>(totals + 1);
+    uint32_t* done = row_total + 28;
+    if (fresh) VX_CUDA(cudaMemsetAsync(ctx->d_frame_small.p, 0, sizeof(FrameTotals) + 32 * 4, ctx->stream));
+    std::memcpy(ctx->h_stage.p, area_xy, xy_bytes);
+    VX_CUDA(cudaMemcpyAsync(ctx->d_zone_xy.p, ctx->h_stage.p, xy_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(cudaEventRecord(ctx->stage_ev, ctx->stream));
+    ctx->stage_pending = true;
+    FrameView fv;
+    fv.cx = view->cam_pos[0]; fv.cy = view->cam_pos[1]; fv.cz = view->cam_pos[2];
+    fv.target_z = view->cam_target_z;
+    fv.lx = view->look[0]; fv.ly = view->look[1]; fv.lz = view->look[2];
+    fv.render_size = view->render_size;
+    fv.head_in_water = view->head_in_water;
+    fv.show_map = view->show_map;
+    // the index list can hold one entry per voxel of the zone in the worst case; start from what the
+    // last frames needed and repeat the frame once if it turns out too small
+    size_t cap_visible = std::max<size_t>(ctx->d_frame_visible.cap / 4, (size_t)n * 1024);
+    const FrameTotals* h = ctx->h_small.as<FrameTotals>();
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        VX_CUDA(ctx->d_frame_visible.ensure(cap_visible * 4));
+        cap_visible = ctx->d_frame_visible.cap / 4;
+        VX_CUDA(cudaMemsetAsync(totals, 0, 16, ctx->stream));  // n_faces, n_areas, n_lamps
+        {
+            ScopedTimer t(ctx, TM_VISIBLE);
+            launch_frame_visible_zone(ctx->d_zone_xy.as<uint2>(), n, device_map(ctx), ctx->d_meshed, ctx->d_face,
+                                      ctx->d_voxels, fv, ctx->d_frame_flags.as<uint8_t>(),
+                                      ctx->d_zone_slot.as<int32_t>(), ctx->d_frame_counts.as<uint32_t>(), row_total,
+                                      done, totals, ctx->d_frame_visible.as<uint32_t>(), (uint32_t)std::min<size_t>(cap_visible, 0xFFFFFFFFull),
+                                      ctx->stream);
+            ctx->timings.other_launches += 4;
+        }
+        VX_CUDA(cudaGetLastError());
+        VX_CUDA(cudaMemcpyAsync(ctx->h_small.p, totals, sizeof(FrameTotals), cudaMemcpyDeviceToHost, ctx->stream));
+        if ((st = sync_stream(ctx)) != VX_OK) return st;
+        if (h->type_first[27] <= cap_visible) break;
+        if (attempt == 1) return fail(ctx, VX_ERR_CUDA, "vx_visible_zone: index list still too small");
+        cap_visible = h->type_first[27];
+    }
+    info->n_visible = h->type_first[27];
+    info->n_faces = h->n_faces;
+    info->n_areas = h->n_areas;
+    info->n_lamps = h->n_lamps;
+    std::memcpy(info->type_first, h->type_first, sizeof info->type_first);
+    const uint32_t nl = std::min<uint32_t>(h->n_lamps, VX_MAX_LIGHTS);
+    std::memcpy(info->lamps, h->lamps, nl * sizeof(uint32_t));
+    ctx->frame_n_visible = info->n_visible;
+    ctx->frame_ready = true;
+    return VX_OK;
 }
 
 int vx_diag_fp64_rate(vx_ctx* ctx, double* gops_per_s, float* ms_out) {

@@ -220,6 +220,136 @@ frame_scatter_kernel(const uint4* __restrict__ recs, const uint32_t* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------- resident zone
+// The same frame over the device-resident mirror of Renderer.meshes (vx_update.cu "retention"): the
+// input is, per area of the render zone, the 32 KiB face-mask volume (0 = no mesh entry) and the
+// voxel bytes, so nothing has to be re-meshed when the zone slides or an edit lands.  One warp per
+// area walks the volume 32 rows at a time (one 16-byte row per lane); rows that hold meshes are then
+// taken two at a time, one voxel per lane, in index order.  A drawn voxel is reported as
+// zone index << 15 | x + 16 y + 256 z.
+template <class Fn>
+__device__ __forceinline__ void walk_zone_area(const uint8_t* __restrict__ vol, const uint8_t* __restrict__ vox,
+                                               uint32_t ax, uint32_t ay, const FrameView& v, int lane, Fn&& fn) {
+    const float max_distance = (float)(v.render_size * AREA_SIZE);  // renderer.rs:530
+    const uint4* vol4 = reinterpret_cast<const uint4*>(vol);
+    for (int batch = 0; batch < VOXELS_IN_AREA / 16 / 32; ++batch) {
+        const uint4 f = vol4[batch * 32 + lane];
+        uint32_t active = __ballot_sync(0xFFFFFFFFu, (f.x | f.y | f.z | f.w) != 0u);
+        while (active) {
+            const int j0 = __ffs(active) - 1;
+            active &= active - 1;
+            int j1 = -1;
+            if (active) {
+                j1 = __ffs(active) - 1;
+                active &= active - 1;
+            }
+            const int my_row = lane < 16 ? j0 : j1;
+            const uint32_t x = lane & 15;
+            uint32_t mask = 0, voxel = 0, local = 0;
+            if (my_row >= 0) {
+                local = (uint32_t)(batch * 32 + my_row) * 16u + x;
+                mask = vol[local];
+                voxel = vox[local];
+            }
+            const bool in = mask != 0u;
+            // the record the batch mesher would hold for this voxel (gx, gy, gz | voxel << 8 | ...)
+            const uint4 rec = make_uint4(ax * AREA_SIZE + x, ay * AREA_SIZE + ((local >> 4) & 15u),
+                                         (local >> 8) | (voxel << 8), 0u);
+            const bool drawn = in && voxel_drawn(rec, v, max_distance);
+            fn(in, drawn, voxel, mask, local);
+        }
+    }
+}
+
+// prepare_visible_areas iterates over `meshes` (renderer.rs:507-519): an area of the zone list counts
+// only if it is resident and meshed.  zone_slot[i] = its pool slot when it is drawn from, else -1.
+__global__ void zone_areas_kernel(const uint2* __restrict__ area_xy, int n, AreaMap map,
+                                  const uint8_t* __restrict__ meshed, FrameView v, uint8_t* __restrict__ area_flag,
+                                  int32_t* __restrict__ zone_slot, FrameTotals* totals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool vis = false;
+    if (i < n) {
+        const uint2 a = area_xy[i];
+        const int slot = area_slot(map, a.x, a.y);
+        vis = slot >= 0 && meshed[slot] && (v.show_map || area_visible(a.x, a.y, v, area_render_distance(v)));
+        area_flag[i] = vis ? 1 : 0;
+        zone_slot[i] = vis ? slot : -1;
+    }
+    const uint32_t cnt = __popc(__ballot_sync(0xFFFFFFFFu, vis));
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&totals->n_areas, cnt);
+}
+
+__global__ void __launch_bounds__(32 * AREAS_PER_CTA)
+zone_count_kernel(const uint2* __restrict__ area_xy, int n, const int32_t* __restrict__ zone_slot,
+                  const uint8_t* __restrict__ face_volume, const uint8_t* __restrict__ pool_voxels, FrameView v,
+                  uint32_t* __restrict__ counts, FrameTotals* totals) {
+    __shared__ uint32_t hist[AREAS_PER_CTA][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i = blockIdx.x * AREAS_PER_CTA + wid;
+    if (i >= n) return;
+    hist[wid][lane] = 0;
+    __syncwarp();
+    uint32_t faces = 0, lamps = 0;
+    const uint2 a = area_xy[i];
+    const int slot = zone_slot[i];
+    if (slot >= 0) {
+        walk_zone_area(face_volume + (size_t)slot * VOXELS_IN_AREA, pool_voxels + (size_t)slot * VOXELS_IN_AREA, a.x, a.y,
+                       v, lane, [&](bool in, bool drawn, uint32_t voxel, uint32_t mask, uint32_t) {
+                           lamps += (in && voxel == V_LAMP) ? 1u : 0u;
+                           faces += drawn ? __popc(mask) : 0u;
+                           const uint32_t key = drawn ? voxel : 31u;
+                           const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+                           if (drawn && lane == __ffs(peers) - 1) hist[wid][voxel] += __popc(peers);
+                           __syncwarp();
+                       });
+    }
+    if (lane < TYPES) counts[(size_t)lane * n + i] = hist[wid][lane];
+    faces = __reduce_add_sync(0xFFFFFFFFu, faces);
+    lamps = __reduce_add_sync(0xFFFFFFFFu, lamps);
+    if (lane == 0) {
+        counts[(size_t)TYPES * n + i] = lamps;
+        if (faces) atomicAdd(&totals->n_faces, (unsigned long long)faces);
+    }
+}
+
+__global__ void __launch_bounds__(32 * AREAS_PER_CTA)
+zone_scatter_kernel(const uint2* __restrict__ area_xy, int n, const int32_t* __restrict__ zone_slot,
+                    const uint8_t* __restrict__ face_volume, const uint8_t* __restrict__ pool_voxels, FrameView v,
+                    const uint32_t* __restrict__ counts, FrameTotals* totals, uint32_t* __restrict__ visible,
+                    uint32_t cap_visible) {
+    __shared__ uint32_t cursor[AREAS_PER_CTA][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i = blockIdx.x * AREAS_PER_CTA + wid;
+    if (i >= n) return;
+    const uint2 a = area_xy[i];
+    const int slot = zone_slot[i];
+    if (slot < 0) return;
+    if (lane < TYPES) cursor[wid][lane] = totals->type_first[lane] + counts[(size_t)lane * n + i];
+    uint32_t lamp_cursor = counts[(size_t)TYPES * n + i];
+    __syncwarp();
+    walk_zone_area(face_volume + (size_t)slot * VOXELS_IN_AREA, pool_voxels + (size_t)slot * VOXELS_IN_AREA, a.x, a.y, v,
+                   lane, [&](bool in, bool drawn, uint32_t voxel, uint32_t, uint32_t local) {
+                       const uint32_t code = ((uint32_t)i << 15) | local;
+                       const uint32_t key = drawn ? voxel : 31u;
+                       const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+                       const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                       uint32_t base = 0;
+                       if (drawn) base = cursor[wid][voxel];
+                       __syncwarp();
+                       if (drawn) {
+                           if (base + rank < cap_visible) visible[base + rank] = code;  // the host repeats the frame with a larger list
+                           if (rank == 0) cursor[wid][voxel] = base + __popc(peers);
+                       }
+                       const uint32_t lamp_mask = __ballot_sync(0xFFFFFFFFu, in && voxel == V_LAMP);
+                       if (in && voxel == V_LAMP) {
+                           const uint32_t k = lamp_cursor + __popc(lamp_mask & ((1u << lane) - 1u));
+                           if (k < FRAME_MAX_LAMPS) totals->lamps[k] = code;
+                       }
+                       lamp_cursor += __popc(lamp_mask);
+                       __syncwarp();
+                   });
+}
+
 }  // namespace
 
 void launch_frame_visible(const uint4* recs, const uint32_t* rec_first, const uint2* area_xy, int n,
@@ -234,4 +364,21 @@ void launch_frame_visible(const uint4* recs, const uint32_t* rec_first, const ui
                                                                   visible);
 }
 
+}  // namespace vx
+
+namespace vx {
+void launch_frame_visible_zone(const uint2* area_xy, int n, AreaMap map, const uint8_t* meshed,
+                               const uint8_t* face_volume, const uint8_t* pool_voxels, const FrameView& view,
+                               uint8_t* area_flag, int32_t* zone_slot, uint32_t* counts, uint32_t* row_total,
+                               uint32_t* done, FrameTotals* totals, uint32_t* visible, uint32_t cap_visible,
+                               cudaStream_t stream) {
+    if (n <= 0) return;
+    zone_areas_kernel<<<(n + 255) / 256, 256, 0, stream>>>(area_xy, n, map, meshed, view, area_flag, zone_slot, totals);
+    const int ctas = (n + AREAS_PER_CTA - 1) / AREAS_PER_CTA;
+    zone_count_kernel<<<ctas, 32 * AREAS_PER_CTA, 0, stream>>>(area_xy, n, zone_slot, face_volume, pool_voxels, view,
+                                                               counts, totals);
+    frame_scan_kernel<<<TYPES + 1, 1024, 0, stream>>>(counts, n, totals, row_total, done);
+    zone_scatter_kernel<<<ctas, 32 * AREAS_PER_CTA, 0, stream>>>(area_xy, n, zone_slot, face_volume, pool_voxels, view,
+                                                                 counts, totals, visible, cap_visible);
+}
 }  // namespace vx

@@ -71,6 +71,32 @@ void launch_frame_visible(const uint4* recs, const uint32_t* rec_first, const ui
                           const FrameView& view, uint8_t* area_flag, uint32_t* counts, uint32_t* row_total,
                           uint32_t* done, FrameTotals* totals, uint32_t* visible, cudaStream_t stream);
 
+// the same frame over the device-resident mirror of Renderer.meshes (mesh retention): zone list of
+// areas, per-slot face-mask volumes; visible[] entries are zone index << 15 | x + 16 y + 256 z
+void launch_frame_visible_zone(const uint2* area_xy, int n, AreaMap map, const uint8_t* meshed,
+                               const uint8_t* face_volume, const uint8_t* pool_voxels, const FrameView& view,
+                               uint8_t* area_flag, int32_t* zone_slot, uint32_t* counts, uint32_t* row_total,
+                               uint32_t* done, FrameTotals* totals, uint32_t* visible, uint32_t cap_visible,
+                               cudaStream_t stream);
+
+// ---- incremental re-meshing (M6), mesh retention, compact records: vx_update.cu
+// hash_keys / hash_vals filled with 0xFF bytes; cand_slot: 7 n words; cand_info: 7 n half-words;
+// rec_count / face_count: one word per 256 candidates
+void launch_update_claim(const uint32_t* xyz, int n, AreaMap map, unsigned long long* hash_keys, uint32_t* hash_vals,
+                         uint32_t hash_cap, int32_t* cand_slot, cudaStream_t stream);
+void launch_update_count(const uint32_t* xyz, int n, AreaMap map, const uint8_t* pool_voxels,
+                         const unsigned long long* hash_keys, const uint32_t* hash_vals, uint32_t hash_cap,
+                         const int32_t* cand_slot, uint16_t* cand_info, uint32_t* rec_count, uint32_t* face_count,
+                         int32_t* status, cudaStream_t stream);
+void launch_update_emit(const uint32_t* xyz, int n, const int32_t* cand_slot, const uint16_t* cand_info,
+                        const uint32_t* rec_first, const uint32_t* face_first, MeshOut out,
+                        uint8_t* face_volume /* may be null */, uint8_t* meshed, cudaStream_t stream);
+void launch_mesh_retain(const uint4* jobs, int n, const uint32_t* rec_first, const uint4* recs, uint8_t* face_volume,
+                        uint8_t* meshed, cudaStream_t stream);
+void launch_mesh_pack(const uint4* recs, uint64_t n, uint32_t* packed, cudaStream_t stream);
+// patches: n pairs {index, -, -, -}, {entry} applied to the device copy of the area map
+void launch_map_patch(const uint4* patches, int n, uint4* entries, cudaStream_t stream);
+
 // ---- area save files (K8 encode, K9 decode), vx_codec.cu; jobs = {ax, ay, slot, 0}
 constexpr uint32_t AREA_FILE_MAX_BYTES = 33300;  // 4 + 3 + 32768 literals + token / length bytes
 // kinds: n * 2048 bytes of scratch written by the size pass and read by the emit pass

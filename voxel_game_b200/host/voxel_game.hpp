@@ -14,6 +14,7 @@
 // No CPU compute path: every method that produces voxels, heights or meshes calls the library and
 // throws VxError when it fails.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <cmath>
@@ -21,6 +22,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -74,7 +76,11 @@ public:
         if (st != VX_OK) throw VxError(st, vx_strerror(st));
         check(vx_set_seed(ctx_, vx_hash_world_name(world_name.c_str())));
     }
-    ~Pipeline() { vx_destroy(ctx_); }
+    // a context created elsewhere (e.g. by the Python plumbing); not destroyed here
+    explicit Pipeline(vx_ctx* borrowed) : ctx_(borrowed), owned_(false) {}
+    ~Pipeline() {
+        if (owned_) vx_destroy(ctx_);
+    }
     Pipeline(const Pipeline&) = delete;
     Pipeline& operator=(const Pipeline&) = delete;
     vx_ctx* raw() const { return ctx_; }
@@ -84,6 +90,7 @@ public:
 
 private:
     vx_ctx* ctx_ = nullptr;
+    bool owned_ = true;
 };
 
 class Area {  // model/area.rs:11-124
@@ -227,7 +234,165 @@ struct LocHash {
 struct RenderArea {  // renderer.rs:48-73
     std::unordered_map<LocKey, MeshInfo, LocHash> mesh_map;
     std::vector<LocKey> lights;  // Lamp voxels with at least one face
+    void insert(const LocKey& key, MeshInfo&& mi) {  // renderer.rs:60-67
+        if (mi.voxel == Voxel::Lamp) {
+            bool known = false;
+            for (const LocKey& l : lights) known = known || l == key;
+            if (!known) lights.push_back(key);
+        } else {
+            drop_light(key);
+        }
+        mesh_map[key] = std::move(mi);
+    }
+    void remove(const LocKey& key) {  // renderer.rs:69-72
+        drop_light(key);
+        mesh_map.erase(key);
+    }
+
+private:
+    void drop_light(const LocKey& key) {
+        for (size_t i = 0; i < lights.size(); ++i)
+            if (lights[i] == key) {
+                lights.erase(lights.begin() + static_cast<long>(i));
+                return;
+            }
+    }
 };
+
+// ---- host-side expansion of the compact record transport (vx_mesh_read_compact) ---------------
+// MeshGenerator::generate_mesh / get_verticies_for_voxel (mesh_generator.rs:109-147,200-498) on the
+// host: the four vertices and six indices of every face of a visible voxel are a pure function of
+// (location, voxel type, face mask).  The arithmetic is the reference's f32 arithmetic (offset -/+
+// 0.5, "offset_z - 0.5 + height_offset", "side_uv.y -= height_offset"; no multiply, so nothing a
+// compiler could contract) and the result is byte-identical to the device's vertex stream
+// (tests/test_gpu_host.py).  Corner table: per direction four (x side, y side, bottom z, uv corner)
+// tuples in the vertex order of the six vec![] blocks of mesh_generator.rs:222-487.
+namespace detail {
+struct Corner {
+    uint8_t px, py, bottom, uv;
+};
+// push order of renderer.rs:139-180: Left(x+1) Right(x-1) Front(y+1) Back(y-1) Down(z+1) Up(z-1)
+constexpr Corner CORNERS[6][4] = {
+    {{1, 0, 1, 1}, {1, 0, 0, 2}, {1, 1, 0, 3}, {1, 1, 1, 0}},
+    {{0, 0, 0, 3}, {0, 0, 1, 0}, {0, 1, 1, 1}, {0, 1, 0, 2}},
+    {{0, 1, 1, 0}, {1, 1, 1, 1}, {1, 1, 0, 2}, {0, 1, 0, 3}},
+    {{0, 0, 0, 3}, {1, 0, 0, 2}, {1, 0, 1, 1}, {0, 0, 1, 0}},
+    {{0, 0, 1, 0}, {1, 0, 1, 1}, {1, 1, 1, 2}, {0, 1, 1, 3}},
+    {{1, 0, 0, 0}, {0, 0, 0, 1}, {0, 1, 0, 2}, {1, 1, 0, 3}},
+};
+constexpr float NORMALS[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};  // mesh_generator.rs:45-50
+// TextureManager::VOXELS_WITH_DIFFERENT_FACES (texture_manager.rs:95-102)
+inline bool has_different_faces(Voxel v) {
+    return v == Voxel::Grass || v == Voxel::Trampoline || v == Voxel::Wood || v == Voxel::StonePillar ||
+           v == Voxel::Bomb || v == Voxel::ActiveBomb;
+}
+}  // namespace detail
+
+// Appends the faces of one voxel: 4 vertices and 6 indices ([0,1,2,0,2,3] + 4 * ordinal) per set bit
+// of face_mask, in bit order.  Returns the number of faces.
+inline unsigned expand_voxel(uint32_t gx, uint32_t gy, uint32_t gz, Voxel voxel, uint32_t face_mask, Vertex* v_out,
+                             uint16_t* i_out) {
+    using namespace detail;
+    const float cx = static_cast<float>(static_cast<int32_t>(gx) - LOCATION_OFFSET);  // location.rs:19-27
+    const float cy = static_cast<float>(static_cast<int32_t>(gy) - LOCATION_OFFSET);
+    const float cz = static_cast<float>(static_cast<int32_t>(gz));
+    float ho = 0.0f;  // get_partial_height_offset (mesh_generator.rs:490-498)
+    switch (voxel) {
+    case Voxel::Water1: ho = 1.0f / 5.0f; break;
+    case Voxel::Water2: ho = 2.0f / 5.0f; break;
+    case Voxel::Water3: ho = 3.0f / 5.0f; break;
+    case Voxel::Water4: ho = 4.0f / 5.0f; break;
+    default: break;
+    }
+    const float xs[2] = {cx - 0.5f, cx + 0.5f}, ys[2] = {cy - 0.5f, cy + 0.5f};
+    const float zs[2] = {cz - 0.5f + ho, cz + 0.5f};  // top, bottom
+    const bool diff = has_different_faces(voxel);
+    unsigned ord = 0;
+    for (int d = 0; d < 6; ++d) {
+        if (!((face_mask >> d) & 1u)) continue;
+        // v of uv corners {0, 1} and {2, 3}: UV_REPEATING 1 / 0; TOP 0.625 / 0.375, SIDE 1 / 0.75,
+        // BOTTOM 0.25 / 0 for voxels with different faces (mesh_generator.rs:61-99)
+        float vhi = 1.0f, vlo = 0.0f;
+        if (diff) {
+            vhi = d == 5 ? 0.625f : (d == 4 ? 0.25f : 1.0f);
+            vlo = d == 5 ? 0.375f : (d == 4 ? 0.0f : 0.75f);
+        }
+        if (d < 4 && ho > 0.0f) {  // mesh_generator.rs:214-220, side faces only
+            if (vhi > 0.0f) vhi -= ho;
+            if (vlo > 0.0f) vlo -= ho;
+        }
+        for (int k = 0; k < 4; ++k) {
+            const Corner c = CORNERS[d][k];
+            Vertex& v = v_out[4 * ord + static_cast<unsigned>(k)];
+            v.position[0] = xs[c.px];
+            v.position[1] = ys[c.py];
+            v.position[2] = zs[c.bottom];
+            v.uv[0] = (c.uv == 1 || c.uv == 2) ? 1.0f : 0.0f;
+            v.uv[1] = c.uv < 2 ? vhi : vlo;
+            v.color[0] = v.color[1] = v.color[2] = v.color[3] = 255;  // mesh_generator.rs:43
+            v.normal[0] = NORMALS[d][0];
+            v.normal[1] = NORMALS[d][1];
+            v.normal[2] = NORMALS[d][2];
+            v.normal[3] = 0.0f;
+        }
+        const uint16_t b = static_cast<uint16_t>(4 * ord);
+        uint16_t* w = i_out + 6 * ord;
+        w[0] = b; w[1] = b + 1; w[2] = b + 2; w[3] = b; w[4] = b + 2; w[5] = b + 3;  // mesh_generator.rs:44
+        ++ord;
+    }
+    return ord;
+}
+
+inline unsigned popcount6(uint32_t m) {
+    unsigned n = 0;
+    for (int d = 0; d < 6; ++d) n += (m >> d) & 1u;
+    return n;
+}
+
+// Runs fn(first, last) over [0, n) in `threads` contiguous pieces.
+template <class Fn> void parallel_ranges(size_t n, unsigned threads, Fn fn) {
+    if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    threads = static_cast<unsigned>(std::min<size_t>(threads, std::max<size_t>(n, 1)));
+    if (threads <= 1) {
+        fn(size_t(0), n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; ++t) pool.emplace_back([=] { fn(n * t / threads, n * (t + 1) / threads); });
+    for (auto& th : pool) th.join();
+}
+
+// The flat stream vx_mesh_read would have delivered, rebuilt from the compact transport: 16-byte
+// records (first_face = running face count in call order), vertices, indices.  face_first (n + 1)
+// is an output too.  Areas are expanded in parallel.
+inline void expand_records(const uint32_t* area_xy, int n, const uint32_t* rec_first, const uint32_t* packed,
+                           uint32_t* face_first, vx_voxel_rec* recs, Vertex* vertices, uint16_t* indices,
+                           unsigned threads = 0) {
+    std::vector<uint32_t> faces(static_cast<size_t>(n) + 1, 0);
+    parallel_ranges(static_cast<size_t>(n), threads, [&](size_t a0, size_t a1) {
+        for (size_t a = a0; a < a1; ++a) {
+            uint32_t f = 0;
+            for (uint32_t q = rec_first[a]; q < rec_first[a + 1]; ++q) f += popcount6(VX_PACKED_MASK(packed[q]));
+            faces[a + 1] = f;
+        }
+    });
+    for (int a = 0; a < n; ++a) faces[a + 1] += faces[a];
+    if (face_first) std::memcpy(face_first, faces.data(), (static_cast<size_t>(n) + 1) * 4);
+    parallel_ranges(static_cast<size_t>(n), threads, [&](size_t a0, size_t a1) {
+        for (size_t a = a0; a < a1; ++a) {
+            const uint32_t gx0 = area_xy[2 * a] * AREA_SIZE, gy0 = area_xy[2 * a + 1] * AREA_SIZE;
+            uint32_t f = faces[a];
+            for (uint32_t q = rec_first[a]; q < rec_first[a + 1]; ++q) {
+                const uint32_t p = packed[q], local = VX_PACKED_LOCAL(p), mask = VX_PACKED_MASK(p);
+                const uint32_t gx = gx0 + (local & 15u), gy = gy0 + ((local >> 4) & 15u), gz = local >> 8;
+                const unsigned nf = popcount6(mask);
+                if (recs) recs[q] = vx_voxel_rec{gx, gy, gz | (VX_PACKED_VOXEL(p) << 8) | (mask << 16) | (nf << 24), f};
+                if (vertices) expand_voxel(gx, gy, gz, static_cast<Voxel>(VX_PACKED_VOXEL(p)), mask, vertices + size_t(f) * 4, indices + size_t(f) * 6);
+                f += nf;
+            }
+        }
+    });
+}
 
 struct Camera3D {  // macroquad::camera::Camera3D, the two fields the visibility pass reads
     float position[3];
@@ -240,11 +405,19 @@ struct FrameResult {  // what one frame draws
     size_t lamps_in_view = 0;
 };
 
+enum class Transport {
+    Compact,  // 4-byte records over PCIe, vertices rebuilt on the host (expand_voxel)
+    Raw       // records + vertex + index streams from the device (vx_mesh_read)
+};
+
 class Renderer {  // graphics/renderer.rs:97-322,365-472
 public:
-    // set_voxel_shader_and_find_visible_areas + render_voxels (renderer.rs:365-452) over the areas of
-    // the last load_all_blocking / update_locations batch: the per-frame filter runs on the device
-    // over the records kept there, the host only receives the indices of the meshes to draw.
+    Transport transport = Transport::Compact;
+    unsigned threads = 0;  // host threads for the per-voxel Mesh construction (0 = all)
+
+    // set_voxel_shader_and_find_visible_areas + render_voxels (renderer.rs:365-452) over `meshes`:
+    // the per-frame filter runs on the device over the resident mirror of the meshes (mesh
+    // retention), the host only receives which voxel meshes to draw, in draw order.
     FrameResult render_voxels(World& world, const Camera3D& camera, uint32_t render_size, bool head_in_water,
                               bool show_map) {
         const Pipeline& p = world.pipeline();
@@ -262,17 +435,26 @@ public:
         v.render_size = render_size;
         v.head_in_water = head_in_water;
         v.show_map = show_map;
+        std::vector<AreaLocation> zone;
+        zone.reserve(meshes_.size());
+        for (const auto& kv : meshes_) zone.push_back(kv.first);
+        const auto xy = flatten(zone);
         vx_visible_info info{};
-        p.check(vx_visible(p.raw(), &v, &info));
-        std::vector<uint32_t> idx(info.n_visible);
-        p.check(vx_visible_read(p.raw(), idx.data(), nullptr));
+        p.check(vx_visible_zone(p.raw(), xy.data(), static_cast<int>(zone.size()), &v, &info));
+        std::vector<uint32_t> codes(info.n_visible);
+        p.check(vx_visible_read(p.raw(), codes.data(), nullptr));
+        auto key_of = [&](uint32_t code) {
+            const AreaLocation a = zone[code >> 15];
+            const uint32_t local = code & 0x7FFFu;
+            return LocKey{a.x * AREA_SIZE + (local & 15u), a.y * AREA_SIZE + ((local >> 4) & 15u), local >> 8};
+        };
         FrameResult f;
         f.visible_areas = info.n_areas;
         f.faces_visible = info.n_faces;
         f.lamps_in_view = info.n_lamps;
-        f.draw_order.reserve(idx.size());
-        for (uint32_t r : idx) f.draw_order.push_back(last_keys_[r]);
-        for (uint32_t k = 0; k < info.n_lamps && k < VX_MAX_LIGHTS; ++k) f.lights.push_back(last_keys_[info.lamps[k]]);
+        f.draw_order.reserve(codes.size());
+        for (uint32_t c : codes) f.draw_order.push_back(key_of(c));
+        for (uint32_t k = 0; k < info.n_lamps && k < VX_MAX_LIGHTS; ++k) f.lights.push_back(key_of(info.lamps[k]));
         return f;
     }
 
@@ -283,54 +465,120 @@ public:
             if (!meshes_.count(a)) todo.push_back(a);
         mesh_batch(world.pipeline(), todo);
     }
-    // update_location for a batch of edits (renderer.rs:239-286): re-mesh the dirty areas
-    void update_locations(World& world, const std::vector<AreaLocation>& dirty) {
-        std::vector<AreaLocation> loaded;
-        for (const auto& a : dirty)
-            if (meshes_.count(a)) loaded.push_back(a);
-        mesh_batch(world.pipeline(), loaded);
+    // update_location (renderer.rs:239-286) for the locations world.set has just changed: the voxel
+    // and its <= 6 neighbours are re-meshed on the device; meshes are inserted / removed here
+    void update_locations(World& world, const std::vector<InternalLocation>& locations) {
+        if (locations.empty()) return;
+        const Pipeline& p = world.pipeline();
+        ensure_retention(p);
+        std::vector<uint32_t> xyz;
+        xyz.reserve(locations.size() * 3);
+        for (const auto& l : locations) {
+            xyz.push_back(l.x);
+            xyz.push_back(l.y);
+            xyz.push_back(l.z);
+        }
+        vx_mesh_info info{};
+        p.check(vx_update_locations(p.raw(), xyz.data(), static_cast<int>(locations.size()), &info));
+        std::vector<vx_voxel_rec> recs(info.n_recs);
+        std::vector<Vertex> vertices(info.n_faces * 4);
+        std::vector<uint16_t> indices(info.n_faces * 6);
+        p.check(vx_update_read(p.raw(), recs.data(), vertices.data(), indices.data()));
+        for (const vx_voxel_rec& rec : recs) {  // set_voxel_mesh (renderer.rs:197-219)
+            const uint32_t gz = rec.packed & 0xFF, nf = rec.packed >> 24;
+            const LocKey key{rec.gx, rec.gy, gz};
+            RenderArea& ra = meshes_[AreaLocation{rec.gx / AREA_SIZE, rec.gy / AREA_SIZE}];  // created if absent (:208-212)
+            if (nf == 0) {
+                ra.remove(key);
+                continue;
+            }
+            MeshInfo mi{static_cast<uint8_t>(nf), static_cast<Voxel>((rec.packed >> 8) & 0xFF), {}};
+            mi.mesh.vertices.assign(vertices.begin() + size_t(rec.first_face) * 4, vertices.begin() + size_t(rec.first_face + nf) * 4);
+            mi.mesh.indices.assign(indices.begin() + size_t(rec.first_face) * 6, indices.begin() + size_t(rec.first_face + nf) * 6);
+            ra.insert(key, std::move(mi));
+        }
     }
-    void unload_area(AreaLocation a) { meshes_.erase(a); }
+    void update_location(World& world, InternalLocation location) { update_locations(world, {location}); }
+    void unload_area(World& world, AreaLocation a) {  // renderer.rs:111-117
+        meshes_.erase(a);
+        const uint32_t xy[2] = {a.x, a.y};
+        world.pipeline().check(vx_mesh_unload(world.pipeline().raw(), xy, 1));
+    }
     size_t get_voxel_face_count() const {  // renderer.rs:455-461
         size_t n = 0;
         for (const auto& kv : meshes_)
             for (const auto& m : kv.second.mesh_map) n += m.second.face_count;
         return n;
     }
+    size_t get_voxel_count() const {
+        size_t n = 0;
+        for (const auto& kv : meshes_) n += kv.second.mesh_map.size();
+        return n;
+    }
     const std::map<AreaLocation, RenderArea>& meshes() const { return meshes_; }
+    void clear() { meshes_.clear(); }
 
 private:
+    void ensure_retention(const Pipeline& p) {
+        if (!retention_on_) {
+            p.check(vx_set_mesh_retention(p.raw(), 1));
+            retention_on_ = true;
+        }
+    }
     void mesh_batch(const Pipeline& p, const std::vector<AreaLocation>& areas) {
         if (areas.empty()) return;
+        ensure_retention(p);
         const auto xy = flatten(areas);
         const int n = static_cast<int>(areas.size());
         vx_mesh_info info{};
         p.check(vx_mesh(p.raw(), xy.data(), n, &info));
-        std::vector<uint32_t> rec_first(n + 1), face_first(n + 1);
-        std::vector<vx_voxel_rec> recs(info.n_recs);
-        std::vector<Vertex> vertices(info.n_faces * 4);
-        std::vector<uint16_t> indices(info.n_faces * 6);
-        p.check(vx_mesh_read(p.raw(), rec_first.data(), face_first.data(), recs.data(), vertices.data(), indices.data()));
-        last_keys_.assign(info.n_recs, LocKey{0, 0, 0});
-        for (int i = 0; i < n; ++i) {
-            RenderArea ra;
-            for (uint32_t r = rec_first[i]; r < rec_first[i + 1]; ++r) {
-                const vx_voxel_rec& rec = recs[r];
-                const uint32_t gz = rec.packed & 0xFF, nf = rec.packed >> 24;
-                const Voxel voxel = static_cast<Voxel>((rec.packed >> 8) & 0xFF);
-                MeshInfo mi{static_cast<uint8_t>(nf), voxel, {}};
-                mi.mesh.vertices.assign(vertices.begin() + size_t(rec.first_face) * 4, vertices.begin() + size_t(rec.first_face + nf) * 4);
-                mi.mesh.indices.assign(indices.begin() + size_t(rec.first_face) * 6, indices.begin() + size_t(rec.first_face + nf) * 6);
-                const LocKey key{rec.gx, rec.gy, gz};
-                last_keys_[r] = key;
-                if (voxel == Voxel::Lamp) ra.lights.push_back(key);  // RenderArea::insert, renderer.rs:60-67
-                ra.mesh_map.emplace(key, std::move(mi));
-            }
-            meshes_[areas[i]] = std::move(ra);
+        std::vector<uint32_t> rec_first(static_cast<size_t>(n) + 1);
+        std::vector<RenderArea> built(static_cast<size_t>(n));
+        if (transport == Transport::Compact) {
+            std::vector<uint32_t> packed(info.n_recs);
+            p.check(vx_mesh_read_compact(p.raw(), rec_first.data(), packed.data()));
+            parallel_ranges(static_cast<size_t>(n), threads, [&](size_t a0, size_t a1) {
+                for (size_t a = a0; a < a1; ++a) {
+                    RenderArea& ra = built[a];
+                    ra.mesh_map.reserve(rec_first[a + 1] - rec_first[a]);
+                    const uint32_t gx0 = areas[a].x * AREA_SIZE, gy0 = areas[a].y * AREA_SIZE;
+                    for (uint32_t q = rec_first[a]; q < rec_first[a + 1]; ++q) {
+                        const uint32_t pk = packed[q], local = VX_PACKED_LOCAL(pk), mask = VX_PACKED_MASK(pk);
+                        const LocKey key{gx0 + (local & 15u), gy0 + ((local >> 4) & 15u), local >> 8};
+                        const unsigned nf = popcount6(mask);
+                        MeshInfo mi{static_cast<uint8_t>(nf), static_cast<Voxel>(VX_PACKED_VOXEL(pk)), {}};
+                        mi.mesh.vertices.resize(4 * nf);
+                        mi.mesh.indices.resize(6 * nf);
+                        expand_voxel(key.x, key.y, key.z, mi.voxel, mask, mi.mesh.vertices.data(), mi.mesh.indices.data());
+                        ra.insert(key, std::move(mi));
+                    }
+                }
+            });
+        } else {
+            std::vector<uint32_t> face_first(static_cast<size_t>(n) + 1);
+            std::vector<vx_voxel_rec> recs(info.n_recs);
+            std::vector<Vertex> vertices(info.n_faces * 4);
+            std::vector<uint16_t> indices(info.n_faces * 6);
+            p.check(vx_mesh_read(p.raw(), rec_first.data(), face_first.data(), recs.data(), vertices.data(), indices.data()));
+            parallel_ranges(static_cast<size_t>(n), threads, [&](size_t a0, size_t a1) {
+                for (size_t a = a0; a < a1; ++a) {
+                    RenderArea& ra = built[a];
+                    ra.mesh_map.reserve(rec_first[a + 1] - rec_first[a]);
+                    for (uint32_t r = rec_first[a]; r < rec_first[a + 1]; ++r) {
+                        const vx_voxel_rec& rec = recs[r];
+                        const uint32_t gz = rec.packed & 0xFF, nf = rec.packed >> 24;
+                        MeshInfo mi{static_cast<uint8_t>(nf), static_cast<Voxel>((rec.packed >> 8) & 0xFF), {}};
+                        mi.mesh.vertices.assign(vertices.begin() + size_t(rec.first_face) * 4, vertices.begin() + size_t(rec.first_face + nf) * 4);
+                        mi.mesh.indices.assign(indices.begin() + size_t(rec.first_face) * 6, indices.begin() + size_t(rec.first_face + nf) * 6);
+                        ra.insert(LocKey{rec.gx, rec.gy, gz}, std::move(mi));
+                    }
+                }
+            });
         }
+        for (int i = 0; i < n; ++i) meshes_[areas[static_cast<size_t>(i)]] = std::move(built[static_cast<size_t>(i)]);
     }
     std::map<AreaLocation, RenderArea> meshes_;
-    std::vector<LocKey> last_keys_;  // record index of the last batch -> voxel location
+    bool retention_on_ = false;
 };
 
 }  // namespace voxel_game
