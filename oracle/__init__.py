@@ -37,6 +37,25 @@ VERTEX_DTYPE = np.dtype(
 assert VERTEX_DTYPE.itemsize == 40 and REC_DTYPE.itemsize == 16
 
 
+def use_native_build() -> bool:
+    """For the CPU-baseline timing legs of bench.py: rebuild the oracle with -march=native ON THE
+    MACHINE THAT RUNS THE TIMING (the library that travels with the repo is -march=x86-64-v2 so that
+    it runs anywhere) and switch this module to it.  Returns False (and changes nothing) if gcc is
+    not available there."""
+    global _LIB_PATH, _lib
+    native = os.path.join(_HERE, "build", "liboracle_native.so")
+    try:
+        r = subprocess.run(["make", "-C", _HERE, "-B", "MARCH=native", "OUT=build/liboracle_native.so"],
+                           capture_output=True)
+    except OSError:
+        return False
+    if r.returncode != 0 or not os.path.exists(native):
+        return False
+    _LIB_PATH = native
+    _lib = None
+    return True
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (oracle/Makefile). Returns the .so path."""
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]

@@ -91,7 +91,7 @@ uint64_t vxh_renderer_voxel_count(void* r) { return static_cast<HostRenderer*>(r
 uint64_t vxh_renderer_area_count(void* r) { return static_cast<HostRenderer*>(r)->renderer.meshes().size(); }
 
 // The Renderer.meshes entries of one area as a dense volume (byte x + 16 y + 256 z = face count of
-// that voxel's mesh, 0 = no entry) plus its lamp count: what the tests compare with the oracle.
+// that voxel's mesh, 0 = no entry) plus its lamp count: what the parity tests compare.
 // Returns -1 if the area has no RenderArea.
 int vxh_renderer_area_face_counts(void* r, uint32_t ax, uint32_t ay, uint8_t* counts_out, uint32_t* lamps_out) {
     auto* h = static_cast<HostRenderer*>(r);
