@@ -176,6 +176,8 @@ def lib():
         L.vgo_lz4_compress_block.argtypes = [u8p, C.c_long, u8p]
         L.vgo_area_file_encode.restype = C.c_long
         L.vgo_area_file_encode.argtypes = [u8p, u8p]
+        L.vgo_area_files_encode.restype = C.c_long
+        L.vgo_area_files_encode.argtypes = [u8p, C.c_int, C.c_int, u8p, C.POINTER(C.c_long)]
         L.vgo_area_file_decode.restype = C.c_int
         L.vgo_area_file_decode.argtypes = [u8p, C.c_long, u8p]
         L.vgo_explode.restype = C.c_int
@@ -537,6 +539,15 @@ def area_file_encode(voxels: np.ndarray) -> bytes:
     out = np.empty(AREA_FILE_MAX_BYTES, np.uint8)
     n = lib().vgo_area_file_encode(_p(v), _p(out))
     return out[:n].tobytes()
+
+
+def area_files_encode(voxels: np.ndarray, threads: int = 0):
+    """store_all_blocking over a batch on `threads` threads (0 = all). -> (total bytes, sizes[n])."""
+    v = np.ascontiguousarray(voxels, np.uint8).reshape(-1, 32768)
+    out = np.empty((v.shape[0], AREA_FILE_MAX_BYTES), np.uint8)
+    sizes = np.zeros(v.shape[0], np.int64)
+    total = lib().vgo_area_files_encode(_p(v), v.shape[0], int(threads), _p(out), _p(sizes, C.c_long))
+    return int(total), sizes
 
 
 def area_file_decode(data: bytes):

@@ -16,6 +16,9 @@
  * "compressed-bytes parity UNPINNED", container layout and decode results pinned by the format.
  */
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "vg_oracle.h"
 
@@ -130,6 +133,22 @@ long vgo_area_file_encode(const uint8_t* voxels, uint8_t* out) {
     out[2] = (uint8_t)(size >> 16);
     out[3] = (uint8_t)(size >> 24);
     return 4 + vgo_lz4_compress_block(payload, PAYLOAD, out + 4);
+}
+
+/* store_all_blocking (world_persistence.rs:54-58): every area through write_binary_object on the
+ * rayon pool; out has n slots of VGO_AREA_FILE_MAX_BYTES, sizes[i] = bytes of file i. Returns the sum. */
+long vgo_area_files_encode(const uint8_t* voxels, int n, int threads, uint8_t* out, long* sizes) {
+    long total = 0;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 8) num_threads(threads) reduction(+ : total)
+#endif
+    for (int i = 0; i < n; ++i) {
+        sizes[i] = vgo_area_file_encode(voxels + (size_t)i * VGO_VOXELS_IN_AREA, out + (size_t)i * VGO_AREA_FILE_MAX_BYTES);
+        total += sizes[i];
+    }
+    (void)threads;
+    return total;
 }
 
 /* read_binary_object::<AreaDTO>(compressed): 0 and the 32768 voxels, or -1 where the reference

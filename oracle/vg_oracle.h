@@ -231,6 +231,7 @@ long vgo_lz4_decompress_block(const uint8_t* src, long n, uint8_t* dst, long cap
 long vgo_lz4_compress_block(const uint8_t* src, long n, uint8_t* dst);
 long vgo_area_file_encode(const uint8_t* voxels, uint8_t* out);
 int vgo_area_file_decode(const uint8_t* file, long n, uint8_t* voxels);
+long vgo_area_files_encode(const uint8_t* voxels, int n, int threads, uint8_t* out, long* sizes);
 
 /* ---------------------------------------------------------------- bomb explosions (physics.c)
  * BombSimulator::handle_explosions / explode_at (bomb_simulator.rs:191-262).  removed / bombs need
