@@ -1,13 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- chunks/sec (gen + light + mesh) of the B200 chunk pipeline.
 
-Workload (BASELINE.json configs[2], the config the metric is quoted on): a 128x128 region of
-chunk columns ("areas") centred on the spawn area, world name "test": generate the region plus
-the one-area ring its border faces need (130x130 = 16 900 areas: noise -> block IDs -> trees ->
-column heights), then mesh the 16 384 inner areas (face culling + vertex/index/record emission).
-One step = one such pass.  With N GPUs every rank does its own 128x128 region (rank r is shifted
-by r*128 areas in x): weak scaling, no data-path collective (areas are pure functions of seed and
-coordinates; the halo ring is regenerated, DESIGN.md "Multi-GPU").
+Workload (BASELINE.json configs[2], the config the metric is quoted on): ONE 128x128 region of
+chunk columns ("areas") centred on the spawn area, world name "test".  A step generates the region
+plus the one-area ring its border faces need (130x130 = 16 900 areas: noise -> block IDs -> trees ->
+column heights) and meshes the 16 384 inner areas (face culling + vertex/index/record emission).
+With N GPUs the region is SHARDED: rank r owns the rows shard_rows(128, N, r) and regenerates the
+ring around its strip (strong scaling, no data-path collective: areas are pure functions of seed
+and coordinates, DESIGN.md "Multi-GPU").  The same line also carries, measured in the same run:
+
+  weak          every rank its own 128x128 region (N > 1 only; round 1's figure)
+  value_cold    the strong step with a region that moves every step (no list caches, unload + load)
+  config5       BASELINE.json configs[4]: 512x512 world pre-generation (generate -> save files ->
+                pinned host memory), rows sharded over the ranks
+  e2e           the step through the C ABI with host buffers: compact transport (save files + 4-byte
+                records) as `value`; raw streams, two pipelined contexts and the C++ host mirror of
+                Renderer::load_all_blocking next to it
+  frame / codec / edit_storm (N = 1): the callers either side of the path
 
   python bench.py --gpus N --steps K --warmup W            our CUDA path
   python bench.py --impl reference --gpus N --steps K ...  the CPU restatement of the reference
@@ -29,12 +38,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-REGION = 128           # areas per side meshed per GPU per step
-CPU_SAMPLE = 64        # cpu_baseline sample: 64x64 areas of the same region
-REF_SAMPLE = 32        # --impl reference: 32x32 areas per step
+REGION = 128           # areas per side of the config-3 region
+C5_REGION = 512        # areas per side of the config-5 world
+C5_BATCH_ROWS = 16     # config 5 is swept in batches of 16 rows x 512 areas
+CPU_SAMPLE = 64        # cpu_baseline sample of the GPU arm: 64x64 areas of the same region
 WORLD_NAME = "test"    # the reference's own test seed (generator.rs:157)
 
-# algorithmic work per unit (DESIGN.md "Roofline accounting")
+# algorithmic work per unit (DESIGN.md "Roofline accounting"; pinned by tests/test_op_counts.py)
 F2_OPS = 58            # f64 add/mul issued per 2-D simplex octave incl. the Fbm accumulate
 F3_OPS = 83            # f64 add/mul issued per 3-D simplex octave incl. the Fbm accumulate
 AREA_BYTES = 32768 + 256
@@ -45,6 +55,14 @@ def env_int(name, default):
         return int(os.environ.get(name, default))
     except ValueError:
         return default
+
+
+def host_threads() -> int:
+    """Every core this process may run on -- NOT OMP_NUM_THREADS (torchrun exports it as 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def measured_peaks():
@@ -110,57 +128,91 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU legs (oracle)
-def cpu_pass(seed, n_side, faithful=True):
-    """One gen+light+mesh pass of the CPU restatement over an n_side^2 sample of the workload
-    region (plus its ring).  faithful: permutation tables rebuilt per area (generator.rs:51), gen
-    parallel over areas on all threads (rayon par_iter, world_persistence.rs:90-93), mesh serial on
-    one thread (renderer.rs:468-472).  generous: tables hoisted, mesh area-parallel too."""
+def cpu_pass(seed, n_side, faithful=True, threads=0):
+    """One gen+light+mesh pass of the CPU restatement over the centred n_side^2 part of the workload
+    region (plus its ring); n_side = REGION is the whole config.  faithful: permutation tables
+    rebuilt per area (generator.rs:51), gen parallel over areas on all threads (rayon par_iter,
+    world_persistence.rs:90-93), mesh serial on one thread (renderer.rs:468-472).  generous: tables
+    hoisted, mesh area-parallel too."""
     import oracle
     from voxel_game_b200.world import region_xy, spawn_region
 
-    ax0, ay0, _, _ = spawn_region(REGION)
+    threads = threads or host_threads()
+    ax0, ay0, _, _ = spawn_region(n_side)
     ring = region_xy(ax0 - 1, ay0 - 1, n_side + 2, n_side + 2)
     inner = region_xy(ax0, ay0, n_side, n_side)
     t0 = time.perf_counter()
-    vox, mh, _, threads = oracle.generate_areas(seed, ring, rebuild_tables_per_area=faithful, threads=0)
+    vox, mh, _, used = oracle.generate_areas(seed, ring, rebuild_tables_per_area=faithful, threads=threads)
     t1 = time.perf_counter()
     world = oracle.World(ax0 - 1, ay0 - 1, n_side + 2, n_side + 2, vox, mh)
     t2 = time.perf_counter()
-    faces, recs = world.mesh_areas(inner, threads=1 if faithful else 0)
+    faces, recs = world.mesh_areas(inner, threads=1 if faithful else threads)
     t3 = time.perf_counter()
     return {"areas": n_side * n_side, "gen_s": t1 - t0, "mesh_s": t3 - t2,
-            "total_s": (t1 - t0) + (t3 - t2), "threads": threads, "faces": faces}
+            "total_s": (t1 - t0) + (t3 - t2), "threads": used, "faces": faces}
+
+
+def cpu_pregen_pass(seed, n_side, threads=0):
+    """Config 5 on the CPU: generate (faithful) + store_all_blocking (bincode + LZ4 per area on the
+    rayon pool, world_persistence.rs:54-58) over a centred n_side^2 sample of the 512x512 world."""
+    import oracle
+    from voxel_game_b200.world import region_xy, spawn_region
+
+    threads = threads or host_threads()
+    ax0, ay0, _, _ = spawn_region(n_side)
+    xy = region_xy(ax0, ay0, n_side, n_side)
+    t0 = time.perf_counter()
+    vox, _, _, used = oracle.generate_areas(seed, xy, rebuild_tables_per_area=True, threads=threads)
+    t1 = time.perf_counter()
+    total, _ = oracle.area_files_encode(vox, threads=threads)
+    t2 = time.perf_counter()
+    return {"areas": len(xy), "gen_s": t1 - t0, "store_s": t2 - t1, "total_s": t2 - t0, "threads": used,
+            "file_bytes": int(total)}
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the same config-3 region (all 128x128 areas + ring per step) on every host
+    thread of the box.  Rank 0 alone works; the thread count is set explicitly (torchrun exports
+    OMP_NUM_THREADS=1) and reported as `cores`."""
     if rank != 0:
         return 0
     import oracle
 
+    native = oracle.use_native_build()  # -march=native on the machine that is timed
+    threads = host_threads()
     seed = oracle.hash_world_name(WORLD_NAME)
+    n_side = args.ref_side
     for _ in range(args.warmup):
-        cpu_pass(seed, REF_SAMPLE)
+        cpu_pass(seed, n_side, threads=threads)
     t0 = time.perf_counter()
     last = None
     for _ in range(args.steps):
-        last = cpu_pass(seed, REF_SAMPLE)
+        last = cpu_pass(seed, n_side, threads=threads)
     dt = time.perf_counter() - t0
-    value = REF_SAMPLE * REF_SAMPLE * args.steps / dt
-    gen = cpu_pass(seed, REF_SAMPLE, faithful=False)
-    sample = (f"{REF_SAMPLE}x{REF_SAMPLE} areas of the {REGION}x{REGION} region per step (+ ring), "
-              "gen parallel on all threads with per-area table rebuild, mesh on 1 thread (as the reference)")
+    value = n_side * n_side * args.steps / dt
+    gen = cpu_pass(seed, n_side, faithful=False, threads=threads)
+    c5 = cpu_pregen_pass(seed, 64, threads=threads)
+    whole = n_side == REGION
+    sample = (f"{'the whole' if whole else f'the centred {n_side}x{n_side} of the'} {REGION}x{REGION} region per step (+ ring), "
+              f"gen parallel on {last['threads']} threads with per-area table rebuild ({last['gen_s']:.2f} s), "
+              f"mesh on 1 thread as the reference ({last['mesh_s']:.2f} s)")
     line = {
         "impl": "reference", "metric": "chunks/sec (gen+light+mesh)", "value": value, "unit": "chunks/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"c3_{REGION}x{REGION}_gen_light_mesh", "world_name": WORLD_NAME,
-                   "seed": seed, "sample": sample,
+                   "seed": seed, "sample": sample, "areas_per_step": n_side * n_side,
+                   "oracle_build": "-O3 -march=native -ffp-contract=off" if native else "-O3 -march=x86-64-v2 -ffp-contract=off (no gcc on this box)",
                    "note": "C restatement of the reference's CPU path (oracle/); the Rust/rayon binary cannot be built in this image (no cargo)"},
         "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": last["threads"], "kind": "port",
                          "sample": sample,
                          "generous_value": gen["areas"] / gen["total_s"],
                          "generous_note": "tables hoisted per seed, mesh area-parallel on all threads"},
+        "config5": {"value": c5["areas"] / c5["total_s"], "unit": "chunks/s", "cores": c5["threads"],
+                    "sample": f"64x64 areas of the {C5_REGION}x{C5_REGION} world: generate {c5['gen_s']:.2f} s + "
+                              f"store_all_blocking (bincode + LZ4 on all threads) {c5['store_s']:.2f} s",
+                    "file_bytes_per_area": c5["file_bytes"] / c5["areas"]},
         "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -175,7 +227,10 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-side", type=int, default=REGION,
+                    help="reference arm: side of the centred part of the region per step (default: all of it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip frame / codec / edit storm / config 5 / e2e variants")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -217,6 +272,20 @@ def main():
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     seed = vg.hash_world_name(WORLD_NAME)
     ctx = vg.Context(local_rank, seed=seed)
     # a stream of our own: torch's default stream is the NULL stream, which vx_set_stream reads as
@@ -225,50 +294,95 @@ def main():
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
-    ax0, ay0, nx, ny = vg.spawn_region(REGION)
-    ax0 += rank * REGION  # weak scaling: every rank owns its own 128x128 region
-    gen_xy = vg.region_xy(ax0 - 1, ay0 - 1, nx + 2, ny + 2)
-    mesh_xy = vg.region_xy(ax0, ay0, nx, ny)
+    def strip(shift_x=0, whole=False):
+        """(generate list, mesh list) of this rank: its rows of the region + the ring around them."""
+        ax0, ay0, nx, ny = vg.spawn_region(REGION)
+        ax0 += shift_x
+        lo, hi = (0, ny) if whole else vg.shard_rows(ny, world, rank)
+        return (vg.region_xy(ax0 - 1, ay0 + lo - 1, nx + 2, hi - lo + 2), vg.region_xy(ax0, ay0 + lo, nx, hi - lo))
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        """W untimed + K timed calls of fn(i) between barriers and device syncs; CUDA events on the
+        stream the kernels run on; -> (ms for the K steps, max over ranks; clocks)."""
+        for i in range(warmup):
+            fn(i)
+        ctx.timings()  # clears the accumulators: kernel times cover the timed steps only
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), clocks
+
+    # ---- device-resident throughput (`value`): the sharded region, same lists every step
+    gen_xy, mesh_xy = strip()
     n_gen, n_mesh = len(gen_xy), len(mesh_xy)
+    last = {}
 
-    def step():
-        ctx.generate(gen_xy, read=False)
-        return ctx.mesh(mesh_xy)
-
-    # ---- device-resident throughput (`value`)
-    ctx.set_timing(True)
-    info = None
-    for _ in range(args.warmup):
-        info = step()
-    ctx.timings()  # clears the accumulators: the kernel times below cover the timed steps only
-    sampler = ClockSampler(local_rank)
-    barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
+    def step(_i):
         ctx.generate(gen_xy, read=False)  # enqueued; vx_mesh is ordered behind it and waits for the totals
-        info = ctx.mesh(mesh_xy)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        tms = torch.tensor([ms], device="cuda")
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-    value = n_mesh * world * args.steps / (ms * 1e-3)
+        last["info"] = ctx.mesh(mesh_xy)
+
+    ctx.set_timing(True)
+    ms, clocks = timed(step, args.steps, args.warmup, sample_clocks=True)
+    info = last["info"]
+    value = REGION * REGION * args.steps / (ms * 1e-3)
     t = ctx.timings()  # kernel times (CUDA events around every launch) accumulated over the timed steps
     kern = {k: t[k] / args.steps for k in ("gen_columns_ms", "gen_caves_ms", "gen_finish_ms", "mesh_count_ms", "mesh_emit_ms")}
     launches = t["mesh_launches"] + t["gen_launches"]
     work = {k: t[k] for k in ("simplex2_evals", "simplex3_evals", "cave_voxels", "cave_columns", "cave_evals")}
+    faces_total = int(sum_over_ranks(info["n_faces"]))
+    recs_total = int(sum_over_ranks(info["n_recs"]))
+    gen_total = int(sum_over_ranks(n_gen))
 
+    # ---- the same step with cold lists (`value_cold`): the region moves by 130 areas every step and
+    # the previous one is unloaded, so no call ever sees a list or a resident set it has seen before
+    ctx.set_timing(False)
+    cold_steps = args.steps
+    cold_lists = [strip(shift_x=130 * (i + 1)) for i in range(cold_steps + 3)]
+    prev = [gen_xy]
+
+    def cold_step(i):
+        g, m = cold_lists[i]
+        ctx.unload(prev[0])
+        ctx.generate(g, read=False)
+        ctx.mesh(m)
+        prev[0] = g
+
+    cold_ms, _ = timed(cold_step, cold_steps, 3)
+    ctx.unload(prev[0])
+    value_cold = REGION * REGION * cold_steps / (cold_ms * 1e-3)
+
+    # ---- weak scaling (N > 1): every rank its own whole region, as in round 1
+    weak = None
+    if world > 1:
+        wg, wm = strip(shift_x=rank * REGION, whole=True)
+
+        def weak_step(_i):
+            ctx.generate(wg, read=False)
+            ctx.mesh(wm)
+
+        w_ms, _ = timed(weak_step, args.steps, 3)
+        weak = {"value": len(wm) * world * args.steps / (w_ms * 1e-3), "unit": "chunks/s", "scaling": "weak",
+                "ms_per_step": w_ms / args.steps, "areas_meshed_per_gpu": len(wm),
+                "note": "every rank generates and meshes its own 128x128 region (round 1's bench line)"}
+        ctx.unload(wg)
+    ctx.generate(gen_xy, read=False)
+    info = ctx.mesh(mesh_xy)  # the resident mesh the sections below read
+
+    extras = not args.no_extras
     # ---- per-frame visibility over the resident mesh (K7; not part of `value`): a camera on the
     # spawn surface with a render distance that covers the whole region
     frame = None
-    if world == 1:
+    if world == 1 and extras:
         view = vg.make_view((8.0, 8.0, 58.0), (9.0, 8.5, 59.0), render_size=REGION // 2)
         ctx.set_timing(True)
         for _ in range(3):
@@ -286,30 +400,16 @@ def main():
         frame_bytes = recs_in_view * 16 + vis["n_visible"] * 4
         frame = {"ms": f_ms, "visible_areas": vis["n_areas"], "records_tested": recs_in_view,
                  "visible_voxels": vis["n_visible"], "visible_faces": vis["n_faces"],
-                 "records_per_s": recs_in_view / (f_ms * 1e-3), "algorithmic_bytes": frame_bytes,
-                 "note": "vx_visible: areas + count + scan + scatter (4 launches); the records are read twice"}
+                 "records_per_s": recs_in_view / (f_ms * 1e-3), "algorithmic_bytes": frame_bytes}
 
-    # ---- world pre-generation through save files (K8 / K9; not part of `value`): generate, compress
-    # on the device, ship the files to pinned host memory; and the way back (files -> resident areas)
+    # ---- save files (K8 / K9; not part of `value`): kernel times of the encoder and the decoder
     codec = None
-    if world == 1:
+    if world == 1 and extras:
         ctx.set_timing(True)
-        total = ctx.encode_areas(gen_xy, read=False)  # first call: sizes the pinned buffer (and loads the kernels)
-        files_pin = vg.PinnedArray((int(total * 1.05) + 4096,), np.uint8)
-        for _ in range(2):
-            ctx.generate(gen_xy, read=False)
-            ctx.encode_areas(gen_xy, out=files_pin.array)
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pre_steps = 5
-        torch.cuda.synchronize()
-        p0.record(stream)
-        for _ in range(pre_steps):
-            ctx.generate(gen_xy, read=False)
-            blob, offs = ctx.encode_areas(gen_xy, out=files_pin.array)
-            enc_ms = ctx.timings()["codec_ms"]
-        p1.record(stream)
-        torch.cuda.synchronize()
-        pre_ms = p0.elapsed_time(p1) / pre_steps
+        total = ctx.encode_areas(gen_xy, read=False)  # first call: sizes the buffers (and loads the kernels)
+        ctx.timings()
+        blob, offs = ctx.encode_areas(gen_xy)
+        enc_ms = ctx.timings()["codec_ms"]
         with vg.Context(local_rank, seed=seed) as other:
             other.set_timing(True)
             other.decode_areas(gen_xy, blob, offs, read_heights=False)
@@ -317,24 +417,79 @@ def main():
             other.decode_areas(gen_xy, blob, offs, read_heights=False)
             dec_ms = other.timings()["codec_ms"]
         codec = {"encode_ms": enc_ms, "decode_ms": dec_ms, "areas": n_gen, "file_bytes_total": int(total),
-                 "file_bytes_per_area": total / n_gen, "ratio_vs_raw": n_gen * 32768 / total,
-                 "pregen_e2e_chunks_per_s": n_gen / (pre_ms * 1e-3), "pregen_e2e_ms": pre_ms,
-                 "pregen_d2h_bytes": int(total) + 8 * (n_gen + 1),
-                 "note": "pregen_e2e = vx_generate + vx_encode_areas + vx_encode_read of every file into pinned host "
-                         "memory (the bytes store_blocking writes to disk); encode reads 32 KiB per area twice"}
-        files_pin.free()
+                 "file_bytes_per_area": total / n_gen, "ratio_vs_raw": n_gen * 32768 / total}
+        del blob
+
+    # ---- config 5 (BASELINE.json configs[4]): 512x512 world pre-generation, rows sharded over the
+    # ranks, swept in batches of 16 rows: generate -> compress on the device -> files and heights in
+    # pinned host memory (the bytes store_all_blocking writes) -> unload.  Two contexts on two host
+    # threads take alternate batches, so the copies of one overlap the kernels of the other.
+    config5 = None
+    if extras:
+        cx0, cy0, cnx, cny = vg.spawn_region(C5_REGION)
+        lo, hi = vg.shard_rows(cny, world, rank)
+        batches = [vg.region_xy(cx0, cy0 + r0, cnx, min(C5_BATCH_ROWS, hi - r0)) for r0 in range(lo, hi, C5_BATCH_ROWS)]
+        max_areas = max(len(b) for b in batches)
+        workers = [ctx, vg.Context(local_rank, seed=seed)]
+        pins = [{"files": vg.PinnedArray((max_areas * 2600 + 4096,), np.uint8),
+                 "mh": vg.PinnedArray((max_areas, 256), np.uint8)} for _ in workers]
+        c5_bytes = [0, 0]
+
+        def c5_worker(k, count_bytes):
+            c, p = workers[k], pins[k]
+            for b in batches[k::2]:
+                c.generate(b, max_height_out=p["mh"].array[: len(b)], read=False)
+                files, _offs = c.encode_areas(b, out=p["files"].array)
+                c.unload(b)
+                if count_bytes:
+                    c5_bytes[k] += len(files)
+
+        def c5_sweep(count_bytes=False):
+            th = [threading.Thread(target=c5_worker, args=(k, count_bytes)) for k in range(2)]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+
+        workers[1].set_timing(False)
+        ctx.unload(gen_xy)
+        c5_sweep()  # warm-up (sizes pools and codec buffers)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        c5_sweep(count_bytes=True)
+        torch.cuda.synchronize()
+        c5_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        c5_files = sum_over_ranks(float(sum(c5_bytes)))
+        c5_d2h = c5_files + (8 + 256) * C5_REGION * C5_REGION
+        config5 = {"value": C5_REGION * C5_REGION / c5_s, "unit": "chunks/s", "ms": c5_s * 1e3,
+                   "areas": C5_REGION * C5_REGION, "areas_per_gpu": (hi - lo) * cnx, "batch_areas": max_areas,
+                   "d2h_bytes": int(c5_d2h), "file_bytes_per_area": c5_files / (C5_REGION * C5_REGION),
+                   "timing": "host wall clock around the whole sweep (device idle before and after), max over ranks",
+                   "note": "vx_generate + vx_encode_areas + vx_encode_read into pinned host memory + vx_unload per batch; "
+                           "two contexts on two host threads per GPU take alternate batches; parity: "
+                           "tests/test_gpu_parity.py::test_config5_512x512_pregeneration_sample"}
+        workers[1].close()
+        for p in pins:
+            for a in p.values():
+                a.free()
+        ctx.generate(gen_xy, read=False)
+        info = ctx.mesh(mesh_xy)
 
     # ---- edit storm (BASELINE.json configs[3]; not part of `value`): 100 000 place/break events over a
-    # loaded 64x64 region in batches of 1 000 -- vx_apply_edits (World::set + column heights) and a
-    # remesh of the dirty areas per batch, as a simulator tick would issue them
+    # loaded 64x64 region in batches of 1 000 -- vx_apply_edits (World::set + column heights), then
+    # vx_update_locations (Renderer::update_location: <= 7 voxel meshes per edit) read back to the host
     edit_storm = None
-    if world == 1:
+    if world == 1 and extras:
         with vg.Context(local_rank, seed=seed) as ec:
             n_side = 64
             ex0, ey0, _, _ = vg.spawn_region(n_side)
+            exy = vg.region_xy(ex0, ey0, n_side, n_side)
+            ec.set_mesh_retention(True)
             ec.generate(vg.region_xy(ex0 - 1, ey0 - 1, n_side + 2, n_side + 2), read=False)
-            ec.mesh(vg.region_xy(ex0, ey0, n_side, n_side))
-            vox0, _ = ec.read_areas(vg.region_xy(ex0, ey0, n_side, n_side))
+            ec.mesh(exy)
+            vox0, _ = ec.read_areas(exy)
             rng = np.random.default_rng(0x5EEDED17)
             n_edits, batch = 100_000, 1000
             gx = rng.integers(0, n_side * 16, n_edits)
@@ -348,24 +503,45 @@ def main():
             edits["gy"] = ey0 * 16 + gy
             edits["gz"] = gz
             edits["voxel"] = np.where(cur != 0, 0, palette[rng.integers(0, 6, n_edits)])
-            for lo in range(0, 3 * batch, batch):  # warm-up
-                d = ec.apply_edits(edits[lo:lo + batch])
-                ec.mesh(d)
+            locs = np.stack([edits["gx"], edits["gy"], edits["gz"]], axis=1).astype(np.uint32)
+
+            def storm(lo_, hi_, incremental):
+                recs_n = faces_n = dirty_n = 0
+                for b0 in range(lo_, hi_, batch):
+                    d = ec.apply_edits(edits[b0:b0 + batch])
+                    if incremental:
+                        di, _r, _v, _i = ec.update_locations(locs[b0:b0 + batch])
+                        recs_n += di["n_recs"]
+                        faces_n += di["n_faces"]
+                    else:
+                        faces_n += ec.mesh(d)["n_faces"]
+                    dirty_n += len(d)
+                ec.sync()
+                return recs_n, faces_n, dirty_n
+
+            half = n_edits // 2
+            storm(0, 3 * batch, True)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            dirty_total = faces_total = 0
-            for lo in range(0, n_edits, batch):
-                d = ec.apply_edits(edits[lo:lo + batch])
-                inf = ec.mesh(d)
-                dirty_total += len(d)
-                faces_total += inf["n_faces"]
-            ec.sync()
-            wall = time.perf_counter() - t0
-            edit_storm = {"edits": n_edits, "batch": batch, "region": "64x64 areas", "ms_per_batch": wall * 1e3 / (n_edits // batch),
-                          "edits_per_s": n_edits / wall, "dirty_areas_remeshed": dirty_total,
-                          "areas_remeshed_per_s": dirty_total / wall, "faces_emitted": int(faces_total),
-                          "note": "wall clock over 100 batches: vx_apply_edits + vx_mesh of the dirty areas (edited area, "
-                                  "plus the neighbour for border columns); meshes stay on the device"}
+            r_n, f_n, _ = storm(3 * batch, half, True)
+            inc_wall = time.perf_counter() - t0
+            inc_edits = half - 3 * batch
+            storm(half, half + 3 * batch, False)
+            t0 = time.perf_counter()
+            _, f2_n, d_n = storm(half + 3 * batch, n_edits, False)
+            re_wall = time.perf_counter() - t0
+            re_edits = n_edits - half - 3 * batch
+            edit_storm = {
+                "edits": n_edits, "batch": batch, "region": "64x64 areas",
+                "incremental": {"ms_per_batch": inc_wall * 1e3 / (inc_edits // batch), "edits_per_s": inc_edits / inc_wall,
+                                "voxel_meshes_per_edit": r_n / inc_edits, "faces_per_edit": f_n / inc_edits,
+                                "d2h_bytes_per_edit": (r_n * 16 + f_n * 172) / inc_edits,
+                                "note": "end to end, wall clock: vx_apply_edits + vx_update_locations + vx_update_read "
+                                        "(records, vertices, indices of the <= 7 voxels per edit in host memory)"},
+                "remesh_dirty_areas": {"ms_per_batch": re_wall * 1e3 / (re_edits // batch), "edits_per_s": re_edits / re_wall,
+                                       "areas_per_batch": d_n / (re_edits // batch), "faces_per_edit": f2_n / re_edits,
+                                       "note": "round 1's form: vx_apply_edits + vx_mesh of the dirty areas, meshes stay on the device"},
+            }
 
     # ---- end to end through the C ABI with host buffers (`e2e`)
     # The pinned buffers are placed when they are allocated: do that from a core next to the GPU
@@ -379,46 +555,118 @@ def main():
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
     except Exception:
         pass
-    pin = {
-        "vox": vg.PinnedArray((n_gen, 32768), np.uint8), "mh": vg.PinnedArray((n_gen, 256), np.uint8),
-        "rf": vg.PinnedArray((n_mesh + 1,), np.uint32), "ff": vg.PinnedArray((n_mesh + 1,), np.uint32),
-        "recs": vg.PinnedArray((info["n_recs"],), vg.REC_DTYPE),
-        "verts": vg.PinnedArray((info["n_faces"] * 4,), vg.VERTEX_DTYPE),
-        "idx": vg.PinnedArray((info["n_faces"] * 6,), np.uint16),
-    }
-    mesh_out = (pin["rf"].array, pin["ff"].array, pin["recs"].array, pin["verts"].array, pin["idx"].array)
-    for p_ in pin.values():
-        p_.array.view(np.uint8).reshape(-1)[::4096] = 0  # touch every page while still next to the GPU
+    ctx.set_timing(False)
+    files_total = ctx.encode_areas(gen_xy, read=False)
+
+    def compact_buffers():
+        p = {"files": vg.PinnedArray((int(files_total * 1.1) + 4096,), np.uint8),
+             "mh": vg.PinnedArray((n_gen, 256), np.uint8),
+             "rf": vg.PinnedArray((n_mesh + 1,), np.uint32),
+             "packed": vg.PinnedArray((int(info["n_recs"] * 1.05) + 1024,), np.uint32)}
+        for a in p.values():
+            a.array.view(np.uint8).reshape(-1)[::4096] = 0  # touch every page while still next to the GPU
+        return p
+
+    def compact_step(c, p):
+        """Everything the host needs of a step, in its compact form: the areas as the reference's own
+        save files (LZ4 of the block IDs, what load_blocking reads), the column heights, and the mesh
+        as 4-byte records (the 16-byte record, vertices and indices are a pure function of them)."""
+        c.generate(gen_xy, max_height_out=p["mh"].array, read=False)
+        c.encode_areas(gen_xy, out=p["files"].array)
+        inf = c.mesh(mesh_xy)
+        c.mesh_read_compact(inf, out=(p["rf"].array, p["packed"].array))
+
+    pin_c = compact_buffers()
+    e2e_steps = max(3, args.steps)
+    e2e_ms, _ = timed(lambda _i: compact_step(ctx, pin_c), e2e_steps, 3)
+    e2e_value = REGION * REGION * e2e_steps / (e2e_ms * 1e-3)
+    h2d = sum_over_ranks((2 * n_gen + n_mesh) * 8)  # the area lists of the three calls {ax, ay}
+    d2h = sum_over_ranks(files_total + 8 * (n_gen + 1) + 256 * n_gen + 4 * (n_mesh + 1) + 4 * info["n_recs"])
+    e2e = {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "transport": "compact",
+           "note": "one context, one host thread: vx_generate (heights to the host) + vx_encode_areas/_read (the areas as the "
+                   "reference's save files) + vx_mesh + vx_mesh_read_compact (4-byte records) into pinned host buffers"}
+
+    if extras:
+        # (b) two contexts on two host threads, each running whole steps: copies of one overlap kernels of the other
+        c2 = vg.Context(local_rank, seed=seed)
+        c2.generate(gen_xy, read=False)
+        c2.mesh(mesh_xy)
+        c2.encode_areas(gen_xy, read=False)
+        pin_c2 = compact_buffers()
+        pair_steps = max(2, e2e_steps // 2)
+
+        def pair_worker(c, p, k):
+            for _ in range(k):
+                compact_step(c, p)
+            c.sync()
+
+        def pair_run(k):
+            th = [threading.Thread(target=pair_worker, args=(c, p, k)) for c, p in ((ctx, pin_c), (c2, pin_c2))]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+
+        pair_run(2)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pair_run(pair_steps)
+        torch.cuda.synchronize()
+        pair_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e["two_contexts"] = {"value": REGION * REGION * 2 * pair_steps / pair_s, "unit": "chunks/s",
+                               "ms_per_step": pair_s * 1e3 / (2 * pair_steps), "steps": 2 * pair_steps,
+                               "note": "the same compact step from two host threads with one context each (wall clock)"}
+        c2.close()
+        for a in pin_c2.values():
+            a.free()
+
+        # (c) raw streams, round 1's e2e: block IDs, heights, 16-byte records, vertices, indices
+        pin = {
+            "vox": vg.PinnedArray((n_gen, 32768), np.uint8), "mh": vg.PinnedArray((n_gen, 256), np.uint8),
+            "rf": vg.PinnedArray((n_mesh + 1,), np.uint32), "ff": vg.PinnedArray((n_mesh + 1,), np.uint32),
+            "recs": vg.PinnedArray((info["n_recs"],), vg.REC_DTYPE),
+            "verts": vg.PinnedArray((info["n_faces"] * 4,), vg.VERTEX_DTYPE),
+            "idx": vg.PinnedArray((info["n_faces"] * 6,), np.uint16),
+        }
+        mesh_out = (pin["rf"].array, pin["ff"].array, pin["recs"].array, pin["verts"].array, pin["idx"].array)
+        for p_ in pin.values():
+            p_.array.view(np.uint8).reshape(-1)[::4096] = 0
+
+        def raw_step(_i):
+            ctx.generate(gen_xy, voxels_out=pin["vox"].array, max_height_out=pin["mh"].array)
+            inf = ctx.mesh(mesh_xy)
+            ctx.mesh_read(inf, out=mesh_out)
+
+        raw_steps = 3
+        raw_ms, _ = timed(raw_step, raw_steps, 1)
+        raw_d2h = sum_over_ranks(n_gen * AREA_BYTES + info["rec_bytes"] + info["vertex_bytes"] + info["index_bytes"] + 8 * (n_mesh + 1))
+        e2e["raw"] = {"value": REGION * REGION * raw_steps / (raw_ms * 1e-3), "unit": "chunks/s",
+                      "ms_per_step": raw_ms / raw_steps, "d2h_bytes_per_step": int(raw_d2h), "steps": raw_steps,
+                      "note": "vx_generate + vx_mesh + vx_mesh_read: raw block IDs, heights, records, vertices, indices (PCIe-bound)"}
+        for p_ in pin.values():
+            p_.free()
     if world == 1:
         os.sched_setaffinity(0, saved_affinity)
-
-    def e2e_step():
-        ctx.generate(gen_xy, voxels_out=pin["vox"].array, max_height_out=pin["mh"].array)
-        inf = ctx.mesh(mesh_xy)
-        ctx.mesh_read(inf, out=mesh_out)
-        return inf
-
-    ctx.set_timing(False)
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    torch.cuda.synchronize()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(stream)
-    for _ in range(e2e_steps):
-        e2e_step()
-    f1.record(stream)
-    torch.cuda.synchronize()
-    barrier()
-    e2e_ms = f0.elapsed_time(f1)
-    if world > 1:
-        tms = torch.tensor([e2e_ms], device="cuda")
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tms.item())
-    e2e_value = n_mesh * world * e2e_steps / (e2e_ms * 1e-3)
-    h2d = (n_gen + n_mesh) * 16  # the two job lists {ax, ay, slot, 0}
-    d2h = n_gen * AREA_BYTES + info["rec_bytes"] + info["vertex_bytes"] + info["index_bytes"] + 2 * 4 * (n_mesh + 1) + 8
+    if extras and world == 1:
+        # (d) what the game would feel: Renderer::load_all_blocking of the C++ host mirror -- device mesh,
+        # transfer, and the per-voxel Mesh maps (HashMap<AreaLocation, RenderArea>) rebuilt on the host
+        hr = vg.HostRenderer(ctx)
+        e2e["host_renderer"] = {}
+        for transport in ("compact", "raw"):
+            hr.clear()
+            t0 = time.perf_counter()
+            hr.load_all_blocking(mesh_xy, transport=transport, threads=0)
+            wall = time.perf_counter() - t0
+            e2e["host_renderer"][transport] = {"value": n_mesh / wall, "unit": "chunks/s (mesh only)", "ms": wall * 1e3,
+                                               "voxel_meshes": hr.voxel_count()}
+        e2e["host_renderer"]["note"] = ("Renderer::load_all_blocking of host/voxel_game.hpp over the 16 384 resident areas, wall clock: "
+                                        "vx_mesh + transfer + one (u8, Voxel, Mesh{Vec<Vertex>, Vec<u16>}) per visible voxel inserted into "
+                                        "per-area hash maps on all host threads (renderer.rs:45-73,197-219)")
+        hr.clear()
+        hr.close()
 
     # ---- rooflines (per kernel, from the CUDA-event durations collected in the timed region)
     hbm_peak, hbm_src = measured_peaks()
@@ -448,7 +696,7 @@ def main():
         "mesh_emit": hbm_roof(mesh_bytes, kern["mesh_emit_ms"]),
     }
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_path):  # dram bytes per launch from the committed ncu --set full capture
+    if world == 1 and os.path.exists(traffic_path):  # dram bytes per launch of the whole-region step (ncu --set full)
         with open(traffic_path) as f:
             for k, v in json.load(f).items():
                 if k in rooflines:
@@ -456,35 +704,42 @@ def main():
     dominant = max(rooflines, key=lambda k: rooflines[k]["ms"])
     roofline = dict(rooflines[dominant], kernel=dominant)
 
+    kernel_sum = sum(kern.values())
     line = {
         "metric": "chunks/sec (gen+light+mesh)", "value": value, "unit": "chunks/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"c3_{REGION}x{REGION}_gen_light_mesh", "areas_meshed_per_gpu": n_mesh,
-                   "areas_generated_per_gpu": n_gen, "world_name": WORLD_NAME, "seed": seed,
-                   "faces_per_gpu": info["n_faces"], "visible_voxels_per_gpu": info["n_recs"],
-                   "parallelism": f"areas sharded x{world}, halo regenerated, no collective",
-                   "l2": "no flush needed: each step streams ~0.55 GB of block IDs and ~1.8 GB of mesh, > 126 MB L2"},
+        "config": {"workload": f"c3_{REGION}x{REGION}_gen_light_mesh", "areas_meshed": REGION * REGION,
+                   "areas_generated": gen_total, "areas_meshed_per_gpu": n_mesh, "areas_generated_per_gpu": n_gen,
+                   "world_name": WORLD_NAME, "seed": seed, "faces": faces_total, "visible_voxels": recs_total,
+                   "parallelism": f"rows of the one region sharded x{world}, halo ring regenerated, no collective",
+                   "l2": "no flush needed: a step streams ~0.55 GB of block IDs and ~1.8 GB of mesh over all ranks, "
+                         "per rank > 126 MB L2 at every N <= 8"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                "note": "vx_generate + vx_mesh + vx_mesh_read into pinned host buffers (block IDs, heights, records, vertices, indices)"},
+        "value_cold": {"value": value_cold, "unit": "chunks/s", "ms_per_step": cold_ms / cold_steps, "steps": cold_steps,
+                       "note": "the region moves by 130 areas every step and the previous one is unloaded: "
+                               "no list or residency cache can hit (vx_unload + vx_generate + vx_mesh)"},
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "rooflines": rooflines,
         "kernel_ms_per_step": kern,
+        "kernel_ms_sum": kernel_sum,
         # the stages separately (device time of their kernels; column heights and bit
         # planes are fused into generation, so LIGHT L1 has no time of its own)
-        "stage_chunks_per_s": {
-            "gen_plus_light": n_gen * world / ((kern["gen_columns_ms"] + kern["gen_caves_ms"] + kern["gen_finish_ms"]) * 1e-3),
-            "mesh": n_mesh * world / ((kern["mesh_count_ms"] + kern["mesh_emit_ms"]) * 1e-3),
+        "stage_chunks_per_s_per_gpu": {
+            "gen_plus_light": n_gen / ((kern["gen_columns_ms"] + kern["gen_caves_ms"] + kern["gen_finish_ms"]) * 1e-3),
+            "mesh": n_mesh / ((kern["mesh_count_ms"] + kern["mesh_emit_ms"]) * 1e-3),
         },
-        "work_per_step": {"simplex2_octave_evals": s2, "simplex3_octave_evals": s3, "cave_voxels": cave_vox,
-                          "cave_octave_evals": cave3, "cave_octave_evals_without_early_exit": 14 * cave_vox,
-                          "f64_ops": s2 * F2_OPS + s3 * F3_OPS},
+        "work_per_step_rank0": {"simplex2_octave_evals": s2, "simplex3_octave_evals": s3, "cave_voxels": cave_vox,
+                                "cave_octave_evals": cave3, "cave_octave_evals_without_early_exit": 14 * cave_vox,
+                                "f64_ops": s2 * F2_OPS + s3 * F3_OPS},
     }
-
+    if weak is not None:
+        line["weak"] = weak
+    if config5 is not None:
+        line["config5"] = config5
     if frame is not None:
         frame["roofline"] = hbm_roof(frame["algorithmic_bytes"], frame["ms"])
         line["frame"] = frame
@@ -497,8 +752,9 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
 
+        native = oracle.use_native_build()
+        threads = host_threads()
         if frame is not None:  # the same frame on one host thread (the reference: rayon par_iter)
-
             recs_h = np.empty(info["n_recs"], vg.REC_DTYPE)
             rf_h = np.empty(n_mesh + 1, np.uint32)
             ctx.mesh_read(info, out=(rf_h, None, recs_h, None, None))
@@ -507,19 +763,21 @@ def main():
             oracle.filter_visible(recs_h, rf_h, mesh_xy, oview)
             frame["cpu_port_ms_1_thread"] = (time.perf_counter() - t0) * 1e3
 
-        c = cpu_pass(oracle.hash_world_name(WORLD_NAME), CPU_SAMPLE, faithful=True)
-        g = cpu_pass(oracle.hash_world_name(WORLD_NAME), CPU_SAMPLE, faithful=False)
+        oseed = oracle.hash_world_name(WORLD_NAME)
+        c = cpu_pass(oseed, CPU_SAMPLE, faithful=True, threads=threads)
+        g = cpu_pass(oseed, CPU_SAMPLE, faithful=False, threads=threads)
         line["cpu_baseline"] = {
             "value": c["areas"] / c["total_s"], "unit": "chunks/s", "cores": c["threads"], "kind": "port",
-            "sample": f"{CPU_SAMPLE}x{CPU_SAMPLE} areas of the same region (+ ring): gen {c['gen_s']:.2f} s on "
+            "sample": f"the centred {CPU_SAMPLE}x{CPU_SAMPLE} areas of the same region (+ ring): gen {c['gen_s']:.2f} s on "
                       f"{c['threads']} threads with per-area table rebuild, mesh {c['mesh_s']:.2f} s on 1 thread",
             "generous_value": g["areas"] / g["total_s"],
             "generous_note": "tables hoisted per seed, mesh area-parallel on all threads",
+            "oracle_build": "-march=native" if native else "-march=x86-64-v2",
             "note": "C restatement of the reference (oracle/), not the Rust/rayon binary (no cargo in this image)",
         }
     if rank == 0:
         print(json.dumps(line), flush=True)
-    for p in pin.values():
+    for p in pin_c.values():
         p.free()
     ctx.close()
     if world > 1:

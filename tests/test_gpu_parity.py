@@ -616,3 +616,42 @@ def test_generate_without_outputs_is_stream_ordered(seed):
         assert info == info2
         for a, b in zip(first, second):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_strips_on_cuda_equal_unsharded(seed, shards):
+    """SURVEY 8(e) on the device: `shards` contexts (one per rank in bench.py --gpus N), each
+    generating its strip of rows of ONE region plus the regenerated ring and meshing its strip,
+    give -- concatenated in rank order -- the block IDs, heights, records, vertices and indices of
+    one context doing the whole region, byte for byte (first_face rebased by the strips before)."""
+    n = 32 if shards < 8 else 40  # 40 rows over 8 ranks: 5 each; 32 over 3: ragged 11/11/10
+    ax0, ay0 = SPAWN - n // 2, SPAWN - n // 2
+    whole_xy = vg.region_xy(ax0, ay0, n, n)
+    with vg.Context(0, seed=seed) as one:
+        one.generate(vg.region_xy(ax0 - 1, ay0 - 1, n + 2, n + 2), read=False)
+        vox, mh = one.read_areas(whole_xy)
+        info = one.mesh(whole_xy)
+        rf, ff, recs, verts, idx = one.mesh_read(info)
+    rec_base = face_base = row = 0
+    for rank in range(shards):
+        lo, hi = vg.shard_rows(n, shards, rank)
+        assert lo == row
+        row = hi
+        with vg.Context(0, seed=seed) as c:
+            c.generate(vg.region_xy(ax0 - 1, ay0 + lo - 1, n + 2, hi - lo + 2), read=False)
+            sxy = vg.region_xy(ax0, ay0 + lo, n, hi - lo)
+            svox, smh = c.read_areas(sxy)
+            sinfo = c.mesh(sxy)
+            srf, sff, srecs, sverts, sidx = c.mesh_read(sinfo)
+        a0, a1 = lo * n, hi * n  # region_xy order: index = ix + nx * iy, so a strip of rows is contiguous
+        assert np.array_equal(svox, vox[a0:a1]) and np.array_equal(smh, mh[a0:a1])
+        assert np.array_equal(srf.astype(np.int64) + rec_base, rf[a0:a1 + 1])
+        assert np.array_equal(sff.astype(np.int64) + face_base, ff[a0:a1 + 1])
+        srecs = srecs.copy()
+        srecs["first_face"] += np.uint32(face_base)
+        assert srecs.tobytes() == recs[rec_base:rec_base + sinfo["n_recs"]].tobytes()
+        assert sverts.tobytes() == verts[4 * face_base:4 * (face_base + sinfo["n_faces"])].tobytes()
+        assert np.array_equal(sidx, idx[6 * face_base:6 * (face_base + sinfo["n_faces"])])
+        rec_base += sinfo["n_recs"]
+        face_base += sinfo["n_faces"]
+    assert row == n and rec_base == info["n_recs"] and face_base == info["n_faces"]
