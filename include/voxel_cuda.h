@@ -111,6 +111,18 @@ int vx_create(int device, vx_ctx** out);         /* binds to `device`, creates a
 void vx_destroy(vx_ctx* ctx);
 const char* vx_strerror(int status);
 const char* vx_last_error(vx_ctx* ctx);
+/* Several calls as one unit.  Every call locks the context for its own duration only, but some
+ * results are fetched by a second call (vx_mesh -> vx_mesh_read / vx_mesh_read_compact,
+ * vx_encode_areas -> vx_encode_read, vx_visible / vx_visible_zone -> vx_visible_read,
+ * vx_update_locations -> vx_update_read; a failed call -> its error text): the second call reads
+ * whatever the LAST first call on the context left, so threads that share a context (rayon workers,
+ * world_persistence.rs:90-93) bracket such a pair with vx_lock / vx_unlock -- the lock is recursive
+ * and held by the calling thread until it unlocks.  The wrappers in rust/, host/ and binding.py do.
+ * vx_last_error returns a pointer into the context (valid until the next failing call: use it only
+ * under vx_lock); vx_copy_last_error copies the text out under the lock and returns its length. */
+int vx_lock(vx_ctx* ctx);
+int vx_unlock(vx_ctx* ctx);
+size_t vx_copy_last_error(vx_ctx* ctx, char* buf, size_t cap);
 /* Run on an external CUDA stream (a cudaStream_t / CUstream handle, e.g. torch's current
  * stream) instead of the context's own; NULL restores the own stream. */
 int vx_set_stream(vx_ctx* ctx, void* cuda_stream);

@@ -83,6 +83,9 @@ extern "C" {
     pub fn vx_destroy(ctx: *mut vx_ctx);
     pub fn vx_strerror(status: c_int) -> *const c_char;
     pub fn vx_last_error(ctx: *mut vx_ctx) -> *const c_char;
+    pub fn vx_copy_last_error(ctx: *mut vx_ctx, buf: *mut c_char, cap: usize) -> usize;
+    pub fn vx_lock(ctx: *mut vx_ctx) -> c_int;
+    pub fn vx_unlock(ctx: *mut vx_ctx) -> c_int;
     pub fn vx_set_stream(ctx: *mut vx_ctx, cuda_stream: *mut c_void) -> c_int;
     pub fn vx_sync(ctx: *mut vx_ctx) -> c_int;
     pub fn vx_host_alloc(bytes: usize) -> *mut c_void;
@@ -116,6 +119,15 @@ extern "C" {
     pub fn vx_visible_read(ctx: *mut vx_ctx, rec_index: *mut u32, area_visible: *mut u8) -> c_int;
     pub fn vx_light(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, light_out: *mut u8,
                     iterations: *mut c_int) -> c_int;
+    pub fn vx_update_locations(ctx: *mut vx_ctx, xyz: *const u32, n: c_int, info: *mut vx_mesh_info) -> c_int;
+    pub fn vx_update_read(ctx: *mut vx_ctx, recs: *mut vx_voxel_rec, vertices: *mut c_void, indices: *mut u16) -> c_int;
+    pub fn vx_mesh_read_compact(ctx: *mut vx_ctx, rec_first: *mut u32, packed_recs: *mut u32) -> c_int;
+    pub fn vx_set_mesh_retention(ctx: *mut vx_ctx, enabled: c_int) -> c_int;
+    pub fn vx_mesh_unload(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int) -> c_int;
+    pub fn vx_read_face_masks(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, masks_out: *mut u8,
+                              meshed_out: *mut u8) -> c_int;
+    pub fn vx_visible_zone(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, view: *const vx_view,
+                           info: *mut vx_visible_info) -> c_int;
 }
 
 #[derive(Debug)]
@@ -124,13 +136,42 @@ pub struct VxError {
     pub message: String,
 }
 
-/// Owns one `vx_ctx` (one CUDA device).  `Send + Sync`: the C side locks internally, which is
-/// what lets `AreaLoader`'s rayon workers share it (service/persistence/world_persistence.rs:90-93).
+/// Owns one `vx_ctx` (one CUDA device).  `Send + Sync`: the C side locks every call internally,
+/// which is what lets `AreaLoader`'s rayon workers share it
+/// (service/persistence/world_persistence.rs:90-93).  Results that are fetched by a SECOND call
+/// (`vx_mesh` -> `vx_mesh_read`, `vx_encode_areas` -> `vx_encode_read`, `vx_visible` ->
+/// `vx_visible_read`, `vx_update_locations` -> `vx_update_read`, a failure -> its error text) belong
+/// to whichever first call ran last on the context, so every method below that makes such a pair
+/// holds a [`Transaction`] (the context's recursive lock, `vx_lock` / `vx_unlock`) across it: two
+/// threads in `mesh()` can never read each other's sizes or buffers.
 pub struct Pipeline {
     ctx: *mut vx_ctx,
 }
 unsafe impl Send for Pipeline {}
 unsafe impl Sync for Pipeline {}
+
+/// RAII guard of the context's recursive lock; calls made by this thread while it lives are one unit.
+pub struct Transaction<'a> {
+    p: &'a Pipeline,
+}
+impl<'a> Transaction<'a> {
+    fn new(p: &'a Pipeline) -> Self {
+        unsafe { vx_lock(p.ctx) };
+        Transaction { p }
+    }
+}
+impl Drop for Transaction<'_> {
+    fn drop(&mut self) {
+        unsafe { vx_unlock(self.p.ctx) };
+    }
+}
+
+/// Result of `update_locations`: one record per touched voxel (`n_faces == 0` = removal).
+pub struct UpdateBatch {
+    pub recs: Vec<vx_voxel_rec>,
+    pub vertices: Vec<u8>,
+    pub indices: Vec<u16>,
+}
 
 /// Flat mesh of a batch of areas; `recs[rec_first[i]..rec_first[i + 1]]` belong to area `i`.
 pub struct MeshBatch {
@@ -158,11 +199,19 @@ impl Pipeline {
         Ok(p)
     }
 
+    /// The calling thread's own unit of several calls (see the type's documentation).
+    pub fn transaction(&self) -> Transaction<'_> {
+        Transaction::new(self)
+    }
+
     fn check(&self, st: c_int) -> Result<(), VxError> {
         if st == 0 {
             return Ok(());
         }
-        let message = unsafe { CStr::from_ptr(vx_last_error(self.ctx)) }.to_string_lossy().into_owned();
+        // copied out under the context's lock: another thread may be assigning the string
+        let mut buf = vec![0 as c_char; 1024];
+        unsafe { vx_copy_last_error(self.ctx, buf.as_mut_ptr(), buf.len()) };
+        let message = unsafe { CStr::from_ptr(buf.as_ptr()) }.to_string_lossy().into_owned();
         Err(VxError { status: st, message })
     }
 
@@ -199,6 +248,7 @@ impl Pipeline {
     pub fn mesh(&self, areas: &[(u32, u32)]) -> Result<MeshBatch, VxError> {
         let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
         let mut info = vx_mesh_info::default();
+        let _pair = self.transaction(); // vx_mesh + vx_mesh_read see the same batch
         self.check(unsafe { vx_mesh(self.ctx, xy.as_ptr(), areas.len() as c_int, &mut info) })?;
         let mut m = MeshBatch {
             rec_first: vec![0; areas.len() + 1],
@@ -238,6 +288,7 @@ impl Pipeline {
     pub fn encode_areas(&self, areas: &[(u32, u32)]) -> Result<Vec<Vec<u8>>, VxError> {
         let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
         let mut total = 0u64;
+        let _pair = self.transaction(); // vx_encode_areas + vx_encode_read
         self.check(unsafe { vx_encode_areas(self.ctx, xy.as_ptr(), areas.len() as c_int, &mut total) })?;
         let mut blob = vec![0u8; total as usize];
         let mut offsets = vec![0u64; areas.len() + 1];
@@ -289,11 +340,70 @@ impl Pipeline {
     /// and the record indices to draw, already in `optimise_render_order`.
     pub fn visible(&self, view: &vx_view) -> Result<(vx_visible_info, Vec<u32>), VxError> {
         let mut info = std::mem::MaybeUninit::<vx_visible_info>::zeroed();
+        let _pair = self.transaction(); // vx_visible + vx_visible_read
         self.check(unsafe { vx_visible(self.ctx, view, info.as_mut_ptr()) })?;
         let info = unsafe { info.assume_init() };
         let mut idx = vec![0u32; info.n_visible as usize];
         self.check(unsafe { vx_visible_read(self.ctx, idx.as_mut_ptr(), std::ptr::null_mut()) })?;
         Ok((info, idx))
+    }
+}
+
+impl Pipeline {
+    /// Body of `Renderer::update_location` (graphics/renderer.rs:239-286) for a batch of locations
+    /// whose voxels `apply_edits` / `explode` have just changed: the <= 7 voxel meshes per location.
+    pub fn update_locations(&self, locations: &[[u32; 3]]) -> Result<UpdateBatch, VxError> {
+        let flat: Vec<u32> = locations.iter().flatten().copied().collect();
+        let mut info = vx_mesh_info::default();
+        let _pair = self.transaction(); // vx_update_locations + vx_update_read
+        self.check(unsafe { vx_update_locations(self.ctx, flat.as_ptr(), locations.len() as c_int, &mut info) })?;
+        let mut u = UpdateBatch {
+            recs: vec![vx_voxel_rec::default(); info.n_recs as usize],
+            vertices: vec![0u8; info.vertex_bytes as usize],
+            indices: vec![0u16; info.n_faces as usize * 6],
+        };
+        self.check(unsafe {
+            vx_update_read(self.ctx, u.recs.as_mut_ptr(), u.vertices.as_mut_ptr() as *mut c_void, u.indices.as_mut_ptr())
+        })?;
+        Ok(u)
+    }
+
+    /// `mesh` with the compact transport: 4 bytes per visible voxel, `(x + 16y + 256z) | voxel << 15 |
+    /// face_mask << 20`; vertices and indices are rebuilt on the host (`MeshGenerator::generate_mesh`
+    /// stays as it is and is fed the mask).  Returns `(rec_first, packed)`.
+    pub fn mesh_compact(&self, areas: &[(u32, u32)]) -> Result<(Vec<u32>, Vec<u32>), VxError> {
+        let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
+        let mut info = vx_mesh_info::default();
+        let _pair = self.transaction(); // vx_mesh + vx_mesh_read_compact
+        self.check(unsafe { vx_mesh(self.ctx, xy.as_ptr(), areas.len() as c_int, &mut info) })?;
+        let mut rec_first = vec![0u32; areas.len() + 1];
+        let mut packed = vec![0u32; info.n_recs as usize];
+        self.check(unsafe { vx_mesh_read_compact(self.ctx, rec_first.as_mut_ptr(), packed.as_mut_ptr()) })?;
+        Ok((rec_first, packed))
+    }
+
+    /// Device mirror of `Renderer.meshes` on / off (graphics/renderer.rs:97-101).
+    pub fn set_mesh_retention(&self, enabled: bool) -> Result<(), VxError> {
+        self.check(unsafe { vx_set_mesh_retention(self.ctx, enabled as c_int) })
+    }
+
+    /// `Renderer::unload_area` (graphics/renderer.rs:111-117) for a batch.
+    pub fn mesh_unload(&self, areas: &[(u32, u32)]) -> Result<(), VxError> {
+        let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
+        self.check(unsafe { vx_mesh_unload(self.ctx, xy.as_ptr(), areas.len() as c_int) })
+    }
+
+    /// One frame over the resident meshes of the render zone: the summary and, per drawn voxel,
+    /// `zone index << 15 | (x + 16y + 256z)` in `optimise_render_order`.
+    pub fn visible_zone(&self, zone: &[(u32, u32)], view: &vx_view) -> Result<(vx_visible_info, Vec<u32>), VxError> {
+        let xy: Vec<u32> = zone.iter().flat_map(|a| [a.0, a.1]).collect();
+        let mut info = std::mem::MaybeUninit::<vx_visible_info>::zeroed();
+        let _pair = self.transaction(); // vx_visible_zone + vx_visible_read
+        self.check(unsafe { vx_visible_zone(self.ctx, xy.as_ptr(), zone.len() as c_int, view, info.as_mut_ptr()) })?;
+        let info = unsafe { info.assume_init() };
+        let mut codes = vec![0u32; info.n_visible as usize];
+        self.check(unsafe { vx_visible_read(self.ctx, codes.as_mut_ptr(), std::ptr::null_mut()) })?;
+        Ok((info, codes))
     }
 }
 

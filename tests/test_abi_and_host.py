@@ -37,6 +37,21 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) <= exported
 
 
+def test_rust_shim_declares_every_header_symbol_and_guards_the_pairs():
+    """rust/voxel_cuda/src/lib.rs cannot be compiled here (no cargo): at least its extern block names
+    every function of the header, and every wrapper that makes a query + read pair holds a
+    Transaction (vx_lock / vx_unlock) across it (Pipeline is Sync)."""
+    src = open(os.path.join(ROOT, "rust", "voxel_cuda", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (vx_[a-z0-9_]+)\s*\(", src))
+    optional = {"vx_set_timing", "vx_get_timings", "vx_diag_fp64_rate"}  # diagnostics the shim does not bind
+    assert set(_header_functions()) - optional <= declared, sorted(set(_header_functions()) - optional - declared)
+    for read_call in ("vx_mesh_read(", "vx_mesh_read_compact(", "vx_encode_read(", "vx_visible_read(", "vx_update_read("):
+        for m in re.finditer(re.escape("            " + read_call) + "|" + re.escape("unsafe { " + read_call), src):
+            body_start = src.rfind("pub fn ", 0, m.start())
+            assert "self.transaction()" in src[body_start:m.start()], f"{read_call} used without a Transaction"
+    assert "vx_copy_last_error" in src
+
+
 def test_library_is_built_for_sm_100a_only():
     out = subprocess.run(["cuobjdump", "--list-elf", vg.LIB_PATH], capture_output=True, text=True)
     if out.returncode != 0:

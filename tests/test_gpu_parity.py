@@ -655,3 +655,44 @@ def test_sharded_strips_on_cuda_equal_unsharded(seed, shards):
         rec_base += sinfo["n_recs"]
         face_base += sinfo["n_faces"]
     assert row == n and rec_base == info["n_recs"] and face_base == info["n_faces"]
+
+
+def test_query_and_read_pairs_are_atomic_across_threads(seed):
+    """vx_mesh -> vx_mesh_read (and the other query + read pairs) fetch what the LAST
+    query on the context left.  Four threads share one context and mesh batches of different sizes;
+    with the pair under vx_lock / vx_unlock (Context.mesh_and_read, the Rust / C++ `Transaction`)
+    every thread gets exactly its own batch, equal to what the batch gives alone."""
+    import threading
+
+    n = 12
+    ax0, ay0 = SPAWN - 6, SPAWN - 6
+    rows = [(0, 1), (1, 4), (4, 6), (6, 12)]  # batches of 12, 36, 24, 72 areas
+    lists = [vg.region_xy(ax0, ay0 + lo, n, hi - lo) for lo, hi in rows]
+    with vg.Context(0, seed=seed) as c:
+        c.generate(vg.region_xy(ax0 - 1, ay0 - 1, n + 2, n + 2), read=False)
+        alone = [c.mesh_and_read(xy) for xy in lists]
+        got, errs = {}, []
+
+        def worker(k):
+            try:
+                for _ in range(25):
+                    info, arrays = c.mesh_and_read(lists[k])
+                    files, offs = c.encode_areas(lists[k])
+                    got[k] = (info, arrays, files.copy(), offs)
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        assert not errs, errs
+        for k in range(4):
+            info, arrays, files, offs = got[k]
+            assert info == alone[k][0]
+            for a, b in zip(arrays, alone[k][1]):
+                assert a.tobytes() == b.tobytes()
+            assert len(offs) == len(lists[k]) + 1 and int(offs[-1]) == len(files)
+            vox, _ = c.read_areas(lists[k])
+            for i in range(len(lists[k])):
+                dec = oracle.area_file_decode(bytes(files[int(offs[i]):int(offs[i + 1])]))
+                assert dec is not None and np.array_equal(dec, vox[i])

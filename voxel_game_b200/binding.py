@@ -6,6 +6,8 @@ device is usable, importing/creating fails loudly.
 """
 from __future__ import annotations
 
+import contextlib
+import functools
 import ctypes as C
 import os
 import subprocess
@@ -43,6 +45,7 @@ ABI_SYMBOLS = [
     "vx_heightmap", "vx_visible", "vx_visible_read", "vx_encode_areas", "vx_encode_read", "vx_decode_areas",
     "vx_explode", "vx_light", "vx_diag_fp64_rate", "vx_update_locations", "vx_update_read",
     "vx_mesh_read_compact", "vx_set_mesh_retention", "vx_mesh_unload", "vx_read_face_masks", "vx_visible_zone",
+    "vx_lock", "vx_unlock", "vx_copy_last_error",
 ]
 
 
@@ -136,6 +139,10 @@ def load():
     L.vx_strerror.argtypes = [C.c_int]
     L.vx_last_error.restype = C.c_char_p
     L.vx_last_error.argtypes = [vp]
+    L.vx_lock.argtypes = [vp]
+    L.vx_unlock.argtypes = [vp]
+    L.vx_copy_last_error.restype = C.c_size_t
+    L.vx_copy_last_error.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.vx_set_stream.argtypes = [vp, vp]
     L.vx_sync.argtypes = [vp]
     L.vx_set_timing.argtypes = [vp, C.c_int]
@@ -172,10 +179,6 @@ def load():
     L.vx_mesh_unload.argtypes = [vp, vp, C.c_int]
     L.vx_read_face_masks.argtypes = [vp, vp, C.c_int, vp, vp]
     L.vx_visible_zone.argtypes = [vp, vp, C.c_int, C.POINTER(View), C.POINTER(VisibleInfo)]
-    for name in ABI_SYMBOLS:
-        fn = getattr(L, name)
-        if fn.restype is C.c_int and name not in ("vx_device_count",):
-            pass
     _lib = L
     return L
 
@@ -245,6 +248,15 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
+def _locked(method):
+    """Run a two-call helper (query + read of its result) under vx_lock."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        with self.transaction():
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
 class Context:
     """One vx_ctx: a CUDA device, a seed and the set of resident areas."""
 
@@ -281,8 +293,19 @@ class Context:
 
     def _check(self, st: int):
         if st != VX_OK:
-            msg = self._lib.vx_last_error(self._h).decode() or self._lib.vx_strerror(st).decode()
-            raise VxError(st, msg)
+            buf = C.create_string_buffer(1024)
+            self._lib.vx_copy_last_error(self._h, buf, len(buf))
+            raise VxError(st, buf.value.decode() or self._lib.vx_strerror(st).decode())
+
+    @contextlib.contextmanager
+    def transaction(self):
+        """vx_lock ... vx_unlock: a call and the read of its result as one unit when several threads
+        share the context (the two-call helpers below take it themselves)."""
+        self._lib.vx_lock(self._h)
+        try:
+            yield self
+        finally:
+            self._lib.vx_unlock(self._h)
 
     def set_seed(self, seed: int):
         self.seed = seed & 0xFFFFFFFFFFFFFFFF
@@ -366,6 +389,12 @@ class Context:
         self._check(self._lib.vx_mesh_read(self._h, _ptr(rf), _ptr(ff), _ptr(recs), _ptr(verts), _ptr(idx)))
         return out
 
+    def mesh_and_read(self, area_xy, compact: bool = False):
+        """mesh() + mesh_read() / mesh_read_compact() under one lock -> (info, arrays)."""
+        with self.transaction():
+            info = self.mesh(area_xy)
+            return info, (self.mesh_read_compact(info) if compact else self.mesh_read(info))
+
     def mesh_read_compact(self, info: dict, out=None):
         """The last mesh as 4-byte records: (rec_first u32[n+1], packed u32[n_recs]); see
         unpack_records / the C++ expander for the way back."""
@@ -393,6 +422,7 @@ class Context:
         self._check(self._lib.vx_read_face_masks(self._h, xy.ctypes.data, n, masks.ctypes.data, meshed.ctypes.data))
         return masks, meshed
 
+    @_locked
     def update_locations(self, xyz, read: bool = True):
         """Renderer::update_location for a batch of internal locations [k,3] -> info dict and, if
         read, (recs, vertices, indices); records with n_faces == 0 are removals."""
@@ -409,6 +439,7 @@ class Context:
                                              _ptr(verts) if verts.size else None, _ptr(idx) if idx.size else None))
         return d, recs, verts, idx
 
+    @_locked
     def visible_zone(self, area_xy, view: View, read: bool = True):
         """Per-frame visibility over the resident meshes of a render zone -> dict and, if read,
         (codes u32[n_visible] = zone index << 15 | local voxel index, area_visible u8[n])."""
@@ -457,6 +488,7 @@ class Context:
         return rgba
 
     # -- area save files
+    @_locked
     def encode_areas(self, area_xy, read: bool = True, out=None):
         """store_blocking for a batch of resident areas -> (files u8[total], offsets u64[n+1]);
         file i = files[offsets[i]:offsets[i+1]].  read=False leaves them on the device and returns
@@ -485,6 +517,7 @@ class Context:
                                               offsets.ctypes.data, ok.ctypes.data, _ptr(mh)))
         return ok, mh
 
+    @_locked
     def visible(self, view: View, read: bool = True):
         """Per-frame visibility over the mesh of the last mesh() call.
         -> dict(n_visible, n_faces, n_areas, n_lamps, type_first[28], lamps[<=64]) and, if read,

@@ -148,7 +148,7 @@ struct vx_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    std::mutex mu;
+    std::recursive_mutex mu;  // recursive: vx_lock / vx_unlock bracket several calls of one thread
     std::string last_error;
 
     bool has_seed = false;
@@ -656,9 +656,32 @@ void vx_destroy(vx_ctx* ctx) {
 
 const char* vx_last_error(vx_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 
+size_t vx_copy_last_error(vx_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx) return 0;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    if (buf && cap) {
+        const size_t k = ctx->last_error.size() < cap - 1 ? ctx->last_error.size() : cap - 1;
+        memcpy(buf, ctx->last_error.data(), k);
+        buf[k] = 0;
+    }
+    return ctx->last_error.size();
+}
+
+int vx_lock(vx_ctx* ctx) {
+    if (!ctx) return VX_ERR_INVALID;
+    ctx->mu.lock();
+    return VX_OK;
+}
+
+int vx_unlock(vx_ctx* ctx) {
+    if (!ctx) return VX_ERR_INVALID;
+    ctx->mu.unlock();
+    return VX_OK;
+}
+
 int vx_set_stream(vx_ctx* ctx, void* cuda_stream) {
     if (!ctx) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     cudaSetDevice(ctx->device);
     sync_stream(ctx);  // nothing stays in flight (or pending in the timers) on the stream being left
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
@@ -667,21 +690,21 @@ int vx_set_stream(vx_ctx* ctx, void* cuda_stream) {
 
 int vx_sync(vx_ctx* ctx) {
     if (!ctx) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     cudaSetDevice(ctx->device);
     return sync_stream(ctx);
 }
 
 int vx_set_timing(vx_ctx* ctx, int enabled) {
     if (!ctx) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     ctx->timing = enabled != 0;
     return VX_OK;
 }
 
 int vx_get_timings(vx_ctx* ctx, vx_timings* out) {
     if (!ctx || !out) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     bool pending = ctx->gen_counters_pending;
     for (int i = 0; i < TM_COUNT; ++i) pending = pending || ctx->ev_used[i];
     if (pending) {  // a call that did not wait (vx_generate without host outputs) is still in flight
@@ -722,7 +745,7 @@ uint64_t vx_hash_world_name(const char* world_name) {
 
 int vx_set_seed(vx_ctx* ctx, uint64_t seed) {
     if (!ctx) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     if (!ctx->d_noise_image) VX_CUDA(cudaMalloc(&ctx->d_noise_image, sizeof(NoiseImage)));
@@ -738,7 +761,7 @@ int vx_set_seed(vx_ctx* ctx, uint64_t seed) {
 int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out,
                 uint8_t* max_height_out) {
     if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     if (!ctx->has_seed) return fail(ctx, VX_ERR_NO_SEED, "vx_generate before vx_set_seed");
     VX_CUDA(cudaSetDevice(ctx->device));
     if (n == 0) return VX_OK;
@@ -772,7 +795,7 @@ int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out
 int vx_upload(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* voxels,
               uint8_t* max_height_out) {
     if (!ctx || n < 0 || (n > 0 && (!area_xy || !voxels))) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     if (n == 0) return VX_OK;
     std::vector<int> slots;
@@ -791,7 +814,7 @@ int vx_upload(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* voxels
 int vx_read_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out,
                   uint8_t* max_height_out) {
     if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     std::vector<int> slots(n);
     for (int i = 0; i < n; ++i) {
@@ -806,7 +829,7 @@ int vx_read_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_o
 
 int vx_unload(vx_ctx* ctx, const uint32_t* area_xy, int n) {
     if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     bool any = false;
     std::vector<int> freed;
     for (int i = 0; i < n; ++i) {
@@ -832,13 +855,13 @@ int vx_unload(vx_ctx* ctx, const uint32_t* area_xy, int n) {
 
 int vx_resident_count(vx_ctx* ctx) {
     if (!ctx) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     return (int)ctx->index.count;
 }
 
 int vx_column_heights(vx_ctx* ctx, const uint8_t* voxels, int n, uint8_t* max_height_out) {
     if (!ctx || n < 0 || (n > 0 && (!voxels || !max_height_out))) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     if (n == 0) return VX_OK;
     // temporary areas outside the resident pool: [voxels n*32768][heights n*256]
@@ -862,7 +885,7 @@ int vx_column_heights(vx_ctx* ctx, const uint8_t* voxels, int n, uint8_t* max_he
 
 int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
     if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     ctx->mesh_n = -1;
     ctx->frame_ready = false;
@@ -1015,7 +1038,7 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
 int vx_mesh_read(vx_ctx* ctx, uint32_t* rec_first, uint32_t* face_first, vx_voxel_rec* recs,
                  void* vertices, uint16_t* indices) {
     if (!ctx) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     if (ctx->mesh_n < 0) return fail(ctx, VX_ERR_NO_MESH, "vx_mesh_read without vx_mesh");
     VX_CUDA(cudaSetDevice(ctx->device));
     const int n = ctx->mesh_n;
@@ -1036,7 +1059,7 @@ int vx_mesh_read(vx_ctx* ctx, uint32_t* rec_first, uint32_t* face_first, vx_voxe
 
 int vx_encode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint64_t* total_bytes) {
     if (!ctx || n < 0 || (n > 0 && !area_xy) || !total_bytes) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     *total_bytes = 0;
     ctx->codec_n = -1;
@@ -1085,7 +1108,7 @@ int vx_encode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint64_t* total
 
 int vx_encode_read(vx_ctx* ctx, uint8_t* files, uint64_t* offsets) {
     if (!ctx) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     if (ctx->codec_n < 0) return fail(ctx, VX_ERR_INVALID, "vx_encode_read without vx_encode_areas");
     VX_CUDA(cudaSetDevice(ctx->device));
     if (ctx->codec_n == 0) {
@@ -1103,7 +1126,7 @@ int vx_encode_read(vx_ctx* ctx, uint8_t* files, uint64_t* offsets) {
 int vx_decode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* files,
                     const uint64_t* offsets, uint8_t* ok, uint8_t* max_height_out) {
     if (!ctx || n < 0 || (n > 0 && (!area_xy || !offsets || !ok))) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     if (n == 0) return VX_OK;
     for (int i = 0; i < n; ++i)
@@ -1156,7 +1179,7 @@ int vx_decode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* 
 
 int vx_visible(vx_ctx* ctx, const vx_view* view, vx_visible_info* info) {
     if (!ctx || !view || !info) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     if (ctx->mesh_n < 0) return fail(ctx, VX_ERR_NO_MESH, "vx_visible without vx_mesh");
     VX_CUDA(cudaSetDevice(ctx->device));
     *info = vx_visible_info{};
@@ -1215,7 +1238,7 @@ int vx_visible(vx_ctx* ctx, const vx_view* view, vx_visible_info* info) {
 
 int vx_visible_read(vx_ctx* ctx, uint32_t* rec_index, uint8_t* area_visible) {
     if (!ctx) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     if (!ctx->frame_ready) return fail(ctx, VX_ERR_NO_MESH, "vx_visible_read without vx_visible");
     VX_CUDA(cudaSetDevice(ctx->device));
     if (ctx->frame_areas == 0) return VX_OK;
@@ -1229,7 +1252,7 @@ int vx_visible_read(vx_ctx* ctx, uint32_t* rec_index, uint8_t* area_visible) {
 
 int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_area_xy, int* n_dirty) {
     if (!ctx || n < 0 || (n > 0 && (!edits || !dirty_area_xy)) || !n_dirty) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     *n_dirty = 0;
     if (n == 0) return VX_OK;
@@ -1290,7 +1313,7 @@ int vx_explode(vx_ctx* ctx, const float* positions, int n, uint32_t* removed_xyz
     if (!ctx || n < 0 || n > 32 || !n_removed || !n_bombs || !n_dirty ||
         (n > 0 && (!positions || !removed_xyz || !bomb_xyz || !dirty_area_xy)))
         return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     *n_removed = *n_bombs = *n_dirty = 0;
     if (n == 0) return VX_OK;
@@ -1365,7 +1388,7 @@ int vx_explode(vx_ctx* ctx, const float* positions, int n, uint32_t* removed_xyz
 int vx_heightmap(vx_ctx* ctx, const uint32_t* area_xy, int n, uint32_t cam_area_x,
                  uint32_t cam_area_y, uint8_t* rgba) {
     if (!ctx || n < 0 || (n > 0 && !area_xy) || !rgba) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     const size_t img_bytes = (size_t)VX_HEIGHTMAP_SIZE * VX_HEIGHTMAP_SIZE * 4;
     int st;
@@ -1393,7 +1416,7 @@ int vx_heightmap(vx_ctx* ctx, const uint32_t* area_xy, int n, uint32_t cam_area_
 
 int vx_light(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* light_out, int* iterations) {
     if (!ctx || n < 0 || (n > 0 && (!area_xy || !light_out))) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     if (iterations) *iterations = 0;
     if (n == 0) return VX_OK;
@@ -1443,7 +1466,7 @@ int vx_light(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* light_out, in
 
 int vx_set_mesh_retention(vx_ctx* ctx, int enabled) {
     if (!ctx) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     const bool on = enabled != 0;
     if (on == ctx->retention) return VX_OK;
@@ -1472,7 +1495,7 @@ int vx_set_mesh_retention(vx_ctx* ctx, int enabled) {
 
 int vx_mesh_unload(vx_ctx* ctx, const uint32_t* area_xy, int n) {
     if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     if (!ctx->retention || n == 0) return VX_OK;  // nothing is kept on the device
     VX_CUDA(cudaSetDevice(ctx->device));
     std::vector<int> slots;
@@ -1485,7 +1508,7 @@ int vx_mesh_unload(vx_ctx* ctx, const uint32_t* area_xy, int n) {
 
 int vx_read_face_masks(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* masks_out, uint8_t* meshed_out) {
     if (!ctx || n < 0 || (n > 0 && !area_xy)) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     if (!ctx->retention) return fail(ctx, VX_ERR_NO_MESH, "vx_read_face_masks: mesh retention is off");
     VX_CUDA(cudaSetDevice(ctx->device));
     std::vector<int> slots(n);
@@ -1501,7 +1524,7 @@ int vx_read_face_masks(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* mas
 
 int vx_update_locations(vx_ctx* ctx, const uint32_t* xyz, int n, vx_mesh_info* info) {
     if (!ctx || n < 0 || (n > 0 && !xyz)) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     ctx->upd_n = -1;
     ctx->upd_info = vx_mesh_info{};
@@ -1627,7 +1650,7 @@ int vx_update_locations(vx_ctx* ctx, const uint32_t* xyz, int n, vx_mesh_info* i
 
 int vx_update_read(vx_ctx* ctx, vx_voxel_rec* recs, void* vertices, uint16_t* indices) {
     if (!ctx) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     if (ctx->upd_n < 0) return fail(ctx, VX_ERR_NO_MESH, "vx_update_read without vx_update_locations");
     VX_CUDA(cudaSetDevice(ctx->device));
     const vx_mesh_info& mi = ctx->upd_info;
@@ -1639,7 +1662,7 @@ int vx_update_read(vx_ctx* ctx, vx_voxel_rec* recs, void* vertices, uint16_t* in
 
 int vx_mesh_read_compact(vx_ctx* ctx, uint32_t* rec_first, uint32_t* packed_recs) {
     if (!ctx) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     if (ctx->mesh_n < 0) return fail(ctx, VX_ERR_NO_MESH, "vx_mesh_read_compact without vx_mesh");
     VX_CUDA(cudaSetDevice(ctx->device));
     const int n = ctx->mesh_n;
@@ -1662,7 +1685,7 @@ int vx_mesh_read_compact(vx_ctx* ctx, uint32_t* rec_first, uint32_t* packed_recs
 
 int vx_visible_zone(vx_ctx* ctx, const uint32_t* area_xy, int n, const vx_view* view, vx_visible_info* info) {
     if (!ctx || !view || !info || n < 0 || (n > 0 && !area_xy) || n > (1 << 17)) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     if (!ctx->retention) return fail(ctx, VX_ERR_NO_MESH, "vx_visible_zone: mesh retention is off");
     VX_CUDA(cudaSetDevice(ctx->device));
     *info = vx_visible_info{};
@@ -1740,7 +1763,7 @@ int vx_visible_zone(vx_ctx* ctx, const uint32_t* area_xy, int n, const vx_view* 
 
 int vx_diag_fp64_rate(vx_ctx* ctx, double* gops_per_s, float* ms_out) {
     if (!ctx || !gops_per_s) return VX_ERR_INVALID;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
     VX_CUDA(ctx->d_tmp.ensure(64));
     const int blocks = ctx->sm_count * 8, iters = 1 << 15;

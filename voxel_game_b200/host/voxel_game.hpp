@@ -85,8 +85,23 @@ public:
     Pipeline& operator=(const Pipeline&) = delete;
     vx_ctx* raw() const { return ctx_; }
     void check(int st) const {
-        if (st != VX_OK) throw VxError(st, vx_last_error(ctx_));
+        if (st == VX_OK) return;
+        char msg[1024] = "";
+        vx_copy_last_error(ctx_, msg, sizeof msg);  // copied out under the context's lock
+        throw VxError(st, msg);
     }
+    // vx_lock ... vx_unlock around a call and the read of its result (vx_mesh -> vx_mesh_read, ...):
+    // the Pipeline may be shared by worker threads, the pair must see its own result
+    class Transaction {
+    public:
+        explicit Transaction(const Pipeline& p) : ctx_(p.raw()) { vx_lock(ctx_); }
+        ~Transaction() { vx_unlock(ctx_); }
+        Transaction(const Transaction&) = delete;
+        Transaction& operator=(const Transaction&) = delete;
+
+    private:
+        vx_ctx* ctx_;
+    };
 
 private:
     vx_ctx* ctx_ = nullptr;
@@ -440,9 +455,13 @@ public:
         for (const auto& kv : meshes_) zone.push_back(kv.first);
         const auto xy = flatten(zone);
         vx_visible_info info{};
-        p.check(vx_visible_zone(p.raw(), xy.data(), static_cast<int>(zone.size()), &v, &info));
-        std::vector<uint32_t> codes(info.n_visible);
-        p.check(vx_visible_read(p.raw(), codes.data(), nullptr));
+        std::vector<uint32_t> codes;
+        {
+            Pipeline::Transaction pair(p);
+            p.check(vx_visible_zone(p.raw(), xy.data(), static_cast<int>(zone.size()), &v, &info));
+            codes.resize(info.n_visible);
+            p.check(vx_visible_read(p.raw(), codes.data(), nullptr));
+        }
         auto key_of = [&](uint32_t code) {
             const AreaLocation a = zone[code >> 15];
             const uint32_t local = code & 0x7FFFu;
@@ -479,11 +498,17 @@ public:
             xyz.push_back(l.z);
         }
         vx_mesh_info info{};
-        p.check(vx_update_locations(p.raw(), xyz.data(), static_cast<int>(locations.size()), &info));
-        std::vector<vx_voxel_rec> recs(info.n_recs);
-        std::vector<Vertex> vertices(info.n_faces * 4);
-        std::vector<uint16_t> indices(info.n_faces * 6);
-        p.check(vx_update_read(p.raw(), recs.data(), vertices.data(), indices.data()));
+        std::vector<vx_voxel_rec> recs;
+        std::vector<Vertex> vertices;
+        std::vector<uint16_t> indices;
+        {
+            Pipeline::Transaction pair(p);
+            p.check(vx_update_locations(p.raw(), xyz.data(), static_cast<int>(locations.size()), &info));
+            recs.resize(info.n_recs);
+            vertices.resize(info.n_faces * 4);
+            indices.resize(info.n_faces * 6);
+            p.check(vx_update_read(p.raw(), recs.data(), vertices.data(), indices.data()));
+        }
         for (const vx_voxel_rec& rec : recs) {  // set_voxel_mesh (renderer.rs:197-219)
             const uint32_t gz = rec.packed & 0xFF, nf = rec.packed >> 24;
             const LocKey key{rec.gx, rec.gy, gz};
@@ -531,12 +556,14 @@ private:
         const auto xy = flatten(areas);
         const int n = static_cast<int>(areas.size());
         vx_mesh_info info{};
+        std::unique_ptr<Pipeline::Transaction> pair(new Pipeline::Transaction(p));  // vx_mesh + its read
         p.check(vx_mesh(p.raw(), xy.data(), n, &info));
         std::vector<uint32_t> rec_first(static_cast<size_t>(n) + 1);
         std::vector<RenderArea> built(static_cast<size_t>(n));
         if (transport == Transport::Compact) {
             std::vector<uint32_t> packed(info.n_recs);
             p.check(vx_mesh_read_compact(p.raw(), rec_first.data(), packed.data()));
+            pair.reset();
             parallel_ranges(static_cast<size_t>(n), threads, [&](size_t a0, size_t a1) {
                 for (size_t a = a0; a < a1; ++a) {
                     RenderArea& ra = built[a];
@@ -560,6 +587,7 @@ private:
             std::vector<Vertex> vertices(info.n_faces * 4);
             std::vector<uint16_t> indices(info.n_faces * 6);
             p.check(vx_mesh_read(p.raw(), rec_first.data(), face_first.data(), recs.data(), vertices.data(), indices.data()));
+            pair.reset();
             parallel_ranges(static_cast<size_t>(n), threads, [&](size_t a0, size_t a1) {
                 for (size_t a = a0; a < a1; ++a) {
                     RenderArea& ra = built[a];
