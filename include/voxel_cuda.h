@@ -139,6 +139,16 @@ void vx_host_free(void* p);
  * (generator.rs:24-28), computed by the Rust side.  Tables are built once per seed instead of
  * once per area. */
 int vx_set_seed(vx_ctx* ctx, uint64_t seed);
+/* libnoise calibration.  The f64 noise arithmetic follows libnoise 1.1.2 as far as it is known
+ * without the crate's source; the choices nothing pins are switches.  Those that
+ * change code are compile-time (csrc/vx_tables.hpp VX_NOISE_VARIANT; vx_noise_variant() returns the
+ * mask this library was built with, 0 by default), the order of the two gradient tables is data:
+ * order2 / order3 are permutations of 0..23 / 0..11 (entry i of the crate's table = entry order[i]
+ * of the canonical tables in csrc/vx_tables.cpp), NULL = canonical.  Takes effect for everything
+ * generated afterwards (the tables of the current seed are rebuilt).  tests/test_reference_dump.py
+ * reports the setting that reproduces a dump of the real crate (rust/parity_dump/). */
+int vx_noise_variant(void);
+int vx_set_gradient_order(vx_ctx* ctx, const uint8_t* order2, const uint8_t* order3);
 /* The same hash, for hosts that are not Rust: SipHash-1-3(k0=k1=0) over name bytes || 0xFF. */
 uint64_t vx_hash_world_name(const char* world_name);
 

@@ -123,6 +123,9 @@ def lib():
         L.vgo_fbm2.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.vgo_fbm3.restype = C.c_double
         L.vgo_fbm3.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.vgo_set_noise_variant.argtypes = [C.c_uint, u8p, u8p]
+        L.vgo_get_noise_variant.restype = C.c_uint
+        L.vgo_op_counts.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
         L.vgo_generator_new.restype = C.c_void_p
         L.vgo_generator_new.argtypes = [C.c_uint64]
         L.vgo_generator_free.argtypes = [C.c_void_p]
@@ -194,6 +197,43 @@ def _p(a, t=C.c_uint8):
 
 def hash_world_name(name: str) -> int:
     return int(lib().vgo_hash_world_name(name.encode("utf-8")))
+
+
+VAR_FBM_RUNNING_FREQ, VAR_TIE2_OTHER, VAR_TIE3_OTHER, VAR_SKEW_EXACT = 1, 2, 4, 8
+
+
+def set_noise_variant(flags: int = 0, order2=None, order3=None):
+    """Flip the unanchored libnoise choices (vg_oracle.h VGO_VAR_*; gradient-table permutations).
+    Global to the library: callers reset it with set_noise_variant() when they are done."""
+    o2 = None if order2 is None else np.ascontiguousarray(order2, np.uint8)
+    o3 = None if order3 is None else np.ascontiguousarray(order3, np.uint8)
+    assert (o2 is None or o2.size == 24) and (o3 is None or o3.size == 12)
+    lib().vgo_set_noise_variant(int(flags), None if o2 is None else _p(o2), None if o3 is None else _p(o3))
+
+
+def noise_variant() -> int:
+    return int(lib().vgo_get_noise_variant())
+
+
+def use_counting_build() -> bool:
+    """Switch this module to a -DVGO_COUNT_OPS build of the oracle (the "counting scalar" of
+    SURVEY.md 8d: every f64 add / multiply of the noise arithmetic goes through a counter)."""
+    global _LIB_PATH, _lib
+    counting = os.path.join(_HERE, "build", "liboracle_count.so")
+    r = subprocess.run(["make", "-C", _HERE, "-B", "EXTRA=-DVGO_COUNT_OPS", "OUT=build/liboracle_count.so"],
+                       capture_output=True)
+    if r.returncode != 0 or not os.path.exists(counting):
+        return False
+    _LIB_PATH = counting
+    _lib = None
+    return True
+
+
+def op_counts(reset: bool = True):
+    """(f64 adds, f64 multiplies) of the noise arithmetic on this thread since the last reset."""
+    a, m = C.c_uint64(0), C.c_uint64(0)
+    lib().vgo_op_counts(C.byref(a), C.byref(m), int(reset))
+    return int(a.value), int(m.value)
 
 
 def max_threads() -> int:

@@ -26,11 +26,69 @@
  *                traversal, literal digits of the skew constants, exact expression grouping.
  * Everything downstream (block IDs) is therefore "bit-exact vs this restatement", not vs a
  * Rust build.  The file is deliberately self-contained so it can be diffed against the crate.
+ *
+ * The unanchored choices are SWITCHES (vgo_set_noise_variant, flags VGO_VAR_* in vg_oracle.h; the
+ * CUDA side has the same switches as the compile-time mask VX_NOISE_VARIANT and
+ * vx_set_gradient_order): Fbm coordinate form, tie-breaks of the 2-D / 3-D simplex traversal,
+ * digits of the 2-D skew constants, order of the gradient tables.  tests/test_reference_dump.py
+ * loads a dump written by the reference itself (rust/parity_dump/) when one is present and reports
+ * which setting reproduces it.
+ *
+ * Built with -DVGO_COUNT_OPS the f64 additions and multiplications of the simplex / Fbm arithmetic
+ * go through counting wrappers (the "counting scalar" of SURVEY.md 8d): vgo_op_counts() then returns
+ * the f64 add and multiply counts of the crate form, which tests/test_op_counts.py pins next to the
+ * counts the kernels issue (bench.py F2_OPS / F3_OPS).
  */
 #include <math.h>
 #include <string.h>
 
 #include "vg_oracle.h"
+
+/* ------------------------------------------------------------------ counting scalar (-DVGO_COUNT_OPS) */
+#ifdef VGO_COUNT_OPS
+static _Thread_local uint64_t t_adds, t_muls;
+static inline double op_add(double a, double b) { ++t_adds; return a + b; }
+static inline double op_sub(double a, double b) { ++t_adds; return a - b; }
+static inline double op_mul(double a, double b) { ++t_muls; return a * b; }
+void vgo_op_counts(uint64_t* adds, uint64_t* muls, int reset) {
+    *adds = t_adds;
+    *muls = t_muls;
+    if (reset) t_adds = t_muls = 0;
+}
+#else
+#define op_add(a, b) ((a) + (b))
+#define op_sub(a, b) ((a) - (b))
+#define op_mul(a, b) ((a) * (b))
+void vgo_op_counts(uint64_t* adds, uint64_t* muls, int reset) {
+    (void)reset;
+    *adds = *muls = 0; /* not a counting build */
+}
+#endif
+
+/* ------------------------------------------------------------------ variant switches */
+static unsigned g_variant = 0;
+static int g_any = 0; /* any switch set */
+static int g_order_set = 0;
+static uint8_t g_order2[24], g_order3[12];
+static double g_skew2 = 0.366025403784439, g_unskew2 = 0.211324865405187; /* the crate's literals as recalled */
+
+/* flags: VGO_VAR_*; order2 / order3: gradient-table permutations (entry i of the crate's table =
+ * entry order[i] of the tables below), NULL = as listed.  Not thread-safe: set before sampling. */
+void vgo_set_noise_variant(unsigned flags, const uint8_t* order2, const uint8_t* order3) {
+    g_variant = flags;
+    g_any = flags != 0 || order2 != NULL || order3 != NULL;
+    g_order_set = (order2 != NULL) || (order3 != NULL);
+    for (int i = 0; i < 24; i++) g_order2[i] = order2 ? order2[i] : (uint8_t)i;
+    for (int i = 0; i < 12; i++) g_order3[i] = order3 ? order3[i] : (uint8_t)i;
+    if (flags & VGO_VAR_SKEW_EXACT) { /* f64 nearest to (sqrt(3) - 1) / 2 and (3 - sqrt(3)) / 6 */
+        g_skew2 = 0x1.76cf5d0b09955p-2;
+        g_unskew2 = 0x1.b0cb174df99c7p-3;
+    } else {
+        g_skew2 = 0.366025403784439;
+        g_unskew2 = 0.211324865405187;
+    }
+}
+unsigned vgo_get_noise_variant(void) { return g_variant; }
 
 /* ------------------------------------------------------------------ SipHash-c-d */
 static inline uint64_t rotl64(uint64_t v, int r) { return (v << r) | (v >> (64 - r)); }
@@ -204,8 +262,11 @@ void vgo_simplex_new(vgo_simplex* s, uint64_t seed) {
 }
 
 /* ------------------------------------------------------------------ simplex noise */
-static const double SKEW_2D = 0.366025403784439;   /* (sqrt(3)-1)/2 */
-static const double UNSKEW_2D = 0.211324865405187; /* (3-sqrt(3))/6 */
+/* V = 1: the switches are consulted; V = 0 (nothing is switched, the usual case and the one the CPU
+ * baseline is timed with): compile-time constants, no table indirection -- the body is compiled twice */
+#define SKEW_2D (V ? g_skew2 : 0.366025403784439)     /* (sqrt(3)-1)/2 */
+#define UNSKEW_2D (V ? g_unskew2 : 0.211324865405187) /* (3-sqrt(3))/6 */
+#define ALWAYS_INLINE static inline __attribute__((always_inline))
 static const double SKEW_3D = 1.0 / 3.0;
 static const double UNSKEW_3D = 1.0 / 6.0;
 static const double R_SQUARED = 0.5;
@@ -234,91 +295,101 @@ static const double GRAD3[GRAD3_N][3] = {
     {1, 1, 0}, {-1, 1, 0}, {1, -1, 0}, {-1, -1, 0}, {1, 0, 1},  {-1, 0, 1},
     {1, 0, -1}, {-1, 0, -1}, {0, 1, 1}, {0, -1, 1}, {0, 1, -1}, {0, -1, -1}};
 
-static inline double contribution2(double x, double y, unsigned gi) {
-    double t = R_SQUARED - x * x - y * y;
+ALWAYS_INLINE double contribution2(double x, double y, unsigned gi, const int V) {
+    double t = op_sub(op_sub(R_SQUARED, op_mul(x, x)), op_mul(y, y));
     if (t <= 0.0) return 0.0;
-    const double* g = GRAD2[gi];
-    t *= t;
-    return t * t * (g[0] * x + g[1] * y);
+    const double* g = GRAD2[(V && g_order_set) ? g_order2[gi] : gi];
+    t = op_mul(t, t);
+    return op_mul(op_mul(t, t), op_add(op_mul(g[0], x), op_mul(g[1], y)));
 }
 
-static inline double contribution3(double x, double y, double z, unsigned gi) {
-    double t = R_SQUARED - x * x - y * y - z * z;
+ALWAYS_INLINE double contribution3(double x, double y, double z, unsigned gi, const int V) {
+    double t = op_sub(op_sub(op_sub(R_SQUARED, op_mul(x, x)), op_mul(y, y)), op_mul(z, z));
     if (t <= 0.0) return 0.0;
-    const double* g = GRAD3[gi];
-    t *= t;
-    return t * t * (g[0] * x + g[1] * y + g[2] * z);
+    const double* g = GRAD3[(V && g_order_set) ? g_order3[gi] : gi];
+    t = op_mul(t, t);
+    return op_mul(op_mul(t, t), op_add(op_add(op_mul(g[0], x), op_mul(g[1], y)), op_mul(g[2], z)));
 }
 
-double vgo_simplex2(const vgo_simplex* s, double x, double y) {
+ALWAYS_INLINE double simplex2_impl(const vgo_simplex* s, double x, double y, const int V) {
     const uint8_t* p = s->perm;
     /* transform into lattice space and floor for the cell origin */
-    double skew = (x + y) * SKEW_2D;
-    double ix = floor(x + skew), iy = floor(y + skew);
+    double skew = op_mul(op_add(x, y), SKEW_2D);
+    double ix = floor(op_add(x, skew)), iy = floor(op_add(y, skew));
     /* input point relative to the unskewed cell origin */
-    double unskew = (ix + iy) * UNSKEW_2D;
-    double x0 = x - ix + unskew, y0 = y - iy + unskew;
+    double unskew = op_mul(op_add(ix, iy), UNSKEW_2D);
+    double x0 = op_add(op_sub(x, ix), unskew), y0 = op_add(op_sub(y, iy), unskew);
     /* middle corner */
     int i1 = 1, j1 = 0;
-    if (x0 < y0) {
+    if ((V && (g_variant & VGO_VAR_TIE2_OTHER)) ? (x0 <= y0) : (x0 < y0)) {
         i1 = 0;
         j1 = 1;
     }
-    double x1 = x0 - (double)i1 + UNSKEW_2D, y1 = y0 - (double)j1 + UNSKEW_2D;
-    double x2 = x0 - 1.0 + 2.0 * UNSKEW_2D, y2 = y0 - 1.0 + 2.0 * UNSKEW_2D;
+    double x1 = op_add(op_sub(x0, (double)i1), UNSKEW_2D), y1 = op_add(op_sub(y0, (double)j1), UNSKEW_2D);
+    double x2 = op_add(op_sub(x0, 1.0), (2.0 * UNSKEW_2D)), y2 = op_add(op_sub(y0, 1.0), (2.0 * UNSKEW_2D));
     /* hashed gradient indices (rem_euclid 256; doubled table makes +1 safe) */
     unsigned i = (unsigned)((long long)ix & 255), j = (unsigned)((long long)iy & 255);
     unsigned gi0 = p[j + p[i]] % GRAD2_N;
     unsigned gi1 = p[j + j1 + p[i + i1]] % GRAD2_N;
     unsigned gi2 = p[j + 1 + p[i + 1]] % GRAD2_N;
-    double n0 = contribution2(x0, y0, gi0);
-    double n1 = contribution2(x1, y1, gi1);
-    double n2 = contribution2(x2, y2, gi2);
-    return (n0 + n1 + n2) * NORM_2D;
+    double n0 = contribution2(x0, y0, gi0, V);
+    double n1 = contribution2(x1, y1, gi1, V);
+    double n2 = contribution2(x2, y2, gi2, V);
+    return op_mul(op_add(op_add(n0, n1), n2), NORM_2D);
 }
 
-double vgo_simplex3(const vgo_simplex* s, double x, double y, double z) {
+ALWAYS_INLINE double simplex3_impl(const vgo_simplex* s, double x, double y, double z, const int V) {
     const uint8_t* p = s->perm;
-    double skew = (x + y + z) * SKEW_3D;
-    double ix = floor(x + skew), iy = floor(y + skew), iz = floor(z + skew);
-    double unskew = (ix + iy + iz) * UNSKEW_3D;
-    double x0 = x - ix + unskew, y0 = y - iy + unskew, z0 = z - iz + unskew;
-    /* simplex traversal: second and third corner offsets */
+    double skew = op_mul(op_add(op_add(x, y), z), SKEW_3D);
+    double ix = floor(op_add(x, skew)), iy = floor(op_add(y, skew)), iz = floor(op_add(z, skew));
+    double unskew = op_mul(op_add(op_add(ix, iy), iz), UNSKEW_3D);
+    double x0 = op_add(op_sub(x, ix), unskew), y0 = op_add(op_sub(y, iy), unskew), z0 = op_add(op_sub(z, iz), unskew);
+    /* simplex traversal: second and third corner offsets; ties count as "greater or equal" in the
+     * order x, y, z (VGO_VAR_TIE3_OTHER: as "less") */
+    const int strict = V && (g_variant & VGO_VAR_TIE3_OTHER) != 0;
+    const int xy = strict ? x0 > y0 : x0 >= y0, yz = strict ? y0 > z0 : y0 >= z0, xz = strict ? x0 > z0 : x0 >= z0;
     int i1, j1, k1, i2, j2, k2;
-    if (x0 >= y0) {
-        if (y0 >= z0) {
+    if (xy) {
+        if (yz) {
             i1 = 1; j1 = 0; k1 = 0; i2 = 1; j2 = 1; k2 = 0;
-        } else if (x0 >= z0) {
+        } else if (xz) {
             i1 = 1; j1 = 0; k1 = 0; i2 = 1; j2 = 0; k2 = 1;
         } else {
             i1 = 0; j1 = 0; k1 = 1; i2 = 1; j2 = 0; k2 = 1;
         }
     } else {
-        if (y0 < z0) {
+        if (!yz) {
             i1 = 0; j1 = 0; k1 = 1; i2 = 0; j2 = 1; k2 = 1;
-        } else if (x0 < z0) {
+        } else if (!xz) {
             i1 = 0; j1 = 1; k1 = 0; i2 = 0; j2 = 1; k2 = 1;
         } else {
             i1 = 0; j1 = 1; k1 = 0; i2 = 1; j2 = 1; k2 = 0;
         }
     }
-    double x1 = x0 - (double)i1 + UNSKEW_3D, y1 = y0 - (double)j1 + UNSKEW_3D,
-           z1 = z0 - (double)k1 + UNSKEW_3D;
-    double x2 = x0 - (double)i2 + 2.0 * UNSKEW_3D, y2 = y0 - (double)j2 + 2.0 * UNSKEW_3D,
-           z2 = z0 - (double)k2 + 2.0 * UNSKEW_3D;
-    double x3 = x0 - 1.0 + 3.0 * UNSKEW_3D, y3 = y0 - 1.0 + 3.0 * UNSKEW_3D,
-           z3 = z0 - 1.0 + 3.0 * UNSKEW_3D;
+    double x1 = op_add(op_sub(x0, (double)i1), UNSKEW_3D), y1 = op_add(op_sub(y0, (double)j1), UNSKEW_3D),
+           z1 = op_add(op_sub(z0, (double)k1), UNSKEW_3D);
+    double x2 = op_add(op_sub(x0, (double)i2), (2.0 * UNSKEW_3D)), y2 = op_add(op_sub(y0, (double)j2), (2.0 * UNSKEW_3D)),
+           z2 = op_add(op_sub(z0, (double)k2), (2.0 * UNSKEW_3D));
+    double x3 = op_add(op_sub(x0, 1.0), (3.0 * UNSKEW_3D)), y3 = op_add(op_sub(y0, 1.0), (3.0 * UNSKEW_3D)),
+           z3 = op_add(op_sub(z0, 1.0), (3.0 * UNSKEW_3D));
     unsigned i = (unsigned)((long long)ix & 255), j = (unsigned)((long long)iy & 255),
              k = (unsigned)((long long)iz & 255);
     unsigned gi0 = p[k + p[j + p[i]]] % GRAD3_N;
     unsigned gi1 = p[k + k1 + p[j + j1 + p[i + i1]]] % GRAD3_N;
     unsigned gi2 = p[k + k2 + p[j + j2 + p[i + i2]]] % GRAD3_N;
     unsigned gi3 = p[k + 1 + p[j + 1 + p[i + 1]]] % GRAD3_N;
-    double n0 = contribution3(x0, y0, z0, gi0);
-    double n1 = contribution3(x1, y1, z1, gi1);
-    double n2 = contribution3(x2, y2, z2, gi2);
-    double n3 = contribution3(x3, y3, z3, gi3);
-    return (n0 + n1 + n2 + n3) * NORM_3D;
+    double n0 = contribution3(x0, y0, z0, gi0, V);
+    double n1 = contribution3(x1, y1, z1, gi1, V);
+    double n2 = contribution3(x2, y2, z2, gi2, V);
+    double n3 = contribution3(x3, y3, z3, gi3, V);
+    return op_mul(op_add(op_add(op_add(n0, n1), n2), n3), NORM_3D);
+}
+
+double vgo_simplex2(const vgo_simplex* s, double x, double y) {
+    return g_any ? simplex2_impl(s, x, y, 1) : simplex2_impl(s, x, y, 0);
+}
+double vgo_simplex3(const vgo_simplex* s, double x, double y, double z) {
+    return g_any ? simplex3_impl(s, x, y, z, 1) : simplex3_impl(s, x, y, z, 0);
 }
 
 /* ------------------------------------------------------------------ Fbm */
@@ -347,32 +418,72 @@ void vgo_fbm_new(vgo_fbm* f, const vgo_simplex* src, int octaves, double frequen
     f->normalization_factor = 1.0 / acc;
 }
 
+/* Fbm::sample.  Default: the point is scaled by the frequency once and by the lacunarity after
+ * every octave.  VGO_VAR_FBM_RUNNING_FREQ: every octave samples point * freq with a running
+ * freq *= lacunarity (the two differ in the last bits: (p * f) * l vs p * (f * l)). */
 double vgo_fbm2(const vgo_fbm* f, double x, double y) {
     double noise = 0.0, amp = 1.0;
-    x *= f->frequency;
-    y *= f->frequency;
-    for (int o = 0; o < f->octaves; o++) {
-        noise += amp * vgo_simplex2(f->src, x, y);
-        x *= f->lacunarity;
-        y *= f->lacunarity;
-        amp *= f->persistence;
+    if (g_variant & VGO_VAR_FBM_RUNNING_FREQ) {
+        double freq = f->frequency;
+        for (int o = 0; o < f->octaves; o++) {
+            noise = op_add(noise, op_mul(amp, vgo_simplex2(f->src, op_mul(x, freq), op_mul(y, freq))));
+            freq = op_mul(freq, f->lacunarity);
+            amp = op_mul(amp, f->persistence);
+        }
+        return op_mul(noise, f->normalization_factor);
     }
-    return noise * f->normalization_factor;
+    x = op_mul(x, f->frequency);
+    y = op_mul(y, f->frequency);
+    if (!g_any) {
+        for (int o = 0; o < f->octaves; o++) {
+            noise = op_add(noise, op_mul(amp, simplex2_impl(f->src, x, y, 0)));
+            x = op_mul(x, f->lacunarity);
+            y = op_mul(y, f->lacunarity);
+            amp = op_mul(amp, f->persistence);
+        }
+        return op_mul(noise, f->normalization_factor);
+    }
+    for (int o = 0; o < f->octaves; o++) {
+        noise = op_add(noise, op_mul(amp, vgo_simplex2(f->src, x, y)));
+        x = op_mul(x, f->lacunarity);
+        y = op_mul(y, f->lacunarity);
+        amp = op_mul(amp, f->persistence);
+    }
+    return op_mul(noise, f->normalization_factor);
 }
 
 double vgo_fbm3(const vgo_fbm* f, double x, double y, double z) {
     double noise = 0.0, amp = 1.0;
-    x *= f->frequency;
-    y *= f->frequency;
-    z *= f->frequency;
-    for (int o = 0; o < f->octaves; o++) {
-        noise += amp * vgo_simplex3(f->src, x, y, z);
-        x *= f->lacunarity;
-        y *= f->lacunarity;
-        z *= f->lacunarity;
-        amp *= f->persistence;
+    if (g_variant & VGO_VAR_FBM_RUNNING_FREQ) {
+        double freq = f->frequency;
+        for (int o = 0; o < f->octaves; o++) {
+            noise = op_add(noise, op_mul(amp, vgo_simplex3(f->src, op_mul(x, freq), op_mul(y, freq), op_mul(z, freq))));
+            freq = op_mul(freq, f->lacunarity);
+            amp = op_mul(amp, f->persistence);
+        }
+        return op_mul(noise, f->normalization_factor);
     }
-    return noise * f->normalization_factor;
+    x = op_mul(x, f->frequency);
+    y = op_mul(y, f->frequency);
+    z = op_mul(z, f->frequency);
+    if (!g_any) {
+        for (int o = 0; o < f->octaves; o++) {
+            noise = op_add(noise, op_mul(amp, simplex3_impl(f->src, x, y, z, 0)));
+            x = op_mul(x, f->lacunarity);
+            y = op_mul(y, f->lacunarity);
+            z = op_mul(z, f->lacunarity);
+            amp = op_mul(amp, f->persistence);
+        }
+        return op_mul(noise, f->normalization_factor);
+    }
+    for (int o = 0; o < f->octaves; o++) {
+        noise = op_add(noise, op_mul(amp, vgo_simplex3(f->src, x, y, z)));
+        x = op_mul(x, f->lacunarity);
+        y = op_mul(y, f->lacunarity);
+        z = op_mul(z, f->lacunarity);
+        amp = op_mul(amp, f->persistence);
+    }
+    return op_mul(noise, f->normalization_factor);
 }
 
 /* gradient tables, exposed so that tests can pin them against the crate's normalisation constants */

@@ -75,6 +75,18 @@ void vgo_fbm_new(vgo_fbm* f, const vgo_simplex* src, int octaves, double frequen
                  double lacunarity, double persistence);
 double vgo_fbm2(const vgo_fbm* f, double x, double y);
 double vgo_fbm3(const vgo_fbm* f, double x, double y, double z);
+
+/* Switches for the choices of libnoise 1.1.2 that nothing on this machine pins (noise_libnoise.c
+ * header).  0 = the recalled crate behaviour every committed fixture was made with. */
+#define VGO_VAR_FBM_RUNNING_FREQ 1u /* Fbm samples point * freq, freq *= lacunarity (default: point *= lacunarity) */
+#define VGO_VAR_TIE2_OTHER 2u       /* 2-D middle corner: x0 == y0 goes to (0,1) (default: (1,0)) */
+#define VGO_VAR_TIE3_OTHER 4u       /* 3-D traversal: strict > (default: >=) */
+#define VGO_VAR_SKEW_EXACT 8u       /* 2-D skew constants: f64 nearest to the exact values (default: 15-digit literals) */
+void vgo_set_noise_variant(unsigned flags, const uint8_t* order2, const uint8_t* order3);
+unsigned vgo_get_noise_variant(void);
+/* f64 additions / multiplications executed by the noise arithmetic on the calling thread since
+ * the last reset; zero unless the library was built with -DVGO_COUNT_OPS. */
+void vgo_op_counts(uint64_t* adds, uint64_t* muls, int reset);
 /* raw pieces exposed for tests */
 void vgo_chacha12_words(uint64_t seed_u64, uint32_t* out, int n_words);
 uint64_t vgo_siphash(int c_rounds, int d_rounds, uint64_t k0, uint64_t k1, const uint8_t* data,

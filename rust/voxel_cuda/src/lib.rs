@@ -92,6 +92,8 @@ extern "C" {
     pub fn vx_host_free(p: *mut c_void);
     pub fn vx_set_seed(ctx: *mut vx_ctx, seed: u64) -> c_int;
     pub fn vx_hash_world_name(world_name: *const c_char) -> u64;
+    pub fn vx_noise_variant() -> c_int;
+    pub fn vx_set_gradient_order(ctx: *mut vx_ctx, order2: *const u8, order3: *const u8) -> c_int;
     pub fn vx_generate(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, voxels_out: *mut u8,
                        max_height_out: *mut u8) -> c_int;
     pub fn vx_upload(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, voxels: *const u8,
@@ -380,6 +382,18 @@ impl Pipeline {
         let mut packed = vec![0u32; info.n_recs as usize];
         self.check(unsafe { vx_mesh_read_compact(self.ctx, rec_first.as_mut_ptr(), packed.as_mut_ptr()) })?;
         Ok((rec_first, packed))
+    }
+
+    /// libnoise calibration (include/voxel_cuda.h): the mask of code switches this library was built
+    /// with, and the order of the crate's two gradient tables as data.
+    pub fn noise_variant() -> i32 {
+        unsafe { vx_noise_variant() }
+    }
+    pub fn set_gradient_order(&self, order2: Option<&[u8; 24]>, order3: Option<&[u8; 12]>) -> Result<(), VxError> {
+        self.check(unsafe {
+            vx_set_gradient_order(self.ctx, order2.map_or(std::ptr::null(), |o| o.as_ptr()),
+                                  order3.map_or(std::ptr::null(), |o| o.as_ptr()))
+        })
     }
 
     /// Device mirror of `Renderer.meshes` on / off (graphics/renderer.rs:97-101).

@@ -1,0 +1,100 @@
+"""Parity-pin kit, device side: every libnoise-calibration switch keeps CUDA == oracle.  The code
+switches are compile-time (VX_NOISE_VARIANT builds under voxel_game_b200/variants/, loaded in a
+subprocess through VX_LIB_PATH), the gradient-table order is data (vx_set_gradient_order)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+import voxel_game_b200 as vg
+from voxel_game_b200.binding import VARIANT_LIBS
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_SCRIPT = r"""
+import sys
+import numpy as np
+import oracle
+import voxel_game_b200 as vg
+mask = int(sys.argv[1])
+assert vg.load().vx_noise_variant() == mask, (vg.LIB_PATH, vg.load().vx_noise_variant())
+oracle.set_noise_variant(mask)
+seed = oracle.hash_world_name("test")
+bad = 0
+with vg.Context(0, seed=seed) as ctx:
+    for (ax0, ay0, n) in ((62497, 62497, 6), (123, 456, 3), (70000, 1000, 4)):
+        ring = vg.region_xy(ax0 - 1, ay0 - 1, n + 2, n + 2)
+        vox, mh = ctx.generate(ring)
+        ovox, omh, stats, _ = oracle.generate_areas(seed, ring)
+        assert np.array_equal(vox, ovox), f"variant {mask}: block IDs differ from the oracle at {ax0},{ay0}"
+        assert np.array_equal(mh, omh)
+        inner = vg.region_xy(ax0, ay0, n, n)
+        info = ctx.mesh(inner)
+        rf, ff, recs, verts, idx = ctx.mesh_read(info)
+        world = oracle.World(ax0 - 1, ay0 - 1, n + 2, n + 2, ovox, omh)
+        faces = sum(world.mesh_area(int(a), int(b)) for a, b in inner)
+        assert faces == info["n_faces"]
+    # the ties the switch is about: columns whose noise input has x == y (global voxel x == y)
+    diag = vg.region_xy(62500, 62500, 1, 1)
+    v1, _ = ctx.generate(diag)
+    o1, _, _, _ = oracle.generate_areas(seed, diag)
+    assert np.array_equal(v1, o1)
+print("ok", mask)
+"""
+
+
+@pytest.mark.parametrize("mask", sorted(VARIANT_LIBS))
+def test_variant_build_equals_oracle_under_the_same_switch(mask):
+    lib = VARIANT_LIBS[mask]
+    assert os.path.exists(lib), f"{lib} missing: __graft_entry__.build() makes it (make -C csrc variants)"
+    env = dict(os.environ, VX_LIB_PATH=lib, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", _SCRIPT, str(mask)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and f"ok {mask}" in r.stdout, r.stdout + r.stderr
+
+
+def test_variant_builds_differ_from_the_default_where_they_should(seed):
+    """The Fbm-form build is not a no-op: against the DEFAULT oracle it differs somewhere in a region
+    (the last-bit differences move a threshold), so the switch really switches."""
+    lib = VARIANT_LIBS[1]
+    script = r"""
+import numpy as np, oracle, voxel_game_b200 as vg
+seed = oracle.hash_world_name("test")
+xy = vg.region_xy(62484, 62484, 32, 32)
+with vg.Context(0, seed=seed) as ctx:
+    vox, _ = ctx.generate(xy)
+ovox, _, _, _ = oracle.generate_areas(seed, xy)
+print("differing voxels", int((vox != ovox).sum()))
+"""
+    env = dict(os.environ, VX_LIB_PATH=lib, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    n = int(r.stdout.strip().split()[-1])
+    assert 0 < n < 200_000, n  # a few thresholds move; the terrain is the same terrain
+
+
+def test_gradient_order_is_data_on_both_sides(seed):
+    assert vg.load().vx_noise_variant() == 0
+    rng = np.random.default_rng(5)
+    order2, order3 = rng.permutation(24).astype(np.uint8), rng.permutation(12).astype(np.uint8)
+    xy = vg.region_xy(62496, 62496, 8, 8)
+    try:
+        with vg.Context(0, seed=seed) as ctx:
+            base, _ = ctx.generate(xy)
+            ctx.set_gradient_order(order2, order3)
+            vox, mh = ctx.generate(xy)
+            oracle.set_noise_variant(0, order2, order3)
+            ovox, omh, _, _ = oracle.generate_areas(seed, xy)
+            assert np.array_equal(vox, ovox) and np.array_equal(mh, omh)
+            assert (vox != base).any()
+            ctx.set_gradient_order(None, None)
+            oracle.set_noise_variant()
+            again, _ = ctx.generate(xy)
+            assert np.array_equal(again, base)
+            with pytest.raises(vg.VxError):
+                ctx.set_gradient_order(np.zeros(24, np.uint8), None)  # not a permutation
+    finally:
+        oracle.set_noise_variant()

@@ -15,7 +15,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvoxel_cuda.so")
+#: VX_LIB_PATH selects another build of the library (the VX_NOISE_VARIANT builds under variants/)
+LIB_PATH = os.environ.get("VX_LIB_PATH") or os.path.join(_HERE, "libvoxel_cuda.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 VOXELS_IN_AREA = 32768
@@ -45,7 +46,7 @@ ABI_SYMBOLS = [
     "vx_heightmap", "vx_visible", "vx_visible_read", "vx_encode_areas", "vx_encode_read", "vx_decode_areas",
     "vx_explode", "vx_light", "vx_diag_fp64_rate", "vx_update_locations", "vx_update_read",
     "vx_mesh_read_compact", "vx_set_mesh_retention", "vx_mesh_unload", "vx_read_face_masks", "vx_visible_zone",
-    "vx_lock", "vx_unlock", "vx_copy_last_error",
+    "vx_lock", "vx_unlock", "vx_copy_last_error", "vx_noise_variant", "vx_set_gradient_order",
 ]
 
 
@@ -102,8 +103,13 @@ def make_view(cam_pos, cam_target, render_size=8, head_in_water=False, show_map=
     return v
 
 
+#: the libnoise-calibration builds (csrc/Makefile `variants`): mask -> path
+VARIANT_LIBS = {v: os.path.join(_HERE, "variants", f"libvoxel_cuda_v{v}.so") for v in (1, 6, 8)}  # Fbm form; both tie-breaks; skew digits
+
+
 def build(verbose: bool = False) -> str:
-    """Compile the CUDA library for sm_100a with nvcc (csrc/Makefile). Returns the .so path."""
+    """Compile the CUDA library for sm_100a with nvcc (csrc/Makefile), the host mirror and the
+    VX_NOISE_VARIANT builds. Returns the .so path."""
     r = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("building libvoxel_cuda.so failed:\n" + r.stdout + r.stderr)
@@ -112,6 +118,9 @@ def build(verbose: bool = False) -> str:
     r = subprocess.run(["make", "-C", os.path.join(_HERE, "host")], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("building libvoxel_host.so failed:\n" + r.stdout + r.stderr)
+    r = subprocess.run(["make", "-C", CSRC, "-j", "4", "variants"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building the VX_NOISE_VARIANT libraries failed:\n" + r.stdout + r.stderr)
     return LIB_PATH
 
 
@@ -152,6 +161,9 @@ def load():
     L.vx_host_free.argtypes = [vp]
     L.vx_host_free.restype = None
     L.vx_set_seed.argtypes = [vp, C.c_uint64]
+    L.vx_noise_variant.restype = C.c_int
+    L.vx_noise_variant.argtypes = []
+    L.vx_set_gradient_order.argtypes = [vp, vp, vp]
     L.vx_hash_world_name.restype = C.c_uint64
     L.vx_hash_world_name.argtypes = [C.c_char_p]
     L.vx_generate.argtypes = [vp, vp, C.c_int, vp, vp]
@@ -310,6 +322,13 @@ class Context:
     def set_seed(self, seed: int):
         self.seed = seed & 0xFFFFFFFFFFFFFFFF
         self._check(self._lib.vx_set_seed(self._h, self.seed))
+
+    def set_gradient_order(self, order2=None, order3=None):
+        """libnoise calibration: permutations of the 2-D (24) / 3-D (12) gradient tables, None = canonical."""
+        o2 = None if order2 is None else np.ascontiguousarray(order2, np.uint8)
+        o3 = None if order3 is None else np.ascontiguousarray(order3, np.uint8)
+        assert (o2 is None or o2.size == 24) and (o3 is None or o3.size == 12)
+        self._check(self._lib.vx_set_gradient_order(self._h, _ptr(o2), _ptr(o3)))
 
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self._lib.vx_set_stream(self._h, cuda_stream_ptr or None))

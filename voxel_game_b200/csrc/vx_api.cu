@@ -152,6 +152,8 @@ struct vx_ctx {
     std::string last_error;
 
     bool has_seed = false;
+    bool has_order = false;  // vx_set_gradient_order: gradient-table permutations (libnoise calibration)
+    uint8_t order2[24] = {}, order3[12] = {};
     NoiseTables tables{};
     NoiseImage* d_noise_image = nullptr;  // lookup tables of the current seed (vx_tables.hpp)
 
@@ -751,11 +753,36 @@ int vx_set_seed(vx_ctx* ctx, uint64_t seed) {
     if (!ctx->d_noise_image) VX_CUDA(cudaMalloc(&ctx->d_noise_image, sizeof(NoiseImage)));
     build_noise_tables(seed, &ctx->tables);
     NoiseImage image;
-    build_noise_image(ctx->tables, &image);
+    build_noise_image(ctx->tables, &image, ctx->has_order ? ctx->order2 : nullptr, ctx->has_order ? ctx->order3 : nullptr);
     VX_CUDA(cudaMemcpy(ctx->d_noise_image, &image, sizeof image, cudaMemcpyHostToDevice));
     ctx->tables.image = ctx->d_noise_image;
     ctx->has_seed = true;
     return VX_OK;
+}
+
+int vx_noise_variant(void) { return VX_NOISE_VARIANT; }
+
+int vx_set_gradient_order(vx_ctx* ctx, const uint8_t* order2, const uint8_t* order3) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    bool seen2[24] = {}, seen3[12] = {};
+    for (int i = 0; i < 24; ++i) {
+        const int v = order2 ? order2[i] : i;
+        if (v >= 24 || seen2[v]) return fail(ctx, VX_ERR_INVALID, "vx_set_gradient_order: order2 is not a permutation of 0..23");
+        seen2[v] = true;
+        ctx->order2[i] = (uint8_t)v;
+    }
+    for (int i = 0; i < 12; ++i) {
+        const int v = order3 ? order3[i] : i;
+        if (v >= 12 || seen3[v]) return fail(ctx, VX_ERR_INVALID, "vx_set_gradient_order: order3 is not a permutation of 0..11");
+        seen3[v] = true;
+        ctx->order3[i] = (uint8_t)v;
+    }
+    ctx->has_order = order2 != nullptr || order3 != nullptr;
+    if (!ctx->has_seed) return VX_OK;
+    // the tables of the current seed again, in the new order; resident areas keep their voxels
+    ctx->last_gen_version = ~0ull;
+    return vx_set_seed(ctx, ctx->tables.seed);
 }
 
 int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out,

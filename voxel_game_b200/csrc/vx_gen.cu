@@ -273,6 +273,7 @@ __device__ __forceinline__ int fbm2_region(const NoiseTables& nt, const NoiseSha
         for (int i = 0; i < NCUTS; ++i) r += b >= cuts[i] ? 1 : 0;
         return r;
     };
+    const double px = x, py = y;
     x *= q.frequency;
     y *= q.frequency;
     double acc = 0.0;
@@ -281,14 +282,23 @@ __device__ __forceinline__ int fbm2_region(const NoiseTables& nt, const NoiseSha
     const double mid = acc * q.norm, rest = SIMPLEX_BOUND * q.amp[1] * q.norm + 1e-9;
     const int r_lo = region(mid - rest), r_hi = region(mid + rest);
     if (r_lo == r_hi) return r_lo;
+#if VX_NOISE_VARIANT & 1
+    x = px * q.freq[1];
+    y = py * q.freq[1];
+#else
+    (void)px, (void)py;
     x *= q.lacunarity;
     y *= q.lacunarity;
+#endif
     acc += q.amp[1] * simplex2<FBM_TABLE<ID>>(s, x, y);
     ++evals;
     return region(acc * q.norm);
 }
 
-__global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_constant__ NoiseTables nt,
+#ifndef VX_K1_CTAS_PER_SM
+#define VX_K1_CTAS_PER_SM 4
+#endif
+__global__ void __launch_bounds__(256, VX_K1_CTAS_PER_SM) gen_columns_kernel(const __grid_constant__ NoiseTables nt,
                                                           const uint4* __restrict__ jobs,
                                                           uint8_t* __restrict__ pool_voxels,
                                                           uint8_t* __restrict__ pool_heights,
@@ -391,8 +401,12 @@ __global__ void __launch_bounds__(256, 4) gen_columns_kernel(const __grid_consta
         const double2 d = sq.acc[i];  // first octave's weighted value, threshold
         // the column's coordinates as its own thread computed them; octave 1 = octave 0 * lacunarity
         const double cx = (double)((c & 15u) + ax * AREA_SIZE), cy = (double)((c >> 4) + ay * AREA_SIZE);
+#if VX_NOISE_VARIANT & 1
+        const double x3 = cx * qa.freq[1], y3 = cy * qa.freq[1], z3 = (double)zi * qa.freq[1];
+#else
         double x3 = cx * qa.frequency, y3 = cy * qa.frequency, z3 = (double)zi * qa.frequency;
         x3 *= qa.lacunarity; y3 *= qa.lacunarity; z3 *= qa.lacunarity;
+#endif
         double acc = d.x;
         acc += qa.amp[1] * simplex3<FBM_TABLE<FBM_ALT>>(sb, sg, x3, y3, z3);
         evals3 += 1;
@@ -562,6 +576,9 @@ struct CaveSmem {
     alignas(16) uint8_t bytes[TAB_BYTES];       // the (doubled) permutation tables (vx_noise.cuh)
     NoiseImage::Code grad3[2][TAB_STRIDE];      // 3-D gradient codes of the two cave tables
     double amp[2][8];              // [0] = noise1, [1] = noise2: running amplitudes
+#if VX_NOISE_VARIANT & 1
+    double freq[2][8];             // running frequencies (the other Fbm form)
+#endif
     double rest[2][9];             // bound of the octaves not yet evaluated (cave_rest) + slack
     CaveWarp warp[8];
 };
@@ -600,6 +617,10 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
     if (tid < 8) {
         sm.amp[0][tid] = tid < 6 ? q1.amp[tid] : 0.0;
         sm.amp[1][tid] = q2.amp[tid];
+#if VX_NOISE_VARIANT & 1
+        sm.freq[0][tid] = tid < 6 ? q1.freq[tid] : 0.0;
+        sm.freq[1][tid] = q2.freq[tid];
+#endif
     }
     if (tid < 18) (&sm.rest[0][0])[tid] = (&nt.cave_rest[0][0])[tid] + 1e-9;
     __syncthreads();
@@ -653,8 +674,13 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
                 __syncwarp();  // nobody is still reading the previous chunk's tables
                 cw.item[lane] = item;
                 if (lane < CAVE_CHUNK) {
+#if VX_NOISE_VARIANT & 1
+                    cw.oa[lane] = make_double2(px, py);  // raw: every octave multiplies by its own frequency
+                    cw.ob[lane] = make_double2(px, py);
+#else
                     cw.oa[lane] = make_double2(px * f1, py * f1);
                     cw.ob[lane] = make_double2(px * f2, py * f2);
+#endif
                 }
                 cw.first[lane + 1] = v;
                 if (lane == 0) cw.first[0] = 0;
@@ -678,8 +704,13 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
                 const unsigned zi = CAVE_MIN_ZI + (w - cw.first[lo]);
                 const double2 oa = cw.oa[lo], ob = cw.ob[lo];
                 const double pz = (double)zi;
+#if VX_NOISE_VARIANT & 1
+                xa = oa.x; ya = oa.y; za = pz;
+                xb = ob.x; yb = ob.y; zb = pz;
+#else
                 xa = oa.x; ya = oa.y; za = pz * f1;
                 xb = ob.x; yb = ob.y; zb = pz * f2;
+#endif
                 a = 0.0; bsum = 0.0;
                 step = 0;
                 out_index = (size_t)(item >> 8) * VOXELS_IN_AREA + (item & 255u) + 256u * (AREA_HEIGHT - zi);
@@ -695,6 +726,19 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
             // one octave of each Fbm per round (noise1 has 6, noise2 has 8): no per-lane selection
             // of coordinates, and two independent evaluations in flight
             const unsigned k = step;
+#if VX_NOISE_VARIANT & 1
+            const double fb = sm.freq[1][k];
+            const double svb = simplex3<FBM_TABLE<FBM_CAVE2>>(sb, sg2, xb * fb, yb * fb, zb * fb);
+            bsum += sm.amp[1][k] * svb;
+            ++my_evals;
+            if (k < 6) {
+                const double fa = sm.freq[0][k];
+                const double sva = simplex3<FBM_TABLE<FBM_CAVE1>>(sb, sg1, xa * fa, ya * fa, za * fa);
+                a += sm.amp[0][k] * sva;
+                ++my_evals;
+            }
+            (void)l1, (void)l2, (void)f1, (void)f2;
+#else
             const double svb = simplex3<FBM_TABLE<FBM_CAVE2>>(sb, sg2, xb, yb, zb);
             bsum += sm.amp[1][k] * svb;
             xb *= l2; yb *= l2; zb *= l2;
@@ -705,6 +749,7 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
                 xa *= l1; ya *= l1; za *= l1;
                 ++my_evals;
             }
+#endif
             ++step;
             const double ca = a * n1, cb = bsum * n2;
             const double ra = sm.rest[0][step < 6 ? step : 6], rb = sm.rest[1][step];

@@ -50,10 +50,17 @@ static_assert(offsetof(NoiseImage, grad3) == offsetof(NoiseShared, grad3), "imag
 // Numeric constants whose low word is not zero cannot be FP64 immediates; as literals ptxas
 // re-materialises each of them with two moves per use.  From the constant bank they are plain
 // instruction operands.
+#if VX_NOISE_VARIANT & 8
+#define VX_SKEW_2D 0x1.76cf5d0b09955p-2    // f64 nearest to (sqrt(3) - 1) / 2
+#define VX_UNSKEW_2D 0x1.b0cb174df99c7p-3  // f64 nearest to (3 - sqrt(3)) / 6
+#else
+#define VX_SKEW_2D 0.366025403784439       // the crate's literals as recalled
+#define VX_UNSKEW_2D 0.211324865405187
+#endif
 __constant__ double c_noise_k[8] = {
-    0.366025403784439,        // 0: 2-D skew
-    0.211324865405187,        // 1: 2-D unskew
-    2.0 * 0.211324865405187,  // 2
+    VX_SKEW_2D,               // 0: 2-D skew
+    VX_UNSKEW_2D,             // 1: 2-D unskew
+    2.0 * VX_UNSKEW_2D,       // 2
     99.83685446303647,        // 3: 2-D normalisation
     1.0 / 3.0,                // 4: 3-D skew
     1.0 / 6.0,                // 5: 3-D unskew
@@ -114,7 +121,11 @@ __device__ __forceinline__ double simplex2(const NoiseShared* s, double x, doubl
     const double fx = floor_split(x + sk, i), fy = floor_split(y + sk, j);
     const double un = (fx + fy) * UNSKEW;
     const double x0 = x - fx + un, y0 = y - fy + un;
+#if VX_NOISE_VARIANT & 2
+    const bool lower = !(x0 <= y0);  // middle corner (1,0) unless x0 <= y0 (the other tie-break)
+#else
     const bool lower = !(x0 < y0);  // middle corner (1,0) unless x0 < y0
+#endif
     const double xm = x0 - 1.0, ym = y0 - 1.0;
     const double x1 = (lower ? xm : x0) + UNSKEW, y1 = (lower ? y0 : ym) + UNSKEW;
     const double x2 = xm + UNSKEW_2, y2 = ym + UNSKEW_2;
@@ -185,7 +196,11 @@ __device__ __forceinline__ double simplex3(unsigned sb, unsigned sg, double x, d
     const double x0 = x - fx + un, y0 = y - fy + un, z0 = z - fz + un;
     // rank the three coordinates: second corner steps along the largest, third corner along the
     // two largest (ties: x before y before z, i.e. x0 >= y0, y0 >= z0, x0 >= z0 count as "greater")
+#if VX_NOISE_VARIANT & 4
+    const bool xy = x0 > y0, yz = y0 > z0, xz = x0 > z0;  // the other tie-break: ties count as "less"
+#else
     const bool xy = x0 >= y0, yz = y0 >= z0, xz = x0 >= z0;
+#endif
     const bool i1 = xy && xz, j1 = !xy && yz, k1 = !xz && !yz;
     const bool i2 = xy || xz, j2 = !xy || yz, k2 = !(xz && yz);
     // "c - step" as a select between c - 1.0 and c (c - 0.0 == c); c - 1.0 also serves corner 3
@@ -217,15 +232,20 @@ __device__ __forceinline__ double simplex3(unsigned sb, unsigned sg, double x, d
 template <int ID>
 __device__ __forceinline__ double fbm2(const NoiseTables& nt, const NoiseShared* s, double x, double y) {
     const FbmParams& q = nt.fbm[ID];
+    double acc = 0.0;
+#if VX_NOISE_VARIANT & 1
+#pragma unroll 1
+    for (int o = 0; o < q.octaves; ++o) acc += q.amp[o] * simplex2<FBM_TABLE<ID>>(s, x * q.freq[o], y * q.freq[o]);
+#else
     x *= q.frequency;
     y *= q.frequency;
-    double acc = 0.0;
 #pragma unroll 1
     for (int o = 0; o < q.octaves; ++o) {
         acc += q.amp[o] * simplex2<FBM_TABLE<ID>>(s, x, y);
         x *= q.lacunarity;
         y *= q.lacunarity;
     }
+#endif
     return acc * q.norm;
 }
 
@@ -233,10 +253,16 @@ template <int ID>
 __device__ __forceinline__ double fbm3(const NoiseTables& nt, const NoiseShared* s, double x, double y,
                                        double z) {
     const FbmParams& q = nt.fbm[ID];
+    double acc = 0.0;
+#if VX_NOISE_VARIANT & 1
+#pragma unroll 1
+    for (int o = 0; o < q.octaves; ++o)
+        acc += q.amp[o] * simplex3<FBM_TABLE<ID>>(smem_address(s->bytes), smem_address(s->grad3), x * q.freq[o],
+                                                  y * q.freq[o], z * q.freq[o]);
+#else
     x *= q.frequency;
     y *= q.frequency;
     z *= q.frequency;
-    double acc = 0.0;
 #pragma unroll 1
     for (int o = 0; o < q.octaves; ++o) {
         acc += q.amp[o] * simplex3<FBM_TABLE<ID>>(smem_address(s->bytes), smem_address(s->grad3), x, y, z);
@@ -244,6 +270,7 @@ __device__ __forceinline__ double fbm3(const NoiseTables& nt, const NoiseShared*
         y *= q.lacunarity;
         z *= q.lacunarity;
     }
+#endif
     return acc * q.norm;
 }
 

@@ -100,11 +100,13 @@ FbmParams make_fbm(int table, int octaves, double f, double l, double p) {
     q.lacunarity = l;
     q.octaves = octaves;
     q.table = table;
-    double sum = 0.0, amp = 1.0;
+    double sum = 0.0, amp = 1.0, freq = f;
     for (int i = 0; i < octaves; ++i) {
         sum = sum + powi(p, i);
         q.amp[i] = amp;
         amp *= p;
+        q.freq[i] = freq;  // the running `freq *= lacunarity` of the other Fbm form (VX_NOISE_VARIANT & 1)
+        freq *= l;
     }
     q.norm = 1.0 / sum;
     return q;
@@ -156,19 +158,24 @@ static const double GRAD2[24][2] = {
     {-0.793353340291235, 0.608761429008721},  {-0.608761429008721, 0.793353340291235},
     {-0.38268343236509, 0.923879532511287},   {-0.130526192220052, 0.99144486137381}};
 
-void build_noise_image(const NoiseTables& tables, NoiseImage* out) {
+void build_noise_image(const NoiseTables& tables, NoiseImage* out, const uint8_t* order2, const uint8_t* order3) {
     const unsigned n = TAB_COUNT * TAB_STRIDE;
     for (unsigned i = 0; i < n; ++i) {
         const unsigned v = tables.perm[i / TAB_STRIDE][i & 255u];
         out->bytes[i] = (uint8_t)v;
         out->bytes[n + i] = (uint8_t)(v % 24u);
     }
-    std::memcpy(out->grad2, GRAD2, sizeof GRAD2);
+    for (int i = 0; i < 24; ++i) {
+        const int src = order2 ? order2[i] % 24 : i;
+        out->grad2[i][0] = GRAD2[src][0];
+        out->grad2[i][1] = GRAD2[src][1];
+    }
     // gradient gi = perm % 12 of the edge-midpoint set: 0..3 (+-1,+-1,0), 4..7 (+-1,0,+-1),
     // 8..11 (0,+-1,+-1); bit 0 negates the first non-zero component, bit 1 the second
     for (int t = 0; t < GRAD3_TABLES; ++t)
         for (unsigned i = 0; i < TAB_STRIDE; ++i) {
-            const unsigned gi = tables.perm[t][i & 255u] % 12u, grp = gi >> 2;
+            const unsigned hashed = tables.perm[t][i & 255u] % 12u;
+            const unsigned gi = order3 ? order3[hashed] % 12u : hashed, grp = gi >> 2;
             out->grad3[t][i].x = (grp == 2u ? 0x7654u : 0x3210u) | ((gi & 1u) << 31);
             out->grad3[t][i].y = (grp == 0u ? 0x3210u : 0x7654u) | (((gi >> 1) & 1u) << 31);
         }

@@ -7,6 +7,18 @@
 #pragma once
 #include <cstdint>
 
+// The choices of libnoise 1.1.2 that nothing on the build machine pins are compile-time switches, bit
+// for bit the flags the repository's CPU checker understands (tests/test_gpu_variants.py);
+// vx_noise_variant() reports the mask a library was built with.  0 = the recalled crate behaviour.
+//   1  Fbm samples point * freq with a running freq *= lacunarity (default: point *= lacunarity)
+//   2  2-D middle corner: x0 == y0 goes to (0,1)                  (default: (1,0))
+//   4  3-D traversal: strict >                                    (default: >=)
+//   8  2-D skew constants: f64 nearest to the exact values        (default: the 15-digit literals)
+// The order of the gradient tables is data: vx_set_gradient_order.
+#ifndef VX_NOISE_VARIANT
+#define VX_NOISE_VARIANT 0
+#endif
+
 namespace vx {
 
 // One Fbm<Simplex> object: which permutation table it reads and its octave schedule.
@@ -15,6 +27,7 @@ struct FbmParams {
     double lacunarity;
     double norm;    // 1 / sum_{i<octaves} persistence^i   (libnoise Fbm::new)
     double amp[8];  // amp[0] = 1, amp[i+1] = amp[i] * persistence  (the running `amp *= p`)
+    double freq[8]; // freq[0] = frequency, freq[i+1] = freq[i] * lacunarity (VX_NOISE_VARIANT & 1 only)
     int octaves;
     int table;      // index into NoiseTables::perm
     int pad[2];
@@ -76,7 +89,10 @@ struct alignas(16) NoiseImage {
 constexpr double SIMPLEX_BOUND = 1.0001;
 
 void build_noise_tables(uint64_t seed, NoiseTables* out);
-void build_noise_image(const NoiseTables& tables, NoiseImage* out);
+// order2 / order3: permutations of the 24 2-D / 12 3-D gradients (entry i of the crate's table =
+// entry order[i] of the canonical tables in vx_tables.cpp), nullptr = canonical order
+void build_noise_image(const NoiseTables& tables, NoiseImage* out, const uint8_t* order2 = nullptr,
+                       const uint8_t* order3 = nullptr);
 uint64_t hash_world_name(const char* name);
 
 }  // namespace vx
