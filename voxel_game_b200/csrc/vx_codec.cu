@@ -312,38 +312,59 @@ __global__ void __launch_bounds__(1024) codec_offsets_kernel(const uint32_t* __r
 
 // ------------------------------------------------------------------------------------- decode
 constexpr uint32_t STAGE_BYTES = 4096;  // compressed files up to this size are parsed from shared memory
+constexpr uint32_t WIN = 512;           // bytes of the most recent output kept in shared memory
 
+// One warp per file, expanding STRAIGHT INTO THE AREA'S POOL SLOT.  Shared memory holds the staged
+// compressed file and a 512-byte window of the most recent output, not the 32 KiB area: an SM keeps
+// 32 files in flight instead of 6 -- the walk over the LZ4 sequences is a chain of dependent steps
+// per file, and files in flight are what hides it.  Payload byte p (bincode: FB 00 80, then 32 768
+// variant bytes) lives in hdr[p] for p < 3 and in vox[p - 3] after that, so voxel rows are 16-byte
+// aligned in the slot; the window is indexed by (p - 3) mod 512, so they are aligned there too.
+//   * a match whose offset fits the window (every match of the row-granular files this library
+//     writes: offsets 16 and 256) is ONE parallel pass: output byte j is window byte
+//     from + (j mod offset), whatever the length -- no rounds, nothing is read back;
+//   * a longer offset (any valid LZ4 file is accepted) reads back what this warp has written, with
+//     ld.global.cg behind a __syncwarp, in doubling rounds;
+//   * voxel ids are checked where they enter the stream (literals); matches only repeat checked bytes.
 struct DecodeSmem {
-    uint8_t raw[16 + VOXELS_IN_AREA];  // payload at raw + 13: its 32768 voxel bytes are 16-byte aligned
     uint8_t in[STAGE_BYTES];
+    alignas(16) uint8_t win[WIN];
+    uint8_t hdr[16];
 };
 
-// dst[0..n) = src[0..n), non-overlapping, by the whole warp; both in shared memory (or src in
-// global memory for a file that was not staged).  16 bytes per lane where both ends are 16-byte
-// aligned -- the files this library writes are row-granular, so nearly every match is -- else
-// byte by byte.
-__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
-    uint32_t done = 0;
-    if ((((uintptr_t)dst | (uintptr_t)src) & 15u) == 0u) {
-        const uint32_t n16 = n >> 4;
-        for (uint32_t k = lane; k < n16; k += 32)
-            reinterpret_cast<uint4*>(dst)[k] = reinterpret_cast<const uint4*>(src)[k];
-        done = n16 << 4;
-    }
-    for (uint32_t k = done + lane; k < n; k += 32) dst[k] = src[k];
+__device__ __forceinline__ uint32_t win_slot(uint32_t p) { return (p + WIN - 3u) & (WIN - 1u); }
+
+__device__ __forceinline__ uint32_t payload_get(const uint8_t* hdr, const uint8_t* vox, uint32_t p) {
+    return p < 3u ? hdr[p] : __ldcg(vox + (p - 3u));
+}
+__device__ __forceinline__ void payload_put(uint8_t* hdr, uint8_t* vox, uint32_t p, uint32_t v) {
+    if (p < 3u) hdr[p] = (uint8_t)v;
+    else vox[p - 3u] = (uint8_t)v;
 }
 
-// One warp per file.  status[i] = 1 if the file expands to a well-formed AreaDTO (then the voxels
-// are in the area's pool slot), 0 where the reference logs an error and generates the area instead
+// payload[dst .. dst + n) = payload[src .. src + n), src + n <= dst, read back from the slot.
+__device__ __forceinline__ void match_copy_far(uint8_t* hdr, uint8_t* vox, uint32_t dst, uint32_t src, uint32_t n, int lane) {
+    uint32_t done = 0;
+    if (src >= 3u && (((dst - 3u) | (src - 3u)) & 15u) == 0u) {
+        const uint32_t n16 = n >> 4;
+        uint4* d = reinterpret_cast<uint4*>(vox + (dst - 3u));
+        const uint4* f = reinterpret_cast<const uint4*>(vox + (src - 3u));
+        for (uint32_t k = lane; k < n16; k += 32) d[k] = __ldcg(f + k);
+        done = n16 << 4;
+    }
+    for (uint32_t k = done + lane; k < n; k += 32) payload_put(hdr, vox, dst + k, payload_get(hdr, vox, src + k));
+}
+
+// status[i] = 1 if the file expands to a well-formed AreaDTO (then the voxels are in the area's pool
+// slot), 0 where the reference logs an error and generates the area instead
 // (world_persistence.rs:66-70): bad size prefix, malformed LZ4 stream, wrong slice length, voxel id
-// >= 27.
+// >= 27 -- the slot then holds garbage and the host releases it.
 __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restrict__ jobs,
                                                           const uint8_t* __restrict__ files,
                                                           const unsigned long long* __restrict__ offsets,
                                                           uint8_t* __restrict__ pool_voxels,
                                                           uint8_t* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    DecodeSmem& sm = *reinterpret_cast<DecodeSmem*>(smem_raw);
+    __shared__ __align__(16) DecodeSmem sm;
     const int lane = threadIdx.x;
     const uint4 job = jobs[blockIdx.x];
     const uint8_t* file = files + offsets[blockIdx.x];
@@ -359,9 +380,12 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
         for (uint32_t i = lane; i < n; i += 32) sm.in[i] = file[i];
         src = sm.in;
     }
+    if (lane < 4) sm.hdr[lane] = 0;
     __syncwarp();
-    uint8_t* out = sm.raw + 13;
+    uint8_t* vox = pool_voxels + (size_t)job.z * VOXELS_IN_AREA;
     uint32_t ip = 4, op = 0;
+    bool bad_voxel = false;   // a literal byte that is no Voxel variant (this lane's share)
+    bool recheck = false;     // a match copied header bytes into the voxels: check them all at the end
     while (ok && ip < n) {
         const uint32_t token = src[ip++];
         uint32_t lit = token >> 4;
@@ -375,7 +399,12 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
             if (!ok) break;
         }
         if (lit > n - ip || lit > PAYLOAD - op) { ok = false; break; }
-        warp_copy(out + op, src + ip, lit, lane);
+        for (uint32_t k = lane; k < lit; k += 32) {
+            const uint32_t v = src[ip + k], p = op + k;
+            payload_put(sm.hdr, vox, p, v);
+            bad_voxel = bad_voxel || (p >= 3u && v >= (uint32_t)V_VARIANTS);
+            if (lit - k <= WIN) sm.win[win_slot(p)] = (uint8_t)v;
+        }
         ip += lit;
         op += lit;
         if (ip == n) break;  // last sequence: literals only
@@ -394,35 +423,83 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
             if (!ok) break;
         }
         if (len > PAYLOAD - op) { ok = false; break; }
-        __syncwarp();  // the literals are in place
-        // An overlapping match repeats the last `offset` bytes.  Copy in rounds: each round copies
-        // from the start of the pattern as much as is already final (offset, then twice that, ...),
-        // so every round is a plain non-overlapping copy.
-        const uint8_t* from = out + op - offset;
-        uint32_t done = 0;
-        while (done < len) {
-            const uint32_t chunk = min(len - done, offset + done);
-            warp_copy(out + op + done, from, chunk, lane);
-            done += chunk;
+        __syncwarp();  // the literals (and everything before them) are in place
+        const uint32_t from = op - offset, end = op + len;
+        recheck = recheck || from < 3u;
+        if (offset <= WIN) {
+            // output byte j = payload[from + j mod offset], all of which are in the window
+            const bool rows = (offset & 15u) == 0u && op >= 3u && ((op - 3u) & 15u) == 0u;
+            uint32_t done = 0;
+            if (rows) {
+                const uint32_t n16 = len >> 4;
+                uint4* d = reinterpret_cast<uint4*>(vox + (op - 3u));
+                for (uint32_t k = lane; k < n16; k += 32)
+                    d[k] = *reinterpret_cast<const uint4*>(sm.win + win_slot(from + (16u * k) % offset));
+                done = n16 << 4;
+            }
+            for (uint32_t j = done + lane; j < len; j += 32)
+                payload_put(sm.hdr, vox, op + j, sm.win[win_slot(from + j % offset)]);
+            // the window moves on to [end - WIN, end): every lane works out its 16 bytes from the old
+            // window, then all write
+            const uint32_t p0 = end - WIN + 16u * (uint32_t)lane;  // may wrap below 0: only p >= op is written
+            uint4 fresh = make_uint4(0, 0, 0, 0);
+            const bool whole = (int32_t)(p0 - op) >= 0 && rows && (len & 15u) == 0u;  // 16 bytes inside the match, row-aligned
+            if (whole) {
+                fresh = *reinterpret_cast<const uint4*>(sm.win + win_slot(from + (p0 - op) % offset));
+            } else {
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (uint32_t b = 0; b < 16; ++b) {
+                    const uint32_t p = p0 + b;
+                    if ((int32_t)(p - op) >= 0 && (int32_t)(end - p) > 0)
+                        w[b >> 2] |= (uint32_t)sm.win[win_slot(from + (p - op) % offset)] << (8u * (b & 3u));
+                }
+                fresh = make_uint4(w[0], w[1], w[2], w[3]);
+            }
             __syncwarp();
+            if (whole) {
+                *reinterpret_cast<uint4*>(sm.win + win_slot(p0)) = fresh;
+            } else {
+                const uint32_t w[4] = {fresh.x, fresh.y, fresh.z, fresh.w};
+#pragma unroll
+                for (uint32_t b = 0; b < 16; ++b) {
+                    const uint32_t p = p0 + b;
+                    if ((int32_t)(p - op) >= 0 && (int32_t)(end - p) > 0) sm.win[win_slot(p)] = (uint8_t)(w[b >> 2] >> (8u * (b & 3u)));
+                }
+            }
+        } else {
+            // An overlapping match repeats the last `offset` bytes.  Copy in rounds: each round copies
+            // from the start of the pattern as much as is already final (offset, then twice that, ...),
+            // so every round is a plain non-overlapping copy.
+            uint32_t done = 0;
+            while (done < len) {
+                const uint32_t chunk = min(len - done, offset + done);
+                match_copy_far(sm.hdr, vox, op + done, from, chunk, lane);
+                done += chunk;
+                __syncwarp();
+            }
+            const uint32_t tail = min(len, WIN);  // the window follows
+            for (uint32_t k = lane; k < tail; k += 32) {
+                const uint32_t p = end - tail + k;
+                sm.win[win_slot(p)] = (uint8_t)payload_get(sm.hdr, vox, p);
+            }
         }
-        op += len;
+        __syncwarp();
+        op = end;
     }
     __syncwarp();
     ok = ok && op == PAYLOAD;
     // bincode: Box<[Voxel]> = varint length (FB 00 80) + one variant byte per voxel, each < 27
-    ok = ok && out[0] == 251 && out[1] == (VOXELS_IN_AREA & 0xFF) && out[2] == (VOXELS_IN_AREA >> 8);
-    uint4* dst = reinterpret_cast<uint4*>(pool_voxels + (size_t)job.z * VOXELS_IN_AREA);
-    const uint4* voxels = reinterpret_cast<const uint4*>(sm.raw + 16);
-    bool valid = true;
-    if (ok) {
+    ok = ok && sm.hdr[0] == 251 && sm.hdr[1] == (VOXELS_IN_AREA & 0xFF) && sm.hdr[2] == (VOXELS_IN_AREA >> 8);
+    bool valid = !bad_voxel;
+    if (ok && recheck) {
+        const uint4* voxels = reinterpret_cast<const uint4*>(vox);
         const uint32_t limit = 0x01010101u * (uint32_t)(V_VARIANTS - 1);
         for (uint32_t w = lane; w < VOXELS_IN_AREA / 16; w += 32) {
-            const uint4 v = voxels[w];
+            const uint4 v = __ldcg(voxels + w);
             // any byte > 26 is not a Voxel variant (per-byte unsigned compare)
             valid = valid && (__vcmpgtu4(v.x, limit) | __vcmpgtu4(v.y, limit) | __vcmpgtu4(v.z, limit) |
                               __vcmpgtu4(v.w, limit)) == 0u;
-            dst[w] = v;
         }
     }
     ok = ok && __all_sync(0xFFFFFFFFu, valid);
@@ -448,8 +525,7 @@ void launch_codec_emit(const uint4* jobs, int n, const uint8_t* pool_voxels, uin
 void launch_codec_decode(const uint4* jobs, int n, const uint8_t* files, const unsigned long long* offsets,
                          uint8_t* pool_voxels, uint8_t* status, cudaStream_t stream) {
     if (n <= 0) return;
-    cudaFuncSetAttribute(codec_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
-    codec_decode_kernel<<<n, 32, sizeof(DecodeSmem), stream>>>(jobs, files, offsets, pool_voxels, status);
+    codec_decode_kernel<<<n, 32, 0, stream>>>(jobs, files, offsets, pool_voxels, status);
 }
 
 }  // namespace vx

@@ -10,7 +10,7 @@
 //                     candidates and ordered placement (trees.rs:142-241), column heights
 //                     (area.rs:34-56) and the S/T bit planes the mesher reads.  Cave-zone columns
 //                     are appended to a work list instead of being carved in place.
-//   K1b gen_caves   : persistent (3 CTAs per SM), warp-autonomous lanes over the list of cave-zone columns
+//   K1b gen_caves   : persistent (7 CTAs of 128 threads per SM), warp-autonomous lanes over the list of cave-zone columns
 //                     (cave_generator.rs:43-64): exact early exit on octave bounds, lanes refill
 //                     themselves, warps claim the next chunk while still busy.  FP64-bound part.
 //   K2  gen_finish  : persistent CTAs over the areas with cave columns (listed by K1): trees, heights,
@@ -226,16 +226,6 @@ __device__ __forceinline__ void planes_of_row(const uint4 q, uint32_t& s_bits, u
     s_bits = s;
     t_bits = t;
 }
-__device__ __forceinline__ void planes_of_area(const uint8_t* vox, uint16_t* planes, int tid) {
-    const uint4* rows = reinterpret_cast<const uint4*>(vox);
-    for (int r = tid; r < VOXELS_IN_AREA / 16; r += 256) {
-        uint32_t sb, tb;
-        planes_of_row(rows[r], sb, tb);
-        planes[r] = (uint16_t)sb;
-        planes[VOXELS_IN_AREA / 16 + r] = (uint16_t)tb;
-    }
-}
-
 // Surface voxels whose second noise octave has to be evaluated; lives where the area is assembled
 // afterwards (GenSmem::vox).
 struct SurfaceQueue {
@@ -566,6 +556,14 @@ static_assert(CAVE_CHUNK >= 1 && CAVE_CHUNK <= CAVE_SLOTS && (CAVE_CHUNK & (CAVE
 // The 14 cave octaves are evaluated in rounds: round k = octave k of noise2 (8 octaves, weights
 // .650 .228 .080 .028 ...) and, for k < 6, octave k of noise1 (6 octaves, .553 .249 .112 .050 ...).
 
+// 128-thread CTAs, 7 per SM: 72 registers per thread without spills, 28 resident warps per SM (256 x 3
+// at 79 registers gives 24; 128 x 8 needs a 64-register cap that spills) -- profiles/r02_ab_caves.log
+#ifndef VX_CAVE_CTAS_PER_SM
+#define VX_CAVE_CTAS_PER_SM 7
+#endif
+#ifndef VX_CAVE_THREADS
+#define VX_CAVE_THREADS 128
+#endif
 struct CaveWarp {  // per-warp description of the claimed chunk
     uint32_t first[CAVE_SLOTS + 1];  // exclusive prefix of per-column voxel counts
     uint32_t item[CAVE_SLOTS];       // slot * 256 + column
@@ -579,9 +577,21 @@ struct CaveSmem {
 #if VX_NOISE_VARIANT & 1
     double freq[2][8];             // running frequencies (the other Fbm form)
 #endif
-    double rest[2][9];             // bound of the octaves not yet evaluated (cave_rest) + slack
-    CaveWarp warp[8];
+    // Per evaluated-octave count s and Fbm f: the raw running sum x of f decides "norm_f * x + rest_f[s] < c"
+    // and "norm_f * x - rest_f[s] >= c" for c = 0.4, 0.8 by comparing the HIGH WORD of x, mapped to a
+    // monotone integer key, with the key of a precomputed threshold: {below 0.4, below 0.8, at least
+    // 0.4, at least 0.8}.  key(x) < key(T) implies x < T, key(x) > key(T) implies x > T; equal high words
+    // decide nothing, which only postpones a verdict (the bound is 2^-20 wider).
+    int4 thr[2][9];
+    double2 zf[AREA_HEIGHT];       // zi * frequency of noise1 / noise2: octave-0 z coordinates
+    CaveWarp warp[VX_CAVE_THREADS / 32];
 };
+
+// Monotone integer key of the high word of a double: a < b as doubles whenever key(a) < key(b).
+__device__ __forceinline__ int hi_key(double x) {
+    const int h = __double2hiint(x);
+    return h ^ ((h >> 31) & 0x7FFFFFFF);
+}
 
 // Max<Fbm, Fbm>::sample + threshold (cave_generator.rs:27-30,43-64) for every voxel of the listed
 // cave-zone columns:  cave  <=>  (70..90).contains(normalise(max(a, b)) as i32)  <=>  0.4 <= m < 0.8
@@ -597,10 +607,7 @@ struct CaveSmem {
 //     one at once (ballot + popc, no atomics, no CTA barrier) instead of idling until the slowest
 //     lane is done.  Lanes of a warp sit at different octaves of different voxels, which costs
 //     nothing because the octave index only selects table rows.
-#ifndef VX_CAVE_CTAS_PER_SM
-#define VX_CAVE_CTAS_PER_SM 3
-#endif
-__global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(const __grid_constant__ NoiseTables nt,
+__global__ void __launch_bounds__(VX_CAVE_THREADS, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(const __grid_constant__ NoiseTables nt,
                                                         const uint32_t* __restrict__ cave_items,
                                                         const uint32_t* __restrict__ cave_count,
                                                         uint8_t* __restrict__ pool_voxels,
@@ -612,8 +619,8 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
     const FbmParams& q1 = nt.fbm[FBM_CAVE1];
     const FbmParams& q2 = nt.fbm[FBM_CAVE2];
     static_assert(FBM_TABLE<FBM_CAVE1> == 0 && FBM_TABLE<FBM_CAVE2> == 1, "grad3[0..1] are the cave tables");
-    load_noise_image(sm.bytes, nt, 0, TAB_BYTES, tid, 256);
-    load_noise_image(sm.grad3, nt, (unsigned)offsetof(NoiseImage, grad3), (unsigned)sizeof(sm.grad3), tid, 256);
+    load_noise_image(sm.bytes, nt, 0, TAB_BYTES, tid, VX_CAVE_THREADS);
+    load_noise_image(sm.grad3, nt, (unsigned)offsetof(NoiseImage, grad3), (unsigned)sizeof(sm.grad3), tid, VX_CAVE_THREADS);
     if (tid < 8) {
         sm.amp[0][tid] = tid < 6 ? q1.amp[tid] : 0.0;
         sm.amp[1][tid] = q2.amp[tid];
@@ -622,7 +629,17 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
         sm.freq[1][tid] = q2.freq[tid];
 #endif
     }
-    if (tid < 18) (&sm.rest[0][0])[tid] = (&nt.cave_rest[0][0])[tid] + 1e-9;
+    if (tid < 18) {
+        const int* t = &nt.cave_thr[0][0][0] + 4 * tid;  // thresholds as integer keys, made by the host (vx_tables.cpp)
+        (&sm.thr[0][0])[tid] = make_int4(t[0], t[1], t[2], t[3]);
+    }
+    if (tid < AREA_HEIGHT) {
+#if VX_NOISE_VARIANT & 1
+        sm.zf[tid] = make_double2((double)tid, (double)tid);
+#else
+        sm.zf[tid] = make_double2((double)tid * q1.frequency, (double)tid * q2.frequency);
+#endif
+    }
     __syncthreads();
     const uint32_t n_items = *cave_count;
     const double f1 = q1.frequency, f2 = q2.frequency, l1 = q1.lacunarity, l2 = q2.lacunarity;
@@ -702,15 +719,9 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
                 }
                 const uint32_t item = cw.item[lo];
                 const unsigned zi = CAVE_MIN_ZI + (w - cw.first[lo]);
-                const double2 oa = cw.oa[lo], ob = cw.ob[lo];
-                const double pz = (double)zi;
-#if VX_NOISE_VARIANT & 1
-                xa = oa.x; ya = oa.y; za = pz;
-                xb = ob.x; yb = ob.y; zb = pz;
-#else
-                xa = oa.x; ya = oa.y; za = pz * f1;
-                xb = ob.x; yb = ob.y; zb = pz * f2;
-#endif
+                const double2 oa = cw.oa[lo], ob = cw.ob[lo], oz = sm.zf[zi];
+                xa = oa.x; ya = oa.y; za = oz.x;
+                xb = ob.x; yb = ob.y; zb = oz.y;
                 a = 0.0; bsum = 0.0;
                 step = 0;
                 out_index = (size_t)(item >> 8) * VOXELS_IN_AREA + (item & 255u) + 256u * (AREA_HEIGHT - zi);
@@ -751,14 +762,14 @@ __global__ void __launch_bounds__(256, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(con
             }
 #endif
             ++step;
-            const double ca = a * n1, cb = bsum * n2;
-            const double ra = sm.rest[0][step < 6 ? step : 6], rb = sm.rest[1][step];
-            const double hi_a = ca + ra, hi_b = cb + rb, lo_m = fmax(ca - ra, cb - rb);
+            // the verdict on integer keys of the two running sums (CaveSmem::thr): no f64 arithmetic
+            const int ka = hi_key(a), kb = hi_key(bsum);
+            const int4 ta = sm.thr[0][step < 6 ? step : 6], tb = sm.thr[1][step];
             int verdict = -1;  // -1 undecided, 0 solid, 1 cave
-            if ((hi_a < 0.4 && hi_b < 0.4) || lo_m >= 0.8) verdict = 0;
-            else if (lo_m >= 0.4 && hi_a < 0.8 && hi_b < 0.8) verdict = 1;
+            if ((ka < ta.x && kb < tb.x) || ka > ta.w || kb > tb.w) verdict = 0;
+            else if ((ka > ta.z || kb > tb.z) && ka < ta.y && kb < tb.y) verdict = 1;
             if (verdict < 0 && step == 8) {  // all octaves done: the crate's own expression
-                const int c = f64_as_i32(normalise(fmax(ca, cb)));
+                const int c = f64_as_i32(normalise(fmax(a * n1, bsum * n2)));
                 verdict = (c >= 70 && c < 90) ? 1 : 0;  // cave_generator.rs:10-11,63
             }
             if (verdict >= 0) {
@@ -857,19 +868,50 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
 }
 
 // ------------------------------------------------------------------------------------------- L1
+// Area::update_all_column_heights (area.rs:34-56) + the S/T bit planes of an uploaded / decoded area.
+// The 32 KiB of voxels are read ONCE, as 16-byte rows (eight independent loads per thread, coalesced);
+// the T plane is kept in shared memory, the slabs above the first one that holds anything opaque are
+// skipped by every column (one ballot per row), and a column then walks T bits, not voxel bytes.
 __global__ void __launch_bounds__(256) column_heights_kernel(const uint4* __restrict__ jobs,
                                                              const uint8_t* __restrict__ pool_voxels,
                                                              uint8_t* __restrict__ pool_heights,
                                                              uint2* __restrict__ slot_xy,
                                                              uint16_t* __restrict__ pool_planes) {
-    const int tid = threadIdx.x;
+    __shared__ uint16_t s_t[VOXELS_IN_AREA / 16];
+    __shared__ int s_first[8];
+    const int tid = threadIdx.x, lane = tid & 31;
     const uint4 job = jobs[blockIdx.x];
     const uint32_t slot = job.z;
-    const uint8_t* vox = pool_voxels + (size_t)slot * VOXELS_IN_AREA;
+    const uint4* rows = reinterpret_cast<const uint4*>(pool_voxels + (size_t)slot * VOXELS_IN_AREA);
     if (tid == 0 && slot_xy) slot_xy[slot] = make_uint2(job.x, job.y);
-    if (pool_planes) planes_of_area(vox, pool_planes + (size_t)slot * (VOXELS_IN_AREA / 8), tid);
-    int z = 0;
-    while (z < AREA_HEIGHT && is_transparent(vox[tid + 256 * z])) ++z;
+    uint4 q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = rows[tid + 256 * k];  // row r = tid + 256 k: y = tid & 15, z = (tid >> 4) + 16 k
+    uint16_t* planes = pool_planes ? pool_planes + (size_t)slot * (VOXELS_IN_AREA / 8) : nullptr;
+    int first = AREA_HEIGHT;  // first slab (from the top) of this thread's rows that is not all transparent
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t sb, tb;
+        planes_of_row(q[k], sb, tb);
+        const int r = tid + 256 * k;
+        s_t[r] = (uint16_t)tb;
+        if (planes) {
+            planes[r] = (uint16_t)sb;
+            planes[VOXELS_IN_AREA / 16 + r] = (uint16_t)tb;
+        }
+        // the 16 rows of a slab sit in one half-warp
+        const unsigned clear = __ballot_sync(0xFFFFFFFFu, tb == 0xFFFFu);
+        const bool slab_clear = ((clear >> (lane & 16)) & 0xFFFFu) == 0xFFFFu;
+        if (!slab_clear) first = min(first, (tid >> 4) + 16 * k);
+    }
+    first = __reduce_min_sync(0xFFFFFFFFu, first);
+    if (lane == 0) s_first[tid >> 5] = first;
+    __syncthreads();
+    int z = s_first[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) z = min(z, s_first[w]);
+    const int x = tid & 15, y = tid >> 4;  // heights are indexed x + 16 y
+    while (z < AREA_HEIGHT && ((s_t[16 * z + y] >> x) & 1u)) ++z;
     pool_heights[(size_t)slot * COLUMNS_IN_AREA + tid] = (uint8_t)(z < AREA_HEIGHT ? z : AREA_HEIGHT - 1);
 }
 
@@ -904,7 +946,7 @@ void launch_gen_columns(const NoiseTables& nt, const uint4* jobs, int n, uint8_t
 void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const uint32_t* cave_count, uint8_t* pool_voxels,
                       const uint8_t* pool_heights, const uint2* slot_xy, unsigned long long* stats,
                       int sm_count, cudaStream_t stream) {
-    gen_caves_kernel<<<sm_count * VX_CAVE_CTAS_PER_SM, 256, 0, stream>>>(nt, cave_items, cave_count, pool_voxels,
+    gen_caves_kernel<<<sm_count * VX_CAVE_CTAS_PER_SM, VX_CAVE_THREADS, 0, stream>>>(nt, cave_items, cave_count, pool_voxels,
                                                        pool_heights, slot_xy, stats);
 }
 

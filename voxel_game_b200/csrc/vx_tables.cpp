@@ -114,6 +114,14 @@ FbmParams make_fbm(int table, int octaves, double f, double l, double p) {
 
 inline uint64_t rol64(uint64_t v, unsigned n) { return (v << n) | (v >> (64u - n)); }
 
+// the device's hi_key (vx_gen.cu): high word of the double, sign-magnitude order made two's-complement order
+inline int high_word_key(double x) {
+    uint64_t b;
+    std::memcpy(&b, &x, sizeof b);
+    const int32_t h = (int32_t)(b >> 32);
+    return h ^ ((h >> 31) & 0x7FFFFFFF);
+}
+
 }  // namespace
 
 void build_noise_tables(uint64_t seed, NoiseTables* out) {
@@ -139,6 +147,10 @@ void build_noise_tables(uint64_t seed, NoiseTables* out) {
             double rest = 0.0;
             for (int i = k; i < q.octaves; ++i) rest += q.amp[i];
             out->cave_rest[f][k] = SIMPLEX_BOUND * q.norm * rest;
+            const double r = out->cave_rest[f][k] + 1e-9;  // the slack the kernel adds to the bound
+            const double t[4] = {(0.4 - r) / q.norm - 1e-9, (0.8 - r) / q.norm - 1e-9, (0.4 + r) / q.norm + 1e-9,
+                                 (0.8 + r) / q.norm + 1e-9};
+            for (int i = 0; i < 4; ++i) out->cave_thr[f][k][i] = high_word_key(t[i]);
         }
     }
 }

@@ -64,6 +64,11 @@ struct NoiseTables {
     // cave_rest[f][k]: upper bound of |norm * sum_{i >= k} amp_i * simplex_i| for the two cave
     // Fbms after k evaluated octaves (SIMPLEX_BOUND * norm * sum of the remaining amplitudes)
     double cave_rest[2][9];
+    // cave_thr[f][k] = integer keys (high word of a double, made monotone) of the thresholds that the
+    // raw running sum x of cave Fbm f is compared with after k octaves: x below [0] / [1] implies
+    // norm * x + rest < 0.4 / 0.8, x above [2] / [3] implies norm * x - rest >= 0.4 / 0.8 (rest =
+    // cave_rest[f][k] plus slack).  key(a) < key(b) implies a < b; equal keys decide nothing.
+    int cave_thr[2][9][4];
     const void* image;  // device copy of the NoiseImage of this seed (set by the owner of the tables)
 };
 
