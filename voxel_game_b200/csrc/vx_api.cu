@@ -1117,7 +1117,7 @@ int vx_encode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint64_t* total
     if ((st = sync_stream(ctx)) != VX_OK) return st;
     collect_timers(ctx);
     const uint64_t total = *ctx->h_small.as<uint64_t>();
-    VX_CUDA(ctx->d_codec_bytes.ensure(std::max<size_t>(16, total)));
+    VX_CUDA(ctx->d_codec_bytes.ensure(total + 32));  // the decoder stages whole 16-byte pieces: slack past the last file
     {
         ScopedTimer t(ctx, TM_CODEC);
         launch_codec_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_codec_kinds.as<uint8_t>(), offsets,
@@ -1164,7 +1164,7 @@ int vx_decode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* 
     int st = acquire_slots(ctx, area_xy, n, slots);
     if (st != VX_OK) return st;
     if ((st = upload_jobs(ctx, area_xy, slots, n)) != VX_OK) return st;
-    VX_CUDA(ctx->d_codec_bytes.ensure(std::max<size_t>(16, total)));
+    VX_CUDA(ctx->d_codec_bytes.ensure(total + 32));  // the decoder stages whole 16-byte pieces: slack past the last file
     VX_CUDA(ctx->d_codec_offsets.ensure((size_t)(n + 1) * 8));
     VX_CUDA(ctx->d_codec_status.ensure((size_t)n));
     ctx->codec_n = -1;  // d_codec_bytes no longer holds the result of vx_encode_areas

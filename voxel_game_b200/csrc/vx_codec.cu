@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(1024) codec_offsets_kernel(const uint32_t* __r
 }
 
 // ------------------------------------------------------------------------------------- decode
-constexpr uint32_t STAGE_BYTES = 4096;  // compressed files up to this size are parsed from shared memory
+constexpr uint32_t STAGE_BYTES = 4096;  // window of the compressed file in shared memory (most files fit whole)
 constexpr uint32_t WIN = 512;           // bytes of the most recent output kept in shared memory
 
 // One warp per file, expanding STRAIGHT INTO THE AREA'S POOL SLOT.  Shared memory holds the staged
@@ -355,6 +355,26 @@ __device__ __forceinline__ void match_copy_far(uint8_t* hdr, uint8_t* vox, uint3
     for (uint32_t k = done + lane; k < n; k += 32) payload_put(hdr, vox, dst + k, payload_get(hdr, vox, src + k));
 }
 
+// LZ4 length extension: bytes are added to `acc` up to and including the first one that is not 255.
+// The warp reads 32 bytes at a time (a 12 KiB match has 48 of them): one ballot finds the terminator,
+// one reduction adds what precedes it.  false = the stream ends first, or the length is absurd.
+__device__ __forceinline__ bool length_extension(const uint8_t* src, uint32_t n, uint32_t& ip, uint32_t& acc, int lane) {
+    while (true) {
+        const uint32_t pos = ip + (uint32_t)lane;
+        const uint32_t b = pos < n ? src[pos] : 0u;  // past the end: reads as a terminator, caught below
+        const unsigned stop = __ballot_sync(0xFFFFFFFFu, b != 255u);
+        if (stop) {
+            const int first = __ffs(stop) - 1;
+            acc += __reduce_add_sync(0xFFFFFFFFu, lane <= first ? b : 0u);
+            ip += (uint32_t)first + 1u;
+            return ip <= n && acc <= PAYLOAD + 255u;
+        }
+        acc += 32u * 255u;
+        ip += 32u;
+        if (acc > PAYLOAD + 255u) return false;
+    }
+}
+
 // status[i] = 1 if the file expands to a well-formed AreaDTO (then the voxels are in the area's pool
 // slot), 0 where the reference logs an error and generates the area instead
 // (world_persistence.rs:66-70): bad size prefix, malformed LZ4 stream, wrong slice length, voxel id
@@ -375,11 +395,26 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
         const uint32_t size = file[0] | (file[1] << 8) | (file[2] << 16) | ((uint32_t)file[3] << 24);
         ok = size == PAYLOAD;
     }
-    const uint8_t* src = file;
-    if (ok && n <= STAGE_BYTES) {
-        for (uint32_t i = lane; i < n; i += 32) sm.in[i] = file[i];
-        src = sm.in;
-    }
+    // Files are packed back to back, so a file starts at any byte: whole 16-byte pieces of the
+    // underlying buffer are staged and the parse reads at the file's position inside them.  A file
+    // longer than the stage is parsed through a sliding window that is refilled between sequences
+    // (the bytes a sequence header can span are bounded); its literals are copied from global memory.
+    const uint32_t head = (uint32_t)((uintptr_t)file & 15u);
+    const uint4* f16 = reinterpret_cast<const uint4*>(file - head);
+    const uint32_t pieces = (head + n + 15u) >> 4;
+    const uint8_t* src = sm.in + head;  // src[t] = file byte t while t < wend
+    uint32_t wend = 0;                  // file bytes [.., wend) are staged
+    auto restage = [&](uint32_t pos) {
+        const uint32_t first = (head + pos) >> 4;  // piece that holds file byte pos
+        const uint32_t count = min(pieces - first, STAGE_BYTES / 16u);
+        __syncwarp();
+        for (uint32_t i = lane; i < count; i += 32) reinterpret_cast<uint4*>(sm.in)[i] = __ldg(f16 + first + i);
+        __syncwarp();
+        src = sm.in + head - 16u * first;  // may point before sm.in: only [pos, wend) is ever read
+        wend = min(n, 16u * (first + count) - head);
+    };
+    constexpr uint32_t HEADER_SPAN = 320;  // token + 2 x 129 length bytes + offset, with room to spare
+    if (ok) restage(0);
     if (lane < 4) sm.hdr[lane] = 0;
     __syncwarp();
     uint8_t* vox = pool_voxels + (size_t)job.z * VOXELS_IN_AREA;
@@ -387,20 +422,14 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
     bool bad_voxel = false;   // a literal byte that is no Voxel variant (this lane's share)
     bool recheck = false;     // a match copied header bytes into the voxels: check them all at the end
     while (ok && ip < n) {
+        if (wend < n && ip + HEADER_SPAN > wend) restage(ip);
         const uint32_t token = src[ip++];
         uint32_t lit = token >> 4;
-        if (lit == 15u) {
-            uint32_t b;
-            do {
-                if (ip >= n) { ok = false; break; }
-                b = src[ip++];
-                lit += b;
-            } while (b == 255u);
-            if (!ok) break;
-        }
+        if (lit == 15u && !length_extension(src, n, ip, lit, lane)) { ok = false; break; }
         if (lit > n - ip || lit > PAYLOAD - op) { ok = false; break; }
+        const uint8_t* lsrc = ip + lit <= wend ? src : file;  // long literal runs of a long file: from global memory
         for (uint32_t k = lane; k < lit; k += 32) {
-            const uint32_t v = src[ip + k], p = op + k;
+            const uint32_t v = lsrc[ip + k], p = op + k;
             payload_put(sm.hdr, vox, p, v);
             bad_voxel = bad_voxel || (p >= 3u && v >= (uint32_t)V_VARIANTS);
             if (lit - k <= WIN) sm.win[win_slot(p)] = (uint8_t)v;
@@ -409,19 +438,12 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
         op += lit;
         if (ip == n) break;  // last sequence: literals only
         if (n - ip < 2u) { ok = false; break; }
+        if (wend < n && ip + HEADER_SPAN > wend) restage(ip);
         const uint32_t offset = src[ip] | (src[ip + 1] << 8);
         ip += 2;
         if (offset == 0u || offset > op) { ok = false; break; }
         uint32_t len = (token & 15u) + 4u;
-        if ((token & 15u) == 15u) {
-            uint32_t b;
-            do {
-                if (ip >= n) { ok = false; break; }
-                b = src[ip++];
-                len += b;
-            } while (b == 255u);
-            if (!ok) break;
-        }
+        if ((token & 15u) == 15u && !length_extension(src, n, ip, len, lane)) { ok = false; break; }
         if (len > PAYLOAD - op) { ok = false; break; }
         __syncwarp();  // the literals (and everything before them) are in place
         const uint32_t from = op - offset, end = op + len;
@@ -429,42 +451,47 @@ __global__ void __launch_bounds__(32) codec_decode_kernel(const uint4* __restric
         if (offset <= WIN) {
             // output byte j = payload[from + j mod offset], all of which are in the window
             const bool rows = (offset & 15u) == 0u && op >= 3u && ((op - 3u) & 15u) == 0u;
+            const bool pow2 = (offset & (offset - 1u)) == 0u;  // 16 and 256, the offsets K8 writes
+            const uint32_t omask = offset - 1u;
+            auto wrap = [&](uint32_t j) { return pow2 ? (j & omask) : j % offset; };
             uint32_t done = 0;
             if (rows) {
                 const uint32_t n16 = len >> 4;
                 uint4* d = reinterpret_cast<uint4*>(vox + (op - 3u));
                 for (uint32_t k = lane; k < n16; k += 32)
-                    d[k] = *reinterpret_cast<const uint4*>(sm.win + win_slot(from + (16u * k) % offset));
+                    d[k] = *reinterpret_cast<const uint4*>(sm.win + win_slot(from + wrap(16u * k)));
                 done = n16 << 4;
             }
             for (uint32_t j = done + lane; j < len; j += 32)
-                payload_put(sm.hdr, vox, op + j, sm.win[win_slot(from + j % offset)]);
+                payload_put(sm.hdr, vox, op + j, sm.win[win_slot(from + wrap(j))]);
             // the window moves on to [end - WIN, end): every lane works out its 16 bytes from the old
-            // window, then all write
+            // window, then all write.  Lanes whose 16 bytes lie before the match keep what is there.
             const uint32_t p0 = end - WIN + 16u * (uint32_t)lane;  // may wrap below 0: only p >= op is written
+            const int32_t rel = (int32_t)(p0 - op);               // where the block starts inside the match
+            const bool touched = rel + 16 > 0;
+            const bool whole = rel >= 0 && rows && (len & 15u) == 0u;  // row-aligned and inside
             uint4 fresh = make_uint4(0, 0, 0, 0);
-            const bool whole = (int32_t)(p0 - op) >= 0 && rows && (len & 15u) == 0u;  // 16 bytes inside the match, row-aligned
-            if (whole) {
-                fresh = *reinterpret_cast<const uint4*>(sm.win + win_slot(from + (p0 - op) % offset));
-            } else {
-                uint32_t w[4] = {0, 0, 0, 0};
+            if (touched) {
+                if (whole) {
+                    fresh = *reinterpret_cast<const uint4*>(sm.win + win_slot(from + wrap((uint32_t)rel)));
+                } else {
+                    uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-                for (uint32_t b = 0; b < 16; ++b) {
-                    const uint32_t p = p0 + b;
-                    if ((int32_t)(p - op) >= 0 && (int32_t)(end - p) > 0)
-                        w[b >> 2] |= (uint32_t)sm.win[win_slot(from + (p - op) % offset)] << (8u * (b & 3u));
+                    for (int b = 0; b < 16; ++b)
+                        if (rel + b >= 0)
+                            w[b >> 2] |= (uint32_t)sm.win[win_slot(from + wrap((uint32_t)(rel + b)))] << (8 * (b & 3));
+                    fresh = make_uint4(w[0], w[1], w[2], w[3]);
                 }
-                fresh = make_uint4(w[0], w[1], w[2], w[3]);
             }
             __syncwarp();
-            if (whole) {
-                *reinterpret_cast<uint4*>(sm.win + win_slot(p0)) = fresh;
-            } else {
-                const uint32_t w[4] = {fresh.x, fresh.y, fresh.z, fresh.w};
+            if (touched) {
+                if (whole) {
+                    *reinterpret_cast<uint4*>(sm.win + win_slot(p0)) = fresh;
+                } else {
+                    const uint32_t w[4] = {fresh.x, fresh.y, fresh.z, fresh.w};
 #pragma unroll
-                for (uint32_t b = 0; b < 16; ++b) {
-                    const uint32_t p = p0 + b;
-                    if ((int32_t)(p - op) >= 0 && (int32_t)(end - p) > 0) sm.win[win_slot(p)] = (uint8_t)(w[b >> 2] >> (8u * (b & 3u)));
+                    for (int b = 0; b < 16; ++b)
+                        if (rel + b >= 0) sm.win[win_slot(p0 + (uint32_t)b)] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
                 }
             }
         } else {
