@@ -572,8 +572,9 @@ def main():
         save files (LZ4 of the block IDs, what load_blocking reads), the column heights, and the mesh
         as 4-byte records (the 16-byte record, vertices and indices are a pure function of them)."""
         c.generate(gen_xy, max_height_out=p["mh"].array, read=False)
-        c.encode_areas(gen_xy, out=p["files"].array)
-        inf = c.mesh(mesh_xy)
+        total = c.encode_areas(gen_xy, read=False)  # returns when the sizes are known
+        inf = c.mesh(mesh_xy)                       # the vertex kernel runs ...
+        c.encode_read(n_gen, total, out=p["files"].array)  # ... while the files cross to the host
         c.mesh_read_compact(inf, out=(p["rf"].array, p["packed"].array))
 
     pin_c = compact_buffers()

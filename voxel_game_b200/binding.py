@@ -522,6 +522,14 @@ class Context:
         self._check(self._lib.vx_encode_read(self._h, files.ctypes.data if files.size else None, offsets.ctypes.data))
         return files[: int(total.value)], offsets
 
+    def encode_read(self, n_areas: int, total: int, out=None):
+        """The files of the last encode_areas(read=False) -> (files u8[total], offsets u64[n+1]).  The copy
+        waits for the encoder only: a mesh() issued in between runs while the files cross to the host."""
+        files = out if out is not None else np.empty(int(total), np.uint8)
+        offsets = np.empty(n_areas + 1, np.uint64)
+        self._check(self._lib.vx_encode_read(self._h, files.ctypes.data if files.size else None, offsets.ctypes.data))
+        return files[: int(total)], offsets
+
     def decode_areas(self, area_xy, files, offsets, read_heights: bool = True):
         """load_blocking for a batch of files -> (ok u8[n], max_height u8[n,256] or None); areas with
         ok == 0 are not resident afterwards (the caller generates them)."""

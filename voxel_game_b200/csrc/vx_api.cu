@@ -148,6 +148,10 @@ struct vx_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // device -> host copies that need not queue behind later kernels: vx_encode_read waits for the
+    // encoder (codec_ev), not for a vx_mesh enqueued after it
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t codec_ev = nullptr;
     std::recursive_mutex mu;  // recursive: vx_lock / vx_unlock bracket several calls of one thread
     std::string last_error;
 
@@ -611,6 +615,12 @@ int vx_create(int device, vx_ctx** out) {
         return VX_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->codec_ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return VX_ERR_CUDA;
+    }
     for (int i = 0; i < TM_COUNT; ++i)
         for (int k = 0; k < 2; ++k) cudaEventCreate(&ctx->ev[i][k]);
     cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming);
@@ -652,6 +662,8 @@ void vx_destroy(vx_ctx* ctx) {
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     for (int i = 0; i < TM_COUNT; ++i)
         for (int k = 0; k < 2; ++k) cudaEventDestroy(ctx->ev[i][k]);
+    cudaEventDestroy(ctx->codec_ev);
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1125,8 +1137,9 @@ int vx_encode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint64_t* total
     }
     ctx->timings.other_launches += 3;
     VX_CUDA(cudaGetLastError());
-    if ((st = sync_stream(ctx)) != VX_OK) return st;
-    collect_timers(ctx);
+    // the sizes are known; the files are being written: vx_encode_read waits for this event only, so a
+    // vx_mesh issued in between runs while the files cross to the host
+    VX_CUDA(cudaEventRecord(ctx->codec_ev, ctx->stream));
     ctx->codec_n = n;
     ctx->codec_total = total;
     *total_bytes = total;
@@ -1142,11 +1155,12 @@ int vx_encode_read(vx_ctx* ctx, uint8_t* files, uint64_t* offsets) {
         if (offsets) offsets[0] = 0;
         return VX_OK;
     }
+    VX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->codec_ev, 0));
     if (files && ctx->codec_total)
-        VX_CUDA(cudaMemcpyAsync(files, ctx->d_codec_bytes.p, ctx->codec_total, cudaMemcpyDeviceToHost, ctx->stream));
+        VX_CUDA(cudaMemcpyAsync(files, ctx->d_codec_bytes.p, ctx->codec_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
     if (offsets)
-        VX_CUDA(cudaMemcpyAsync(offsets, ctx->d_codec_offsets.p, (size_t)(ctx->codec_n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+        VX_CUDA(cudaMemcpyAsync(offsets, ctx->d_codec_offsets.p, (size_t)(ctx->codec_n + 1) * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     return VX_OK;
 }
 
