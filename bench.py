@@ -294,11 +294,27 @@ def main():
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
-    def strip(shift_x=0, whole=False):
+    plans = {}
+
+    def plan(shift_x):
+        """Rows of the region (moved by shift_x areas) per rank.  One rank: all of them.  Several: strips of
+        equal COST, not equal height -- a cave-zone column costs ~30x an ordinary one, and the caves are
+        not spread evenly: vx_cave_columns (a cost hint from the seed alone) weighs the rows, every rank
+        computes the same cut (voxel_game_b200/world.py balanced_rows)."""
+        if shift_x not in plans:
+            ax0, ay0, nx, ny = vg.spawn_region(REGION)
+            if world == 1:
+                plans[shift_x] = [(0, ny)]
+            else:
+                cc, cv = ctx.cave_columns(vg.region_xy(ax0 + shift_x - 1, ay0 - 1, nx + 2, ny + 2))
+                plans[shift_x] = vg.balanced_rows(*vg.row_costs(cc, cv, nx, ny), world)
+        return plans[shift_x]
+
+    def strip(shift_x=0, whole=False, plan_of=None):
         """(generate list, mesh list) of this rank: its rows of the region + the ring around them."""
         ax0, ay0, nx, ny = vg.spawn_region(REGION)
         ax0 += shift_x
-        lo, hi = (0, ny) if whole else vg.shard_rows(ny, world, rank)
+        lo, hi = (0, ny) if whole else plan(shift_x if plan_of is None else plan_of)[rank]
         return (vg.region_xy(ax0 - 1, ay0 + lo - 1, nx + 2, hi - lo + 2), vg.region_xy(ax0, ay0 + lo, nx, hi - lo))
 
     def timed(fn, steps, warmup, sample_clocks=False):
@@ -347,7 +363,9 @@ def main():
     # the previous one is unloaded, so no call ever sees a list or a resident set it has seen before
     ctx.set_timing(False)
     cold_steps = args.steps
-    cold_lists = [strip(shift_x=130 * (i + 1)) for i in range(cold_steps + 3)]
+    # (the strips keep the main region's row cut, so every step has the same shape: this measures the
+    # step without caches, not a re-planning per step)
+    cold_lists = [strip(shift_x=130 * (i + 1), plan_of=0) for i in range(cold_steps + 3)]
     prev = [gen_xy]
 
     def cold_step(i):
@@ -706,6 +724,7 @@ def main():
     roofline = dict(rooflines[dominant], kernel=dominant)
 
     kernel_sum = sum(kern.values())
+    kernel_sum_max = max_over_ranks(kernel_sum)
     line = {
         "metric": "chunks/sec (gen+light+mesh)", "value": value, "unit": "chunks/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -714,7 +733,9 @@ def main():
         "config": {"workload": f"c3_{REGION}x{REGION}_gen_light_mesh", "areas_meshed": REGION * REGION,
                    "areas_generated": gen_total, "areas_meshed_per_gpu": n_mesh, "areas_generated_per_gpu": n_gen,
                    "world_name": WORLD_NAME, "seed": seed, "faces": faces_total, "visible_voxels": recs_total,
-                   "parallelism": f"rows of the one region sharded x{world}, halo ring regenerated, no collective",
+                   "parallelism": f"rows of the one region sharded x{world} into strips of equal cost "
+                                  "(vx_cave_columns cost hint), halo ring regenerated, no collective",
+                   "rows_per_rank": [list(r) for r in plan(0)],
                    "l2": "no flush needed: a step streams ~0.55 GB of block IDs and ~1.8 GB of mesh over all ranks, "
                          "per rank > 126 MB L2 at every N <= 8"},
         "clocks": clocks,
@@ -727,6 +748,7 @@ def main():
         "rooflines": rooflines,
         "kernel_ms_per_step": kern,
         "kernel_ms_sum": kernel_sum,
+        "kernel_ms_sum_max_over_ranks": kernel_sum_max,
         # the stages separately (device time of their kernels; column heights and bit
         # planes are fused into generation, so LIGHT L1 has no time of its own)
         "stage_chunks_per_s_per_gpu": {

@@ -331,6 +331,16 @@ int vx_visible_zone(vx_ctx* ctx, const uint32_t* area_xy, int n, const vx_view* 
  * 0..15 per voxel over the resident areas listed, see DESIGN.md "L-ext". light_out n*32768. */
 int vx_light(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* light_out, int* iterations);
 
+/* ---- cost hint for sharding, computed from the seed alone -- nothing is generated or made resident:
+ * per listed area the number of cave-zone columns (CaveGenerator::is_cave_zone,
+ * cave_generator.rs:36-41), 0..256, and (cave_voxels_out, may be NULL) the number of voxels of those
+ * columns that run the cave noise (should_be_cave's range 25 <= z_inverted < 115 up to the terrain
+ * height, cave_generator.rs:43-64).  A cave voxel costs up to 14 3-D noise octaves, a whole ordinary
+ * column 16-18 2-D octaves, and caves are not spread evenly: a region is cut into equal-COST strips
+ * for several GPUs by these counts (voxel_game_b200/world.py balanced_rows; bench.py --gpus N). */
+int vx_cave_columns(vx_ctx* ctx, const uint32_t* area_xy, int n, uint32_t* cave_columns_out,
+                    uint32_t* cave_voxels_out);
+
 /* ---- diagnostics: measured FP64 DADD+DMUL issue rate of this GPU in Gop/s (no FMA), the
  * roofline denominator of the noise kernels. */
 int vx_diag_fp64_rate(vx_ctx* ctx, double* gops_per_s, float* ms);

@@ -92,6 +92,8 @@ extern "C" {
     pub fn vx_host_free(p: *mut c_void);
     pub fn vx_set_seed(ctx: *mut vx_ctx, seed: u64) -> c_int;
     pub fn vx_hash_world_name(world_name: *const c_char) -> u64;
+    pub fn vx_cave_columns(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, cave_columns_out: *mut u32,
+                           cave_voxels_out: *mut u32) -> c_int;
     pub fn vx_noise_variant() -> c_int;
     pub fn vx_set_gradient_order(ctx: *mut vx_ctx, order2: *const u8, order3: *const u8) -> c_int;
     pub fn vx_generate(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, voxels_out: *mut u8,
@@ -382,6 +384,17 @@ impl Pipeline {
         let mut packed = vec![0u32; info.n_recs as usize];
         self.check(unsafe { vx_mesh_read_compact(self.ctx, rec_first.as_mut_ptr(), packed.as_mut_ptr()) })?;
         Ok((rec_first, packed))
+    }
+
+    /// Cost hint for sharding a region over several GPUs, from the seed alone: per area the cave-zone
+    /// columns and the voxels that run the cave noise.
+    pub fn cave_columns(&self, areas: &[(u32, u32)]) -> Result<(Vec<u32>, Vec<u32>), VxError> {
+        let xy: Vec<u32> = areas.iter().flat_map(|a| [a.0, a.1]).collect();
+        let (mut cols, mut vox) = (vec![0u32; areas.len()], vec![0u32; areas.len()]);
+        self.check(unsafe {
+            vx_cave_columns(self.ctx, xy.as_ptr(), areas.len() as c_int, cols.as_mut_ptr(), vox.as_mut_ptr())
+        })?;
+        Ok((cols, vox))
     }
 
     /// libnoise calibration (include/voxel_cuda.h): the mask of code switches this library was built

@@ -52,6 +52,20 @@ def test_rust_shim_declares_every_header_symbol_and_guards_the_pairs():
     assert "vx_copy_last_error" in src
 
 
+def test_variant_libraries_are_current():
+    """The VX_NOISE_VARIANT builds (parity-pin kit) come from the same sources as the default library:
+    every declared symbol is exported, so a stale variant cannot sneak onto the GPU box."""
+    from voxel_game_b200.binding import VARIANT_LIBS
+
+    declared = set(_header_functions())
+    for mask, path in VARIANT_LIBS.items():
+        assert os.path.exists(path), f"{path} missing: __graft_entry__.build()"
+        out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+        exported = set(re.findall(r"\sT\s+(vx_[a-z0-9_]+)$", out, flags=re.M))
+        assert declared <= exported, (mask, sorted(declared - exported))
+        assert os.path.getmtime(path) >= os.path.getmtime(vg.LIB_PATH) - 600, f"{path} is older than the default library"
+
+
 def test_library_is_built_for_sm_100a_only():
     out = subprocess.run(["cuobjdump", "--list-elf", vg.LIB_PATH], capture_output=True, text=True)
     if out.returncode != 0:
@@ -176,6 +190,27 @@ def test_golden_regions_cover_caves_lakes_cold_and_trees():
 
 
 # ------------------------------------------------------------------------------ sharding (N > 1)
+def test_balanced_rows_partition_by_cost():
+    """Equal-cost strips for the sharded step: contiguous, non-empty, covering every row once; on
+    skewed costs the largest strip cost (ring rows included) beats the equal-height cut."""
+    rng = np.random.default_rng(0)
+    for nx, ny, n_ranks in ((128, 128, 8), (128, 128, 3), (16, 9, 9), (32, 40, 5)):
+        cc = np.zeros((ny + 2, nx + 2))
+        cc[ny // 3: ny // 2, nx // 4: 3 * nx // 4] = 256 * rng.random((ny // 2 - ny // 3, 3 * nx // 4 - nx // 4))
+        gen, mesh = vg.row_costs(cc.ravel(), 40 * cc.ravel(), nx, ny)
+        strips = vg.balanced_rows(gen, mesh, n_ranks)
+        assert len(strips) == n_ranks and strips[0][0] == 0 and strips[-1][1] == ny
+        assert all(a < b for a, b in strips) and all(strips[i][1] == strips[i + 1][0] for i in range(n_ranks - 1))
+        worst = max(vg.strip_cost(gen, mesh, a, b) for a, b in strips)
+        equal = max(vg.strip_cost(gen, mesh, *vg.shard_rows(ny, n_ranks, r)) for r in range(n_ranks))
+        assert worst <= equal * 1.0001
+        if ny >= 4 * n_ranks:
+            assert worst < 0.8 * equal
+    # uniform cost: the equal-height cut (up to the ring rows, which make the end strips a little cheaper)
+    gen, mesh = vg.row_costs(np.zeros(130 * 130), np.zeros(130 * 130), 128, 128)
+    assert all(14 <= b - a <= 18 for a, b in vg.balanced_rows(gen, mesh, 8))
+
+
 def test_shard_rows_partition():
     for ny, ws in [(128, 1), (128, 2), (128, 8), (130, 8), (7, 3), (5, 8)]:
         spans = [vg.shard_rows(ny, ws, r) for r in range(ws)]

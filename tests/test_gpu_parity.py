@@ -696,3 +696,27 @@ def test_query_and_read_pairs_are_atomic_across_threads(seed):
             for i in range(len(lists[k])):
                 dec = oracle.area_file_decode(bytes(files[int(offs[i]):int(offs[i + 1])]))
                 assert dec is not None and np.array_equal(dec, vox[i])
+
+
+def test_cave_columns_cost_hint_equals_is_cave_zone(ctx, seed):
+    """vx_cave_columns = per area the columns for which CaveGenerator::is_cave_zone
+    (cave_generator.rs:36-41) holds and their voxels in should_be_cave's range, from the seed alone;
+    the oracle's per-column samples agree, and so do the work counters of a generate over the list."""
+    xy = vg.region_xy(SPAWN - 8, SPAWN - 8, 16, 16)
+    cols, vox = ctx.cave_columns(xy)
+    gen = oracle.Generator(seed)
+    want_c, want_v = np.zeros(len(xy), np.uint32), np.zeros(len(xy), np.uint32)
+    for i, (ax, ay) in enumerate(xy):
+        for x in range(16):
+            for y in range(16):
+                h, cave, _, _ = gen.sample_column(int(ax), int(ay), x, y)
+                if cave:
+                    want_c[i] += 1
+                    want_v[i] += max(0, min(h, 114) - 25 + 1)
+    assert np.array_equal(cols, want_c) and np.array_equal(vox, want_v)
+    assert cols.max() == 256 and (cols == 0).sum() > 50  # whole cave areas and cave-free ones
+    ctx.set_timing(True)
+    ctx.generate(xy, read=False)
+    t = ctx.timings()
+    assert t["cave_columns"] == int(cols.sum()) and t["cave_voxels"] == int(vox.sum())
+    ctx.set_timing(False)

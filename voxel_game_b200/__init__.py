@@ -9,7 +9,7 @@ from .binding import (  # noqa: F401
     build, hash_world_name, load, make_view, unpack_records,
 )
 from .host import HOST_LIB_PATH, HOST_SYMBOLS, HostRenderer, expand_records, load_host  # noqa: F401
-from .world import region_xy, render_zone, shard_rows, spawn_region  # noqa: F401
+from .world import balanced_rows, region_xy, render_zone, row_costs, shard_rows, spawn_region, strip_cost  # noqa: F401
 
 __all__ = ["Context", "PinnedArray", "VxError", "build", "load", "hash_world_name", "region_xy",
            "shard_rows", "spawn_region", "ABI_SYMBOLS", "REC_DTYPE", "VERTEX_DTYPE", "EDIT_DTYPE",

@@ -47,6 +47,7 @@ ABI_SYMBOLS = [
     "vx_explode", "vx_light", "vx_diag_fp64_rate", "vx_update_locations", "vx_update_read",
     "vx_mesh_read_compact", "vx_set_mesh_retention", "vx_mesh_unload", "vx_read_face_masks", "vx_visible_zone",
     "vx_lock", "vx_unlock", "vx_copy_last_error", "vx_noise_variant", "vx_set_gradient_order",
+    "vx_cave_columns",
 ]
 
 
@@ -161,6 +162,7 @@ def load():
     L.vx_host_free.argtypes = [vp]
     L.vx_host_free.restype = None
     L.vx_set_seed.argtypes = [vp, C.c_uint64]
+    L.vx_cave_columns.argtypes = [vp, vp, C.c_int, vp, vp]
     L.vx_noise_variant.restype = C.c_int
     L.vx_noise_variant.argtypes = []
     L.vx_set_gradient_order.argtypes = [vp, vp, vp]
@@ -329,6 +331,14 @@ class Context:
         o3 = None if order3 is None else np.ascontiguousarray(order3, np.uint8)
         assert (o2 is None or o2.size == 24) and (o3 is None or o3.size == 12)
         self._check(self._lib.vx_set_gradient_order(self._h, _ptr(o2), _ptr(o3)))
+
+    def cave_columns(self, area_xy):
+        """(cave-zone columns, cave-noise voxels) per area from the seed alone: the cost hint for sharding."""
+        xy = _xy(area_xy)
+        cols = np.zeros(xy.shape[0], np.uint32)
+        vox = np.zeros(xy.shape[0], np.uint32)
+        self._check(self._lib.vx_cave_columns(self._h, xy.ctypes.data, xy.shape[0], cols.ctypes.data, vox.ctypes.data))
+        return cols, vox
 
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self._lib.vx_set_stream(self._h, cuda_stream_ptr or None))

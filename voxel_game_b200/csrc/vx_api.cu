@@ -1802,6 +1802,28 @@ int vx_visible_zone(vx_ctx* ctx, const uint32_t* area_xy, int n, const vx_view* 
     return VX_OK;
 }
 
+int vx_cave_columns(vx_ctx* ctx, const uint32_t* area_xy, int n, uint32_t* cave_columns_out, uint32_t* cave_voxels_out) {
+    if (!ctx || n < 0 || (n > 0 && (!area_xy || !cave_columns_out))) return VX_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    if (!ctx->has_seed) return fail(ctx, VX_ERR_NO_SEED, "vx_cave_columns before vx_set_seed");
+    VX_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) return VX_OK;
+    int st = sync_stream(ctx);  // d_tmp may be in use by a call that did not wait
+    if (st != VX_OK) return st;
+    VX_CUDA(ctx->d_tmp.ensure((size_t)n * 16));
+    uint2* d_xy = ctx->d_tmp.as<uint2>();
+    uint32_t* d_columns = reinterpret_cast<uint32_t*>(d_xy + n);
+    uint32_t* d_voxels = d_columns + n;
+    VX_CUDA(cudaMemcpyAsync(d_xy, area_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    launch_cave_columns(ctx->tables, d_xy, n, d_columns, d_voxels, ctx->stream);
+    ctx->timings.other_launches += 1;
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaMemcpyAsync(cave_columns_out, d_columns, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cave_voxels_out)
+        VX_CUDA(cudaMemcpyAsync(cave_voxels_out, d_voxels, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_stream(ctx);
+}
+
 int vx_diag_fp64_rate(vx_ctx* ctx, double* gops_per_s, float* ms_out) {
     if (!ctx || !gops_per_s) return VX_ERR_INVALID;
     std::lock_guard<std::recursive_mutex> lock(ctx->mu);

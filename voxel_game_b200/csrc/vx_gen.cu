@@ -642,6 +642,11 @@ __global__ void __launch_bounds__(VX_CAVE_THREADS, VX_CAVE_CTAS_PER_SM) gen_cave
     }
     __syncthreads();
     const uint32_t n_items = *cave_count;
+    // Columns per claim: CAVE_CHUNK when there is plenty of work; fewer (a power of two) when the list is
+    // short -- a strip of a sharded region -- so that every warp still gets ~6 claims and the counter can
+    // even them out.  Unclaimed slots of the per-warp table hold empty columns.
+    uint32_t claim = CAVE_CHUNK;
+    while (claim > 1u && (unsigned long long)n_items < 6ull * claim * gridDim.x * (VX_CAVE_THREADS / 32)) claim >>= 1;
     const double f1 = q1.frequency, f2 = q2.frequency, l1 = q1.lacunarity, l2 = q2.lacunarity;
     const double n1 = q1.norm, n2 = q2.norm;
     const unsigned sb = smem_address(sm.bytes), sg1 = smem_address(sm.grad3[0]), sg2 = smem_address(sm.grad3[1]);
@@ -664,13 +669,13 @@ __global__ void __launch_bounds__(VX_CAVE_THREADS, VX_CAVE_CTAS_PER_SM) gen_cave
             unsigned chunk = 0;
             if (lane == 0) chunk = atomicAdd(chunk_counter, 1u);
             chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
-            if ((unsigned long long)chunk * CAVE_CHUNK >= n_items) {
+            if ((unsigned long long)chunk * claim >= n_items) {
                 more = false;
             } else {
-                const uint32_t idx = chunk * CAVE_CHUNK + lane;
+                const uint32_t idx = chunk * claim + lane;
                 uint32_t item = 0, cnt = 0;
                 double px = 0.0, py = 0.0;
-                if (lane < CAVE_CHUNK && idx < n_items) {
+                if (lane < (int)claim && idx < n_items) {
                     item = cave_items[idx];
                     const unsigned H = pool_heights[item] & 0x7Fu;
                     // should_be_cave evaluates the noise for CAVE_MIN_ZI <= zi < CAVE_MAX_ZI, zi <= H
@@ -915,6 +920,50 @@ __global__ void __launch_bounds__(256) column_heights_kernel(const uint4* __rest
     pool_heights[(size_t)slot * COLUMNS_IN_AREA + tid] = (uint8_t)(z < AREA_HEIGHT ? z : AREA_HEIGHT - 1);
 }
 
+// ------------------------------------------------------------------------------------------- cost hint
+// Cave-zone columns per area (CaveGenerator::is_cave_zone, cave_generator.rs:36-41) and the voxels of
+// those columns that run the cave noise (should_be_cave's range, cave_generator.rs:43-64), without
+// generating anything: a cave voxel costs up to 14 3-D octaves against 16-18 2-D octaves for a whole
+// ordinary column, so these are the weights by which a region is cut into equal-cost strips for several
+// GPUs.  One CTA per area, one thread per column; only cave-zone columns evaluate their terrain height.
+__global__ void __launch_bounds__(256) cave_columns_kernel(const __grid_constant__ NoiseTables nt,
+                                                           const uint2* __restrict__ area_xy,
+                                                           uint32_t* __restrict__ columns,
+                                                           uint32_t* __restrict__ voxels) {
+    __shared__ __align__(256) NoiseShared sm;
+    __shared__ unsigned s_n[2];
+    const int tid = threadIdx.x;
+    load_noise_shared<FBM_TABLE<FBM_ALT>>(&sm, nt, tid, 256);
+    if (tid < 2) s_n[tid] = 0;
+    __syncthreads();
+    const uint2 a = area_xy[blockIdx.x];
+    const double px = (double)((tid & 15) + a.x * AREA_SIZE), py = (double)((tid >> 4) + a.y * AREA_SIZE);
+    const int cave_cuts[1] = {80};
+    unsigned evals = 0;
+    const bool cave_zone = fbm2_region<FBM_CAVE_CHECK>(nt, &sm, px, py, cave_cuts, evals) == 1;
+    unsigned cnt = 0;
+    if (cave_zone) {  // TerrainTypeGenerator::sample (terrain_type.rs:26-32), as in gen_columns_kernel
+        const double n1 = fbm2<FBM_HEIGHT1>(nt, &sm, px, py), n2 = fbm2<FBM_HEIGHT2>(nt, &sm, px, py);
+        double value = fmax(n1, n2);
+        value = value < 0.1 ? 0.1 : (value > 1.0 ? 1.0 : value);
+        const double height_mod = 1.0 - (fbm2<FBM_HEIGHT_MOD>(nt, &sm, px, py) + 1.0) / 2.0;
+        const unsigned H = f64_as_u32(height_mod * value * 0.55 * 128.0) + 32u;
+        const unsigned top = H < CAVE_MAX_ZI - 1 ? H : CAVE_MAX_ZI - 1;
+        cnt = top >= CAVE_MIN_ZI ? top - CAVE_MIN_ZI + 1 : 0;
+    }
+    const unsigned n = __popc(__ballot_sync(0xFFFFFFFFu, cave_zone));
+    const unsigned v = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if ((tid & 31) == 0 && n) {
+        atomicAdd(&s_n[0], n);
+        atomicAdd(&s_n[1], v);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        columns[blockIdx.x] = s_n[0];
+        if (voxels) voxels[blockIdx.x] = s_n[1];
+    }
+}
+
 // ------------------------------------------------------------------------------------------- diag
 // DADD + DMUL issue-rate probe: 8 independent chains per thread, one add and one multiply per
 // chain per step, nothing contractable (-fmad=false).  2 * 8 * iters ops per thread.
@@ -964,6 +1013,12 @@ void launch_column_heights(const uint4* jobs, int n, const uint8_t* pool_voxels,
                            cudaStream_t stream) {
     if (n <= 0) return;
     column_heights_kernel<<<n, 256, 0, stream>>>(jobs, pool_voxels, pool_heights, slot_xy, pool_planes);
+}
+
+void launch_cave_columns(const NoiseTables& nt, const uint2* area_xy, int n, uint32_t* columns, uint32_t* voxels,
+                         cudaStream_t stream) {
+    if (n <= 0) return;
+    cave_columns_kernel<<<n, 256, 0, stream>>>(nt, area_xy, columns, voxels);
 }
 
 void launch_fp64_rate(double* sink, int blocks, int iters, cudaStream_t stream) {

@@ -134,6 +134,8 @@ void launch_light_relax(const uint4* jobs, int n, const uint8_t* pool_voxels, Ar
                         cudaStream_t stream);
 
 // ---- diagnostics
+void launch_cave_columns(const NoiseTables& nt, const uint2* area_xy, int n, uint32_t* columns, uint32_t* voxels,
+                         cudaStream_t stream);
 void launch_fp64_rate(double* sink, int blocks, int iters, cudaStream_t stream);
 
 }  // namespace vx
