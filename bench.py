@@ -537,6 +537,26 @@ def main():
                 ec.sync()
                 return recs_n, faces_n, dirty_n
 
+            # the water simulator's tick on the device: every lake surface voxel of the region
+            # whose sides are loaded, as one ordered check list -- a sequential chain by construction
+            a_i, l_i = np.nonzero(vox0 == 14)  # WaterSource
+            wx = ex0 * 16 + (a_i % n_side) * 16 + (l_i & 15)
+            wy = ey0 * 16 + (a_i // n_side) * 16 + ((l_i >> 4) & 15)
+            wz = l_i >> 8
+            inside = (wx > ex0 * 16) & (wx < (ex0 + n_side) * 16 - 1) & (wy > ey0 * 16) & (wy < (ey0 + n_side) * 16 - 1)
+            wcheck = np.stack([wx, wy, wz], axis=1)[inside][:4000].astype(np.uint32)
+            water = None
+            if len(wcheck):
+                ec.water_tick(wcheck[:64])
+                t0 = time.perf_counter()
+                wchanged, wnext = ec.water_tick(wcheck)
+                wwall = time.perf_counter() - t0
+                water = {"locations": int(len(wcheck)), "ms": wwall * 1e3, "us_per_location": wwall * 1e6 / len(wcheck),
+                         "changed": int(len(wchanged)), "queued_for_next_tick": int(len(wnext)),
+                         "note": "vx_water_tick over the lake-surface sources of the region in array order: one thread "
+                                 "applies the reference's loop body location by location (the order is an input); "
+                                 "latency-bound by construction"}
+
             half = n_edits // 2
             storm(0, 3 * batch, True)
             torch.cuda.synchronize()
@@ -556,6 +576,7 @@ def main():
                                 "d2h_bytes_per_edit": (r_n * 16 + f_n * 172) / inc_edits,
                                 "note": "end to end, wall clock: vx_apply_edits + vx_update_locations + vx_update_read "
                                         "(records, vertices, indices of the <= 7 voxels per edit in host memory)"},
+                "water_tick": water,
                 "remesh_dirty_areas": {"ms_per_batch": re_wall * 1e3 / (re_edits // batch), "edits_per_s": re_edits / re_wall,
                                        "areas_per_batch": d_n / (re_edits // batch), "faces_per_edit": f2_n / re_edits,
                                        "note": "round 1's form: vx_apply_edits + vx_mesh of the dirty areas, meshes stay on the device"},

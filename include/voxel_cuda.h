@@ -221,6 +221,39 @@ int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_are
 int vx_explode(vx_ctx* ctx, const float* positions, int n, uint32_t* removed_xyz, int* n_removed,
                uint32_t* bomb_xyz, int* n_bombs, uint32_t* dirty_area_xy, int* n_dirty);
 
+/* ---- water and falling voxels: the world-mutating loops of WaterSimulator::simulate_voxels
+ * (service/physics/water_simulator.rs:55-77 with check_flow_stopped :79-108, flow_down :184-206,
+ * flow_sides :110-150), FallingVoxelSimulator::update_voxels (falling_voxel_simulator.rs:105-150,
+ * recursion included) and the retain pass of simulate_falling (:152-166, retain_or_place_voxel
+ * :189-221).  These loops mutate the world while they iterate -- the water tick over a HashSet, whose
+ * order std randomises per process -- so THE ORDER IS AN INPUT: the caller passes its locations in the
+ * order its own iteration yields them and the device applies them one after the other exactly as the
+ * reference's loop body does.  Given the same order the result is the reference's.  Every world.set
+ * lands in the resident voxels, column heights and bit planes; the changed locations come back in
+ * order and go to vx_update_locations (renderer.update_location after every set).  Coordinates are
+ * internal (InternalLocation), z < 128.  The areas of every location and of its four side neighbours
+ * must be resident (checked up front: VX_ERR_NOT_LOADED and nothing changes).
+ *   vx_water_tick     check_xyz: the tick's check_locations (mem::take), n triples.
+ *                     changed_xyzv: x, y, z, new voxel per world.set (room for 4 * n quadruples);
+ *                     next_xyz: the locations inserted into the NEXT tick's check_locations, in insertion
+ *                     order, duplicates included -- the caller's set dedups (room for 7 * n triples).
+ *   vx_falling_check  check_xyz: the locations update_voxels is called with, in call order.
+ *                     spawned_xyzv: x, y, z, voxel of every falling entity created (= voxel removed;
+ *                     position = the location, velocity 0), in creation order; water_next_xyz: what
+ *                     water_simulator.location_updated inserted.  A chain can empty whole columns:
+ *                     the caller states the capacities in entries; VX_ERR_INVALID if one is too small
+ *                     (what was applied until then stays applied and is reported).
+ *   vx_falling_land   after the caller has advanced its entities (velocity += delta * 0.2, capped at
+ *                     3; position.z += velocity): positions (player coordinates, 3 floats each) and
+ *                     voxel types in Vec order.  keep[i] = 1: the entity keeps falling; placed_xyzv:
+ *                     the voxels put down (room for n quadruples); water_next_xyz as above (7 * n). */
+int vx_water_tick(vx_ctx* ctx, const uint32_t* check_xyz, int n, uint32_t* changed_xyzv, int* n_changed,
+                  uint32_t* next_xyz, int* n_next);
+int vx_falling_check(vx_ctx* ctx, const uint32_t* check_xyz, int n, uint32_t* spawned_xyzv, int cap_spawned,
+                     int* n_spawned, uint32_t* water_next_xyz, int cap_next, int* n_next);
+int vx_falling_land(vx_ctx* ctx, const float* positions, const uint8_t* voxel_types, int n, uint8_t* keep,
+                    uint32_t* placed_xyzv, int* n_placed, uint32_t* water_next_xyz, int* n_next);
+
 /* ---- height map: replaces HeightMap::generate_height_map's pixel loop (height_map.rs:41-85).
  * rgba is the persistent 512*512*4 pixel buffer (stale pixels persist, as in the reference);
  * areas with |dx| or |dy| >= 16 from the camera area are skipped (height_map.rs:90-101);

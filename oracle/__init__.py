@@ -183,6 +183,13 @@ def lib():
         L.vgo_area_files_encode.argtypes = [u8p, C.c_int, C.c_int, u8p, C.POINTER(C.c_long)]
         L.vgo_area_file_decode.restype = C.c_int
         L.vgo_area_file_decode.argtypes = [u8p, C.c_long, u8p]
+        lp = C.POINTER(C.c_long)
+        L.vgo_water_tick.restype = C.c_int
+        L.vgo_water_tick.argtypes = [C.POINTER(_World), u32p, C.c_int, u32p, lp, u32p, lp]
+        L.vgo_falling_check.restype = C.c_int
+        L.vgo_falling_check.argtypes = [C.POINTER(_World), u32p, C.c_int, u32p, C.c_long, lp, u32p, C.c_long, lp]
+        L.vgo_falling_land.restype = C.c_int
+        L.vgo_falling_land.argtypes = [C.POINTER(_World), C.POINTER(C.c_float), u8p, C.c_int, u8p, u32p, lp, u32p, lp]
         L.vgo_explode.restype = C.c_int
         L.vgo_explode.argtypes = [C.POINTER(_World), C.POINTER(C.c_float), C.c_int, u32p, C.POINTER(C.c_long),
                                   u32p, C.POINTER(C.c_long)]
@@ -476,6 +483,42 @@ class World:
                              C.byref(nr), _p(bombs, C.c_uint32), C.byref(nb)) != 0:
             raise ValueError("explosion reaches outside the loaded grid")
         return removed[: nr.value].copy(), bombs[: nb.value].copy()
+
+    def water_tick(self, check_xyz):
+        """WaterSimulator::simulate_voxels over an ORDERED list -> (changed [k,4], next [m,3])."""
+        loc = np.ascontiguousarray(check_xyz, np.uint32).reshape(-1, 3)
+        n = loc.shape[0]
+        changed = np.zeros((max(4 * n, 1), 4), np.uint32)
+        nxt = np.zeros((max(7 * n, 1), 3), np.uint32)
+        nc, nn = C.c_long(0), C.c_long(0)
+        if lib().vgo_water_tick(C.byref(self._w), _p(loc, C.c_uint32), n, _p(changed, C.c_uint32), C.byref(nc),
+                                _p(nxt, C.c_uint32), C.byref(nn)) != 0:
+            raise ValueError("water tick reaches outside the loaded grid")
+        return changed[: nc.value].copy(), nxt[: nn.value].copy()
+
+    def falling_check(self, check_xyz, cap_spawned=1 << 16, cap_next=7 << 16):
+        loc = np.ascontiguousarray(check_xyz, np.uint32).reshape(-1, 3)
+        spawned = np.zeros((cap_spawned, 4), np.uint32)
+        nxt = np.zeros((cap_next, 3), np.uint32)
+        ns, nn = C.c_long(0), C.c_long(0)
+        rc = lib().vgo_falling_check(C.byref(self._w), _p(loc, C.c_uint32), loc.shape[0], _p(spawned, C.c_uint32), cap_spawned,
+                                     C.byref(ns), _p(nxt, C.c_uint32), cap_next, C.byref(nn))
+        if rc != 0:
+            raise ValueError(f"falling check failed ({rc})")
+        return spawned[: ns.value].copy(), nxt[: nn.value].copy()
+
+    def falling_land(self, positions, voxel_types):
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        types = np.ascontiguousarray(voxel_types, np.uint8).reshape(-1)
+        n = pos.shape[0]
+        keep = np.zeros(max(n, 1), np.uint8)
+        placed = np.zeros((max(n, 1), 4), np.uint32)
+        nxt = np.zeros((max(7 * n, 1), 3), np.uint32)
+        npl, nn = C.c_long(0), C.c_long(0)
+        if lib().vgo_falling_land(C.byref(self._w), pos.ctypes.data_as(C.POINTER(C.c_float)), _p(types), n, _p(keep),
+                                  _p(placed, C.c_uint32), C.byref(npl), _p(nxt, C.c_uint32), C.byref(nn)) != 0:
+            raise ValueError("falling voxel outside the loaded grid")
+        return keep[:n].copy(), placed[: npl.value].copy(), nxt[: nn.value].copy()
 
     def light_flood(self) -> np.ndarray:
         light = np.zeros_like(self.voxels)

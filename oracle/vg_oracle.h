@@ -249,6 +249,13 @@ long vgo_area_files_encode(const uint8_t* voxels, int n, int threads, uint8_t* o
  * BombSimulator::handle_explosions / explode_at (bomb_simulator.rs:191-262).  removed / bombs need
  * room for 3 * 1331 * n words. */
 #define VGO_EXPLOSION_CANDIDATES 1331 /* (2 * ceil(4.5) + 1)^3 */
+/* water / falling-voxel simulators as functions of ORDERED lists (physics.c) */
+int vgo_water_tick(vgo_world* w, const uint32_t* check, int n, uint32_t* changed, long* n_changed, uint32_t* next,
+                   long* n_next);
+int vgo_falling_check(vgo_world* w, const uint32_t* check, int n, uint32_t* spawned, long cap_spawned, long* n_spawned,
+                      uint32_t* water_next, long cap_next, long* n_next);
+int vgo_falling_land(vgo_world* w, const float* positions, const uint8_t* types, int n, uint8_t* keep, uint32_t* placed,
+                     long* n_placed, uint32_t* water_next, long* n_next);
 int vgo_explode(vgo_world* w, const float* positions, int n, uint32_t* removed, long* n_removed,
                 uint32_t* bombs, long* n_bombs);
 

@@ -94,6 +94,12 @@ extern "C" {
     pub fn vx_hash_world_name(world_name: *const c_char) -> u64;
     pub fn vx_cave_columns(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, cave_columns_out: *mut u32,
                            cave_voxels_out: *mut u32) -> c_int;
+    pub fn vx_water_tick(ctx: *mut vx_ctx, check_xyz: *const u32, n: c_int, changed_xyzv: *mut u32, n_changed: *mut c_int,
+                         next_xyz: *mut u32, n_next: *mut c_int) -> c_int;
+    pub fn vx_falling_check(ctx: *mut vx_ctx, check_xyz: *const u32, n: c_int, spawned_xyzv: *mut u32, cap_spawned: c_int,
+                            n_spawned: *mut c_int, water_next_xyz: *mut u32, cap_next: c_int, n_next: *mut c_int) -> c_int;
+    pub fn vx_falling_land(ctx: *mut vx_ctx, positions: *const f32, voxel_types: *const u8, n: c_int, keep: *mut u8,
+                           placed_xyzv: *mut u32, n_placed: *mut c_int, water_next_xyz: *mut u32, n_next: *mut c_int) -> c_int;
     pub fn vx_noise_variant() -> c_int;
     pub fn vx_set_gradient_order(ctx: *mut vx_ctx, order2: *const u8, order3: *const u8) -> c_int;
     pub fn vx_generate(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, voxels_out: *mut u8,
@@ -384,6 +390,61 @@ impl Pipeline {
         let mut packed = vec![0u32; info.n_recs as usize];
         self.check(unsafe { vx_mesh_read_compact(self.ctx, rec_first.as_mut_ptr(), packed.as_mut_ptr()) })?;
         Ok((rec_first, packed))
+    }
+
+    /// Body of `WaterSimulator::simulate_voxels` (service/physics/water_simulator.rs:55-77): `check` is
+    /// `mem::take(&mut self.check_locations)` drained into a Vec -- the order of that Vec is the order
+    /// applied.  Returns (changed: x, y, z, new voxel -> `update_locations`; next: what to insert into
+    /// `self.check_locations`).
+    #[allow(clippy::type_complexity)]
+    pub fn water_tick(&self, check: &[[u32; 3]]) -> Result<(Vec<[u32; 4]>, Vec<[u32; 3]>), VxError> {
+        let n = check.len();
+        let flat: Vec<u32> = check.iter().flatten().copied().collect();
+        let mut changed = vec![0u32; 16 * n.max(1)];
+        let mut next = vec![0u32; 21 * n.max(1)];
+        let (mut nc, mut nn) = (0 as c_int, 0 as c_int);
+        self.check(unsafe {
+            vx_water_tick(self.ctx, flat.as_ptr(), n as c_int, changed.as_mut_ptr(), &mut nc, next.as_mut_ptr(), &mut nn)
+        })?;
+        Ok((changed.chunks(4).take(nc as usize).map(|c| [c[0], c[1], c[2], c[3]]).collect(),
+            next.chunks(3).take(nn as usize).map(|c| [c[0], c[1], c[2]]).collect()))
+    }
+
+    /// Body of `FallingVoxelSimulator::update_voxels` (falling_voxel_simulator.rs:105-150) for a batch of
+    /// calls in order: the entities to create (x, y, z, voxel; position = location, velocity 0) and the
+    /// locations `water_simulator.location_updated` inserts.
+    #[allow(clippy::type_complexity)]
+    pub fn falling_check(&self, check: &[[u32; 3]], capacity: usize) -> Result<(Vec<[u32; 4]>, Vec<[u32; 3]>), VxError> {
+        let flat: Vec<u32> = check.iter().flatten().copied().collect();
+        let mut spawned = vec![0u32; 4 * capacity.max(1)];
+        let mut next = vec![0u32; 21 * capacity.max(1)];
+        let (mut ns, mut nn) = (0 as c_int, 0 as c_int);
+        self.check(unsafe {
+            vx_falling_check(self.ctx, flat.as_ptr(), check.len() as c_int, spawned.as_mut_ptr(), capacity as c_int, &mut ns,
+                             next.as_mut_ptr(), (7 * capacity) as c_int, &mut nn)
+        })?;
+        Ok((spawned.chunks(4).take(ns as usize).map(|c| [c[0], c[1], c[2], c[3]]).collect(),
+            next.chunks(3).take(nn as usize).map(|c| [c[0], c[1], c[2]]).collect()))
+    }
+
+    /// The `retain` pass of `simulate_falling` (:152-166) after the positions have been advanced:
+    /// which entities keep falling, which voxels were put down, what the water simulator is told.
+    #[allow(clippy::type_complexity)]
+    pub fn falling_land(&self, positions: &[[f32; 3]], voxel_types: &[u8]) -> Result<(Vec<bool>, Vec<[u32; 4]>, Vec<[u32; 3]>), VxError> {
+        let n = positions.len();
+        assert_eq!(voxel_types.len(), n);
+        let flat: Vec<f32> = positions.iter().flatten().copied().collect();
+        let mut keep = vec![0u8; n.max(1)];
+        let mut placed = vec![0u32; 4 * n.max(1)];
+        let mut next = vec![0u32; 21 * n.max(1)];
+        let (mut np, mut nn) = (0 as c_int, 0 as c_int);
+        self.check(unsafe {
+            vx_falling_land(self.ctx, flat.as_ptr(), voxel_types.as_ptr(), n as c_int, keep.as_mut_ptr(), placed.as_mut_ptr(),
+                            &mut np, next.as_mut_ptr(), &mut nn)
+        })?;
+        Ok((keep.into_iter().take(n).map(|k| k != 0).collect(),
+            placed.chunks(4).take(np as usize).map(|c| [c[0], c[1], c[2], c[3]]).collect(),
+            next.chunks(3).take(nn as usize).map(|c| [c[0], c[1], c[2]]).collect()))
     }
 
     /// Cost hint for sharding a region over several GPUs, from the seed alone: per area the cave-zone

@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "vx_explode", "vx_light", "vx_diag_fp64_rate", "vx_update_locations", "vx_update_read",
     "vx_mesh_read_compact", "vx_set_mesh_retention", "vx_mesh_unload", "vx_read_face_masks", "vx_visible_zone",
     "vx_lock", "vx_unlock", "vx_copy_last_error", "vx_noise_variant", "vx_set_gradient_order",
-    "vx_cave_columns",
+    "vx_cave_columns", "vx_water_tick", "vx_falling_check", "vx_falling_land",
 ]
 
 
@@ -163,6 +163,10 @@ def load():
     L.vx_host_free.restype = None
     L.vx_set_seed.argtypes = [vp, C.c_uint64]
     L.vx_cave_columns.argtypes = [vp, vp, C.c_int, vp, vp]
+    ip = C.POINTER(C.c_int)
+    L.vx_water_tick.argtypes = [vp, vp, C.c_int, vp, ip, vp, ip]
+    L.vx_falling_check.argtypes = [vp, vp, C.c_int, vp, C.c_int, ip, vp, C.c_int, ip]
+    L.vx_falling_land.argtypes = [vp, vp, vp, C.c_int, vp, vp, ip, vp, ip]
     L.vx_noise_variant.restype = C.c_int
     L.vx_noise_variant.argtypes = []
     L.vx_set_gradient_order.argtypes = [vp, vp, vp]
@@ -508,6 +512,47 @@ class Context:
         self._check(self._lib.vx_explode(self._h, pos.ctypes.data, n, removed.ctypes.data, C.byref(nr),
                                          bombs.ctypes.data, C.byref(nb), dirty.ctypes.data, C.byref(nd)))
         return removed[: nr.value].copy(), bombs[: nb.value].copy(), dirty[: nd.value].copy()
+
+    # -- water / falling voxels (ordered lists, applied one location after the other)
+    def water_tick(self, check_xyz):
+        """WaterSimulator::simulate_voxels over check_xyz [n,3] in this order -> (changed [k,4] u32:
+        x, y, z, new voxel; next [m,3] u32: insertions into the next tick's check_locations)."""
+        loc = np.ascontiguousarray(check_xyz, np.uint32).reshape(-1, 3)
+        n = loc.shape[0]
+        changed = np.zeros((max(4 * n, 1), 4), np.uint32)
+        nxt = np.zeros((max(7 * n, 1), 3), np.uint32)
+        nc, nn = C.c_int(0), C.c_int(0)
+        st = self._lib.vx_water_tick(self._h, loc.ctypes.data, n, changed.ctypes.data, C.byref(nc), nxt.ctypes.data, C.byref(nn))
+        self._check(st)
+        return changed[: nc.value].copy(), nxt[: nn.value].copy()
+
+    def falling_check(self, check_xyz, cap_spawned: int = 1 << 16, cap_next: int = 7 << 16):
+        """FallingVoxelSimulator::update_voxels for each of check_xyz [n,3] in order -> (spawned [k,4]:
+        x, y, z, voxel of every entity created; water_next [m,3])."""
+        loc = np.ascontiguousarray(check_xyz, np.uint32).reshape(-1, 3)
+        spawned = np.zeros((max(cap_spawned, 1), 4), np.uint32)
+        nxt = np.zeros((max(cap_next, 1), 3), np.uint32)
+        ns, nn = C.c_int(0), C.c_int(0)
+        st = self._lib.vx_falling_check(self._h, loc.ctypes.data, loc.shape[0], spawned.ctypes.data, cap_spawned,
+                                        C.byref(ns), nxt.ctypes.data, cap_next, C.byref(nn))
+        self._check(st)
+        return spawned[: ns.value].copy(), nxt[: nn.value].copy()
+
+    def falling_land(self, positions, voxel_types):
+        """The retain pass of simulate_falling over entities in Vec order (positions already advanced)
+        -> (keep u8[n], placed [k,4] u32, water_next [m,3] u32)."""
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        types = np.ascontiguousarray(voxel_types, np.uint8).reshape(-1)
+        n = pos.shape[0]
+        assert types.shape[0] == n
+        keep = np.zeros(max(n, 1), np.uint8)
+        placed = np.zeros((max(n, 1), 4), np.uint32)
+        nxt = np.zeros((max(7 * n, 1), 3), np.uint32)
+        npl, nn = C.c_int(0), C.c_int(0)
+        st = self._lib.vx_falling_land(self._h, pos.ctypes.data, types.ctypes.data, n, keep.ctypes.data, placed.ctypes.data,
+                                       C.byref(npl), nxt.ctypes.data, C.byref(nn))
+        self._check(st)
+        return keep[:n].copy(), placed[: npl.value].copy(), nxt[: nn.value].copy()
 
     def heightmap(self, area_xy, cam_ax: int, cam_ay: int, rgba=None) -> np.ndarray:
         xy = _xy(area_xy)

@@ -567,6 +567,77 @@ int clear_mesh_slots(vx_ctx* ctx, std::vector<int>& slots) {
 }  // namespace
 
 // =========================================================================================== ABI
+namespace {
+
+// Every area a simulator loop can read for these locations (the location's own column and its four
+// sides) is resident -- checked up front, so that a call either runs whole or changes nothing.
+int sim_check_resident(vx_ctx* ctx, const uint32_t* xyz, int n, const char* who) {
+    for (int i = 0; i < n; ++i) {
+        const uint32_t x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        if (z >= (uint32_t)AREA_HEIGHT) return fail(ctx, VX_ERR_INVALID, (std::string(who) + ": z >= 128").c_str());
+        const uint32_t xs[3] = {x, x + 1, x - 1}, ys[3] = {y, y + 1, y - 1};
+        for (int k = 0; k < 3; ++k)
+            if (host_slot(ctx, xs[k] / AREA_SIZE, y / AREA_SIZE) < 0 || host_slot(ctx, x / AREA_SIZE, ys[k] / AREA_SIZE) < 0)
+                return fail(ctx, VX_ERR_NOT_LOADED, (std::string(who) + ": an area next to a location is not resident").c_str());
+    }
+    return VX_OK;
+}
+
+// Runs one of the three ordered-list kernels: `in_bytes` of input go to the device, two lists
+// (entries of a_words / 3 words) and optionally n keep bytes come back.
+struct SimCall {
+    const void* in0; size_t in0_bytes;
+    const void* in1; size_t in1_bytes;
+    uint32_t* a; int cap_a; int a_words; int* n_a;
+    uint32_t* b; int cap_b; int* n_b;
+    uint8_t* keep; int n_keep;
+};
+
+template <typename Launch>
+int run_sim(vx_ctx* ctx, const SimCall& c, Launch launch) {
+    int st;
+    if ((st = upload_map(ctx)) != VX_OK) return st;
+    if ((st = sync_stream(ctx)) != VX_OK) return st;  // d_edits may be in use by a call that did not wait
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t off_in1 = up16(c.in0_bytes), off_a = off_in1 + up16(c.in1_bytes);
+    const size_t off_b = off_a + up16((size_t)c.cap_a * c.a_words * 4), off_keep = off_b + up16((size_t)c.cap_b * 12);
+    VX_CUDA(ctx->d_edits.ensure(off_keep + up16((size_t)c.n_keep) + 16));
+    VX_CUDA(ctx->d_counters.ensure(64));
+    uint8_t* base = ctx->d_edits.as<uint8_t>();
+    VX_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
+    VX_CUDA(cudaMemcpyAsync(base, c.in0, c.in0_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (c.in1_bytes) VX_CUDA(cudaMemcpyAsync(base + off_in1, c.in1, c.in1_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t* counters = ctx->d_counters.as<uint32_t>();  // [0] entries of a, [1] entries of b, [2] status
+    {
+        ScopedTimer t(ctx, TM_EDIT);
+        launch(base, base + off_in1, reinterpret_cast<uint32_t*>(base + off_a), reinterpret_cast<uint32_t*>(base + off_b),
+               base + off_keep, counters, reinterpret_cast<int32_t*>(counters + 2));
+    }
+    ctx->timings.other_launches += 1;
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(ctx->h_small.ensure(16));
+    uint32_t* hs = ctx->h_small.as<uint32_t>();
+    VX_CUDA(cudaMemcpyAsync(hs, counters, 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((st = sync_stream(ctx)) != VX_OK) return st;
+    collect_timers(ctx);
+    const uint32_t na = hs[0], nb = hs[1];
+    const int32_t status = (int32_t)hs[2];
+    // whatever was applied before a failure stays applied and is reported, like a panic half way through
+    // the reference's loop would leave it
+    if (na) VX_CUDA(cudaMemcpyAsync(c.a, base + off_a, (size_t)na * c.a_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nb) VX_CUDA(cudaMemcpyAsync(c.b, base + off_b, (size_t)nb * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (c.n_keep) VX_CUDA(cudaMemcpyAsync(c.keep, base + off_keep, (size_t)c.n_keep, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((st = sync_stream(ctx)) != VX_OK) return st;
+    *c.n_a = (int)na;
+    *c.n_b = (int)nb;
+    if (status != 0)
+        return fail(ctx, status, status == VX_ERR_NOT_LOADED ? "simulator step reached an area that is not resident"
+                                                             : "simulator step: an output list is too small or a location is out of range");
+    return VX_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int vx_device_count(void) {
@@ -1800,6 +1871,65 @@ int vx_visible_zone(vx_ctx* ctx, const uint32_t* area_xy, int n, const vx_view* 
     ctx->frame_n_visible = info->n_visible;
     ctx->frame_ready = true;
     return VX_OK;
+}
+
+int vx_water_tick(vx_ctx* ctx, const uint32_t* check_xyz, int n, uint32_t* changed_xyzv, int* n_changed,
+                  uint32_t* next_xyz, int* n_next) {
+    if (!ctx || n < 0 || !n_changed || !n_next || (n > 0 && (!check_xyz || !changed_xyzv || !next_xyz))) return VX_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    *n_changed = *n_next = 0;
+    if (n == 0) return VX_OK;
+    int st = sim_check_resident(ctx, check_xyz, n, "vx_water_tick");
+    if (st != VX_OK) return st;
+    SimCall c{check_xyz, (size_t)n * 12, nullptr, 0, changed_xyzv, 4 * n, 4, n_changed, next_xyz, 7 * n, n_next, nullptr, 0};
+    return run_sim(ctx, c, [&](uint8_t* in0, uint8_t*, uint32_t* a, uint32_t* b, uint8_t*, uint32_t* counts, int32_t* status) {
+        launch_water_tick(reinterpret_cast<const uint32_t*>(in0), n, device_map(ctx), ctx->d_voxels, ctx->d_heights,
+                          ctx->d_planes, a, (uint32_t)(4 * n), b, (uint32_t)(7 * n), counts, status, ctx->stream);
+    });
+}
+
+int vx_falling_check(vx_ctx* ctx, const uint32_t* check_xyz, int n, uint32_t* spawned_xyzv, int cap_spawned,
+                     int* n_spawned, uint32_t* water_next_xyz, int cap_next, int* n_next) {
+    if (!ctx || n < 0 || cap_spawned < 0 || cap_next < 0 || !n_spawned || !n_next ||
+        (n > 0 && (!check_xyz || !spawned_xyzv || !water_next_xyz)))
+        return VX_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    *n_spawned = *n_next = 0;
+    if (n == 0) return VX_OK;
+    int st = sim_check_resident(ctx, check_xyz, n, "vx_falling_check");
+    if (st != VX_OK) return st;
+    SimCall c{check_xyz, (size_t)n * 12, nullptr, 0, spawned_xyzv, cap_spawned, 4, n_spawned, water_next_xyz, cap_next, n_next,
+              nullptr, 0};
+    return run_sim(ctx, c, [&](uint8_t* in0, uint8_t*, uint32_t* a, uint32_t* b, uint8_t*, uint32_t* counts, int32_t* status) {
+        launch_falling_check(reinterpret_cast<const uint32_t*>(in0), n, device_map(ctx), ctx->d_voxels, ctx->d_heights,
+                             ctx->d_planes, a, (uint32_t)cap_spawned, b, (uint32_t)cap_next, counts, status, ctx->stream);
+    });
+}
+
+int vx_falling_land(vx_ctx* ctx, const float* positions, const uint8_t* voxel_types, int n, uint8_t* keep,
+                    uint32_t* placed_xyzv, int* n_placed, uint32_t* water_next_xyz, int* n_next) {
+    if (!ctx || n < 0 || !n_placed || !n_next || (n > 0 && (!positions || !voxel_types || !keep || !placed_xyzv || !water_next_xyz)))
+        return VX_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    *n_placed = *n_next = 0;
+    if (n == 0) return VX_OK;
+    for (int i = 0; i < n; ++i) {
+        const float px = positions[3 * i], py = positions[3 * i + 1], pz = positions[3 * i + 2];
+        if (!(std::fabs(px) < 1.0e6f && std::fabs(py) < 1.0e6f && std::fabs(pz) < 1.0e6f))
+            return fail(ctx, VX_ERR_INVALID, "vx_falling_land: position out of range");
+        if (voxel_types[i] >= V_VARIANTS) return fail(ctx, VX_ERR_INVALID, "vx_falling_land: voxel id >= 27");
+        const uint32_t gx = (uint32_t)((int)std::round(px) + LOCATION_OFFSET), gy = (uint32_t)((int)std::round(py) + LOCATION_OFFSET);
+        if (host_slot(ctx, gx / AREA_SIZE, gy / AREA_SIZE) < 0)
+            return fail(ctx, VX_ERR_NOT_LOADED, "vx_falling_land: the area under a falling voxel is not resident");
+    }
+    SimCall c{positions, (size_t)n * 12, voxel_types, (size_t)n, placed_xyzv, n, 4, n_placed, water_next_xyz, 7 * n, n_next, keep, n};
+    return run_sim(ctx, c, [&](uint8_t* in0, uint8_t* in1, uint32_t* a, uint32_t* b, uint8_t* d_keep, uint32_t* counts, int32_t* status) {
+        launch_falling_land(reinterpret_cast<const float*>(in0), in1, n, device_map(ctx), ctx->d_voxels, ctx->d_heights,
+                            ctx->d_planes, d_keep, a, (uint32_t)n, b, (uint32_t)(7 * n), counts, status, ctx->stream);
+    });
 }
 
 int vx_cave_columns(vx_ctx* ctx, const uint32_t* area_xy, int n, uint32_t* cave_columns_out, uint32_t* cave_voxels_out) {

@@ -134,6 +134,16 @@ void launch_light_relax(const uint4* jobs, int n, const uint8_t* pool_voxels, Ar
                         cudaStream_t stream);
 
 // ---- diagnostics
+// vx_sim.cu: the world-mutating loops of the water / falling-voxel simulators, one ordered list each
+void launch_water_tick(const uint32_t* check, int n, AreaMap map, uint8_t* voxels, uint8_t* heights, uint16_t* planes,
+                       uint32_t* changed, uint32_t cap_changed, uint32_t* next, uint32_t cap_next, uint32_t* counts,
+                       int32_t* status, cudaStream_t stream);
+void launch_falling_check(const uint32_t* check, int n, AreaMap map, uint8_t* voxels, uint8_t* heights, uint16_t* planes,
+                          uint32_t* spawned, uint32_t cap_spawned, uint32_t* next, uint32_t cap_next, uint32_t* counts,
+                          int32_t* status, cudaStream_t stream);
+void launch_falling_land(const float* positions, const uint8_t* types, int n, AreaMap map, uint8_t* voxels,
+                         uint8_t* heights, uint16_t* planes, uint8_t* keep, uint32_t* placed, uint32_t cap_placed,
+                         uint32_t* next, uint32_t cap_next, uint32_t* counts, int32_t* status, cudaStream_t stream);
 void launch_cave_columns(const NoiseTables& nt, const uint2* area_xy, int n, uint32_t* columns, uint32_t* voxels,
                          cudaStream_t stream);
 void launch_fp64_rate(double* sink, int blocks, int iters, cudaStream_t stream);
