@@ -55,6 +55,19 @@ def test_mesh_stream_byte_exact(ctx, seed):
     assert info["n_faces"] == base
 
 
+def test_mesh_stream_byte_exact_config2_region(ctx, seed):
+    """The whole 32 x 32 region of config 2 (1 024 areas, ~600 000 faces, caves, lakes, trees, all three
+    biomes): records, vertices and indices of every area equal the oracle's stream byte for byte, in
+    the reference's order.  (At config-3 size the mesh is checked through sampled face counts and
+    properties, test_full_size_128x128_properties.)"""
+    n = 32
+    ax0, ay0 = SPAWN - 16, SPAWN - 16
+    world = oracle.World.generate(seed, ax0 - 1, ay0 - 1, n + 2, n + 2)
+    ctx.generate(vg.region_xy(ax0 - 1, ay0 - 1, n + 2, n + 2), read=False)
+    faces = _compare_mesh(ctx, world, vg.region_xy(ax0, ay0, n, n))
+    assert faces > 400_000
+
+
 def _compare_mesh(ctx, world, xy):
     info = ctx.mesh(xy)
     rec_first, face_first, recs, verts, idx = ctx.mesh_read(info)
