@@ -553,9 +553,9 @@ def main():
                 wwall = time.perf_counter() - t0
                 water = {"locations": int(len(wcheck)), "ms": wwall * 1e3, "us_per_location": wwall * 1e6 / len(wcheck),
                          "changed": int(len(wchanged)), "queued_for_next_tick": int(len(wnext)),
-                         "note": "vx_water_tick over the lake-surface sources of the region in array order: one thread "
-                                 "applies the reference's loop body location by location (the order is an input); "
-                                 "latency-bound by construction"}
+                         "note": "vx_water_tick over the lake-surface sources of the region in array order: one warp "
+                                 "applies the reference's loop body location by location (the order is an input), its "
+                                 "lanes fetching the seven voxels side by side; latency-bound by construction"}
 
             half = n_edits // 2
             storm(0, 3 * batch, True)

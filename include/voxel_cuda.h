@@ -176,6 +176,11 @@ int vx_read_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_o
  * ignored. */
 int vx_unload(vx_ctx* ctx, const uint32_t* area_xy, int n);
 int vx_resident_count(vx_ctx* ctx);
+/* The resident-area pool: slots allocated, device memory behind them, and whether the pool arrays are
+ * virtual-memory ranges that grow by mapping more physical memory (no copy, stable pointers; DESIGN.md
+ * 3) or -- on a driver without that API -- plain allocations that grow by allocate-copy-free.  Any
+ * pointer may be NULL. */
+int vx_pool_info(vx_ctx* ctx, uint64_t* capacity_areas, uint64_t* committed_bytes, int* virtual_memory);
 
 /* Area::update_all_column_heights (area.rs:34-44) as a stand-alone operator on host data. */
 int vx_column_heights(vx_ctx* ctx, const uint8_t* voxels, int n, uint8_t* max_height_out);

@@ -110,6 +110,7 @@ extern "C" {
                          max_height_out: *mut u8) -> c_int;
     pub fn vx_unload(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int) -> c_int;
     pub fn vx_resident_count(ctx: *mut vx_ctx) -> c_int;
+    pub fn vx_pool_info(ctx: *mut vx_ctx, capacity_areas: *mut u64, committed_bytes: *mut u64, virtual_memory: *mut c_int) -> c_int;
     pub fn vx_column_heights(ctx: *mut vx_ctx, voxels: *const u8, n: c_int, max_height_out: *mut u8) -> c_int;
     pub fn vx_mesh(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, info: *mut vx_mesh_info) -> c_int;
     pub fn vx_mesh_read(ctx: *mut vx_ctx, rec_first: *mut u32, face_first: *mut u32,

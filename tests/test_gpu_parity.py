@@ -733,3 +733,31 @@ def test_cave_columns_cost_hint_equals_is_cave_zone(ctx, seed):
     t = ctx.timings()
     assert t["cave_columns"] == int(cols.sum()) and t["cave_voxels"] == int(vox.sum())
     ctx.set_timing(False)
+
+
+def test_pool_grows_in_place_by_mapping_memory(seed):
+    """The resident-area pool is a set of virtual-memory ranges on B200: growth maps more physical
+    memory behind them -- resident areas keep their bytes (nothing is copied, nothing moves) and the
+    committed size follows the capacity instead of doubling past it."""
+    with vg.Context(0, seed=seed) as c:
+        info0 = c.pool_info()
+        assert info0["virtual_memory"], "the CUDA virtual-memory API is available on every B200 driver"
+        assert info0["capacity_areas"] == 0 and info0["committed_bytes"] == 0
+        first = vg.region_xy(100, 200, 20, 20)
+        vox0, mh0 = c.generate(first)
+        c.set_mesh_retention(True)
+        c.mesh(vg.region_xy(101, 201, 18, 18))
+        masks0, _ = c.read_face_masks(first)
+        caps = [c.pool_info()["capacity_areas"]]
+        for k in range(1, 6):  # each batch forces the pool to grow
+            c.generate(vg.region_xy(1000 * k, 300, 40 * k, 40), read=False)
+            caps.append(c.pool_info()["capacity_areas"])
+        assert caps == sorted(caps) and caps[-1] > 4 * caps[0]
+        vox1, mh1 = c.read_areas(first)
+        masks1, _ = c.read_face_masks(first)
+        assert np.array_equal(vox0, vox1) and np.array_equal(mh0, mh1) and np.array_equal(masks0, masks1)
+        info = c.pool_info()
+        per_area = 32768 + 256 + 8192 + 8 + 32768 + 1
+        assert info["committed_bytes"] < info["capacity_areas"] * per_area + 6 * (64 << 20)
+        c.set_mesh_retention(False)  # the face masks' physical memory goes back to the driver
+        assert c.pool_info()["committed_bytes"] < info["committed_bytes"]

@@ -48,6 +48,7 @@ ABI_SYMBOLS = [
     "vx_mesh_read_compact", "vx_set_mesh_retention", "vx_mesh_unload", "vx_read_face_masks", "vx_visible_zone",
     "vx_lock", "vx_unlock", "vx_copy_last_error", "vx_noise_variant", "vx_set_gradient_order",
     "vx_cave_columns", "vx_water_tick", "vx_falling_check", "vx_falling_land",
+    "vx_pool_info",
 ]
 
 
@@ -177,6 +178,7 @@ def load():
     L.vx_read_areas.argtypes = [vp, vp, C.c_int, vp, vp]
     L.vx_unload.argtypes = [vp, vp, C.c_int]
     L.vx_resident_count.argtypes = [vp]
+    L.vx_pool_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
     L.vx_column_heights.argtypes = [vp, vp, C.c_int, vp]
     L.vx_mesh.argtypes = [vp, vp, C.c_int, C.POINTER(MeshInfo)]
     L.vx_mesh_read.argtypes = [vp, vp, vp, vp, vp, vp]
@@ -390,6 +392,11 @@ class Context:
     def unload(self, area_xy):
         xy = _xy(area_xy)
         self._check(self._lib.vx_unload(self._h, xy.ctypes.data, xy.shape[0]))
+
+    def pool_info(self) -> dict:
+        cap, committed, virt = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        self._check(self._lib.vx_pool_info(self._h, C.byref(cap), C.byref(committed), C.byref(virt)))
+        return {"capacity_areas": int(cap.value), "committed_bytes": int(committed.value), "virtual_memory": bool(virt.value)}
 
     def resident_count(self) -> int:
         return int(self._lib.vx_resident_count(self._h))

@@ -9,12 +9,114 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>  // types and prototypes of the virtual-memory API; the entry points are fetched at run time
+
 #include "../../include/voxel_cuda.h"
 #include "vx_kernels.hpp"
 
 using namespace vx;
 
 namespace {
+
+// ---- growable pool arrays -----------------------------------------------------------------------
+// The resident-area pool (voxels, heights, planes, slot_xy, face masks) grows while a world streams in.
+// Growing by allocate-copy-free needs twice the pool for a moment (10 GiB at config 5), a device sync,
+// and moves every pointer.  Instead each array reserves a range of VIRTUAL addresses once (64 GiB of
+// voxels = 2 M areas, nothing is committed) and physical memory is mapped behind what is in use, chunk
+// by chunk (CUDA virtual memory management: cuMemAddressReserve / cuMemCreate / cuMemMap): growth
+// copies nothing, waits for nothing, and the base pointers never change.  The driver entry points are
+// resolved through the runtime (cudaGetDriverEntryPoint), so the library does not link libcuda.
+struct VmApi {
+    decltype(&cuMemGetAllocationGranularity) granularity = nullptr;
+    decltype(&cuMemAddressReserve) reserve = nullptr;
+    decltype(&cuMemAddressFree) address_free = nullptr;
+    decltype(&cuMemCreate) create = nullptr;
+    decltype(&cuMemRelease) release = nullptr;
+    decltype(&cuMemMap) map = nullptr;
+    decltype(&cuMemUnmap) unmap = nullptr;
+    decltype(&cuMemSetAccess) set_access = nullptr;
+    bool ok = false;
+    bool load() {
+        auto get = [](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess &&
+                   q == cudaDriverEntryPointSuccess && *fn != nullptr;
+        };
+        ok = get("cuMemGetAllocationGranularity", (void**)&granularity) && get("cuMemAddressReserve", (void**)&reserve) &&
+             get("cuMemAddressFree", (void**)&address_free) && get("cuMemCreate", (void**)&create) &&
+             get("cuMemRelease", (void**)&release) && get("cuMemMap", (void**)&map) && get("cuMemUnmap", (void**)&unmap) &&
+             get("cuMemSetAccess", (void**)&set_access);
+        if (!ok) cudaGetLastError();
+        return ok;
+    }
+};
+
+struct VmArray {
+    CUdeviceptr base = 0;
+    size_t reserved = 0, mapped = 0, chunk = 0;
+    std::vector<CUmemGenericAllocationHandle> handles;
+    template <class T> T* as() const { return reinterpret_cast<T*>(base); }
+    // chunk_hint: physical memory is committed in pieces of about this size (a multiple of the granularity)
+    bool reserve(const VmApi& api, int device, size_t max_bytes, size_t chunk_hint) {
+        CUmemAllocationProp prop = {};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = device;
+        size_t gran = 0;
+        if (api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0) return false;
+        chunk = ((std::max(chunk_hint, gran) + gran - 1) / gran) * gran;
+        reserved = ((max_bytes + chunk - 1) / chunk) * chunk;
+        if (api.reserve(&base, reserved, 0, 0, 0) != CUDA_SUCCESS) {
+            base = 0;
+            reserved = 0;
+            return false;
+        }
+        return true;
+    }
+    // at least `bytes` are backed by physical memory afterwards; new memory is not initialised
+    cudaError_t grow(const VmApi& api, int device, size_t bytes) {
+        if (bytes > reserved) return cudaErrorMemoryAllocation;
+        while (mapped < bytes) {
+            CUmemAllocationProp prop = {};
+            prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+            prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+            prop.location.id = device;
+            CUmemGenericAllocationHandle h;
+            if (api.create(&h, chunk, &prop, 0) != CUDA_SUCCESS) return cudaErrorMemoryAllocation;
+            if (api.map(base + mapped, chunk, 0, h, 0) != CUDA_SUCCESS) {
+                api.release(h);
+                return cudaErrorMemoryAllocation;
+            }
+            CUmemAccessDesc access = {};
+            access.location = prop.location;
+            access.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+            if (api.set_access(base + mapped, chunk, &access, 1) != CUDA_SUCCESS) {
+                api.unmap(base + mapped, chunk);
+                api.release(h);
+                return cudaErrorMemoryAllocation;
+            }
+            handles.push_back(h);
+            mapped += chunk;
+        }
+        return cudaSuccess;
+    }
+    void unmap_all(const VmApi& api) {  // the reservation stays
+        for (size_t i = 0; i < handles.size(); ++i) {
+            api.unmap(base + i * chunk, chunk);
+            api.release(handles[i]);
+        }
+        handles.clear();
+        mapped = 0;
+    }
+    void destroy(const VmApi& api) {
+        if (!base) return;
+        unmap_all(api);
+        api.address_free(base, reserved);
+        base = 0;
+        reserved = 0;
+    }
+};
+constexpr size_t VM_MAX_AREAS = size_t(1) << 21;  // 2 M areas: 64 GiB of voxels, more than a B200 holds
 
 struct DevBuf {  // grow-only device scratch buffer (contents not preserved on growth)
     void* p = nullptr;
@@ -173,6 +275,11 @@ struct vx_ctx {
     bool retention = false;
     uint8_t* d_face = nullptr;
     uint8_t* d_meshed = nullptr;
+    // the six pool arrays above as growable virtual-memory ranges (VmArray); vmm == false (the driver
+    // lacks the API): plain cudaMalloc arrays that grow by allocate-copy-free
+    VmApi vm;
+    bool vmm = false;
+    VmArray vm_voxels, vm_heights, vm_planes, vm_xy, vm_face, vm_meshed;
     std::vector<uint64_t> slot_key;    // per slot; ~0 = free
     std::vector<int> free_slots;
     HostAreaMap index;
@@ -333,6 +440,33 @@ int sync_stream(vx_ctx* ctx) {
 int grow_pool(vx_ctx* ctx, int min_capacity) {
     if (min_capacity <= ctx->capacity) return VX_OK;
     int new_cap = std::max({min_capacity, ctx->capacity * 2, 256});
+    if (ctx->vmm) {
+        // map more physical memory behind the arrays: no copy, no wait, no pointer changes.  Growth is
+        // geometric only up to 64 Ki areas a step, the rest of the GPU is not claimed ahead of need.
+        new_cap = std::max(min_capacity, std::min(new_cap, ctx->capacity + 65536));
+        if ((size_t)new_cap > VM_MAX_AREAS) return fail(ctx, VX_ERR_OOM, "more than 2 M resident areas");
+        const size_t c = (size_t)new_cap;
+        cudaError_t e = ctx->vm_voxels.grow(ctx->vm, ctx->device, c * VOXELS_IN_AREA);
+        if (e == cudaSuccess) e = ctx->vm_heights.grow(ctx->vm, ctx->device, c * COLUMNS_IN_AREA);
+        if (e == cudaSuccess) e = ctx->vm_planes.grow(ctx->vm, ctx->device, c * 4096 * sizeof(uint16_t));
+        if (e == cudaSuccess) e = ctx->vm_xy.grow(ctx->vm, ctx->device, c * sizeof(uint2));
+        if (e == cudaSuccess && ctx->retention) {
+            const size_t old_face = (size_t)ctx->capacity * VOXELS_IN_AREA;
+            e = ctx->vm_face.grow(ctx->vm, ctx->device, c * VOXELS_IN_AREA);
+            if (e == cudaSuccess) e = ctx->vm_meshed.grow(ctx->vm, ctx->device, c);
+            // slots that have never been meshed hold an empty mesh
+            if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_face + old_face, 0, c * VOXELS_IN_AREA - old_face, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_meshed + ctx->capacity, 0, c - (size_t)ctx->capacity, ctx->stream);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, VX_ERR_OOM, "pool growth: out of device memory");  // what was mapped stays mapped: harmless
+        }
+        ctx->slot_key.resize(new_cap, ~0ull);
+        for (int s = new_cap - 1; s >= ctx->capacity; --s) ctx->free_slots.push_back(s);  // pop -> ascending
+        ctx->capacity = new_cap;
+        return VX_OK;
+    }
     uint8_t *nv = nullptr, *nh = nullptr, *nf = nullptr, *nm = nullptr;
     uint16_t* np = nullptr;
     uint2* nxy = nullptr;
@@ -702,6 +836,27 @@ int vx_create(int device, vx_ctx** out) {
         vx_destroy(ctx);
         return VX_ERR_CUDA;
     }
+    // the pool arrays as virtual-memory ranges (see VmArray); without the API: cudaMalloc arrays
+    if (ctx->vm.load()) {
+        const size_t big = size_t(64) << 20, small = size_t(2) << 20;
+        ctx->vmm = ctx->vm_voxels.reserve(ctx->vm, device, VM_MAX_AREAS * VOXELS_IN_AREA, big) &&
+                   ctx->vm_heights.reserve(ctx->vm, device, VM_MAX_AREAS * COLUMNS_IN_AREA, small) &&
+                   ctx->vm_planes.reserve(ctx->vm, device, VM_MAX_AREAS * 4096 * sizeof(uint16_t), big / 4) &&
+                   ctx->vm_xy.reserve(ctx->vm, device, VM_MAX_AREAS * sizeof(uint2), small) &&
+                   ctx->vm_face.reserve(ctx->vm, device, VM_MAX_AREAS * VOXELS_IN_AREA, big) &&
+                   ctx->vm_meshed.reserve(ctx->vm, device, VM_MAX_AREAS, small);
+        if (ctx->vmm) {
+            ctx->d_voxels = ctx->vm_voxels.as<uint8_t>();
+            ctx->d_heights = ctx->vm_heights.as<uint8_t>();
+            ctx->d_planes = ctx->vm_planes.as<uint16_t>();
+            ctx->d_slot_xy = ctx->vm_xy.as<uint2>();
+            ctx->d_face = ctx->vm_face.as<uint8_t>();
+            ctx->d_meshed = ctx->vm_meshed.as<uint8_t>();
+        } else {
+            for (VmArray* a : {&ctx->vm_voxels, &ctx->vm_heights, &ctx->vm_planes, &ctx->vm_xy, &ctx->vm_face, &ctx->vm_meshed})
+                a->destroy(ctx->vm);
+        }
+    }
     *out = ctx;
     return VX_OK;
 }
@@ -710,8 +865,13 @@ void vx_destroy(vx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
-    cudaFree(ctx->d_face); cudaFree(ctx->d_meshed);
+    if (ctx->vmm) {
+        for (VmArray* a : {&ctx->vm_voxels, &ctx->vm_heights, &ctx->vm_planes, &ctx->vm_xy, &ctx->vm_face, &ctx->vm_meshed})
+            a->destroy(ctx->vm);
+    } else {
+        cudaFree(ctx->d_voxels); cudaFree(ctx->d_heights); cudaFree(ctx->d_planes); cudaFree(ctx->d_slot_xy);
+        cudaFree(ctx->d_face); cudaFree(ctx->d_meshed);
+    }
     cudaFree(ctx->d_noise_image);
     DevBuf* bufs[] = {&ctx->d_map, &ctx->d_map_patch, &ctx->d_jobs, &ctx->d_gen_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters, &ctx->d_gen_counters,
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
@@ -959,6 +1119,23 @@ int vx_unload(vx_ctx* ctx, const uint32_t* area_xy, int n) {
         ++ctx->index_version;
         // keep hand-out order ascending so later batches stay contiguous where possible
         std::sort(ctx->free_slots.begin(), ctx->free_slots.end(), std::greater<int>());
+    }
+    return VX_OK;
+}
+
+int vx_pool_info(vx_ctx* ctx, uint64_t* capacity_areas, uint64_t* committed_bytes, int* virtual_memory) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    if (capacity_areas) *capacity_areas = (uint64_t)ctx->capacity;
+    if (virtual_memory) *virtual_memory = ctx->vmm ? 1 : 0;
+    if (committed_bytes) {
+        if (ctx->vmm) {
+            *committed_bytes = ctx->vm_voxels.mapped + ctx->vm_heights.mapped + ctx->vm_planes.mapped + ctx->vm_xy.mapped +
+                               ctx->vm_face.mapped + ctx->vm_meshed.mapped;
+        } else {
+            const uint64_t per_area = VOXELS_IN_AREA + COLUMNS_IN_AREA + 8192 + 8 + (ctx->retention ? VOXELS_IN_AREA + 1 : 0);
+            *committed_bytes = (uint64_t)ctx->capacity * per_area;
+        }
     }
     return VX_OK;
 }
@@ -1584,7 +1761,23 @@ int vx_set_mesh_retention(vx_ctx* ctx, int enabled) {
     if (on == ctx->retention) return VX_OK;
     int st;
     if ((st = sync_stream(ctx)) != VX_OK) return st;
-    if (on) {
+    if (ctx->vmm) {
+        if (on && ctx->capacity > 0) {
+            cudaError_t e = ctx->vm_face.grow(ctx->vm, ctx->device, (size_t)ctx->capacity * VOXELS_IN_AREA);
+            if (e == cudaSuccess) e = ctx->vm_meshed.grow(ctx->vm, ctx->device, (size_t)ctx->capacity);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                ctx->vm_face.unmap_all(ctx->vm);
+                ctx->vm_meshed.unmap_all(ctx->vm);
+                return fail(ctx, VX_ERR_OOM, "mesh retention allocation");
+            }
+            VX_CUDA(cudaMemsetAsync(ctx->d_face, 0, (size_t)ctx->capacity * VOXELS_IN_AREA, ctx->stream));
+            VX_CUDA(cudaMemsetAsync(ctx->d_meshed, 0, (size_t)ctx->capacity, ctx->stream));
+        } else if (!on) {  // give the physical memory back, keep the address range
+            ctx->vm_face.unmap_all(ctx->vm);
+            ctx->vm_meshed.unmap_all(ctx->vm);
+        }
+    } else if (on) {
         if (ctx->capacity > 0) {
             VX_CUDA(cudaMalloc(&ctx->d_face, (size_t)ctx->capacity * VOXELS_IN_AREA));
             cudaError_t e = cudaMalloc(&ctx->d_meshed, (size_t)ctx->capacity);

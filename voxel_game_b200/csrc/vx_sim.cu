@@ -10,10 +10,11 @@
 //
 // These loops mutate the world WHILE they iterate, the water tick over a HashSet: the outcome depends
 // on the iteration order, which std randomises per process.  So the order is an INPUT here: the caller
-// hands over its locations in the order its own iteration yields them and ONE thread applies them one
-// after the other, exactly as the reference's loop body does -- given the same order, the same world.
-// That makes these kernels latency-bound by construction (a chain of dependent voxel reads per
-// location, microseconds each); what they buy is residency, not throughput: the edits land in the
+// hands over its locations in the order its own iteration yields them and they are applied one after
+// the other, exactly as the reference's loop body does -- given the same order, the same world (the
+// water tick runs as one warp whose lanes fetch a location's seven voxels side by side; the falling
+// loops as one thread).  That makes these kernels latency-bound by construction (a dependent memory
+// round trip per location, microseconds each); what they buy is residency, not throughput: the edits land in the
 // device's voxels, planes and column heights, and the list of changed locations goes straight into
 // vx_update_locations (the reference calls renderer.update_location after every set).
 #include "vx_kernels.hpp"
@@ -124,34 +125,48 @@ __device__ __forceinline__ int water_level(uint32_t v) {
     return v == V_NONE ? 0 : 1000;
 }
 
-__global__ void water_tick_kernel(const uint32_t* __restrict__ check, int n, SimWorld w, List changed, List next,
-                                  uint32_t* __restrict__ counts) {
-    for (int i = 0; i < n && *w.status == 0; ++i) {
+// One warp: lane k < 7 fetches the k-th voxel of the location's neighbourhood (itself, the four sides,
+// up, down), so a location costs one round trip to memory instead of seven in a row; every lane then
+// runs the (uniform) decision, lane 0 writes.  Still one location after the other.
+__global__ void __launch_bounds__(32) water_tick_kernel(const uint32_t* __restrict__ check, int n, SimWorld w, List changed,
+                                                        List next, uint32_t* __restrict__ counts) {
+    const int lane = threadIdx.x;
+    const unsigned FULL = 0xFFFFFFFFu;
+    for (int i = 0; i < n; ++i) {
         const uint32_t x = check[3 * i], y = check[3 * i + 1], z = check[3 * i + 2];
-        uint32_t voxel;
-        if (!sim_get(w, x, y, z, voxel)) break;
+        // get_bordering's order behind the location itself: x + 1, x - 1, y + 1, y - 1, z - 1 (if z > 0), z + 1 (if it exists)
+        uint32_t mx = x, my = y, mz = z;
+        bool exists = lane < 7;
+        if (lane == 1) mx += 1u;
+        else if (lane == 2) mx -= 1u;
+        else if (lane == 3) my += 1u;
+        else if (lane == 4) my -= 1u;
+        else if (lane == 5) { exists = z > 0u; mz -= 1u; }
+        else if (lane == 6) { exists = z + 1u < (uint32_t)AREA_HEIGHT; mz += 1u; }
+        uint32_t mine = V_NONE;
+        bool ok = true;
+        if (exists) ok = sim_get(w, mx, my, mz, mine);
+        if (__any_sync(FULL, !ok)) break;  // the status is set
+        const uint32_t voxel = __shfl_sync(FULL, mine, 0);
         if (!is_water(voxel)) continue;
-        // get_bordering: the four sides, then up (z - 1) if z > 0, then down (z + 1) if it exists
-        const uint32_t bx[4] = {x + 1, x - 1, x, x}, by[4] = {y, y, y + 1, y - 1};
         uint32_t bv[6], bz[6];
-        int nb = 0;
-        bool has_down = false, ok = true;
-        uint32_t down = V_NONE;
-        for (int k = 0; k < 4 && ok; ++k, ++nb) {
-            ok = sim_get(w, bx[k], by[k], z, bv[nb]);
-            bz[nb] = z;
+        int nb = 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bv[k] = __shfl_sync(FULL, mine, k + 1);
+            bz[k] = z;
         }
-        if (ok && z > 0u) {
-            ok = sim_get(w, x, y, z - 1u, bv[nb]);
+        const uint32_t up = __shfl_sync(FULL, mine, 5), down = __shfl_sync(FULL, mine, 6);
+        const bool has_down = z + 1u < (uint32_t)AREA_HEIGHT;
+        if (z > 0u) {
+            bv[nb] = up;
             bz[nb++] = z - 1u;
         }
-        if (ok && z + 1u < (uint32_t)AREA_HEIGHT) {
-            ok = sim_get(w, x, y, z + 1u, bv[nb]);
-            bz[nb] = z + 1u;
-            down = bv[nb++];
-            has_down = true;
+        if (has_down) {
+            bv[nb] = down;
+            bz[nb++] = z + 1u;
         }
-        if (!ok) break;
+        const uint32_t bx[4] = {x + 1, x - 1, x, x}, by[4] = {y, y, y + 1, y - 1};
         // check_flow_stopped
         bool stopped = voxel != V_WATER_SOURCE;
         if (stopped) {
@@ -164,32 +179,34 @@ __global__ void water_tick_kernel(const uint32_t* __restrict__ check, int n, Sim
                 }
             }
         }
-        if (stopped) {
-            sim_set(w, x, y, z, V_NONE);
-            push4(changed, x, y, z, V_NONE);
-            water_location_updated(next, x, y, z);
-            continue;
+        if (lane == 0) {
+            if (stopped) {
+                sim_set(w, x, y, z, V_NONE);
+                push4(changed, x, y, z, V_NONE);
+                water_location_updated(next, x, y, z);
+            } else if (has_down && (down == V_NONE || (down != V_WATER_SOURCE && is_water(down)))) {  // flow_down
+                sim_set(w, x, y, z + 1u, V_WATER_DOWN);
+                push4(changed, x, y, z + 1u, V_WATER_DOWN);
+                push3(next, x, y, z + 1u);
+            } else if (!(voxel == V_WATER4 || !has_down || (is_water(down) && down != V_WATER_SOURCE))) {
+                // flow_sides, on the bordering voxels as they were read above
+                const int level = water_level(voxel);
+                const uint32_t lower = voxel <= V_WATER_DOWN ? (uint32_t)V_WATER1 : voxel + 1u;  // reduce_water_level
+                for (int k = 0; k < 4; ++k) {
+                    if (level <= water_level(bv[k])) continue;
+                    sim_set(w, bx[k], by[k], z, lower);
+                    push4(changed, bx[k], by[k], z, lower);
+                    push3(next, bx[k], by[k], z);
+                }
+            }
         }
-        // flow_down
-        if (has_down && (down == V_NONE || (down != V_WATER_SOURCE && is_water(down)))) {
-            sim_set(w, x, y, z + 1u, V_WATER_DOWN);
-            push4(changed, x, y, z + 1u, V_WATER_DOWN);
-            push3(next, x, y, z + 1u);
-            continue;
-        }
-        // flow_sides, on the bordering voxels as they were read above
-        if (voxel == V_WATER4 || !has_down || (is_water(down) && down != V_WATER_SOURCE)) continue;
-        const int level = water_level(voxel);
-        const uint32_t lower = voxel <= V_WATER_DOWN ? (uint32_t)V_WATER1 : voxel + 1u;  // reduce_water_level
-        for (int k = 0; k < 4; ++k) {
-            if (level <= water_level(bv[k])) continue;
-            sim_set(w, bx[k], by[k], z, lower);
-            push4(changed, bx[k], by[k], z, lower);
-            push3(next, bx[k], by[k], z);
-        }
+        __syncwarp();  // lane 0's writes are visible to the lanes that read the next location
+        if (__shfl_sync(FULL, (int)(*changed.status != 0 && lane == 0), 0)) break;  // an output list overflowed
     }
-    counts[0] = changed.n;
-    counts[1] = next.n;
+    if (lane == 0) {
+        counts[0] = changed.n;
+        counts[1] = next.n;
+    }
 }
 
 // update_voxels recurses into the voxel above every voxel it drops; the recursion sits inside the loop
@@ -295,7 +312,7 @@ SimWorld make_world(AreaMap map, uint8_t* voxels, uint8_t* heights, uint16_t* pl
 void launch_water_tick(const uint32_t* check, int n, AreaMap map, uint8_t* voxels, uint8_t* heights, uint16_t* planes,
                        uint32_t* changed, uint32_t cap_changed, uint32_t* next, uint32_t cap_next, uint32_t* counts,
                        int32_t* status, cudaStream_t stream) {
-    water_tick_kernel<<<1, 1, 0, stream>>>(check, n, make_world(map, voxels, heights, planes, status),
+    water_tick_kernel<<<1, 32, 0, stream>>>(check, n, make_world(map, voxels, heights, planes, status),
                                            List{changed, 0u, cap_changed, status}, List{next, 0u, cap_next, status}, counts);
 }
 
