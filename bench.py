@@ -420,6 +420,24 @@ def main():
                  "visible_voxels": vis["n_visible"], "visible_faces": vis["n_faces"],
                  "records_per_s": recs_in_view / (f_ms * 1e-3), "algorithmic_bytes": frame_bytes}
 
+    # ---- L-ext (north star only; the reference has no voxel light): the max(neighbour - 1) relaxation
+    # over the 32x32 areas around the spawn, levels 0..15 per voxel
+    light = None
+    if world == 1 and extras:
+        lx0, ly0, _, _ = vg.spawn_region(32)
+        lxy = vg.region_xy(lx0, ly0, 32, 32)
+        ctx.set_timing(True)
+        ctx.light(lxy)
+        ctx.timings()
+        levels, l_iters = ctx.light(lxy)
+        l_ms = ctx.timings()["light_ms"]
+        light = {"areas": len(lxy), "ms": l_ms, "launches": l_iters + 2, "chunks_per_s": len(lxy) / (l_ms * 1e-3),
+                 "lit_voxels": int((levels > 0).sum()),
+                 "algorithmic_bytes": len(lxy) * (32768 * 2 + 256 + (l_iters) * (3 * 32768 + 4 * 2048)),
+                 "note": "extension, no reference parity (oracle/light_ext.c is the spec): init + one relaxation launch "
+                         "per round until no area changes; each launch relaxes every area to its own fixed point in "
+                         "shared memory with a one-voxel halo"}
+
     # ---- save files (K8 / K9; not part of `value`): kernel times of the encoder and the decoder
     codec = None
     if world == 1 and extras:
@@ -789,6 +807,9 @@ def main():
         line["frame"] = frame
     if edit_storm is not None:
         line["edit_storm"] = edit_storm
+    if light is not None:
+        light["roofline"] = hbm_roof(light["algorithmic_bytes"], light["ms"])
+        line["light_ext"] = light
     if codec is not None:
         codec["encode_roofline"] = hbm_roof(n_gen * 32768 + codec["file_bytes_total"], codec["encode_ms"])
         codec["decode_roofline"] = hbm_roof(n_gen * (32768 + 8192 + 256) + codec["file_bytes_total"], codec["decode_ms"])
