@@ -544,14 +544,15 @@ def main():
             def storm(lo_, hi_, incremental):
                 recs_n = faces_n = dirty_n = 0
                 for b0 in range(lo_, hi_, batch):
-                    d = ec.apply_edits(edits[b0:b0 + batch])
                     if incremental:
+                        ec.apply_edits(edits[b0:b0 + batch], want_dirty=False)
                         di, _r, _v, _i = ec.update_locations(locs[b0:b0 + batch])
                         recs_n += di["n_recs"]
                         faces_n += di["n_faces"]
                     else:
+                        d = ec.apply_edits(edits[b0:b0 + batch])
                         faces_n += ec.mesh(d)["n_faces"]
-                    dirty_n += len(d)
+                        dirty_n += len(d)
                 ec.sync()
                 return recs_n, faces_n, dirty_n
 

@@ -206,7 +206,9 @@ int vx_mesh_read(vx_ctx* ctx, uint32_t* rec_first, uint32_t* face_first, vx_voxe
  * height upkeep) for a batch applied in array order (later edits win), and reports the areas whose
  * meshes Renderer::update_location (renderer.rs:239-286) would have touched: the edited area plus
  * the edge neighbour when the edit is on a border column.  The caller then re-runs vx_mesh on
- * dirty_area_xy.  dirty_area_xy must have room for 3*n pairs; all edited areas must be resident. */
+ * dirty_area_xy (room for 3*n pairs) -- or passes dirty_area_xy = n_dirty = NULL and follows up with
+ * vx_update_locations, the exact incremental form, which needs no dirty list: the call then returns as
+ * soon as its kernels are enqueued.  All edited areas must be resident. */
 int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_area_xy,
                    int* n_dirty);
 

@@ -128,7 +128,12 @@ def test_update_locations_reproduce_the_enclosed_water_quirk(seed):
             before = world.face_mask.copy()
             for e in edits:
                 world.apply_edit(int(e["gx"]), int(e["gy"]), int(e["gz"]), int(e["voxel"]))
-            ctx.apply_edits(edits)
+            if batch_no % 2:  # the form that only enqueues (no dirty list): the caller's array may be reused at once
+                scratch = edits.copy()
+                assert ctx.apply_edits(scratch, want_dirty=False) is None
+                scratch[:] = 0
+            else:
+                ctx.apply_edits(edits)
             locs = np.stack([gx, gy, gz], axis=1).astype(np.uint32)
             info, recs, verts, idx = ctx.update_locations(locs)
             assert info["n_recs"] == len(recs) and info["n_faces"] * 4 == len(verts)

@@ -498,10 +498,14 @@ class Context:
         return out, idx, flags
 
     # -- edits
-    def apply_edits(self, edits) -> np.ndarray:
-        """World::set for a batch (array order). Returns the dirty areas as [k,2] u32."""
+    def apply_edits(self, edits, want_dirty: bool = True):
+        """World::set for a batch (array order). Returns the dirty areas as [k,2] u32, or None with
+        want_dirty=False (the call then only enqueues; follow up with update_locations)."""
         e = np.ascontiguousarray(edits, dtype=EDIT_DTYPE)
         n = e.shape[0]
+        if not want_dirty:
+            self._check(self._lib.vx_apply_edits(self._h, e.ctypes.data, n, None, None))
+            return None
         dirty = np.empty((max(3 * n, 1), 2), np.uint32)
         nd = C.c_int(0)
         self._check(self._lib.vx_apply_edits(self._h, e.ctypes.data, n, dirty.ctypes.data, C.byref(nd)))

@@ -254,6 +254,10 @@ struct vx_ctx {
     // encoder (codec_ev), not for a vx_mesh enqueued after it
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t codec_ev = nullptr;
+    // vx_apply_edits that does not wait: the batch is staged in pinned memory of the context's own
+    PinnedBuf h_edits;
+    cudaEvent_t edits_ev = nullptr;
+    bool edits_pending = false;
     std::recursive_mutex mu;  // recursive: vx_lock / vx_unlock bracket several calls of one thread
     std::string last_error;
 
@@ -821,7 +825,8 @@ int vx_create(int device, vx_ctx** out) {
     }
     ctx->stream = ctx->own_stream;
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->codec_ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->codec_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->edits_ev, cudaEventDisableTiming) != cudaSuccess) {
         cudaStreamDestroy(ctx->own_stream);
         delete ctx;
         return VX_ERR_CUDA;
@@ -894,6 +899,8 @@ void vx_destroy(vx_ctx* ctx) {
     for (int i = 0; i < TM_COUNT; ++i)
         for (int k = 0; k < 2; ++k) cudaEventDestroy(ctx->ev[i][k]);
     cudaEventDestroy(ctx->codec_ev);
+    cudaEventDestroy(ctx->edits_ev);
+    ctx->h_edits.release();
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -1540,10 +1547,10 @@ int vx_visible_read(vx_ctx* ctx, uint32_t* rec_index, uint8_t* area_visible) {
 }
 
 int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_area_xy, int* n_dirty) {
-    if (!ctx || n < 0 || (n > 0 && (!edits || !dirty_area_xy)) || !n_dirty) return VX_ERR_INVALID;
+    if (!ctx || n < 0 || (n > 0 && !edits) || (dirty_area_xy && !n_dirty)) return VX_ERR_INVALID;
     std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     VX_CUDA(cudaSetDevice(ctx->device));
-    *n_dirty = 0;
+    if (n_dirty) *n_dirty = 0;
     if (n == 0) return VX_OK;
     for (int i = 0; i < n; ++i) {  // all-or-nothing validation (reference: world_actions.rs guards)
         if (edits[i].gz >= (uint32_t)AREA_HEIGHT || edits[i].voxel >= (uint32_t)V_VARIANTS)
@@ -1566,7 +1573,21 @@ int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_are
     VX_CUDA(cudaMemsetAsync(ctx->d_dirty_flags.p, 0, (size_t)ctx->capacity * 4, ctx->stream));
     VX_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
     static_assert(sizeof(vx_edit) == sizeof(uint4), "vx_edit layout");
-    VX_CUDA(cudaMemcpyAsync(ctx->d_edits.p, edits, (size_t)n * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+    const void* edits_src = edits;
+    if (!dirty_area_xy) {  // the call will not wait: the caller's array must not be read after it returns
+        if (ctx->edits_pending) {
+            VX_CUDA(cudaEventSynchronize(ctx->edits_ev));
+            ctx->edits_pending = false;
+        }
+        VX_CUDA(ctx->h_edits.ensure((size_t)n * sizeof(uint4)));
+        std::memcpy(ctx->h_edits.p, edits, (size_t)n * sizeof(uint4));
+        edits_src = ctx->h_edits.p;
+    }
+    VX_CUDA(cudaMemcpyAsync(ctx->d_edits.p, edits_src, (size_t)n * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+    if (!dirty_area_xy) {
+        VX_CUDA(cudaEventRecord(ctx->edits_ev, ctx->stream));
+        ctx->edits_pending = true;
+    }
     uint32_t* counters = ctx->d_counters.as<uint32_t>();
     {
         ScopedTimer t(ctx, TM_EDIT);
@@ -1577,15 +1598,17 @@ int vx_apply_edits(vx_ctx* ctx, const vx_edit* edits, int n, uint32_t* dirty_are
     }
     ctx->timings.other_launches += 3;
     VX_CUDA(cudaGetLastError());
-    VX_CUDA(ctx->h_small.ensure(16 + (size_t)ctx->capacity * 4));
+    // No dirty list wanted (the caller follows up with vx_update_locations, which needs none): everything
+    // was validated on the host, so the call returns with the kernels enqueued, like vx_generate.
+    if (!dirty_area_xy) return VX_OK;
+    // the counters and as many dirty slots as the batch can have produced, in one wait
+    const size_t max_dirty = std::min<size_t>((size_t)3 * n, (size_t)ctx->capacity);
+    VX_CUDA(ctx->h_small.ensure(16 + max_dirty * 4));
     uint32_t* hs = ctx->h_small.as<uint32_t>();
     VX_CUDA(cudaMemcpyAsync(hs, counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    VX_CUDA(cudaStreamSynchronize(ctx->stream));
-    const uint32_t nd = hs[0];
-    if (nd) {
-        VX_CUDA(cudaMemcpyAsync(hs + 4, ctx->d_dirty_slots.p, (size_t)nd * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    }
+    VX_CUDA(cudaMemcpyAsync(hs + 4, ctx->d_dirty_slots.p, max_dirty * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if ((st = sync_stream(ctx)) != VX_OK) return st;
+    const uint32_t nd = hs[0];
     std::vector<uint32_t> ds(hs + 4, hs + 4 + nd);
     std::sort(ds.begin(), ds.end());  // deterministic order
     for (uint32_t i = 0; i < nd; ++i) {

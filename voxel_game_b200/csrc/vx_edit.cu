@@ -95,18 +95,29 @@ __global__ void edits_apply_kernel(const uint4* __restrict__ edits, int n, AreaM
     if (ly == AREA_SIZE - 1) flag_dirty(area_slot(map, ax, ay + 1), dirty_flags, dirty_slots, dirty_count);
 }
 
-__global__ void edits_heights_kernel(const uint4* __restrict__ edits, int n, AreaMap map,
-                                     const uint8_t* __restrict__ pool_voxels, uint8_t* pool_heights) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per edit: lane l looks at z = l, l + 32, l + 64, l + 96 of the edited column (four
+// independent loads), a ballot per group finds the first voxel from the top that is not transparent.
+// (One thread per edit walked the column as 128 dependent loads, 70 us per batch of 1 000.)
+__global__ void __launch_bounds__(256) edits_heights_kernel(const uint4* __restrict__ edits, int n, AreaMap map,
+                                                            const uint8_t* __restrict__ pool_voxels,
+                                                            uint8_t* pool_heights) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n) return;
     const uint4 e = edits[i];
     const Located l = locate(e, map);
     if (l.slot < 0) return;
     const uint32_t col = l.local & 255u;
     const uint8_t* vox = pool_voxels + (size_t)l.slot * VOXELS_IN_AREA + col;
-    int z = 0;
-    while (z < AREA_HEIGHT && is_transparent(vox[256 * z])) ++z;
-    pool_heights[(size_t)l.slot * COLUMNS_IN_AREA + col] = (uint8_t)(z < AREA_HEIGHT ? z : AREA_HEIGHT - 1);
+    bool opaque[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) opaque[g] = !is_transparent(vox[256 * (32 * g + lane)]);
+    int z = AREA_HEIGHT - 1;  // calculate_column_height: nothing opaque -> AREA_HEIGHT - 1 (area.rs:46-56)
+#pragma unroll
+    for (int g = 3; g >= 0; --g) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, opaque[g]);
+        if (m) z = 32 * g + __ffs(m) - 1;
+    }
+    if (lane == 0) pool_heights[(size_t)l.slot * COLUMNS_IN_AREA + col] = (uint8_t)z;
 }
 
 // ------------------------------------------------------------------------------ explosions
@@ -293,7 +304,7 @@ void launch_apply_edits(const uint4* edits, int n, AreaMap map, uint8_t* pool_vo
     edits_apply_kernel<<<blocks, 256, 0, stream>>>(edits, n, map, pool_voxels, pool_planes, hash_keys, hash_vals,
                                                    hash_cap - 1, dirty_flags, dirty_slots,
                                                    dirty_count);
-    edits_heights_kernel<<<blocks, 256, 0, stream>>>(edits, n, map, pool_voxels, pool_heights);
+    edits_heights_kernel<<<(n + 7) / 8, 256, 0, stream>>>(edits, n, map, pool_voxels, pool_heights);
 }
 
 void launch_explode(const float* positions, int n, AreaMap map, uint8_t* pool_voxels, uint8_t* pool_heights,
