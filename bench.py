@@ -576,6 +576,23 @@ def main():
                                  "applies the reference's loop body location by location (the order is an input), its "
                                  "lanes fetching the seven voxels side by side; latency-bound by construction"}
 
+            # the per-frame pass over the RESIDENT meshes of a render zone (mesh retention: nothing is re-meshed
+            # when the zone slides or an edit lands): render distance 31 around the spawn = 63 x 63 areas
+            zone = vg.render_zone(vg.world.SPAWN_AREA, 31)
+            zview = vg.make_view((8.0, 8.0, 58.0), (9.0, 8.5, 59.0), render_size=31)
+            ec.set_timing(True)
+            for _ in range(3):
+                zinfo = ec.visible_zone(zone, zview, read=False)
+            ec.timings()
+            z_ms = 0.0
+            for _ in range(10):
+                zinfo = ec.visible_zone(zone, zview, read=False)
+                z_ms += ec.timings()["visible_ms"]
+            ec.set_timing(False)
+            zone_frame = {"ms": z_ms / 10, "zone_areas": int(len(zone)), "visible_areas": zinfo["n_areas"],
+                          "visible_voxels": zinfo["n_visible"], "visible_faces": zinfo["n_faces"],
+                          "note": "vx_visible_zone over the retained face-mask volumes of the zone (32 KiB per visible area)"}
+
             half = n_edits // 2
             storm(0, 3 * batch, True)
             torch.cuda.synchronize()
@@ -596,6 +613,7 @@ def main():
                                 "note": "end to end, wall clock: vx_apply_edits + vx_update_locations + vx_update_read "
                                         "(records, vertices, indices of the <= 7 voxels per edit in host memory)"},
                 "water_tick": water,
+                "zone_frame": zone_frame,
                 "remesh_dirty_areas": {"ms_per_batch": re_wall * 1e3 / (re_edits // batch), "edits_per_s": re_edits / re_wall,
                                        "areas_per_batch": d_n / (re_edits // batch), "faces_per_edit": f2_n / re_edits,
                                        "note": "round 1's form: vx_apply_edits + vx_mesh of the dirty areas, meshes stay on the device"},

@@ -314,7 +314,7 @@ struct vx_ctx {
     DevBuf d_gen_counters;  // cave work list size + work accounting of vx_generate; no other call touches it
     DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
     DevBuf d_heightmap, d_light, d_slot_to_job, d_finished, d_warp_totals, d_mesh_nbr;
-    DevBuf d_mesh_xy, d_frame_flags, d_frame_counts, d_frame_small, d_frame_visible;  // per-frame visibility (K7)
+    DevBuf d_mesh_xy, d_frame_flags, d_frame_counts, d_frame_small, d_frame_visible, d_frame_codes;  // per-frame visibility (K7)
     DevBuf d_codec_sizes, d_codec_offsets, d_codec_bytes, d_codec_status, d_codec_kinds;  // area save files (K8 / K9)
     // incremental updates (vx_update_locations) and the compact record transport
     DevBuf d_upd_xyz, d_upd_slot, d_upd_info, d_upd_rec_count, d_upd_face_count, d_upd_rec_first, d_upd_face_first;
@@ -883,7 +883,7 @@ void vx_destroy(vx_ctx* ctx) {
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
                       &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_warp_totals, &ctx->d_mesh_nbr, &ctx->d_mesh_xy, &ctx->d_frame_flags,
                       &ctx->d_frame_counts, &ctx->d_frame_small, &ctx->d_frame_visible, &ctx->d_codec_sizes,
-                      &ctx->d_codec_offsets, &ctx->d_codec_bytes, &ctx->d_codec_status, &ctx->d_codec_kinds, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
+                      &ctx->d_frame_codes, &ctx->d_codec_offsets, &ctx->d_codec_bytes, &ctx->d_codec_status, &ctx->d_codec_kinds, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
                       &ctx->d_vertices, &ctx->d_indices, &ctx->d_upd_xyz, &ctx->d_upd_slot, &ctx->d_upd_info,
                       &ctx->d_upd_rec_count, &ctx->d_upd_face_count, &ctx->d_upd_rec_first, &ctx->d_upd_face_first,
                       &ctx->d_upd_recs, &ctx->d_upd_vertices, &ctx->d_upd_indices, &ctx->d_packed, &ctx->d_zone_xy,
@@ -1491,6 +1491,7 @@ int vx_visible(vx_ctx* ctx, const vx_view* view, vx_visible_info* info) {
     VX_CUDA(ctx->d_frame_flags.ensure((size_t)n));
     VX_CUDA(ctx->d_frame_counts.ensure((size_t)28 * n * 4));
     VX_CUDA(ctx->d_frame_visible.ensure(std::max<size_t>(16, n_recs * 4)));
+    VX_CUDA(ctx->d_frame_codes.ensure(std::max<size_t>(16, n_recs)));
     const bool fresh = ctx->d_frame_small.p == nullptr;
     VX_CUDA(ctx->d_frame_small.ensure(sizeof(FrameTotals) + 32 * 4));
     VX_CUDA(ctx->h_small.ensure(sizeof(FrameTotals)));
@@ -1510,7 +1511,7 @@ int vx_visible(vx_ctx* ctx, const vx_view* view, vx_visible_info* info) {
         ScopedTimer t(ctx, TM_VISIBLE);
         launch_frame_visible(ctx->d_recs.as<uint4>(), ctx->d_rec_first.as<uint32_t>(), ctx->d_mesh_xy.as<uint2>(), n, fv,
                              ctx->d_frame_flags.as<uint8_t>(), ctx->d_frame_counts.as<uint32_t>(), row_total, done,
-                             totals, ctx->d_frame_visible.as<uint32_t>(), ctx->stream);
+                             totals, ctx->d_frame_visible.as<uint32_t>(), ctx->d_frame_codes.as<uint8_t>(), ctx->stream);
         ctx->timings.other_launches += 4;
     }
     VX_CUDA(cudaGetLastError());

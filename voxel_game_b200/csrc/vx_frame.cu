@@ -90,7 +90,8 @@ __global__ void frame_areas_kernel(const uint2* __restrict__ area_xy, int n, Fra
 // lamp records of area i (all of them, drawn or not: RenderArea.lights, renderer.rs:60-67).
 __global__ void __launch_bounds__(32 * AREAS_PER_CTA)
 frame_count_kernel(const uint4* __restrict__ recs, const uint32_t* __restrict__ rec_first, int n, FrameView v,
-                   const uint8_t* __restrict__ area_flag, uint32_t* __restrict__ counts, FrameTotals* totals) {
+                   const uint8_t* __restrict__ area_flag, uint32_t* __restrict__ counts, FrameTotals* totals,
+                   uint8_t* __restrict__ codes) {
     __shared__ uint32_t hist[AREAS_PER_CTA][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int i = blockIdx.x * AREAS_PER_CTA + wid;
@@ -108,6 +109,9 @@ frame_count_kernel(const uint4* __restrict__ recs, const uint32_t* __restrict__ 
             const bool drawn = in && voxel_drawn(rec, v, max_distance);
             lamps += (in && voxel == V_LAMP) ? 1u : 0u;
             faces += drawn ? rec.z >> 24 : 0u;
+            // what the scatter pass needs of this record, so that it reads one byte instead of sixteen
+            // and repeats none of the arithmetic: voxel type | 0x80 if it is not drawn
+            if (in) codes[q] = (uint8_t)(voxel | (drawn ? 0u : 0x80u));
             const uint32_t key = drawn ? voxel : 31u;
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
             if (drawn && lane == __ffs(peers) - 1) hist[wid][voxel] += __popc(peers);
@@ -134,10 +138,16 @@ __global__ void __launch_bounds__(1024) frame_scan_kernel(uint32_t* __restrict__
     uint32_t* row = counts + (size_t)blockIdx.x * n;
     if (tid == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + tid;
-        const uint32_t c = i < n ? row[i] : 0u;
-        uint32_t inc = c;
+    constexpr int PER = 16;  // consecutive entries per thread: 16 384 areas are one round
+    for (int base = 0; base < n; base += 1024 * PER) {
+        const int i0 = base + tid * PER;
+        uint32_t c[PER], mine = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            c[k] = i0 + k < n ? row[i0 + k] : 0u;
+            mine += c[k];
+        }
+        uint32_t inc = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
@@ -155,10 +165,14 @@ __global__ void __launch_bounds__(1024) frame_scan_kernel(uint32_t* __restrict__
             s_w[lane] = w;
         }
         __syncthreads();
-        const uint32_t before = carry + (wid ? s_w[wid - 1] : 0u) + inc - c;
-        if (i < n) row[i] = before;
+        uint32_t run = carry + (wid ? s_w[wid - 1] : 0u) + inc - mine;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            if (i0 + k < n) row[i0 + k] = run;
+            run += c[k];
+        }
         __syncthreads();
-        if (tid == 1023) carry = before + c;
+        if (tid == 1023) carry = run;
         __syncthreads();
     }
     if (tid == 0) {
@@ -180,10 +194,11 @@ __global__ void __launch_bounds__(1024) frame_scan_kernel(uint32_t* __restrict__
     }
 }
 
-// Same walk as the count kernel; every drawn record's index goes to its slot: type group, then area
-// order, then record order (deterministic; the reference's order inside a group is HashMap order).
+// The walk of the count kernel over its one-byte codes; every drawn record's index goes to its slot:
+// type group, then area order, then record order (deterministic; the reference's order inside a group
+// is HashMap order).
 __global__ void __launch_bounds__(32 * AREAS_PER_CTA)
-frame_scatter_kernel(const uint4* __restrict__ recs, const uint32_t* __restrict__ rec_first, int n, FrameView v,
+frame_scatter_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ rec_first, int n,
                      const uint8_t* __restrict__ area_flag, const uint32_t* __restrict__ counts,
                      FrameTotals* totals, uint32_t* __restrict__ visible) {
     __shared__ uint32_t cursor[AREAS_PER_CTA][32];
@@ -193,13 +208,12 @@ frame_scatter_kernel(const uint4* __restrict__ recs, const uint32_t* __restrict_
     if (lane < TYPES) cursor[wid][lane] = totals->type_first[lane] + counts[(size_t)lane * n + i];
     uint32_t lamp_cursor = counts[(size_t)TYPES * n + i];
     __syncwarp();
-    const float max_distance = (float)(v.render_size * AREA_SIZE);
     const uint32_t q0 = rec_first[i], q1 = rec_first[i + 1];
     for (uint32_t q = q0 + lane; q - lane < q1; q += 32) {
         const bool in = q < q1;
-        const uint4 rec = in ? recs[q] : make_uint4(0, 0, 0, 0);
-        const uint32_t voxel = (rec.z >> 8) & 0xFFu;
-        const bool drawn = in && voxel_drawn(rec, v, max_distance);
+        const uint32_t code = in ? codes[q] : 0xFFu;
+        const uint32_t voxel = code & 0x7Fu;
+        const bool drawn = in && !(code & 0x80u);
         const uint32_t key = drawn ? voxel : 31u;
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
         const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
@@ -354,14 +368,13 @@ zone_scatter_kernel(const uint2* __restrict__ area_xy, int n, const int32_t* __r
 
 void launch_frame_visible(const uint4* recs, const uint32_t* rec_first, const uint2* area_xy, int n,
                           const FrameView& view, uint8_t* area_flag, uint32_t* counts, uint32_t* row_total,
-                          uint32_t* done, FrameTotals* totals, uint32_t* visible, cudaStream_t stream) {
+                          uint32_t* done, FrameTotals* totals, uint32_t* visible, uint8_t* codes, cudaStream_t stream) {
     if (n <= 0) return;
     frame_areas_kernel<<<(n + 255) / 256, 256, 0, stream>>>(area_xy, n, view, area_flag, totals);
     const int ctas = (n + AREAS_PER_CTA - 1) / AREAS_PER_CTA;
-    frame_count_kernel<<<ctas, 32 * AREAS_PER_CTA, 0, stream>>>(recs, rec_first, n, view, area_flag, counts, totals);
+    frame_count_kernel<<<ctas, 32 * AREAS_PER_CTA, 0, stream>>>(recs, rec_first, n, view, area_flag, counts, totals, codes);
     frame_scan_kernel<<<TYPES + 1, 1024, 0, stream>>>(counts, n, totals, row_total, done);
-    frame_scatter_kernel<<<ctas, 32 * AREAS_PER_CTA, 0, stream>>>(recs, rec_first, n, view, area_flag, counts, totals,
-                                                                  visible);
+    frame_scatter_kernel<<<ctas, 32 * AREAS_PER_CTA, 0, stream>>>(codes, rec_first, n, area_flag, counts, totals, visible);
 }
 
 }  // namespace vx

@@ -69,7 +69,7 @@ struct FrameTotals {  // zero n_faces / n_areas before the launch
 // counts: 28 * n words; row_total: 28 words; done: one word, zero before the first launch
 void launch_frame_visible(const uint4* recs, const uint32_t* rec_first, const uint2* area_xy, int n,
                           const FrameView& view, uint8_t* area_flag, uint32_t* counts, uint32_t* row_total,
-                          uint32_t* done, FrameTotals* totals, uint32_t* visible, cudaStream_t stream);
+                          uint32_t* done, FrameTotals* totals, uint32_t* visible, uint8_t* codes, cudaStream_t stream);
 
 // the same frame over the device-resident mirror of Renderer.meshes (mesh retention): zone list of
 // areas, per-slot face-mask volumes; visible[] entries are zone index << 15 | x + 16 y + 256 z
