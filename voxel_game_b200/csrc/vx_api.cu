@@ -441,6 +441,27 @@ int sync_stream(vx_ctx* ctx) {
 }
 
 // ---- pool ---------------------------------------------------------------------------------
+// free_slots is kept sorted in DESCENDING order: pop_back hands out the smallest free slot, so the fresh
+// slots of a batch ascend and a batch lands contiguously where it can.
+// Slots [lo, hi) -- all larger than any slot the pool had -- become free.
+void add_free_range(vx_ctx* ctx, int lo, int hi) {
+    std::vector<int> fresh;
+    fresh.reserve((size_t)(hi - lo) + ctx->free_slots.size());
+    for (int s = hi - 1; s >= lo; --s) fresh.push_back(s);
+    fresh.insert(fresh.end(), ctx->free_slots.begin(), ctx->free_slots.end());
+    ctx->free_slots.swap(fresh);
+}
+
+// `freed` (any order) joins the free list: one merge instead of sorting the whole list per call
+void add_free_slots(vx_ctx* ctx, std::vector<int>& freed) {
+    if (freed.empty()) return;
+    if (std::is_sorted(freed.begin(), freed.end())) std::reverse(freed.begin(), freed.end());  // the usual case
+    else std::sort(freed.begin(), freed.end(), std::greater<int>());
+    std::vector<int> merged(ctx->free_slots.size() + freed.size());
+    std::merge(ctx->free_slots.begin(), ctx->free_slots.end(), freed.begin(), freed.end(), merged.begin(), std::greater<int>());
+    ctx->free_slots.swap(merged);
+}
+
 int grow_pool(vx_ctx* ctx, int min_capacity) {
     if (min_capacity <= ctx->capacity) return VX_OK;
     int new_cap = std::max({min_capacity, ctx->capacity * 2, 256});
@@ -467,7 +488,7 @@ int grow_pool(vx_ctx* ctx, int min_capacity) {
             return fail(ctx, VX_ERR_OOM, "pool growth: out of device memory");  // what was mapped stays mapped: harmless
         }
         ctx->slot_key.resize(new_cap, ~0ull);
-        for (int s = new_cap - 1; s >= ctx->capacity; --s) ctx->free_slots.push_back(s);  // pop -> ascending
+        add_free_range(ctx, ctx->capacity, new_cap);
         ctx->capacity = new_cap;
         return VX_OK;
     }
@@ -527,7 +548,7 @@ int grow_pool(vx_ctx* ctx, int min_capacity) {
     ctx->d_voxels = nv; ctx->d_heights = nh; ctx->d_planes = np; ctx->d_slot_xy = nxy;
     ctx->d_face = nf; ctx->d_meshed = nm;
     ctx->slot_key.resize(new_cap, ~0ull);
-    for (int s = new_cap - 1; s >= ctx->capacity; --s) ctx->free_slots.push_back(s);  // pop -> ascending
+    add_free_range(ctx, ctx->capacity, new_cap);
     ctx->capacity = new_cap;
     return VX_OK;
 }
@@ -1113,7 +1134,6 @@ int vx_unload(vx_ctx* ctx, const uint32_t* area_xy, int n) {
         const int s = ctx->index.erase(area_xy[2 * i], area_xy[2 * i + 1]);
         if (s < 0) continue;
         ctx->slot_key[s] = ~0ull;
-        ctx->free_slots.push_back(s);
         freed.push_back(s);
         any = true;
     }
@@ -1124,8 +1144,7 @@ int vx_unload(vx_ctx* ctx, const uint32_t* area_xy, int n) {
         }
         ctx->map_dirty = true;
         ++ctx->index_version;
-        // keep hand-out order ascending so later batches stay contiguous where possible
-        std::sort(ctx->free_slots.begin(), ctx->free_slots.end(), std::greater<int>());
+        add_free_slots(ctx, freed);  // hand-out order stays ascending, so later batches stay contiguous where possible
     }
     return VX_OK;
 }
