@@ -1777,15 +1777,21 @@ int vx_light(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* light_out, in
         ctx->timings.other_launches += 2;
         // levels travel at most 15 voxels, i.e. across at most one area border per launch pair;
         // the bound below is generous and only guards against a logic error
-        for (; iters < 64; ++iters) {
-            VX_CUDA(cudaMemsetAsync(flag, 0, 4, ctx->stream));
-            launch_light_relax(jobs, n, ctx->d_voxels, device_map(ctx), ctx->d_slot_to_job.as<int32_t>(),
-                               ctx->d_light.as<uint8_t>(), flag, ctx->stream);
-            ctx->timings.other_launches += 1;
-            VX_CUDA(cudaMemcpyAsync(host_flag, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        // Two launches per look at the flag: the last launch of a run only confirms that nothing moves
+        // any more, so the host would otherwise wait once per launch for an answer that is "go on" every
+        // time but the last.
+        while (iters < 64) {
+            VX_CUDA(cudaMemsetAsync(flag, 0, 8, ctx->stream));
+            for (int k = 0; k < 2; ++k) {
+                launch_light_relax(jobs, n, ctx->d_voxels, device_map(ctx), ctx->d_slot_to_job.as<int32_t>(),
+                                   ctx->d_light.as<uint8_t>(), flag + k, ctx->stream);
+                ctx->timings.other_launches += 1;
+            }
+            iters += 2;
+            VX_CUDA(cudaMemcpyAsync(host_flag, flag, 8, cudaMemcpyDeviceToHost, ctx->stream));
             VX_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (*host_flag == 0) {
-                ++iters;
+            if (host_flag[1] == 0) {  // the second launch of the pair changed nothing: the fixed point
+                if (host_flag[0] == 0) --iters;  // ... and it was already reached before the pair's second launch
                 break;
             }
         }
