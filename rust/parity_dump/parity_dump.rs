@@ -102,7 +102,7 @@ fn sample_points(rng: &mut Rng, dim: usize) -> Vec<f64> {
             pts.push(v);
         }
     }
-    for i in 0..50 {
+    for i in 0..50usize {
         for d in 0..dim {
             pts.push((i * (d + 1)) as f64);
         }
