@@ -111,6 +111,79 @@ int main() {
     CHECK(renderer.meshes().at({62500, 62500}).lights.empty());
     CHECK(world.get_height(lamp_at) > 20);
 
+    // water (water_simulator.rs): in a walled 3 x 3 basin on a stone plate in the air a source fills its
+    // four sides with Water1 and the corners with Water2, and everything dries up again once the source
+    // is gone (on open ground a stream would run downhill for ever: the front advances as the tail
+    // dries); the meshes end as they began.  Falling sand (falling_voxel_simulator.rs): placed in the air
+    // it becomes an entity and comes to rest on the ground.
+    {
+        WaterSimulator water;
+        FallingVoxelSimulator falling;
+        const Location col{5, 6, 0};
+        const uint32_t ground = world.get_height(col.to_internal());  // first opaque z of the column
+        const int32_t plate_z = static_cast<int32_t>(ground) - 12, basin_z = plate_z - 1;
+        CHECK(plate_z > 2);
+        std::vector<std::pair<InternalLocation, Voxel>> build, demolish;
+        std::vector<InternalLocation> built;
+        for (int dx = -2; dx <= 2; ++dx)
+            for (int dy = -2; dy <= 2; ++dy) {
+                const InternalLocation floor = Location{5 + dx, 6 + dy, plate_z}.to_internal();
+                CHECK(world.get(floor) == Voxel::None);
+                build.push_back({floor, Voxel::Stone});
+                if (dx == -2 || dx == 2 || dy == -2 || dy == 2) {
+                    const InternalLocation wall = Location{5 + dx, 6 + dy, basin_z}.to_internal();
+                    CHECK(world.get(wall) == Voxel::None);
+                    build.push_back({wall, Voxel::Stone});
+                }
+            }
+        for (const auto& e : build) {
+            built.push_back(e.first);
+            demolish.push_back({e.first, Voxel::None});
+        }
+        world.set_batch(build);
+        renderer.update_locations(world, built);
+        const size_t with_basin = renderer.get_voxel_face_count();
+        CHECK(with_basin > before);
+        const InternalLocation src = Location{5, 6, basin_z}.to_internal();
+        world.set_batch({{src, Voxel::WaterSource}});
+        renderer.update_location(world, src);
+        water.location_updated(src);
+        size_t changed_total = 0;
+        for (int tick = 0; tick < 8; ++tick) changed_total += water.simulate_voxels(world, renderer);
+        CHECK(changed_total >= 8);
+        CHECK(world.get({src.x + 1, src.y, src.z}) == Voxel::Water1 && world.get({src.x, src.y - 1, src.z}) == Voxel::Water1);
+        CHECK(world.get({src.x + 1, src.y + 1, src.z}) == Voxel::Water2 && world.get({src.x - 1, src.y - 1, src.z}) == Voxel::Water2);
+        CHECK(world.get({src.x + 2, src.y, src.z}) == Voxel::Stone);  // the wall holds
+        CHECK(renderer.get_voxel_face_count() > with_basin);
+        world.set_batch({{src, Voxel::None}});
+        renderer.update_location(world, src);
+        water.location_updated(src);
+        for (int tick = 0; tick < 40 && water.pending(); ++tick) water.simulate_voxels(world, renderer);
+        CHECK(water.pending() == 0);
+        for (int dx = -1; dx <= 1; ++dx)
+            for (int dy = -1; dy <= 1; ++dy) CHECK(world.get({src.x + dx, src.y + dy, src.z}) == Voxel::None);
+        CHECK(renderer.get_voxel_face_count() == with_basin);
+        world.set_batch(demolish);
+        renderer.update_locations(world, built);
+        CHECK(renderer.get_voxel_face_count() == before);
+
+        const InternalLocation sand = Location{5, 6, static_cast<int32_t>(ground) - 6}.to_internal();
+        world.set_batch({{sand, Voxel::Sand}});
+        renderer.update_location(world, sand);
+        CHECK(renderer.get_voxel_face_count() == before + 6);
+        falling.update_voxels(world, renderer, water, sand);
+        CHECK(falling.simulated_voxels().size() == 1 && world.get(sand) == Voxel::None);
+        CHECK(renderer.get_voxel_face_count() == before);
+        for (int step = 0; step < 200 && !falling.simulated_voxels().empty(); ++step)
+            falling.simulate_falling(world, renderer, water, 0.5f);
+        CHECK(falling.simulated_voxels().empty());
+        CHECK(world.get({sand.x, sand.y, ground - 1}) == Voxel::Sand);
+        CHECK(world.get_height(sand) == ground - 1);
+        world.set_batch({{InternalLocation{sand.x, sand.y, ground - 1}, Voxel::None}});
+        renderer.update_location(world, {sand.x, sand.y, ground - 1});
+        CHECK(renderer.get_voxel_face_count() == before);
+    }
+
     // one frame (renderer.rs:365-452): everything in the map view, a strict subset when looking +x
     // from the spawn column, nothing drawn twice, every drawn voxel has a mesh
     // (the frame runs over the resident meshes of the whole zone; nothing is re-meshed for it)

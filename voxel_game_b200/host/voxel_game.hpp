@@ -24,6 +24,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <utility>
 #include <vector>
 
@@ -59,6 +60,10 @@ struct Location {  // player-facing coordinates, model/location.rs:8-27
     InternalLocation to_internal() const {
         return {static_cast<uint32_t>(x + LOCATION_OFFSET), static_cast<uint32_t>(y + LOCATION_OFFSET),
                 static_cast<uint32_t>(z)};
+    }
+    static Location from_internal(InternalLocation l) {  // location.rs:19-27
+        return {static_cast<int32_t>(l.x) - LOCATION_OFFSET, static_cast<int32_t>(l.y) - LOCATION_OFFSET,
+                static_cast<int32_t>(l.z)};
     }
 };
 
@@ -213,6 +218,20 @@ public:
             it->second.has_changed = true;
         }
         return out;
+    }
+    // The device changed voxels behind the host copies (simulator ticks): read the touched areas again.
+    void refresh(const std::vector<InternalLocation>& changed) {
+        std::vector<AreaLocation> seen;
+        for (const auto& l : changed) {
+            const AreaLocation a = convert_global_to_area_location(l);
+            if (std::find(seen.begin(), seen.end(), a) != seen.end()) continue;
+            seen.push_back(a);
+            auto it = areas_.find(a);
+            if (it == areas_.end()) continue;
+            const uint32_t xy[2] = {a.x, a.y};
+            p_->check(vx_read_areas(p_->raw(), xy, 1, it->second.voxels_.data(), it->second.max_height_.data()));
+            it->second.has_changed = true;
+        }
     }
     size_t get_loaded_areas_count() const { return areas_.size(); }
     const Area& get_area_without_loading(AreaLocation a) const { return areas_.at(a); }
@@ -607,6 +626,118 @@ private:
     }
     std::map<AreaLocation, RenderArea> meshes_;
     bool retention_on_ = false;
+};
+
+// service/physics/water_simulator.rs.  check_locations is a HashSet in the reference and its tick
+// iterates it while it mutates the world, so the outcome depends on the iteration order; this mirror
+// iterates in insertion order and hands that order to the device (vx_water_tick applies the list one
+// location after the other, exactly as simulate_voxels' loop body does).
+class WaterSimulator {
+public:
+    void location_updated(InternalLocation l) {  // :38-53, the reference's own conditions for z - 1 / z + 1
+        insert(l);
+        insert({l.x + 1, l.y, l.z});
+        insert({l.x - 1, l.y, l.z});
+        insert({l.x, l.y + 1, l.z});
+        insert({l.x, l.y - 1, l.z});
+        if (l.z - 1u < AREA_HEIGHT) insert({l.x, l.y, l.z - 1});
+        if (l.z > 0) insert({l.x, l.y, l.z + 1});
+    }
+    // simulate_voxels (:55-77); returns the number of voxels it set
+    size_t simulate_voxels(World& world, Renderer& renderer) {
+        std::vector<InternalLocation> check;
+        check.swap(order_);  // mem::take
+        set_.clear();
+        if (check.empty()) return 0;
+        const Pipeline& p = world.pipeline();
+        std::vector<uint32_t> xyz, changed(16 * check.size()), next(21 * check.size());
+        for (const auto& l : check) {
+            xyz.push_back(l.x);
+            xyz.push_back(l.y);
+            xyz.push_back(l.z);
+        }
+        int nc = 0, nn = 0;
+        p.check(vx_water_tick(p.raw(), xyz.data(), static_cast<int>(check.size()), changed.data(), &nc, next.data(), &nn));
+        std::vector<InternalLocation> touched;
+        for (int i = 0; i < nc; ++i) touched.push_back({changed[4 * i], changed[4 * i + 1], changed[4 * i + 2]});
+        world.refresh(touched);
+        renderer.update_locations(world, touched);  // renderer.update_location after every world.set
+        for (int i = 0; i < nn; ++i) insert({next[3 * i], next[3 * i + 1], next[3 * i + 2]});
+        return static_cast<size_t>(nc);
+    }
+    size_t pending() const { return order_.size(); }
+    // check_locations.insert: what the device reports as queued by location_updated goes in as it comes
+    void insert(InternalLocation l) {
+        if (l.z >= AREA_HEIGHT) return;  // the reference would index past the area (z = 127 is never edited)
+        if (set_.insert(LocKey{l.x, l.y, l.z}).second) order_.push_back(l);
+    }
+
+private:
+    std::vector<InternalLocation> order_;
+    std::unordered_set<LocKey, LocHash> set_;
+};
+
+// service/physics/falling_voxel_simulator.rs without the entity meshes and the drawing
+struct SimulatedVoxel {
+    Voxel voxel_type;
+    float position[3];
+    float velocity;
+};
+class FallingVoxelSimulator {
+public:
+    // update_voxels (:105-150) for one location: unsupported falling voxels around it (and, recursively,
+    // above them) leave the world and become entities
+    void update_voxels(World& world, Renderer& renderer, WaterSimulator& water, InternalLocation location) {
+        const Pipeline& p = world.pipeline();
+        const uint32_t xyz[3] = {location.x, location.y, location.z};
+        const int cap = 4096;
+        std::vector<uint32_t> spawned(4 * cap), next(21 * cap);
+        int ns = 0, nn = 0;
+        p.check(vx_falling_check(p.raw(), xyz, 1, spawned.data(), cap, &ns, next.data(), 7 * cap, &nn));
+        std::vector<InternalLocation> touched;
+        for (int i = 0; i < ns; ++i) {
+            const InternalLocation l{spawned[4 * i], spawned[4 * i + 1], spawned[4 * i + 2]};
+            touched.push_back(l);
+            const Location w = Location::from_internal(l);
+            simulated_.push_back({static_cast<Voxel>(spawned[4 * i + 3]),
+                                  {static_cast<float>(w.x), static_cast<float>(w.y), static_cast<float>(w.z)}, 0.0f});
+        }
+        world.refresh(touched);
+        renderer.update_locations(world, touched);
+        for (int i = 0; i < nn; ++i) water.insert({next[3 * i], next[3 * i + 1], next[3 * i + 2]});  // location_updated, expanded
+    }
+    // simulate_falling (:152-166): gravity on the host, the retain pass on the device
+    void simulate_falling(World& world, Renderer& renderer, WaterSimulator& water, float delta) {
+        if (simulated_.empty()) return;
+        std::vector<float> pos;
+        std::vector<uint8_t> types;
+        for (auto& v : simulated_) {
+            v.velocity += delta * 0.2f;                       // GRAVITY
+            v.velocity = v.velocity < 3.0f ? v.velocity : 3.0f;  // MAX_FALL_SPEED
+            v.position[2] += v.velocity;
+            pos.insert(pos.end(), v.position, v.position + 3);
+            types.push_back(static_cast<uint8_t>(v.voxel_type));
+        }
+        const Pipeline& p = world.pipeline();
+        const int n = static_cast<int>(simulated_.size());
+        std::vector<uint8_t> keep(simulated_.size());
+        std::vector<uint32_t> placed(4 * simulated_.size()), next(21 * simulated_.size());
+        int np = 0, nn = 0;
+        p.check(vx_falling_land(p.raw(), pos.data(), types.data(), n, keep.data(), placed.data(), &np, next.data(), &nn));
+        std::vector<InternalLocation> touched;
+        for (int i = 0; i < np; ++i) touched.push_back({placed[4 * i], placed[4 * i + 1], placed[4 * i + 2]});
+        world.refresh(touched);
+        renderer.update_locations(world, touched);
+        for (int i = 0; i < nn; ++i) water.insert({next[3 * i], next[3 * i + 1], next[3 * i + 2]});
+        std::vector<SimulatedVoxel> kept;
+        for (size_t i = 0; i < simulated_.size(); ++i)
+            if (keep[i]) kept.push_back(simulated_[i]);
+        simulated_.swap(kept);
+    }
+    const std::vector<SimulatedVoxel>& simulated_voxels() const { return simulated_; }
+
+private:
+    std::vector<SimulatedVoxel> simulated_;
 };
 
 }  // namespace voxel_game
