@@ -259,24 +259,22 @@ struct __align__(16) GenSmem {
 // can still move the value across a cut.  Returns the number of cuts <= the value.  These noises
 // have wavelengths of hundreds of voxels: the 32 columns of a warp nearly always agree.
 template <int ID, int NCUTS>
-__device__ __forceinline__ int fbm2_region(const NoiseTables& nt, const NoiseShared* s, double x, double y,
-                                           const int (&cuts)[NCUTS], unsigned& evals) {
-    const FbmParams& q = nt.fbm[ID];
-    auto region = [&](double v) {
-        const int b = f64_as_i32(normalise(v));
-        int r = 0;
+__device__ __forceinline__ int region_of(double v, const int (&cuts)[NCUTS]) {
+    const int b = f64_as_i32(normalise(v));
+    int r = 0;
 #pragma unroll
-        for (int i = 0; i < NCUTS; ++i) r += b >= cuts[i] ? 1 : 0;
-        return r;
-    };
-    const double px = x, py = y;
-    x *= q.frequency;
-    y *= q.frequency;
-    double acc = 0.0;
-    acc += q.amp[0] * simplex2<FBM_TABLE<ID>>(s, x, y);
-    ++evals;
+    for (int i = 0; i < NCUTS; ++i) r += b >= cuts[i] ? 1 : 0;
+    return r;
+}
+
+// The part of fbm2_region behind the first octave: `acc` holds its weighted value, (x, y) its
+// coordinates, (px, py) the point itself.
+template <int ID, int NCUTS>
+__device__ __forceinline__ int region_finish(const NoiseTables& nt, const NoiseShared* s, double acc, double x, double y,
+                                             double px, double py, const int (&cuts)[NCUTS], unsigned& evals) {
+    const FbmParams& q = nt.fbm[ID];
     const double mid = acc * q.norm, rest = SIMPLEX_BOUND * q.amp[1] * q.norm + 1e-9;
-    const int r_lo = region(mid - rest), r_hi = region(mid + rest);
+    const int r_lo = region_of<ID>(mid - rest, cuts), r_hi = region_of<ID>(mid + rest, cuts);
     if (r_lo == r_hi) return r_lo;
 #if VX_NOISE_VARIANT & 1
     x = px * q.freq[1];
@@ -288,7 +286,37 @@ __device__ __forceinline__ int fbm2_region(const NoiseTables& nt, const NoiseSha
 #endif
     acc += q.amp[1] * simplex2<FBM_TABLE<ID>>(s, x, y);
     ++evals;
-    return region(acc * q.norm);
+    return region_of<ID>(acc * q.norm, cuts);
+}
+
+template <int ID, int NCUTS>
+__device__ __forceinline__ int fbm2_region(const NoiseTables& nt, const NoiseShared* s, double x, double y,
+                                           const int (&cuts)[NCUTS], unsigned& evals) {
+    const FbmParams& q = nt.fbm[ID];
+    const double px = x, py = y;
+    x *= q.frequency;
+    y *= q.frequency;
+    double acc = 0.0;
+    acc += q.amp[0] * simplex2<FBM_TABLE<ID>>(s, x, y);
+    ++evals;
+    return region_finish<ID>(nt, s, acc, x, y, px, py, cuts, evals);
+}
+
+// Two such Fbms over the same point: their first octaves side by side (two independent evaluations in
+// flight), then each one's verdict -- and second octave, where it is still needed -- on its own.
+template <int IDA, int NA, int IDB, int NB>
+__device__ __forceinline__ void fbm2_region_pair(const NoiseTables& nt, const NoiseShared* s, double px, double py,
+                                                 const int (&cuts_a)[NA], const int (&cuts_b)[NB], unsigned& evals,
+                                                 int& ra, int& rb) {
+    const FbmParams& qa = nt.fbm[IDA];
+    const FbmParams& qb = nt.fbm[IDB];
+    const double xa = px * qa.frequency, ya = py * qa.frequency, xb = px * qb.frequency, yb = py * qb.frequency;
+    double acc_a = 0.0, acc_b = 0.0;
+    acc_a += qa.amp[0] * simplex2<FBM_TABLE<IDA>>(s, xa, ya);
+    acc_b += qb.amp[0] * simplex2<FBM_TABLE<IDB>>(s, xb, yb);
+    evals += 2;
+    ra = region_finish<IDA>(nt, s, acc_a, xa, ya, px, py, cuts_a, evals);
+    rb = region_finish<IDB>(nt, s, acc_b, xb, yb, px, py, cuts_b, evals);
 }
 
 #ifndef VX_K1_CTAS_PER_SM
@@ -328,15 +356,26 @@ __global__ void __launch_bounds__(256, VX_K1_CTAS_PER_SM) gen_columns_kernel(con
     const double px = (double)(x + ax * AREA_SIZE), py = (double)(y + ay * AREA_SIZE);
 
     // TerrainTypeGenerator::sample (terrain_type.rs:26-32)
+#ifdef VX_K1_SERIAL_FBM
     const double n1 = fbm2<FBM_HEIGHT1>(nt, s, px, py), n2 = fbm2<FBM_HEIGHT2>(nt, s, px, py);
+    const double nm = fbm2<FBM_HEIGHT_MOD>(nt, s, px, py);
+#else
+    double n1, n2, nm;  // 6 + 4 + 2 octaves, two evaluations side by side per iteration
+    fbm2_three<FBM_HEIGHT1, FBM_HEIGHT2, FBM_HEIGHT_MOD, 6, 4>(nt, s, px, py, n1, n2, nm);
+#endif
     double value = fmax(n1, n2);
     value = value < 0.1 ? 0.1 : (value > 1.0 ? 1.0 : value);
-    const double height_mod = 1.0 - (fbm2<FBM_HEIGHT_MOD>(nt, s, px, py) + 1.0) / 2.0;
+    const double height_mod = 1.0 - (nm + 1.0) / 2.0;
     const unsigned H = f64_as_u32(height_mod * value * 0.55 * 128.0) + 32u;
     unsigned evals2 = 12, evals3 = 0;  // simplex evaluations of this column (work accounting)
     // CaveGenerator::is_cave_zone (cave_generator.rs:36-41): normalise(v) as i32 >= 80
+    // and BiomeTypeGenerator::sample (biome_type.rs:25-34): 0..20 Dry, 20..80 Wet, everything else (below
+    // 0 too) Cold -- the two noises' first octaves run side by side
     const int cave_cuts[1] = {80};
-    const bool cave_zone = fbm2_region<FBM_CAVE_CHECK>(nt, s, px, py, cave_cuts, evals2) == 1;
+    const int biome_cuts[3] = {0, 20, 80};
+    int cave_region, biome_region;
+    fbm2_region_pair<FBM_CAVE_CHECK, 1, FBM_BIOME, 3>(nt, s, px, py, cave_cuts, biome_cuts, evals2, cave_region, biome_region);
+    const bool cave_zone = cave_region == 1;
     // LakeGenerator::sample_lake_depth (lake_generator.rs:27-52)
     unsigned lake_depth = 0;
     if (!cave_zone && H <= LAKE_MAX_TERRAIN && H > LAKE_TOP_ZI) {
@@ -344,10 +383,6 @@ __global__ void __launch_bounds__(256, VX_K1_CTAS_PER_SM) gen_columns_kernel(con
         const int d = (f64_as_i32(normalise(fbm2<FBM_LAKE>(nt, s, px, py))) - 70) / 3;
         lake_depth = d < 2 ? 0u : (unsigned)d;
     }
-    // BiomeTypeGenerator::sample (biome_type.rs:25-34)
-    //   0..20 Dry, 20..80 Wet, everything else (below 0 too) Cold
-    const int biome_cuts[3] = {0, 20, 80};
-    const int biome_region = fbm2_region<FBM_BIOME>(nt, s, px, py, biome_cuts, evals2);
     const int biome = biome_region == 1 ? DRY : (biome_region == 2 ? WET : COLD);
 
     // The four topmost voxels first (k-th voxel from H - 3): should_generate_alternative_voxel
@@ -355,7 +390,10 @@ __global__ void __launch_bounds__(256, VX_K1_CTAS_PER_SM) gen_columns_kernel(con
     // threshold.  The second octave is bounded by |simplex| <= SIMPLEX_BOUND, so it is needed only
     // where it can still change the verdict (normalise() is monotone: testing it at the bounds is
     // exact) -- about a quarter of the evaluations, scattered over the lanes.  Those are queued and
-    // evaluated densely by the whole CTA instead of by half-empty warps.
+    // evaluated densely by the whole CTA instead of by half-empty warps.  (Queueing the FIRST octaves
+    // too -- only 2.6 of a column's 4 surface voxels consult the noise -- was measured and lost: 0.478 ->
+    // 0.497 ms, the listing, the extra barrier and the shared atomics cost more than the idle lanes;
+    // so was evaluating two surface voxels side by side per iteration: it spills at the 64-register cap.)
     // A lake column never consults the noise where the lake overrides the voxel
     // (lake_generator.rs:54-74 replaces the value; the reference computes it and throws it away).
     SurfaceQueue& sq = *reinterpret_cast<SurfaceQueue*>(sm.vox);  // the area is assembled there afterwards
