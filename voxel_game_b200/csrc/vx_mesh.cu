@@ -406,9 +406,21 @@ __global__ void __launch_bounds__(1024) mesh_offsets_kernel(const uint32_t* __re
 
 // ------------------------------------------------------------------------------------- emit
 // (corner codes, face descriptors and vertex assembly: vx_face.cuh)
-constexpr int LIST_FACES = 3072;   // face descriptors buffered per flush (typical area: ~800)
-constexpr int ROW_CAP = 512;       // rows with faces staged per pass (typical area: ~100)
-constexpr int WARP_FACES = 16;     // faces a warp assembles per staging round (2 lanes per face)
+#ifndef VX_EMIT_LIST
+#define VX_EMIT_LIST 3072
+#endif
+#ifndef VX_EMIT_ROWS
+#define VX_EMIT_ROWS 512
+#endif
+#ifndef VX_EMIT_WARP_FACES
+#define VX_EMIT_WARP_FACES 16
+#endif
+#ifndef VX_EMIT_CTAS
+#define VX_EMIT_CTAS 5
+#endif
+constexpr int LIST_FACES = VX_EMIT_LIST;        // face descriptors buffered per flush (typical area: ~800)
+constexpr int ROW_CAP = VX_EMIT_ROWS;           // rows with faces staged per pass (typical area: ~100)
+constexpr int WARP_FACES = VX_EMIT_WARP_FACES;  // faces a warp assembles per staging round (2 lanes per face)
 constexpr int FACE_U4 = 10;        // uint4 per face (4 vertices x 40 B)
 constexpr int HALF_U4 = 5;         // a lane stages two vertices: 5 uint4 at (lane / 2) * 10 + (lane % 2) * 5,
                                    // so the 8 lanes of a store phase hit 8 different bank groups
@@ -495,7 +507,7 @@ __device__ __forceinline__ void flush_faces(EmitSmem& sm, uint32_t count, uint32
 //      z levels, i.e. in a few warps of phase A; spreading them over the CTA by voxel is what keeps
 //      the warps evenly busy.
 //   C  flush: lane pairs expand descriptors into 160-byte vertex blocks (flush_faces).
-__global__ void __launch_bounds__(256, 5) mesh_emit_kernel(const uint4* __restrict__ jobs,
+__global__ void __launch_bounds__(256, VX_EMIT_CTAS) mesh_emit_kernel(const uint4* __restrict__ jobs,
                                                         const uint4* __restrict__ nbr,
                                                         const uint8_t* __restrict__ pool_voxels,
                                                         const uint16_t* __restrict__ pool_planes,
