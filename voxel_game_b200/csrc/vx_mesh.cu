@@ -145,6 +145,17 @@ __device__ __forceinline__ bool slab_pair_empty(const PlaneTile& p, int z0) {
     return !(faces0 || faces1);
 }
 
+// bit x = byte x of a equals byte x of b (16 bytes, little endian over .x .y .z .w)
+__device__ __forceinline__ uint32_t equal_bytes(const uint4 a, const uint4 b) {
+    // __vcmpeq4: 0xFF per equal byte; the four top bits are gathered by a multiply whose partial
+    // products land on distinct bits, the wanted ones on bits 28..31
+    const uint32_t e0 = ((__vcmpeq4(a.x, b.x) & 0x80808080u) * 0x00204081u) >> 28;
+    const uint32_t e1 = ((__vcmpeq4(a.y, b.y) & 0x80808080u) * 0x00204081u) >> 28;
+    const uint32_t e2 = ((__vcmpeq4(a.z, b.z) & 0x80808080u) * 0x00204081u) >> 28;
+    const uint32_t e3 = ((__vcmpeq4(a.w, b.w) & 0x80808080u) * 0x00204081u) >> 28;
+    return e0 | (e1 << 4) | (e2 << 8) | (e3 << 12);
+}
+
 __device__ __forceinline__ RowMasks row_masks(const PlaneTile& p, const AreaView& a, int r) {
     RowMasks k;
     const uint32_t s = p.S[r];
@@ -171,6 +182,43 @@ __device__ __forceinline__ RowMasks row_masks(const PlaneTile& p, const AreaView
     // transparent non-None voxels: apply cur != nbr, the top-face rule for partial-height water
     // (mesh_generator.rs:515-518) and the enclosed-voxel pre-filter (area.rs:126-201)
     uint32_t w = s & t;
+#ifndef VX_MESH_BYTEWISE_REFINE
+    // All 16 voxels of the row at once: the row and the rows it is compared with are 16-byte loads
+    // (issued together, no per-voxel chain of byte loads through a water body), cur == nbr is a
+    // byte-wise compare whose results are gathered into a 16-bit mask.
+    if (w) {
+        const uint4* rows = reinterpret_cast<const uint4*>(a.vox);
+        const uint4 c = rows[r];
+        if (k.m[0] & w) {
+            const uint32_t halo = ((k.m[0] & w) >> 15) ? a.vox_n[0][16 * r] : 0u;
+            const uint4 n = make_uint4(__funnelshift_r(c.x, c.y, 8), __funnelshift_r(c.y, c.z, 8),
+                                       __funnelshift_r(c.z, c.w, 8), (c.w >> 8) | (halo << 24));
+            k.m[0] &= ~(equal_bytes(c, n) & w);
+        }
+        if (k.m[1] & w) {
+            const uint32_t halo = (k.m[1] & w & 1u) ? a.vox_n[1][16 * r + 15] : 0u;
+            const uint4 n = make_uint4((c.x << 8) | halo, __funnelshift_l(c.x, c.y, 8), __funnelshift_l(c.y, c.z, 8),
+                                       __funnelshift_l(c.z, c.w, 8));
+            k.m[1] &= ~(equal_bytes(c, n) & w);
+        }
+        if (k.m[2] & w)
+            k.m[2] &= ~(equal_bytes(c, y < 15 ? rows[r + 1] : reinterpret_cast<const uint4*>(a.vox_n[2])[r - 15]) & w);
+        if (k.m[3] & w)
+            k.m[3] &= ~(equal_bytes(c, y > 0 ? rows[r - 1] : reinterpret_cast<const uint4*>(a.vox_n[3])[r + 15]) & w);
+        if (k.m[4] & w) k.m[4] &= ~(equal_bytes(c, rows[r + 16]) & w);  // a face bit implies z < AREA_HEIGHT - 1
+        if (k.m[5] & w) k.m[5] &= ~(equal_bytes(c, rows[r - 16]) & w);  // a face bit implies z > 0
+        const uint4 partial = make_uint4(c.x & 0xFCFCFCFCu, c.y & 0xFCFCFCFCu, c.z & 0xFCFCFCFCu, c.w & 0xFCFCFCFCu);
+        static_assert(V_WATER1 == 16 && V_WATER4 == 19, "partial-height voxels are the IDs 0x10..0x13");
+        const uint32_t ph = equal_bytes(partial, make_uint4(0x10101010u, 0x10101010u, 0x10101010u, 0x10101010u)) & w;
+        if (ph && z > 0) {
+            const uint32_t any_plain = k.m[0] | k.m[1] | k.m[2] | k.m[3] | k.m[4] | k.m[5];
+            const uint32_t interior = (y > 0 && y < 15 && z < AREA_HEIGHT - 1) ? 0x7FFEu : 0u;
+            // an enclosed interior voxel is dropped by get_renderable_voxels_for_area before the
+            // top-face rule is ever consulted (world.rs:137-139)
+            k.m[5] |= ph & (any_plain | ~interior) & 0xFFFFu;
+        }
+    }
+#else
     while (w) {
         const int x = __ffs(w) - 1;
         w &= w - 1;
@@ -203,6 +251,7 @@ __device__ __forceinline__ RowMasks row_masks(const PlaneTile& p, const AreaView
             if (any_plain || !interior) k.m[5] |= bit;
         }
     }
+#endif
     return k;
 }
 
@@ -257,7 +306,10 @@ __device__ __forceinline__ uint32_t pack_warp_total(uint32_t faces, uint32_t rec
 
 // Per area: faces and visible voxels, in total and per (256-row chunk, warp) -- the latter, 64
 // words per area, let the emit kernel place every row without recounting the area.
-__global__ void __launch_bounds__(256) mesh_count_kernel(const uint4* __restrict__ jobs,
+#ifndef VX_COUNT_CTAS_PER_SM
+#define VX_COUNT_CTAS_PER_SM 8
+#endif
+__global__ void __launch_bounds__(256, VX_COUNT_CTAS_PER_SM) mesh_count_kernel(const uint4* __restrict__ jobs,
                                                          const uint4* __restrict__ nbr,
                                                          const uint8_t* __restrict__ pool_voxels,
                                                          const uint16_t* __restrict__ pool_planes,
