@@ -651,6 +651,13 @@ __device__ __forceinline__ int hi_key(double x) {
 //     one at once (ballot + popc, no atomics, no CTA barrier) instead of idling until the slowest
 //     lane is done.  Lanes of a warp sit at different octaves of different voxels, which costs
 //     nothing because the octave index only selects table rows.
+//   * Measured and rejected (round 2; both bit-exact, the code is in the history at e074ab7): an Fbm
+//     whose upper bound has fallen below 0.4 cannot change the verdict any more, so evaluating one
+//     octave per iteration, of the Fbm that still matters, needs 3.49 instead of 4.47 evaluations per
+//     voxel -- but one evaluation in flight per thread is slower than the two of a round (0.304 ->
+//     0.320 ms, profiles/r02_ab_caves_single.log); and two voxels per lane, one octave of each per
+//     iteration with the per-voxel state in shared memory, pays the refill and the verdict once per
+//     evaluation instead of once per two (0.329 ms at 72 registers, profiles/r02_ab_caves_dual.log).
 __global__ void __launch_bounds__(VX_CAVE_THREADS, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(const __grid_constant__ NoiseTables nt,
                                                         const uint32_t* __restrict__ cave_items,
                                                         const uint32_t* __restrict__ cave_count,
@@ -782,53 +789,6 @@ __global__ void __launch_bounds__(VX_CAVE_THREADS, VX_CAVE_CTAS_PER_SM) gen_cave
             continue;                           // an empty chunk (or lanes waiting for the next one)
         }
         if (busy) {
-#ifdef VX_CAVE_SINGLE
-            // One octave per iteration, of the Fbm that can still change the verdict.  step = octaves of
-            // noise1 done | octaves of noise2 done << 4 | noise1 dropped << 8 | noise2 dropped << 9.  An Fbm
-            // whose upper bound is below 0.4 can never lift max(a, b) to 0.4 and never to 0.8: the
-            // verdict is the other Fbm's alone, so it is dropped (its sum becomes a large negative
-            // number, which every comparison below and the final fmax read as "below everything").
-            // Both alive: the one with fewer octaves done, noise2 first -- the rounds of the paired
-            // form, one evaluation at a time (3.5 instead of 4.5 evaluations per voxel).
-            {
-                const unsigned sa = step & 15u, sk = (step >> 4) & 15u;
-                const bool alive_a = !(step & 0x100u) && sa < 6u, alive_b = !(step & 0x200u) && sk < 8u;
-                const bool pick_b = alive_b && (!alive_a || sk <= sa);
-                const unsigned sbt = sb + (pick_b ? (unsigned)TAB_STRIDE : 0u);
-                const unsigned sgt = pick_b ? sg2 : sg1;
-                const double px = pick_b ? xb : xa, py = pick_b ? yb : ya, pz = pick_b ? zb : za;
-                const double amp = sm.amp[pick_b ? 1 : 0][pick_b ? sk : sa];
-#if VX_NOISE_VARIANT & 1
-                const double fr = sm.freq[pick_b ? 1 : 0][pick_b ? sk : sa];
-                const double sv = simplex3<0>(sbt, sgt, px * fr, py * fr, pz * fr);
-                (void)l1, (void)l2, (void)f1, (void)f2;
-                if (pick_b) { bsum += amp * sv; step += 16u; } else { a += amp * sv; step += 1u; }
-#else
-                const double sv = simplex3<0>(sbt, sgt, px, py, pz);
-                const double l = pick_b ? l2 : l1;
-                const double nx = px * l, ny = py * l, nz = pz * l;
-                if (pick_b) { bsum += amp * sv; xb = nx; yb = ny; zb = nz; step += 16u; }
-                else { a += amp * sv; xa = nx; ya = ny; za = nz; step += 1u; }
-#endif
-                ++my_evals;
-            }
-            const unsigned sa = step & 15u, sk = (step >> 4) & 15u;
-            const int ka = hi_key(a), kb = hi_key(bsum);
-            const int4 ta = sm.thr[0][sa], tb = sm.thr[1][sk];
-            int verdict = -1;  // -1 undecided, 0 solid, 1 cave
-            if ((ka < ta.x && kb < tb.x) || ka > ta.w || kb > tb.w) verdict = 0;
-            else if ((ka > ta.z || kb > tb.z) && ka < ta.y && kb < tb.y) verdict = 1;
-            if (verdict < 0) {
-                constexpr double DROPPED = -1.0e300;
-                if (ka < ta.x) { a = DROPPED; step |= 0x100u; }
-                if (kb < tb.x) { bsum = DROPPED; step |= 0x200u; }
-                if (((step & 0x100u) || sa == 6u) && ((step & 0x200u) || sk == 8u)) {
-                    // nothing left to evaluate: the crate's own expression over what can matter
-                    const int c = f64_as_i32(normalise(fmax(a * n1, bsum * n2)));
-                    verdict = (c >= 70 && c < 90) ? 1 : 0;  // cave_generator.rs:10-11,63
-                }
-            }
-#else
             // one octave of each Fbm per round (noise1 has 6, noise2 has 8): no per-lane selection
             // of coordinates, and two independent evaluations in flight
             const unsigned k = step;
@@ -867,237 +827,9 @@ __global__ void __launch_bounds__(VX_CAVE_THREADS, VX_CAVE_CTAS_PER_SM) gen_cave
                 const int c = f64_as_i32(normalise(fmax(a * n1, bsum * n2)));
                 verdict = (c >= 70 && c < 90) ? 1 : 0;  // cave_generator.rs:10-11,63
             }
-#endif
             if (verdict >= 0) {
                 if (verdict) pool_voxels[out_index] = V_NONE;  // leave air
                 busy = false;
-            }
-        }
-    }
-    my_evals = __reduce_add_sync(0xFFFFFFFFu, my_evals);
-    if (lane == 0 && my_evals) atomicAdd(&stats[3], (unsigned long long)my_evals);
-}
-
-// ------------------------------------------------------------------------------------------ K1b'
-// The same work with every evaluation a useful one.  The paired kernel above runs one octave of EACH
-// Fbm per round; but an Fbm whose upper bound has fallen below 0.4 can never lift max(a, b) to 0.4 (nor
-// to 0.8), so the verdict is the other Fbm's alone and its remaining octaves are wasted -- 22 % of all
-// evaluations.  Evaluating one octave per iteration, of the Fbm that still matters, needs 3.5 instead
-// of 4.5 evaluations per voxel, but one evaluation in flight per thread is slower than two (measured:
-// 0.304 -> 0.320 ms, profiles/r02_ab_caves_single.log).  So a lane works on TWO voxels at once, one
-// octave of each per iteration: two independent evaluations in flight, all of them needed.  The
-// per-voxel state (coordinates and running sum of both Fbms) lives in shared memory -- an iteration
-// loads the state of the Fbm it picked, evaluates, stores it back; registers keep only the two
-// integer keys of the sums, the octave counters and the output index of each voxel.
-struct CaveDualSmem {
-    CaveSmem base;
-    double2 st[2][2][2][VX_CAVE_THREADS];  // [voxel slot][Fbm][(x, y) | (z, sum)][thread]
-};
-
-#ifndef VX_CAVE_DUAL_CTAS_PER_SM
-#define VX_CAVE_DUAL_CTAS_PER_SM 6
-#endif
-__global__ void __launch_bounds__(VX_CAVE_THREADS, VX_CAVE_DUAL_CTAS_PER_SM) gen_caves_dual_kernel(
-        const __grid_constant__ NoiseTables nt, const uint32_t* __restrict__ cave_items,
-        const uint32_t* __restrict__ cave_count, uint8_t* __restrict__ pool_voxels,
-        const uint8_t* __restrict__ pool_heights, const uint2* __restrict__ slot_xy,
-        unsigned long long* __restrict__ stats) {
-    extern __shared__ __align__(256) unsigned char cave_dual_raw[];
-    CaveDualSmem& ds = *reinterpret_cast<CaveDualSmem*>(cave_dual_raw);
-    CaveSmem& sm = ds.base;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const FbmParams& q1 = nt.fbm[FBM_CAVE1];
-    const FbmParams& q2 = nt.fbm[FBM_CAVE2];
-    load_noise_image(sm.bytes, nt, 0, TAB_BYTES, tid, VX_CAVE_THREADS);
-    load_noise_image(sm.grad3, nt, (unsigned)offsetof(NoiseImage, grad3), (unsigned)sizeof(sm.grad3), tid, VX_CAVE_THREADS);
-    if (tid < 8) {
-        sm.amp[0][tid] = tid < 6 ? q1.amp[tid] : 0.0;
-        sm.amp[1][tid] = q2.amp[tid];
-#if VX_NOISE_VARIANT & 1
-        sm.freq[0][tid] = tid < 6 ? q1.freq[tid] : 0.0;
-        sm.freq[1][tid] = q2.freq[tid];
-#endif
-    }
-    if (tid < 18) {
-        const int* t = &nt.cave_thr[0][0][0] + 4 * tid;
-        (&sm.thr[0][0])[tid] = make_int4(t[0], t[1], t[2], t[3]);
-    }
-    if (tid < AREA_HEIGHT) {
-#if VX_NOISE_VARIANT & 1
-        sm.zf[tid] = make_double2((double)tid, (double)tid);
-#else
-        sm.zf[tid] = make_double2((double)tid * q1.frequency, (double)tid * q2.frequency);
-#endif
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) (&ds.st[0][0][0][0])[i * VX_CAVE_THREADS + tid] = make_double2(0.0, 0.0);  // idle slots evaluate this
-    __syncthreads();
-    const uint32_t n_items = *cave_count;
-    constexpr uint32_t claim = CAVE_CHUNK;
-    const double f1 = q1.frequency, f2 = q2.frequency, l1 = q1.lacunarity, l2 = q2.lacunarity;
-    const double n1 = q1.norm, n2 = q2.norm;
-    const unsigned sb = smem_address(sm.bytes), sg1 = smem_address(sm.grad3[0]), sg2 = smem_address(sm.grad3[1]);
-    CaveWarp& cw = sm.warp[tid >> 5];
-    unsigned* chunk_counter = reinterpret_cast<unsigned*>(&stats[4]);
-    const unsigned lanes_below = (1u << lane) - 1u;
-    unsigned my_evals = 0;
-    constexpr unsigned BUSY = 0x400u, DROP_A = 0x100u, DROP_B = 0x200u;
-    constexpr int KEY_DROPPED = (int)0x80000001;  // below the key of every threshold
-
-    uint32_t next = 0, total = 0;  // unclaimed voxels [next, total) of the warp's current chunk
-    bool more = true;              // the global list still has unclaimed chunks
-    // per voxel slot: octaves of noise1 done | of noise2 done << 4 | DROP_A | DROP_B | BUSY; keys of the two sums
-    unsigned step0 = 0, step1 = 0;
-    int ka0 = 0, kb0 = 0, ka1 = 0, kb1 = 0;
-    size_t out0 = 0, out1 = 0;
-
-    // idle lanes take the next voxels of the chunk, in lane order (claiming the next chunk when this one is used up)
-    auto refill = [&](const int slot, unsigned& step, int& ka, int& kb, size_t& out) {
-        const unsigned want = __ballot_sync(0xFFFFFFFFu, !(step & BUSY));
-        if (want != 0 && next >= total && more) {
-            unsigned chunk = 0;
-            if (lane == 0) chunk = atomicAdd(chunk_counter, 1u);
-            chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
-            if ((unsigned long long)chunk * claim >= n_items) {
-                more = false;
-            } else {
-                const uint32_t idx = chunk * claim + lane;
-                uint32_t item = 0, cnt = 0;
-                double px = 0.0, py = 0.0;
-                if (lane < (int)claim && idx < n_items) {
-                    item = cave_items[idx];
-                    const unsigned H = pool_heights[item] & 0x7Fu;
-                    const unsigned top = H < CAVE_MAX_ZI - 1 ? H : CAVE_MAX_ZI - 1;
-                    cnt = top >= CAVE_MIN_ZI ? top - CAVE_MIN_ZI + 1 : 0;
-                    const uint2 axy = slot_xy[item >> 8];
-                    px = (double)((item & 15u) + axy.x * AREA_SIZE);
-                    py = (double)(((item >> 4) & 15u) + axy.y * AREA_SIZE);
-                }
-                uint32_t v = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
-                    if (lane >= d) v += o;
-                }
-                __syncwarp();  // nobody is still reading the previous chunk's tables
-                cw.item[lane] = item;
-                if (lane < CAVE_CHUNK) {
-#if VX_NOISE_VARIANT & 1
-                    cw.oa[lane] = make_double2(px, py);
-                    cw.ob[lane] = make_double2(px, py);
-#else
-                    cw.oa[lane] = make_double2(px * f1, py * f1);
-                    cw.ob[lane] = make_double2(px * f2, py * f2);
-#endif
-                }
-                cw.first[lane + 1] = v;
-                if (lane == 0) cw.first[0] = 0;
-                __syncwarp();
-                total = cw.first[CAVE_SLOTS];
-                next = 0;
-                if (lane == 0) atomicAdd(&stats[2], (unsigned long long)total);  // cave voxels evaluated
-            }
-        }
-        if (!(step & BUSY)) {
-            const uint32_t w = next + __popc(want & lanes_below);
-            if (w < total) {
-                int lo = 0, hi = CAVE_CHUNK;  // column with first[lo] <= w < first[lo + 1]
-#pragma unroll
-                for (int q = 0; (1 << q) < CAVE_CHUNK; ++q) {
-                    const int mid = (lo + hi) >> 1;
-                    if (cw.first[mid] <= w) lo = mid; else hi = mid;
-                }
-                const uint32_t item = cw.item[lo];
-                const unsigned zi = CAVE_MIN_ZI + (w - cw.first[lo]);
-                const double2 oa = cw.oa[lo], ob = cw.ob[lo], oz = sm.zf[zi];
-                ds.st[slot][0][0][tid] = oa;
-                ds.st[slot][0][1][tid] = make_double2(oz.x, 0.0);
-                ds.st[slot][1][0][tid] = ob;
-                ds.st[slot][1][1][tid] = make_double2(oz.y, 0.0);
-                ka = kb = 0;  // hi_key(0.0)
-                step = BUSY;
-                out = (size_t)(item >> 8) * VOXELS_IN_AREA + (item & 255u) + 256u * (AREA_HEIGHT - zi);
-            }
-        }
-        next = min(total, next + (uint32_t)__popc(want));
-    };
-    // which Fbm a slot evaluates next: the one that is alive; both alive: fewer octaves done, noise2 first
-    auto pick = [&](const unsigned step) -> bool {
-        const unsigned sa = step & 15u, sk = (step >> 4) & 15u;
-        const bool alive_a = !(step & DROP_A) && sa < 6u, alive_b = !(step & DROP_B) && sk < 8u;
-        return alive_b && (!alive_a || sk <= sa);
-    };
-    // after the evaluation: new key, counters, verdict (-1 undecided, 0 solid, 1 cave)
-    auto settle = [&](const int slot, const bool pb, const double sum, unsigned& step, int& ka, int& kb) -> int {
-        step += pb ? 16u : 1u;
-        if (pb) kb = hi_key(sum); else ka = hi_key(sum);
-        const unsigned sa = step & 15u, sk = (step >> 4) & 15u;
-        const int4 ta = sm.thr[0][sa], tb = sm.thr[1][sk];
-        int verdict = -1;
-        if ((ka < ta.x && kb < tb.x) || ka > ta.w || kb > tb.w) verdict = 0;
-        else if ((ka > ta.z || kb > tb.z) && ka < ta.y && kb < tb.y) verdict = 1;
-        if (verdict < 0) {
-            if (ka < ta.x) { ka = KEY_DROPPED; step |= DROP_A; }
-            if (kb < tb.x) { kb = KEY_DROPPED; step |= DROP_B; }
-            if (((step & DROP_A) || sa == 6u) && ((step & DROP_B) || sk == 8u)) {
-                // nothing left to evaluate: the crate's own expression over the sums that can matter
-                // (a dropped Fbm is below 0.4 whatever its remaining octaves are: if it were the maximum the
-                // voxel would be solid, and it is solid by the other sum alone as well)
-                const double va = (step & DROP_A) ? -2.0 : ds.st[slot][0][1][tid].y * n1;
-                const double vb = (step & DROP_B) ? -2.0 : ds.st[slot][1][1][tid].y * n2;
-                const int c = f64_as_i32(normalise(fmax(va, vb)));
-                verdict = (c >= 70 && c < 90) ? 1 : 0;  // cave_generator.rs:10-11,63
-            }
-        }
-        return verdict;
-    };
-
-    while (true) {
-        refill(0, step0, ka0, kb0, out0);
-        refill(1, step1, ka1, kb1, out1);
-        if (!__any_sync(0xFFFFFFFFu, ((step0 | step1) & BUSY) != 0u)) {
-            if (!more && next >= total) break;  // list exhausted and nothing in flight
-            continue;
-        }
-        // both slots evaluate, busy or not (an idle slot repeats a harmless evaluation): one basic
-        // block with two independent evaluations for the scheduler
-        const bool pb0 = pick(step0), pb1 = pick(step1);
-        const double2 p0 = ds.st[0][pb0][0][tid], q0 = ds.st[0][pb0][1][tid];
-        const double2 p1 = ds.st[1][pb1][0][tid], q1s = ds.st[1][pb1][1][tid];
-        const unsigned o0 = pb0 ? (step0 >> 4) & 15u : step0 & 15u, o1 = pb1 ? (step1 >> 4) & 15u : step1 & 15u;
-        const double amp0 = sm.amp[pb0][o0 & 7u], amp1 = sm.amp[pb1][o1 & 7u];
-#if VX_NOISE_VARIANT & 1
-        const double fr0 = sm.freq[pb0][o0 & 7u], fr1 = sm.freq[pb1][o1 & 7u];
-        const double sv0 = simplex3<0>(sb + (pb0 ? (unsigned)TAB_STRIDE : 0u), pb0 ? sg2 : sg1, p0.x * fr0, p0.y * fr0, q0.x * fr0);
-        const double sv1 = simplex3<0>(sb + (pb1 ? (unsigned)TAB_STRIDE : 0u), pb1 ? sg2 : sg1, p1.x * fr1, p1.y * fr1, q1s.x * fr1);
-        (void)l1, (void)l2, (void)f1, (void)f2;
-        const double2 np0 = p0, np1 = p1;
-        const double2 nq0 = make_double2(q0.x, q0.y + amp0 * sv0), nq1 = make_double2(q1s.x, q1s.y + amp1 * sv1);
-#else
-        const double sv0 = simplex3<0>(sb + (pb0 ? (unsigned)TAB_STRIDE : 0u), pb0 ? sg2 : sg1, p0.x, p0.y, q0.x);
-        const double sv1 = simplex3<0>(sb + (pb1 ? (unsigned)TAB_STRIDE : 0u), pb1 ? sg2 : sg1, p1.x, p1.y, q1s.x);
-        const double la = pb0 ? l2 : l1, lb = pb1 ? l2 : l1;
-        const double2 np0 = make_double2(p0.x * la, p0.y * la), np1 = make_double2(p1.x * lb, p1.y * lb);
-        const double2 nq0 = make_double2(q0.x * la, q0.y + amp0 * sv0), nq1 = make_double2(q1s.x * lb, q1s.y + amp1 * sv1);
-#endif
-        if (step0 & BUSY) {
-            ds.st[0][pb0][0][tid] = np0;
-            ds.st[0][pb0][1][tid] = nq0;
-            ++my_evals;
-            const int verdict = settle(0, pb0, nq0.y, step0, ka0, kb0);
-            if (verdict >= 0) {
-                if (verdict) pool_voxels[out0] = V_NONE;  // leave air
-                step0 = 0;
-            }
-        }
-        if (step1 & BUSY) {
-            ds.st[1][pb1][0][tid] = np1;
-            ds.st[1][pb1][1][tid] = nq1;
-            ++my_evals;
-            const int verdict = settle(1, pb1, nq1.y, step1, ka1, kb1);
-            if (verdict >= 0) {
-                if (verdict) pool_voxels[out1] = V_NONE;
-                step1 = 0;
             }
         }
     }
@@ -1313,16 +1045,8 @@ void launch_gen_columns(const NoiseTables& nt, const uint4* jobs, int n, uint8_t
 void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const uint32_t* cave_count, uint8_t* pool_voxels,
                       const uint8_t* pool_heights, const uint2* slot_xy, unsigned long long* stats,
                       int sm_count, cudaStream_t stream) {
-#ifdef VX_CAVE_DUAL
-    static const bool opted = cudaFuncSetAttribute(gen_caves_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)sizeof(CaveDualSmem)) == cudaSuccess;
-    (void)opted;
-    gen_caves_dual_kernel<<<sm_count * VX_CAVE_DUAL_CTAS_PER_SM, VX_CAVE_THREADS, sizeof(CaveDualSmem), stream>>>(
-        nt, cave_items, cave_count, pool_voxels, pool_heights, slot_xy, stats);
-#else
     gen_caves_kernel<<<sm_count * VX_CAVE_CTAS_PER_SM, VX_CAVE_THREADS, 0, stream>>>(nt, cave_items, cave_count, pool_voxels,
                                                        pool_heights, slot_xy, stats);
-#endif
 }
 
 void launch_gen_finish(const uint4* jobs, const uint32_t* cave_areas, const uint32_t* cave_area_count, int n,

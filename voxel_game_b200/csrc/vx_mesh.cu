@@ -290,18 +290,6 @@ __device__ __forceinline__ unsigned long long warp_inclusive_scan64(unsigned lon
     return v;
 }
 
-// The planes of the area that the CTA `ahead` places further down the grid will read (the one that
-// takes this CTA's place on the SM, roughly): requested into L2 now, so that its first round trip is
-// to L2 instead of HBM.  64 threads, one 128-byte line each = the 8 KiB of S and T.
-__device__ __forceinline__ void prefetch_planes_ahead(const uint4* __restrict__ jobs, const uint16_t* pool_planes,
-                                                      int ahead, int tid) {
-    const int j = (int)blockIdx.x + ahead;
-    if (tid < 64 && j < (int)gridDim.x) {
-        const char* p = reinterpret_cast<const char*>(pool_planes + (size_t)jobs[j].z * (2 * ROWS));
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 128 * tid));
-    }
-}
-
 // ------------------------------------------------------------------------------------- count
 // faces | visible voxels << 16 of one row
 __device__ __forceinline__ uint32_t row_counts(const RowMasks& k) {
@@ -318,6 +306,9 @@ __device__ __forceinline__ uint32_t pack_warp_total(uint32_t faces, uint32_t rec
 
 // Per area: faces and visible voxels, in total and per (256-row chunk, warp) -- the latter, 64
 // words per area, let the emit kernel place every row without recounting the area.
+// Eight CTAs per SM (32 registers): the kernel is a chain of dependent round trips per area, so it
+// is the resident warps that hide them (6 CTAs at 40 registers: 0.102 ms, 8: 0.076 ms).  Requesting
+// the planes of the CTA that follows on the SM into L2 ahead of time changed nothing (measured).
 #ifndef VX_COUNT_CTAS_PER_SM
 #define VX_COUNT_CTAS_PER_SM 8
 #endif
@@ -333,9 +324,6 @@ __global__ void __launch_bounds__(256, VX_COUNT_CTAS_PER_SM) mesh_count_kernel(c
     __shared__ PlaneTile tile;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const AreaView a = make_view(jobs[blockIdx.x], nbr[blockIdx.x], pool_voxels, pool_planes);
-#ifdef VX_COUNT_PREFETCH
-    prefetch_planes_ahead(jobs, pool_planes, VX_COUNT_PREFETCH, tid);
-#endif
     load_plane_tile(tile, a, tid);
     __syncthreads();
     uint32_t* wt = warp_totals + (size_t)blockIdx.x * 64;
@@ -611,9 +599,6 @@ __global__ void __launch_bounds__(256, VX_EMIT_CTAS) mesh_emit_kernel(const uint
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(a.vox + (size_t)(c * 256 + tid) * 16));
         }
     }
-#ifdef VX_EMIT_PREFETCH
-    prefetch_planes_ahead(jobs, pool_planes, VX_EMIT_PREFETCH, tid);
-#endif
     load_plane_tile(sm.planes, a, tid);
     if (wid == 0) {  // running sums of the 64 (chunk, warp) totals, two per lane
         const unsigned long long t0 = widen(w2.x), t1 = widen(w2.y);
