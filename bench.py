@@ -317,11 +317,14 @@ def main():
         lo, hi = (0, ny) if whole else plan(shift_x if plan_of is None else plan_of)[rank]
         return (vg.region_xy(ax0 - 1, ay0 + lo - 1, nx + 2, hi - lo + 2), vg.region_xy(ax0, ay0 + lo, nx, hi - lo))
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def timed(fn, steps, warmup, sample_clocks=False, finish=None):
         """W untimed + K timed calls of fn(i) between barriers and device syncs; CUDA events on the
-        stream the kernels run on; -> (ms for the K steps, max over ranks; clocks)."""
+        stream the kernels run on; -> (ms for the K steps, max over ranks; clocks).  `finish` runs after
+        the K calls, inside the timed region (deferred copies of the last step)."""
         for i in range(warmup):
             fn(i)
+        if finish:
+            finish()
         ctx.timings()  # clears the accumulators: kernel times cover the timed steps only
         sampler = ClockSampler(local_rank) if sample_clocks else None
         barrier()
@@ -332,6 +335,8 @@ def main():
         e0.record(stream)
         for i in range(steps):
             fn(warmup + i)
+        if finish:
+            finish()
         e1.record(stream)
         torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
@@ -468,17 +473,24 @@ def main():
         max_areas = max(len(b) for b in batches)
         workers = [ctx, vg.Context(local_rank, seed=seed)]
         pins = [{"files": vg.PinnedArray((max_areas * 2600 + 4096,), np.uint8),
-                 "mh": vg.PinnedArray((max_areas, 256), np.uint8)} for _ in workers]
+                 "off": vg.PinnedArray((max_areas + 1,), np.uint64),
+                 "mh": vg.PinnedArray((max_areas, 256), np.uint8)} for _ in range(2 * len(workers))]
         c5_bytes = [0, 0]
 
         def c5_worker(k, count_bytes):
-            c, p = workers[k], pins[k]
-            for b in batches[k::2]:
+            c, sets = workers[k], pins[2 * k: 2 * k + 2]
+            c.set_deferred_reads(True)  # the files of a batch cross to the host while the next one is generated
+            for j, b in enumerate(batches[k::2]):
+                p = sets[j & 1]
                 c.generate(b, max_height_out=p["mh"].array[: len(b)], read=False)
-                files, _offs = c.encode_areas(b, out=p["files"].array)
+                total = c.encode_areas(b, read=False)
+                c.wait_reads()  # the other set is complete (this is where a writer thread would take it)
+                c.encode_read(len(b), total, out=p["files"].array, offsets_out=p["off"].array[: len(b) + 1])
                 c.unload(b)
                 if count_bytes:
-                    c5_bytes[k] += len(files)
+                    c5_bytes[k] += int(total)
+            c.wait_reads()
+            c.set_deferred_reads(False)
 
         def c5_sweep(count_bytes=False):
             th = [threading.Thread(target=c5_worker, args=(k, count_bytes)) for k in range(2)]
@@ -503,7 +515,8 @@ def main():
                    "areas": C5_REGION * C5_REGION, "areas_per_gpu": (hi - lo) * cnx, "batch_areas": max_areas,
                    "d2h_bytes": int(c5_d2h), "file_bytes_per_area": c5_files / (C5_REGION * C5_REGION),
                    "timing": "host wall clock around the whole sweep (device idle before and after), max over ranks",
-                   "note": "vx_generate + vx_encode_areas + vx_encode_read into pinned host memory + vx_unload per batch; "
+                   "note": "vx_generate + vx_encode_areas + vx_encode_read (deferred: the files cross while the next batch is "
+                           "generated) into pinned host memory + vx_unload per batch; "
                            "two contexts on two host threads per GPU take alternate batches; parity: "
                            "tests/test_gpu_parity.py::test_config5_512x512_pregeneration_sample"}
         workers[1].close()
@@ -654,15 +667,42 @@ def main():
         c.mesh_read_compact(inf, out=(p["rf"].array, p["packed"].array))
 
     pin_c = compact_buffers()
+    pin_d = compact_buffers()
+    for p_ in (pin_c, pin_d):
+        p_["off"] = vg.PinnedArray((n_gen + 1,), np.uint64)
     e2e_steps = max(3, args.steps)
-    e2e_ms, _ = timed(lambda _i: compact_step(ctx, pin_c), e2e_steps, 3)
+
+    def deferred_step(i):
+        """The same step with deferred reads (vx_set_deferred_reads): the files and the records of step i
+        cross to the host while step i + 1 is generated; two sets of pinned buffers, the older one is
+        complete (vx_wait_reads) before the next reads are issued."""
+        p = (pin_c, pin_d)[i & 1]
+        ctx.generate(gen_xy, max_height_out=p["mh"].array, read=False)
+        total = ctx.encode_areas(gen_xy, read=False)
+        inf = ctx.mesh(mesh_xy)
+        ctx.wait_reads()
+        ctx.encode_read(n_gen, total, out=p["files"].array, offsets_out=p["off"].array)
+        ctx.mesh_read_compact(inf, out=(p["rf"].array, p["packed"].array))
+
+    ctx.set_deferred_reads(True)
+    e2e_ms, _ = timed(deferred_step, e2e_steps, 3, finish=ctx.wait_reads)
+    ctx.set_deferred_reads(False)
+    blocking_ms, _ = timed(lambda _i: compact_step(ctx, pin_c), e2e_steps, 3)
     e2e_value = REGION * REGION * e2e_steps / (e2e_ms * 1e-3)
     h2d = sum_over_ranks((2 * n_gen + n_mesh) * 8)  # the area lists of the three calls {ax, ay}
     d2h = sum_over_ranks(files_total + 8 * (n_gen + 1) + 256 * n_gen + 4 * (n_mesh + 1) + 4 * info["n_recs"])
     e2e = {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "transport": "compact",
+           "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "transport": "compact, deferred reads",
            "note": "one context, one host thread: vx_generate (heights to the host) + vx_encode_areas/_read (the areas as the "
-                   "reference's save files) + vx_mesh + vx_mesh_read_compact (4-byte records) into pinned host buffers"}
+                   "reference's save files) + vx_mesh + vx_mesh_read_compact (4-byte records) into pinned host buffers; with "
+                   "vx_set_deferred_reads the copies of step i run while step i + 1 is generated (two buffer sets, vx_wait_reads "
+                   "before a set is reused; the last step's copies are waited for inside the timed region)",
+           "blocking": {"value": REGION * REGION * e2e_steps / (blocking_ms * 1e-3), "unit": "chunks/s",
+                        "ms_per_step": blocking_ms / e2e_steps, "steps": e2e_steps,
+                        "note": "the same calls, every read waited for before the next call is issued (round 2's earlier figure)"}}
+    pin_d["off"].free()
+    for k_ in ("files", "mh", "rf", "packed"):
+        pin_d[k_].free()
 
     if extras:
         # (b) two contexts on two host threads, each running whole steps: copies of one overlap kernels of the other

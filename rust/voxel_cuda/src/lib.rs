@@ -110,6 +110,8 @@ extern "C" {
                          max_height_out: *mut u8) -> c_int;
     pub fn vx_unload(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int) -> c_int;
     pub fn vx_resident_count(ctx: *mut vx_ctx) -> c_int;
+    pub fn vx_set_deferred_reads(ctx: *mut vx_ctx, enabled: c_int) -> c_int;
+    pub fn vx_wait_reads(ctx: *mut vx_ctx) -> c_int;
     pub fn vx_pool_info(ctx: *mut vx_ctx, capacity_areas: *mut u64, committed_bytes: *mut u64, virtual_memory: *mut c_int) -> c_int;
     pub fn vx_column_heights(ctx: *mut vx_ctx, voxels: *const u8, n: c_int, max_height_out: *mut u8) -> c_int;
     pub fn vx_mesh(ctx: *mut vx_ctx, area_xy: *const u32, n: c_int, info: *mut vx_mesh_info) -> c_int;
@@ -304,6 +306,7 @@ impl Pipeline {
         let mut blob = vec![0u8; total as usize];
         let mut offsets = vec![0u64; areas.len() + 1];
         self.check(unsafe { vx_encode_read(self.ctx, blob.as_mut_ptr(), offsets.as_mut_ptr()) })?;
+        self.check(unsafe { vx_wait_reads(self.ctx) })?; // no-op unless deferred reads are on
         Ok(offsets.windows(2).map(|w| blob[w[0] as usize..w[1] as usize].to_vec()).collect())
     }
 
@@ -390,7 +393,33 @@ impl Pipeline {
         let mut rec_first = vec![0u32; areas.len() + 1];
         let mut packed = vec![0u32; info.n_recs as usize];
         self.check(unsafe { vx_mesh_read_compact(self.ctx, rec_first.as_mut_ptr(), packed.as_mut_ptr()) })?;
+        self.check(unsafe { vx_wait_reads(self.ctx) })?; // no-op unless deferred reads are on
         Ok((rec_first, packed))
+    }
+
+    /// Deferred reads (`vx_set_deferred_reads`): `encode_read_into` / `mesh_read_compact_into` return
+    /// before their copies are done, so one thread can issue the next step at once; the buffers are
+    /// valid after `wait_reads`.  A pre-generation tool uses this with two sets of pinned buffers
+    /// (`vx_host_alloc`); the game's own paths keep the blocking wrappers above.
+    pub fn set_deferred_reads(&self, enabled: bool) -> Result<(), VxError> {
+        self.check(unsafe { vx_set_deferred_reads(self.ctx, enabled as c_int) })
+    }
+
+    pub fn wait_reads(&self) -> Result<(), VxError> {
+        self.check(unsafe { vx_wait_reads(self.ctx) })
+    }
+
+    /// # Safety
+    /// `files` (the size `vx_encode_areas` reported) and `offsets` (n + 1, or null) must stay valid and
+    /// untouched until `wait_reads` returns; pinned memory, or the copy is not asynchronous.
+    pub unsafe fn encode_read_into(&self, files: *mut u8, offsets: *mut u64) -> Result<(), VxError> {
+        self.check(vx_encode_read(self.ctx, files, offsets))
+    }
+
+    /// # Safety
+    /// As `encode_read_into`: `rec_first` (n + 1) and `packed` (`n_recs` of the last `vx_mesh`).
+    pub unsafe fn mesh_read_compact_into(&self, rec_first: *mut u32, packed: *mut u32) -> Result<(), VxError> {
+        self.check(vx_mesh_read_compact(self.ctx, rec_first, packed))
     }
 
     /// Body of `WaterSimulator::simulate_voxels` (service/physics/water_simulator.rs:55-77): `check` is

@@ -335,3 +335,49 @@ def test_mesh_after_column_heights_operator_uses_fresh_jobs(ctx, seed):
     b = ctx.mesh_read(ctx.mesh(xy))
     for u, v in zip(a, b):
         assert u.tobytes() == v.tobytes()
+
+
+@pytest.mark.gpu
+def test_deferred_reads_equal_blocking_reads(seed):
+    """vx_set_deferred_reads: encode_read / mesh_read_compact return before their copies are done; after
+    wait_reads the pinned buffers hold exactly what the blocking calls deliver -- also when the next step
+    (another region) has been issued in between, which overwrites every device buffer the copies read."""
+    xy_a = vg.region_xy(SPAWN - 6, SPAWN - 6, 12, 12)
+    xy_b = vg.region_xy(SPAWN + 40, SPAWN - 6, 12, 12)
+    with vg.Context(0, seed=seed) as c:
+        want = {}
+        for name, xy in (("a", xy_a), ("b", xy_b)):
+            c.generate(xy, read=False)
+            total = c.encode_areas(xy, read=False)
+            inf = c.mesh(xy[: len(xy) // 2])
+            files, offsets = c.encode_read(len(xy), total)
+            rf, packed = c.mesh_read_compact(inf)
+            want[name] = (files.copy(), offsets.copy(), rf.copy(), packed.copy())
+        c.set_deferred_reads(True)
+        bufs = {}
+        for name, xy in (("a", xy_a), ("b", xy_b)):
+            c.generate(xy, read=False)
+            total = c.encode_areas(xy, read=False)
+            inf = c.mesh(xy[: len(xy) // 2])
+            b = {"files": vg.PinnedArray((int(total),), np.uint8), "off": vg.PinnedArray((len(xy) + 1,), np.uint64),
+                 "rf": vg.PinnedArray((len(xy) // 2 + 1,), np.uint32), "packed": vg.PinnedArray((inf["n_recs"],), np.uint32)}
+            for a in b.values():
+                a.array.view(np.uint8)[...] = 0xEE
+            c.encode_read(len(xy), total, out=b["files"].array, offsets_out=b["off"].array)
+            c.mesh_read_compact(inf, out=(b["rf"].array, b["packed"].array))
+            bufs[name] = b  # not waited for: step "b" is issued while the copies of "a" may still run
+        c.wait_reads()
+        for name in ("a", "b"):
+            files, offsets, rf, packed = want[name]
+            b = bufs[name]
+            assert np.array_equal(b["files"].array, files)
+            assert np.array_equal(b["off"].array, offsets)
+            assert np.array_equal(b["rf"].array, rf)
+            assert np.array_equal(b["packed"].array, packed)
+        # library-owned (pageable) buffers are complete on return even in this mode
+        total = c.encode_areas(xy_a, read=False)
+        files, offsets = c.encode_read(len(xy_a), total)
+        assert np.array_equal(files, want["a"][0]) and np.array_equal(offsets, want["a"][1])
+        c.set_deferred_reads(False)
+        for a in [x for b in bufs.values() for x in b.values()]:
+            a.free()

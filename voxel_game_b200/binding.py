@@ -48,7 +48,7 @@ ABI_SYMBOLS = [
     "vx_mesh_read_compact", "vx_set_mesh_retention", "vx_mesh_unload", "vx_read_face_masks", "vx_visible_zone",
     "vx_lock", "vx_unlock", "vx_copy_last_error", "vx_noise_variant", "vx_set_gradient_order",
     "vx_cave_columns", "vx_water_tick", "vx_falling_check", "vx_falling_land",
-    "vx_pool_info",
+    "vx_pool_info", "vx_set_deferred_reads", "vx_wait_reads",
 ]
 
 
@@ -196,6 +196,8 @@ def load():
     L.vx_update_read.argtypes = [vp, vp, vp, vp]
     L.vx_mesh_read_compact.argtypes = [vp, vp, vp]
     L.vx_set_mesh_retention.argtypes = [vp, C.c_int]
+    L.vx_set_deferred_reads.argtypes = [vp, C.c_int]
+    L.vx_wait_reads.argtypes = [vp]
     L.vx_mesh_unload.argtypes = [vp, vp, C.c_int]
     L.vx_read_face_masks.argtypes = [vp, vp, C.c_int, vp, vp]
     L.vx_visible_zone.argtypes = [vp, vp, C.c_int, C.POINTER(View), C.POINTER(VisibleInfo)]
@@ -287,6 +289,7 @@ class Context:
         if st != VX_OK:
             raise VxError(st, self._lib.vx_strerror(st).decode())
         self._h = h
+        self._deferred = False
         self.device = device
         if world_name is not None:
             seed = hash_world_name(world_name)
@@ -439,10 +442,13 @@ class Context:
         """The last mesh as 4-byte records: (rec_first u32[n+1], packed u32[n_recs]); see
         unpack_records / the C++ expander for the way back."""
         n = self._mesh_n
-        if out is None:
+        own = out is None
+        if own:
             out = (np.empty(n + 1, np.uint32), np.empty(info["n_recs"], np.uint32))
         rf, packed = out
         self._check(self._lib.vx_mesh_read_compact(self._h, _ptr(rf), _ptr(packed)))
+        if self._deferred and own:
+            self.wait_reads()  # buffers of our own (pageable): nothing to defer
         return out
 
     # -- Renderer.meshes on the device
@@ -586,15 +592,31 @@ class Context:
         files = out if out is not None else np.empty(int(total.value), np.uint8)
         offsets = np.empty(xy.shape[0] + 1, np.uint64)
         self._check(self._lib.vx_encode_read(self._h, files.ctypes.data if files.size else None, offsets.ctypes.data))
+        if self._deferred:
+            self.wait_reads()  # this form returns the files: nothing to defer
         return files[: int(total.value)], offsets
 
-    def encode_read(self, n_areas: int, total: int, out=None):
+    def encode_read(self, n_areas: int, total: int, out=None, offsets_out=None):
         """The files of the last encode_areas(read=False) -> (files u8[total], offsets u64[n+1]).  The copy
-        waits for the encoder only: a mesh() issued in between runs while the files cross to the host."""
+        waits for the encoder only: a mesh() issued in between runs while the files cross to the host.
+        With deferred reads on, `out` (and `offsets_out`, else the offsets are not fetched) must be pinned
+        and are valid after wait_reads()."""
         files = out if out is not None else np.empty(int(total), np.uint8)
-        offsets = np.empty(n_areas + 1, np.uint64)
-        self._check(self._lib.vx_encode_read(self._h, files.ctypes.data if files.size else None, offsets.ctypes.data))
+        offsets = offsets_out
+        if offsets is None and (out is None or not self._deferred):
+            offsets = np.empty(n_areas + 1, np.uint64)
+        self._check(self._lib.vx_encode_read(self._h, files.ctypes.data if files.size else None, _ptr(offsets)))
+        if self._deferred and out is None:
+            self.wait_reads()  # a buffer of our own (pageable): nothing to defer
         return files[: int(total)], offsets
+
+    def set_deferred_reads(self, enabled: bool):
+        """vx_set_deferred_reads: encode_read / mesh_read_compact return before their copies are done."""
+        self._check(self._lib.vx_set_deferred_reads(self._h, int(bool(enabled))))
+        self._deferred = bool(enabled)
+
+    def wait_reads(self):
+        self._check(self._lib.vx_wait_reads(self._h))
 
     def decode_areas(self, area_xy, files, offsets, read_heights: bool = True):
         """load_blocking for a batch of files -> (ok u8[n], max_height u8[n,256] or None); areas with

@@ -254,6 +254,11 @@ struct vx_ctx {
     // encoder (codec_ev), not for a vx_mesh enqueued after it
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t codec_ev = nullptr;
+    // deferred reads (vx_set_deferred_reads): vx_encode_read / vx_mesh_read_compact leave their copies on
+    // copy_stream and return; files_ev / packed_ev mark the end of the last such copy, and whatever would
+    // overwrite the device buffers they read waits for them on the device
+    bool deferred_reads = false, files_pending = false, packed_pending = false;
+    cudaEvent_t files_ev = nullptr, packed_ev = nullptr, pack_done_ev = nullptr;
     // vx_apply_edits that does not wait: the batch is staged in pinned memory of the context's own
     PinnedBuf h_edits;
     cudaEvent_t edits_ev = nullptr;
@@ -847,6 +852,9 @@ int vx_create(int device, vx_ctx** out) {
     ctx->stream = ctx->own_stream;
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->codec_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->files_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->packed_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->pack_done_ev, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->edits_ev, cudaEventDisableTiming) != cudaSuccess) {
         cudaStreamDestroy(ctx->own_stream);
         delete ctx;
@@ -891,6 +899,7 @@ void vx_destroy(vx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);  // deferred reads still in flight
     if (ctx->vmm) {
         for (VmArray* a : {&ctx->vm_voxels, &ctx->vm_heights, &ctx->vm_planes, &ctx->vm_xy, &ctx->vm_face, &ctx->vm_meshed})
             a->destroy(ctx->vm);
@@ -920,6 +929,9 @@ void vx_destroy(vx_ctx* ctx) {
     for (int i = 0; i < TM_COUNT; ++i)
         for (int k = 0; k < 2; ++k) cudaEventDestroy(ctx->ev[i][k]);
     cudaEventDestroy(ctx->codec_ev);
+    cudaEventDestroy(ctx->files_ev);
+    cudaEventDestroy(ctx->packed_ev);
+    cudaEventDestroy(ctx->pack_done_ev);
     cudaEventDestroy(ctx->edits_ev);
     ctx->h_edits.release();
     cudaStreamDestroy(ctx->copy_stream);
@@ -1206,6 +1218,8 @@ int vx_mesh(vx_ctx* ctx, const uint32_t* area_xy, int n, vx_mesh_info* info) {
     int st;
     if (n > 0) {
         if (ctx->capacity == 0) return fail(ctx, VX_ERR_NOT_LOADED, "vx_mesh: area not resident");
+        // rec_first of the previous mesh may still be crossing to the host (deferred read)
+        if (ctx->packed_pending) VX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->packed_ev, 0));
         // the area list goes to the device as is; slots, neighbour residency and the set of bit
         // planes to refresh are resolved there (mesh_prepare_kernel), not in a host loop
         const size_t xy_bytes = (size_t)n * sizeof(uint2);
@@ -1386,6 +1400,8 @@ int vx_encode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint64_t* total
         slots[i] = host_slot(ctx, area_xy[2 * i], area_xy[2 * i + 1]);
         if (slots[i] < 0) return fail(ctx, VX_ERR_NOT_LOADED, "vx_encode_areas: area not resident");
     }
+    // the files of the previous call may still be crossing to the host (deferred read)
+    if (ctx->files_pending) VX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->files_ev, 0));
     int st;
     if ((st = upload_jobs(ctx, area_xy, slots, n)) != VX_OK) return st;
     VX_CUDA(ctx->d_codec_sizes.ensure((size_t)n * 4));
@@ -1434,6 +1450,11 @@ int vx_encode_read(vx_ctx* ctx, uint8_t* files, uint64_t* offsets) {
         VX_CUDA(cudaMemcpyAsync(files, ctx->d_codec_bytes.p, ctx->codec_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
     if (offsets)
         VX_CUDA(cudaMemcpyAsync(offsets, ctx->d_codec_offsets.p, (size_t)(ctx->codec_n + 1) * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (ctx->deferred_reads) {  // valid after vx_wait_reads
+        VX_CUDA(cudaEventRecord(ctx->files_ev, ctx->copy_stream));
+        ctx->files_pending = true;
+        return VX_OK;
+    }
     VX_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     return VX_OK;
 }
@@ -1456,6 +1477,7 @@ int vx_decode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, const uint8_t* 
     VX_CUDA(ctx->d_codec_offsets.ensure((size_t)(n + 1) * 8));
     VX_CUDA(ctx->d_codec_status.ensure((size_t)n));
     ctx->codec_n = -1;  // d_codec_bytes no longer holds the result of vx_encode_areas
+    if (ctx->files_pending) VX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->files_ev, 0));
     // offsets relative to the first file, as uploaded
     std::vector<uint64_t> rel(n + 1);
     for (int i = 0; i <= n; ++i) rel[i] = offsets[i] - offsets[0];
@@ -2025,6 +2047,25 @@ int vx_mesh_read_compact(vx_ctx* ctx, uint32_t* rec_first, uint32_t* packed_recs
         return VX_OK;
     }
     const uint64_t n_recs = ctx->mesh_info.n_recs;
+    if (ctx->deferred_reads) {
+        // the pack kernel stays on the main stream, the copies go to the copy stream behind it: whatever the
+        // caller enqueues next (the next vx_generate) runs while they cross to the host
+        if (packed_recs && n_recs) {
+            if (ctx->packed_pending) VX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->packed_ev, 0));  // d_packed is reused
+            VX_CUDA(ctx->d_packed.ensure(n_recs * 4));
+            launch_mesh_pack(ctx->d_recs.as<uint4>(), n_recs, ctx->d_packed.as<uint32_t>(), ctx->stream);
+            ctx->timings.mesh_launches += 1;
+            VX_CUDA(cudaGetLastError());
+        }
+        VX_CUDA(cudaEventRecord(ctx->pack_done_ev, ctx->stream));
+        VX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pack_done_ev, 0));
+        if (rec_first) VX_CUDA(cudaMemcpyAsync(rec_first, ctx->d_rec_first.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (packed_recs && n_recs)
+            VX_CUDA(cudaMemcpyAsync(packed_recs, ctx->d_packed.p, n_recs * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        VX_CUDA(cudaEventRecord(ctx->packed_ev, ctx->copy_stream));
+        ctx->packed_pending = true;
+        return VX_OK;
+    }
     if (rec_first) VX_CUDA(cudaMemcpyAsync(rec_first, ctx->d_rec_first.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (packed_recs && n_recs) {
         VX_CUDA(ctx->d_packed.ensure(n_recs * 4));
@@ -2034,6 +2075,28 @@ int vx_mesh_read_compact(vx_ctx* ctx, uint32_t* rec_first, uint32_t* packed_recs
         VX_CUDA(cudaMemcpyAsync(packed_recs, ctx->d_packed.p, n_recs * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int vx_set_deferred_reads(vx_ctx* ctx, int enabled) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    if (!enabled) {
+        const int st = vx_wait_reads(ctx);
+        if (st != VX_OK) return st;
+    }
+    ctx->deferred_reads = enabled != 0;
+    return VX_OK;
+}
+
+int vx_wait_reads(vx_ctx* ctx) {
+    if (!ctx) return VX_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    VX_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->files_pending) VX_CUDA(cudaEventSynchronize(ctx->files_ev));
+    if (ctx->packed_pending) VX_CUDA(cudaEventSynchronize(ctx->packed_ev));
+    ctx->files_pending = ctx->packed_pending = false;
+    VX_CUDA(cudaGetLastError());
     return VX_OK;
 }
 

@@ -89,6 +89,10 @@ public:
     Pipeline(const Pipeline&) = delete;
     Pipeline& operator=(const Pipeline&) = delete;
     vx_ctx* raw() const { return ctx_; }
+    // vx_set_deferred_reads / vx_wait_reads: vx_encode_read and vx_mesh_read_compact into pinned buffers
+    // return before their copies are done (one thread pipelining pre-generation steps)
+    void set_deferred_reads(bool on) const { check(vx_set_deferred_reads(ctx_, on ? 1 : 0)); }
+    void wait_reads() const { check(vx_wait_reads(ctx_)); }
     void check(int st) const {
         if (st == VX_OK) return;
         char msg[1024] = "";
@@ -582,6 +586,7 @@ private:
         if (transport == Transport::Compact) {
             std::vector<uint32_t> packed(info.n_recs);
             p.check(vx_mesh_read_compact(p.raw(), rec_first.data(), packed.data()));
+            p.check(vx_wait_reads(p.raw()));  // no-op unless the caller turned deferred reads on
             pair.reset();
             parallel_ranges(static_cast<size_t>(n), threads, [&](size_t a0, size_t a1) {
                 for (size_t a = a0; a < a1; ++a) {
