@@ -672,17 +672,18 @@ def main():
         p_["off"] = vg.PinnedArray((n_gen + 1,), np.uint64)
     e2e_steps = max(3, args.steps)
 
-    def deferred_step(i):
+    def deferred_step(i, c=None, sets=None):
         """The same step with deferred reads (vx_set_deferred_reads): the files and the records of step i
         cross to the host while step i + 1 is generated; two sets of pinned buffers, the older one is
         complete (vx_wait_reads) before the next reads are issued."""
-        p = (pin_c, pin_d)[i & 1]
-        ctx.generate(gen_xy, max_height_out=p["mh"].array, read=False)
-        total = ctx.encode_areas(gen_xy, read=False)
-        inf = ctx.mesh(mesh_xy)
-        ctx.wait_reads()
-        ctx.encode_read(n_gen, total, out=p["files"].array, offsets_out=p["off"].array)
-        ctx.mesh_read_compact(inf, out=(p["rf"].array, p["packed"].array))
+        c = c or ctx
+        p = (sets or (pin_c, pin_d))[i & 1]
+        c.generate(gen_xy, max_height_out=p["mh"].array, read=False)
+        total = c.encode_areas(gen_xy, read=False)
+        inf = c.mesh(mesh_xy)
+        c.wait_reads()
+        c.encode_read(n_gen, total, out=p["files"].array, offsets_out=p["off"].array)
+        c.mesh_read_compact(inf, out=(p["rf"].array, p["packed"].array))
 
     ctx.set_deferred_reads(True)
     e2e_ms, _ = timed(deferred_step, e2e_steps, 3, finish=ctx.wait_reads)
@@ -700,26 +701,27 @@ def main():
            "blocking": {"value": REGION * REGION * e2e_steps / (blocking_ms * 1e-3), "unit": "chunks/s",
                         "ms_per_step": blocking_ms / e2e_steps, "steps": e2e_steps,
                         "note": "the same calls, every read waited for before the next call is issued (round 2's earlier figure)"}}
-    pin_d["off"].free()
-    for k_ in ("files", "mh", "rf", "packed"):
-        pin_d[k_].free()
-
     if extras:
         # (b) two contexts on two host threads, each running whole steps: copies of one overlap kernels of the other
         c2 = vg.Context(local_rank, seed=seed)
         c2.generate(gen_xy, read=False)
         c2.mesh(mesh_xy)
         c2.encode_areas(gen_xy, read=False)
-        pin_c2 = compact_buffers()
+        pin_c2, pin_d2 = compact_buffers(), compact_buffers()
+        for p_ in (pin_c2, pin_d2):
+            p_["off"] = vg.PinnedArray((n_gen + 1,), np.uint64)
         pair_steps = max(2, e2e_steps // 2)
 
-        def pair_worker(c, p, k):
-            for _ in range(k):
-                compact_step(c, p)
+        def pair_worker(c, sets, k):
+            c.set_deferred_reads(True)
+            for i in range(k):
+                deferred_step(i, c, sets)
+            c.wait_reads()
+            c.set_deferred_reads(False)
             c.sync()
 
         def pair_run(k):
-            th = [threading.Thread(target=pair_worker, args=(c, p, k)) for c, p in ((ctx, pin_c), (c2, pin_c2))]
+            th = [threading.Thread(target=pair_worker, args=(c, p, k)) for c, p in ((ctx, (pin_c, pin_d)), (c2, (pin_c2, pin_d2)))]
             for x in th:
                 x.start()
             for x in th:
@@ -735,11 +737,14 @@ def main():
         barrier()
         e2e["two_contexts"] = {"value": REGION * REGION * 2 * pair_steps / pair_s, "unit": "chunks/s",
                                "ms_per_step": pair_s * 1e3 / (2 * pair_steps), "steps": 2 * pair_steps,
-                               "note": "the same compact step from two host threads with one context each (wall clock)"}
+                               "note": "the same deferred-read step from two host threads with one context each (wall clock)"}
         c2.close()
-        for a in pin_c2.values():
+        for a in list(pin_c2.values()) + list(pin_d2.values()):
             a.free()
 
+    for a in pin_d.values():
+        a.free()
+    if extras:
         # (c) raw streams, round 1's e2e: block IDs, heights, 16-byte records, vertices, indices
         pin = {
             "vox": vg.PinnedArray((n_gen, 32768), np.uint8), "mh": vg.PinnedArray((n_gen, 256), np.uint8),

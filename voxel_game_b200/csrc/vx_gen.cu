@@ -860,8 +860,13 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
     const unsigned x = tid & 15, y = tid >> 4;
 
     // the carved area comes into shared memory in one sweep; the column walks below would
-    // otherwise be chains of dependent HBM reads
-    for (int i = tid; i < VOXELS_IN_AREA / 16; i += 256) s_vox[i] = area[i];
+    // otherwise be chains of dependent HBM reads.  Only the slabs that can differ from Stone: zi <=
+    // ALWAYS_STONE_ZI is Stone in every column of every area (the lowest surface is 32, the deepest
+    // lake bed 34 - 10; caves start at zi = 25), nothing below reads or changes those rows.
+    constexpr int ALWAYS_STONE_ZI = 23;
+    static_assert(ALWAYS_STONE_ZI < (int)CAVE_MIN_ZI && ALWAYS_STONE_ZI <= 32 - 4 && ALWAYS_STONE_ZI <= (int)LAKE_TOP_ZI - 10 - 1, "");
+    constexpr int ROWS_USED = (AREA_HEIGHT - ALWAYS_STONE_ZI) * 16;
+    for (int i = tid; i < ROWS_USED; i += 256) s_vox[i] = area[i];
     if (tid == 0) s_min_z = AREA_HEIGHT;
     __syncthreads();
     uint8_t* vox = reinterpret_cast<uint8_t*>(s_vox);
@@ -885,10 +890,7 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
     __syncthreads();
 
     // Column heights (update_all_column_heights, area.rs:34-56) and bit planes in one walk, as in K1.
-    // Everything above s_min_z is None; zi <= ALWAYS_STONE_ZI is Stone in every column of
-    // every area (the lowest surface is 32, the deepest lake bed 34 - 10; caves start at zi = 25).
-    constexpr int ALWAYS_STONE_ZI = 23;
-    static_assert(ALWAYS_STONE_ZI < (int)CAVE_MIN_ZI && ALWAYS_STONE_ZI <= 32 - 4 && ALWAYS_STONE_ZI <= (int)LAKE_TOP_ZI - 10 - 1, "");
+    // Everything above s_min_z is None, everything from z_hi on is Stone.
     const int z_lo = s_min_z, z_hi = AREA_HEIGHT - ALWAYS_STONE_ZI;
     uint16_t* planes = pool_planes + (size_t)slot * (VOXELS_IN_AREA / 8);
     {
@@ -917,7 +919,7 @@ __global__ void __launch_bounds__(256) gen_finish_kernel(const uint4* __restrict
     heights[tid] = (uint8_t)top;
     // trees only touch the slabs from s_min_z down to the surface; write those back
     const int first_row = s_min_z * 16;
-    for (int i = first_row + tid; i < VOXELS_IN_AREA / 16; i += 256) area[i] = s_vox[i];
+    for (int i = first_row + tid; i < ROWS_USED; i += 256) area[i] = s_vox[i];
     __syncthreads();  // shared memory is reused by the next area of this CTA
     }
 }
