@@ -345,15 +345,16 @@ int vx_update_read(vx_ctx* ctx, vx_voxel_rec* recs, void* vertices, uint16_t* in
 #define VX_PACKED_MASK(p) (((p) >> 20) & 0x3Fu)
 int vx_mesh_read_compact(vx_ctx* ctx, uint32_t* rec_first, uint32_t* packed_recs);
 
-/* ---- deferred reads: one host thread keeps the device busy across steps.  While on, vx_encode_read and
- * vx_mesh_read_compact enqueue their device -> host copies on the context's copy stream and return
- * at once; the destination buffers (pinned host memory -- a copy into pageable memory is not
- * asynchronous) hold the result after vx_wait_reads.  The next step's vx_generate / vx_encode_areas /
- * vx_mesh can be issued right away: a call that would overwrite what a pending copy still reads
- * waits for it on the device, not on the host.  Use two sets of destination buffers and call
- * vx_wait_reads before consuming (or reusing) the older one.  Replaces nothing in the reference: its
- * loader hands areas to the main thread through a queue (world_persistence.rs:97-123), this is the
- * same decoupling for the device -> host direction.  vx_set_deferred_reads(ctx, 0) waits first. */
+/* ---- deferred reads: one host thread keeps the device busy across steps.  While on, vx_encode_read
+ * and vx_mesh_read_compact -- and vx_generate when it is asked for the heights only -- enqueue their
+ * device -> host copies on the context's copy stream and return at once; the destination buffers
+ * (pinned host memory -- a copy into pageable memory is not asynchronous) hold the result after
+ * vx_wait_reads.  The next step's vx_generate / vx_encode_areas / vx_mesh can be issued right away:
+ * a call that would overwrite what a pending copy still reads waits for it on the device, not on
+ * the host.  Use two sets of destination buffers and call vx_wait_reads before consuming (or
+ * reusing) the older one.  Replaces nothing in the reference: its loader hands areas to the main
+ * thread through a queue (world_persistence.rs:97-123), this is the same decoupling for the device
+ * -> host direction.  vx_set_deferred_reads(ctx, 0) waits first. */
 int vx_set_deferred_reads(vx_ctx* ctx, int enabled);
 int vx_wait_reads(vx_ctx* ctx);
 

@@ -347,29 +347,33 @@ def test_deferred_reads_equal_blocking_reads(seed):
     with vg.Context(0, seed=seed) as c:
         want = {}
         for name, xy in (("a", xy_a), ("b", xy_b)):
-            c.generate(xy, read=False)
+            _, mh = c.generate(xy)
             total = c.encode_areas(xy, read=False)
             inf = c.mesh(xy[: len(xy) // 2])
             files, offsets = c.encode_read(len(xy), total)
             rf, packed = c.mesh_read_compact(inf)
-            want[name] = (files.copy(), offsets.copy(), rf.copy(), packed.copy())
+            want[name] = (files.copy(), offsets.copy(), rf.copy(), packed.copy(), mh.copy())
         c.set_deferred_reads(True)
         bufs = {}
         for name, xy in (("a", xy_a), ("b", xy_b)):
-            c.generate(xy, read=False)
+            mh_pin = vg.PinnedArray((len(xy), 256), np.uint8)
+            mh_pin.array[...] = 0xEE
+            c.generate(xy, max_height_out=mh_pin.array, read=False)  # heights only: deferred as well
             total = c.encode_areas(xy, read=False)
             inf = c.mesh(xy[: len(xy) // 2])
-            b = {"files": vg.PinnedArray((int(total),), np.uint8), "off": vg.PinnedArray((len(xy) + 1,), np.uint64),
+            b = {"mh": mh_pin, "files": vg.PinnedArray((int(total),), np.uint8), "off": vg.PinnedArray((len(xy) + 1,), np.uint64),
                  "rf": vg.PinnedArray((len(xy) // 2 + 1,), np.uint32), "packed": vg.PinnedArray((inf["n_recs"],), np.uint32)}
-            for a in b.values():
-                a.array.view(np.uint8)[...] = 0xEE
+            for k_, a in b.items():
+                if k_ != "mh":
+                    a.array.view(np.uint8)[...] = 0xEE
             c.encode_read(len(xy), total, out=b["files"].array, offsets_out=b["off"].array)
             c.mesh_read_compact(inf, out=(b["rf"].array, b["packed"].array))
             bufs[name] = b  # not waited for: step "b" is issued while the copies of "a" may still run
         c.wait_reads()
         for name in ("a", "b"):
-            files, offsets, rf, packed = want[name]
+            files, offsets, rf, packed, mh = want[name]
             b = bufs[name]
+            assert np.array_equal(b["mh"].array, mh)
             assert np.array_equal(b["files"].array, files)
             assert np.array_equal(b["off"].array, offsets)
             assert np.array_equal(b["rf"].array, rf)

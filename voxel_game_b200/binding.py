@@ -366,7 +366,9 @@ class Context:
     # -- generation / light
     def generate(self, area_xy, voxels_out=None, max_height_out=None, read=True):
         """AreaLoader::load_all_blocking for disk misses. Returns (voxels[n,32768], max_height[n,256])
-        (None, None when read=False and no output buffers are given)."""
+        (None, None when read=False and no output buffers are given).  With deferred reads on, a call
+        that asks for the heights only (read=False, max_height_out=pinned) returns before they have
+        arrived: wait_reads()."""
         xy = _xy(area_xy)
         n = xy.shape[0]
         if read and voxels_out is None:

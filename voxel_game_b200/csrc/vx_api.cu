@@ -257,8 +257,8 @@ struct vx_ctx {
     // deferred reads (vx_set_deferred_reads): vx_encode_read / vx_mesh_read_compact leave their copies on
     // copy_stream and return; files_ev / packed_ev mark the end of the last such copy, and whatever would
     // overwrite the device buffers they read waits for them on the device
-    bool deferred_reads = false, files_pending = false, packed_pending = false;
-    cudaEvent_t files_ev = nullptr, packed_ev = nullptr, pack_done_ev = nullptr;
+    bool deferred_reads = false, files_pending = false, packed_pending = false, heights_pending = false;
+    cudaEvent_t files_ev = nullptr, packed_ev = nullptr, pack_done_ev = nullptr, heights_ev = nullptr, heights_staged_ev = nullptr;
     // vx_apply_edits that does not wait: the batch is staged in pinned memory of the context's own
     PinnedBuf h_edits;
     cudaEvent_t edits_ev = nullptr;
@@ -318,7 +318,7 @@ struct vx_ctx {
     DevBuf d_jobs, d_gen_jobs, d_list, d_missing, d_cave_items, d_counters, d_rec_count, d_face_count;
     DevBuf d_gen_counters;  // cave work list size + work accounting of vx_generate; no other call touches it
     DevBuf d_hash_keys, d_hash_vals, d_dirty_flags, d_dirty_slots, d_edits, d_tmp;
-    DevBuf d_heightmap, d_light, d_slot_to_job, d_finished, d_warp_totals, d_mesh_nbr;
+    DevBuf d_heightmap, d_light, d_slot_to_job, d_finished, d_warp_totals, d_mesh_nbr, d_heights_stage;
     DevBuf d_mesh_xy, d_frame_flags, d_frame_counts, d_frame_small, d_frame_visible, d_frame_codes;  // per-frame visibility (K7)
     DevBuf d_codec_sizes, d_codec_offsets, d_codec_bytes, d_codec_status, d_codec_kinds;  // area save files (K8 / K9)
     // incremental updates (vx_update_locations) and the compact record transport
@@ -655,7 +655,7 @@ int upload_jobs(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>& sl
 // copy per-slot records (stride bytes each) of the listed slots to/from a packed host array, one
 // cudaMemcpyAsync per run of consecutive slots
 int copy_slots(vx_ctx* ctx, const std::vector<int>& slots, int n, uint8_t* dev_base, size_t stride,
-               uint8_t* host, bool to_host) {
+               uint8_t* host, bool to_host, bool host_is_device = false) {
     int i = 0;
     while (i < n) {
         int j = i + 1;
@@ -663,7 +663,8 @@ int copy_slots(vx_ctx* ctx, const std::vector<int>& slots, int n, uint8_t* dev_b
         uint8_t* d = dev_base + (size_t)slots[i] * stride;
         uint8_t* h = host + (size_t)i * stride;
         const size_t bytes = (size_t)(j - i) * stride;
-        if (to_host) VX_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (host_is_device) VX_CUDA(cudaMemcpyAsync(to_host ? h : d, to_host ? d : h, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        else if (to_host) VX_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         else VX_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
         i = j;
     }
@@ -855,6 +856,8 @@ int vx_create(int device, vx_ctx** out) {
         cudaEventCreateWithFlags(&ctx->files_ev, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->packed_ev, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->pack_done_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->heights_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->heights_staged_ev, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->edits_ev, cudaEventDisableTiming) != cudaSuccess) {
         cudaStreamDestroy(ctx->own_stream);
         delete ctx;
@@ -911,7 +914,7 @@ void vx_destroy(vx_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_map, &ctx->d_map_patch, &ctx->d_jobs, &ctx->d_gen_jobs, &ctx->d_list, &ctx->d_missing, &ctx->d_cave_items, &ctx->d_counters, &ctx->d_gen_counters,
                       &ctx->d_rec_count, &ctx->d_face_count, &ctx->d_hash_keys, &ctx->d_hash_vals,
                       &ctx->d_dirty_flags, &ctx->d_dirty_slots, &ctx->d_edits, &ctx->d_tmp,
-                      &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_warp_totals, &ctx->d_mesh_nbr, &ctx->d_mesh_xy, &ctx->d_frame_flags,
+                      &ctx->d_heightmap, &ctx->d_light, &ctx->d_slot_to_job, &ctx->d_finished, &ctx->d_warp_totals, &ctx->d_mesh_nbr, &ctx->d_heights_stage, &ctx->d_mesh_xy, &ctx->d_frame_flags,
                       &ctx->d_frame_counts, &ctx->d_frame_small, &ctx->d_frame_visible, &ctx->d_codec_sizes,
                       &ctx->d_frame_codes, &ctx->d_codec_offsets, &ctx->d_codec_bytes, &ctx->d_codec_status, &ctx->d_codec_kinds, &ctx->d_rec_first, &ctx->d_face_first, &ctx->d_recs,
                       &ctx->d_vertices, &ctx->d_indices, &ctx->d_upd_xyz, &ctx->d_upd_slot, &ctx->d_upd_info,
@@ -932,6 +935,8 @@ void vx_destroy(vx_ctx* ctx) {
     cudaEventDestroy(ctx->files_ev);
     cudaEventDestroy(ctx->packed_ev);
     cudaEventDestroy(ctx->pack_done_ev);
+    cudaEventDestroy(ctx->heights_ev);
+    cudaEventDestroy(ctx->heights_staged_ev);
     cudaEventDestroy(ctx->edits_ev);
     ctx->h_edits.release();
     cudaStreamDestroy(ctx->copy_stream);
@@ -1091,6 +1096,22 @@ int vx_generate(vx_ctx* ctx, const uint32_t* area_xy, int n, uint8_t* voxels_out
         return st;
     }
     ctx->last_gen_version = ctx->index_version;  // d_gen_jobs now holds exactly this list
+    if (ctx->deferred_reads && max_height_out && !voxels_out) {
+        // Deferred read of the heights: gathered into a staging buffer on the main stream (device to
+        // device, microseconds), copied to the host from there on the copy stream -- later calls may
+        // change the pool's heights at once, only the staging buffer has to outlive the copy.
+        const size_t bytes = (size_t)n * COLUMNS_IN_AREA;
+        if (ctx->heights_pending) VX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->heights_ev, 0));
+        VX_CUDA(ctx->d_heights_stage.ensure(bytes));
+        if ((st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, ctx->d_heights_stage.as<uint8_t>(), true, true)) != VX_OK) return st;
+        VX_CUDA(cudaEventRecord(ctx->heights_staged_ev, ctx->stream));
+        VX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->heights_staged_ev, 0));
+        VX_CUDA(cudaMemcpyAsync(max_height_out, ctx->d_heights_stage.p, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        VX_CUDA(cudaEventRecord(ctx->heights_ev, ctx->copy_stream));
+        ctx->heights_pending = true;
+        if (ctx->timing) ctx->gen_counters_pending = true;
+        return VX_OK;
+    }
     if (voxels_out && (st = copy_slots(ctx, slots, n, ctx->d_voxels, VOXELS_IN_AREA, voxels_out, true)) != VX_OK) return st;
     if (max_height_out && (st = copy_slots(ctx, slots, n, ctx->d_heights, COLUMNS_IN_AREA, max_height_out, true)) != VX_OK) return st;
     // work accounting of this call (the roofline numerators): fetched when the timings are read
@@ -2095,7 +2116,8 @@ int vx_wait_reads(vx_ctx* ctx) {
     VX_CUDA(cudaSetDevice(ctx->device));
     if (ctx->files_pending) VX_CUDA(cudaEventSynchronize(ctx->files_ev));
     if (ctx->packed_pending) VX_CUDA(cudaEventSynchronize(ctx->packed_ev));
-    ctx->files_pending = ctx->packed_pending = false;
+    if (ctx->heights_pending) VX_CUDA(cudaEventSynchronize(ctx->heights_ev));
+    ctx->files_pending = ctx->packed_pending = ctx->heights_pending = false;
     VX_CUDA(cudaGetLastError());
     return VX_OK;
 }
