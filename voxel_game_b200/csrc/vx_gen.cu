@@ -85,7 +85,7 @@ enum TreeType { T_NONE = 0, T_SHORT, T_TALL, T_TALL_CACTUS, T_DEAD, T_HUGE, T_SH
 
 // trees.rs:15-75, indexed by TreeType (trees.rs:77-87)
 __constant__ uint8_t c_tree_cells_n[8] = {0, 8, 9, 3, 2, 27, 1, 1};
-__constant__ TreeCell c_tree_cells[8][27] = {
+__device__ const TreeCell c_tree_cells[8][27] = {  // global, not __constant__: the lanes of a warp read 27 different cells (one coalesced load; the constant bank would serialise them)
     {},
     // Short
     {{0, 0, -1, V_WOOD}, {0, 0, -2, V_WOOD}, {0, 0, -3, V_WOOD}, {0, 0, -4, V_LEAVES},
