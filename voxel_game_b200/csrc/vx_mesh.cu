@@ -323,10 +323,14 @@ __global__ void __launch_bounds__(256, VX_COUNT_CTAS_PER_SM) mesh_count_kernel(c
     __shared__ uint32_t s_busy[2];  // bit c * 8 + w: (chunk c, warp w) may have faces
     __shared__ PlaneTile tile;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const AreaView a = make_view(jobs[blockIdx.x], nbr[blockIdx.x], pool_voxels, pool_planes);
+    // last area first: generation has just written the planes in list order, the end of the list is
+    // what the L2 still holds (count 0.0769 -> 0.0754 ms; emit walks the list the same way: 0.3455 ->
+    // 0.3435, profiles/r02_ab_mesh_order.log)
+    const unsigned area = gridDim.x - 1u - blockIdx.x;
+    const AreaView a = make_view(jobs[area], nbr[area], pool_voxels, pool_planes);
     load_plane_tile(tile, a, tid);
     __syncthreads();
-    uint32_t* wt = warp_totals + (size_t)blockIdx.x * 64;
+    uint32_t* wt = warp_totals + (size_t)area * 64;
     if (tid < 64) {  // one thread per (chunk, warp): rows of two slabs
         const bool empty = slab_pair_empty(tile, 16 * (tid >> 3) + 2 * (tid & 7));
         if (empty) wt[tid] = 0u;
@@ -363,8 +367,8 @@ __global__ void __launch_bounds__(256, VX_COUNT_CTAS_PER_SM) mesh_count_kernel(c
             f += s_faces[i];
             q += s_recs[i];
         }
-        face_count[blockIdx.x] = f;
-        rec_count[blockIdx.x] = q;
+        face_count[area] = f;
+        rec_count[area] = q;
     }
 }
 
@@ -573,14 +577,15 @@ __global__ void __launch_bounds__(256, VX_EMIT_CTAS) mesh_emit_kernel(const uint
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // everything this CTA needs from global memory before the planes, requested together
     const uint32_t stream_faces = out.face_first[n], stream_recs = out.rec_first[n];
-    const uint4 job = jobs[blockIdx.x];
-    const uint4 nb = nbr[blockIdx.x];
-    const uint32_t face_base = out.face_first[blockIdx.x];
-    const uint32_t rec_base = out.rec_first[blockIdx.x];
+    const unsigned area = gridDim.x - 1u - blockIdx.x;  // as the count kernel
+    const uint4 job = jobs[area];
+    const uint4 nb = nbr[area];
+    const uint32_t face_base = out.face_first[area];
+    const uint32_t rec_base = out.rec_first[area];
     uint2 w2 = make_uint2(0u, 0u);
-    if (wid == 0) w2 = reinterpret_cast<const uint2*>(warp_totals + (size_t)blockIdx.x * (CHUNKS * 8))[lane];
+    if (wid == 0) w2 = reinterpret_cast<const uint2*>(warp_totals + (size_t)area * (CHUNKS * 8))[lane];
     // this warp's own (chunk, warp) totals, lane c = chunk c: which voxel rows phase A will read
-    const uint32_t my_total = lane < CHUNKS ? warp_totals[(size_t)blockIdx.x * (CHUNKS * 8) + lane * 8 + wid] : 0u;
+    const uint32_t my_total = lane < CHUNKS ? warp_totals[(size_t)area * (CHUNKS * 8) + lane * 8 + wid] : 0u;
     // launched speculatively right behind the offsets scan: if the stream does not fit the arena
     // the whole grid backs off and the host, which sees the totals afterwards, enlarges it and
     // launches again
