@@ -686,7 +686,7 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
         ctx->stage_pending = true;
         ctx->last_gen_version = ~0ull;  // whatever list d_gen_jobs held before is gone
     }
-    VX_CUDA(ctx->d_cave_items.ensure((size_t)n * COLUMNS_IN_AREA * sizeof(uint32_t)));
+    VX_CUDA(ctx->d_cave_items.ensure((size_t)n * COLUMNS_IN_AREA * sizeof(CaveItem)));
     VX_CUDA(ctx->d_finished.ensure((size_t)n * sizeof(uint32_t)));  // K2 work list
     VX_CUDA(ctx->d_gen_counters.ensure(64));
     VX_CUDA(cudaMemsetAsync(ctx->d_gen_counters.p, 0, 64, ctx->stream));
@@ -696,12 +696,12 @@ int generate_async(vx_ctx* ctx, const uint32_t* area_xy, const std::vector<int>&
     {
         ScopedTimer t(ctx, TM_GEN_COLUMNS);
         launch_gen_columns(ctx->tables, jobs, n, ctx->d_voxels, ctx->d_heights, ctx->d_slot_xy,
-                           ctx->d_cave_items.as<uint32_t>(), cave_count, stats, ctx->d_planes,
+                           ctx->d_cave_items.as<CaveItem>(), cave_count, stats, ctx->d_planes,
                            ctx->d_finished.as<uint32_t>(), ctx->stream);
     }
     {
         ScopedTimer t(ctx, TM_GEN_CAVES, TM_GEN_COLUMNS);
-        launch_gen_caves(ctx->tables, ctx->d_cave_items.as<uint32_t>(), cave_count, ctx->d_voxels, ctx->d_heights,
+        launch_gen_caves(ctx->tables, ctx->d_cave_items.as<CaveItem>(), cave_count, ctx->d_voxels, ctx->d_heights,
                          ctx->d_slot_xy, stats, ctx->sm_count, ctx->stream);
     }
     {

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256, VX_K1_CTAS_PER_SM) gen_columns_kernel(con
                                                           uint8_t* __restrict__ pool_voxels,
                                                           uint8_t* __restrict__ pool_heights,
                                                           uint2* __restrict__ slot_xy,
-                                                          uint32_t* __restrict__ cave_items,
+                                                          CaveItem* __restrict__ cave_items,
                                                           uint32_t* __restrict__ cave_count,
                                                           unsigned long long* __restrict__ stats,
                                                           uint16_t* __restrict__ pool_planes,
@@ -589,6 +589,9 @@ __global__ void __launch_bounds__(256, VX_K1_CTAS_PER_SM) gen_columns_kernel(con
 #ifndef VX_CAVE_CHUNK
 #define VX_CAVE_CHUNK 8
 #endif
+#ifndef VX_CAVE_TAIL
+#define VX_CAVE_TAIL 4  // columns per claim near the end of the list (0: always VX_CAVE_CHUNK)
+#endif
 // Cave columns a warp claims at a time (lane c < CAVE_CHUNK describes column c).  A column is 8..78
 // voxels and a region has ~87 000 cave columns for 3 552 warps: with 32 columns per claim most
 // warps got exactly one chunk (a quarter of them none) and the kernel lasted as long as the
@@ -659,7 +662,7 @@ __device__ __forceinline__ int hi_key(double x) {
 //     iteration with the per-voxel state in shared memory, pays the refill and the verdict once per
 //     evaluation instead of once per two (0.329 ms at 72 registers, profiles/r02_ab_caves_dual.log).
 __global__ void __launch_bounds__(VX_CAVE_THREADS, VX_CAVE_CTAS_PER_SM) gen_caves_kernel(const __grid_constant__ NoiseTables nt,
-                                                        const uint32_t* __restrict__ cave_items,
+                                                        const CaveItem* __restrict__ cave_items,
                                                         const uint32_t* __restrict__ cave_count,
                                                         uint8_t* __restrict__ pool_voxels,
                                                         const uint8_t* __restrict__ pool_heights,
@@ -716,6 +719,32 @@ __global__ void __launch_bounds__(VX_CAVE_THREADS, VX_CAVE_CTAS_PER_SM) gen_cave
         if (want != 0 && next >= total && more) {
             // The current chunk is used up: claim the next columns right away.  Lanes that are
             // still evaluating keep their state in registers, so the warp never drains.
+#if VX_CAVE_TAIL
+            // Guided claims: CAVE_CHUNK columns while plenty are left, VX_CAVE_TAIL once the rest of the
+            // list is less than one full claim per warp of the grid -- the last claims are what the
+            // kernel's end waits for, and smaller ones even the warps out.  The counter counts columns;
+            // the size is picked from a plain (possibly stale) read of it, which can only pick a size.
+            // Tail claims of 4: 0.3030 -> 0.2975 ms for the whole region, no change for a rank's strip
+            // of eight; of 2 or 1: 0.319 / 0.379 -- a claim is a chain of four dependent global accesses
+            // that the whole warp waits for (profiles/r02_ab_cave_claims.log; sizing the claim from the
+            // warp's previous claim instead of the extra read never shrinks it: the counter moves by
+            // one whole tail between two claims of a warp).
+            unsigned first_col = 0, seen = 0;
+            if (lane == 0) seen = *reinterpret_cast<volatile unsigned*>(chunk_counter);
+            seen = __shfl_sync(0xFFFFFFFFu, seen, 0);
+            const unsigned tail = gridDim.x * (VX_CAVE_THREADS / 32) * CAVE_CHUNK;
+            const unsigned size = (seen < n_items && n_items - seen > tail) ? (unsigned)CAVE_CHUNK : (unsigned)VX_CAVE_TAIL;
+            if (lane == 0) first_col = atomicAdd(chunk_counter, size);
+            first_col = __shfl_sync(0xFFFFFFFFu, first_col, 0);
+            (void)claim;
+            if (first_col >= n_items) {
+                more = false;
+            } else {
+                const uint32_t idx = first_col + lane;
+                uint32_t item = 0, cnt = 0;
+                double px = 0.0, py = 0.0;
+                if (lane < (int)size && idx < n_items) {
+#else
             unsigned chunk = 0;
             if (lane == 0) chunk = atomicAdd(chunk_counter, 1u);
             chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
@@ -726,16 +755,17 @@ __global__ void __launch_bounds__(VX_CAVE_THREADS, VX_CAVE_CTAS_PER_SM) gen_cave
                 uint32_t item = 0, cnt = 0;
                 double px = 0.0, py = 0.0;
                 if (lane < (int)claim && idx < n_items) {
+#endif
                     item = cave_items[idx];
                     const unsigned H = pool_heights[item] & 0x7Fu;
-                    // should_be_cave evaluates the noise for CAVE_MIN_ZI <= zi < CAVE_MAX_ZI, zi <= H
-                    // (in a cave zone lake_depth is 0, so the voxel is never None/WaterSource)
-                    const unsigned top = H < CAVE_MAX_ZI - 1 ? H : CAVE_MAX_ZI - 1;
-                    cnt = top >= CAVE_MIN_ZI ? top - CAVE_MIN_ZI + 1 : 0;
                     const uint2 axy = slot_xy[item >> 8];
                     // algorithms.rs:19-26: u32 sum, then cast
                     px = (double)((item & 15u) + axy.x * AREA_SIZE);
                     py = (double)(((item >> 4) & 15u) + axy.y * AREA_SIZE);
+                    // should_be_cave evaluates the noise for CAVE_MIN_ZI <= zi < CAVE_MAX_ZI, zi <= H
+                    // (in a cave zone lake_depth is 0, so the voxel is never None/WaterSource)
+                    const unsigned top = H < CAVE_MAX_ZI - 1 ? H : CAVE_MAX_ZI - 1;
+                    cnt = top >= CAVE_MIN_ZI ? top - CAVE_MIN_ZI + 1 : 0;
                 }
                 uint32_t v = cnt;
 #pragma unroll
@@ -1036,7 +1066,7 @@ __global__ void __launch_bounds__(256) fp64_rate_kernel(double* sink, int iters)
 }  // namespace
 
 void launch_gen_columns(const NoiseTables& nt, const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
-                        uint2* slot_xy, uint32_t* cave_items, uint32_t* cave_count,
+                        uint2* slot_xy, CaveItem* cave_items, uint32_t* cave_count,
                         unsigned long long* stats, uint16_t* pool_planes, uint32_t* cave_areas,
                         cudaStream_t stream) {
     if (n <= 0) return;
@@ -1044,7 +1074,7 @@ void launch_gen_columns(const NoiseTables& nt, const uint4* jobs, int n, uint8_t
                                               cave_count, stats, pool_planes, cave_areas);
 }
 
-void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const uint32_t* cave_count, uint8_t* pool_voxels,
+void launch_gen_caves(const NoiseTables& nt, const CaveItem* cave_items, const uint32_t* cave_count, uint8_t* pool_voxels,
                       const uint8_t* pool_heights, const uint2* slot_xy, unsigned long long* stats,
                       int sm_count, cudaStream_t stream) {
     gen_caves_kernel<<<sm_count * VX_CAVE_CTAS_PER_SM, VX_CAVE_THREADS, 0, stream>>>(nt, cave_items, cave_count, pool_voxels,

@@ -12,12 +12,16 @@ namespace vx {
 
 // ---- generation (K1, K1b, K2) and column heights (L1)
 // jobs: n entries {area x, area y, slot, 0}
+// One cave-zone column for K1b: slot * 256 + column.  (A 16-byte item that also carries the terrain
+// height and the global x, y -- one load per claim instead of a chain of three -- was measured: no gain
+// for K1b, K1 loses 1 % to the wider scattered stores; profiles/r02_ab_cave_claims.log.)
+typedef uint32_t CaveItem;
 void launch_gen_columns(const NoiseTables& nt, const uint4* jobs, int n, uint8_t* pool_voxels, uint8_t* pool_heights,
-                        uint2* slot_xy, uint32_t* cave_items, uint32_t* cave_count,
+                        uint2* slot_xy, CaveItem* cave_items, uint32_t* cave_count,
                         unsigned long long* stats /* [5]: simplex2, alt simplex3, cave voxels, cave evals, cursor */,
                         uint16_t* pool_planes, uint32_t* cave_areas /* jobs K2 has to finish; counted at cave_count[1] */,
                         cudaStream_t stream);
-void launch_gen_caves(const NoiseTables& nt, const uint32_t* cave_items, const uint32_t* cave_count,
+void launch_gen_caves(const NoiseTables& nt, const CaveItem* cave_items, const uint32_t* cave_count,
                       uint8_t* pool_voxels, const uint8_t* pool_heights, const uint2* slot_xy,
                       unsigned long long* stats, int sm_count, cudaStream_t stream);
 void launch_gen_finish(const uint4* jobs, const uint32_t* cave_areas, const uint32_t* cave_area_count, int n,
