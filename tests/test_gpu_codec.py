@@ -177,3 +177,20 @@ def test_reference_persistence_tests(world_name, locations):
         assert ok.all()
         v2, _ = c.read_areas(xy)
         assert np.array_equal(v2, vox) and np.array_equal(mh2, mh)   # assert_areas_equal
+
+
+def test_encode_emit_pass_is_speculative_and_backs_off(seed):
+    """vx_encode_areas launches its emit pass behind the size pass before the host knows the total, into
+    the buffer kept from earlier calls; when the files do not fit, the kernel backs off and the pass is
+    launched again.  Small -> large (back-off) -> small (fits) -> large again (fits), each checked."""
+    small = vg.region_xy(SPAWN - 2, SPAWN - 2, 3, 3)
+    large = vg.region_xy(SPAWN - 10, SPAWN - 10, 20, 20)
+    with vg.Context(0, seed=seed) as c:
+        vox_s, _ = c.generate(small)
+        vox_l, _ = c.generate(large)
+        for xy, vox in ((small, vox_s), (large, vox_l), (small, vox_s), (large, vox_l)):
+            blob, offsets = c.encode_areas(xy)
+            assert offsets[-1] == len(blob)
+            for i, f in enumerate(_files(blob, offsets)):
+                got = oracle.area_file_decode(f)
+                assert got is not None and np.array_equal(got, vox[i])

@@ -1437,14 +1437,28 @@ int vx_encode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint64_t* total
     }
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaMemcpyAsync(ctx->h_small.p, offsets + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if ((st = sync_stream(ctx)) != VX_OK) return st;
-    collect_timers(ctx);
+    // The emit pass goes out right behind the size pass, before the host knows the total, when the
+    // buffer kept from earlier calls may do: it backs off by itself if the files do not fit.  The host
+    // waits for the total only.  (With the timers on the passes are issued one after the other.)
+    const size_t cap_before = ctx->d_codec_bytes.cap;
+    const bool speculative = !ctx->timing && cap_before > 32;
+    if (speculative) {
+        VX_CUDA(cudaEventRecord(ctx->totals_ev, ctx->stream));
+        launch_codec_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_codec_kinds.as<uint8_t>(), offsets,
+                          ctx->d_codec_bytes.as<uint8_t>(), cap_before - 32, ctx->stream);
+        VX_CUDA(cudaGetLastError());
+        VX_CUDA(cudaEventSynchronize(ctx->totals_ev));
+    } else {
+        if ((st = sync_stream(ctx)) != VX_OK) return st;
+        collect_timers(ctx);
+    }
     const uint64_t total = *ctx->h_small.as<uint64_t>();
-    VX_CUDA(ctx->d_codec_bytes.ensure(total + 32));  // the decoder stages whole 16-byte pieces: slack past the last file
-    {
+    if (!speculative || total + 32 > cap_before) {
+        if (speculative && (st = sync_stream(ctx)) != VX_OK) return st;  // the buffer is about to be replaced
+        VX_CUDA(ctx->d_codec_bytes.ensure(total + 32));  // the decoder stages whole 16-byte pieces: slack past the last file
         ScopedTimer t(ctx, TM_CODEC);
         launch_codec_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_codec_kinds.as<uint8_t>(), offsets,
-                          ctx->d_codec_bytes.as<uint8_t>(), ctx->stream);
+                          ctx->d_codec_bytes.as<uint8_t>(), ctx->d_codec_bytes.cap, ctx->stream);
     }
     ctx->timings.other_launches += 3;
     VX_CUDA(cudaGetLastError());

@@ -108,8 +108,11 @@ __global__ void __launch_bounds__(256) codec_encode_kernel(const uint4* __restri
                                                            uint8_t* __restrict__ kinds,
                                                            uint32_t* __restrict__ sizes,
                                                            const unsigned long long* __restrict__ offsets,
-                                                           uint8_t* __restrict__ out) {
+                                                           uint8_t* __restrict__ out, unsigned long long cap_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // launched speculatively right behind the size pass, before the host knows the total: if the files
+    // do not fit the buffer kept from earlier calls the whole grid backs off and the host launches again
+    if (EMIT && offsets[gridDim.x] > cap_bytes) return;
     SizeSmem& ss = *reinterpret_cast<SizeSmem*>(smem_raw);
     EmitSmem& sm = *reinterpret_cast<EmitSmem*>(smem_raw);
     uint8_t* sm_kind = EMIT ? sm.kind : ss.kind;
@@ -541,14 +544,14 @@ void launch_codec_sizes(const uint4* jobs, int n, const uint8_t* pool_voxels, ui
                         unsigned long long* offsets, cudaStream_t stream) {
     if (n <= 0) return;
     cudaFuncSetAttribute(codec_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SizeSmem));
-    codec_encode_kernel<false><<<n, 256, sizeof(SizeSmem), stream>>>(jobs, pool_voxels, kinds, sizes, nullptr, nullptr);
+    codec_encode_kernel<false><<<n, 256, sizeof(SizeSmem), stream>>>(jobs, pool_voxels, kinds, sizes, nullptr, nullptr, 0ull);
     codec_offsets_kernel<<<1, 1024, 0, stream>>>(sizes, n, offsets);
 }
 
 void launch_codec_emit(const uint4* jobs, int n, const uint8_t* pool_voxels, uint8_t* kinds,
-                       const unsigned long long* offsets, uint8_t* out, cudaStream_t stream) {
+                       const unsigned long long* offsets, uint8_t* out, unsigned long long cap_bytes, cudaStream_t stream) {
     if (n <= 0) return;
-    codec_encode_kernel<true><<<n, 256, sizeof(EmitSmem), stream>>>(jobs, pool_voxels, kinds, nullptr, offsets, out);
+    codec_encode_kernel<true><<<n, 256, sizeof(EmitSmem), stream>>>(jobs, pool_voxels, kinds, nullptr, offsets, out, cap_bytes);
 }
 
 void launch_codec_decode(const uint4* jobs, int n, const uint8_t* files, const unsigned long long* offsets,

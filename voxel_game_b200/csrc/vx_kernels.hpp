@@ -107,7 +107,8 @@ constexpr uint32_t AREA_FILE_MAX_BYTES = 33300;  // 4 + 3 + 32768 literals + tok
 void launch_codec_sizes(const uint4* jobs, int n, const uint8_t* pool_voxels, uint8_t* kinds, uint32_t* sizes,
                         unsigned long long* offsets /* n + 1 */, cudaStream_t stream);
 void launch_codec_emit(const uint4* jobs, int n, const uint8_t* pool_voxels, uint8_t* kinds,
-                       const unsigned long long* offsets, uint8_t* out, cudaStream_t stream);
+                       const unsigned long long* offsets, uint8_t* out, unsigned long long cap_bytes /* backs off beyond */,
+                       cudaStream_t stream);
 void launch_codec_decode(const uint4* jobs, int n, const uint8_t* files, const unsigned long long* offsets,
                          uint8_t* pool_voxels, uint8_t* status /* n */, cudaStream_t stream);
 
