@@ -1441,7 +1441,11 @@ int vx_encode_areas(vx_ctx* ctx, const uint32_t* area_xy, int n, uint64_t* total
     // buffer kept from earlier calls may do: it backs off by itself if the files do not fit.  The host
     // waits for the total only.  (With the timers on the passes are issued one after the other.)
     const size_t cap_before = ctx->d_codec_bytes.cap;
+#ifdef VX_ENCODE_NO_SPECULATION  // A/B switch (profiles/r02_ab_encode_spec.log)
+    const bool speculative = false;
+#else
     const bool speculative = !ctx->timing && cap_before > 32;
+#endif
     if (speculative) {
         VX_CUDA(cudaEventRecord(ctx->totals_ev, ctx->stream));
         launch_codec_emit(ctx->d_jobs.as<uint4>(), n, ctx->d_voxels, ctx->d_codec_kinds.as<uint8_t>(), offsets,
