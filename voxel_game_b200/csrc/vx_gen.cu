@@ -246,6 +246,7 @@ struct __align__(16) GenSmem {
     NoiseShared noise;
     unsigned cave_n;
     unsigned cave_base;
+    unsigned cave_cursor; // next free entry of the CTA's block of cave items
     unsigned evals[2];    // 2-D / 3-D octave evaluations of the CTA
     unsigned queue_n;     // entries of the SurfaceQueue
     unsigned stone_rows;  // zi <= stone_rows is Stone in every column of the area
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(256, VX_K1_CTAS_PER_SM) gen_columns_kernel(con
     load_noise_shared<FBM_TABLE<FBM_ALT>>(&sm.noise, nt, tid, 256);
     if (tid == 0) {
         sm.cave_n = 0;
+        sm.cave_cursor = 0;
         sm.evals[0] = sm.evals[1] = 0;
         sm.queue_n = 0;
         sm.stone_rows = AREA_HEIGHT;
@@ -510,7 +512,6 @@ __global__ void __launch_bounds__(256, VX_K1_CTAS_PER_SM) gen_columns_kernel(con
         atomicAdd(&stats[0], (unsigned long long)sm.evals[0]);
         atomicAdd(&stats[1], (unsigned long long)sm.evals[1]);
     }
-    __syncthreads();                    // everyone has read it before it is reused as a cursor
 
     if (n_cave != 0) {
         // Cave zone in this area: K1b carves it in HBM and K2 finishes it (trees, heights, planes).
@@ -518,12 +519,11 @@ __global__ void __launch_bounds__(256, VX_K1_CTAS_PER_SM) gen_columns_kernel(con
         heights[tid] = (uint8_t)(H | (cave_zone ? 0x80u : 0u));
         if (tid == 0) {
             sm.cave_base = atomicAdd(cave_count, n_cave);
-            sm.cave_n = 0;
             // K2's work list: the jobs that still need finishing (cave_count + 1 counts them)
             cave_areas[atomicAdd(cave_count + 1, 1u)] = blockIdx.x;
         }
         __syncthreads();
-        if (cave_zone) cave_items[sm.cave_base + atomicAdd(&sm.cave_n, 1u)] = slot * COLUMNS_IN_AREA + tid;
+        if (cave_zone) cave_items[sm.cave_base + atomicAdd(&sm.cave_cursor, 1u)] = slot * COLUMNS_IN_AREA + tid;
     } else {
         // No caves (most areas): trees, column heights and bit planes straight from shared memory.
         // The topmost generated non-None voxel (generator.rs:91-93,100) is the surface voxel, or the
